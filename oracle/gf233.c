@@ -1,0 +1,152 @@
+/* ORACLE (test infrastructure only). See gf233.h for provenance. */
+#include "gf233.h"
+#include <string.h>
+#if defined(__PCLMUL__)
+#include <immintrin.h>
+#include <wmmintrin.h>
+#endif
+
+const gf_t GF_ZERO = {{0, 0, 0, 0}};
+const gf_t GF_ONE = {{1, 0, 0, 0}};
+static int g_portable = 0;
+void gf_set_portable(int on) { g_portable = on; }
+
+void gf_add(gf_t *r, const gf_t *a, const gf_t *b) {
+    for (int i = 0; i < 4; i++) r->w[i] = a->w[i] ^ b->w[i];
+}
+int gf_is_zero(const gf_t *a) { return (a->w[0] | a->w[1] | a->w[2] | a->w[3]) == 0; }
+int gf_eq(const gf_t *a, const gf_t *b) { return memcmp(a->w, b->w, 32) == 0; }
+
+/* c[0..7] (466 significant bits) -> reduced mod x^233 + x^74 + 1 */
+static void gf_reduce(gf_t *r, uint64_t c[8]) {
+    for (int i = 7; i >= 4; i--) {
+        uint64_t t = c[i];
+        /* x^(64i+k) = x^(64(i-4)+23+k) + x^(64(i-3)+33+k) */
+        c[i - 4] ^= t << 23;
+        c[i - 3] ^= t >> 41;
+        c[i - 3] ^= t << 33;
+        c[i - 2] ^= t >> 31;
+    }
+    uint64_t t = c[3] >> 41; /* bits 233.. of the low half */
+    c[0] ^= t;
+    c[1] ^= t << 10;
+    c[3] &= (1ULL << 41) - 1;
+    memcpy(r->w, c, 32);
+}
+
+static void clmul64_portable(uint64_t *lo, uint64_t *hi, uint64_t a, uint64_t b) {
+    uint64_t l = 0, h = 0;
+    for (int i = 0; i < 64; i++) {
+        if ((a >> i) & 1) {
+            l ^= b << i;
+            if (i) h ^= b >> (64 - i);
+        }
+    }
+    *lo = l;
+    *hi = h;
+}
+
+static void mul_portable(uint64_t c[8], const gf_t *a, const gf_t *b) {
+    memset(c, 0, 64);
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            uint64_t l, h;
+            clmul64_portable(&l, &h, a->w[i], b->w[j]);
+            c[i + j] ^= l;
+            c[i + j + 1] ^= h;
+        }
+}
+
+#if defined(__PCLMUL__)
+static void mul_pclmul(uint64_t c[8], const gf_t *a, const gf_t *b) {
+    memset(c, 0, 64);
+    for (int i = 0; i < 4; i++) {
+        __m128i ai = _mm_cvtsi64_si128((long long)a->w[i]);
+        for (int j = 0; j < 4; j++) {
+            __m128i bj = _mm_cvtsi64_si128((long long)b->w[j]);
+            __m128i p = _mm_clmulepi64_si128(ai, bj, 0x00);
+            c[i + j] ^= (uint64_t)_mm_cvtsi128_si64(p);
+            c[i + j + 1] ^= (uint64_t)_mm_extract_epi64(p, 1);
+        }
+    }
+}
+#endif
+
+void gf_mul(gf_t *r, const gf_t *a, const gf_t *b) {
+    uint64_t c[8];
+#if defined(__PCLMUL__)
+    if (!g_portable) mul_pclmul(c, a, b);
+    else
+#endif
+        mul_portable(c, a, b);
+    gf_reduce(r, c);
+}
+
+static uint64_t spread32(uint32_t v) {
+    uint64_t x = v;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFULL;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFULL;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0FULL;
+    x = (x | (x << 2)) & 0x3333333333333333ULL;
+    x = (x | (x << 1)) & 0x5555555555555555ULL;
+    return x;
+}
+void gf_sqr(gf_t *r, const gf_t *a) {
+    uint64_t c[8];
+    for (int i = 0; i < 4; i++) {
+        c[2 * i] = spread32((uint32_t)a->w[i]);
+        c[2 * i + 1] = spread32((uint32_t)(a->w[i] >> 32));
+    }
+    gf_reduce(r, c);
+}
+void gf_sqr_n(gf_t *r, const gf_t *a, int n) {
+    gf_t t = *a;
+    for (int i = 0; i < n; i++) gf_sqr(&t, &t);
+    *r = t;
+}
+
+/* Itoh-Tsujii: a^(2^233-2) = (a^(2^232-1))^2, chain 1,2,3,6,7,14,28,29,58,116,232 */
+void gf_inv(gf_t *r, const gf_t *a) {
+    gf_t b1 = *a, b2, b3, b6, b7, b14, b28, b29, b58, b116, b232, t;
+    gf_sqr(&t, &b1);          gf_mul(&b2, &t, &b1);
+    gf_sqr(&t, &b2);          gf_mul(&b3, &t, &b1);
+    gf_sqr_n(&t, &b3, 3);     gf_mul(&b6, &t, &b3);
+    gf_sqr(&t, &b6);          gf_mul(&b7, &t, &b1);
+    gf_sqr_n(&t, &b7, 7);     gf_mul(&b14, &t, &b7);
+    gf_sqr_n(&t, &b14, 14);   gf_mul(&b28, &t, &b14);
+    gf_sqr(&t, &b28);         gf_mul(&b29, &t, &b1);
+    gf_sqr_n(&t, &b29, 29);   gf_mul(&b58, &t, &b29);
+    gf_sqr_n(&t, &b58, 58);   gf_mul(&b116, &t, &b58);
+    gf_sqr_n(&t, &b116, 116); gf_mul(&b232, &t, &b116);
+    gf_sqr(r, &b232);
+}
+
+void gf_sqrt(gf_t *r, const gf_t *a) { gf_sqr_n(r, a, 232); }
+
+int gf_trace(const gf_t *a) {
+    gf_t acc = *a, t = *a;
+    for (int i = 1; i < 233; i++) {
+        gf_sqr(&t, &t);
+        gf_add(&acc, &acc, &t);
+    }
+    /* the trace lies in GF(2) */
+    return (int)(acc.w[0] & 1);
+}
+
+void gf_halftrace(gf_t *r, const gf_t *a) {
+    gf_t z = *a;
+    for (int i = 1; i <= 116; i++) {
+        gf_sqr_n(&z, &z, 2);
+        gf_add(&z, &z, a);
+    }
+    *r = z;
+}
+
+void gf_to_le30(uint8_t out[30], const gf_t *a) {
+    for (int i = 0; i < 30; i++) out[i] = (uint8_t)(a->w[i >> 3] >> (8 * (i & 7)));
+}
+int gf_from_le30(gf_t *r, const uint8_t in[30]) {
+    memset(r->w, 0, 32);
+    for (int i = 0; i < 30; i++) r->w[i >> 3] |= (uint64_t)in[i] << (8 * (i & 7));
+    return (r->w[3] >> 41) == 0;
+}

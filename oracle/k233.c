@@ -1,0 +1,297 @@
+/* ORACLE (test infrastructure only). See k233.h for provenance. */
+#include "k233.h"
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* NIST K-233 generator (FIPS 186-4 D.1.3.2 / SEC 2 sect233k1) */
+static k233_pt g_gen;
+static int g_gen_ready = 0;
+static void hex_to_gf(gf_t *r, const char *hex) {
+    /* big-endian hex string, up to 60 digits */
+    memset(r->w, 0, 32);
+    size_t n = strlen(hex);
+    for (size_t i = 0; i < n; i++) {
+        char c = hex[n - 1 - i];
+        uint64_t v = (c >= '0' && c <= '9') ? (uint64_t)(c - '0') : (uint64_t)((c | 32) - 'a' + 10);
+        r->w[i >> 4] |= v << (4 * (i & 15));
+    }
+}
+static const k233_pt *gen(void) {
+    if (!g_gen_ready) {
+        hex_to_gf(&g_gen.x, "017232BA853A7E731AF129F22FF4149563A419C26BF50A4C9D6EEFAD6126");
+        hex_to_gf(&g_gen.y, "01DB537DECE819B7F70F555A67C427A8CD9BF18AEB9B56E0C11056FAE6A3");
+        g_gen.inf = 0;
+        g_gen_ready = 1;
+    }
+    return &g_gen;
+}
+void k233_generator(k233_pt *r) { *r = *gen(); }
+
+int k233_on_curve(const k233_pt *p) {
+    if (p->inf) return 1;
+    gf_t l, r, t;
+    gf_sqr(&l, &p->y);
+    gf_mul(&t, &p->x, &p->y);
+    gf_add(&l, &l, &t); /* y^2 + xy */
+    gf_sqr(&t, &p->x);
+    gf_mul(&r, &t, &p->x);
+    gf_add(&r, &r, &GF_ONE); /* x^3 + 1 */
+    return gf_eq(&l, &r);
+}
+void k233_neg(k233_pt *r, const k233_pt *p) {
+    *r = *p;
+    if (!p->inf) gf_add(&r->y, &p->x, &p->y);
+}
+int k233_eq(const k233_pt *p, const k233_pt *q) {
+    if (p->inf || q->inf) return p->inf && q->inf;
+    return gf_eq(&p->x, &q->x) && gf_eq(&p->y, &q->y);
+}
+void k233_dbl(k233_pt *r, const k233_pt *p) {
+    if (p->inf || gf_is_zero(&p->x)) { /* 2*(0,1) = infinity */
+        r->inf = 1;
+        r->x = GF_ZERO;
+        r->y = GF_ZERO;
+        return;
+    }
+    gf_t l, t, x3, y3;
+    gf_inv(&t, &p->x);
+    gf_mul(&l, &t, &p->y);
+    gf_add(&l, &l, &p->x); /* lambda = x + y/x */
+    gf_sqr(&x3, &l);
+    gf_add(&x3, &x3, &l); /* a = 0 */
+    gf_sqr(&y3, &p->x);
+    gf_add(&t, &l, &GF_ONE);
+    gf_mul(&t, &t, &x3);
+    gf_add(&y3, &y3, &t); /* x^2 + (lambda+1) x3 */
+    r->x = x3;
+    r->y = y3;
+    r->inf = 0;
+}
+void k233_add(k233_pt *r, const k233_pt *p, const k233_pt *q) {
+    if (p->inf) { *r = *q; return; }
+    if (q->inf) { *r = *p; return; }
+    if (gf_eq(&p->x, &q->x)) {
+        if (gf_eq(&p->y, &q->y)) { k233_dbl(r, p); return; }
+        r->inf = 1; r->x = GF_ZERO; r->y = GF_ZERO; /* q = -p */
+        return;
+    }
+    gf_t l, t, x3, y3, dx;
+    gf_add(&dx, &p->x, &q->x);
+    gf_add(&t, &p->y, &q->y);
+    gf_inv(&l, &dx);
+    gf_mul(&l, &l, &t);
+    gf_sqr(&x3, &l);
+    gf_add(&x3, &x3, &l);
+    gf_add(&x3, &x3, &dx);
+    gf_add(&t, &p->x, &x3);
+    gf_mul(&y3, &l, &t);
+    gf_add(&y3, &y3, &x3);
+    gf_add(&y3, &y3, &p->y);
+    r->x = x3;
+    r->y = y3;
+    r->inf = 0;
+}
+
+/* ---- Lopez-Dahab projective (x = X/Z, y = Y/Z^2), HMV "Guide to ECC" Alg. 3.24/3.25, a=0 b=1 ---- */
+typedef struct { gf_t X, Y, Z; } ld_pt; /* Z == 0: infinity */
+
+static void ld_dbl(ld_pt *r, const ld_pt *p) {
+    if (gf_is_zero(&p->Z)) { *r = *p; return; }
+    gf_t z2, x2, z4, x4, y2, t;
+    ld_pt o;
+    gf_sqr(&z2, &p->Z);
+    gf_sqr(&x2, &p->X);
+    gf_mul(&o.Z, &z2, &x2);
+    gf_sqr(&z4, &z2);
+    gf_sqr(&x4, &x2);
+    gf_add(&o.X, &x4, &z4);
+    gf_sqr(&y2, &p->Y);
+    gf_add(&y2, &y2, &z4);
+    gf_mul(&t, &o.X, &y2);
+    gf_mul(&o.Y, &z4, &o.Z);
+    gf_add(&o.Y, &o.Y, &t);
+    *r = o;
+}
+static void ld_from_affine(ld_pt *r, const k233_pt *p) {
+    if (p->inf) { r->X = GF_ONE; r->Y = GF_ZERO; r->Z = GF_ZERO; return; }
+    r->X = p->x; r->Y = p->y; r->Z = GF_ONE;
+}
+static void ld_add_mixed(ld_pt *r, const ld_pt *p, const k233_pt *q) {
+    if (q->inf) { *r = *p; return; }
+    if (gf_is_zero(&p->Z)) { ld_from_affine(r, q); return; }
+    gf_t A, B, C, D, E, F, G, z2, t;
+    ld_pt o;
+    gf_sqr(&z2, &p->Z);
+    gf_mul(&t, &q->y, &z2);
+    gf_add(&A, &p->Y, &t);
+    gf_mul(&t, &q->x, &p->Z);
+    gf_add(&B, &p->X, &t);
+    if (gf_is_zero(&B)) {
+        if (gf_is_zero(&A)) { ld_pt qq; ld_from_affine(&qq, q); ld_dbl(r, &qq); return; }
+        r->X = GF_ONE; r->Y = GF_ZERO; r->Z = GF_ZERO;
+        return;
+    }
+    gf_mul(&C, &p->Z, &B);
+    gf_sqr(&t, &B);
+    gf_mul(&D, &t, &C); /* a = 0 */
+    gf_sqr(&o.Z, &C);
+    gf_mul(&E, &A, &C);
+    gf_sqr(&t, &A);
+    gf_add(&o.X, &t, &D);
+    gf_add(&o.X, &o.X, &E);
+    gf_mul(&t, &q->x, &o.Z);
+    gf_add(&F, &o.X, &t);
+    gf_add(&t, &q->x, &q->y);
+    gf_sqr(&G, &o.Z);
+    gf_mul(&G, &G, &t);
+    gf_add(&t, &E, &o.Z);
+    gf_mul(&o.Y, &t, &F);
+    gf_add(&o.Y, &o.Y, &G);
+    *r = o;
+}
+static void ld_to_affine(k233_pt *r, const ld_pt *p) {
+    if (gf_is_zero(&p->Z)) { r->inf = 1; r->x = GF_ZERO; r->y = GF_ZERO; return; }
+    gf_t zi, zi2;
+    gf_inv(&zi, &p->Z);
+    gf_sqr(&zi2, &zi);
+    gf_mul(&r->x, &p->X, &zi);
+    gf_mul(&r->y, &p->Y, &zi2);
+    r->inf = 0;
+}
+
+/* width-4 NAF, left-to-right, LD accumulator */
+void k233_mul_bytes(k233_pt *r, const k233_pt *p, const uint8_t *k, size_t klen) {
+    uint64_t e[5] = {0, 0, 0, 0, 0};
+    if (klen > 32) klen = 32;
+    for (size_t i = 0; i < klen; i++) e[i >> 3] |= (uint64_t)k[i] << (8 * (i & 7));
+    int8_t naf[264];
+    int len = 0;
+    while (e[0] | e[1] | e[2] | e[3] | e[4]) {
+        int d = 0;
+        if (e[0] & 1) {
+            d = (int)(e[0] & 15);
+            if (d >= 8) d -= 16;
+            /* e -= d */
+            if (d > 0) {
+                e[0] -= (uint64_t)d; /* low 4 bits >= d: no borrow */
+            } else {
+                uint64_t add = (uint64_t)(-d);
+                for (int i = 0; i < 5 && add; i++) {
+                    uint64_t s = e[i] + add;
+                    add = s < e[i];
+                    e[i] = s;
+                }
+            }
+        }
+        naf[len++] = (int8_t)d;
+        for (int i = 0; i < 4; i++) e[i] = (e[i] >> 1) | (e[i + 1] << 63);
+        e[4] >>= 1;
+    }
+    if (p->inf || len == 0) { r->inf = 1; r->x = GF_ZERO; r->y = GF_ZERO; return; }
+    k233_pt tab[4], p2, nq; /* 1P 3P 5P 7P */
+    tab[0] = *p;
+    k233_dbl(&p2, p);
+    for (int i = 1; i < 4; i++) k233_add(&tab[i], &tab[i - 1], &p2);
+    ld_pt acc;
+    acc.X = GF_ONE; acc.Y = GF_ZERO; acc.Z = GF_ZERO;
+    for (int i = len - 1; i >= 0; i--) {
+        ld_dbl(&acc, &acc);
+        int d = naf[i];
+        if (d > 0) ld_add_mixed(&acc, &acc, &tab[d >> 1]);
+        else if (d < 0) { k233_neg(&nq, &tab[(-d) >> 1]); ld_add_mixed(&acc, &acc, &nq); }
+    }
+    ld_to_affine(r, &acc);
+}
+
+void k233_mul_fr(k233_pt *r, const k233_pt *p, const fr_t *k) {
+    /* fr_to_le_bytes (curve.rs:162-182): canonical limbs, LE bytes, truncate to 30, strip trailing zeros */
+    uint64_t c[4];
+    uint8_t b[32];
+    fr_to_canonical(c, k);
+    for (int i = 0; i < 32; i++) b[i] = (uint8_t)(c[i >> 3] >> (8 * (i & 7)));
+    size_t len = 30;
+    while (len && b[len - 1] == 0) len--;
+    k233_mul_bytes(r, p, b, len);
+}
+
+void xsk233_encode(uint8_t out[30], const k233_pt *p) {
+    if (p->inf) { memset(out, 0, 30); return; }
+    /* Q = P + N has w(Q) = w(P) + 1 = (y + 1 + x)/x */
+    gf_t t, xi, w;
+    gf_add(&t, &p->y, &p->x);
+    gf_add(&t, &t, &GF_ONE);
+    gf_inv(&xi, &p->x);
+    gf_mul(&w, &t, &xi);
+    gf_to_le30(out, &w);
+}
+
+int xsk233_decode(k233_pt *p, const uint8_t in[30]) {
+    gf_t w, d, e, f, x1, x2, y1, lam, u2, t;
+    p->inf = 1; p->x = GF_ZERO; p->y = GF_ZERO;
+    if (!gf_from_le30(&w, in)) return 0;
+    if (gf_is_zero(&w)) return 1; /* neutral */
+    gf_sqr(&d, &w);
+    gf_add(&d, &d, &w); /* d = w^2 + w + a, a = 0 */
+    if (gf_is_zero(&d)) return 0; /* w = 1: x = 1, an order-4 point */
+    gf_inv(&t, &d);
+    gf_sqr(&e, &t); /* b/d^2 */
+    if (gf_trace(&e)) return 0;
+    gf_halftrace(&f, &e);
+    gf_mul(&x1, &d, &f);   /* roots of x^2 + d x + 1 */
+    gf_add(&x2, &x1, &d);
+    if (gf_trace(&x1)) return 0; /* not in 2E: outside E[r] u (E[r]+N) */
+    /* T1 = (x1, x1 w + 1) has w-coordinate w.  T1 is in E[r]+N iff its halves are not doubles. */
+    gf_mul(&y1, &x1, &w);
+    gf_add(&y1, &y1, &GF_ONE);
+    gf_halftrace(&lam, &x1);            /* lam^2 + lam = x1 (+a) */
+    gf_add(&t, &lam, &GF_ONE);
+    gf_mul(&t, &t, &x1);
+    gf_add(&u2, &y1, &t);               /* u^2 = y + (lam+1) x, u = x(half) */
+    gf_t xp;
+    if (gf_trace(&u2)) xp = x2;         /* T1 = Q in the coset: P = Q + N has x = 1/x1 = x2 */
+    else xp = x1;                       /* T1 in E[r]: Q = -T1 + N, P = -T1, x = x1 */
+    /* P has w-coordinate w + 1: y = x (w+1) + 1 */
+    gf_add(&t, &w, &GF_ONE);
+    gf_mul(&p->y, &xp, &t);
+    gf_add(&p->y, &p->y, &GF_ONE);
+    p->x = xp;
+    p->inf = 0;
+    return 1;
+}
+
+void k233_msm(k233_pt *r, const fr_t *scalars, const k233_pt *points, size_t n, int nthreads) {
+    int nt = 1;
+#ifdef _OPENMP
+    nt = nthreads > 0 ? nthreads : omp_get_max_threads();
+#endif
+    (void)nthreads;
+    k233_pt *part = (k233_pt *)malloc((size_t)nt * sizeof(k233_pt));
+    for (int t = 0; t < nt; t++) { part[t].inf = 1; part[t].x = GF_ZERO; part[t].y = GF_ZERO; }
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nt)
+#endif
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        ld_pt acc;
+        acc.X = GF_ONE; acc.Y = GF_ZERO; acc.Z = GF_ZERO;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 64)
+#endif
+        for (long i = 0; i < (long)n; i++) {
+            k233_pt s;
+            k233_mul_fr(&s, &points[i], &scalars[i]);
+            ld_add_mixed(&acc, &acc, &s);
+        }
+        ld_to_affine(&part[tid], &acc);
+    }
+    k233_pt acc = part[0];
+    for (int t = 1; t < nt; t++) k233_add(&acc, &acc, &part[t]);
+    *r = acc;
+    free(part);
+}

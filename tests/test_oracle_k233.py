@@ -1,0 +1,92 @@
+"""Oracle K-233 group law + xsk233 codec (oracle/k233.c).
+
+Group law is pinned against OpenSSL NID_sect233k1.  The reference's own tests for this
+layer are algebraic only (curve.rs:198-248, io_utils.rs:253-267); they are restated here.
+"""
+import ctypes as C
+import random
+
+TWO_G_X = 0x01A96A52534C02824C92539163F2ED13243FEB57B45ADBE4CF7EC61957F6
+
+
+def _be30(v):
+    return v.to_bytes(30, "big")
+
+
+def _ossl_mul(ossl, O, k, p, q=None):
+    ox, oy = (C.c_ubyte * 30)(), (C.c_ubyte * 30)()
+    x, y = O.pt_xy(p)
+    if q is None:
+        r = ossl.ossl_ec_mul_add(k.to_bytes(32, "big"), 32, _be30(x), _be30(y), None, None, ox, oy)
+    else:
+        qx, qy = O.pt_xy(q)
+        r = ossl.ossl_ec_mul_add(k.to_bytes(32, "big"), 32, _be30(x), _be30(y), _be30(qx), _be30(qy), ox, oy)
+    assert r in (1, 2)
+    return None if r == 2 else (int.from_bytes(bytes(ox), "big"), int.from_bytes(bytes(oy), "big"))
+
+
+def test_group_law_vs_openssl(oracle, ossl):
+    O = oracle
+    rnd = random.Random(4)
+    G = O.generator()
+    assert O.lib().k233_on_curve(C.byref(G))
+    assert O.pt_xy(O.pt_mul(G, 2))[0] == TWO_G_X
+    for _ in range(12):
+        k, k2 = rnd.randrange(O.P), rnd.randrange(O.P)
+        pk = O.pt_mul(G, k)
+        assert O.pt_xy(pk) == _ossl_mul(ossl, O, k, G)
+        p2 = O.pt_mul(pk, k2)
+        assert O.pt_xy(p2) == _ossl_mul(ossl, O, k2, pk)
+        assert O.pt_xy(O.pt_add(pk, p2)) == _ossl_mul(ossl, O, k2, pk, pk)
+    assert O.pt_mul(G, O.P).inf
+    assert O.pt_xy(O.pt_mul(G, O.P - 1)) == O.pt_xy(O.pt_neg(G))
+    assert O.pt_add(G, O.pt_neg(G)).inf
+    assert O.pt_xy(O.pt_add(G, G)) == O.pt_xy(O.pt_mul(G, 2))
+
+
+def test_psm_homomorphism(oracle):
+    """curve.rs:198-215: k1*G + k2*G == (k1+k2)*G"""
+    O = oracle
+    rnd = random.Random(5)
+    G = O.generator()
+    for _ in range(5):
+        k1, k2 = rnd.randrange(O.P), rnd.randrange(O.P)
+        lhs = O.pt_add(O.pt_mul(G, k1), O.pt_mul(G, k2))
+        assert O.pt_encode(lhs) == O.pt_encode(O.pt_mul(G, (k1 + k2) % O.P))
+
+
+def test_msm_all_generator(oracle):
+    """curve.rs:218-232: msm(scalars, [G]*n) == (sum scalars)*G"""
+    O = oracle
+    rnd = random.Random(6)
+    n = 300
+    ks = [rnd.randrange(O.P) for _ in range(n)]
+    pts = O.points_to_array([O.generator()] * n)
+    got = O.msm(O.mont_array(ks), pts, 2)
+    assert O.pt_encode(got) == O.pt_encode(O.pt_mul(O.generator(), sum(ks) % O.P))
+
+
+def test_codec_round_trip(oracle):
+    """curve.rs:236-248 and io_utils.rs:253-267: G and the neutral round-trip and decode as valid."""
+    O = oracle
+    rnd = random.Random(7)
+    for p in [O.generator(), O.pt()] + [O.pt_mul(O.generator(), rnd.randrange(1, O.P)) for _ in range(10)]:
+        b = O.pt_encode(p)
+        q, ok = O.pt_decode(b)
+        assert ok and O.pt_xy(q) == O.pt_xy(p)
+    assert O.pt_encode(O.pt()) == bytes(30)
+
+
+def test_decode_rejects_points_outside_the_group(oracle):
+    O = oracle
+    rnd = random.Random(8)
+    valid = 0
+    for _ in range(120):
+        w = rnd.getrandbits(233).to_bytes(30, "little")
+        q, ok = O.pt_decode(w)
+        if ok:
+            valid += 1
+            assert O.lib().k233_on_curve(C.byref(q)) and O.pt_mul(q, O.P).inf and O.pt_encode(q) == w
+    assert 10 < valid < 60  # one w in four names a group element
+    assert not O.pt_decode((1).to_bytes(30, "little"))[1]  # w = 1: x = 1, an order-4 point
+    assert not O.pt_decode(bytes(29) + b"\x02")[1]  # bit 233 set
