@@ -1,0 +1,430 @@
+// C ABI of libdvpari (include/dvpari.h): contexts, SRS slots, MSM entry points, self-tests.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "../../include/dvpari.h"
+#include "ctx.cuh"
+#include "fr.cuh"
+#include "host_gf.hpp"
+#include "k233_codec.cuh"
+
+using namespace dvp;
+
+#define CKC(x)                                                                                           \
+    do {                                                                                                 \
+        cudaError_t e_ = (x);                                                                            \
+        if (e_ != cudaSuccess) {                                                                         \
+            fprintf(stderr, "[dvpari] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return DVP_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+static inline uint32_t cdivu(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------- kernels
+__global__ void k_decode30(const uint8_t *__restrict__ in, size_t n, AffPt *__restrict__ out,
+                           unsigned long long *__restrict__ first_bad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t b[30];
+    for (int k = 0; k < 30; k++) b[k] = in[i * 30 + k];
+    AffPt p;
+    if (!xsk233_decode_pt(b, p)) atomicMin(first_bad, (unsigned long long)i);
+    pt_store(&out[i], p);
+}
+__global__ void k_encode30(const AffPt *__restrict__ in, size_t n, uint8_t *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t b[30];
+    xsk233_encode_pt(b, pt_load(&in[i]));
+    for (int k = 0; k < 30; k++) out[i * 30 + k] = b[k];
+}
+// out = a (+) b on encodings; ok[0] = both decoded
+__global__ void k_point_add30(const uint8_t *__restrict__ ab, uint8_t *__restrict__ out, int *__restrict__ ok) {
+    uint8_t a[30], b[30], r[30];
+    for (int k = 0; k < 30; k++) {
+        a[k] = ab[k];
+        b[k] = ab[30 + k];
+    }
+    AffPt p, q;
+    const bool oa = xsk233_decode_pt(a, p), ob = xsk233_decode_pt(b, q);
+    xsk233_encode_pt(r, pt_add_slow(p, q));
+    for (int k = 0; k < 30; k++) out[k] = r[k];
+    ok[0] = oa && ob;
+}
+
+__global__ void k_selftest(int op, const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+                           uint32_t *__restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (op <= 2) {
+        gf x, y, r;
+        for (int k = 0; k < 8; k++) {
+            x.v[k] = a[i * 8 + k];
+            y.v[k] = b ? b[i * 8 + k] : 0;
+        }
+        r = op == 0 ? gf_mul(x, y) : op == 1 ? gf_sqr(x) : gf_inv(x);
+        for (int k = 0; k < 8; k++) out[i * 8 + k] = r.v[k];
+    } else if (op <= 4) {
+        fr x, y;
+        for (int k = 0; k < 8; k++) {
+            x.v[k] = a[i * 8 + k];
+            y.v[k] = b ? b[i * 8 + k] : 0;
+        }
+        if (op == 3) {
+            fr r = fr_mul(x, y);
+            for (int k = 0; k < 8; k++) out[i * 8 + k] = r.v[k];
+        } else {
+            uint32_t c[8];
+            fr_to_canonical(c, x);
+            for (int k = 0; k < 8; k++) out[i * 8 + k] = c[k];
+        }
+    } else {
+        AffPt p, q;
+        for (int k = 0; k < 8; k++) {
+            p.x.v[k] = a[i * 16 + k];
+            p.y.v[k] = a[i * 16 + 8 + k];
+            q.x.v[k] = b[i * 16 + k];
+            q.y.v[k] = b[i * 16 + 8 + k];
+        }
+        AffPt r = pt_add_slow(p, q);
+        for (int k = 0; k < 8; k++) {
+            out[i * 16 + k] = r.x.v[k];
+            out[i * 16 + 8 + k] = r.y.v[k];
+        }
+    }
+}
+
+// dependent chains of the field primitives, 2 independent chains per thread
+__global__ void __launch_bounds__(256) k_microbench(int op, int iters, uint32_t *__restrict__ sink) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (op < 2) {
+        gf a, b;
+        for (int k = 0; k < 8; k++) {
+            a.v[k] = t * 2654435761u + k * 40503u + 1;
+            b.v[k] = t * 2246822519u + k * 9176u + 7;
+        }
+        a.v[7] &= 0x1ff;
+        b.v[7] &= 0x1ff;
+        for (int i = 0; i < iters; i++) {
+            if (op == 0) {
+                a = gf_mul(a, b);
+                b = gf_mul(b, a);
+            } else {
+                a = gf_sqr(a);
+                b = gf_sqr(b);
+            }
+        }
+        uint32_t s = 0;
+        for (int k = 0; k < 8; k++) s ^= a.v[k] ^ b.v[k];
+        if (s == 0x12345678u) sink[0] = s;
+    } else {
+        fr a, b;
+        for (int k = 0; k < 8; k++) {
+            a.v[k] = t * 2654435761u + k * 40503u + 1;
+            b.v[k] = t * 2246822519u + k * 9176u + 7;
+        }
+        a.v[7] &= 0x7f;
+        b.v[7] &= 0x7f;
+        for (int i = 0; i < iters; i++) {
+            a = fr_mul(a, b);
+            b = fr_mul(b, a);
+        }
+        uint32_t s = 0;
+        for (int k = 0; k < 8; k++) s ^= a.v[k] ^ b.v[k];
+        if (s == 0x12345678u) sink[0] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------- context
+int ctx_decode_into(dvp_ctx *ctx, const uint8_t *pts30, size_t n, AffPt *d_out, int64_t *first_invalid) {
+    int rc;
+    if ((rc = ctx->bytes.reserve(n * 30 + 16)) != 0) return rc;
+    if ((rc = ctx->small.reserve(64)) != 0) return rc;
+    unsigned long long init = ~0ull;
+    CKC(cudaMemcpyAsync(ctx->bytes.p, pts30, n * 30, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemcpyAsync(ctx->small.p, &init, 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_decode30<<<cdivu(n, 128), 128, 0, ctx->stream>>>((const uint8_t *)ctx->bytes.p, n, d_out,
+                                                      (unsigned long long *)ctx->small.p);
+    CKC(cudaGetLastError());
+    unsigned long long bad = 0;
+    CKC(cudaMemcpyAsync(&bad, ctx->small.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    if (bad != ~0ull) {
+        if (first_invalid) *first_invalid = (int64_t)bad;
+        return DVP_ERR_INVALID_POINT;
+    }
+    return DVP_OK;
+}
+
+extern "C" {
+
+const char *dvp_strerror(int code) {
+    switch (code) {
+    case DVP_OK: return "ok";
+    case DVP_ERR_BAD_ARG: return "bad argument";
+    case DVP_ERR_CUDA: return "CUDA error";
+    case DVP_ERR_OOM: return "out of device memory";
+    case DVP_ERR_INVALID_POINT: return "invalid point encoding";
+    case DVP_ERR_LENGTH_MISMATCH: return "scalar/point length mismatch";
+    case DVP_ERR_UNSATISFIED: return "R1CS row not satisfied";
+    case DVP_ERR_ALPHA_IN_DOMAIN: return "challenge lies in the evaluation domain";
+    case DVP_ERR_INTERNAL: return "internal error";
+    case DVP_ERR_NO_DEVICE: return "no CUDA device";
+    case DVP_ERR_NCCL: return "NCCL error";
+    }
+    return "unknown error";
+}
+int dvp_abi_version(void) { return 1; }
+
+int dvp_ctx_create(int device, dvp_ctx **out) {
+    if (!out) return DVP_ERR_BAD_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return DVP_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return DVP_ERR_BAD_ARG;
+    CKC(cudaSetDevice(device));
+    dvp_ctx *c = new dvp_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return DVP_ERR_CUDA;
+    }
+    int rc = c->msm.init(c->stream);
+    if (rc) {
+        dvp_ctx_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return DVP_OK;
+}
+void dvp_ctx_destroy(dvp_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->msm.destroy();
+    for (auto &s : ctx->slots) s.buf.release();
+    ctx->bytes.release();
+    ctx->small.release();
+    ctx->scal.release();
+    ctx->adhoc.release();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
+    if (!ctx || !name) return DVP_ERR_BAD_ARG;
+    if (!strcmp(name, "msm_window_bits")) {
+        if (value != 0 && (value < 4 || value > 20)) return DVP_ERR_BAD_ARG;
+        ctx->msm.force_window_bits = (int)value;
+        return DVP_OK;
+    }
+    if (!strcmp(name, "timing")) {
+        ctx->msm.timing = value != 0;
+        return DVP_OK;
+    }
+    return DVP_ERR_BAD_ARG;
+}
+
+static int slot_ok(dvp_ctx *ctx, int slot) { return ctx && slot >= 0 && slot < DVP_MAX_SRS_SLOTS; }
+
+int dvp_srs_append(dvp_ctx *ctx, int slot, const uint8_t *pts30, size_t n, int64_t *first_invalid) {
+    if (!slot_ok(ctx, slot) || (!pts30 && n)) return DVP_ERR_BAD_ARG;
+    CKC(cudaSetDevice(ctx->device));
+    SrsSlot &s = ctx->slots[slot];
+    const size_t need = (s.n + n) * sizeof(AffPt);
+    if (need > s.buf.cap) {
+        DevBuf nb;
+        int rc = nb.reserve(need);
+        if (rc) return rc;
+        if (s.n) CKC(cudaMemcpyAsync(nb.p, s.buf.p, s.n * sizeof(AffPt), cudaMemcpyDeviceToDevice, ctx->stream));
+        CKC(cudaStreamSynchronize(ctx->stream));
+        s.buf.release();
+        s.buf = nb;
+    }
+    if (n == 0) return DVP_OK;
+    int rc = ctx_decode_into(ctx, pts30, n, s.buf.as<AffPt>() + s.n, first_invalid);
+    if (rc) return rc;
+    s.n += n;
+    return DVP_OK;
+}
+int dvp_srs_load(dvp_ctx *ctx, int slot, const uint8_t *pts30, size_t n, int64_t *first_invalid) {
+    if (!slot_ok(ctx, slot)) return DVP_ERR_BAD_ARG;
+    ctx->slots[slot].n = 0;
+    return dvp_srs_append(ctx, slot, pts30, n, first_invalid);
+}
+int dvp_srs_size(dvp_ctx *ctx, int slot, size_t *n) {
+    if (!slot_ok(ctx, slot) || !n) return DVP_ERR_BAD_ARG;
+    *n = ctx->slots[slot].n;
+    return DVP_OK;
+}
+int dvp_srs_free(dvp_ctx *ctx, int slot) {
+    if (!slot_ok(ctx, slot)) return DVP_ERR_BAD_ARG;
+    CKC(cudaSetDevice(ctx->device));
+    ctx->slots[slot].buf.release();
+    ctx->slots[slot].n = 0;
+    return DVP_OK;
+}
+int dvp_srs_read(dvp_ctx *ctx, int slot, size_t offset, size_t n, uint8_t *pts30) {
+    if (!slot_ok(ctx, slot) || (!pts30 && n)) return DVP_ERR_BAD_ARG;
+    SrsSlot &s = ctx->slots[slot];
+    if (offset > s.n || n > s.n - offset) return DVP_ERR_LENGTH_MISMATCH;
+    if (!n) return DVP_OK;
+    CKC(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->bytes.reserve(n * 30)) != 0) return rc;
+    k_encode30<<<cdivu(n, 128), 128, 0, ctx->stream>>>(s.buf.as<AffPt>() + offset, n, (uint8_t *)ctx->bytes.p);
+    CKC(cudaGetLastError());
+    CKC(cudaMemcpyAsync(pts30, ctx->bytes.p, n * 30, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    return DVP_OK;
+}
+
+int dvp_msm_device(dvp_ctx *ctx, int slot, size_t offset, const void *d_scalars, size_t n, uint8_t out30[30]) {
+    if (!slot_ok(ctx, slot) || !out30 || (!d_scalars && n)) return DVP_ERR_BAD_ARG;
+    SrsSlot &s = ctx->slots[slot];
+    if (offset > s.n || n > s.n - offset) return DVP_ERR_LENGTH_MISMATCH;
+    CKC(cudaSetDevice(ctx->device));
+    AffPt r;
+    int rc = ctx->msm.run(s.buf.as<AffPt>() + offset, (const uint32_t *)d_scalars, n, &r);
+    if (rc) return rc;
+    host::encode30(out30, r);
+    return DVP_OK;
+}
+int dvp_msm(dvp_ctx *ctx, int slot, size_t offset, const uint64_t *scalars_mont, size_t n, uint8_t out30[30]) {
+    if (!slot_ok(ctx, slot) || !out30 || (!scalars_mont && n)) return DVP_ERR_BAD_ARG;
+    SrsSlot &s = ctx->slots[slot];
+    if (offset > s.n || n > s.n - offset) return DVP_ERR_LENGTH_MISMATCH;
+    CKC(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->scal.reserve(n * 32 + 32)) != 0) return rc;
+    if (n) CKC(cudaMemcpyAsync(ctx->scal.p, scalars_mont, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    return dvp_msm_device(ctx, slot, offset, ctx->scal.p, n, out30);
+}
+int dvp_msm_adhoc(dvp_ctx *ctx, const uint8_t *pts30, const uint64_t *scalars_mont, size_t n, uint8_t out30[30]) {
+    if (!ctx || !out30 || ((!pts30 || !scalars_mont) && n)) return DVP_ERR_BAD_ARG;
+    CKC(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->adhoc.reserve(n * sizeof(AffPt) + 64)) != 0) return rc;
+    if ((rc = ctx->scal.reserve(n * 32 + 32)) != 0) return rc;
+    AffPt r = pt_inf();
+    if (n) {
+        if ((rc = ctx_decode_into(ctx, pts30, n, ctx->adhoc.as<AffPt>(), nullptr)) != 0) return rc;
+        CKC(cudaMemcpyAsync(ctx->scal.p, scalars_mont, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = ctx->msm.run(ctx->adhoc.as<AffPt>(), ctx->scal.as<uint32_t>(), n, &r)) != 0) return rc;
+    }
+    host::encode30(out30, r);
+    return DVP_OK;
+}
+int dvp_msm_last_stats(dvp_ctx *ctx, dvp_msm_stats *out) {
+    if (!ctx || !out) return DVP_ERR_BAD_ARG;
+    const MsmStats &s = ctx->msm.last;
+    out->window_bits = s.window_bits;
+    out->windows = s.windows;
+    out->rounds_main = s.rounds_main;
+    out->rounds_a = s.rounds_a;
+    out->rounds_b = s.rounds_b;
+    out->launches = s.launches;
+    out->ms_recode_sort = s.ms_recode_sort;
+    out->ms_accumulate = s.ms_accumulate;
+    out->ms_reduce = s.ms_reduce;
+    out->ms_tail = s.ms_tail;
+    return DVP_OK;
+}
+
+int dvp_point_add(dvp_ctx *ctx, const uint8_t a30[30], const uint8_t b30[30], uint8_t out30[30]) {
+    if (!ctx || !a30 || !b30 || !out30) return DVP_ERR_BAD_ARG;
+    CKC(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->small.reserve(128)) != 0) return rc;
+    uint8_t h[60];
+    memcpy(h, a30, 30);
+    memcpy(h + 30, b30, 30);
+    uint8_t *d = (uint8_t *)ctx->small.p;
+    CKC(cudaMemcpyAsync(d, h, 60, cudaMemcpyHostToDevice, ctx->stream));
+    k_point_add30<<<1, 1, 0, ctx->stream>>>(d, d + 64, (int *)(d + 96));
+    CKC(cudaGetLastError());
+    uint8_t res[36];
+    CKC(cudaMemcpyAsync(res, d + 64, 36, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    int ok;
+    memcpy(&ok, res + 32, 4);
+    if (!ok) return DVP_ERR_INVALID_POINT;
+    memcpy(out30, res, 30);
+    return DVP_OK;
+}
+
+int dvp_dev_alloc(dvp_ctx *ctx, size_t bytes, void **dptr) {
+    if (!ctx || !dptr) return DVP_ERR_BAD_ARG;
+    CKC(cudaSetDevice(ctx->device));
+    if (cudaMalloc(dptr, bytes ? bytes : 1) != cudaSuccess) return DVP_ERR_OOM;
+    return DVP_OK;
+}
+int dvp_dev_free(dvp_ctx *ctx, void *dptr) {
+    if (!ctx) return DVP_ERR_BAD_ARG;
+    CKC(cudaSetDevice(ctx->device));
+    CKC(cudaFree(dptr));
+    return DVP_OK;
+}
+int dvp_dev_upload(dvp_ctx *ctx, void *dptr, const void *host, size_t bytes) {
+    if (!ctx || !dptr || !host) return DVP_ERR_BAD_ARG;
+    CKC(cudaSetDevice(ctx->device));
+    CKC(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    return DVP_OK;
+}
+int dvp_dev_download(dvp_ctx *ctx, void *host, const void *dptr, size_t bytes) {
+    if (!ctx || !dptr || !host) return DVP_ERR_BAD_ARG;
+    CKC(cudaSetDevice(ctx->device));
+    CKC(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    return DVP_OK;
+}
+
+int dvp_selftest_op(dvp_ctx *ctx, int op, const void *a, const void *b, void *out, size_t n) {
+    if (!ctx || !a || !out || op < 0 || op > 5) return DVP_ERR_BAD_ARG;
+    if ((op == 0 || op == 3 || op == 5) && !b) return DVP_ERR_BAD_ARG;
+    if (!n) return DVP_OK;
+    CKC(cudaSetDevice(ctx->device));
+    const size_t esz = op == 5 ? 64 : 32;
+    void *da = nullptr, *db = nullptr, *dout = nullptr;
+    CKC(cudaMalloc(&da, n * esz));
+    CKC(cudaMalloc(&db, n * esz));
+    CKC(cudaMalloc(&dout, n * esz));
+    CKC(cudaMemcpyAsync(da, a, n * esz, cudaMemcpyHostToDevice, ctx->stream));
+    if (b) CKC(cudaMemcpyAsync(db, b, n * esz, cudaMemcpyHostToDevice, ctx->stream));
+    k_selftest<<<cdivu(n, 128), 128, 0, ctx->stream>>>(op, (const uint32_t *)da, b ? (const uint32_t *)db : nullptr,
+                                                      (uint32_t *)dout, n);
+    CKC(cudaGetLastError());
+    CKC(cudaMemcpyAsync(out, dout, n * esz, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dout);
+    return DVP_OK;
+}
+
+int dvp_microbench(dvp_ctx *ctx, int op, int iters, double *ops_per_sec) {
+    if (!ctx || !ops_per_sec || op < 0 || op > 2 || iters <= 0) return DVP_ERR_BAD_ARG;
+    CKC(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->small.reserve(128)) != 0) return rc;
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 4, threads = 256;
+    cudaEvent_t e0, e1;
+    CKC(cudaEventCreate(&e0));
+    CKC(cudaEventCreate(&e1));
+    k_microbench<<<blocks, threads, 0, ctx->stream>>>(op, 4, (uint32_t *)ctx->small.p); // warm-up
+    CKC(cudaEventRecord(e0, ctx->stream));
+    k_microbench<<<blocks, threads, 0, ctx->stream>>>(op, iters, (uint32_t *)ctx->small.p);
+    CKC(cudaEventRecord(e1, ctx->stream));
+    CKC(cudaEventSynchronize(e1));
+    float ms = 0;
+    CKC(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ops_per_sec = (double)blocks * threads * 2.0 * iters / (ms * 1e-3);
+    return DVP_OK;
+}
+
+} // extern "C"

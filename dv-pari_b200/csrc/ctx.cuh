@@ -1,0 +1,19 @@
+// The opaque context behind dvp_ctx: one device, one stream, resident SRS slots, grow-only scratch.
+#pragma once
+#include "../../include/dvpari.h"
+#include "msm.cuh"
+
+struct SrsSlot {
+    dvp::DevBuf buf; // AffPt[n], decoded once (replaces read_point_vec_from_file per prove)
+    size_t n = 0;
+};
+
+struct dvp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    dvp::MsmEngine msm;
+    SrsSlot slots[DVP_MAX_SRS_SLOTS];
+    dvp::DevBuf bytes, small, scal, adhoc;
+};
+
+int ctx_decode_into(dvp_ctx *ctx, const uint8_t *pts30, size_t n, dvp::AffPt *d_out, int64_t *first_invalid);

@@ -1,0 +1,108 @@
+// dvp_hostcheck_op: runs the SAME __host__ __device__ source that the kernels execute, on the CPU.
+// It exists only so the `-m "not gpu"` tests can pin the device arithmetic (GF(2^233), Fr, point
+// addition, the 30-byte codec, the PCLMUL host tail) against the oracle without a GPU.  No product
+// path calls it; every dvp_* entry point that computes needs a CUDA device.
+#include <cstring>
+#include "../../include/dvpari.h"
+#include "fr.cuh"
+#include "host_gf.hpp"
+#include "k233_codec.cuh"
+
+using namespace dvp;
+
+extern "C" int dvp_hostcheck_op(int op, const void *a_, const void *b_, void *out_, size_t n) {
+    const uint8_t *a = (const uint8_t *)a_, *b = (const uint8_t *)b_;
+    uint8_t *out = (uint8_t *)out_;
+    for (size_t i = 0; i < n; i++) {
+        switch (op) {
+        case 0: case 1: case 2: case 6: case 7: {
+            gf x, y = gf_zero(), r;
+            memcpy(x.v, a + i * 32, 32);
+            if (b) memcpy(y.v, b + i * 32, 32);
+            r = op == 0 ? gf_mul(x, y) : op == 1 ? gf_sqr(x) : op == 2 ? gf_inv(x) : op == 6 ? host::hmul(x, y) : host::hinv(x);
+            memcpy(out + i * 32, r.v, 32);
+            break;
+        }
+        case 3: {
+            fr x, y;
+            memcpy(x.v, a + i * 32, 32);
+            memcpy(y.v, b + i * 32, 32);
+            fr r = fr_mul(x, y);
+            memcpy(out + i * 32, r.v, 32);
+            break;
+        }
+        case 4: {
+            fr x;
+            memcpy(x.v, a + i * 32, 32);
+            uint32_t c[8];
+            fr_to_canonical(c, x);
+            memcpy(out + i * 32, c, 32);
+            break;
+        }
+        case 5: { // affine add, 64-byte points
+            AffPt p, q;
+            memcpy(&p, a + i * 64, 64);
+            memcpy(&q, b + i * 64, 64);
+            AffPt r = pt_add_slow(p, q);
+            memcpy(out + i * 64, &r, 64);
+            break;
+        }
+        case 8: { // decode: 30 bytes -> 64-byte point + validity byte (out stride 65)
+            AffPt p;
+            bool ok = xsk233_decode_pt(a + i * 30, p);
+            memcpy(out + i * 65, &p, 64);
+            out[i * 65 + 64] = ok ? 1 : 0;
+            break;
+        }
+        case 9: { // encode: 64-byte point -> 30 bytes (device formula) ; 10: host tail formula
+            AffPt p;
+            memcpy(&p, a + i * 64, 64);
+            xsk233_encode_pt(out + i * 30, p);
+            break;
+        }
+        case 10: {
+            AffPt p;
+            memcpy(&p, a + i * 64, 64);
+            host::encode30(out + i * 30, p);
+            break;
+        }
+        case 11: { // host LD accumulator: 2*a + b  (a, b affine 64-byte) -> affine
+            AffPt p, q;
+            memcpy(&p, a + i * 64, 64);
+            memcpy(&q, b + i * 64, 64);
+            host::LdPt acc = host::ld_add_affine(host::ld_inf(), p);
+            acc = host::ld_dbl(acc);
+            acc = host::ld_add_affine(acc, q);
+            AffPt r = host::ld_to_affine(acc);
+            memcpy(out + i * 64, &r, 64);
+            break;
+        }
+        case 12: { // fr_add / 13 fr_sub / 14 fr_inv
+            fr x, y;
+            memcpy(x.v, a + i * 32, 32);
+            memcpy(y.v, b + i * 32, 32);
+            fr r = fr_add(x, y);
+            memcpy(out + i * 32, r.v, 32);
+            break;
+        }
+        case 13: {
+            fr x, y;
+            memcpy(x.v, a + i * 32, 32);
+            memcpy(y.v, b + i * 32, 32);
+            fr r = fr_sub(x, y);
+            memcpy(out + i * 32, r.v, 32);
+            break;
+        }
+        case 14: {
+            fr x;
+            memcpy(x.v, a + i * 32, 32);
+            fr r = fr_inv(x);
+            memcpy(out + i * 32, r.v, 32);
+            break;
+        }
+        default:
+            return DVP_ERR_BAD_ARG;
+        }
+    }
+    return DVP_OK;
+}

@@ -1,0 +1,788 @@
+// sect233k1 multi-scalar multiplication for sm_100a.
+//
+// Replaces curve::multi_scalar_mul (/root/reference/src/curve.rs:141-158; call sites
+// src/proving.rs:463,512,680).  The reference does one tau-adic scalar multiplication per point and
+// a tree sum; the group element is unique, so any algorithm matches bit for bit.  Here:
+//
+//   recode      Montgomery Fr -> canonical 232-bit integer -> W signed c-bit digits
+//   sort        counting sort of (point, window) entries by bucket (histogram, scan, scatter)
+//   accumulate  every bucket is a segment; segments are tree-reduced in rounds of independent
+//               affine additions sharing one inversion (Montgomery trick, hierarchical)
+//   reduce      sum_b (b+1) B_b per window without a serial running sum: rows/columns of the bucket
+//               matrix (level A), then per-bit subset sums (level B), both on the same tree engine
+//   tail        the host folds the W*c per-bit partial sums with one 232-step double-and-add
+//
+// Everything between the scalars and the W*c partial sums stays on the device; a single 8-byte
+// read-back (the longest bucket) sizes the rounds.
+#include "msm.cuh"
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+#include "../../include/dvpari.h"
+#include "fr.cuh"
+#include "host_gf.hpp"
+
+namespace dvp {
+
+#define CK(x)                                                                                       \
+    do {                                                                                            \
+        cudaError_t e_ = (x);                                                                       \
+        if (e_ != cudaSuccess) {                                                                    \
+            fprintf(stderr, "[dvpari] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__,  \
+                    __LINE__);                                                                      \
+            return DVP_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+int DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        p = nullptr;
+        return DVP_ERR_OOM;
+    }
+    cap = want;
+    return 0;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+int choose_window_bits(size_t n) {
+    // adds ~ n*W + tail(2^(c-1)*W); the tail rounds are latency-bound, so stay a little below the
+    // arithmetic optimum
+    if (n <= (1u << 10)) return 6;
+    if (n <= (1u << 13)) return 8;
+    if (n <= (1u << 16)) return 11;
+    if (n <= (1u << 18)) return 13;
+    if (n <= (1u << 21)) return 15;
+    return 16;
+}
+
+// ------------------------------------------------------------------------------------------------
+// recode + histogram
+// ------------------------------------------------------------------------------------------------
+__global__ void k_recode_count(const uint32_t *__restrict__ scalars, uint32_t n, int c, int W, uint32_t nb,
+                               uint32_t *__restrict__ keys, uint32_t *__restrict__ seg_len) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr a;
+    const uint4 *q = reinterpret_cast<const uint4 *>(scalars + (size_t)i * 8);
+    uint4 lo = q[0], hi = q[1];
+    a.v[0] = lo.x; a.v[1] = lo.y; a.v[2] = lo.z; a.v[3] = lo.w;
+    a.v[4] = hi.x; a.v[5] = hi.y; a.v[6] = hi.z; a.v[7] = hi.w;
+    uint32_t k[9];
+    fr_to_canonical(k, a);
+    k[8] = 0;
+    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
+    uint32_t carry = 0;
+    for (int j = 0; j < W; j++) {
+        const int bit = j * c, w = bit >> 5, sh = bit & 31;
+        uint32_t raw = 0;
+        if (w < 8) {
+            uint64_t two = (uint64_t)k[w] | ((uint64_t)k[w + 1] << 32);
+            raw = (uint32_t)(two >> sh) & mask;
+        }
+        raw += carry;
+        uint32_t d, neg;
+        if (raw > half) {
+            d = (1u << c) - raw;
+            neg = 1;
+            carry = 1;
+        } else {
+            d = raw;
+            neg = 0;
+            carry = 0;
+        }
+        uint32_t out = 0xffffffffu;
+        if (d) {
+            const uint32_t key = (uint32_t)j * nb + d - 1;
+            out = (key << 1) | neg;
+            atomicAdd(&seg_len[key], 1u);
+        }
+        keys[(size_t)j * n + i] = out;
+    }
+}
+
+__global__ void k_scatter(const uint32_t *__restrict__ keys, uint32_t n, size_t total, uint32_t *__restrict__ cursor,
+                          uint32_t *__restrict__ entries) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const uint32_t k = keys[e];
+    if (k == 0xffffffffu) return;
+    const uint32_t i = (uint32_t)(e % n);
+    const uint32_t pos = atomicAdd(&cursor[k >> 1], 1u);
+    entries[pos] = i | ((k & 1u) << 31);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-wide exclusive scans over segment lengths.
+//   MODE 0: value = L                    -> start[s]                  (counting-sort offsets)
+//   MODE 1: value = (L/2, (L+1)/2) packed -> task_start[s], out_start[s], new_len[s]
+// info[0] = max L, info[1] = total tasks, info[2] = total outputs
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <int MODE> __device__ __forceinline__ uint64_t scan_val(uint32_t L) {
+    if (MODE == 0) return L;
+    return (uint64_t)(L >> 1) | ((uint64_t)((L + 1) >> 1) << 32);
+}
+
+__device__ __forceinline__ uint64_t block_reduce_u64(uint64_t v, uint64_t *sh) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        v = lane < (blockDim.x >> 5) ? sh[lane] : 0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[0] = v;
+    }
+    __syncthreads();
+    v = sh[0];
+    __syncthreads();
+    return v;
+}
+
+template <int MODE>
+__global__ void k_scan1(const uint32_t *__restrict__ len, uint32_t nseg, uint64_t *__restrict__ blk_sum,
+                        uint32_t *__restrict__ info) {
+    __shared__ uint64_t sh[32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint64_t s = 0;
+    uint32_t mx = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const uint32_t idx = base + k;
+        const uint32_t L = idx < nseg ? len[idx] : 0;
+        s += scan_val<MODE>(L);
+        mx = max(mx, L);
+    }
+    s = block_reduce_u64(s, sh);
+    if (threadIdx.x == 0) blk_sum[blockIdx.x] = s;
+    if (MODE == 1) {
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0 && mx) atomicMax(&info[0], mx);
+    }
+}
+
+// single block: exclusive scan of blk_sum[0..nblk) in place; blk_sum[nblk] = total
+__global__ void k_scan2(uint64_t *__restrict__ blk_sum, uint32_t nblk) {
+    __shared__ uint64_t sh[SCAN_THREADS];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nblk; base += SCAN_THREADS) {
+        const uint32_t idx = base + threadIdx.x;
+        const uint64_t v = idx < nblk ? blk_sum[idx] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < SCAN_THREADS; o <<= 1) {
+            uint64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        const uint64_t incl = sh[threadIdx.x];
+        if (idx < nblk) blk_sum[idx] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == SCAN_THREADS - 1) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) blk_sum[nblk] = carry;
+}
+
+template <int MODE>
+__global__ void k_scan3(const uint32_t *__restrict__ len, uint32_t nseg, const uint64_t *__restrict__ blk_sum,
+                        uint32_t *__restrict__ out_a, uint32_t *__restrict__ out_b, uint32_t *__restrict__ new_len,
+                        uint32_t *__restrict__ info) {
+    __shared__ uint64_t sh[32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint64_t v[SCAN_ITEMS];
+    uint32_t L[SCAN_ITEMS];
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const uint32_t idx = base + k;
+        L[k] = idx < nseg ? len[idx] : 0;
+        v[k] = scan_val<MODE>(L[k]);
+        s += v[k];
+    }
+    // exclusive scan of the per-thread sums across the block
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sh[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t w = sh[lane];
+        uint64_t wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        sh[lane] = wi - w;
+    }
+    __syncthreads();
+    uint64_t run = blk_sum[blockIdx.x] + sh[wid] + (incl - s);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const uint32_t idx = base + k;
+        if (idx < nseg) {
+            if (MODE == 0) {
+                out_a[idx] = (uint32_t)run;
+                out_b[idx] = (uint32_t)run;
+            } else {
+                out_a[idx] = (uint32_t)run;
+                out_b[idx] = (uint32_t)(run >> 32);
+                new_len[idx] = (L[k] + 1) >> 1;
+            }
+        }
+        run += v[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        const uint64_t tot = blk_sum[gridDim.x];
+        if (MODE == 0) {
+            out_a[nseg] = (uint32_t)tot;
+        } else {
+            out_a[nseg] = (uint32_t)tot;
+            out_b[nseg] = (uint32_t)(tot >> 32);
+            info[1] = (uint32_t)tot;
+            info[2] = (uint32_t)(tot >> 32);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tree rounds
+// ------------------------------------------------------------------------------------------------
+template <bool INDEXED>
+__device__ __forceinline__ gf fetch_x(const AffPt *__restrict__ src, const uint32_t *__restrict__ ent, uint32_t pos) {
+    if (INDEXED) return gf_load(&src[ent[pos] & 0x7fffffffu].x);
+    return gf_load(&src[pos].x);
+}
+template <bool INDEXED>
+__device__ __forceinline__ AffPt fetch_pt(const AffPt *__restrict__ src, const uint32_t *__restrict__ ent, uint32_t pos) {
+    if (INDEXED) {
+        const uint32_t e = ent[pos];
+        AffPt p = pt_load(&src[e & 0x7fffffffu]);
+        if (e >> 31) p.y = gf_add(p.y, p.x);
+        return p;
+    }
+    return pt_load(&src[pos]);
+}
+
+// largest s in [0, nseg) with start[s] <= t  (start has nseg + 1 entries, start[nseg] = total > t)
+__device__ __forceinline__ uint32_t seg_search(const uint32_t *__restrict__ start, uint32_t nseg, uint32_t t) {
+    uint32_t lo = 0, hi = nseg; // invariant: start[lo] <= t < start[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (start[mid] <= t) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// pass 1: per task resolve (a, b, out), form the denominator, chain a per-thread prefix product
+template <bool INDEXED, int B>
+__global__ void __launch_bounds__(256)
+    k_pass1(const AffPt *__restrict__ src, const uint32_t *__restrict__ ent, const uint32_t *__restrict__ in_start,
+            const uint32_t *__restrict__ task_start, const uint32_t *__restrict__ out_start, uint32_t nseg,
+            const uint32_t *__restrict__ info, uint4 *__restrict__ desc, gf *__restrict__ prefix,
+            gf *__restrict__ thr_total) {
+    const uint32_t ntasks = info[1];
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = gtid & 31, warp = gtid >> 5;
+    const uint32_t base = warp * (32u * B);
+    gf acc = gf_one();
+    uint32_t s = 0xffffffffu;
+#pragma unroll 1
+    for (int k = 0; k < B; k++) {
+        const uint32_t t = base + k * 32 + lane;
+        if (t >= ntasks) break;
+        if (s == 0xffffffffu) s = seg_search(task_start, nseg, t);
+        else
+            while (task_start[s + 1] <= t) s++;
+        const uint32_t j = t - task_start[s];
+        const uint32_t a = in_start[s] + 2 * j, o = out_start[s] + j;
+        desc[t] = make_uint4(a, a + 1, o, 0);
+        const gf x1 = fetch_x<INDEXED>(src, ent, a), x2 = fetch_x<INDEXED>(src, ent, a + 1);
+        gf d = gf_add(x1, x2);
+        if (gf_is_zero(x1) | gf_is_zero(x2)) d = gf_one();
+        else if (gf_is_zero(d)) {
+            const AffPt p1 = fetch_pt<INDEXED>(src, ent, a), p2 = fetch_pt<INDEXED>(src, ent, a + 1);
+            d = gf_eq(p1.y, p2.y) ? x1 : gf_one();
+        }
+        gf_store(&prefix[t], acc);
+        acc = gf_mul(acc, d);
+    }
+    gf_store(&thr_total[gtid], acc);
+}
+
+// pass 2: walk the same tasks backwards with the inverse of the thread total, finish the additions
+template <bool INDEXED, int B>
+__global__ void __launch_bounds__(256)
+    k_pass2(const AffPt *__restrict__ src, const uint32_t *__restrict__ ent, const uint32_t *__restrict__ info,
+            const uint4 *__restrict__ desc, const gf *__restrict__ prefix, const gf *__restrict__ thr_inv,
+            AffPt *__restrict__ dst) {
+    const uint32_t ntasks = info[1];
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = gtid & 31, warp = gtid >> 5;
+    const uint32_t base = warp * (32u * B);
+    if (base + lane >= ntasks) return;
+    gf inv = gf_load(&thr_inv[gtid]);
+#pragma unroll 1
+    for (int k = B - 1; k >= 0; k--) {
+        const uint32_t t = base + k * 32 + lane;
+        if (t >= ntasks) continue;
+        const uint4 de = desc[t];
+        const AffPt p1 = fetch_pt<INDEXED>(src, ent, de.x), p2 = fetch_pt<INDEXED>(src, ent, de.y);
+        gf d;
+        const int kind = pair_classify(p1, p2, d);
+        const gf dinv = gf_mul(inv, gf_load(&prefix[t]));
+        if (k) inv = gf_mul(inv, d);
+        pt_store(&dst[de.z], pair_finish(p1, p2, kind, dinv));
+    }
+}
+
+// segments of odd length carry their last element to the next round
+template <bool INDEXED>
+__global__ void k_copy_odd(const AffPt *__restrict__ src, const uint32_t *__restrict__ ent,
+                           const uint32_t *__restrict__ in_start, const uint32_t *__restrict__ len,
+                           const uint32_t *__restrict__ out_start, uint32_t nseg, AffPt *__restrict__ dst) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    const uint32_t L = len[s];
+    if (L & 1) pt_store(&dst[out_start[s] + (L >> 1)], fetch_pt<INDEXED>(src, ent, in_start[s] + L - 1));
+}
+
+// after the last round every segment holds 0 or 1 points
+template <bool INDEXED>
+__global__ void k_finalize(const AffPt *__restrict__ src, const uint32_t *__restrict__ ent,
+                           const uint32_t *__restrict__ in_start, const uint32_t *__restrict__ len, uint32_t nseg,
+                           AffPt *__restrict__ dst) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    AffPt p = pt_inf();
+    if (len[s]) p = fetch_pt<INDEXED>(src, ent, in_start[s]);
+    pt_store(&dst[s], p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// hierarchical batched inversion of n non-zero field elements
+// ------------------------------------------------------------------------------------------------
+__global__ void k_binv_direct(const gf *__restrict__ in, gf *__restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    gf_store(&out[i], gf_inv(gf_load(&in[i])));
+}
+__global__ void k_binv_up(const gf *__restrict__ in, uint32_t n, uint32_t G, gf *__restrict__ pre,
+                          gf *__restrict__ tot) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lo = g * G;
+    if (lo >= n) return;
+    const uint32_t hi = min(n, lo + G);
+    gf acc = gf_one();
+    for (uint32_t i = lo; i < hi; i++) {
+        gf_store(&pre[i], acc);
+        acc = gf_mul(acc, gf_load(&in[i]));
+    }
+    gf_store(&tot[g], acc);
+}
+__global__ void k_binv_down(const gf *__restrict__ in, uint32_t n, uint32_t G, const gf *__restrict__ pre,
+                            const gf *__restrict__ tot_inv, gf *__restrict__ out) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lo = g * G;
+    if (lo >= n) return;
+    const uint32_t hi = min(n, lo + G);
+    gf inv = gf_load(&tot_inv[g]);
+    for (uint32_t i = hi; i-- > lo;) {
+        const gf v = gf_load(&in[i]);
+        gf_store(&out[i], gf_mul(inv, gf_load(&pre[i])));
+        if (i > lo) inv = gf_mul(inv, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// index lists for the two reduction levels (all segments have equal, power-of-two length)
+// ------------------------------------------------------------------------------------------------
+// level A: window w has nb = R*m buckets b = hi*m + lo.  Entries: nb row-major then nb column-major.
+__global__ void k_gen_level_a(uint32_t W, uint32_t nb, uint32_t lm, uint32_t *__restrict__ ent) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= W * 2 * nb) return;
+    const uint32_t w = e / (2 * nb), r = e % (2 * nb);
+    const uint32_t m = 1u << lm, R = nb >> lm;
+    uint32_t b;
+    if (r < nb) b = r;
+    else {
+        const uint32_t q = r - nb, lo = q / R, hi = q % R;
+        b = hi * m + lo;
+    }
+    ent[e] = w * nb + b;
+}
+// level B: per window lm column-bit subsets (m/2 each), lr row-bit subsets (R/2 each), then all m columns.
+// Source layout rc[w*(R+m) + hi] (rows) and rc[w*(R+m) + R + lo] (columns).
+__global__ void k_gen_level_b(uint32_t W, uint32_t lr, uint32_t lm, uint32_t *__restrict__ ent) {
+    const uint32_t R = 1u << lr, m = 1u << lm;
+    const uint32_t per = lm * (m >> 1) + lr * (R >> 1) + m;
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= W * per) return;
+    const uint32_t w = e / per;
+    uint32_t r = e % per;
+    const uint32_t basew = w * (R + m);
+    if (r < lm * (m >> 1)) {
+        const uint32_t t = r / (m >> 1), q = r % (m >> 1);
+        // q-th index with bit t set
+        const uint32_t lo = ((q >> t) << (t + 1)) | (1u << t) | (q & ((1u << t) - 1));
+        ent[e] = basew + R + lo;
+        return;
+    }
+    r -= lm * (m >> 1);
+    if (r < lr * (R >> 1)) {
+        const uint32_t t = r / (R >> 1), q = r % (R >> 1);
+        const uint32_t hi = ((q >> t) << (t + 1)) | (1u << t) | (q & ((1u << t) - 1));
+        ent[e] = basew + hi;
+        return;
+    }
+    r -= lr * (R >> 1);
+    ent[e] = basew + R + r;
+}
+// segment tables: nper segments per group with lengths given by a small pattern
+__global__ void k_gen_segs_a(uint32_t W, uint32_t nb, uint32_t lm, uint32_t *__restrict__ start,
+                             uint32_t *__restrict__ len) {
+    const uint32_t m = 1u << lm, R = nb >> lm, per = R + m;
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > W * per) return;
+    if (s == W * per) {
+        start[s] = W * 2 * nb;
+        return;
+    }
+    const uint32_t w = s / per, r = s % per;
+    if (r < R) {
+        start[s] = w * 2 * nb + r * m;
+        len[s] = m;
+    } else {
+        start[s] = w * 2 * nb + nb + (r - R) * R;
+        len[s] = R;
+    }
+}
+__global__ void k_gen_segs_b(uint32_t W, uint32_t lr, uint32_t lm, uint32_t *__restrict__ start,
+                             uint32_t *__restrict__ len) {
+    const uint32_t R = 1u << lr, m = 1u << lm, c = lr + lm + 1;
+    const uint32_t per = lm * (m >> 1) + lr * (R >> 1) + m;
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > W * c) return;
+    if (s == W * c) {
+        start[s] = W * per;
+        return;
+    }
+    const uint32_t w = s / c, q = s % c;
+    if (q < lm) {
+        start[s] = w * per + q * (m >> 1);
+        len[s] = m >> 1;
+    } else if (q < lm + lr) {
+        start[s] = w * per + lm * (m >> 1) + (q - lm) * (R >> 1);
+        len[s] = R >> 1;
+    } else {
+        start[s] = w * per + lm * (m >> 1) + lr * (R >> 1);
+        len[s] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------
+int MsmEngine::init(cudaStream_t s) {
+    stream = s;
+    CK(cudaMallocHost(&h_info, 64));
+    for (auto &e : ev) CK(cudaEventCreate(&e));
+    return 0;
+}
+void MsmEngine::destroy() {
+    DevBuf *all[] = {&keys, &entries, &seg_len[0], &seg_len[1], &seg_start[0], &seg_start[1], &c_len, &c_start,
+                     &task_start, &cursor, &blk, &info, &pp[0], &pp[1], &prefix, &desc, &thr_total, &thr_inv,
+                     &lvl_pre[0], &lvl_pre[1], &lvl_tot[0], &lvl_tot[1], &lvl_inv[0], &lvl_inv[1], &buckets, &rc,
+                     &hb, &ents2};
+    for (auto b : all) b->release();
+    if (h_info) cudaFreeHost(h_info);
+    if (h_pts) cudaFreeHost(h_pts);
+    h_info = h_pts = nullptr;
+    h_pts_cap = 0;
+    for (auto &e : ev)
+        if (e) cudaEventDestroy(e), e = nullptr;
+}
+
+namespace {
+
+inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
+constexpr uint32_t BINV_G = 16;        // group size of one batched-inversion level
+constexpr uint32_t BINV_DIRECT = 8192; // at or below this many elements every thread inverts its own
+
+struct Tree {
+    MsmEngine &E;
+    cudaStream_t st;
+    explicit Tree(MsmEngine &e) : E(e), st(e.stream) {}
+
+    int scan_plan(const uint32_t *len, uint32_t nseg, uint32_t *task_start, uint32_t *out_start, uint32_t *new_len) {
+        const uint32_t nblk = cdiv(nseg, SCAN_TILE);
+        k_scan1<1><<<nblk, SCAN_THREADS, 0, st>>>(len, nseg, E.blk.as<uint64_t>(), E.info.as<uint32_t>());
+        k_scan2<<<1, SCAN_THREADS, 0, st>>>(E.blk.as<uint64_t>(), nblk);
+        k_scan3<1><<<nblk, SCAN_THREADS, 0, st>>>(len, nseg, E.blk.as<uint64_t>(), task_start, out_start, new_len,
+                                                  E.info.as<uint32_t>());
+        E.launches += 3;
+        CK(cudaGetLastError());
+        return 0;
+    }
+
+    // n non-zero elements in -> inverses out
+    int batch_inv(const gf *in, gf *out, uint32_t n, int depth) {
+        if (n <= BINV_DIRECT || depth >= 2) {
+            k_binv_direct<<<cdiv(n, 128), 128, 0, st>>>(in, out, n);
+            E.launches++;
+            CK(cudaGetLastError());
+            return 0;
+        }
+        const uint32_t ng = cdiv(n, BINV_G);
+        gf *pre = E.lvl_pre[depth].as<gf>(), *tot = E.lvl_tot[depth].as<gf>(), *inv = E.lvl_inv[depth].as<gf>();
+        k_binv_up<<<cdiv(ng, 128), 128, 0, st>>>(in, n, BINV_G, pre, tot);
+        E.launches++;
+        int rc = batch_inv(tot, inv, ng, depth + 1);
+        if (rc) return rc;
+        k_binv_down<<<cdiv(ng, 128), 128, 0, st>>>(in, n, BINV_G, pre, inv, out);
+        E.launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
+
+    template <bool INDEXED, int B>
+    int round(const AffPt *src, const uint32_t *ent, const uint32_t *in_start, const uint32_t *len,
+              const uint32_t *task_start, const uint32_t *out_start, uint32_t nseg, size_t task_ub, AffPt *dst) {
+        const uint32_t nblk = cdiv(cdiv(task_ub, B), 256);
+        const uint32_t nthr = nblk * 256;
+        k_pass1<INDEXED, B><<<nblk, 256, 0, st>>>(src, ent, in_start, task_start, out_start, nseg,
+                                                  E.info.as<uint32_t>(), E.desc.as<uint4>(), E.prefix.as<gf>(),
+                                                  E.thr_total.as<gf>());
+        E.launches++;
+        int rc = batch_inv(E.thr_total.as<gf>(), E.thr_inv.as<gf>(), nthr, 0);
+        if (rc) return rc;
+        k_pass2<INDEXED, B><<<nblk, 256, 0, st>>>(src, ent, E.info.as<uint32_t>(), E.desc.as<uint4>(),
+                                                  E.prefix.as<gf>(), E.thr_inv.as<gf>(), dst);
+        k_copy_odd<INDEXED><<<cdiv(nseg, 256), 256, 0, st>>>(src, ent, in_start, len, out_start, nseg, dst);
+        E.launches += 2;
+        CK(cudaGetLastError());
+        return 0;
+    }
+
+    template <bool INDEXED>
+    int round_b(int B, const AffPt *src, const uint32_t *ent, const uint32_t *in_start, const uint32_t *len,
+                const uint32_t *task_start, const uint32_t *out_start, uint32_t nseg, size_t task_ub, AffPt *dst) {
+        if (B == 16) return round<INDEXED, 16>(src, ent, in_start, len, task_start, out_start, nseg, task_ub, dst);
+        if (B == 4) return round<INDEXED, 4>(src, ent, in_start, len, task_start, out_start, nseg, task_ub, dst);
+        return round<INDEXED, 1>(src, ent, in_start, len, task_start, out_start, nseg, task_ub, dst);
+    }
+
+    // Reduce every segment of the index list `ent` over `src` to one point: dst[s], s < nseg.
+    // start0 (nseg+1 entries) / len0 (nseg) describe the segments and are only read; they must not be
+    // the engine's own seg_start[] / seg_len[] ping-pong arrays.  total_ub bounds the entry count.
+    // max_len_hint != 0: the longest segment is known, no read-back.
+    int reduce(const AffPt *src, const uint32_t *ent, const uint32_t *start0, const uint32_t *len0, uint32_t nseg,
+               size_t total_ub, uint32_t max_len_hint, AffPt *dst, int *rounds_out) {
+        uint32_t *ts = E.task_start.as<uint32_t>(), *info = E.info.as<uint32_t>();
+        uint32_t *elen[2] = {E.seg_len[0].as<uint32_t>(), E.seg_len[1].as<uint32_t>()};
+        uint32_t *estart[2] = {E.seg_start[0].as<uint32_t>(), E.seg_start[1].as<uint32_t>()};
+        CK(cudaMemsetAsync(info, 0, 16, st));
+        // plan of round 0: caller tables -> engine set 1
+        int rc = scan_plan(len0, nseg, ts, estart[1], elen[1]);
+        if (rc) return rc;
+        uint32_t maxlen = max_len_hint;
+        if (!maxlen) {
+            CK(cudaMemcpyAsync(E.h_info, info, 16, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            maxlen = ((uint32_t *)E.h_info)[0];
+        }
+        int rounds = 0;
+        while ((1ull << rounds) < maxlen) rounds++;
+        if (rounds_out) *rounds_out = rounds;
+        if (rounds == 0) {
+            k_finalize<true><<<cdiv(nseg, 256), 256, 0, st>>>(src, ent, start0, len0, nseg, dst);
+            E.launches++;
+            CK(cudaGetLastError());
+            return 0;
+        }
+        const uint32_t *in_start = start0, *in_len = len0;
+        const AffPt *cur_src = src;
+        for (int r = 0; r < rounds; r++) {
+            const int o = (r + 1) & 1; // engine set written by this round's plan
+            // tasks_r <= total/2^(r+1) + nseg/2
+            const size_t task_ub = (total_ub >> (r + 1)) + nseg / 2 + 1;
+            const int B = task_ub >= (1u << 21) ? 16 : task_ub >= (1u << 17) ? 4 : 1;
+            AffPt *out = E.pp[r & 1].as<AffPt>();
+            if (r == 0) rc = round_b<true>(B, src, ent, in_start, in_len, ts, estart[o], nseg, task_ub, out);
+            else rc = round_b<false>(B, cur_src, nullptr, in_start, in_len, ts, estart[o], nseg, task_ub, out);
+            if (rc) return rc;
+            cur_src = out;
+            in_start = estart[o];
+            in_len = elen[o];
+            if (r + 1 < rounds) {
+                CK(cudaMemsetAsync(info, 0, 16, st));
+                rc = scan_plan(in_len, nseg, ts, estart[o ^ 1], elen[o ^ 1]);
+                if (rc) return rc;
+            }
+        }
+        k_finalize<false><<<cdiv(nseg, 256), 256, 0, st>>>(cur_src, nullptr, in_start, in_len, nseg, dst);
+        E.launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
+};
+
+} // namespace
+
+int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, AffPt *h_result) {
+    *h_result = pt_inf();
+    if (n == 0) return 0;
+    if (n >= (1ull << 31)) return DVP_ERR_BAD_ARG;
+    launches = 0;
+    const int c = force_window_bits ? force_window_bits : choose_window_bits(n);
+    if (c < 4 || c > 20) return DVP_ERR_BAD_ARG;
+    const int W = (233 + c - 1) / c;
+    const uint32_t nb = 1u << (c - 1);
+    const uint32_t nseg = (uint32_t)W * nb;
+    const size_t total = (size_t)W * n;
+    if (total >= (1ull << 32)) return DVP_ERR_BAD_ARG;
+    // bucket matrix of a window: m = 2^lm columns, R = 2^lr rows, nb = R*m
+    const uint32_t lm = (uint32_t)c / 2, lr = (uint32_t)(c - 1) - lm;
+    const uint32_t R = 1u << lr, m = 1u << lm;
+    const uint32_t nseg_a = (uint32_t)W * (R + m), nent_a = (uint32_t)W * 2 * nb;
+    const uint32_t per_b = lm * (m >> 1) + lr * (R >> 1) + m;
+    const uint32_t nseg_b = (uint32_t)W * (uint32_t)c, nent_b = (uint32_t)W * per_b;
+    const size_t nseg_max = std::max<size_t>(nseg, std::max(nseg_a, nseg_b)) + 1;
+    const size_t ent_max = std::max<size_t>(total, std::max(nent_a, nent_b));
+
+    int rc;
+#define RS(buf, bytes) \
+    if ((rc = (buf).reserve(bytes)) != 0) return rc
+    RS(keys, total * 4);
+    RS(entries, total * 4);
+    for (int i = 0; i < 2; i++) {
+        RS(seg_len[i], nseg_max * 4);
+        RS(seg_start[i], nseg_max * 4);
+    }
+    RS(c_len, nseg_max * 4);
+    RS(c_start, nseg_max * 4);
+    RS(task_start, nseg_max * 4);
+    RS(cursor, nseg_max * 4);
+    RS(blk, (nseg_max / SCAN_TILE + 8) * 8);
+    RS(info, 64);
+    const size_t task_ub0 = ent_max / 2 + nseg_max / 2 + 1; // round-0 bound, the largest
+    const size_t out_ub0 = ent_max / 2 + nseg_max + 1;      // outputs of round 0 (ceil halves)
+    RS(pp[0], out_ub0 * sizeof(AffPt));
+    RS(pp[1], (out_ub0 / 2 + nseg_max + 1) * sizeof(AffPt));
+    RS(prefix, task_ub0 * sizeof(gf));
+    RS(desc, task_ub0 * sizeof(uint4));
+    const size_t thr_ub = std::max<size_t>(task_ub0 / 16, 1u << 19) + 1024; // B = 16 / 4 / 1 regimes
+    RS(thr_total, thr_ub * sizeof(gf));
+    RS(thr_inv, thr_ub * sizeof(gf));
+    RS(lvl_pre[0], thr_ub * sizeof(gf));
+    RS(lvl_tot[0], (thr_ub / BINV_G + 2) * sizeof(gf));
+    RS(lvl_inv[0], (thr_ub / BINV_G + 2) * sizeof(gf));
+    RS(lvl_pre[1], (thr_ub / BINV_G + 2) * sizeof(gf));
+    RS(lvl_tot[1], (thr_ub / BINV_G / BINV_G + 2) * sizeof(gf));
+    RS(lvl_inv[1], (thr_ub / BINV_G / BINV_G + 2) * sizeof(gf));
+    RS(buckets, (size_t)nseg * sizeof(AffPt));
+    RS(this->rc, (size_t)nseg_a * sizeof(AffPt));
+    RS(hb, (size_t)nseg_b * sizeof(AffPt));
+    RS(ents2, (size_t)std::max(nent_a, nent_b) * 4);
+#undef RS
+    const size_t hb_bytes = (size_t)nseg_b * sizeof(AffPt);
+    if (h_pts_cap < hb_bytes) {
+        if (h_pts) cudaFreeHost(h_pts);
+        h_pts = nullptr;
+        h_pts_cap = 0;
+        CK(cudaMallocHost(&h_pts, hb_bytes));
+        h_pts_cap = hb_bytes;
+    }
+
+    cudaStream_t st = stream;
+    if (timing) cudaEventRecord(ev[0], st);
+    // ---- recode + histogram, bucket offsets, scatter (a counting sort by bucket)
+    uint32_t *d_len = c_len.as<uint32_t>(), *d_start = c_start.as<uint32_t>();
+    CK(cudaMemsetAsync(d_len, 0, (size_t)nseg * 4, st));
+    k_recode_count<<<cdiv(n, 128), 128, 0, st>>>(d_scalars, (uint32_t)n, c, W, nb, keys.as<uint32_t>(), d_len);
+    {
+        const uint32_t nblk = cdiv(nseg, SCAN_TILE);
+        k_scan1<0><<<nblk, SCAN_THREADS, 0, st>>>(d_len, nseg, blk.as<uint64_t>(), info.as<uint32_t>());
+        k_scan2<<<1, SCAN_THREADS, 0, st>>>(blk.as<uint64_t>(), nblk);
+        k_scan3<0><<<nblk, SCAN_THREADS, 0, st>>>(d_len, nseg, blk.as<uint64_t>(), d_start, cursor.as<uint32_t>(),
+                                                  nullptr, info.as<uint32_t>());
+    }
+    k_scatter<<<cdiv(total, 256), 256, 0, st>>>(keys.as<uint32_t>(), (uint32_t)n, total, cursor.as<uint32_t>(),
+                                                entries.as<uint32_t>());
+    launches += 5;
+    CK(cudaGetLastError());
+    if (timing) cudaEventRecord(ev[1], st);
+
+    Tree tree(*this);
+    MsmStats stt;
+    stt.window_bits = c;
+    stt.windows = W;
+    // ---- bucket accumulation: one segment per (window, bucket)
+    rc = tree.reduce(d_points, entries.as<uint32_t>(), d_start, d_len, nseg, total, 0, buckets.as<AffPt>(),
+                     &stt.rounds_main);
+    if (rc) return rc;
+    if (timing) cudaEventRecord(ev[2], st);
+
+    // ---- level A: row and column sums of each window's bucket matrix
+    k_gen_level_a<<<cdiv(nent_a, 256), 256, 0, st>>>((uint32_t)W, nb, lm, ents2.as<uint32_t>());
+    k_gen_segs_a<<<cdiv(nseg_a + 1, 256), 256, 0, st>>>((uint32_t)W, nb, lm, d_start, d_len);
+    launches += 2;
+    rc = tree.reduce(buckets.as<AffPt>(), ents2.as<uint32_t>(), d_start, d_len, nseg_a, nent_a, std::max(R, m),
+                     this->rc.as<AffPt>(), &stt.rounds_a);
+    if (rc) return rc;
+    // ---- level B: per-bit subset sums of the row / column sums
+    k_gen_level_b<<<cdiv(nent_b, 256), 256, 0, st>>>((uint32_t)W, lr, lm, ents2.as<uint32_t>());
+    k_gen_segs_b<<<cdiv(nseg_b + 1, 256), 256, 0, st>>>((uint32_t)W, lr, lm, d_start, d_len);
+    launches += 2;
+    rc = tree.reduce(this->rc.as<AffPt>(), ents2.as<uint32_t>(), d_start, d_len, nseg_b, nent_b,
+                     std::max(R >> 1, m), hb.as<AffPt>(), &stt.rounds_b);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_pts, hb.as<AffPt>(), hb_bytes, cudaMemcpyDeviceToHost, st));
+    if (timing) cudaEventRecord(ev[3], st);
+    CK(cudaStreamSynchronize(st));
+
+    // ---- host tail: sum_w 2^(c w) [ sum_{q<c-1} 2^q HB[w][q] + HB[w][c-1] ]
+    {
+        const AffPt *hp = (const AffPt *)h_pts;
+        host::LdPt acc = host::ld_inf();
+        for (int pos = W * c - 1; pos >= 0; pos--) {
+            acc = host::ld_dbl(acc);
+            const int w = pos / c, q = pos % c;
+            if (q < c - 1) acc = host::ld_add_affine(acc, hp[w * c + q]);
+            if (q == 0) acc = host::ld_add_affine(acc, hp[w * c + c - 1]);
+        }
+        *h_result = host::ld_to_affine(acc);
+    }
+    stt.launches = launches;
+    if (timing) {
+        cudaEventRecord(ev[4], st);
+        cudaEventSynchronize(ev[4]);
+        cudaEventElapsedTime(&stt.ms_recode_sort, ev[0], ev[1]);
+        cudaEventElapsedTime(&stt.ms_accumulate, ev[1], ev[2]);
+        cudaEventElapsedTime(&stt.ms_reduce, ev[2], ev[3]);
+        cudaEventElapsedTime(&stt.ms_tail, ev[3], ev[4]);
+    }
+    last = stt;
+    return 0;
+}
+
+} // namespace dvp

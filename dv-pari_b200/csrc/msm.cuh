@@ -1,0 +1,48 @@
+// MSM engine interface (device-resident points, Montgomery Fr scalars) -- see msm.cu.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "k233.cuh"
+
+namespace dvp {
+
+// Grow-only device scratch owned by a context.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes); // 0 on success
+    void release();
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct MsmStats {
+    int window_bits = 0, windows = 0, rounds_main = 0, rounds_a = 0, rounds_b = 0;
+    unsigned long long launches = 0; // kernels launched by the last msm
+    float ms_recode_sort = 0, ms_accumulate = 0, ms_reduce = 0, ms_tail = 0;
+};
+
+struct MsmEngine {
+    cudaStream_t stream = nullptr;
+    // scratch
+    DevBuf keys, entries, seg_len[2], seg_start[2], c_len, c_start, task_start, cursor, blk, info, pp[2], prefix, desc,
+        thr_total, thr_inv, lvl_pre[2], lvl_tot[2], lvl_inv[2], buckets, rc, hb, ents2;
+    void *h_info = nullptr; // pinned
+    void *h_pts = nullptr;  // pinned, receives the per-bit partial sums
+    size_t h_pts_cap = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long launches = 0;
+    MsmStats last;
+    int force_window_bits = 0; // 0 = choose from n
+    bool timing = false;
+
+    int init(cudaStream_t s);
+    void destroy();
+    // sum_i scalars[i] * points[i]; scalars are device pointers to n x 8 x u32 Montgomery limbs.
+    // Result: affine E[r] point (or infinity) on the host.  Returns 0 or a DVP_ERR_* code.
+    int run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, AffPt *h_result);
+};
+
+int choose_window_bits(size_t n);
+
+} // namespace dvp

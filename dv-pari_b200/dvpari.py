@@ -1,0 +1,254 @@
+"""Host-side mirror of the reference's prover-facing interface over libdvpari's C ABI.
+
+Names follow /root/reference/src/curve.rs and src/proving.rs (`multi_scalar_mul`, `CurvePoint`,
+`Fr`), so a parity test reads like the reference's own test.  Everything here is plumbing: ctypes
+calls into libdvpari.so (hand-written sm_100a kernels).  There is no CPU fallback -- without the
+built library, or without a CUDA device, construction fails loudly.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdvpari.so")
+
+P = 3450873173395281893717377931138512760570940988862252126328087024741343  # src/curve.rs:17
+R = 1 << 256
+R_INV = pow(R, -1, P)
+
+OK = 0
+ERR_NAMES = {
+    1: "BAD_ARG", 2: "CUDA", 3: "OOM", 4: "INVALID_POINT", 5: "LENGTH_MISMATCH", 6: "UNSATISFIED",
+    7: "ALPHA_IN_DOMAIN", 8: "INTERNAL", 9: "NO_DEVICE", 10: "NCCL",
+}
+
+
+class DvpError(RuntimeError):
+    def __init__(self, code, what=""):
+        self.code = code
+        super().__init__(f"libdvpari: {ERR_NAMES.get(code, code)} {what}".strip())
+
+
+class MsmStats(C.Structure):
+    _fields_ = [("window_bits", C.c_int), ("windows", C.c_int), ("rounds_main", C.c_int), ("rounds_a", C.c_int),
+                ("rounds_b", C.c_int), ("launches", C.c_ulonglong), ("ms_recode_sort", C.c_float),
+                ("ms_accumulate", C.c_float), ("ms_reduce", C.c_float), ("ms_tail", C.c_float)]
+
+
+def build(force=False):
+    """Compile libdvpari.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = []
+    for root, _, files in os.walk(os.path.join(_HERE, "csrc")):
+        srcs += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".hpp"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "dvpari.h"))
+    stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-j4", "libdvpari.so"])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load libdvpari.so.  Raises if it has not been built: the product path has no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        L.dvp_strerror.restype = C.c_char_p
+        vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+        L.dvp_ctx_create.argtypes = [i32, C.POINTER(vp)]
+        L.dvp_ctx_destroy.argtypes = [vp]
+        L.dvp_ctx_destroy.restype = None
+        L.dvp_ctx_set.argtypes = [vp, C.c_char_p, C.c_long]
+        L.dvp_srs_load.argtypes = [vp, i32, vp, sz, C.POINTER(C.c_int64)]
+        L.dvp_srs_append.argtypes = [vp, i32, vp, sz, C.POINTER(C.c_int64)]
+        L.dvp_srs_size.argtypes = [vp, i32, C.POINTER(sz)]
+        L.dvp_srs_free.argtypes = [vp, i32]
+        L.dvp_srs_read.argtypes = [vp, i32, sz, sz, vp]
+        L.dvp_msm.argtypes = [vp, i32, sz, vp, sz, vp]
+        L.dvp_msm_device.argtypes = [vp, i32, sz, vp, sz, vp]
+        L.dvp_msm_adhoc.argtypes = [vp, vp, vp, sz, vp]
+        L.dvp_msm_last_stats.argtypes = [vp, C.POINTER(MsmStats)]
+        L.dvp_point_add.argtypes = [vp, vp, vp, vp]
+        L.dvp_dev_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+        L.dvp_dev_free.argtypes = [vp, vp]
+        L.dvp_dev_upload.argtypes = [vp, vp, vp, sz]
+        L.dvp_dev_download.argtypes = [vp, vp, vp, sz]
+        L.dvp_selftest_op.argtypes = [vp, i32, vp, vp, vp, sz]
+        L.dvp_microbench.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
+        L.dvp_hostcheck_op.argtypes = [i32, vp, vp, vp, sz]
+        _lib = L
+    return _lib
+
+
+def _ck(rc, what=""):
+    if rc != OK:
+        raise DvpError(rc, what)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ------------------------------------------------------------------------------------- Fr helpers
+def fr_to_mont(vals):
+    """canonical ints -> (n,4) uint64 Montgomery limbs: the in-memory layout of the reference's Vec<Fr>."""
+    out = np.zeros((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        m = (int(v) % P) * R % P
+        out[i] = [(m >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(4)]
+    return out
+
+
+def fr_from_mont(arr):
+    arr = np.asarray(arr, dtype=np.uint64).reshape(-1, 4)
+    return [sum(int(row[k]) << (64 * k) for k in range(4)) * R_INV % P for row in arr]
+
+
+class Context:
+    """One CUDA device + resident SRS slots (replaces the per-prove artifact re-reads)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _ck(lib().dvp_ctx_create(device, C.byref(self._h)), "dvp_ctx_create")
+
+    def close(self):
+        if self._h:
+            lib().dvp_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set(self, name, value):
+        _ck(lib().dvp_ctx_set(self._h, name.encode(), int(value)), name)
+
+    # -- SRS slots ---------------------------------------------------------------------------
+    def srs_load(self, slot, pts30, append=False):
+        """pts30: bytes or (n,30) uint8 -- the payload of a point-vector file (io_utils.rs:187-239)."""
+        a = np.frombuffer(pts30, dtype=np.uint8) if isinstance(pts30, (bytes, bytearray)) else np.ascontiguousarray(pts30, dtype=np.uint8)
+        assert a.size % 30 == 0
+        bad = C.c_int64(-1)
+        fn = lib().dvp_srs_append if append else lib().dvp_srs_load
+        rc = fn(self._h, slot, _ptr(a), a.size // 30, C.byref(bad))
+        if rc != OK:
+            raise DvpError(rc, f"point {bad.value}")
+
+    def srs_size(self, slot):
+        n = C.c_size_t()
+        _ck(lib().dvp_srs_size(self._h, slot, C.byref(n)))
+        return n.value
+
+    def srs_read(self, slot, offset, n):
+        out = np.zeros((n, 30), dtype=np.uint8)
+        _ck(lib().dvp_srs_read(self._h, slot, offset, n, _ptr(out)))
+        return out
+
+    def srs_free(self, slot):
+        _ck(lib().dvp_srs_free(self._h, slot))
+
+    # -- multi_scalar_mul (curve.rs:141-158) -------------------------------------------------
+    def multi_scalar_mul(self, scalars_mont, slot, offset=0):
+        """scalars_mont: (n,4) uint64 Montgomery limbs.  Returns the 30-byte CurvePoint::to_bytes of the sum."""
+        s = np.ascontiguousarray(scalars_mont, dtype=np.uint64).reshape(-1, 4)
+        out = np.zeros(30, dtype=np.uint8)
+        _ck(lib().dvp_msm(self._h, slot, offset, _ptr(s), s.shape[0], _ptr(out)), "dvp_msm")
+        return out.tobytes()
+
+    def multi_scalar_mul_device(self, d_scalars, n, slot, offset=0):
+        out = np.zeros(30, dtype=np.uint8)
+        _ck(lib().dvp_msm_device(self._h, slot, offset, d_scalars, n, _ptr(out)), "dvp_msm_device")
+        return out.tobytes()
+
+    def multi_scalar_mul_adhoc(self, scalars_mont, pts30):
+        s = np.ascontiguousarray(scalars_mont, dtype=np.uint64).reshape(-1, 4)
+        a = np.ascontiguousarray(pts30, dtype=np.uint8).reshape(-1, 30)
+        if a.shape[0] != s.shape[0]:
+            raise DvpError(5, "multi_scalar_mul: scalars.len() != points.len()")  # curve.rs:142
+        out = np.zeros(30, dtype=np.uint8)
+        _ck(lib().dvp_msm_adhoc(self._h, _ptr(a), _ptr(s), s.shape[0], _ptr(out)), "dvp_msm_adhoc")
+        return out.tobytes()
+
+    def msm_stats(self):
+        st = MsmStats()
+        _ck(lib().dvp_msm_last_stats(self._h, C.byref(st)))
+        return {f[0]: getattr(st, f[0]) for f in MsmStats._fields_}
+
+    def point_add(self, a30, b30):
+        """CurvePoint::add on encodings (curve.rs:76-82)."""
+        a = np.frombuffer(bytes(a30), dtype=np.uint8).copy()
+        b = np.frombuffer(bytes(b30), dtype=np.uint8).copy()
+        out = np.zeros(30, dtype=np.uint8)
+        _ck(lib().dvp_point_add(self._h, _ptr(a), _ptr(b), _ptr(out)), "dvp_point_add")
+        return out.tobytes()
+
+    # -- device memory -----------------------------------------------------------------------
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        _ck(lib().dvp_dev_alloc(self._h, nbytes, C.byref(p)))
+        return p
+
+    def dev_free(self, p):
+        _ck(lib().dvp_dev_free(self._h, p))
+
+    def dev_upload(self, p, arr):
+        arr = np.ascontiguousarray(arr)
+        _ck(lib().dvp_dev_upload(self._h, p, _ptr(arr), arr.nbytes))
+
+    def dev_download(self, p, arr):
+        _ck(lib().dvp_dev_download(self._h, _ptr(arr), p, arr.nbytes))
+
+    # -- self tests ---------------------------------------------------------------------------
+    def selftest_op(self, op, a, b=None):
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        out = np.zeros_like(a)
+        bb = np.ascontiguousarray(b, dtype=np.uint32) if b is not None else None
+        _ck(lib().dvp_selftest_op(self._h, op, _ptr(a), _ptr(bb), _ptr(out), a.shape[0]))
+        return out
+
+    def microbench(self, op, iters):
+        v = C.c_double()
+        _ck(lib().dvp_microbench(self._h, op, iters, C.byref(v)))
+        return v.value
+
+
+def hostcheck_op(op, a, b=None, out_stride=None):
+    """Same __host__ __device__ source as the kernels, evaluated on the CPU (tests only)."""
+    a = np.ascontiguousarray(a)
+    n = a.shape[0]
+    if out_stride is None:
+        out = np.zeros_like(a)
+    else:
+        out = np.zeros((n, out_stride), dtype=np.uint8)
+    bb = np.ascontiguousarray(b) if b is not None else None
+    _ck(lib().dvp_hostcheck_op(op, _ptr(a), _ptr(bb), _ptr(out), n))
+    return out
+
+
+def random_fr_mont(n, seed):
+    """n uniform Fr elements directly as (n,4) uint64 Montgomery limbs (vectorised rejection sampling).
+
+    A uniform residue's Montgomery form is again uniform in [0,p), so uniform limbs below p are a
+    uniform Vec<Fr>.  Used for synthetic scalars in benchmarks and large tests."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    p_limbs = [(P >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(4)]
+    out = np.zeros((0, 4), dtype=np.uint64)
+    while out.shape[0] < n:
+        raw = rng.integers(0, 1 << 64, size=(n + 1024, 4), dtype=np.uint64)
+        raw[:, 3] &= np.uint64((1 << 40) - 1)
+        # lexicographic raw < p from the top limb down
+        lt = np.zeros(raw.shape[0], dtype=bool)
+        eq = np.ones(raw.shape[0], dtype=bool)
+        for k in (3, 2, 1, 0):
+            lt |= eq & (raw[:, k] < np.uint64(p_limbs[k]))
+            eq &= raw[:, k] == np.uint64(p_limbs[k])
+        out = np.concatenate([out, raw[lt]])
+    return np.ascontiguousarray(out[:n])

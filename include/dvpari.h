@@ -1,0 +1,103 @@
+/*
+ * libdvpari -- C ABI of the B200 (sm_100a) accelerator for DV-Pari's prover hot path.
+ *
+ * Every entry point replaces one Rust call site of the reference (alpenlabs/dv-pari); the
+ * file:line it replaces is cited beside it.  Conventions:
+ *   - Fr values cross the boundary exactly as the reference holds them in memory:
+ *     ark-ff `Fp256<MontBackend<FqConfig,4>>` = 4 x u64 little-endian limbs of v*2^256 mod p,
+ *     fully reduced (src/curve.rs:16-22).  A `Vec<Fr>` can be passed zero-copy.
+ *   - curve points cross as the 30-byte xsk233 encoding (`CompressedCurvePoint`, src/curve.rs:67).
+ *   - the caller owns every host buffer; the library owns device memory behind opaque handles.
+ *   - calls are synchronous, one thread per context; the functions never unwind: they return
+ *     DVP_OK or a DVP_ERR_* code where the reference would panic.
+ *   - there is no CPU fallback: without a CUDA device dvp_ctx_create fails with DVP_ERR_NO_DEVICE.
+ */
+#ifndef DVPARI_H
+#define DVPARI_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    DVP_OK = 0,
+    DVP_ERR_BAD_ARG = 1,
+    DVP_ERR_CUDA = 2,
+    DVP_ERR_OOM = 3,
+    DVP_ERR_INVALID_POINT = 4,   /* a 30-byte encoding did not decode (reference: assert!, io_utils.rs:223) */
+    DVP_ERR_LENGTH_MISMATCH = 5, /* reference: assert_eq!(scalars.len(), points.len()), curve.rs:142 */
+    DVP_ERR_UNSATISFIED = 6,     /* reference: assert_eq!(a*b, c+i), proving.rs:389-395 */
+    DVP_ERR_ALPHA_IN_DOMAIN = 7, /* reference: assert!(!dom.contains(alpha)), proving.rs:548-556 */
+    DVP_ERR_INTERNAL = 8,
+    DVP_ERR_NO_DEVICE = 9,
+    DVP_ERR_NCCL = 10
+};
+
+#define DVP_MAX_SRS_SLOTS 16
+
+typedef struct dvp_ctx dvp_ctx;
+
+typedef struct dvp_msm_stats {
+    int window_bits, windows, rounds_main, rounds_a, rounds_b;
+    unsigned long long launches; /* kernels launched by the last MSM on this context */
+    float ms_recode_sort, ms_accumulate, ms_reduce, ms_tail; /* filled when timing is enabled */
+} dvp_msm_stats;
+
+const char *dvp_strerror(int code);
+int dvp_abi_version(void);
+
+/* One context = one CUDA device + one private stream + grow-only scratch. */
+int dvp_ctx_create(int device, dvp_ctx **out);
+void dvp_ctx_destroy(dvp_ctx *ctx);
+/* knobs: "msm_window_bits" (0 = automatic), "timing" (0/1).  Unknown name -> DVP_ERR_BAD_ARG. */
+int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value);
+
+/*
+ * SRS slots: decode once, keep the affine points resident in HBM.
+ * Replaces the per-prove `read_point_vec_from_file` + decode of g_m / g_q / g_k
+ * (src/proving.rs:462,511,666-673; src/io_utils.rs:187-239).  `pts30` = n x 30 bytes, the payload
+ * of a point-vector file after its u64 count.  On DVP_ERR_INVALID_POINT *first_invalid (if not
+ * NULL) receives the index of the first encoding that failed to decode.
+ */
+int dvp_srs_load(dvp_ctx *ctx, int slot, const uint8_t *pts30, size_t n, int64_t *first_invalid);
+/* Append to a slot (g_k_0 | g_k_1 | g_k_2 concatenation, src/proving.rs:666-673). */
+int dvp_srs_append(dvp_ctx *ctx, int slot, const uint8_t *pts30, size_t n, int64_t *first_invalid);
+int dvp_srs_size(dvp_ctx *ctx, int slot, size_t *n);
+int dvp_srs_free(dvp_ctx *ctx, int slot);
+/* Read points back as 30-byte encodings (CurvePoint::to_bytes, src/curve.rs:93-100). */
+int dvp_srs_read(dvp_ctx *ctx, int slot, size_t offset, size_t n, uint8_t *pts30);
+
+/*
+ * multi_scalar_mul(&[Fr], &[CurvePoint]) -> CurvePoint  (src/curve.rs:141-158).
+ * scalars_mont: n x 4 u64 Montgomery limbs (host).  Points: slot[offset .. offset+n).
+ * out30 = CurvePoint::to_bytes of the sum.  n = 0 gives the neutral (30 zero bytes).
+ */
+int dvp_msm(dvp_ctx *ctx, int slot, size_t offset, const uint64_t *scalars_mont, size_t n, uint8_t out30[30]);
+/* Same with the scalars already in device memory (n x 32 bytes). */
+int dvp_msm_device(dvp_ctx *ctx, int slot, size_t offset, const void *d_scalars_mont, size_t n, uint8_t out30[30]);
+/* One-shot form with encoded points from the host: decode + MSM (src/srs.rs:422). */
+int dvp_msm_adhoc(dvp_ctx *ctx, const uint8_t *pts30, const uint64_t *scalars_mont, size_t n, uint8_t out30[30]);
+int dvp_msm_last_stats(dvp_ctx *ctx, dvp_msm_stats *out);
+
+/* CurvePoint::add on encodings (src/curve.rs:76-82): out = a (+) b.  Runs on the device of ctx. */
+int dvp_point_add(dvp_ctx *ctx, const uint8_t a30[30], const uint8_t b30[30], uint8_t out30[30]);
+
+/* Device-memory helpers so that callers (benchmarks, language bindings) can keep inputs resident. */
+int dvp_dev_alloc(dvp_ctx *ctx, size_t bytes, void **dptr);
+int dvp_dev_free(dvp_ctx *ctx, void *dptr);
+int dvp_dev_upload(dvp_ctx *ctx, void *dptr, const void *host, size_t bytes);
+int dvp_dev_download(dvp_ctx *ctx, void *host, const void *dptr, size_t bytes);
+
+/* Self-test kernels: evaluate the device field/point primitives on caller data (parity tests).
+ * op: 0 gf_mul(a,b)  1 gf_sqr(a)  2 gf_inv(a)  3 fr_mul(a,b)  4 fr_to_canonical(a)  5 affine add (a,b = 64-byte points)
+ * a, b, out: n elements of 32 bytes (64 for op 5), host memory. */
+int dvp_selftest_op(dvp_ctx *ctx, int op, const void *a, const void *b, void *out, size_t n);
+/* Integer-pipe microbenchmark: op 0 gf_mul chain, 1 gf_sqr chain, 2 fr_mul chain; returns ops per second. */
+int dvp_microbench(dvp_ctx *ctx, int op, int iters, double *ops_per_sec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

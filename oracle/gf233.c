@@ -18,7 +18,8 @@ int gf_is_zero(const gf_t *a) { return (a->w[0] | a->w[1] | a->w[2] | a->w[3]) =
 int gf_eq(const gf_t *a, const gf_t *b) { return memcmp(a->w, b->w, 32) == 0; }
 
 /* c[0..7] (466 significant bits) -> reduced mod x^233 + x^74 + 1 */
-static void gf_reduce(gf_t *r, uint64_t c[8]) {
+static inline __attribute__((always_inline)) void gf_reduce(gf_t *r, uint64_t c[8]) {
+#pragma GCC unroll 4
     for (int i = 7; i >= 4; i--) {
         uint64_t t = c[i];
         /* x^(64i+k) = x^(64(i-4)+23+k) + x^(64(i-3)+33+k) */
@@ -31,7 +32,7 @@ static void gf_reduce(gf_t *r, uint64_t c[8]) {
     c[0] ^= t;
     c[1] ^= t << 10;
     c[3] &= (1ULL << 41) - 1;
-    memcpy(r->w, c, 32);
+    r->w[0] = c[0]; r->w[1] = c[1]; r->w[2] = c[2]; r->w[3] = c[3];
 }
 
 static void clmul64_portable(uint64_t *lo, uint64_t *hi, uint64_t a, uint64_t b) {
@@ -59,16 +60,28 @@ static void mul_portable(uint64_t c[8], const gf_t *a, const gf_t *b) {
 
 #if defined(__PCLMUL__)
 static void mul_pclmul(uint64_t c[8], const gf_t *a, const gf_t *b) {
-    memset(c, 0, 64);
-    for (int i = 0; i < 4; i++) {
-        __m128i ai = _mm_cvtsi64_si128((long long)a->w[i]);
-        for (int j = 0; j < 4; j++) {
-            __m128i bj = _mm_cvtsi64_si128((long long)b->w[j]);
-            __m128i p = _mm_clmulepi64_si128(ai, bj, 0x00);
-            c[i + j] ^= (uint64_t)_mm_cvtsi128_si64(p);
-            c[i + j + 1] ^= (uint64_t)_mm_extract_epi64(p, 1);
-        }
-    }
+    /* 16 products accumulated in seven 128-bit columns (column k sits at bit offset 64 k) */
+    __m128i a01 = _mm_loadu_si128((const __m128i *)&a->w[0]), a23 = _mm_loadu_si128((const __m128i *)&a->w[2]);
+    __m128i b01 = _mm_loadu_si128((const __m128i *)&b->w[0]), b23 = _mm_loadu_si128((const __m128i *)&b->w[2]);
+    __m128i k0 = _mm_clmulepi64_si128(a01, b01, 0x00);
+    __m128i k1 = _mm_xor_si128(_mm_clmulepi64_si128(a01, b01, 0x10), _mm_clmulepi64_si128(a01, b01, 0x01));
+    __m128i k2 = _mm_xor_si128(_mm_clmulepi64_si128(a01, b01, 0x11),
+                               _mm_xor_si128(_mm_clmulepi64_si128(a01, b23, 0x00), _mm_clmulepi64_si128(a23, b01, 0x00)));
+    __m128i k3 = _mm_xor_si128(_mm_xor_si128(_mm_clmulepi64_si128(a01, b23, 0x10), _mm_clmulepi64_si128(a01, b23, 0x01)),
+                               _mm_xor_si128(_mm_clmulepi64_si128(a23, b01, 0x10), _mm_clmulepi64_si128(a23, b01, 0x01)));
+    __m128i k4 = _mm_xor_si128(_mm_clmulepi64_si128(a23, b23, 0x00),
+                               _mm_xor_si128(_mm_clmulepi64_si128(a01, b23, 0x11), _mm_clmulepi64_si128(a23, b01, 0x11)));
+    __m128i k5 = _mm_xor_si128(_mm_clmulepi64_si128(a23, b23, 0x10), _mm_clmulepi64_si128(a23, b23, 0x01));
+    __m128i k6 = _mm_clmulepi64_si128(a23, b23, 0x11);
+    /* fold odd columns into the even ones */
+    k0 = _mm_xor_si128(k0, _mm_slli_si128(k1, 8));
+    k2 = _mm_xor_si128(k2, _mm_xor_si128(_mm_srli_si128(k1, 8), _mm_slli_si128(k3, 8)));
+    k4 = _mm_xor_si128(k4, _mm_xor_si128(_mm_srli_si128(k3, 8), _mm_slli_si128(k5, 8)));
+    k6 = _mm_xor_si128(k6, _mm_srli_si128(k5, 8));
+    c[0] = (uint64_t)_mm_cvtsi128_si64(k0); c[1] = (uint64_t)_mm_extract_epi64(k0, 1);
+    c[2] = (uint64_t)_mm_cvtsi128_si64(k2); c[3] = (uint64_t)_mm_extract_epi64(k2, 1);
+    c[4] = (uint64_t)_mm_cvtsi128_si64(k4); c[5] = (uint64_t)_mm_extract_epi64(k4, 1);
+    c[6] = (uint64_t)_mm_cvtsi128_si64(k6); c[7] = (uint64_t)_mm_extract_epi64(k6, 1);
 }
 #endif
 
@@ -93,6 +106,19 @@ static uint64_t spread32(uint32_t v) {
 }
 void gf_sqr(gf_t *r, const gf_t *a) {
     uint64_t c[8];
+#if defined(__PCLMUL__)
+    if (!g_portable) {
+        __m128i a01 = _mm_loadu_si128((const __m128i *)&a->w[0]), a23 = _mm_loadu_si128((const __m128i *)&a->w[2]);
+        __m128i k0 = _mm_clmulepi64_si128(a01, a01, 0x00), k2 = _mm_clmulepi64_si128(a01, a01, 0x11);
+        __m128i k4 = _mm_clmulepi64_si128(a23, a23, 0x00), k6 = _mm_clmulepi64_si128(a23, a23, 0x11);
+        c[0] = (uint64_t)_mm_cvtsi128_si64(k0); c[1] = (uint64_t)_mm_extract_epi64(k0, 1);
+        c[2] = (uint64_t)_mm_cvtsi128_si64(k2); c[3] = (uint64_t)_mm_extract_epi64(k2, 1);
+        c[4] = (uint64_t)_mm_cvtsi128_si64(k4); c[5] = (uint64_t)_mm_extract_epi64(k4, 1);
+        c[6] = (uint64_t)_mm_cvtsi128_si64(k6); c[7] = (uint64_t)_mm_extract_epi64(k6, 1);
+        gf_reduce(r, c);
+        return;
+    }
+#endif
     for (int i = 0; i < 4; i++) {
         c[2 * i] = spread32((uint32_t)a->w[i]);
         c[2 * i + 1] = spread32((uint32_t)(a->w[i] >> 32));

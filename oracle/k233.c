@@ -295,3 +295,58 @@ void k233_msm(k233_pt *r, const fr_t *scalars, const k233_pt *points, size_t n, 
     *r = acc;
     free(part);
 }
+
+/* ---- bulk helpers for fixtures and benchmarks (OpenMP) ---- */
+/* out[i] = P0 + i * Q, i < n  (cheap synthetic SRS: one affine addition per point) */
+void k233_chain_points(k233_pt *out, size_t n, const k233_pt *p0, const k233_pt *q) {
+    int nt = 1;
+#ifdef _OPENMP
+    nt = omp_get_max_threads();
+#endif
+    size_t chunk = (n + (size_t)nt - 1) / (size_t)nt;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1)
+#endif
+    for (int t = 0; t < nt; t++) {
+        size_t lo = (size_t)t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+        if (lo >= hi) continue;
+        uint8_t kb[8];
+        for (int i = 0; i < 8; i++) kb[i] = (uint8_t)((uint64_t)lo >> (8 * i));
+        k233_pt cur;
+        k233_mul_bytes(&cur, q, kb, 8);
+        k233_add(&cur, &cur, p0);
+        for (size_t i = lo; i < hi; i++) {
+            out[i] = cur;
+            k233_add(&cur, &cur, q);
+        }
+    }
+}
+/* out[i] = k_i * P (k_i Montgomery Fr): point_scalar_mul(_gen) in bulk (curve.rs:113-137, srs.rs:126-160) */
+void k233_mul_batch(k233_pt *out, const k233_pt *p, const fr_t *k, size_t n) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
+    for (long i = 0; i < (long)n; i++) k233_mul_fr(&out[i], p, &k[i]);
+}
+void xsk233_encode_batch(uint8_t *out30, const k233_pt *pts, size_t n) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (long i = 0; i < (long)n; i++) xsk233_encode(out30 + 30 * (size_t)i, &pts[i]);
+}
+/* returns the index of the first invalid encoding, or -1 */
+long xsk233_decode_batch(k233_pt *pts, const uint8_t *in30, size_t n) {
+    long bad = -1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (long i = 0; i < (long)n; i++) {
+        if (!xsk233_decode(&pts[i], in30 + 30 * (size_t)i)) {
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+            if (bad < 0 || i < bad) bad = i;
+        }
+    }
+    return bad;
+}

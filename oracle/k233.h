@@ -50,6 +50,12 @@ int  xsk233_decode(k233_pt *p, const uint8_t in[30]); /* non-zero on success (cu
 /* multi_scalar_mul (curve.rs:141-158): per-point scalar mul, then sum. nthreads<=0: all cores */
 void k233_msm(k233_pt *r, const fr_t *scalars, const k233_pt *points, size_t n, int nthreads);
 
+/* bulk helpers for fixtures and benchmarks (OpenMP over all cores) */
+void k233_chain_points(k233_pt *out, size_t n, const k233_pt *p0, const k233_pt *q); /* out[i] = p0 + i q */
+void k233_mul_batch(k233_pt *out, const k233_pt *p, const fr_t *k, size_t n);         /* out[i] = k_i p */
+void xsk233_encode_batch(uint8_t *out30, const k233_pt *pts, size_t n);
+long xsk233_decode_batch(k233_pt *pts, const uint8_t *in30, size_t n); /* first invalid index or -1 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -199,3 +199,51 @@ def msm(scalars_mont, pts_arr, nthreads=0):
     r = Pt()
     lib().k233_msm(C.byref(r), sc.ctypes.data_as(C.c_void_p), C.cast(pts_arr, C.c_void_p), n, nthreads)
     return r
+
+
+# ---------------------------------------------------------------- bulk fixtures
+def chain_points(n, p0, q):
+    """ctypes Pt array with out[i] = p0 + i*q"""
+    arr = (Pt * n)()
+    lib().k233_chain_points(arr, C.c_size_t(n), C.byref(p0), C.byref(q))
+    return arr
+
+
+def mul_batch(p, scalars_mont):
+    """out[i] = k_i * p for (n,4) uint64 Montgomery scalars"""
+    sc = np.ascontiguousarray(scalars_mont, dtype=np.uint64)
+    n = sc.shape[0]
+    arr = (Pt * n)()
+    lib().k233_mul_batch(arr, C.byref(p), sc.ctypes.data_as(C.c_void_p), C.c_size_t(n))
+    return arr
+
+
+def encode_batch(pts_arr):
+    n = len(pts_arr)
+    out = np.zeros((n, 30), dtype=np.uint8)
+    lib().xsk233_encode_batch(out.ctypes.data_as(C.c_void_p), pts_arr, C.c_size_t(n))
+    return out
+
+
+def decode_batch(enc):
+    enc = np.ascontiguousarray(enc, dtype=np.uint8).reshape(-1, 30)
+    arr = (Pt * enc.shape[0])()
+    lib().xsk233_decode_batch.restype = C.c_long
+    bad = lib().xsk233_decode_batch(arr, enc.ctypes.data_as(C.c_void_p), C.c_size_t(enc.shape[0]))
+    return arr, bad
+
+
+def random_fr_mont(n, seed):
+    """n uniform Fr elements as (n,4) uint64 Montgomery limbs, from numpy's PCG64 with rejection"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    vals = []
+    while len(vals) < n:
+        raw = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+        raw[:, 3] &= np.uint64((1 << 40) - 1)  # 232 bits
+        for row in raw:
+            v = limbs_to_int(row)
+            if v < P:
+                vals.append(v)
+                if len(vals) == n:
+                    break
+    return vals, mont_array(vals)

@@ -1,0 +1,138 @@
+"""multi_scalar_mul parity (curve.rs:141-158): the CUDA path through the C ABI against the oracle.
+
+Cases follow the reference's tests (curve.rs:198-232) plus the degenerate inputs of SURVEY section 8d:
+all points = G, zero / one / p-1 scalars, duplicate and negated points, neutral points, ragged sizes."""
+import random
+
+import numpy as np
+import pytest
+
+import dvpari
+
+pytestmark = pytest.mark.gpu
+P = dvpari.P
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = dvpari.Context(0)
+    yield c
+    c.close()
+
+
+def _oracle_msm(O, vals, pts_arr):
+    return O.pt_encode(O.msm(O.mont_array(vals), pts_arr, 0))
+
+
+def test_msm_matches_oracle_random(ctx, oracle):
+    O = oracle
+    G = O.generator()
+    for n, seed in [(1, 1), (2, 2), (3, 3), (33, 4), (1000, 5), (4099, 6)]:
+        rnd = random.Random(seed)
+        ks = [rnd.randrange(P) for _ in range(n)]
+        pts = O.mul_batch(G, O.mont_array([rnd.randrange(1, P) for _ in range(n)]))
+        ctx.srs_load(0, O.encode_batch(pts))
+        got = ctx.multi_scalar_mul(dvpari.fr_to_mont(ks), 0)
+        assert got == _oracle_msm(O, ks, pts), n
+
+
+def test_msm_all_points_generator(ctx, oracle):
+    """curve.rs:218-232 (n = 10_000, every point = G): msm == (sum k) * G"""
+    O = oracle
+    rnd = random.Random(7)
+    n = 10_000
+    ks = [rnd.randrange(P) for _ in range(n)]
+    enc = np.tile(np.frombuffer(O.pt_encode(O.generator()), dtype=np.uint8), (n, 1))
+    ctx.srs_load(0, enc)
+    got = ctx.multi_scalar_mul(dvpari.fr_to_mont(ks), 0)
+    assert got == O.pt_encode(O.pt_mul(O.generator(), sum(ks) % P))
+
+
+def test_msm_degenerate_scalars_and_points(ctx, oracle):
+    O = oracle
+    rnd = random.Random(8)
+    G = O.generator()
+    base = [O.pt_mul(G, rnd.randrange(1, P)) for _ in range(64)]
+    pts = base + base + [O.pt_neg(p) for p in base] + [O.pt()] * 16  # duplicates, negations, neutral points
+    n = len(pts)
+    arr = O.points_to_array(pts)
+    enc = O.encode_batch(arr)
+    ctx.srs_load(1, enc)
+    cases = {
+        "zeros": [0] * n,
+        "ones": [1] * n,
+        "p-1": [P - 1] * n,
+        "same": [rnd.randrange(P)] * n,
+        "small": [rnd.randrange(4) for _ in range(n)],
+        "mixed": [rnd.choice([0, 1, P - 1, rnd.randrange(P), 1 << 231, (1 << 16) - 1, 1 << 15]) for _ in range(n)],
+    }
+    for name, ks in cases.items():
+        got = ctx.multi_scalar_mul(dvpari.fr_to_mont(ks), 1)
+        assert got == _oracle_msm(O, ks, arr), name
+    # cancelling pairs: k*P + k*(-P) = neutral = 30 zero bytes
+    ks = [5] * 64 + [0] * 64 + [5] * 64 + [9] * 16
+    assert ctx.multi_scalar_mul(dvpari.fr_to_mont(ks), 1) == bytes(30)
+
+
+def test_msm_every_window_size(ctx, oracle):
+    O = oracle
+    rnd = random.Random(9)
+    G = O.generator()
+    n = 700
+    ks = [rnd.randrange(P) for _ in range(n)]
+    pts = O.mul_batch(G, O.mont_array([rnd.randrange(1, P) for _ in range(n)]))
+    ctx.srs_load(0, O.encode_batch(pts))
+    want = _oracle_msm(O, ks, pts)
+    for c in (4, 5, 7, 8, 10, 13, 16):
+        ctx.set("msm_window_bits", c)
+        assert ctx.multi_scalar_mul(dvpari.fr_to_mont(ks), 0) == want, c
+    ctx.set("msm_window_bits", 0)
+
+
+def test_msm_offset_empty_and_length_errors(ctx, oracle):
+    O = oracle
+    rnd = random.Random(10)
+    G = O.generator()
+    n = 300
+    ks = [rnd.randrange(P) for _ in range(n)]
+    pts = O.mul_batch(G, O.mont_array([rnd.randrange(1, P) for _ in range(n)]))
+    enc = O.encode_batch(pts)
+    ctx.srs_load(2, enc[:100])
+    ctx.srs_load(2, enc[100:], append=True)  # g_k_0 | g_k_1 | g_k_2 style concatenation
+    got = ctx.multi_scalar_mul(dvpari.fr_to_mont(ks[50:250]), 2, offset=50)
+    assert got == O.pt_encode(O.msm(O.mont_array(ks[50:250]), O.points_to_array([pts[i] for i in range(50, 250)]), 0))
+    assert ctx.multi_scalar_mul(np.zeros((0, 4), dtype=np.uint64), 2) == bytes(30)
+    with pytest.raises(dvpari.DvpError) as e:  # curve.rs:142 assert_eq!(scalars.len(), points.len())
+        ctx.multi_scalar_mul(dvpari.fr_to_mont([1] * 301), 2)
+    assert e.value.code == 5
+    # ad-hoc form (srs.rs:422: a 2-term msm with a fresh point)
+    got = ctx.multi_scalar_mul_adhoc(dvpari.fr_to_mont(ks[:2]), enc[:2])
+    assert got == O.pt_encode(O.msm(O.mont_array(ks[:2]), O.points_to_array([pts[0], pts[1]]), 0))
+
+
+def test_msm_2_16_config(ctx, oracle):
+    """BASELINE config: sect233k1 MSM 2^16 points, random scalars, true random subgroup points."""
+    O = oracle
+    n = 1 << 16
+    sc = dvpari.random_fr_mont(n, 0xD5A10001)
+    pts = O.mul_batch(O.generator(), dvpari.random_fr_mont(n, 0xD5A10002))
+    ctx.srs_load(0, O.encode_batch(pts))
+    got = ctx.multi_scalar_mul(sc, 0)
+    assert got == O.pt_encode(O.msm(sc, pts, 0))
+
+
+def test_msm_2_20_closed_form(ctx, oracle):
+    """Full-size property: for points P_i = A + i*Q the sum is (sum k_i) A + (sum i k_i) Q."""
+    O = oracle
+    n = 1 << 20
+    G = O.generator()
+    a, q = O.pt_mul(G, 0x1234567), O.pt_mul(G, 0x7654321)
+    pts = O.chain_points(n, a, q)
+    ctx.srs_load(0, O.encode_batch(pts))
+    sc = dvpari.random_fr_mont(n, 0xD5A10007)
+    ks = dvpari.fr_from_mont(sc)
+    s0 = sum(ks) % P
+    s1 = sum(i * k for i, k in enumerate(ks)) % P
+    want = O.pt_encode(O.pt_add(O.pt_mul(a, s0), O.pt_mul(q, s1)))
+    assert ctx.multi_scalar_mul(sc, 0) == want
+    ctx.srs_free(0)

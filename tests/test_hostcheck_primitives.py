@@ -1,0 +1,115 @@
+"""The kernels' own __host__ __device__ source (gf233.cuh, fr.cuh, k233*.cuh, host_gf.hpp), evaluated on
+the CPU through dvp_hostcheck_op and compared with the oracle.  No GPU needed; the GPU runs of the
+same source are in test_gpu_primitives.py."""
+import random
+
+import numpy as np
+
+import dvpari
+
+P = dvpari.P
+
+
+def gf_arr(vals):
+    return np.array([[(v >> (32 * k)) & 0xFFFFFFFF for k in range(8)] for v in vals], dtype=np.uint32)
+
+
+def gf_ints(arr):
+    return [sum(int(r[k]) << (32 * k) for k in range(8)) for r in arr]
+
+
+def pt_arr(O, pts):
+    out = np.zeros((len(pts), 16), dtype=np.uint32)
+    for i, p in enumerate(pts):
+        xy = O.pt_xy(p)
+        if xy is not None:
+            out[i, :8] = gf_arr([xy[0]])[0]
+            out[i, 8:] = gf_arr([xy[1]])[0]
+    return out
+
+
+def pt_from_row(O, row):
+    x, y = gf_ints([row[:8]])[0], gf_ints([row[8:]])[0]
+    return O.pt() if x == 0 else O.pt(x, y)
+
+
+def test_gf_mul_sqr_inv(oracle):
+    rnd = random.Random(11)
+    edge = [0, 1, (1 << 233) - 1, 1 << 232, 0x1111111111111111111111111111111111111111111111111111111111, (1 << 233) - 2]
+    a = edge + [rnd.getrandbits(233) for _ in range(300)]
+    b = a[1:] + a[:1]
+    A, B = gf_arr(a), gf_arr(b)
+    for op in (0, 6):  # device multiplier, PCLMUL host-tail multiplier
+        got = gf_ints(dvpari.hostcheck_op(op, A, B))
+        assert got == [oracle.gf_mul(x, y) for x, y in zip(a, b)]
+    assert gf_ints(dvpari.hostcheck_op(1, A)) == [oracle.gf_sqr(x) for x in a]
+    for op in (2, 7):
+        assert gf_ints(dvpari.hostcheck_op(op, A[:60])) == [oracle.gf_inv(x) for x in a[:60]]
+
+
+def test_fr_ops(oracle):
+    rnd = random.Random(12)
+    edge = [0, 1, P - 1, P - 2, 1 << 231, (1 << 231) - 1, 2]
+    a = edge + [rnd.randrange(P) for _ in range(300)]
+    b = a[3:] + a[:3]
+    A = dvpari.fr_to_mont(a).view(np.uint32).reshape(-1, 8)
+    B = dvpari.fr_to_mont(b).view(np.uint32).reshape(-1, 8)
+    mul = dvpari.hostcheck_op(3, A, B).view(np.uint64).reshape(-1, 4)
+    assert dvpari.fr_from_mont(mul) == [x * y % P for x, y in zip(a, b)]
+    can = dvpari.hostcheck_op(4, A)
+    assert gf_ints(can) == a
+    add = dvpari.hostcheck_op(12, A, B).view(np.uint64).reshape(-1, 4)
+    assert dvpari.fr_from_mont(add) == [(x + y) % P for x, y in zip(a, b)]
+    sub = dvpari.hostcheck_op(13, A, B).view(np.uint64).reshape(-1, 4)
+    assert dvpari.fr_from_mont(sub) == [(x - y) % P for x, y in zip(a, b)]
+    inv = dvpari.hostcheck_op(14, A[:40], B[:40]).view(np.uint64).reshape(-1, 4)
+    assert dvpari.fr_from_mont(inv) == [pow(x, -1, P) if x else 0 for x in a[:40]]
+    # the bytes are exactly ark's Montgomery limbs, fully reduced
+    for row in mul:
+        assert sum(int(row[k]) << (64 * k) for k in range(4)) < P
+
+
+def test_point_add_complete(oracle):
+    O = oracle
+    rnd = random.Random(13)
+    G = O.generator()
+    pts = [O.pt_mul(G, rnd.randrange(1, P)) for _ in range(12)]
+    inf = O.pt()
+    lhs = pts + [pts[0], pts[1], inf, pts[2], inf]
+    rhs = pts[1:] + pts[:1] + [pts[0], O.pt_neg(pts[1]), pts[3], inf, inf]  # generic, double, negation, infinities
+    got = dvpari.hostcheck_op(5, pt_arr(O, lhs), pt_arr(O, rhs))
+    for row, p, q in zip(got, lhs, rhs):
+        assert O.pt_xy(pt_from_row(O, row)) == O.pt_xy(O.pt_add(p, q))
+    # host LD accumulator used by the MSM tail: 2a + b
+    got = dvpari.hostcheck_op(11, pt_arr(O, lhs), pt_arr(O, rhs))
+    for row, p, q in zip(got, lhs, rhs):
+        assert O.pt_xy(pt_from_row(O, row)) == O.pt_xy(O.pt_add(O.pt_add(p, p), q))
+
+
+def test_codec_matches_oracle(oracle):
+    O = oracle
+    rnd = random.Random(14)
+    G = O.generator()
+    pts = [O.pt_mul(G, rnd.randrange(1, P)) for _ in range(10)] + [O.pt(), G]
+    enc = np.frombuffer(b"".join(O.pt_encode(p) for p in pts), dtype=np.uint8).reshape(-1, 30)
+    for op in (9, 10):
+        got = dvpari.hostcheck_op(op, pt_arr(O, pts), out_stride=30)
+        assert got.tobytes() == enc.tobytes()
+    dec = dvpari.hostcheck_op(8, enc, out_stride=65)
+    for row, p in zip(dec, pts):
+        assert row[64] == 1
+        assert O.pt_xy(pt_from_row(O, row[:64].copy().view(np.uint32))) == O.pt_xy(p)
+    # random byte strings: validity and value agree with the oracle
+    raw = np.array([list(rnd.getrandbits(233).to_bytes(30, "little")) for _ in range(60)], dtype=np.uint8)
+    raw[0, 29] = 0x02  # bit 233 set
+    raw[1] = 0
+    raw[1, 0] = 1  # w = 1
+    dec = dvpari.hostcheck_op(8, raw, out_stride=65)
+    nvalid = 0
+    for row, b in zip(dec, raw):
+        q, ok = O.pt_decode(b.tobytes())
+        assert bool(row[64]) == ok
+        if ok:
+            nvalid += 1
+            assert O.pt_xy(pt_from_row(O, row[:64].copy().view(np.uint32))) == O.pt_xy(q)
+    assert 0 < nvalid < 40
