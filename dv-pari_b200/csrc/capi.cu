@@ -95,10 +95,13 @@ __global__ void k_selftest(int op, const uint32_t *__restrict__ a, const uint32_
     }
 }
 
-// dependent chains of the field primitives, 2 independent chains per thread
-__global__ void __launch_bounds__(256) k_microbench(int op, int iters, uint32_t *__restrict__ sink) {
+// dependent chains of the field primitives, 2 independent chains per thread.
+// MINB = minimum resident blocks per SM (caps the register budget: 1 -> 255, 2 -> 128, 3 -> 80).
+template <int OP, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_microbench(int iters, uint32_t *__restrict__ sink) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (op < 2) {
+    uint32_t s = 0;
+    if (OP < 2) {
         gf a, b;
         for (int k = 0; k < 8; k++) {
             a.v[k] = t * 2654435761u + k * 40503u + 1;
@@ -106,8 +109,9 @@ __global__ void __launch_bounds__(256) k_microbench(int op, int iters, uint32_t 
         }
         a.v[7] &= 0x1ff;
         b.v[7] &= 0x1ff;
+#pragma unroll 1
         for (int i = 0; i < iters; i++) {
-            if (op == 0) {
+            if (OP == 0) {
                 a = gf_mul(a, b);
                 b = gf_mul(b, a);
             } else {
@@ -115,9 +119,7 @@ __global__ void __launch_bounds__(256) k_microbench(int op, int iters, uint32_t 
                 b = gf_sqr(b);
             }
         }
-        uint32_t s = 0;
         for (int k = 0; k < 8; k++) s ^= a.v[k] ^ b.v[k];
-        if (s == 0x12345678u) sink[0] = s;
     } else {
         fr a, b;
         for (int k = 0; k < 8; k++) {
@@ -126,14 +128,20 @@ __global__ void __launch_bounds__(256) k_microbench(int op, int iters, uint32_t 
         }
         a.v[7] &= 0x7f;
         b.v[7] &= 0x7f;
+#pragma unroll 1
         for (int i = 0; i < iters; i++) {
             a = fr_mul(a, b);
             b = fr_mul(b, a);
         }
-        uint32_t s = 0;
         for (int k = 0; k < 8; k++) s ^= a.v[k] ^ b.v[k];
-        if (s == 0x12345678u) sink[0] = s;
     }
+    if (s == 0x12345678u) sink[0] = s;
+}
+
+template <int MINB> static void launch_microbench(int op, int blocks, cudaStream_t st, int iters, uint32_t *sink) {
+    if (op == 0) k_microbench<0, MINB><<<blocks, 256, 0, st>>>(iters, sink);
+    else if (op == 1) k_microbench<1, MINB><<<blocks, 256, 0, st>>>(iters, sink);
+    else k_microbench<2, MINB><<<blocks, 256, 0, st>>>(iters, sink);
 }
 
 // ---------------------------------------------------------------------------------------- context
@@ -216,6 +224,11 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
     if (!strcmp(name, "msm_window_bits")) {
         if (value != 0 && (value < 4 || value > 20)) return DVP_ERR_BAD_ARG;
         ctx->msm.force_window_bits = (int)value;
+        return DVP_OK;
+    }
+    if (!strcmp(name, "pass2_minb")) {
+        if (value < 1 || value > 3) return DVP_ERR_BAD_ARG;
+        ctx->msm.pass2_minb = (int)value;
         return DVP_OK;
     }
     if (!strcmp(name, "timing")) {
@@ -404,26 +417,33 @@ int dvp_selftest_op(dvp_ctx *ctx, int op, const void *a, const void *b, void *ou
 }
 
 int dvp_microbench(dvp_ctx *ctx, int op, int iters, double *ops_per_sec) {
-    if (!ctx || !ops_per_sec || op < 0 || op > 2 || iters <= 0) return DVP_ERR_BAD_ARG;
+    // op = primitive (0 gf_mul, 1 gf_sqr, 2 fr_mul) + 10 * (resident blocks per SM - 1)
+    if (!ctx || !ops_per_sec || op < 0 || op % 10 > 2 || op / 10 > 2 || iters <= 0) return DVP_ERR_BAD_ARG;
     CKC(cudaSetDevice(ctx->device));
     int rc;
     if ((rc = ctx->small.reserve(128)) != 0) return rc;
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, ctx->device));
-    const int blocks = prop.multiProcessorCount * 4, threads = 256;
+    const int minb = op / 10 + 1, prim = op % 10;
+    const int blocks = prop.multiProcessorCount * minb * 2;
     cudaEvent_t e0, e1;
     CKC(cudaEventCreate(&e0));
     CKC(cudaEventCreate(&e1));
-    k_microbench<<<blocks, threads, 0, ctx->stream>>>(op, 4, (uint32_t *)ctx->small.p); // warm-up
-    CKC(cudaEventRecord(e0, ctx->stream));
-    k_microbench<<<blocks, threads, 0, ctx->stream>>>(op, iters, (uint32_t *)ctx->small.p);
+    uint32_t *sink = (uint32_t *)ctx->small.p;
+    for (int rep = 0; rep < 2; rep++) {
+        const int it = rep ? iters : 4;
+        if (rep) CKC(cudaEventRecord(e0, ctx->stream));
+        if (minb == 1) launch_microbench<1>(prim, blocks, ctx->stream, it, sink);
+        else if (minb == 2) launch_microbench<2>(prim, blocks, ctx->stream, it, sink);
+        else launch_microbench<3>(prim, blocks, ctx->stream, it, sink);
+    }
     CKC(cudaEventRecord(e1, ctx->stream));
     CKC(cudaEventSynchronize(e1));
     float ms = 0;
     CKC(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    *ops_per_sec = (double)blocks * threads * 2.0 * iters / (ms * 1e-3);
+    *ops_per_sec = (double)blocks * 256 * 2.0 * iters / (ms * 1e-3);
     return DVP_OK;
 }
 

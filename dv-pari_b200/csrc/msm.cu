@@ -330,8 +330,8 @@ __global__ void __launch_bounds__(256)
 }
 
 // pass 2: walk the same tasks backwards with the inverse of the thread total, finish the additions
-template <bool INDEXED, int B>
-__global__ void __launch_bounds__(256)
+template <bool INDEXED, int B, int MINB>
+__global__ void __launch_bounds__(256, MINB)
     k_pass2(const AffPt *__restrict__ src, const uint32_t *__restrict__ ent, const uint32_t *__restrict__ info,
             const uint4 *__restrict__ desc, const gf *__restrict__ prefix, const gf *__restrict__ thr_inv,
             AffPt *__restrict__ dst) {
@@ -575,8 +575,15 @@ struct Tree {
         E.launches++;
         int rc = batch_inv(E.thr_total.as<gf>(), E.thr_inv.as<gf>(), nthr, 0);
         if (rc) return rc;
-        k_pass2<INDEXED, B><<<nblk, 256, 0, st>>>(src, ent, E.info.as<uint32_t>(), E.desc.as<uint4>(),
-                                                  E.prefix.as<gf>(), E.thr_inv.as<gf>(), dst);
+        if (E.pass2_minb == 2)
+            k_pass2<INDEXED, B, 2><<<nblk, 256, 0, st>>>(src, ent, E.info.as<uint32_t>(), E.desc.as<uint4>(),
+                                                         E.prefix.as<gf>(), E.thr_inv.as<gf>(), dst);
+        else if (E.pass2_minb == 3)
+            k_pass2<INDEXED, B, 3><<<nblk, 256, 0, st>>>(src, ent, E.info.as<uint32_t>(), E.desc.as<uint4>(),
+                                                         E.prefix.as<gf>(), E.thr_inv.as<gf>(), dst);
+        else
+            k_pass2<INDEXED, B, 1><<<nblk, 256, 0, st>>>(src, ent, E.info.as<uint32_t>(), E.desc.as<uint4>(),
+                                                         E.prefix.as<gf>(), E.thr_inv.as<gf>(), dst);
         k_copy_odd<INDEXED><<<cdiv(nseg, 256), 256, 0, st>>>(src, ent, in_start, len, out_start, nseg, dst);
         E.launches += 2;
         CK(cudaGetLastError());

@@ -35,6 +35,7 @@ struct MsmEngine {
     MsmStats last;
     int force_window_bits = 0; // 0 = choose from n
     bool timing = false;
+    int pass2_minb = 1; // resident blocks per SM the pass-2 kernel is compiled for (register cap)
 
     int init(cudaStream_t s);
     void destroy();

@@ -82,6 +82,7 @@ def lib():
         L.dvp_selftest_op.argtypes = [vp, i32, vp, vp, vp, sz]
         L.dvp_microbench.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
         L.dvp_hostcheck_op.argtypes = [i32, vp, vp, vp, sz]
+        L.dvp_pipebench.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -213,6 +214,11 @@ class Context:
         bb = np.ascontiguousarray(b, dtype=np.uint32) if b is not None else None
         _ck(lib().dvp_selftest_op(self._h, op, _ptr(a), _ptr(bb), _ptr(out), a.shape[0]))
         return out
+
+    def pipebench(self, mode, iters, blocks_per_sm):
+        v = C.c_double()
+        _ck(lib().dvp_pipebench(self._h, mode, iters, blocks_per_sm, C.byref(v)))
+        return v.value
 
     def microbench(self, op, iters):
         v = C.c_double()

@@ -97,6 +97,12 @@ int dvp_selftest_op(dvp_ctx *ctx, int op, const void *a, const void *b, void *ou
 /* Integer-pipe microbenchmark: op 0 gf_mul chain, 1 gf_sqr chain, 2 fr_mul chain; returns ops per second. */
 int dvp_microbench(dvp_ctx *ctx, int op, int iters, double *ops_per_sec);
 
+/* Raw integer-pipe issue rates (thread-instructions per second over the whole GPU): the roofline
+ * denominators for the field kernels.  mode: 0 IMAD.WIDE  1 LOP3  2 IMAD  3 IMAD.WIDE:LOP3 = 1:2  4 SHF  5 IADD */
+int dvp_pipebench(dvp_ctx *ctx, int mode, int iters, int blocks_per_sm, double *instr_per_sec);
+/* Same source as the kernels, evaluated on the CPU; used only by the CPU-side parity tests. */
+int dvp_hostcheck_op(int op, const void *a, const void *b, void *out, size_t n);
+
 #ifdef __cplusplus
 }
 #endif
