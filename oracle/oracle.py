@@ -247,3 +247,242 @@ def random_fr_mont(n, seed):
                 if len(vals) == n:
                     break
     return vals, mont_array(vals)
+
+
+# ---------------------------------------------------------------- ECFFT domain
+class Domain:
+    """ecfft_domain wrapper: leaves, extend (D -> D'), chain-rule vanishing-polynomial helpers."""
+
+    class _S(C.Structure):
+        _fields_ = [("log_n2", C.c_int), ("n2", C.c_size_t), ("leaves", C.c_void_p), ("levels", C.c_int),
+                    ("dec", C.c_void_p), ("rec", C.c_void_p), ("x0", C.c_void_p), ("t", C.c_void_p),
+                    ("last", C.c_void_p)]
+
+    def __init__(self, log_n2):
+        L = lib()
+        L.ecfft_domain_new.restype = C.POINTER(Domain._S)
+        self._d = L.ecfft_domain_new(log_n2)
+        self.log_n2 = log_n2
+        self.n2 = 1 << log_n2
+        self.n = self.n2 >> 1
+
+    def __del__(self):
+        try:
+            lib().ecfft_domain_free(self._d)
+        except Exception:
+            pass
+
+    def _arr(self, ptr, count):
+        buf = (C.c_uint64 * (4 * count)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.uint64).reshape(count, 4).copy()
+
+    def leaves_mont(self):
+        return self._arr(self._d.contents.leaves, self.n2)
+
+    def leaves(self):
+        return mont_array_to_ints(self.leaves_mont())
+
+    def isogenies(self):
+        return (mont_array_to_ints(self._arr(self._d.contents.x0, self.log_n2)),
+                mont_array_to_ints(self._arr(self._d.contents.t, self.log_n2)))
+
+    def extend_mont(self, evals_mont):
+        a = np.ascontiguousarray(evals_mont, dtype=np.uint64).reshape(self.n, 4)
+        out = np.zeros_like(a)
+        lib().ecfft_extend(self._d, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def extend(self, evals):
+        return mont_array_to_ints(self.extend_mont(mont_array(evals)))
+
+    def vanish_at(self, shift, x):
+        r = Fr()
+        lib().ecfft_vanish_at(self._d, shift, C.byref(fr_mont(x)), C.byref(r))
+        return fr_int(r)
+
+    def vanish_derivative_on_roots_mont(self, shift):
+        out = np.zeros((self.n, 4), dtype=np.uint64)
+        lib().ecfft_vanish_derivative_on_roots(self._d, shift, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def vanish_on_other_mont(self, shift):
+        out = np.zeros((self.n, 4), dtype=np.uint64)
+        lib().ecfft_vanish_on_other(self._d, shift, out.ctypes.data_as(C.c_void_p))
+        return out
+
+
+# ---------------------------------------------------------------- R1CS + protocol
+class _R1csS(C.Structure):
+    _fields_ = [("nrows", C.c_size_t), ("n", C.c_size_t), ("k", C.c_size_t), ("nwires", C.c_size_t),
+                ("rowptr", C.c_void_p * 3), ("wire", C.c_void_p * 3), ("coeff", C.c_void_p * 3),
+                ("coeffs", C.c_void_p), ("ncoeffs", C.c_size_t)]
+
+
+class _TrapdoorS(C.Structure):
+    _fields_ = [("tau", Fr), ("delta", Fr), ("epsilon", Fr)]
+
+
+class _SrsS(C.Structure):
+    _fields_ = [("g_m", C.c_void_p), ("g_q", C.c_void_p), ("g_k", C.c_void_p), ("z_vals2inv", C.c_void_p),
+                ("bar_wts", C.c_void_p)]
+
+
+class R1CS:
+    """Sparse R1CS in the dump's own order (gnark_r1cs.rs:1-20).
+
+    rows: list of (L, R, O), each a list of (wire_id, coeff_id); coeffs: canonical ints."""
+
+    def __init__(self, coeffs, rows, num_public, nwires):
+        self.nrows = len(rows)
+        self.n = 1
+        while self.n < max(self.nrows, 1):
+            self.n *= 2
+        self.n = max(self.n, 2)
+        self.k = num_public
+        self.nwires = nwires
+        self.coeffs_int = list(coeffs)
+        self.coeffs = mont_array(coeffs) if len(coeffs) else np.zeros((1, 4), dtype=np.uint64)
+        self.rowptr, self.wire, self.coeff = [], [], []
+        for which in range(3):
+            rp, wi, ci = [0], [], []
+            for row in rows:
+                for (w, c) in row[which]:
+                    wi.append(w)
+                    ci.append(c)
+                rp.append(len(wi))
+            self.rowptr.append(np.array(rp, dtype=np.uint32))
+            self.wire.append(np.array(wi if wi else [0], dtype=np.uint32))
+            self.coeff.append(np.array(ci if ci else [0], dtype=np.uint32))
+        self._s = _R1csS()
+        self._s.nrows, self._s.n, self._s.k, self._s.nwires = self.nrows, self.n, self.k, self.nwires
+        for which in range(3):
+            self._s.rowptr[which] = self.rowptr[which].ctypes.data
+            self._s.wire[which] = self.wire[which].ctypes.data
+            self._s.coeff[which] = self.coeff[which].ctypes.data
+        self._s.coeffs = self.coeffs.ctypes.data
+        self._s.ncoeffs = len(coeffs)
+
+    @classmethod
+    def from_arrays(cls, coeffs_mont, rowptr, wire, coeff, nrows, num_public, nwires):
+        """Adopt prebuilt CSR arrays (large synthetic circuits)."""
+        self = cls.__new__(cls)
+        self.nrows, self.k, self.nwires = nrows, num_public, nwires
+        self.n = 2
+        while self.n < nrows:
+            self.n *= 2
+        self.coeffs = np.ascontiguousarray(coeffs_mont, dtype=np.uint64)
+        self.coeffs_int = None
+        self.rowptr = [np.ascontiguousarray(x, dtype=np.uint32) for x in rowptr]
+        self.wire = [np.ascontiguousarray(x, dtype=np.uint32) for x in wire]
+        self.coeff = [np.ascontiguousarray(x, dtype=np.uint32) for x in coeff]
+        self._s = _R1csS()
+        self._s.nrows, self._s.n, self._s.k, self._s.nwires = self.nrows, self.n, self.k, self.nwires
+        for which in range(3):
+            self._s.rowptr[which] = self.rowptr[which].ctypes.data
+            self._s.wire[which] = self.wire[which].ctypes.data
+            self._s.coeff[which] = self.coeff[which].ctypes.data
+        self._s.coeffs = self.coeffs.ctypes.data
+        self._s.ncoeffs = self.coeffs.shape[0]
+        return self
+
+
+def trapdoor(tau, delta, epsilon):
+    t = _TrapdoorS()
+    t.tau, t.delta, t.epsilon = fr_mont(tau), fr_mont(delta), fr_mont(epsilon)
+    return t
+
+
+def r1cs_eval(r1cs, dom, assignment_mont):
+    """get_matrix_evaluations_from_witness (proving.rs:348-403): returns (a, b, c, i) Montgomery arrays, bad_row"""
+    n = r1cs.n
+    w = np.ascontiguousarray(assignment_mont, dtype=np.uint64)
+    outs = [np.zeros((n, 4), dtype=np.uint64) for _ in range(4)]
+    L = lib()
+    L.r1cs_eval.restype = C.c_long
+    bad = L.r1cs_eval(C.byref(r1cs._s), dom._d, w.ctypes.data_as(C.c_void_p), *[o.ctypes.data_as(C.c_void_p) for o in outs])
+    return outs, bad
+
+
+class Srs:
+    def __init__(self, r1cs, dom, td):
+        L = lib()
+        L.dv_setup.restype = C.POINTER(_SrsS)
+        self._p = L.dv_setup(C.byref(r1cs._s), dom._d, C.byref(td))
+        self.n, self.nwires = r1cs.n, r1cs.nwires
+
+    def __del__(self):
+        try:
+            lib().dv_srs_free(self._p)
+        except Exception:
+            pass
+
+    def _enc(self, ptr, count):
+        arr = C.cast(ptr, C.POINTER(Pt * count)).contents
+        return encode_batch(arr)
+
+    def g_m30(self):
+        return self._enc(self._p.contents.g_m, self.nwires)
+
+    def g_q30(self):
+        return self._enc(self._p.contents.g_q, self.n)
+
+    def g_k30(self):
+        return self._enc(self._p.contents.g_k, 4 * self.n)
+
+    def _frs(self, ptr, count):
+        buf = (C.c_uint64 * (4 * count)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.uint64).reshape(count, 4).copy()
+
+    def z_vals2inv_mont(self):
+        return self._frs(self._p.contents.z_vals2inv, self.n)
+
+    def bar_wts_mont(self):
+        return self._frs(self._p.contents.bar_wts, self.n)
+
+
+def prove(r1cs, dom, srs, assignment_mont, want_stages=False, nthreads=0):
+    """Proof::prove (proving.rs:426-688).  Returns (118 proof bytes, status, stages or None)."""
+    w = np.ascontiguousarray(assignment_mont, dtype=np.uint64)
+    proof = (C.c_uint8 * 118)()
+    st = np.zeros((13 * r1cs.n, 4), dtype=np.uint64) if want_stages else None
+    L = lib()
+    L.dv_prove.restype = C.c_long
+    rc = L.dv_prove(C.byref(r1cs._s), dom._d, srs._p, w.ctypes.data_as(C.c_void_p), proof,
+                    st.ctypes.data_as(C.c_void_p) if want_stages else None, nthreads)
+    return bytes(proof), rc, st
+
+
+def verify(td, public_ints, proof118):
+    """SRS::verify (srs.rs:374-428)"""
+    pub = mont_array(public_ints)
+    return bool(lib().dv_verify(C.byref(td), pub.ctypes.data_as(C.c_void_p), C.c_size_t(len(public_ints)),
+                                (C.c_uint8 * 118).from_buffer_copy(proof118)))
+
+
+def transcript_alpha(commit_p30, public_ints):
+    pub = mont_array(public_ints)
+    r = Fr()
+    lib().dv_transcript_alpha((C.c_uint8 * 30).from_buffer_copy(commit_p30), pub.ctypes.data_as(C.c_void_p),
+                              C.c_size_t(len(public_ints)), C.byref(r))
+    return fr_int(r)
+
+
+def toy_r1cs():
+    """The five-constraint circuit of dvsnark_test.rs:34-128; returns (R1CS, public ints, private ints)."""
+    ONE, O_, W, Y, Z, X, T, S = range(8)
+    c1 = lambda w: (w, 0)
+    c2 = lambda w: (w, 1)
+    rows = [
+        ([c1(X)], [c1(X)], [c1(Y)]),
+        ([c1(Y), c1(Z)], [c1(ONE)], [c1(W)]),
+        ([c2(Z)], [c1(ONE)], [c1(T)]),
+        ([c1(X), c1(T)], [c1(ONE)], [c1(S)]),
+        ([c1(W), c1(S)], [c1(ONE)], [c1(O_)]),
+    ]
+    x, z = 3, 4
+    y = x * x
+    w = y + z
+    t = z + z
+    s = x + t
+    o = w + s
+    return R1CS([1, 2], rows, 2, 8), [o, w], [y, z, x, t, s]
