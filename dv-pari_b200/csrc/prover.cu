@@ -1,0 +1,874 @@
+// Fr-side prover kernels and the device-resident Proof::prove for sm_100a.
+//
+// Replaces, on the prover path of /root/reference/src/proving.rs:426-688:
+//   build_sect_ecfft_tree / get_both_domains      src/ec_fft.rs:93-239,179-189   -> dvp_domain_create
+//   FFTree::extend(.., Moiety::S1) x4             src/proving.rs:410-422         -> k_extend_down/up
+//   get_matrix_evaluations_from_witness           src/proving.rs:348-403         -> k_r1cs_eval
+//   r / q / K-scalar pointwise passes             src/proving.rs:492-509,599-654 -> k_quotient, k_kscalars
+//   evaluate_poly_at_alpha_using_barycentric_..   src/ec_fft.rs:455-491          -> k_bary_partial
+//   prover precomputes (bar_wts, z_vals2inv)      src/proving.rs:225-325         -> chain-rule kernels
+// Fr is 8 x u32 Montgomery limbs in ark's memory layout (fr.cuh).  Every vector stays in HBM between
+// stages; the host sees only the two commitments, alpha and the two evaluations.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "../../include/dvpari.h"
+#include "ctx.cuh"
+#include "fr.cuh"
+#include "host_gf.hpp"
+#include "transcript_host.hpp"
+
+using namespace dvp;
+
+#define CKP(x)                                                                                            \
+    do {                                                                                                  \
+        cudaError_t e_ = (x);                                                                             \
+        if (e_ != cudaSuccess) {                                                                          \
+            fprintf(stderr, "[dvpari] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return DVP_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+static inline uint32_t cdivp(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ fr fr_load(const fr *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = q[0], b = q[1];
+    fr r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void fr_store(fr *p, const fr &v) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    q[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+}
+// v^(2^e)
+__host__ __device__ inline fr fr_pow2k(fr v, int e) {
+    for (int i = 0; i < e; i++) v = fr_sqr(v);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// domain construction
+// ------------------------------------------------------------------------------------------------
+struct SwPt {
+    fr x, y;
+};
+struct SwConsts {
+    fr A;
+    SwPt C;        // coset offset
+    SwPt pow2[28]; // pow2[b] = 2^b * g  (g = generator of the order-N subgroup)
+};
+
+// leaf_i = x(C + i g): Jacobian accumulation over the set bits of i, one inversion per leaf.
+__global__ void k_dom_leaves(const SwConsts *__restrict__ sc, uint32_t N, int logN, fr *__restrict__ leaves) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    // (X, Y, Z) with x = X/Z^2, y = Y/Z^3, start from the affine coset point
+    fr X = sc->C.x, Y = sc->C.y, Z = fr_one();
+    for (int b = 0; b < logN; b++) {
+        if (!((i >> b) & 1)) continue;
+        // mixed addition (X,Y,Z) + (x2,y2); the operands are never equal or opposite (C is off the subgroup)
+        const fr x2 = sc->pow2[b].x, y2 = sc->pow2[b].y;
+        const fr Z2 = fr_sqr(Z);
+        const fr U2 = fr_mul(x2, Z2), S2 = fr_mul(y2, fr_mul(Z2, Z));
+        const fr H = fr_sub(U2, X), Rr = fr_sub(S2, Y);
+        const fr H2 = fr_sqr(H), H3 = fr_mul(H2, H), V = fr_mul(X, H2);
+        fr X3 = fr_sub(fr_sub(fr_sqr(Rr), H3), fr_add(V, V));
+        fr Y3 = fr_sub(fr_mul(Rr, fr_sub(V, X3)), fr_mul(Y, H3));
+        Z = fr_mul(Z, H);
+        X = X3;
+        Y = Y3;
+    }
+    const fr zi = fr_inv(Z);
+    fr_store(&leaves[i], fr_mul(X, fr_sqr(zi)));
+}
+
+// next layer: out[i] = psi(in[i]) = in[i] + t/(in[i] - x0), i < half
+__global__ void k_dom_next_layer(const fr *__restrict__ in, uint32_t half, fr x0, fr t, fr *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    const fr x = fr_load(&in[i]);
+    fr_store(&out[i], fr_add(x, fr_mul(t, fr_inv(fr_sub(x, x0)))));
+}
+
+// v^(h-1) with h = 2^e:  prod_{i<e} v^(2^i)
+__device__ inline fr pow_hm1(fr b, int e) {
+    fr acc = fr_one();
+    for (int i = 0; i < e; i++) {
+        acc = fr_mul(acc, b);
+        b = fr_sqr(b);
+    }
+    return acc;
+}
+
+// level matrices for sub-problems of size m = 2h on layer L (2m points): pair j uses the even leaves
+// (2j, 2j+m) as sources and the odd leaves (2j+1, 2j+1+m) as targets.
+//   P(s) = (P0(psi(s)) + s P1(psi(s))) v(s)^(h-1),  v(x) = x - x0
+__global__ void k_dom_matrices(const fr *__restrict__ L, uint32_t h, int e, fr x0, fr *__restrict__ dec,
+                               fr *__restrict__ rec) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= h) return;
+    const uint32_t m = 2 * h;
+    const fr s0 = fr_load(&L[2 * j]), s1 = fr_load(&L[2 * j + m]);
+    const fr t0 = fr_load(&L[2 * j + 1]), t1 = fr_load(&L[2 * j + 1 + m]);
+    const fr vs0 = pow_hm1(fr_sub(s0, x0), e), vs1 = pow_hm1(fr_sub(s1, x0), e);
+    const fr vt0 = pow_hm1(fr_sub(t0, x0), e), vt1 = pow_hm1(fr_sub(t1, x0), e);
+    fr_store(&rec[4 * j + 0], vt0);
+    fr_store(&rec[4 * j + 1], fr_mul(t0, vt0));
+    fr_store(&rec[4 * j + 2], vt1);
+    fr_store(&rec[4 * j + 3], fr_mul(t1, vt1));
+    // inverse of [[vs0, s0 vs0], [vs1, s1 vs1]]
+    const fr dinv = fr_inv(fr_mul(fr_mul(vs0, vs1), fr_sub(s1, s0)));
+    fr_store(&dec[4 * j + 0], fr_mul(fr_mul(s1, vs1), dinv));
+    fr_store(&dec[4 * j + 1], fr_neg(fr_mul(fr_mul(s0, vs0), dinv)));
+    fr_store(&dec[4 * j + 2], fr_neg(fr_mul(vs1, dinv)));
+    fr_store(&dec[4 * j + 3], fr_mul(vs0, dinv));
+}
+
+// chain rule, one level: for the m points s_j = L[2j + shift] of S^k
+//   deriv:  out[j] = v(s)^(m/2) psi'(s) prev[j mod h]      (Z'_S on its roots)
+//   other:  out[j] = v(t)^(m/2) prev[j mod h], t = L[2j + 1 - shift]   (Z_S on the other half-domain)
+__global__ void k_chain_level(const fr *__restrict__ L, uint32_t m, int e2, fr x0, fr t, int shift, int deriv,
+                              const fr *__restrict__ prev, fr *__restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint32_t h = m >> 1;
+    const fr s = fr_load(&L[2 * j + (deriv ? shift : 1 - shift)]);
+    const fr v = fr_sub(s, x0);
+    fr f = fr_pow2k(v, e2);
+    if (deriv) {
+        const fr vi = fr_inv(v);
+        f = fr_mul(f, fr_sub(fr_one(), fr_mul(t, fr_sqr(vi))));
+    }
+    fr_store(&out[j], fr_mul(f, fr_load(&prev[h ? j % h : 0])));
+}
+__global__ void k_fr_inv_each(fr *__restrict__ v, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_store(&v[i], fr_inv(fr_load(&v[i])));
+}
+
+// ------------------------------------------------------------------------------------------------
+// ECFFT extend: in-place 2x2 butterflies, level k has sub-problems of size m = n >> k
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_extend_level(fr *__restrict__ data, uint32_t n, uint32_t h, const fr *__restrict__ mats, int npoly,
+                   size_t stride) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; // butterfly index in [0, n/2)
+    if (g >= (n >> 1)) return;
+    const uint32_t j = g % h, s = g / h;
+    const uint32_t i0 = s * 2 * h + j, i1 = i0 + h;
+    const fr m0 = fr_load(&mats[4 * j]), m1 = fr_load(&mats[4 * j + 1]);
+    const fr m2 = fr_load(&mats[4 * j + 2]), m3 = fr_load(&mats[4 * j + 3]);
+    for (int p = 0; p < npoly; p++) {
+        fr *d = data + (size_t)p * stride;
+        const fr x0 = fr_load(&d[i0]), x1 = fr_load(&d[i1]);
+        fr_store(&d[i0], fr_add(fr_mul(m0, x0), fr_mul(m1, x1)));
+        fr_store(&d[i1], fr_add(fr_mul(m2, x0), fr_mul(m3, x1)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// R1CS rows: a = A w, b = B w, c = C w - i, i = sum_j x_j d^j; first unsatisfied row recorded
+// ------------------------------------------------------------------------------------------------
+struct R1csDev {
+    const uint32_t *rowptr[3];
+    const uint32_t *wire[3];
+    const uint32_t *coeff[3];
+    const fr *coeffs;
+    uint32_t nrows, n, k;
+};
+__device__ __forceinline__ fr row_dot(const R1csDev &r, int which, uint32_t row, const fr *__restrict__ w) {
+    fr acc = fr_zero();
+    for (uint32_t p = r.rowptr[which][row]; p < r.rowptr[which][row + 1]; p++)
+        acc = fr_add(acc, fr_mul(fr_load(&r.coeffs[r.coeff[which][p]]), fr_load(&w[r.wire[which][p]])));
+    return acc;
+}
+__global__ void __launch_bounds__(128)
+    k_r1cs_eval(R1csDev r, const fr *__restrict__ w, const fr *__restrict__ leaves, fr *__restrict__ a,
+                fr *__restrict__ b, fr *__restrict__ c, fr *__restrict__ iv, unsigned long long *__restrict__ first_bad) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= r.n) return;
+    fr av = fr_zero(), bv = fr_zero(), cw = fr_zero();
+    if (row < r.nrows) {
+        av = row_dot(r, 0, row, w);
+        bv = row_dot(r, 1, row, w);
+        cw = row_dot(r, 2, row, w);
+    }
+    const fr d = fr_load(&leaves[2 * row]);
+    fr pw = fr_one(), ival = fr_zero();
+    for (uint32_t j = 0; j < r.k; j++) {
+        ival = fr_add(ival, fr_mul(fr_load(&w[1 + j]), pw));
+        pw = fr_mul(pw, d);
+    }
+    fr_store(&a[row], av);
+    fr_store(&b[row], bv);
+    fr_store(&c[row], fr_sub(cw, ival));
+    fr_store(&iv[row], ival);
+    if (!fr_eq(fr_mul(av, bv), cw)) atomicMin(first_bad, (unsigned long long)row);
+}
+
+// i(X) has degree k-1 < n, so its extension to D' is its evaluation there
+__global__ void k_ivals_ext(const fr *__restrict__ w, uint32_t k, const fr *__restrict__ leaves, uint32_t n,
+                            fr *__restrict__ i2) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const fr d = fr_load(&leaves[2 * row + 1]);
+    fr pw = fr_one(), ival = fr_zero();
+    for (uint32_t j = 0; j < k; j++) {
+        ival = fr_add(ival, fr_mul(fr_load(&w[1 + j]), pw));
+        pw = fr_mul(pw, d);
+    }
+    fr_store(&i2[row], ival);
+}
+
+// r' = a' b' - i',  q = (r' - c') z_inv     (proving.rs:492-509)
+// c2r holds c' on entry and r' on exit (r' is needed again for the K scalars, c' is not)
+__global__ void k_quotient(const fr *__restrict__ a2, const fr *__restrict__ b2, fr *__restrict__ c2r,
+                           const fr *__restrict__ i2, const fr *__restrict__ zinv, uint32_t n, fr *__restrict__ q) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fr cv = fr_load(&c2r[i]);
+    const fr r = fr_sub(fr_mul(fr_load(&a2[i]), fr_load(&b2[i])), fr_load(&i2[i]));
+    fr_store(&q[i], fr_mul(fr_sub(r, cv), fr_load(&zinv[i])));
+    fr_store(&c2r[i], r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched Fr inversion (Montgomery trick, two levels of 16) of out[i] = 1/(leaves[i] - alpha)
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t FRB = 16;
+__global__ void k_frb_up(const fr *__restrict__ leaves, fr alpha, uint32_t n, fr *__restrict__ pre, fr *__restrict__ tot) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lo = g * FRB;
+    if (lo >= n) return;
+    const uint32_t hi = min(n, lo + FRB);
+    fr acc = fr_one();
+    for (uint32_t i = lo; i < hi; i++) {
+        fr_store(&pre[i], acc);
+        acc = fr_mul(acc, fr_sub(fr_load(&leaves[i]), alpha));
+    }
+    fr_store(&tot[g], acc);
+}
+__global__ void k_frb_down(const fr *__restrict__ leaves, fr alpha, uint32_t n, const fr *__restrict__ pre,
+                           const fr *__restrict__ tot_inv, fr *__restrict__ out) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lo = g * FRB;
+    if (lo >= n) return;
+    const uint32_t hi = min(n, lo + FRB);
+    fr inv = fr_load(&tot_inv[g]);
+    for (uint32_t i = hi; i-- > lo;) {
+        const fr v = fr_sub(fr_load(&leaves[i]), alpha);
+        fr_store(&out[i], fr_mul(inv, fr_load(&pre[i])));
+        if (i > lo) inv = fr_mul(inv, v);
+    }
+}
+
+// partial sums of y_i w_i /(alpha - d_i) for y = a and b: one Fr pair per block  (ec_fft.rs:455-491)
+// dinv[2i] = 1/(d_i - alpha), so the term is -y_i w_i dinv[2i]
+__global__ void __launch_bounds__(256)
+    k_bary_partial(const fr *__restrict__ a, const fr *__restrict__ b, const fr *__restrict__ wts,
+                   const fr *__restrict__ dinv, uint32_t n, fr *__restrict__ part) {
+    __shared__ fr sa[256], sb[256];
+    fr accA = fr_zero(), accB = fr_zero();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const fr wi = fr_mul(fr_load(&wts[i]), fr_load(&dinv[2 * i]));
+        accA = fr_add(accA, fr_mul(fr_load(&a[i]), wi));
+        accB = fr_add(accB, fr_mul(fr_load(&b[i]), wi));
+    }
+    sa[threadIdx.x] = accA;
+    sb[threadIdx.x] = accB;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            sa[threadIdx.x] = fr_add(sa[threadIdx.x], sa[threadIdx.x + o]);
+            sb[threadIdx.x] = fr_add(sb[threadIdx.x], sb[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        part[2 * blockIdx.x] = fr_neg(sa[0]);
+        part[2 * blockIdx.x + 1] = fr_neg(sb[0]);
+    }
+}
+
+// K scalars (proving.rs:599-654): k_a | k_b | k_r (interleaved D, D'), contiguous for the 4n-point MSM
+__global__ void k_kscalars(const fr *__restrict__ a, const fr *__restrict__ b, const fr *__restrict__ iv,
+                           const fr *__restrict__ r2, const fr *__restrict__ dinv, fr a0, fr b0, fr r0, uint32_t n,
+                           fr *__restrict__ ks) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fr av = fr_load(&a[i]), bv = fr_load(&b[i]);
+    const fr d1 = fr_load(&dinv[2 * i]), d2 = fr_load(&dinv[2 * i + 1]);
+    fr_store(&ks[i], fr_mul(fr_sub(av, a0), d1));
+    fr_store(&ks[n + i], fr_mul(fr_sub(bv, b0), d1));
+    const fr rv = fr_sub(fr_mul(av, bv), fr_load(&iv[i]));
+    fr_store(&ks[2 * n + 2 * i], fr_mul(fr_sub(rv, r0), d1));
+    fr_store(&ks[2 * n + 2 * i + 1], fr_mul(fr_sub(fr_load(&r2[i]), r0), d2));
+}
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct dvp_domain {
+    dvp_ctx *ctx = nullptr;
+    int log_n2 = 0;
+    uint32_t n2 = 0, n = 0;
+    int levels = 0;
+    DevBuf leaves;               // 2n Fr
+    std::vector<DevBuf> dec, rec; // per level
+    DevBuf z_vals2inv, bar_wts;  // n Fr each
+    std::vector<fr> x0, t;       // isogeny chain (host)
+    fr last[2];
+    DevBuf work;                 // extend workspace
+};
+struct dvp_r1cs {
+    dvp_ctx *ctx = nullptr;
+    R1csDev dev;
+    DevBuf bufs[10];
+    size_t nwires = 0;
+};
+struct dvp_prover {
+    dvp_ctx *ctx = nullptr;
+    dvp_domain *dom = nullptr;
+    dvp_r1cs *r1cs = nullptr;
+    int slot_gm = 0, slot_gq = 0, slot_gk = 0;
+    DevBuf vec;  // 13 n Fr: a b c i a' b' c' i' q | k_a k_b k_r(2n)   (r' reuses c' after q)
+    DevBuf wit, dinv, pre, tot, tot2, pre2, part;
+    void *h_part = nullptr;
+    float ms[8] = {0};
+};
+
+// host-side Fr helpers on the isogeny chain
+static void sw_dbl_host(SwPt &p, const fr &A) {
+    const fr three = fr_from_u64(3);
+    const fr lam = fr_mul(fr_add(fr_mul(three, fr_sqr(p.x)), A), fr_inv(fr_add(p.y, p.y)));
+    const fr x3 = fr_sub(fr_sub(fr_sqr(lam), p.x), p.x);
+    const fr y3 = fr_sub(fr_mul(lam, fr_sub(p.x, x3)), p.y);
+    p.x = x3;
+    p.y = y3;
+}
+static fr fr_from_dec_host(const char *s) {
+    fr acc = fr_zero();
+    const fr ten = fr_from_u64(10);
+    for (; *s; s++) acc = fr_add(fr_mul(acc, ten), fr_from_u64((uint64_t)(*s - '0')));
+    return acc;
+}
+// Z_S(x) for S = D (shift 0) or D' (shift 1):  Z_S(x) = v(x)^(|S|/2) Z_psi(S)(psi(x))
+static fr vanish_at_host(const dvp_domain *d, int shift, fr x) {
+    fr acc = fr_one();
+    for (int k = 0; k < d->levels; k++) {
+        const fr v = fr_sub(x, d->x0[k]);
+        acc = fr_mul(acc, fr_pow2k(v, d->levels - k - 1));
+        x = fr_add(x, fr_mul(d->t[k], fr_inv(v)));
+    }
+    return fr_mul(acc, fr_sub(x, d->last[shift]));
+}
+
+static int run_chain(dvp_domain *d, const std::vector<DevBuf *> &layers, int shift, int deriv, fr *out, fr *tmp) {
+    // level `levels`: one root; walk up to level 0
+    cudaStream_t st = d->ctx->stream;
+    const fr base = deriv ? fr_one() : fr_sub(d->last[1 - shift], d->last[shift]);
+    fr *cur = (d->levels & 1) ? tmp : out, *nxt = (d->levels & 1) ? out : tmp;
+    CKP(cudaMemcpyAsync(cur, &base, sizeof(fr), cudaMemcpyHostToDevice, st));
+    for (int k = d->levels - 1; k >= 0; k--) {
+        const uint32_t m = d->n >> k;
+        k_chain_level<<<cdivp(m, 128), 128, 0, st>>>(layers[k]->as<fr>(), m, d->levels - k - 1, d->x0[k], d->t[k], shift,
+                                                    deriv, cur, nxt);
+        fr *sw = cur;
+        cur = nxt;
+        nxt = sw;
+    }
+    CKP(cudaGetLastError());
+    // after `levels` swaps the result sits in `out`
+    k_fr_inv_each<<<cdivp(d->n, 128), 128, 0, st>>>(out, d->n);
+    CKP(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int dvp_domain_create(dvp_ctx *ctx, unsigned log2_2n, dvp_domain **out) {
+    if (!ctx || !out || log2_2n < 2 || log2_2n > 28) return DVP_ERR_BAD_ARG;
+    *out = nullptr;
+    CKP(cudaSetDevice(ctx->device));
+    dvp_domain *d = new dvp_domain();
+    d->ctx = ctx;
+    d->log_n2 = (int)log2_2n;
+    d->n2 = 1u << log2_2n;
+    d->n = d->n2 >> 1;
+    d->levels = d->log_n2 - 1;
+    cudaStream_t st = ctx->stream;
+    int rc = 0;
+    // constants: /root/reference/src/ec_fft.rs:209-229
+    SwConsts sc;
+    sc.A = fr_from_dec_host("2125753088427212854352924174339172498722499297750753614229533284661082");
+    SwPt G;
+    G.x = fr_from_dec_host("1969398527398874941115360315313056361667745675958024267654083765592400");
+    G.y = fr_from_dec_host("917696706299601920847965073366118878832337776859300472447868491055982");
+    sc.C.x = fr_from_dec_host("1557215852494830750811239888869886110709986867282698163663807961412586");
+    sc.C.y = fr_from_dec_host("2302954593454110051167704558708330032236229062988890422530712548754008");
+    SwPt g = G;
+    for (int i = 0; i < 28 - d->log_n2; i++) sw_dbl_host(g, sc.A); // ec_fft.rs:121-124
+    sc.pow2[0] = g;
+    for (int b = 1; b < 28; b++) {
+        sc.pow2[b] = sc.pow2[b - 1];
+        if (b < d->log_n2) sw_dbl_host(sc.pow2[b], sc.A);
+    }
+    // isogeny chain (x0_k, t_k): kernel = the order-2 point of <g_k>
+    d->x0.resize(d->log_n2);
+    d->t.resize(d->log_n2);
+    {
+        fr Ak = sc.A;
+        SwPt gk = g;
+        for (int k = 0; k < d->log_n2; k++) {
+            SwPt K = gk;
+            for (uint32_t o = d->n2 >> k; o > 2; o >>= 1) sw_dbl_host(K, Ak);
+            if (!fr_is_zero(K.y)) {
+                delete d;
+                return DVP_ERR_INTERNAL;
+            }
+            const fr x0 = K.x, t = fr_add(fr_mul(fr_from_u64(3), fr_sqr(x0)), Ak);
+            d->x0[k] = x0;
+            d->t[k] = t;
+            if ((d->n2 >> k) > 2) {
+                const fr di = fr_inv(fr_sub(gk.x, x0)), q = fr_mul(t, di);
+                SwPt ng;
+                ng.x = fr_add(gk.x, q);
+                ng.y = fr_sub(gk.y, fr_mul(fr_mul(q, di), gk.y));
+                gk = ng;
+                Ak = fr_sub(Ak, fr_mul(fr_from_u64(5), t));
+            }
+        }
+    }
+    // layers on the device
+    std::vector<DevBuf> layer_store(d->log_n2);
+    std::vector<DevBuf *> layers(d->log_n2);
+    DevBuf dsc;
+    auto fail = [&](int code) {
+        for (auto &b : layer_store) b.release();
+        dsc.release();
+        dvp_domain_destroy(d);
+        return code;
+    };
+    if ((rc = d->leaves.reserve((size_t)d->n2 * sizeof(fr))) || (rc = dsc.reserve(sizeof(SwConsts)))) return fail(rc);
+    if (cudaMemcpyAsync(dsc.p, &sc, sizeof(sc), cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(DVP_ERR_CUDA);
+    k_dom_leaves<<<cdivp(d->n2, 128), 128, 0, st>>>(dsc.as<SwConsts>(), d->n2, d->log_n2, d->leaves.as<fr>());
+    layers[0] = &d->leaves;
+    for (int k = 0; k + 1 < d->log_n2; k++) {
+        const uint32_t half = d->n2 >> (k + 1);
+        if ((rc = layer_store[k + 1].reserve((size_t)half * sizeof(fr)))) return fail(rc);
+        layers[k + 1] = &layer_store[k + 1];
+        k_dom_next_layer<<<cdivp(half, 128), 128, 0, st>>>(layers[k]->as<fr>(), half, d->x0[k], d->t[k],
+                                                          layers[k + 1]->as<fr>());
+    }
+    if (cudaGetLastError() != cudaSuccess) return fail(DVP_ERR_CUDA);
+    // the D / D' chains end on the two leaves of layer `levels`
+    if (cudaMemcpyAsync(d->last, layers[d->levels]->p, 2 * sizeof(fr), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        return fail(DVP_ERR_CUDA);
+    // extend matrices
+    d->dec.resize(d->levels);
+    d->rec.resize(d->levels);
+    for (int k = 0; k < d->levels; k++) {
+        const uint32_t h = d->n >> (k + 1);
+        if ((rc = d->dec[k].reserve((size_t)h * 4 * sizeof(fr))) || (rc = d->rec[k].reserve((size_t)h * 4 * sizeof(fr))))
+            return fail(rc);
+        int e = 0;
+        while ((1u << e) < h) e++;
+        k_dom_matrices<<<cdivp(h, 64), 64, 0, st>>>(layers[k]->as<fr>(), h, e, d->x0[k], d->dec[k].as<fr>(),
+                                                   d->rec[k].as<fr>());
+    }
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return fail(DVP_ERR_CUDA);
+    // prover precomputes: bar_wts = 1/Z'_D(d_i), z_vals2inv = 1/Z_D(d'_i)  (proving.rs:225-325)
+    if ((rc = d->bar_wts.reserve((size_t)d->n * sizeof(fr))) || (rc = d->z_vals2inv.reserve((size_t)d->n * sizeof(fr))) ||
+        (rc = d->work.reserve((size_t)d->n * sizeof(fr))))
+        return fail(rc);
+    if ((rc = run_chain(d, layers, 0, 1, d->bar_wts.as<fr>(), d->work.as<fr>()))) return fail(rc);
+    if ((rc = run_chain(d, layers, 0, 0, d->z_vals2inv.as<fr>(), d->work.as<fr>()))) return fail(rc);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return fail(DVP_ERR_CUDA);
+    for (int k = 1; k < d->log_n2; k++) layer_store[k].release();
+    dsc.release();
+    *out = d;
+    return DVP_OK;
+}
+
+void dvp_domain_destroy(dvp_domain *d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    d->leaves.release();
+    for (auto &b : d->dec) b.release();
+    for (auto &b : d->rec) b.release();
+    d->z_vals2inv.release();
+    d->bar_wts.release();
+    d->work.release();
+    delete d;
+}
+
+int dvp_domain_leaves(dvp_domain *d, uint64_t *out) {
+    if (!d || !out) return DVP_ERR_BAD_ARG;
+    CKP(cudaSetDevice(d->ctx->device));
+    CKP(cudaMemcpy(out, d->leaves.p, (size_t)d->n2 * 32, cudaMemcpyDeviceToHost));
+    return DVP_OK;
+}
+int dvp_domain_precomputes(dvp_domain *d, uint64_t *z_vals2inv, uint64_t *bar_wts) {
+    if (!d) return DVP_ERR_BAD_ARG;
+    CKP(cudaSetDevice(d->ctx->device));
+    if (z_vals2inv) CKP(cudaMemcpy(z_vals2inv, d->z_vals2inv.p, (size_t)d->n * 32, cudaMemcpyDeviceToHost));
+    if (bar_wts) CKP(cudaMemcpy(bar_wts, d->bar_wts.p, (size_t)d->n * 32, cudaMemcpyDeviceToHost));
+    return DVP_OK;
+}
+// Z_D(x) (shift 0) or Z_D'(x) (shift 1) for a Montgomery x; the value of z_poly.evaluate(x) (ec_fft.rs:475)
+int dvp_domain_vanish_at(dvp_domain *d, int shift, const uint64_t x_mont[4], uint64_t out_mont[4]) {
+    if (!d || !x_mont || !out_mont || (shift != 0 && shift != 1)) return DVP_ERR_BAD_ARG;
+    fr x;
+    memcpy(x.v, x_mont, 32);
+    const fr r = vanish_at_host(d, shift, x);
+    memcpy(out_mont, r.v, 32);
+    return DVP_OK;
+}
+
+// in-place extend of npoly vectors of n Fr (device), D -> D'
+static int extend_device(dvp_domain *d, fr *data, int npoly, size_t stride) {
+    cudaStream_t st = d->ctx->stream;
+    const uint32_t n = d->n;
+    for (int k = 0; k < d->levels; k++)
+        k_extend_level<<<cdivp(n / 2, 256), 256, 0, st>>>(data, n, n >> (k + 1), d->dec[k].as<fr>(), npoly, stride);
+    for (int k = d->levels - 1; k >= 0; k--)
+        k_extend_level<<<cdivp(n / 2, 256), 256, 0, st>>>(data, n, n >> (k + 1), d->rec[k].as<fr>(), npoly, stride);
+    CKP(cudaGetLastError());
+    return 0;
+}
+
+// FFTree::extend(evals, Moiety::S1) for npoly vectors (host buffers, npoly x n x 4 u64)
+int dvp_ecfft_extend(dvp_domain *d, const uint64_t *in, uint64_t *out, int npoly) {
+    if (!d || !in || !out || npoly <= 0) return DVP_ERR_BAD_ARG;
+    CKP(cudaSetDevice(d->ctx->device));
+    DevBuf tmp;
+    int rc = tmp.reserve((size_t)npoly * d->n * sizeof(fr));
+    if (rc) return rc;
+    cudaStream_t st = d->ctx->stream;
+    CKP(cudaMemcpyAsync(tmp.p, in, (size_t)npoly * d->n * 32, cudaMemcpyHostToDevice, st));
+    rc = extend_device(d, tmp.as<fr>(), npoly, d->n);
+    if (!rc) {
+        CKP(cudaMemcpyAsync(out, tmp.p, (size_t)npoly * d->n * 32, cudaMemcpyDeviceToHost, st));
+        CKP(cudaStreamSynchronize(st));
+    }
+    tmp.release();
+    return rc;
+}
+int dvp_ecfft_extend_device(dvp_domain *d, void *d_data, int npoly) {
+    if (!d || !d_data || npoly <= 0) return DVP_ERR_BAD_ARG;
+    CKP(cudaSetDevice(d->ctx->device));
+    int rc = extend_device(d, (fr *)d_data, npoly, d->n);
+    if (rc) return rc;
+    CKP(cudaStreamSynchronize(d->ctx->stream));
+    return DVP_OK;
+}
+
+int dvp_r1cs_load(dvp_ctx *ctx, size_t nrows, size_t k, size_t nwires, const uint32_t *const rowptr[3],
+                  const uint32_t *const wire[3], const uint32_t *const coeff[3], const uint64_t *coeffs_mont,
+                  size_t ncoeffs, dvp_r1cs **out) {
+    if (!ctx || !out || !rowptr || !wire || !coeff || (!coeffs_mont && ncoeffs) || nwires < 1 + k) return DVP_ERR_BAD_ARG;
+    *out = nullptr;
+    CKP(cudaSetDevice(ctx->device));
+    // validate indices on the host: the reference would panic on an out-of-range index
+    for (int w = 0; w < 3; w++) {
+        if (!rowptr[w] || rowptr[w][0] != 0) return DVP_ERR_BAD_ARG;
+        for (size_t r = 0; r < nrows; r++)
+            if (rowptr[w][r + 1] < rowptr[w][r]) return DVP_ERR_BAD_ARG;
+        const size_t nnz = rowptr[w][nrows];
+        for (size_t p = 0; p < nnz; p++)
+            if (wire[w][p] >= nwires || coeff[w][p] >= ncoeffs) return DVP_ERR_BAD_ARG;
+    }
+    dvp_r1cs *r = new dvp_r1cs();
+    r->ctx = ctx;
+    r->nwires = nwires;
+    size_t n = 2;
+    while (n < nrows) n <<= 1; // rows.next_power_of_two(), gnark_r1cs.rs:291 (at least one pair)
+    r->dev.nrows = (uint32_t)nrows;
+    r->dev.n = (uint32_t)n;
+    r->dev.k = (uint32_t)k;
+    int rc = 0;
+    auto up = [&](DevBuf &b, const void *src, size_t bytes) -> const void * {
+        if (rc) return nullptr;
+        if ((rc = b.reserve(bytes ? bytes : 4))) return nullptr;
+        if (bytes && cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = DVP_ERR_CUDA;
+        return b.p;
+    };
+    for (int w = 0; w < 3; w++) {
+        const size_t nnz = rowptr[w][nrows];
+        r->dev.rowptr[w] = (const uint32_t *)up(r->bufs[3 * w], rowptr[w], (nrows + 1) * 4);
+        r->dev.wire[w] = (const uint32_t *)up(r->bufs[3 * w + 1], wire[w], nnz * 4);
+        r->dev.coeff[w] = (const uint32_t *)up(r->bufs[3 * w + 2], coeff[w], nnz * 4);
+    }
+    r->dev.coeffs = (const fr *)up(r->bufs[9], coeffs_mont, ncoeffs * 32);
+    if (rc) {
+        for (auto &b : r->bufs) b.release();
+        delete r;
+        return rc;
+    }
+    *out = r;
+    return DVP_OK;
+}
+void dvp_r1cs_destroy(dvp_r1cs *r) {
+    if (!r) return;
+    cudaSetDevice(r->ctx->device);
+    for (auto &b : r->bufs) b.release();
+    delete r;
+}
+
+static int r1cs_eval_device(dvp_r1cs *r, dvp_domain *d, const fr *d_w, fr *a, fr *b, fr *c, fr *iv, int64_t *first_bad) {
+    dvp_ctx *ctx = r->ctx;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = ctx->small.reserve(64))) return rc;
+    unsigned long long init = ~0ull, bad = 0;
+    CKP(cudaMemcpyAsync(ctx->small.p, &init, 8, cudaMemcpyHostToDevice, st));
+    k_r1cs_eval<<<cdivp(r->dev.n, 128), 128, 0, st>>>(r->dev, d_w, d->leaves.as<fr>(), a, b, c, iv,
+                                                     (unsigned long long *)ctx->small.p);
+    CKP(cudaGetLastError());
+    CKP(cudaMemcpyAsync(&bad, ctx->small.p, 8, cudaMemcpyDeviceToHost, st));
+    CKP(cudaStreamSynchronize(st));
+    if (first_bad) *first_bad = bad == ~0ull ? -1 : (int64_t)bad;
+    return bad == ~0ull ? DVP_OK : DVP_ERR_UNSATISFIED;
+}
+
+// get_matrix_evaluations_from_witness (proving.rs:348-403), host buffers: assignment nwires x 4, outputs n x 4 each
+int dvp_r1cs_eval(dvp_r1cs *r, dvp_domain *d, const uint64_t *assignment, uint64_t *a, uint64_t *b, uint64_t *c,
+                  uint64_t *iv, int64_t *first_bad_row) {
+    if (!r || !d || !assignment || !a || !b || !c || !iv) return DVP_ERR_BAD_ARG;
+    if (d->n != r->dev.n) return DVP_ERR_LENGTH_MISMATCH;
+    CKP(cudaSetDevice(r->ctx->device));
+    DevBuf w, o;
+    int rc;
+    const size_t n = r->dev.n;
+    if ((rc = w.reserve(r->nwires * 32)) || (rc = o.reserve(4 * n * 32))) {
+        w.release();
+        o.release();
+        return rc;
+    }
+    CKP(cudaMemcpyAsync(w.p, assignment, r->nwires * 32, cudaMemcpyHostToDevice, r->ctx->stream));
+    fr *ov = o.as<fr>();
+    rc = r1cs_eval_device(r, d, w.as<fr>(), ov, ov + n, ov + 2 * n, ov + 3 * n, first_bad_row);
+    if (rc == DVP_OK || rc == DVP_ERR_UNSATISFIED) {
+        cudaMemcpy(a, ov, n * 32, cudaMemcpyDeviceToHost);
+        cudaMemcpy(b, ov + n, n * 32, cudaMemcpyDeviceToHost);
+        cudaMemcpy(c, ov + 2 * n, n * 32, cudaMemcpyDeviceToHost);
+        cudaMemcpy(iv, ov + 3 * n, n * 32, cudaMemcpyDeviceToHost);
+    }
+    w.release();
+    o.release();
+    return rc;
+}
+
+int dvp_prover_create(dvp_ctx *ctx, dvp_domain *dom, dvp_r1cs *r1cs, int slot_gm, int slot_gq, int slot_gk,
+                      dvp_prover **out) {
+    if (!ctx || !dom || !r1cs || !out) return DVP_ERR_BAD_ARG;
+    *out = nullptr;
+    if (dom->n != r1cs->dev.n) return DVP_ERR_LENGTH_MISMATCH;
+    const size_t n = dom->n;
+    // multi_scalar_mul asserts scalars.len() == points.len() (curve.rs:142)
+    if (ctx->slots[slot_gm].n != r1cs->nwires || ctx->slots[slot_gq].n != n || ctx->slots[slot_gk].n != 4 * n)
+        return DVP_ERR_LENGTH_MISMATCH;
+    CKP(cudaSetDevice(ctx->device));
+    dvp_prover *p = new dvp_prover();
+    p->ctx = ctx;
+    p->dom = dom;
+    p->r1cs = r1cs;
+    p->slot_gm = slot_gm;
+    p->slot_gq = slot_gq;
+    p->slot_gk = slot_gk;
+    int rc = 0;
+    const size_t ng = (2 * n + FRB - 1) / FRB;
+    if ((rc = p->vec.reserve(13 * n * sizeof(fr))) || (rc = p->wit.reserve(r1cs->nwires * sizeof(fr))) ||
+        (rc = p->dinv.reserve(2 * n * sizeof(fr))) || (rc = p->pre.reserve(2 * n * sizeof(fr))) ||
+        (rc = p->tot.reserve(ng * sizeof(fr))) || (rc = p->tot2.reserve((ng / FRB + 2) * sizeof(fr))) ||
+        (rc = p->pre2.reserve(ng * sizeof(fr))) || (rc = p->part.reserve(2 * 1024 * sizeof(fr))) ||
+        cudaMallocHost(&p->h_part, 2 * 1024 * sizeof(fr)) != cudaSuccess) {
+        dvp_prover_destroy(p);
+        return rc ? rc : DVP_ERR_OOM;
+    }
+    *out = p;
+    return DVP_OK;
+}
+void dvp_prover_destroy(dvp_prover *p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    DevBuf *all[] = {&p->vec, &p->wit, &p->dinv, &p->pre, &p->tot, &p->tot2, &p->pre2, &p->part};
+    for (auto b : all) b->release();
+    if (p->h_part) cudaFreeHost(p->h_part);
+    delete p;
+}
+
+} // extern "C"
+
+// out[i] = 1/(leaves[i] - alpha) for the 2n leaves: two Montgomery-trick levels, then one inversion per group
+__global__ void k_frb_up2(const fr *__restrict__ in, uint32_t n, fr *__restrict__ pre, fr *__restrict__ tot) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lo = g * FRB;
+    if (lo >= n) return;
+    const uint32_t hi = min(n, lo + FRB);
+    fr acc = fr_one();
+    for (uint32_t i = lo; i < hi; i++) {
+        fr_store(&pre[i], acc);
+        acc = fr_mul(acc, fr_load(&in[i]));
+    }
+    fr_store(&tot[g], fr_inv(acc)); // top level: invert the group product directly
+}
+__global__ void k_frb_down2(fr *__restrict__ inout, uint32_t n, const fr *__restrict__ pre, const fr *__restrict__ tot_inv) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lo = g * FRB;
+    if (lo >= n) return;
+    const uint32_t hi = min(n, lo + FRB);
+    fr inv = fr_load(&tot_inv[g]);
+    for (uint32_t i = hi; i-- > lo;) {
+        const fr v = fr_load(&inout[i]);
+        fr_store(&inout[i], fr_mul(inv, fr_load(&pre[i])));
+        if (i > lo) inv = fr_mul(inv, v);
+    }
+}
+
+static int denominators(dvp_prover *p, const fr &alpha) {
+    cudaStream_t st = p->ctx->stream;
+    const uint32_t n2 = p->dom->n2;
+    const uint32_t ng = cdivp(n2, FRB), ng2 = cdivp(ng, FRB);
+    const fr *leaves = p->dom->leaves.as<fr>();
+    k_frb_up<<<cdivp(ng, 128), 128, 0, st>>>(leaves, alpha, n2, p->pre.as<fr>(), p->tot.as<fr>());
+    k_frb_up2<<<cdivp(ng2, 64), 64, 0, st>>>(p->tot.as<fr>(), ng, p->pre2.as<fr>(), p->tot2.as<fr>());
+    k_frb_down2<<<cdivp(ng2, 64), 64, 0, st>>>(p->tot.as<fr>(), ng, p->pre2.as<fr>(), p->tot2.as<fr>());
+    k_frb_down<<<cdivp(ng, 128), 128, 0, st>>>(leaves, alpha, n2, p->pre.as<fr>(), p->tot.as<fr>(), p->dinv.as<fr>());
+    CKP(cudaGetLastError());
+    return 0;
+}
+
+static void fr_to_le29_host(uint8_t out[29], const fr &a) {
+    uint32_t c[8];
+    fr_to_canonical(c, a);
+    for (int i = 0; i < 29; i++) out[i] = (uint8_t)(c[i >> 2] >> (8 * (i & 3)));
+}
+
+// Proof::prove (proving.rs:426-688) with everything resident on the device.
+// stages (optional, host, 13 n x 4 u64): a b c i a' b' c' i' q k_a k_b k_r(2n)
+static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64_t *priv, size_t npriv,
+                      uint8_t proof[118], uint64_t *stages) {
+    dvp_ctx *ctx = p->ctx;
+    dvp_domain *d = p->dom;
+    dvp_r1cs *r = p->r1cs;
+    cudaStream_t st = ctx->stream;
+    const size_t n = d->n;
+    if (k != r->dev.k) return DVP_ERR_BAD_ARG;                    // assert_eq!(inst.num_public_inputs, ..) proving.rs:361
+    if (1 + k + npriv != r->nwires) return DVP_ERR_LENGTH_MISMATCH; // msm(assignment, g_m) length check, curve.rs:142
+    CKP(cudaSetDevice(ctx->device));
+    cudaEvent_t ev[8];
+    for (auto &e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], st);
+    fr *V = p->vec.as<fr>();
+    fr *a = V, *b = V + n, *c = V + 2 * n, *iv = V + 3 * n, *a2 = V + 4 * n, *b2 = V + 5 * n, *c2 = V + 6 * n,
+       *i2 = V + 7 * n, *q = V + 8 * n, *ks = V + 9 * n;
+    // assignment = [1, public.., private..]  (proving.rs:449-452)
+    fr *w = p->wit.as<fr>();
+    const fr one = fr_one();
+    CKP(cudaMemcpyAsync(w, &one, 32, cudaMemcpyHostToDevice, st));
+    if (k) CKP(cudaMemcpyAsync(w + 1, pub, k * 32, cudaMemcpyHostToDevice, st));
+    if (npriv) CKP(cudaMemcpyAsync(w + 1 + k, priv, npriv * 32, cudaMemcpyHostToDevice, st));
+    int64_t bad = -1;
+    int rc = r1cs_eval_device(r, d, w, a, b, c, iv, &bad);
+    if (rc) return rc;
+    cudaEventRecord(ev[1], st);
+    // commitment to the witness, proving.rs:462-463
+    AffPt msm_gm, msm_q, kzg;
+    if ((rc = ctx->msm.run(ctx->slots[p->slot_gm].buf.as<AffPt>(), (const uint32_t *)w, r->nwires, &msm_gm))) return rc;
+    cudaEventRecord(ev[2], st);
+    // extend a, b, c to D' (i' in closed form), proving.rs:475-482
+    CKP(cudaMemcpyAsync(a2, a, 3 * n * sizeof(fr), cudaMemcpyDeviceToDevice, st));
+    if ((rc = extend_device(d, a2, 3, n))) return rc;
+    k_ivals_ext<<<cdivp(n, 128), 128, 0, st>>>(w, (uint32_t)k, d->leaves.as<fr>(), (uint32_t)n, i2);
+    if (stages) {
+        CKP(cudaMemcpyAsync(stages, V, 8 * n * 32, cudaMemcpyDeviceToHost, st));
+        CKP(cudaStreamSynchronize(st));
+    }
+    // r' (overwrites c') and q, proving.rs:492-509
+    k_quotient<<<cdivp(n, 128), 128, 0, st>>>(a2, b2, c2, i2, d->z_vals2inv.as<fr>(), (uint32_t)n, q);
+    CKP(cudaGetLastError());
+    cudaEventRecord(ev[3], st);
+    if ((rc = ctx->msm.run(ctx->slots[p->slot_gq].buf.as<AffPt>(), (const uint32_t *)q, n, &msm_q))) return rc;
+    cudaEventRecord(ev[4], st);
+    const AffPt commit = host::aff_add(msm_q, msm_gm); // proving.rs:515
+    host::encode30(proof, commit);
+    // Fiat-Shamir challenge, proving.rs:517-558
+    std::vector<uint8_t> pub29(29 * k + 1);
+    std::vector<fr> pubv(k);
+    for (size_t j = 0; j < k; j++) {
+        memcpy(pubv[j].v, pub + 4 * j, 32);
+        fr_to_le29_host(&pub29[29 * j], pubv[j]);
+    }
+    uint8_t al[32];
+    if (!host::transcript_alpha(proof, pub29.data(), k, al)) return DVP_ERR_BAD_ARG;
+    uint32_t alc[8];
+    memcpy(alc, al, 32);
+    const fr alpha = fr_from_canonical(alc);
+    // 1/(leaf - alpha) for all 2n leaves; a zero denominator means alpha is in D u D'
+    if ((rc = denominators(p, alpha))) return rc;
+    // a0, b0 by barycentric evaluation, i0 by Horner (ec_fft.rs:455-491, srs.rs:412)
+    const int nblk = 592;
+    k_bary_partial<<<nblk, 256, 0, st>>>(a, b, d->bar_wts.as<fr>(), p->dinv.as<fr>(), (uint32_t)n, p->part.as<fr>());
+    CKP(cudaGetLastError());
+    CKP(cudaMemcpyAsync(p->h_part, p->part.p, 2 * nblk * sizeof(fr), cudaMemcpyDeviceToHost, st));
+    CKP(cudaStreamSynchronize(st));
+    const fr za = vanish_at_host(d, 0, alpha);
+    if (fr_is_zero(za) || fr_is_zero(vanish_at_host(d, 1, alpha))) return DVP_ERR_ALPHA_IN_DOMAIN;
+    fr sa = fr_zero(), sb = fr_zero();
+    const fr *hp = (const fr *)p->h_part;
+    for (int i = 0; i < nblk; i++) {
+        sa = fr_add(sa, hp[2 * i]);
+        sb = fr_add(sb, hp[2 * i + 1]);
+    }
+    const fr a0 = fr_mul(sa, za), b0 = fr_mul(sb, za);
+    fr i0 = fr_zero(), pw = fr_one();
+    for (size_t j = 0; j < k; j++) {
+        i0 = fr_add(i0, fr_mul(pubv[j], pw));
+        pw = fr_mul(pw, alpha);
+    }
+    const fr r0 = fr_sub(fr_mul(a0, b0), i0);
+    k_kscalars<<<cdivp(n, 128), 128, 0, st>>>(a, b, iv, c2, p->dinv.as<fr>(), a0, b0, r0, (uint32_t)n, ks);
+    CKP(cudaGetLastError());
+    cudaEventRecord(ev[5], st);
+    if (stages) {
+        CKP(cudaMemcpyAsync(stages + 8 * n * 4, q, 5 * n * 32, cudaMemcpyDeviceToHost, st));
+        CKP(cudaStreamSynchronize(st));
+    }
+    if ((rc = ctx->msm.run(ctx->slots[p->slot_gk].buf.as<AffPt>(), (const uint32_t *)ks, 4 * n, &kzg))) return rc;
+    cudaEventRecord(ev[6], st);
+    cudaEventSynchronize(ev[6]);
+    host::encode30(proof + 30, kzg);
+    fr_to_le29_host(proof + 60, a0);
+    fr_to_le29_host(proof + 89, b0);
+    for (int i = 0; i < 6; i++) cudaEventElapsedTime(&p->ms[i], ev[i], ev[i + 1]);
+    for (auto &e : ev) cudaEventDestroy(e);
+    return DVP_OK;
+}
+
+extern "C" {
+int dvp_prove(dvp_prover *p, const uint64_t *public_mont, size_t k, const uint64_t *private_mont, size_t npriv,
+              uint8_t proof118[118]) {
+    if (!p || !proof118 || (!public_mont && k) || (!private_mont && npriv)) return DVP_ERR_BAD_ARG;
+    return prove_impl(p, public_mont, k, private_mont, npriv, proof118, nullptr);
+}
+int dvp_prove_stages(dvp_prover *p, const uint64_t *public_mont, size_t k, const uint64_t *private_mont, size_t npriv,
+                     uint8_t proof118[118], uint64_t *stages) {
+    if (!p || !proof118 || !stages || (!public_mont && k) || (!private_mont && npriv)) return DVP_ERR_BAD_ARG;
+    return prove_impl(p, public_mont, k, private_mont, npriv, proof118, stages);
+}
+// stage times of the last prove in ms: r1cs, msm g_m, extend+quotient, msm g_q, challenge+K scalars, msm g_k
+int dvp_prove_last_times(dvp_prover *p, float ms[6]) {
+    if (!p || !ms) return DVP_ERR_BAD_ARG;
+    for (int i = 0; i < 6; i++) ms[i] = p->ms[i];
+    return DVP_OK;
+}
+}

@@ -83,6 +83,24 @@ def lib():
         L.dvp_microbench.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
         L.dvp_hostcheck_op.argtypes = [i32, vp, vp, vp, sz]
         L.dvp_pipebench.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_double)]
+        L.dvp_domain_create.argtypes = [vp, C.c_uint, C.POINTER(vp)]
+        L.dvp_domain_destroy.argtypes = [vp]
+        L.dvp_domain_destroy.restype = None
+        L.dvp_domain_leaves.argtypes = [vp, vp]
+        L.dvp_domain_precomputes.argtypes = [vp, vp, vp]
+        L.dvp_domain_vanish_at.argtypes = [vp, i32, vp, vp]
+        L.dvp_ecfft_extend.argtypes = [vp, vp, vp, i32]
+        L.dvp_ecfft_extend_device.argtypes = [vp, vp, i32]
+        L.dvp_r1cs_load.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp, sz, C.POINTER(vp)]
+        L.dvp_r1cs_destroy.argtypes = [vp]
+        L.dvp_r1cs_destroy.restype = None
+        L.dvp_r1cs_eval.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int64)]
+        L.dvp_prover_create.argtypes = [vp, vp, vp, i32, i32, i32, C.POINTER(vp)]
+        L.dvp_prover_destroy.argtypes = [vp]
+        L.dvp_prover_destroy.restype = None
+        L.dvp_prove.argtypes = [vp, vp, sz, vp, sz, vp]
+        L.dvp_prove_stages.argtypes = [vp, vp, sz, vp, sz, vp, vp]
+        L.dvp_prove_last_times.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -258,3 +276,136 @@ def random_fr_mont(n, seed):
             eq &= raw[:, k] == np.uint64(p_limbs[k])
         out = np.concatenate([out, raw[lt]])
     return np.ascontiguousarray(out[:n])
+
+
+class Domain:
+    """D / D' of the 2n-leaf ECFFT tree (build_sect_ecfft_tree + get_both_domains, ec_fft.rs:93-239)."""
+
+    def __init__(self, ctx, log2_2n):
+        self.ctx = ctx
+        self.n2 = 1 << log2_2n
+        self.n = self.n2 >> 1
+        self._h = C.c_void_p()
+        _ck(lib().dvp_domain_create(ctx._h, log2_2n, C.byref(self._h)), "dvp_domain_create")
+
+    def close(self):
+        if self._h:
+            lib().dvp_domain_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def leaves(self):
+        out = np.zeros((self.n2, 4), dtype=np.uint64)
+        _ck(lib().dvp_domain_leaves(self._h, _ptr(out)))
+        return out
+
+    def precomputes(self):
+        z, w = np.zeros((self.n, 4), dtype=np.uint64), np.zeros((self.n, 4), dtype=np.uint64)
+        _ck(lib().dvp_domain_precomputes(self._h, _ptr(z), _ptr(w)))
+        return z, w
+
+    def vanish_at(self, shift, x_mont):
+        x = np.ascontiguousarray(x_mont, dtype=np.uint64).reshape(4)
+        out = np.zeros(4, dtype=np.uint64)
+        _ck(lib().dvp_domain_vanish_at(self._h, shift, _ptr(x), _ptr(out)))
+        return out
+
+    def extend(self, evals_mont):
+        """tree2n.extend(evals, Moiety::S1) for one (n,4) or several (p,n,4) vectors (proving.rs:410-422)."""
+        a = np.ascontiguousarray(evals_mont, dtype=np.uint64)
+        npoly = 1 if a.ndim == 2 else a.shape[0]
+        if a.size != npoly * self.n * 4:
+            raise DvpError(5, "extend: evals.len() != n")
+        out = np.zeros_like(a)
+        _ck(lib().dvp_ecfft_extend(self._h, _ptr(a), _ptr(out), npoly), "dvp_ecfft_extend")
+        return out
+
+
+class R1CSInstance:
+    """R1CSInstance (gnark_r1cs.rs:261-267) resident on the device, CSR per matrix in dump order."""
+
+    def __init__(self, ctx, nrows, num_public, nwires, rowptr, wire, coeff, coeffs_mont):
+        self.ctx = ctx
+        self.nrows, self.k, self.nwires = nrows, num_public, nwires
+        self.n = 2
+        while self.n < nrows:
+            self.n *= 2
+        self._keep = [[np.ascontiguousarray(x, dtype=np.uint32) for x in grp] for grp in (rowptr, wire, coeff)]
+        cm = np.ascontiguousarray(coeffs_mont, dtype=np.uint64).reshape(-1, 4)
+        arrs = []
+        for grp in self._keep:
+            arr = (C.c_void_p * 3)(*[x.ctypes.data for x in grp])
+            arrs.append(arr)
+        self._h = C.c_void_p()
+        _ck(lib().dvp_r1cs_load(ctx._h, nrows, num_public, nwires, arrs[0], arrs[1], arrs[2], _ptr(cm), cm.shape[0],
+                                C.byref(self._h)), "dvp_r1cs_load")
+
+    def close(self):
+        if self._h:
+            lib().dvp_r1cs_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def eval(self, dom, assignment_mont):
+        """get_matrix_evaluations_from_witness (proving.rs:348-403) -> (a, b, c, i); raises on a bad row."""
+        w = np.ascontiguousarray(assignment_mont, dtype=np.uint64).reshape(-1, 4)
+        if w.shape[0] != self.nwires:
+            raise DvpError(5, "assignment length")
+        outs = [np.zeros((self.n, 4), dtype=np.uint64) for _ in range(4)]
+        bad = C.c_int64(-1)
+        rc = lib().dvp_r1cs_eval(self._h, dom._h, _ptr(w), *[_ptr(o) for o in outs], C.byref(bad))
+        if rc != OK:
+            raise DvpError(rc, f"constraint {bad.value}")
+        return outs
+
+
+class Prover:
+    """Proof::prove with resident artifacts: SRS slots g_m / g_q / g_k, domain, R1CS (proving.rs:426-688)."""
+
+    def __init__(self, ctx, dom, r1cs, slot_gm=0, slot_gq=1, slot_gk=2):
+        self.ctx, self.dom, self.r1cs = ctx, dom, r1cs
+        self._h = C.c_void_p()
+        _ck(lib().dvp_prover_create(ctx._h, dom._h, r1cs._h, slot_gm, slot_gq, slot_gk, C.byref(self._h)),
+            "dvp_prover_create")
+
+    def close(self):
+        if self._h:
+            lib().dvp_prover_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def prove(self, public_mont, private_mont, want_stages=False):
+        pub = np.ascontiguousarray(public_mont, dtype=np.uint64).reshape(-1, 4)
+        priv = np.ascontiguousarray(private_mont, dtype=np.uint64).reshape(-1, 4)
+        proof = np.zeros(118, dtype=np.uint8)
+        if want_stages:
+            st = np.zeros((13 * self.dom.n, 4), dtype=np.uint64)
+            rc = lib().dvp_prove_stages(self._h, _ptr(pub), pub.shape[0], _ptr(priv), priv.shape[0], _ptr(proof), _ptr(st))
+        else:
+            st = None
+            rc = lib().dvp_prove(self._h, _ptr(pub), pub.shape[0], _ptr(priv), priv.shape[0], _ptr(proof))
+        _ck(rc, "dvp_prove")
+        return (proof.tobytes(), st) if want_stages else proof.tobytes()
+
+    def last_times(self):
+        ms = np.zeros(6, dtype=np.float32)
+        _ck(lib().dvp_prove_last_times(self._h, _ptr(ms)))
+        return dict(zip(["r1cs", "msm_gm", "extend_quotient", "msm_gq", "challenge_kscalars", "msm_gk"], ms.tolist()))
+
+
+def proof_to_bits(proof118):
+    """Proof::to_bits (proving.rs:691-718): 240 + 240 + 232 + 232 little-endian bits."""
+    bits = []
+    for lo, hi, nbits in ((0, 30, 240), (30, 60, 240), (60, 89, 232), (89, 118, 232)):
+        chunk = proof118[lo:hi]
+        bits += [(chunk[i // 8] >> (i % 8)) & 1 for i in range(nbits)]
+    return bits
+
+
+def proof_from_bits(bits):
+    """Proof::from_bits (proving.rs:721-770)."""
+    assert len(bits) == 944
+    out = bytearray()
+    pos = 0
+    for nbytes in (30, 30, 29, 29):
+        for _ in range(nbytes):
+            out.append(sum(bits[pos + i] << i for i in range(8)))
+            pos += 8
+    return bytes(out)

@@ -97,6 +97,59 @@ int dvp_selftest_op(dvp_ctx *ctx, int op, const void *a, const void *b, void *ou
 /* Integer-pipe microbenchmark: op 0 gf_mul chain, 1 gf_sqr chain, 2 fr_mul chain; returns ops per second. */
 int dvp_microbench(dvp_ctx *ctx, int op, int iters, double *ops_per_sec);
 
+/*
+ * Evaluation domain of the prover: D = even leaves, D' = odd leaves of the 2n-leaf ECFFT tree built from
+ * the constants at src/ec_fft.rs:205-229 (build_sect_ecfft_tree / get_both_domains, ec_fft.rs:93-239).
+ * Also holds the extend matrices (FFTree.decompose/recombine_matrices) and the domain-specific prover
+ * precomputes bar_wts and z_vals2inv (prover_prepares_precomputes, src/proving.rs:225-325), all on device.
+ */
+typedef struct dvp_domain dvp_domain;
+int dvp_domain_create(dvp_ctx *ctx, unsigned log2_2n, dvp_domain **out);
+void dvp_domain_destroy(dvp_domain *dom);
+int dvp_domain_leaves(dvp_domain *dom, uint64_t *leaves_mont /* 2n x 4 */);
+int dvp_domain_precomputes(dvp_domain *dom, uint64_t *z_vals2inv /* n x 4 or NULL */, uint64_t *bar_wts /* n x 4 or NULL */);
+/* z_poly.evaluate(x) for the vanishing polynomial of D (shift 0) or D' (shift 1) (ec_fft.rs:475) */
+int dvp_domain_vanish_at(dvp_domain *dom, int shift, const uint64_t x_mont[4], uint64_t out_mont[4]);
+
+/* FFTree::extend(evals, Moiety::S1) (src/proving.rs:410-422): npoly vectors of n Fr on D -> values on D'. */
+int dvp_ecfft_extend(dvp_domain *dom, const uint64_t *in, uint64_t *out, int npoly);
+/* In place on device memory (npoly x n x 32 bytes, contiguous). */
+int dvp_ecfft_extend_device(dvp_domain *dom, void *d_data, int npoly);
+
+/*
+ * R1CS in the dump's own order (src/gnark_r1cs.rs:1-20): three CSR matrices L, R, O over one coefficient
+ * table (Montgomery limbs).  nrows is padded to n = next_power_of_two (gnark_r1cs.rs:291); the
+ * Vandermonde block of update_to_include_vandermode_matrix_d (gnark_r1cs.rs:333-386) is applied on the fly.
+ */
+typedef struct dvp_r1cs dvp_r1cs;
+int dvp_r1cs_load(dvp_ctx *ctx, size_t nrows, size_t num_public, size_t nwires, const uint32_t *const rowptr[3],
+                  const uint32_t *const wire[3], const uint32_t *const coeff[3], const uint64_t *coeffs_mont,
+                  size_t ncoeffs, dvp_r1cs **out);
+void dvp_r1cs_destroy(dvp_r1cs *r1cs);
+/* get_matrix_evaluations_from_witness (src/proving.rs:348-403): assignment = [1, public.., private..] (nwires x 4);
+ * a, b, c, i: n x 4 each.  DVP_ERR_UNSATISFIED and *first_bad_row on a row with a*b != c + i. */
+int dvp_r1cs_eval(dvp_r1cs *r1cs, dvp_domain *dom, const uint64_t *assignment, uint64_t *a, uint64_t *b, uint64_t *c,
+                  uint64_t *i, int64_t *first_bad_row);
+
+/*
+ * Proof::prove(cache_dir, public_inputs, private_inputs) (src/proving.rs:426-688) with the artifacts resident:
+ * SRS slots hold g_m (nwires points), g_q (n) and g_k_0|g_k_1|g_k_2 (4n).
+ * proof118 = commit_p (30) | kzg_k (30) | a0 (29 bytes LE) | b0 (29 bytes LE)  -- the fields of `Proof`
+ * (proving.rs:40-50; FrBits bit i = bit i of the little-endian bytes).
+ */
+typedef struct dvp_prover dvp_prover;
+int dvp_prover_create(dvp_ctx *ctx, dvp_domain *dom, dvp_r1cs *r1cs, int slot_gm, int slot_gq, int slot_gk,
+                      dvp_prover **out);
+void dvp_prover_destroy(dvp_prover *p);
+int dvp_prove(dvp_prover *p, const uint64_t *public_mont, size_t k, const uint64_t *private_mont, size_t npriv,
+              uint8_t proof118[118]);
+/* Same, also returning the intermediate vectors for parity tests:
+ * stages = 13 n x 4 u64: a b c i a' b' c' i' q k_a k_b k_r(2n). */
+int dvp_prove_stages(dvp_prover *p, const uint64_t *public_mont, size_t k, const uint64_t *private_mont, size_t npriv,
+                     uint8_t proof118[118], uint64_t *stages);
+/* ms per stage of the last prove: r1cs, msm g_m, extend+quotient, msm g_q, challenge+K scalars, msm g_k */
+int dvp_prove_last_times(dvp_prover *p, float ms[6]);
+
 /* Raw integer-pipe issue rates (thread-instructions per second over the whole GPU): the roofline
  * denominators for the field kernels.  mode: 0 IMAD.WIDE  1 LOP3  2 IMAD  3 IMAD.WIDE:LOP3 = 1:2  4 SHF  5 IADD */
 int dvp_pipebench(dvp_ctx *ctx, int mode, int iters, int blocks_per_sm, double *instr_per_sec);

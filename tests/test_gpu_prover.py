@@ -1,0 +1,164 @@
+"""Fr-side hot path on the device against the oracle: domain, extend, R1CS rows, full prove.
+
+Mirrors the reference's tests: leaf order (ec_fft.rs:633-645), extend == interpolation (ec_fft.rs:883-907),
+and setup -> prove -> verify on the toy circuit (dvsnark_test.rs:131-180) with byte-equal proofs."""
+import random
+
+import numpy as np
+import pytest
+
+import dvpari
+from test_oracle_protocol import random_r1cs
+
+pytestmark = pytest.mark.gpu
+P = dvpari.P
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = dvpari.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("log_n2", [2, 3, 5, 8, 13])
+def test_domain_and_precomputes(ctx, oracle, log_n2):
+    O = oracle
+    od = O.Domain(log_n2)
+    gd = dvpari.Domain(ctx, log_n2)
+    assert gd.leaves().tobytes() == od.leaves_mont().tobytes()
+    z, w = gd.precomputes()
+    # bar_wts = 1/Z'_D(d_i), z_vals2inv = 1/Z_D(d'_i)
+    want_w = od.vanish_derivative_on_roots_mont(0)
+    want_z = od.vanish_on_other_mont(0)
+    O.lib().fr_batch_inv(want_w.ctypes.data, want_w.shape[0])
+    O.lib().fr_batch_inv(want_z.ctypes.data, want_z.shape[0])
+    assert w.tobytes() == want_w.tobytes()
+    assert z.tobytes() == want_z.tobytes()
+    x = 0x1234567890ABCDEF1234567890ABCDEF
+    for shift in (0, 1):
+        got = dvpari.fr_from_mont(gd.vanish_at(shift, dvpari.fr_to_mont([x])[0]))[0]
+        assert got == od.vanish_at(shift, x)
+    gd.close()
+
+
+@pytest.mark.parametrize("log_n2", [2, 4, 9, 15])
+def test_extend_matches_oracle(ctx, oracle, log_n2):
+    O = oracle
+    od = O.Domain(log_n2)
+    gd = dvpari.Domain(ctx, log_n2)
+    n = od.n
+    ev = np.stack([dvpari.random_fr_mont(n, 300 + log_n2 + p) for p in range(3)])
+    got = gd.extend(ev)
+    for p in range(3):
+        assert got[p].tobytes() == od.extend_mont(ev[p]).tobytes()
+    # zeros and a constant stay what they are
+    const = np.tile(dvpari.fr_to_mont([7]), (n, 1))
+    assert gd.extend(const).tobytes() == const.tobytes()
+    with pytest.raises(dvpari.DvpError):
+        gd.extend(ev[0][: n // 2])
+    gd.close()
+
+
+def _load_circuit(ctx, r1cs):
+    return dvpari.R1CSInstance(ctx, r1cs.nrows, r1cs.k, r1cs.nwires, r1cs.rowptr, r1cs.wire, r1cs.coeff, r1cs.coeffs)
+
+
+def test_r1cs_rows_match_oracle(ctx, oracle):
+    O = oracle
+    rnd = random.Random(41)
+    r1cs, w = random_r1cs(O, rnd, 200, 1 + 2 + 230, 2)
+    od = O.Domain(r1cs.n.bit_length())
+    gd = dvpari.Domain(ctx, r1cs.n.bit_length())
+    inst = _load_circuit(ctx, r1cs)
+    wm = O.mont_array(w)
+    want, bad = O.r1cs_eval(r1cs, od, wm)
+    assert bad == -1
+    got = inst.eval(gd, wm)
+    for g, x in zip(got, want):
+        assert g.tobytes() == x.tobytes()
+    # an unsatisfied row is reported with its index (reference: assert_eq! panic, proving.rs:389-395)
+    w_bad = list(w)
+    w_bad[1 + 2 + 30 + 17] = (w_bad[1 + 2 + 30 + 17] + 1) % P
+    _, want_bad = O.r1cs_eval(r1cs, od, O.mont_array(w_bad))
+    with pytest.raises(dvpari.DvpError) as e:
+        inst.eval(gd, O.mont_array(w_bad))
+    assert e.value.code == 6 and str(want_bad) in str(e.value)
+    inst.close()
+    gd.close()
+
+
+def _prove_both(ctx, O, r1cs, w, td):
+    log_n2 = r1cs.n.bit_length()
+    od = O.Domain(log_n2)
+    srs = O.Srs(r1cs, od, td)
+    wm = O.mont_array(w)
+    want_proof, rc, want_st = O.prove(r1cs, od, srs, wm, want_stages=True)
+    assert rc == 0
+    gd = dvpari.Domain(ctx, log_n2)
+    inst = _load_circuit(ctx, r1cs)
+    ctx.srs_load(0, srs.g_m30())
+    ctx.srs_load(1, srs.g_q30())
+    ctx.srs_load(2, srs.g_k30())
+    prover = dvpari.Prover(ctx, gd, inst, 0, 1, 2)
+    k = r1cs.k
+    got_proof, got_st = prover.prove(wm[1:1 + k], wm[1 + k:], want_stages=True)
+    n = r1cs.n
+    names = ["a", "b", "c", "i", "a'", "b'", "c'", "i'", "q", "k_a", "k_b", "k_r", "k_r(2)"]
+    for s, name in enumerate(names):
+        assert got_st[s * n:(s + 1) * n].tobytes() == want_st[s * n:(s + 1) * n].tobytes(), name
+    assert got_proof == want_proof
+    assert O.verify(td, w[1:1 + k], got_proof)
+    prover.close()
+    inst.close()
+    gd.close()
+    return got_proof
+
+
+def test_toy_prove_is_bit_exact_and_verifies(ctx, oracle):
+    """dvsnark_test.rs:131-180 through the C ABI: same 118 bytes as the oracle, verifier accepts."""
+    O = oracle
+    r1cs, pub, priv = O.toy_r1cs()
+    rnd = random.Random(43)
+    td = O.trapdoor(rnd.randrange(1, P), rnd.randrange(1, P), rnd.randrange(1, P))
+    proof = _prove_both(ctx, O, r1cs, [1] + pub + priv, td)
+    assert dvpari.proof_from_bits(dvpari.proof_to_bits(proof)) == proof
+    assert len(dvpari.proof_to_bits(proof)) == 944
+
+
+@pytest.mark.parametrize("nrows,k", [(13, 2), (200, 3), (1000, 2)])
+def test_random_circuit_prove_is_bit_exact(ctx, oracle, nrows, k):
+    O = oracle
+    rnd = random.Random(500 + nrows)
+    r1cs, w = random_r1cs(O, rnd, nrows, 1 + k + nrows + 7, k)
+    td = O.trapdoor(rnd.randrange(1, P), rnd.randrange(1, P), rnd.randrange(1, P))
+    _prove_both(ctx, O, r1cs, w, td)
+
+
+def test_prove_rejects_bad_witness_and_lengths(ctx, oracle):
+    O = oracle
+    r1cs, pub, priv = O.toy_r1cs()
+    td = O.trapdoor(3, 5, 7)
+    od = O.Domain(4)
+    srs = O.Srs(r1cs, od, td)
+    gd = dvpari.Domain(ctx, 4)
+    inst = _load_circuit(ctx, r1cs)
+    ctx.srs_load(0, srs.g_m30())
+    ctx.srs_load(1, srs.g_q30())
+    ctx.srs_load(2, srs.g_k30())
+    prover = dvpari.Prover(ctx, gd, inst, 0, 1, 2)
+    bad_priv = list(priv)
+    bad_priv[0] += 1
+    with pytest.raises(dvpari.DvpError) as e:
+        prover.prove(O.mont_array(pub), O.mont_array(bad_priv))
+    assert e.value.code == 6
+    with pytest.raises(dvpari.DvpError) as e:
+        prover.prove(O.mont_array(pub), O.mont_array(priv[:-1]))
+    assert e.value.code == 5
+    ctx.srs_load(1, srs.g_q30()[:4])
+    with pytest.raises(dvpari.DvpError) as e:
+        dvpari.Prover(ctx, gd, inst, 0, 1, 2)
+    assert e.value.code == 5
+    prover.close()
+    inst.close()
+    gd.close()
