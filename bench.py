@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""Headline benchmark: sect233k1 MSM points/s at 2^20 points per GPU (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm on host cores
+
+A step = one multi_scalar_mul (curve.rs:141-158) of 2^LG uniformly random Fr scalars against 2^LG
+resident SRS points, per GPU.  With N > 1 (torchrun) every rank owns a contiguous point range of the
+N*2^LG-point MSM (weak scaling); the 30-byte partial sums are all-gathered over NCCL and folded.
+`value` times the device-resident call (scalars already in HBM); `e2e` times the host-buffer C-ABI
+call dvp_msm (scalars copied from the host inside the timed region, 30-byte result back).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "dv-pari_b200"))
+
+METRIC = "sect233k1 MSM points/s"
+UNIT = "points/s"
+# static facts about the dominant kernel (k_pass2, one batched affine addition per task), see DESIGN.md
+PASS2_BYTES_PER_ADD = 128 + 32 + 16 + 64  # two points in, prefix product, task descriptor, one point out
+PASS2_ALU_INSTR_PER_ADD = 3184             # LOP3+SHF+ISETP+SEL thread-instructions per addition (cuobjdump -sass count of k_pass2)
+ALU_PIPE_PEAK = 1.84e13                    # measured LOP3 thread-instr/s on this pool's B200 (profiles/r1_pipe_rates.json)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) > 8:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_msm_sample(ctx_or_none, lg_sample, seed, nthreads=0):
+    """The oracle's restatement of the reference algorithm (per-point scalar multiplication + sum,
+    curve.rs:141-158) on host cores, on a bounded sample.  Returns (points/s, cores, seconds, result)."""
+    from oracle import oracle as O
+    import dvpari
+
+    n = 1 << lg_sample
+    sc = dvpari.random_fr_mont(n, seed)
+    if ctx_or_none is not None:
+        pts, bad = O.decode_batch(ctx_or_none.srs_read(0, 0, n))
+        assert bad < 0
+    else:
+        pts = O.mul_batch(O.generator(), dvpari.random_fr_mont(n, seed + 1))
+    cores = os.cpu_count() if nthreads <= 0 else nthreads
+    t0 = time.perf_counter()
+    res = O.msm(sc, pts, nthreads)
+    dt = time.perf_counter() - t0
+    return n / dt, cores, dt, O.pt_encode(res), sc
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    import __graft_entry__ as g
+
+    if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "all"])
+    lg_s = args.cpu_lg
+    for _ in range(args.warmup):
+        cpu_msm_sample(None, min(lg_s, 10), 11)
+    t0 = time.perf_counter()
+    tot = 0
+    for s in range(args.steps):
+        pps, cores, dt, _, _ = cpu_msm_sample(None, lg_s, 100 + s)
+        tot += 1 << lg_s
+    dt = time.perf_counter() - t0
+    v = tot / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 (GF(2^233) via PCLMULQDQ)", "data": "synthetic",
+        "config": {"workload": f"msm 2^{args.lg} points per GPU, sect233k1, uniform Fr scalars",
+                   "note": "C restatement of the reference algorithm (the Rust crate cannot be built offline); "
+                           f"each step is a 2^{lg_s}-point sample of the workload"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{args.steps} x 2^{lg_s} points, per-point wNAF scalar mul + sum, OpenMP all cores"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lg", type=int, default=20, help="log2 of the points per GPU")
+    ap.add_argument("--cpu-lg", type=int, default=17, help="log2 of the CPU-baseline sample")
+    ap.add_argument("--window-bits", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = dist_env()
+    import numpy as np
+    import torch
+
+    import dvpari
+
+    if not os.path.exists(dvpari.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = 1 << args.lg
+    ctx = dvpari.Context(local)
+    if args.window_bits:
+        ctx.set("msm_window_bits", args.window_bits)
+    # this rank's range of the N*2^lg-point SRS and of the scalar vector
+    ctx.srs_random(0, n, 0xD5A10002 + rank)
+    sc_host = dvpari.random_fr_mont(n, 0xD5A10001 + rank)
+    pinned = torch.empty((n, 4), dtype=torch.int64).pin_memory()
+    pinned.numpy().view(np.uint64)[:] = sc_host
+    sc_pinned = pinned.numpy().view(np.uint64)
+    d_sc = ctx.dev_alloc(n * 32)
+    ctx.dev_upload(d_sc, sc_host)
+
+    def fold(partial30):
+        """all-gather the 30-byte partial sums and fold them (CurvePoint::add, curve.rs:76-82)."""
+        if not use_dist:
+            return partial30
+        t = torch.frombuffer(bytearray(partial30) + b"\0\0", dtype=torch.uint8).cuda()
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        acc = bytes(outs[0].cpu().numpy()[:30])
+        for o in outs[1:]:
+            acc = ctx.point_add(acc, bytes(o.cpu().numpy()[:30]))
+        return acc
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = fn()
+        sync_all()
+        dt = time.perf_counter() - t0
+        if use_dist:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, out
+
+    step_dev = lambda: fold(ctx.multi_scalar_mul_device(d_sc, n, 0))
+    step_e2e = lambda: fold(ctx.multi_scalar_mul(sc_pinned, 0))
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dt, res_dev = timed(step_dev, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    dt_e2e, res_e2e = timed(step_e2e, args.steps)
+    assert res_dev == res_e2e, "device-resident and host-buffer calls disagree"
+
+    # one instrumented step: stage split, launches, the dominant kernel's duration (CUDA events in the library)
+    ctx.set("timing", 1)
+    ctx.multi_scalar_mul_device(d_sc, n, 0)
+    st = ctx.msm_stats()
+    ctx.set("timing", 0)
+
+    if rank == 0:
+        hbm_peak, which = peaks()
+        k_ms, k_adds = st["ms_pass2_round0"], st["adds_round0"]
+        achieved = k_adds * PASS2_BYTES_PER_ADD / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        alu = k_adds * PASS2_ALU_INSTR_PER_ADD / (k_ms * 1e-3) if k_ms > 0 else 0.0
+        # bounded CPU baseline on the same SRS points (first 2^cpu_lg of rank 0's range), checked against the GPU
+        lg_s = min(args.cpu_lg, args.lg)
+        pps, cores, cdt, cpu_res, sc_s = cpu_msm_sample(ctx, lg_s, 0xD5A10009)
+        gpu_res = ctx.multi_scalar_mul(sc_s, 0)
+        assert gpu_res == cpu_res, "GPU MSM differs from the CPU oracle on the baseline sample"
+        line = {
+            "metric": METRIC, "value": world * n * args.steps / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 (GF(2^233) carry-less arithmetic on 8x32-bit limbs; Fr 8x32-bit Montgomery)",
+            "data": "synthetic",
+            "config": {"workload": f"msm 2^{args.lg} points per GPU, sect233k1, uniform Fr scalars, SRS resident in HBM",
+                       "window_bits": st["window_bits"], "windows": st["windows"],
+                       "rounds": [st["rounds_main"], st["rounds_a"], st["rounds_b"]],
+                       "l2": "per-step working set (sort keys, ping-pong point buffers, prefix products: >1 GB at 2^20) exceeds the 126 MB L2",
+                       "parallelism": f"point-range sharding x{world}, NCCL all-gather of 30-byte partial sums" if world > 1 else "single GPU",
+                       "stage_ms": {"recode_sort": st["ms_recode_sort"], "accumulate": st["ms_accumulate"],
+                                    "reduce": st["ms_reduce"], "tail": st["ms_tail"]}},
+            "e2e": {"value": world * n * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": n * 32,
+                    "d2h_bytes_per_step": 30 + st["windows"] * st["window_bits"] * 64, "ms_per_step": 1e3 * dt_e2e / args.steps},
+            "gpu_launches": int(st["launches"]) * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "k_pass2<indexed,16> (round 0 of the bucket accumulation)",
+                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": 1.826e9 if args.lg == 20 else None, "peak_source": which,
+                         "launch_ms": k_ms, "adds_per_launch": k_adds, "bytes_per_add": PASS2_BYTES_PER_ADD,
+                         "note": "integer-issue bound, not HBM bound: see int_issue"},
+            "int_issue": {"achieved": alu, "peak": ALU_PIPE_PEAK, "unit": "ALU-pipe thread-instr/s", "frac": alu / ALU_PIPE_PEAK,
+                          "instr_per_add": PASS2_ALU_INSTR_PER_ADD, "peak_source": "measured LOP3 issue rate, profiles/r1_pipe_rates.json"},
+            "cpu_baseline": {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"2^{lg_s} of the same SRS points, oracle k233_msm (per-point wNAF scalar mul + sum, curve.rs:141-158), "
+                                       f"{cdt:.2f} s, result equal to the GPU's"},
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.dev_free(d_sc)
+    ctx.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

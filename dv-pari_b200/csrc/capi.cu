@@ -53,6 +53,31 @@ __global__ void k_point_add30(const uint8_t *__restrict__ ab, uint8_t *__restric
     ok[0] = oa && ob;
 }
 
+// Synthetic SRS: uniformly random group elements by rejection sampling of the 233-bit encoding
+// (one w in four names an element of the group).  Deterministic in (seed, index).
+__device__ __forceinline__ uint64_t splitmix64(uint64_t &x) {
+    uint64_t z = (x += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__global__ void k_random_points(uint64_t seed, size_t n, AffPt *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t st = seed ^ (0xd1b54a32d192ed03ull * (i + 1));
+    AffPt p;
+    for (;;) {
+        uint8_t b[32];
+        for (int k = 0; k < 4; k++) {
+            const uint64_t v = splitmix64(st);
+            for (int j = 0; j < 8; j++) b[8 * k + j] = (uint8_t)(v >> (8 * j));
+        }
+        b[29] &= 0x01; // 233 bits
+        if (xsk233_decode_pt(b, p) && !pt_is_inf(p)) break;
+    }
+    pt_store(&out[i], p);
+}
+
 __global__ void k_selftest(int op, const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
                            uint32_t *__restrict__ out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,6 +290,19 @@ int dvp_srs_load(dvp_ctx *ctx, int slot, const uint8_t *pts30, size_t n, int64_t
     ctx->slots[slot].n = 0;
     return dvp_srs_append(ctx, slot, pts30, n, first_invalid);
 }
+int dvp_srs_random(dvp_ctx *ctx, int slot, size_t n, uint64_t seed) {
+    if (!slot_ok(ctx, slot)) return DVP_ERR_BAD_ARG;
+    CKC(cudaSetDevice(ctx->device));
+    SrsSlot &s = ctx->slots[slot];
+    int rc;
+    if ((rc = s.buf.reserve((n ? n : 1) * sizeof(AffPt))) != 0) return rc;
+    s.n = n;
+    if (!n) return DVP_OK;
+    k_random_points<<<cdivu(n, 64), 64, 0, ctx->stream>>>(seed, n, s.buf.as<AffPt>());
+    CKC(cudaGetLastError());
+    CKC(cudaStreamSynchronize(ctx->stream));
+    return DVP_OK;
+}
 int dvp_srs_size(dvp_ctx *ctx, int slot, size_t *n) {
     if (!slot_ok(ctx, slot) || !n) return DVP_ERR_BAD_ARG;
     *n = ctx->slots[slot].n;
@@ -341,6 +379,8 @@ int dvp_msm_last_stats(dvp_ctx *ctx, dvp_msm_stats *out) {
     out->ms_accumulate = s.ms_accumulate;
     out->ms_reduce = s.ms_reduce;
     out->ms_tail = s.ms_tail;
+    out->ms_pass2_round0 = s.ms_pass2_round0;
+    out->adds_round0 = s.adds_round0;
     return DVP_OK;
 }
 

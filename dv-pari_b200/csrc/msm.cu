@@ -506,6 +506,7 @@ int MsmEngine::init(cudaStream_t s) {
     stream = s;
     CK(cudaMallocHost(&h_info, 64));
     for (auto &e : ev) CK(cudaEventCreate(&e));
+    for (auto &e : ev_k) CK(cudaEventCreate(&e));
     return 0;
 }
 void MsmEngine::destroy() {
@@ -519,6 +520,8 @@ void MsmEngine::destroy() {
     h_info = h_pts = nullptr;
     h_pts_cap = 0;
     for (auto &e : ev)
+        if (e) cudaEventDestroy(e), e = nullptr;
+    for (auto &e : ev_k)
         if (e) cudaEventDestroy(e), e = nullptr;
 }
 
@@ -575,6 +578,8 @@ struct Tree {
         E.launches++;
         int rc = batch_inv(E.thr_total.as<gf>(), E.thr_inv.as<gf>(), nthr, 0);
         if (rc) return rc;
+        const bool mark = E.want_k;
+        if (mark) cudaEventRecord(E.ev_k[0], st);
         if (E.pass2_minb == 2)
             k_pass2<INDEXED, B, 2><<<nblk, 256, 0, st>>>(src, ent, E.info.as<uint32_t>(), E.desc.as<uint4>(),
                                                          E.prefix.as<gf>(), E.thr_inv.as<gf>(), dst);
@@ -584,6 +589,10 @@ struct Tree {
         else
             k_pass2<INDEXED, B, 1><<<nblk, 256, 0, st>>>(src, ent, E.info.as<uint32_t>(), E.desc.as<uint4>(),
                                                          E.prefix.as<gf>(), E.thr_inv.as<gf>(), dst);
+        if (mark) {
+            cudaEventRecord(E.ev_k[1], st);
+            E.want_k = false;
+        }
         k_copy_odd<INDEXED><<<cdiv(nseg, 256), 256, 0, st>>>(src, ent, in_start, len, out_start, nseg, dst);
         E.launches += 2;
         CK(cudaGetLastError());
@@ -616,6 +625,7 @@ struct Tree {
             CK(cudaMemcpyAsync(E.h_info, info, 16, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             maxlen = ((uint32_t *)E.h_info)[0];
+            E.h_round0_tasks = ((uint32_t *)E.h_info)[1];
         }
         int rounds = 0;
         while ((1ull << rounds) < maxlen) rounds++;
@@ -744,10 +754,15 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     stt.window_bits = c;
     stt.windows = W;
     // ---- bucket accumulation: one segment per (window, bucket)
+    want_k = timing;
     rc = tree.reduce(d_points, entries.as<uint32_t>(), d_start, d_len, nseg, total, 0, buckets.as<AffPt>(),
                      &stt.rounds_main);
     if (rc) return rc;
-    if (timing) cudaEventRecord(ev[2], st);
+    want_k = false;
+    if (timing) {
+        // info[1] still holds the task count of the last planned round; round 0's count is read separately
+        cudaEventRecord(ev[2], st);
+    }
 
     // ---- level A: row and column sums of each window's bucket matrix
     k_gen_level_a<<<cdiv(nent_a, 256), 256, 0, st>>>((uint32_t)W, nb, lm, ents2.as<uint32_t>());
@@ -787,6 +802,8 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         cudaEventElapsedTime(&stt.ms_accumulate, ev[1], ev[2]);
         cudaEventElapsedTime(&stt.ms_reduce, ev[2], ev[3]);
         cudaEventElapsedTime(&stt.ms_tail, ev[3], ev[4]);
+        if (stt.rounds_main > 0) cudaEventElapsedTime(&stt.ms_pass2_round0, ev_k[0], ev_k[1]);
+        stt.adds_round0 = h_round0_tasks;
     }
     last = stt;
     return 0;

@@ -20,6 +20,9 @@ struct MsmStats {
     int window_bits = 0, windows = 0, rounds_main = 0, rounds_a = 0, rounds_b = 0;
     unsigned long long launches = 0; // kernels launched by the last msm
     float ms_recode_sort = 0, ms_accumulate = 0, ms_reduce = 0, ms_tail = 0;
+    // the dominant kernel: pass 2 of round 0 of the bucket accumulation (one launch)
+    float ms_pass2_round0 = 0;
+    unsigned long long adds_round0 = 0, adds_total = 0;
 };
 
 struct MsmEngine {
@@ -31,6 +34,9 @@ struct MsmEngine {
     void *h_pts = nullptr;  // pinned, receives the per-bit partial sums
     size_t h_pts_cap = 0;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_k[2] = {nullptr, nullptr}; // around the dominant kernel
+    unsigned long long h_round0_tasks = 0;    // additions in round 0 of the last reduce with a read-back
+    bool want_k = false;                      // armed for the next pass-2 launch
     unsigned long long launches = 0;
     MsmStats last;
     int force_window_bits = 0; // 0 = choose from n

@@ -34,7 +34,8 @@ class DvpError(RuntimeError):
 class MsmStats(C.Structure):
     _fields_ = [("window_bits", C.c_int), ("windows", C.c_int), ("rounds_main", C.c_int), ("rounds_a", C.c_int),
                 ("rounds_b", C.c_int), ("launches", C.c_ulonglong), ("ms_recode_sort", C.c_float),
-                ("ms_accumulate", C.c_float), ("ms_reduce", C.c_float), ("ms_tail", C.c_float)]
+                ("ms_accumulate", C.c_float), ("ms_reduce", C.c_float), ("ms_tail", C.c_float),
+                ("ms_pass2_round0", C.c_float), ("adds_round0", C.c_ulonglong)]
 
 
 def build(force=False):
@@ -68,6 +69,7 @@ def lib():
         L.dvp_srs_load.argtypes = [vp, i32, vp, sz, C.POINTER(C.c_int64)]
         L.dvp_srs_append.argtypes = [vp, i32, vp, sz, C.POINTER(C.c_int64)]
         L.dvp_srs_size.argtypes = [vp, i32, C.POINTER(sz)]
+        L.dvp_srs_random.argtypes = [vp, i32, sz, C.c_uint64]
         L.dvp_srs_free.argtypes = [vp, i32]
         L.dvp_srs_read.argtypes = [vp, i32, sz, sz, vp]
         L.dvp_msm.argtypes = [vp, i32, sz, vp, sz, vp]
@@ -160,6 +162,10 @@ class Context:
         rc = fn(self._h, slot, _ptr(a), a.size // 30, C.byref(bad))
         if rc != OK:
             raise DvpError(rc, f"point {bad.value}")
+
+    def srs_random(self, slot, n, seed):
+        """n uniformly random group elements, deterministic in (seed, index)."""
+        _ck(lib().dvp_srs_random(self._h, slot, n, seed), "dvp_srs_random")
 
     def srs_size(self, slot):
         n = C.c_size_t()

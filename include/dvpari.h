@@ -43,6 +43,8 @@ typedef struct dvp_msm_stats {
     int window_bits, windows, rounds_main, rounds_a, rounds_b;
     unsigned long long launches; /* kernels launched by the last MSM on this context */
     float ms_recode_sort, ms_accumulate, ms_reduce, ms_tail; /* filled when timing is enabled */
+    float ms_pass2_round0;            /* the dominant kernel: one launch, CUDA events on the launching stream */
+    unsigned long long adds_round0;   /* affine additions that launch finished */
 } dvp_msm_stats;
 
 const char *dvp_strerror(int code);
@@ -64,6 +66,9 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value);
 int dvp_srs_load(dvp_ctx *ctx, int slot, const uint8_t *pts30, size_t n, int64_t *first_invalid);
 /* Append to a slot (g_k_0 | g_k_1 | g_k_2 concatenation, src/proving.rs:666-673). */
 int dvp_srs_append(dvp_ctx *ctx, int slot, const uint8_t *pts30, size_t n, int64_t *first_invalid);
+/* Fill a slot with n uniformly random group elements, deterministic in (seed, index): synthetic SRS
+ * for benchmarks and full-size tests (read them back with dvp_srs_read). */
+int dvp_srs_random(dvp_ctx *ctx, int slot, size_t n, uint64_t seed);
 int dvp_srs_size(dvp_ctx *ctx, int slot, size_t *n);
 int dvp_srs_free(dvp_ctx *ctx, int slot);
 /* Read points back as 30-byte encodings (CurvePoint::to_bytes, src/curve.rs:93-100). */
