@@ -456,6 +456,11 @@ int dvp_selftest_op(dvp_ctx *ctx, int op, const void *a, const void *b, void *ou
     return DVP_OK;
 }
 
+int dvp_latency_probe(dvp_ctx *ctx, int mode, int iters, float *us_per_op) {
+    if (!ctx || !us_per_op || mode < 0 || mode > 2 || iters <= 0) return DVP_ERR_BAD_ARG;
+    CKC(cudaSetDevice(ctx->device));
+    return latency_probe(ctx->msm, mode, iters, us_per_op);
+}
 int dvp_microbench(dvp_ctx *ctx, int op, int iters, double *ops_per_sec) {
     // op = primitive (0 gf_mul, 1 gf_sqr, 2 fr_mul) + 10 * (resident blocks per SM - 1)
     if (!ctx || !ops_per_sec || op < 0 || op % 10 > 2 || op / 10 > 2 || iters <= 0) return DVP_ERR_BAD_ARG;

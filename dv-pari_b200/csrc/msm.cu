@@ -34,6 +34,8 @@ namespace dvp {
         }                                                                                           \
     } while (0)
 
+static inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
+
 int DevBuf::reserve(size_t bytes) {
     if (bytes <= cap) return 0;
     if (p) cudaFree(p);
@@ -53,6 +55,26 @@ void DevBuf::release() {
     cap = 0;
 }
 
+__global__ void k_latency_probe(int mode, int iters, const gf *__restrict__ tabs, uint32_t *__restrict__ sink);
+// microseconds per operation for a single warp running a dependent chain
+int latency_probe(MsmEngine &E, int mode, int iters, float *us_per_op) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    if (E.info.reserve(64)) return DVP_ERR_OOM;
+    k_latency_probe<<<1, 32, 0, E.stream>>>(mode, 2, E.msqr_tabs.as<gf>(), E.info.as<uint32_t>());
+    cudaEventRecord(e0, E.stream);
+    k_latency_probe<<<1, 32, 0, E.stream>>>(mode, iters, E.msqr_tabs.as<gf>(), E.info.as<uint32_t>());
+    cudaEventRecord(e1, E.stream);
+    if (cudaEventSynchronize(e1) != cudaSuccess) return DVP_ERR_CUDA;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *us_per_op = ms * 1e3f / iters;
+    return 0;
+}
+
 int choose_window_bits(size_t n) {
     // adds ~ n*W + tail(2^(c-1)*W); the tail rounds are latency-bound, so stay a little below the
     // arithmetic optimum
@@ -67,7 +89,10 @@ int choose_window_bits(size_t n) {
 // ------------------------------------------------------------------------------------------------
 // recode + histogram
 // ------------------------------------------------------------------------------------------------
-__global__ void k_recode_count(const uint32_t *__restrict__ scalars, uint32_t n, int c, int W, uint32_t nb,
+// Window j covers bits [off_j, off_j + width_j) with width_j = base + (j < rem), off_j = j*base + min(j, rem):
+// the 233 scalar bits are spread evenly over the W windows so that no window is nearly empty (a
+// short top window would put all n entries into a handful of buckets and double the tree depth).
+__global__ void k_recode_count(const uint32_t *__restrict__ scalars, uint32_t n, int base, int rem, int W, uint32_t nb,
                                uint32_t *__restrict__ keys, uint32_t *__restrict__ seg_len) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -79,10 +104,11 @@ __global__ void k_recode_count(const uint32_t *__restrict__ scalars, uint32_t n,
     uint32_t k[9];
     fr_to_canonical(k, a);
     k[8] = 0;
-    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
     uint32_t carry = 0;
     for (int j = 0; j < W; j++) {
-        const int bit = j * c, w = bit >> 5, sh = bit & 31;
+        const int c = base + (j < rem ? 1 : 0);
+        const int bit = j * base + min(j, rem), w = bit >> 5, sh = bit & 31;
+        const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
         uint32_t raw = 0;
         if (w < 8) {
             uint64_t two = (uint64_t)k[w] | ((uint64_t)k[w + 1] << 32);
@@ -311,8 +337,18 @@ __global__ void __launch_bounds__(256)
         const uint32_t t = base + k * 32 + lane;
         if (t >= ntasks) break;
         if (s == 0xffffffffu) s = seg_search(task_start, nseg, t);
-        else
-            while (task_start[s + 1] <= t) s++;
+        else {
+            // the next task is usually in the same or the next segment; runs of empty segments
+            // (finished buckets, unused bucket slots) are skipped by a fresh binary search
+            int steps = 0;
+            while (task_start[s + 1] <= t) {
+                s++;
+                if (++steps == 4) {
+                    s = seg_search(task_start, nseg, t);
+                    break;
+                }
+            }
+        }
         const uint32_t j = t - task_start[s];
         const uint32_t a = in_start[s] + 2 * j, o = out_start[s] + j;
         desc[t] = make_uint4(a, a + 1, o, 0);
@@ -328,6 +364,11 @@ __global__ void __launch_bounds__(256)
     }
     gf_store(&thr_total[gtid], acc);
 }
+
+// One shared copy of the 1.2k-instruction multiplier for the pass-2 loop: four inlined copies are 86 KB
+// of code (I-cache misses were 10 % of the stalls) and push the kernel to 255 registers; called out of
+// line the loop fits 128 registers, i.e. twice the resident warps.
+__device__ __noinline__ gf gf_mul_call(const gf a, const gf b) { return gf_mul(a, b); }
 
 // pass 2: walk the same tasks backwards with the inverse of the thread total, finish the additions
 template <bool INDEXED, int B, int MINB>
@@ -349,9 +390,19 @@ __global__ void __launch_bounds__(256, MINB)
         const AffPt p1 = fetch_pt<INDEXED>(src, ent, de.x), p2 = fetch_pt<INDEXED>(src, ent, de.y);
         gf d;
         const int kind = pair_classify(p1, p2, d);
-        const gf dinv = gf_mul(inv, gf_load(&prefix[t]));
-        if (k) inv = gf_mul(inv, d);
-        pt_store(&dst[de.z], pair_finish(p1, p2, kind, dinv));
+        const gf dinv = gf_mul_call(inv, gf_load(&prefix[t]));
+        if (k) inv = gf_mul_call(inv, d);
+        AffPt r;
+        if (kind >= 2) {
+            r = pair_finish(p1, p2, kind, dinv);
+        } else {
+            // chord / tangent: lambda = num/d (+ x1 for the tangent), see pair_finish
+            gf lam = gf_mul_call(kind == 1 ? p1.y : gf_add(p1.y, p2.y), dinv);
+            if (kind == 1) lam = gf_add(lam, p1.x);
+            r.x = gf_add(gf_add(gf_sqr(lam), lam), gf_add(p1.x, p2.x));
+            r.y = gf_add(gf_add(gf_mul_call(lam, gf_add(p1.x, r.x)), r.x), p1.y);
+        }
+        pt_store(&dst[de.z], r);
     }
 }
 
@@ -379,12 +430,79 @@ __global__ void k_finalize(const AffPt *__restrict__ src, const uint32_t *__rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// table-driven inversion: x -> x^(2^k) is GF(2)-linear, so for k in {7,14,29,58,116} it is 30 byte-indexed
+// lookups (one 32-byte row per input byte) xor-ed together.  Itoh-Tsujii then needs 8 single squarings,
+// 5 table passes and 10 multiplications instead of 232 squarings: the inversion sits on the critical
+// path of every round of the tree, so its latency (not its throughput) is what matters.
+// ------------------------------------------------------------------------------------------------
+constexpr int MSQ_TABLES = 5;
+__device__ __constant__ int MSQ_K[MSQ_TABLES] = {7, 14, 29, 58, 116};
+constexpr size_t MSQ_TABLE_ELEMS = 30 * 256; // gf rows per table
+
+__global__ void k_build_msqr_tables(gf *__restrict__ tabs) {
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= MSQ_TABLES * MSQ_TABLE_ELEMS) return;
+    const uint32_t t = id / MSQ_TABLE_ELEMS, r = id % MSQ_TABLE_ELEMS, pos = r >> 8, v = r & 255;
+    gf x = gf_zero();
+    x.v[pos >> 2] = v << (8 * (pos & 3));
+    if (pos == 29) x.v[7] &= 0x1ffu; // bits >= 233 do not exist
+    gf_store(&tabs[id], gf_sqr_n(x, MSQ_K[t]));
+}
+__device__ __forceinline__ gf gf_msqr_tab(const gf &x, const gf *__restrict__ tab) {
+    uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int pos = 0; pos < 30; pos++) {
+        const uint32_t b = (x.v[pos >> 2] >> (8 * (pos & 3))) & 255u;
+        const uint4 *row = reinterpret_cast<const uint4 *>(tab + pos * 256 + b);
+        const uint4 lo = __ldg(row), hi = __ldg(row + 1);
+        acc[0] ^= lo.x; acc[1] ^= lo.y; acc[2] ^= lo.z; acc[3] ^= lo.w;
+        acc[4] ^= hi.x; acc[5] ^= hi.y; acc[6] ^= hi.z; acc[7] ^= hi.w;
+    }
+    gf r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = acc[i];
+    return r;
+}
+// chain 1,2,3,6,7,14,28,29,58,116,232; 0 -> 0
+__device__ __noinline__ gf gf_inv_tab(const gf &a, const gf *__restrict__ tabs) {
+    const gf *t7 = tabs, *t14 = tabs + MSQ_TABLE_ELEMS, *t29 = tabs + 2 * MSQ_TABLE_ELEMS,
+             *t58 = tabs + 3 * MSQ_TABLE_ELEMS, *t116 = tabs + 4 * MSQ_TABLE_ELEMS;
+    const gf b2 = gf_mul(gf_sqr(a), a);
+    const gf b3 = gf_mul(gf_sqr(b2), a);
+    const gf b6 = gf_mul(gf_sqr(gf_sqr(gf_sqr(b3))), b3);
+    const gf b7 = gf_mul(gf_sqr(b6), a);
+    const gf b14 = gf_mul(gf_msqr_tab(b7, t7), b7);
+    const gf b28 = gf_mul(gf_msqr_tab(b14, t14), b14);
+    const gf b29 = gf_mul(gf_sqr(b28), a);
+    const gf b58 = gf_mul(gf_msqr_tab(b29, t29), b29);
+    const gf b116 = gf_mul(gf_msqr_tab(b58, t58), b58);
+    const gf b232 = gf_mul(gf_msqr_tab(b116, t116), b116);
+    return gf_sqr(b232);
+}
+
+// single-warp latency probe: iters dependent inversions (mode 0 Itoh-Tsujii by squarings, 1 table-driven, 2 gf_mul)
+__global__ void k_latency_probe(int mode, int iters, const gf *__restrict__ tabs, uint32_t *__restrict__ sink) {
+    gf a;
+    for (int k = 0; k < 8; k++) a.v[k] = threadIdx.x * 2654435761u + k * 40503u + 1;
+    a.v[7] &= 0x1ff;
+    gf b = a;
+    for (int i = 0; i < iters; i++) {
+        if (mode == 0) a = gf_inv(a);
+        else if (mode == 1) a = gf_inv_tab(a, tabs);
+        else a = gf_mul(a, b);
+    }
+    uint32_t s = 0;
+    for (int k = 0; k < 8; k++) s ^= a.v[k];
+    if (s == 0x12345678u) sink[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
 // hierarchical batched inversion of n non-zero field elements
 // ------------------------------------------------------------------------------------------------
-__global__ void k_binv_direct(const gf *__restrict__ in, gf *__restrict__ out, uint32_t n) {
+__global__ void k_binv_direct(const gf *__restrict__ in, gf *__restrict__ out, uint32_t n, const gf *__restrict__ tabs) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    gf_store(&out[i], gf_inv(gf_load(&in[i])));
+    gf_store(&out[i], gf_inv_tab(gf_load(&in[i]), tabs));
 }
 __global__ void k_binv_up(const gf *__restrict__ in, uint32_t n, uint32_t G, gf *__restrict__ pre,
                           gf *__restrict__ tot) {
@@ -507,13 +625,18 @@ int MsmEngine::init(cudaStream_t s) {
     CK(cudaMallocHost(&h_info, 64));
     for (auto &e : ev) CK(cudaEventCreate(&e));
     for (auto &e : ev_k) CK(cudaEventCreate(&e));
+    int rc = msqr_tabs.reserve(MSQ_TABLES * MSQ_TABLE_ELEMS * sizeof(gf));
+    if (rc) return rc;
+    k_build_msqr_tables<<<cdiv(MSQ_TABLES * MSQ_TABLE_ELEMS, 128), 128, 0, s>>>(msqr_tabs.as<gf>());
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
     return 0;
 }
 void MsmEngine::destroy() {
     DevBuf *all[] = {&keys, &entries, &seg_len[0], &seg_len[1], &seg_start[0], &seg_start[1], &c_len, &c_start,
                      &task_start, &cursor, &blk, &info, &pp[0], &pp[1], &prefix, &desc, &thr_total, &thr_inv,
                      &lvl_pre[0], &lvl_pre[1], &lvl_tot[0], &lvl_tot[1], &lvl_inv[0], &lvl_inv[1], &buckets, &rc,
-                     &hb, &ents2};
+                     &hb, &ents2, &msqr_tabs};
     for (auto b : all) b->release();
     if (h_info) cudaFreeHost(h_info);
     if (h_pts) cudaFreeHost(h_pts);
@@ -527,7 +650,6 @@ void MsmEngine::destroy() {
 
 namespace {
 
-inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
 constexpr uint32_t BINV_G = 16;        // group size of one batched-inversion level
 constexpr uint32_t BINV_DIRECT = 8192; // at or below this many elements every thread inverts its own
 
@@ -550,18 +672,20 @@ struct Tree {
     // n non-zero elements in -> inverses out
     int batch_inv(const gf *in, gf *out, uint32_t n, int depth) {
         if (n <= BINV_DIRECT || depth >= 2) {
-            k_binv_direct<<<cdiv(n, 128), 128, 0, st>>>(in, out, n);
+            k_binv_direct<<<cdiv(n, 64), 64, 0, st>>>(in, out, n, E.msqr_tabs.as<gf>());
             E.launches++;
             CK(cudaGetLastError());
             return 0;
         }
-        const uint32_t ng = cdiv(n, BINV_G);
+        // small batches are latency-bound (serial multiplications per thread): use a small fan-in
+        const uint32_t G = n <= 16 * BINV_DIRECT ? (n <= 4 * BINV_DIRECT ? 4 : 8) : BINV_G;
+        const uint32_t ng = cdiv(n, G);
         gf *pre = E.lvl_pre[depth].as<gf>(), *tot = E.lvl_tot[depth].as<gf>(), *inv = E.lvl_inv[depth].as<gf>();
-        k_binv_up<<<cdiv(ng, 128), 128, 0, st>>>(in, n, BINV_G, pre, tot);
+        k_binv_up<<<cdiv(ng, 64), 64, 0, st>>>(in, n, G, pre, tot);
         E.launches++;
         int rc = batch_inv(tot, inv, ng, depth + 1);
         if (rc) return rc;
-        k_binv_down<<<cdiv(ng, 128), 128, 0, st>>>(in, n, BINV_G, pre, inv, out);
+        k_binv_down<<<cdiv(ng, 64), 64, 0, st>>>(in, n, G, pre, inv, out);
         E.launches++;
         CK(cudaGetLastError());
         return 0;
@@ -670,9 +794,13 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     if (n == 0) return 0;
     if (n >= (1ull << 31)) return DVP_ERR_BAD_ARG;
     launches = 0;
-    const int c = force_window_bits ? force_window_bits : choose_window_bits(n);
-    if (c < 4 || c > 20) return DVP_ERR_BAD_ARG;
-    const int W = (233 + c - 1) / c;
+    const int c_req = force_window_bits ? force_window_bits : choose_window_bits(n);
+    if (c_req < 4 || c_req > 20) return DVP_ERR_BAD_ARG;
+    // W windows of width base or base+1 covering exactly 233 bits (bit 232 of a scalar < p is zero, so the
+    // top window never carries out); c = the widest window sizes the bucket tables
+    const int W = (233 + c_req - 1) / c_req;
+    const int base = 233 / W, rem = 233 % W;
+    const int c = base + (rem ? 1 : 0);
     const uint32_t nb = 1u << (c - 1);
     const uint32_t nseg = (uint32_t)W * nb;
     const size_t total = (size_t)W * n;
@@ -711,11 +839,11 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     RS(thr_total, thr_ub * sizeof(gf));
     RS(thr_inv, thr_ub * sizeof(gf));
     RS(lvl_pre[0], thr_ub * sizeof(gf));
-    RS(lvl_tot[0], (thr_ub / BINV_G + 2) * sizeof(gf));
-    RS(lvl_inv[0], (thr_ub / BINV_G + 2) * sizeof(gf));
-    RS(lvl_pre[1], (thr_ub / BINV_G + 2) * sizeof(gf));
-    RS(lvl_tot[1], (thr_ub / BINV_G / BINV_G + 2) * sizeof(gf));
-    RS(lvl_inv[1], (thr_ub / BINV_G / BINV_G + 2) * sizeof(gf));
+    RS(lvl_tot[0], (thr_ub / 4 + 2) * sizeof(gf));
+    RS(lvl_inv[0], (thr_ub / 4 + 2) * sizeof(gf));
+    RS(lvl_pre[1], (thr_ub / 4 + 2) * sizeof(gf));
+    RS(lvl_tot[1], (thr_ub / 16 + 2) * sizeof(gf));
+    RS(lvl_inv[1], (thr_ub / 16 + 2) * sizeof(gf));
     RS(buckets, (size_t)nseg * sizeof(AffPt));
     RS(this->rc, (size_t)nseg_a * sizeof(AffPt));
     RS(hb, (size_t)nseg_b * sizeof(AffPt));
@@ -735,7 +863,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     // ---- recode + histogram, bucket offsets, scatter (a counting sort by bucket)
     uint32_t *d_len = c_len.as<uint32_t>(), *d_start = c_start.as<uint32_t>();
     CK(cudaMemsetAsync(d_len, 0, (size_t)nseg * 4, st));
-    k_recode_count<<<cdiv(n, 128), 128, 0, st>>>(d_scalars, (uint32_t)n, c, W, nb, keys.as<uint32_t>(), d_len);
+    k_recode_count<<<cdiv(n, 128), 128, 0, st>>>(d_scalars, (uint32_t)n, base, rem, W, nb, keys.as<uint32_t>(), d_len);
     {
         const uint32_t nblk = cdiv(nseg, SCAN_TILE);
         k_scan1<0><<<nblk, SCAN_THREADS, 0, st>>>(d_len, nseg, blk.as<uint64_t>(), info.as<uint32_t>());
@@ -782,15 +910,19 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     if (timing) cudaEventRecord(ev[3], st);
     CK(cudaStreamSynchronize(st));
 
-    // ---- host tail: sum_w 2^(c w) [ sum_{q<c-1} 2^q HB[w][q] + HB[w][c-1] ]
+    // ---- host tail: sum_w 2^(off_w) [ sum_{q<c-1} 2^q HB[w][q] + HB[w][c-1] ], one double-and-add pass
     {
         const AffPt *hp = (const AffPt *)h_pts;
+        std::vector<std::vector<int>> at(W * c + 1);
+        for (int w = 0; w < W; w++) {
+            const int off = w * base + std::min(w, rem);
+            for (int q = 0; q < c - 1; q++) at[off + q].push_back(w * c + q);
+            at[off].push_back(w * c + c - 1);
+        }
         host::LdPt acc = host::ld_inf();
-        for (int pos = W * c - 1; pos >= 0; pos--) {
+        for (int pos = W * c; pos >= 0; pos--) {
             acc = host::ld_dbl(acc);
-            const int w = pos / c, q = pos % c;
-            if (q < c - 1) acc = host::ld_add_affine(acc, hp[w * c + q]);
-            if (q == 0) acc = host::ld_add_affine(acc, hp[w * c + c - 1]);
+            for (int idx : at[pos]) acc = host::ld_add_affine(acc, hp[idx]);
         }
         *h_result = host::ld_to_affine(acc);
     }

@@ -29,7 +29,7 @@ struct MsmEngine {
     cudaStream_t stream = nullptr;
     // scratch
     DevBuf keys, entries, seg_len[2], seg_start[2], c_len, c_start, task_start, cursor, blk, info, pp[2], prefix, desc,
-        thr_total, thr_inv, lvl_pre[2], lvl_tot[2], lvl_inv[2], buckets, rc, hb, ents2;
+        thr_total, thr_inv, lvl_pre[2], lvl_tot[2], lvl_inv[2], buckets, rc, hb, ents2, msqr_tabs;
     void *h_info = nullptr; // pinned
     void *h_pts = nullptr;  // pinned, receives the per-bit partial sums
     size_t h_pts_cap = 0;
@@ -41,7 +41,7 @@ struct MsmEngine {
     MsmStats last;
     int force_window_bits = 0; // 0 = choose from n
     bool timing = false;
-    int pass2_minb = 1; // resident blocks per SM the pass-2 kernel is compiled for (register cap)
+    int pass2_minb = 2; // resident blocks per SM the pass-2 kernel is compiled for (register cap)
 
     int init(cudaStream_t s);
     void destroy();
@@ -51,5 +51,6 @@ struct MsmEngine {
 };
 
 int choose_window_bits(size_t n);
+int latency_probe(MsmEngine &E, int mode, int iters, float *us_per_op);
 
 } // namespace dvp

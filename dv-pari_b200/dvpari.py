@@ -84,6 +84,7 @@ def lib():
         L.dvp_selftest_op.argtypes = [vp, i32, vp, vp, vp, sz]
         L.dvp_microbench.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
         L.dvp_hostcheck_op.argtypes = [i32, vp, vp, vp, sz]
+        L.dvp_latency_probe.argtypes = [vp, i32, i32, C.POINTER(C.c_float)]
         L.dvp_pipebench.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_double)]
         L.dvp_domain_create.argtypes = [vp, C.c_uint, C.POINTER(vp)]
         L.dvp_domain_destroy.argtypes = [vp]
@@ -238,6 +239,11 @@ class Context:
         bb = np.ascontiguousarray(b, dtype=np.uint32) if b is not None else None
         _ck(lib().dvp_selftest_op(self._h, op, _ptr(a), _ptr(bb), _ptr(out), a.shape[0]))
         return out
+
+    def latency_probe(self, mode, iters):
+        v = C.c_float()
+        _ck(lib().dvp_latency_probe(self._h, mode, iters, C.byref(v)))
+        return v.value
 
     def pipebench(self, mode, iters, blocks_per_sm):
         v = C.c_double()

@@ -155,6 +155,9 @@ int dvp_prove_stages(dvp_prover *p, const uint64_t *public_mont, size_t k, const
 /* ms per stage of the last prove: r1cs, msm g_m, extend+quotient, msm g_q, challenge+K scalars, msm g_k */
 int dvp_prove_last_times(dvp_prover *p, float ms[6]);
 
+/* Single-warp latency of a dependent chain, microseconds per op: mode 0 gf inversion by squarings,
+ * 1 table-driven gf inversion, 2 gf multiplication. */
+int dvp_latency_probe(dvp_ctx *ctx, int mode, int iters, float *us_per_op);
 /* Raw integer-pipe issue rates (thread-instructions per second over the whole GPU): the roofline
  * denominators for the field kernels.  mode: 0 IMAD.WIDE  1 LOP3  2 IMAD  3 IMAD.WIDE:LOP3 = 1:2  4 SHF  5 IADD */
 int dvp_pipebench(dvp_ctx *ctx, int mode, int iters, int blocks_per_sm, double *instr_per_sec);
