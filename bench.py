@@ -226,10 +226,13 @@ def main():
     assert res_dev == res_e2e, "device-resident and host-buffer calls disagree"
 
     # one instrumented step: stage split, launches, the dominant kernel's duration (CUDA events in the library)
+    # (single lane here so that no other stream shares the GPU with the kernel being timed)
     ctx.set("timing", 1)
+    ctx.set("msm_lanes", 1)
     ctx.multi_scalar_mul_device(d_sc, n, 0)
     st = ctx.msm_stats()
     ctx.set("timing", 0)
+    ctx.set("msm_lanes", 0)
 
     if rank == 0:
         hbm_peak, which = peaks()

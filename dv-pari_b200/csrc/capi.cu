@@ -251,6 +251,11 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
         ctx->msm.force_window_bits = (int)value;
         return DVP_OK;
     }
+    if (!strcmp(name, "msm_lanes")) {
+        if (value < 0 || value > 16) return DVP_ERR_BAD_ARG;
+        ctx->msm.force_lanes = (int)value;
+        return DVP_OK;
+    }
     if (!strcmp(name, "pass2_minb")) {
         if (value < 1 || value > 3) return DVP_ERR_BAD_ARG;
         ctx->msm.pass2_minb = (int)value;

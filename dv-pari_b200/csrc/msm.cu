@@ -61,10 +61,10 @@ int latency_probe(MsmEngine &E, int mode, int iters, float *us_per_op) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    if (E.info.reserve(64)) return DVP_ERR_OOM;
-    k_latency_probe<<<1, 32, 0, E.stream>>>(mode, 2, E.msqr_tabs.as<gf>(), E.info.as<uint32_t>());
+    if (E.hb.reserve(64)) return DVP_ERR_OOM;
+    k_latency_probe<<<1, 32, 0, E.stream>>>(mode, 2, E.msqr_tabs.as<gf>(), E.hb.as<uint32_t>());
     cudaEventRecord(e0, E.stream);
-    k_latency_probe<<<1, 32, 0, E.stream>>>(mode, iters, E.msqr_tabs.as<gf>(), E.info.as<uint32_t>());
+    k_latency_probe<<<1, 32, 0, E.stream>>>(mode, iters, E.msqr_tabs.as<gf>(), E.hb.as<uint32_t>());
     cudaEventRecord(e1, E.stream);
     if (cudaEventSynchronize(e1) != cudaSuccess) return DVP_ERR_CUDA;
     float ms = 0;
@@ -135,14 +135,15 @@ __global__ void k_recode_count(const uint32_t *__restrict__ scalars, uint32_t n,
     }
 }
 
-__global__ void k_scatter(const uint32_t *__restrict__ keys, uint32_t n, size_t total, uint32_t *__restrict__ cursor,
-                          uint32_t *__restrict__ entries) {
+// keys: the (window-major) slice of one lane; key_base = first bucket key of that slice
+__global__ void k_scatter(const uint32_t *__restrict__ keys, uint32_t n, size_t total, uint32_t key_base,
+                          uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const uint32_t k = keys[e];
     if (k == 0xffffffffu) return;
     const uint32_t i = (uint32_t)(e % n);
-    const uint32_t pos = atomicAdd(&cursor[k >> 1], 1u);
+    const uint32_t pos = atomicAdd(&cursor[(k >> 1) - key_base], 1u);
     entries[pos] = i | ((k & 1u) << 31);
 }
 
@@ -620,11 +621,33 @@ __global__ void k_gen_segs_b(uint32_t W, uint32_t lr, uint32_t lm, uint32_t *__r
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
+int MsmLane::init() {
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    CK(cudaMallocHost(&h_info, 64));
+    for (auto &e : ev_k) CK(cudaEventCreate(&e));
+    for (auto &e : ev_s) CK(cudaEventCreate(&e));
+    return 0;
+}
+void MsmLane::destroy() {
+    DevBuf *all[] = {&entries, &seg_len[0], &seg_len[1], &seg_start[0], &seg_start[1], &c_len, &c_start, &task_start,
+                     &cursor, &blk, &info, &pp[0], &pp[1], &prefix, &desc, &thr_total, &thr_inv, &lvl_pre[0],
+                     &lvl_pre[1], &lvl_tot[0], &lvl_tot[1], &lvl_inv[0], &lvl_inv[1], &buckets, &rc, &ents2};
+    for (auto b : all) b->release();
+    if (h_info) cudaFreeHost(h_info);
+    h_info = nullptr;
+    for (auto &e : ev_k)
+        if (e) cudaEventDestroy(e), e = nullptr;
+    for (auto &e : ev_s)
+        if (e) cudaEventDestroy(e), e = nullptr;
+    if (done) cudaEventDestroy(done), done = nullptr;
+    if (stream) cudaStreamDestroy(stream), stream = nullptr;
+}
+
 int MsmEngine::init(cudaStream_t s) {
     stream = s;
-    CK(cudaMallocHost(&h_info, 64));
     for (auto &e : ev) CK(cudaEventCreate(&e));
-    for (auto &e : ev_k) CK(cudaEventCreate(&e));
+    CK(cudaEventCreateWithFlags(&ev_recode, cudaEventDisableTiming));
     int rc = msqr_tabs.reserve(MSQ_TABLES * MSQ_TABLE_ELEMS * sizeof(gf));
     if (rc) return rc;
     k_build_msqr_tables<<<cdiv(MSQ_TABLES * MSQ_TABLE_ELEMS, 128), 128, 0, s>>>(msqr_tabs.as<gf>());
@@ -633,38 +656,38 @@ int MsmEngine::init(cudaStream_t s) {
     return 0;
 }
 void MsmEngine::destroy() {
-    DevBuf *all[] = {&keys, &entries, &seg_len[0], &seg_len[1], &seg_start[0], &seg_start[1], &c_len, &c_start,
-                     &task_start, &cursor, &blk, &info, &pp[0], &pp[1], &prefix, &desc, &thr_total, &thr_inv,
-                     &lvl_pre[0], &lvl_pre[1], &lvl_tot[0], &lvl_tot[1], &lvl_inv[0], &lvl_inv[1], &buckets, &rc,
-                     &hb, &ents2, &msqr_tabs};
-    for (auto b : all) b->release();
-    if (h_info) cudaFreeHost(h_info);
+    for (auto &l : lanes) l.destroy();
+    lanes.clear();
+    keys.release();
+    len_all.release();
+    hb.release();
+    msqr_tabs.release();
     if (h_pts) cudaFreeHost(h_pts);
-    h_info = h_pts = nullptr;
+    h_pts = nullptr;
     h_pts_cap = 0;
     for (auto &e : ev)
         if (e) cudaEventDestroy(e), e = nullptr;
-    for (auto &e : ev_k)
-        if (e) cudaEventDestroy(e), e = nullptr;
+    if (ev_recode) cudaEventDestroy(ev_recode), ev_recode = nullptr;
 }
 
 namespace {
 
-constexpr uint32_t BINV_G = 16;        // group size of one batched-inversion level
+constexpr uint32_t BINV_G = 16;        // group size of one batched-inversion level (large batches)
 constexpr uint32_t BINV_DIRECT = 8192; // at or below this many elements every thread inverts its own
 
 struct Tree {
     MsmEngine &E;
+    MsmLane &L;
     cudaStream_t st;
-    explicit Tree(MsmEngine &e) : E(e), st(e.stream) {}
+    Tree(MsmEngine &e, MsmLane &l) : E(e), L(l), st(l.stream) {}
 
     int scan_plan(const uint32_t *len, uint32_t nseg, uint32_t *task_start, uint32_t *out_start, uint32_t *new_len) {
         const uint32_t nblk = cdiv(nseg, SCAN_TILE);
-        k_scan1<1><<<nblk, SCAN_THREADS, 0, st>>>(len, nseg, E.blk.as<uint64_t>(), E.info.as<uint32_t>());
-        k_scan2<<<1, SCAN_THREADS, 0, st>>>(E.blk.as<uint64_t>(), nblk);
-        k_scan3<1><<<nblk, SCAN_THREADS, 0, st>>>(len, nseg, E.blk.as<uint64_t>(), task_start, out_start, new_len,
-                                                  E.info.as<uint32_t>());
-        E.launches += 3;
+        k_scan1<1><<<nblk, SCAN_THREADS, 0, st>>>(len, nseg, L.blk.as<uint64_t>(), L.info.as<uint32_t>());
+        k_scan2<<<1, SCAN_THREADS, 0, st>>>(L.blk.as<uint64_t>(), nblk);
+        k_scan3<1><<<nblk, SCAN_THREADS, 0, st>>>(len, nseg, L.blk.as<uint64_t>(), task_start, out_start, new_len,
+                                                  L.info.as<uint32_t>());
+        L.launches += 3;
         CK(cudaGetLastError());
         return 0;
     }
@@ -673,20 +696,20 @@ struct Tree {
     int batch_inv(const gf *in, gf *out, uint32_t n, int depth) {
         if (n <= BINV_DIRECT || depth >= 2) {
             k_binv_direct<<<cdiv(n, 64), 64, 0, st>>>(in, out, n, E.msqr_tabs.as<gf>());
-            E.launches++;
+            L.launches++;
             CK(cudaGetLastError());
             return 0;
         }
         // small batches are latency-bound (serial multiplications per thread): use a small fan-in
         const uint32_t G = n <= 16 * BINV_DIRECT ? (n <= 4 * BINV_DIRECT ? 4 : 8) : BINV_G;
         const uint32_t ng = cdiv(n, G);
-        gf *pre = E.lvl_pre[depth].as<gf>(), *tot = E.lvl_tot[depth].as<gf>(), *inv = E.lvl_inv[depth].as<gf>();
+        gf *pre = L.lvl_pre[depth].as<gf>(), *tot = L.lvl_tot[depth].as<gf>(), *inv = L.lvl_inv[depth].as<gf>();
         k_binv_up<<<cdiv(ng, 64), 64, 0, st>>>(in, n, G, pre, tot);
-        E.launches++;
+        L.launches++;
         int rc = batch_inv(tot, inv, ng, depth + 1);
         if (rc) return rc;
         k_binv_down<<<cdiv(ng, 64), 64, 0, st>>>(in, n, G, pre, inv, out);
-        E.launches++;
+        L.launches++;
         CK(cudaGetLastError());
         return 0;
     }
@@ -697,28 +720,28 @@ struct Tree {
         const uint32_t nblk = cdiv(cdiv(task_ub, B), 256);
         const uint32_t nthr = nblk * 256;
         k_pass1<INDEXED, B><<<nblk, 256, 0, st>>>(src, ent, in_start, task_start, out_start, nseg,
-                                                  E.info.as<uint32_t>(), E.desc.as<uint4>(), E.prefix.as<gf>(),
-                                                  E.thr_total.as<gf>());
-        E.launches++;
-        int rc = batch_inv(E.thr_total.as<gf>(), E.thr_inv.as<gf>(), nthr, 0);
+                                                  L.info.as<uint32_t>(), L.desc.as<uint4>(), L.prefix.as<gf>(),
+                                                  L.thr_total.as<gf>());
+        L.launches++;
+        int rc = batch_inv(L.thr_total.as<gf>(), L.thr_inv.as<gf>(), nthr, 0);
         if (rc) return rc;
-        const bool mark = E.want_k;
-        if (mark) cudaEventRecord(E.ev_k[0], st);
+        const bool mark = L.want_k;
+        if (mark) cudaEventRecord(L.ev_k[0], st);
         if (E.pass2_minb == 2)
-            k_pass2<INDEXED, B, 2><<<nblk, 256, 0, st>>>(src, ent, E.info.as<uint32_t>(), E.desc.as<uint4>(),
-                                                         E.prefix.as<gf>(), E.thr_inv.as<gf>(), dst);
+            k_pass2<INDEXED, B, 2><<<nblk, 256, 0, st>>>(src, ent, L.info.as<uint32_t>(), L.desc.as<uint4>(),
+                                                         L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
         else if (E.pass2_minb == 3)
-            k_pass2<INDEXED, B, 3><<<nblk, 256, 0, st>>>(src, ent, E.info.as<uint32_t>(), E.desc.as<uint4>(),
-                                                         E.prefix.as<gf>(), E.thr_inv.as<gf>(), dst);
+            k_pass2<INDEXED, B, 3><<<nblk, 256, 0, st>>>(src, ent, L.info.as<uint32_t>(), L.desc.as<uint4>(),
+                                                         L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
         else
-            k_pass2<INDEXED, B, 1><<<nblk, 256, 0, st>>>(src, ent, E.info.as<uint32_t>(), E.desc.as<uint4>(),
-                                                         E.prefix.as<gf>(), E.thr_inv.as<gf>(), dst);
+            k_pass2<INDEXED, B, 1><<<nblk, 256, 0, st>>>(src, ent, L.info.as<uint32_t>(), L.desc.as<uint4>(),
+                                                         L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
         if (mark) {
-            cudaEventRecord(E.ev_k[1], st);
-            E.want_k = false;
+            cudaEventRecord(L.ev_k[1], st);
+            L.want_k = false;
         }
         k_copy_odd<INDEXED><<<cdiv(nseg, 256), 256, 0, st>>>(src, ent, in_start, len, out_start, nseg, dst);
-        E.launches += 2;
+        L.launches += 2;
         CK(cudaGetLastError());
         return 0;
     }
@@ -731,57 +754,56 @@ struct Tree {
         return round<INDEXED, 1>(src, ent, in_start, len, task_start, out_start, nseg, task_ub, dst);
     }
 
-    // Reduce every segment of the index list `ent` over `src` to one point: dst[s], s < nseg.
-    // start0 (nseg+1 entries) / len0 (nseg) describe the segments and are only read; they must not be
-    // the engine's own seg_start[] / seg_len[] ping-pong arrays.  total_ub bounds the entry count.
-    // max_len_hint != 0: the longest segment is known, no read-back.
-    int reduce(const AffPt *src, const uint32_t *ent, const uint32_t *start0, const uint32_t *len0, uint32_t nseg,
-               size_t total_ub, uint32_t max_len_hint, AffPt *dst, int *rounds_out) {
-        uint32_t *ts = E.task_start.as<uint32_t>(), *info = E.info.as<uint32_t>();
-        uint32_t *elen[2] = {E.seg_len[0].as<uint32_t>(), E.seg_len[1].as<uint32_t>()};
-        uint32_t *estart[2] = {E.seg_start[0].as<uint32_t>(), E.seg_start[1].as<uint32_t>()};
+    // Plan of round 0: caller tables -> engine set 1; info[0] = longest segment, info[1] = tasks of round 0.
+    int plan0(const uint32_t *len0, uint32_t nseg, bool readback) {
+        uint32_t *info = L.info.as<uint32_t>();
         CK(cudaMemsetAsync(info, 0, 16, st));
-        // plan of round 0: caller tables -> engine set 1
-        int rc = scan_plan(len0, nseg, ts, estart[1], elen[1]);
+        int rc = scan_plan(len0, nseg, L.task_start.as<uint32_t>(), L.seg_start[1].as<uint32_t>(), L.seg_len[1].as<uint32_t>());
         if (rc) return rc;
-        uint32_t maxlen = max_len_hint;
-        if (!maxlen) {
-            CK(cudaMemcpyAsync(E.h_info, info, 16, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            maxlen = ((uint32_t *)E.h_info)[0];
-            E.h_round0_tasks = ((uint32_t *)E.h_info)[1];
-        }
-        int rounds = 0;
-        while ((1ull << rounds) < maxlen) rounds++;
-        if (rounds_out) *rounds_out = rounds;
-        if (rounds == 0) {
+        if (readback) CK(cudaMemcpyAsync(L.h_info, info, 16, cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
+
+    // Reduce every segment of the index list `ent` over `src` to one point: dst[s], s < nseg, given that
+    // plan0 has run.  start0 (nseg+1) / len0 (nseg) describe the segments and are only read; they must not
+    // be the lane's own seg_start[] / seg_len[] ping-pong arrays.  total_ub bounds the entry count.
+    int rounds(const AffPt *src, const uint32_t *ent, const uint32_t *start0, const uint32_t *len0, uint32_t nseg,
+               size_t total_ub, uint32_t maxlen, AffPt *dst, int *rounds_out) {
+        uint32_t *ts = L.task_start.as<uint32_t>(), *info = L.info.as<uint32_t>();
+        uint32_t *elen[2] = {L.seg_len[0].as<uint32_t>(), L.seg_len[1].as<uint32_t>()};
+        uint32_t *estart[2] = {L.seg_start[0].as<uint32_t>(), L.seg_start[1].as<uint32_t>()};
+        int nr = 0;
+        while ((1ull << nr) < maxlen) nr++;
+        if (rounds_out) *rounds_out = nr;
+        if (nr == 0) {
             k_finalize<true><<<cdiv(nseg, 256), 256, 0, st>>>(src, ent, start0, len0, nseg, dst);
-            E.launches++;
+            L.launches++;
             CK(cudaGetLastError());
             return 0;
         }
         const uint32_t *in_start = start0, *in_len = len0;
         const AffPt *cur_src = src;
-        for (int r = 0; r < rounds; r++) {
-            const int o = (r + 1) & 1; // engine set written by this round's plan
+        int rc;
+        for (int r = 0; r < nr; r++) {
+            const int o = (r + 1) & 1; // lane set written by this round's plan
             // tasks_r <= total/2^(r+1) + nseg/2
             const size_t task_ub = (total_ub >> (r + 1)) + nseg / 2 + 1;
             const int B = task_ub >= (1u << 21) ? 16 : task_ub >= (1u << 17) ? 4 : 1;
-            AffPt *out = E.pp[r & 1].as<AffPt>();
+            AffPt *out = L.pp[r & 1].as<AffPt>();
             if (r == 0) rc = round_b<true>(B, src, ent, in_start, in_len, ts, estart[o], nseg, task_ub, out);
             else rc = round_b<false>(B, cur_src, nullptr, in_start, in_len, ts, estart[o], nseg, task_ub, out);
             if (rc) return rc;
             cur_src = out;
             in_start = estart[o];
             in_len = elen[o];
-            if (r + 1 < rounds) {
+            if (r + 1 < nr) {
                 CK(cudaMemsetAsync(info, 0, 16, st));
                 rc = scan_plan(in_len, nseg, ts, estart[o ^ 1], elen[o ^ 1]);
                 if (rc) return rc;
             }
         }
         k_finalize<false><<<cdiv(nseg, 256), 256, 0, st>>>(cur_src, nullptr, in_start, in_len, nseg, dst);
-        E.launches++;
+        L.launches++;
         CK(cudaGetLastError());
         return 0;
     }
@@ -793,7 +815,6 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     *h_result = pt_inf();
     if (n == 0) return 0;
     if (n >= (1ull << 31)) return DVP_ERR_BAD_ARG;
-    launches = 0;
     const int c_req = force_window_bits ? force_window_bits : choose_window_bits(n);
     if (c_req < 4 || c_req > 20) return DVP_ERR_BAD_ARG;
     // W windows of width base or base+1 covering exactly 233 bits (bit 232 of a scalar < p is zero, so the
@@ -802,54 +823,78 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     const int base = 233 / W, rem = 233 % W;
     const int c = base + (rem ? 1 : 0);
     const uint32_t nb = 1u << (c - 1);
-    const uint32_t nseg = (uint32_t)W * nb;
     const size_t total = (size_t)W * n;
     if (total >= (1ull << 32)) return DVP_ERR_BAD_ARG;
     // bucket matrix of a window: m = 2^lm columns, R = 2^lr rows, nb = R*m
     const uint32_t lm = (uint32_t)c / 2, lr = (uint32_t)(c - 1) - lm;
     const uint32_t R = 1u << lr, m = 1u << lm;
-    const uint32_t nseg_a = (uint32_t)W * (R + m), nent_a = (uint32_t)W * 2 * nb;
     const uint32_t per_b = lm * (m >> 1) + lr * (R >> 1) + m;
-    const uint32_t nseg_b = (uint32_t)W * (uint32_t)c, nent_b = (uint32_t)W * per_b;
-    const size_t nseg_max = std::max<size_t>(nseg, std::max(nseg_a, nseg_b)) + 1;
-    const size_t ent_max = std::max<size_t>(total, std::max(nent_a, nent_b));
+    // lanes: independent chains of rounds over disjoint window ranges
+    int NL = force_lanes ? force_lanes : (n >= (1u << 17) ? 4 : n >= (1u << 13) ? 2 : 1);
+    NL = std::max(1, std::min(NL, W));
+    while ((int)lanes.size() < NL) {
+        lanes.emplace_back();
+        int rc0 = lanes.back().init();
+        if (rc0) return rc0;
+    }
 
     int rc;
 #define RS(buf, bytes) \
     if ((rc = (buf).reserve(bytes)) != 0) return rc
     RS(keys, total * 4);
-    RS(entries, total * 4);
-    for (int i = 0; i < 2; i++) {
-        RS(seg_len[i], nseg_max * 4);
-        RS(seg_start[i], nseg_max * 4);
+    RS(len_all, ((size_t)W * nb + 1) * 4);
+    RS(hb, (size_t)W * c * sizeof(AffPt));
+    struct Part {
+        int w0, wn;
+        uint32_t nseg, nseg_a, nent_a, nseg_b, nent_b;
+        size_t total;
+    };
+    std::vector<Part> part(NL);
+    for (int l = 0; l < NL; l++) {
+        Part &p = part[l];
+        p.w0 = (int)((long long)W * l / NL);
+        p.wn = (int)((long long)W * (l + 1) / NL) - p.w0;
+        p.nseg = (uint32_t)p.wn * nb;
+        p.total = (size_t)p.wn * n;
+        p.nseg_a = (uint32_t)p.wn * (R + m);
+        p.nent_a = (uint32_t)p.wn * 2 * nb;
+        p.nseg_b = (uint32_t)p.wn * (uint32_t)c;
+        p.nent_b = (uint32_t)p.wn * per_b;
+        MsmLane &L = lanes[l];
+        const size_t nseg_max = std::max<size_t>(p.nseg, std::max(p.nseg_a, p.nseg_b)) + 1;
+        const size_t ent_max = std::max<size_t>(p.total, std::max(p.nent_a, p.nent_b));
+        RS(L.entries, p.total * 4);
+        for (int i = 0; i < 2; i++) {
+            RS(L.seg_len[i], nseg_max * 4);
+            RS(L.seg_start[i], nseg_max * 4);
+        }
+        RS(L.c_len, nseg_max * 4);
+        RS(L.c_start, nseg_max * 4);
+        RS(L.task_start, nseg_max * 4);
+        RS(L.cursor, nseg_max * 4);
+        RS(L.blk, (nseg_max / SCAN_TILE + 8) * 8);
+        RS(L.info, 64);
+        const size_t task_ub0 = ent_max / 2 + nseg_max / 2 + 1; // round-0 bound, the largest
+        const size_t out_ub0 = ent_max / 2 + nseg_max + 1;      // outputs of round 0 (ceil halves)
+        RS(L.pp[0], out_ub0 * sizeof(AffPt));
+        RS(L.pp[1], (out_ub0 / 2 + nseg_max + 1) * sizeof(AffPt));
+        RS(L.prefix, task_ub0 * sizeof(gf));
+        RS(L.desc, task_ub0 * sizeof(uint4));
+        const size_t thr_ub = std::max<size_t>(task_ub0 / 16, 1u << 19) + 1024; // B = 16 / 4 / 1 regimes
+        RS(L.thr_total, thr_ub * sizeof(gf));
+        RS(L.thr_inv, thr_ub * sizeof(gf));
+        RS(L.lvl_pre[0], thr_ub * sizeof(gf));
+        RS(L.lvl_tot[0], (thr_ub / 4 + 2) * sizeof(gf));
+        RS(L.lvl_inv[0], (thr_ub / 4 + 2) * sizeof(gf));
+        RS(L.lvl_pre[1], (thr_ub / 4 + 2) * sizeof(gf));
+        RS(L.lvl_tot[1], (thr_ub / 16 + 2) * sizeof(gf));
+        RS(L.lvl_inv[1], (thr_ub / 16 + 2) * sizeof(gf));
+        RS(L.buckets, (size_t)p.nseg * sizeof(AffPt));
+        RS(L.rc, (size_t)p.nseg_a * sizeof(AffPt));
+        RS(L.ents2, (size_t)std::max(p.nent_a, p.nent_b) * 4);
     }
-    RS(c_len, nseg_max * 4);
-    RS(c_start, nseg_max * 4);
-    RS(task_start, nseg_max * 4);
-    RS(cursor, nseg_max * 4);
-    RS(blk, (nseg_max / SCAN_TILE + 8) * 8);
-    RS(info, 64);
-    const size_t task_ub0 = ent_max / 2 + nseg_max / 2 + 1; // round-0 bound, the largest
-    const size_t out_ub0 = ent_max / 2 + nseg_max + 1;      // outputs of round 0 (ceil halves)
-    RS(pp[0], out_ub0 * sizeof(AffPt));
-    RS(pp[1], (out_ub0 / 2 + nseg_max + 1) * sizeof(AffPt));
-    RS(prefix, task_ub0 * sizeof(gf));
-    RS(desc, task_ub0 * sizeof(uint4));
-    const size_t thr_ub = std::max<size_t>(task_ub0 / 16, 1u << 19) + 1024; // B = 16 / 4 / 1 regimes
-    RS(thr_total, thr_ub * sizeof(gf));
-    RS(thr_inv, thr_ub * sizeof(gf));
-    RS(lvl_pre[0], thr_ub * sizeof(gf));
-    RS(lvl_tot[0], (thr_ub / 4 + 2) * sizeof(gf));
-    RS(lvl_inv[0], (thr_ub / 4 + 2) * sizeof(gf));
-    RS(lvl_pre[1], (thr_ub / 4 + 2) * sizeof(gf));
-    RS(lvl_tot[1], (thr_ub / 16 + 2) * sizeof(gf));
-    RS(lvl_inv[1], (thr_ub / 16 + 2) * sizeof(gf));
-    RS(buckets, (size_t)nseg * sizeof(AffPt));
-    RS(this->rc, (size_t)nseg_a * sizeof(AffPt));
-    RS(hb, (size_t)nseg_b * sizeof(AffPt));
-    RS(ents2, (size_t)std::max(nent_a, nent_b) * 4);
 #undef RS
-    const size_t hb_bytes = (size_t)nseg_b * sizeof(AffPt);
+    const size_t hb_bytes = (size_t)W * c * sizeof(AffPt);
     if (h_pts_cap < hb_bytes) {
         if (h_pts) cudaFreeHost(h_pts);
         h_pts = nullptr;
@@ -860,54 +905,83 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
 
     cudaStream_t st = stream;
     if (timing) cudaEventRecord(ev[0], st);
-    // ---- recode + histogram, bucket offsets, scatter (a counting sort by bucket)
-    uint32_t *d_len = c_len.as<uint32_t>(), *d_start = c_start.as<uint32_t>();
-    CK(cudaMemsetAsync(d_len, 0, (size_t)nseg * 4, st));
-    k_recode_count<<<cdiv(n, 128), 128, 0, st>>>(d_scalars, (uint32_t)n, base, rem, W, nb, keys.as<uint32_t>(), d_len);
-    {
-        const uint32_t nblk = cdiv(nseg, SCAN_TILE);
-        k_scan1<0><<<nblk, SCAN_THREADS, 0, st>>>(d_len, nseg, blk.as<uint64_t>(), info.as<uint32_t>());
-        k_scan2<<<1, SCAN_THREADS, 0, st>>>(blk.as<uint64_t>(), nblk);
-        k_scan3<0><<<nblk, SCAN_THREADS, 0, st>>>(d_len, nseg, blk.as<uint64_t>(), d_start, cursor.as<uint32_t>(),
-                                                  nullptr, info.as<uint32_t>());
-    }
-    k_scatter<<<cdiv(total, 256), 256, 0, st>>>(keys.as<uint32_t>(), (uint32_t)n, total, cursor.as<uint32_t>(),
-                                                entries.as<uint32_t>());
-    launches += 5;
+    // ---- recode + histogram for every window (context stream)
+    uint32_t *d_len_all = len_all.as<uint32_t>();
+    CK(cudaMemsetAsync(d_len_all, 0, (size_t)W * nb * 4, st));
+    k_recode_count<<<cdiv(n, 128), 128, 0, st>>>(d_scalars, (uint32_t)n, base, rem, W, nb, keys.as<uint32_t>(), d_len_all);
     CK(cudaGetLastError());
-    if (timing) cudaEventRecord(ev[1], st);
-
-    Tree tree(*this);
+    CK(cudaEventRecord(ev_recode, st));
+    unsigned long long launches = 2;
+    // ---- per lane: bucket offsets, scatter (counting sort by bucket), plan of round 0
+    for (int l = 0; l < NL; l++) {
+        MsmLane &L = lanes[l];
+        const Part &p = part[l];
+        L.launches = 0;
+        CK(cudaStreamWaitEvent(L.stream, ev_recode, 0));
+        const uint32_t *len0 = d_len_all + (size_t)p.w0 * nb;
+        const uint32_t nblk = cdiv(p.nseg, SCAN_TILE);
+        k_scan1<0><<<nblk, SCAN_THREADS, 0, L.stream>>>(len0, p.nseg, L.blk.as<uint64_t>(), L.info.as<uint32_t>());
+        k_scan2<<<1, SCAN_THREADS, 0, L.stream>>>(L.blk.as<uint64_t>(), nblk);
+        k_scan3<0><<<nblk, SCAN_THREADS, 0, L.stream>>>(len0, p.nseg, L.blk.as<uint64_t>(), L.c_start.as<uint32_t>(),
+                                                        L.cursor.as<uint32_t>(), nullptr, L.info.as<uint32_t>());
+        k_scatter<<<cdiv(p.total, 256), 256, 0, L.stream>>>(keys.as<uint32_t>() + (size_t)p.w0 * n, (uint32_t)n, p.total,
+                                                            (uint32_t)p.w0 * nb, L.cursor.as<uint32_t>(),
+                                                            L.entries.as<uint32_t>());
+        L.launches += 4;
+        CK(cudaGetLastError());
+        if (timing && l == 0) cudaEventRecord(L.ev_s[0], L.stream);
+        Tree tree(*this, L);
+        if ((rc = tree.plan0(len0, p.nseg, true))) return rc;
+    }
     MsmStats stt;
     stt.window_bits = c;
     stt.windows = W;
-    // ---- bucket accumulation: one segment per (window, bucket)
-    want_k = timing;
-    rc = tree.reduce(d_points, entries.as<uint32_t>(), d_start, d_len, nseg, total, 0, buckets.as<AffPt>(),
-                     &stt.rounds_main);
-    if (rc) return rc;
-    want_k = false;
-    if (timing) {
-        // info[1] still holds the task count of the last planned round; round 0's count is read separately
-        cudaEventRecord(ev[2], st);
+    stt.lanes = NL;
+    // ---- per lane: accumulate buckets, then the two reduction levels into this lane's slice of hb
+    for (int l = 0; l < NL; l++) {
+        MsmLane &L = lanes[l];
+        const Part &p = part[l];
+        Tree tree(*this, L);
+        CK(cudaStreamSynchronize(L.stream)); // the 16-byte read-back that sizes this lane's rounds
+        const uint32_t maxlen = ((uint32_t *)L.h_info)[0];
+        if (l == 0) stt.adds_round0 = ((uint32_t *)L.h_info)[1];
+        const uint32_t *len0 = d_len_all + (size_t)p.w0 * nb;
+        L.want_k = timing && l == 0;
+        int r_main = 0, r_a = 0, r_b = 0;
+        rc = tree.rounds(d_points, L.entries.as<uint32_t>(), L.c_start.as<uint32_t>(), len0, p.nseg, p.total, maxlen,
+                         L.buckets.as<AffPt>(), &r_main);
+        if (rc) return rc;
+        L.want_k = false;
+        if (timing && l == 0) cudaEventRecord(L.ev_s[1], L.stream);
+        // level A: row and column sums of each window's bucket matrix
+        uint32_t *d_start = L.c_start.as<uint32_t>(), *d_len = L.c_len.as<uint32_t>();
+        k_gen_level_a<<<cdiv(p.nent_a, 256), 256, 0, L.stream>>>((uint32_t)p.wn, nb, lm, L.ents2.as<uint32_t>());
+        k_gen_segs_a<<<cdiv(p.nseg_a + 1, 256), 256, 0, L.stream>>>((uint32_t)p.wn, nb, lm, d_start, d_len);
+        L.launches += 2;
+        if ((rc = tree.plan0(d_len, p.nseg_a, false))) return rc;
+        rc = tree.rounds(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,
+                         std::max(R, m), L.rc.as<AffPt>(), &r_a);
+        if (rc) return rc;
+        // level B: per-bit subset sums of the row / column sums
+        k_gen_level_b<<<cdiv(p.nent_b, 256), 256, 0, L.stream>>>((uint32_t)p.wn, lr, lm, L.ents2.as<uint32_t>());
+        k_gen_segs_b<<<cdiv(p.nseg_b + 1, 256), 256, 0, L.stream>>>((uint32_t)p.wn, lr, lm, d_start, d_len);
+        L.launches += 2;
+        if ((rc = tree.plan0(d_len, p.nseg_b, false))) return rc;
+        rc = tree.rounds(L.rc.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_b, p.nent_b,
+                         std::max(R >> 1, m), hb.as<AffPt>() + (size_t)p.w0 * c, &r_b);
+        if (rc) return rc;
+        if (timing && l == 0) cudaEventRecord(L.ev_s[2], L.stream);
+        CK(cudaEventRecord(L.done, L.stream));
+        stt.rounds_main = std::max(stt.rounds_main, r_main);
+        stt.rounds_a = r_a;
+        stt.rounds_b = r_b;
     }
-
-    // ---- level A: row and column sums of each window's bucket matrix
-    k_gen_level_a<<<cdiv(nent_a, 256), 256, 0, st>>>((uint32_t)W, nb, lm, ents2.as<uint32_t>());
-    k_gen_segs_a<<<cdiv(nseg_a + 1, 256), 256, 0, st>>>((uint32_t)W, nb, lm, d_start, d_len);
-    launches += 2;
-    rc = tree.reduce(buckets.as<AffPt>(), ents2.as<uint32_t>(), d_start, d_len, nseg_a, nent_a, std::max(R, m),
-                     this->rc.as<AffPt>(), &stt.rounds_a);
-    if (rc) return rc;
-    // ---- level B: per-bit subset sums of the row / column sums
-    k_gen_level_b<<<cdiv(nent_b, 256), 256, 0, st>>>((uint32_t)W, lr, lm, ents2.as<uint32_t>());
-    k_gen_segs_b<<<cdiv(nseg_b + 1, 256), 256, 0, st>>>((uint32_t)W, lr, lm, d_start, d_len);
-    launches += 2;
-    rc = tree.reduce(this->rc.as<AffPt>(), ents2.as<uint32_t>(), d_start, d_len, nseg_b, nent_b,
-                     std::max(R >> 1, m), hb.as<AffPt>(), &stt.rounds_b);
-    if (rc) return rc;
+    for (int l = 0; l < NL; l++) {
+        CK(cudaStreamWaitEvent(st, lanes[l].done, 0));
+        launches += lanes[l].launches;
+    }
     CK(cudaMemcpyAsync(h_pts, hb.as<AffPt>(), hb_bytes, cudaMemcpyDeviceToHost, st));
-    if (timing) cudaEventRecord(ev[3], st);
+    if (timing) cudaEventRecord(ev[1], st);
     CK(cudaStreamSynchronize(st));
 
     // ---- host tail: sum_w 2^(off_w) [ sum_{q<c-1} 2^q HB[w][q] + HB[w][c-1] ], one double-and-add pass
@@ -928,14 +1002,16 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     }
     stt.launches = launches;
     if (timing) {
-        cudaEventRecord(ev[4], st);
-        cudaEventSynchronize(ev[4]);
-        cudaEventElapsedTime(&stt.ms_recode_sort, ev[0], ev[1]);
-        cudaEventElapsedTime(&stt.ms_accumulate, ev[1], ev[2]);
-        cudaEventElapsedTime(&stt.ms_reduce, ev[2], ev[3]);
-        cudaEventElapsedTime(&stt.ms_tail, ev[3], ev[4]);
-        if (stt.rounds_main > 0) cudaEventElapsedTime(&stt.ms_pass2_round0, ev_k[0], ev_k[1]);
-        stt.adds_round0 = h_round0_tasks;
+        cudaEventRecord(ev[2], st);
+        cudaEventSynchronize(ev[2]);
+        MsmLane &L0 = lanes[0];
+        float t_all = 0;
+        cudaEventElapsedTime(&t_all, ev[0], ev[1]);
+        cudaEventElapsedTime(&stt.ms_recode_sort, ev[0], L0.ev_s[0]);
+        cudaEventElapsedTime(&stt.ms_accumulate, L0.ev_s[0], L0.ev_s[1]);
+        cudaEventElapsedTime(&stt.ms_reduce, L0.ev_s[1], L0.ev_s[2]);
+        cudaEventElapsedTime(&stt.ms_tail, ev[1], ev[2]);
+        if (stt.rounds_main > 0) cudaEventElapsedTime(&stt.ms_pass2_round0, L0.ev_k[0], L0.ev_k[1]);
     }
     last = stt;
     return 0;

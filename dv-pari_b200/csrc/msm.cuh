@@ -2,6 +2,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <vector>
 #include <cuda_runtime.h>
 #include "k233.cuh"
 
@@ -17,7 +18,7 @@ struct DevBuf {
 };
 
 struct MsmStats {
-    int window_bits = 0, windows = 0, rounds_main = 0, rounds_a = 0, rounds_b = 0;
+    int window_bits = 0, windows = 0, rounds_main = 0, rounds_a = 0, rounds_b = 0, lanes = 0;
     unsigned long long launches = 0; // kernels launched by the last msm
     float ms_recode_sort = 0, ms_accumulate = 0, ms_reduce = 0, ms_tail = 0;
     // the dominant kernel: pass 2 of round 0 of the bucket accumulation (one launch)
@@ -25,21 +26,32 @@ struct MsmStats {
     unsigned long long adds_round0 = 0, adds_total = 0;
 };
 
-struct MsmEngine {
+// One independent chain of tree rounds: its own stream and scratch.  The windows of an MSM are split
+// over the lanes so that the latency-bound late rounds of one lane overlap the big early rounds of another.
+struct MsmLane {
     cudaStream_t stream = nullptr;
-    // scratch
-    DevBuf keys, entries, seg_len[2], seg_start[2], c_len, c_start, task_start, cursor, blk, info, pp[2], prefix, desc,
-        thr_total, thr_inv, lvl_pre[2], lvl_tot[2], lvl_inv[2], buckets, rc, hb, ents2, msqr_tabs;
-    void *h_info = nullptr; // pinned
-    void *h_pts = nullptr;  // pinned, receives the per-bit partial sums
-    size_t h_pts_cap = 0;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_k[2] = {nullptr, nullptr}; // around the dominant kernel
-    unsigned long long h_round0_tasks = 0;    // additions in round 0 of the last reduce with a read-back
-    bool want_k = false;                      // armed for the next pass-2 launch
+    cudaEvent_t done = nullptr;
+    DevBuf entries, seg_len[2], seg_start[2], c_len, c_start, task_start, cursor, blk, info, pp[2], prefix, desc,
+        thr_total, thr_inv, lvl_pre[2], lvl_tot[2], lvl_inv[2], buckets, rc, ents2;
+    void *h_info = nullptr; // pinned, 64 bytes
     unsigned long long launches = 0;
+    // timing of the dominant kernel (lane 0 only)
+    cudaEvent_t ev_k[2] = {nullptr, nullptr}, ev_s[3] = {nullptr, nullptr, nullptr};
+    bool want_k = false;
+    int init();
+    void destroy();
+};
+
+struct MsmEngine {
+    cudaStream_t stream = nullptr; // the context's stream: recode, final read-back
+    std::vector<MsmLane> lanes;
+    DevBuf keys, len_all, hb, msqr_tabs;
+    void *h_pts = nullptr; // pinned, receives the per-bit partial sums
+    size_t h_pts_cap = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}, ev_recode = nullptr;
     MsmStats last;
     int force_window_bits = 0; // 0 = choose from n
+    int force_lanes = 0;       // 0 = choose from n
     bool timing = false;
     int pass2_minb = 2; // resident blocks per SM the pass-2 kernel is compiled for (register cap)
 

@@ -53,7 +53,8 @@ int dvp_abi_version(void);
 /* One context = one CUDA device + one private stream + grow-only scratch. */
 int dvp_ctx_create(int device, dvp_ctx **out);
 void dvp_ctx_destroy(dvp_ctx *ctx);
-/* knobs: "msm_window_bits" (0 = automatic), "timing" (0/1).  Unknown name -> DVP_ERR_BAD_ARG. */
+/* knobs: "msm_window_bits" (0 = automatic), "msm_lanes" (0 = automatic: concurrent window groups),
+ * "pass2_minb" (1..3), "timing" (0/1).  Unknown name -> DVP_ERR_BAD_ARG. */
 int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value);
 
 /*
