@@ -256,6 +256,15 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
         ctx->msm.force_lanes = (int)value;
         return DVP_OK;
     }
+    if (!strcmp(name, "binv_direct")) {
+        if (value < 64 || value > (1 << 20)) return DVP_ERR_BAD_ARG;
+        ctx->msm.binv_direct = (uint32_t)value;
+        return DVP_OK;
+    }
+    if (!strcmp(name, "msm_profile")) {
+        ctx->msm.profile = value != 0;
+        return DVP_OK;
+    }
     if (!strcmp(name, "pass2_minb")) {
         if (value < 1 || value > 3) return DVP_ERR_BAD_ARG;
         ctx->msm.pass2_minb = (int)value;
@@ -386,6 +395,17 @@ int dvp_msm_last_stats(dvp_ctx *ctx, dvp_msm_stats *out) {
     out->ms_tail = s.ms_tail;
     out->ms_pass2_round0 = s.ms_pass2_round0;
     out->adds_round0 = s.adds_round0;
+    return DVP_OK;
+}
+
+/* development: per-category kernel time of the last MSM run with the "msm_profile" knob set.
+ * categories: 0 sort 1 plan 2 pass1 3 binv_up 4 binv_direct 5 binv_down 6 pass2 7 misc */
+int dvp_msm_last_profile(dvp_ctx *ctx, float ms[8], unsigned count[8]) {
+    if (!ctx || !ms || !count) return DVP_ERR_BAD_ARG;
+    for (int i = 0; i < 8; i++) {
+        ms[i] = i < dvp::PC_COUNT ? ctx->msm.prof_ms[i] : 0.f;
+        count[i] = i < dvp::PC_COUNT ? ctx->msm.prof_n[i] : 0u;
+    }
     return DVP_OK;
 }
 

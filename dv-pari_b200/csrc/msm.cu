@@ -6,6 +6,7 @@
 //
 //   recode      Montgomery Fr -> canonical 232-bit integer -> W signed c-bit digits
 //   sort        counting sort of (point, window) entries by bucket (histogram, scan, scatter)
+//   plan        per round one launch: scans over the segment lengths + one (a, b, out) descriptor per addition
 //   accumulate  every bucket is a segment; segments are tree-reduced in rounds of independent
 //               affine additions sharing one inversion (Montgomery trick, hierarchical)
 //   reduce      sum_b (b+1) B_b per window without a serial running sum: rows/columns of the bucket
@@ -293,71 +294,136 @@ __global__ void k_scan3(const uint32_t *__restrict__ len, uint32_t nseg, const u
 // ------------------------------------------------------------------------------------------------
 // tree rounds
 // ------------------------------------------------------------------------------------------------
-template <bool INDEXED>
-__device__ __forceinline__ gf fetch_x(const AffPt *__restrict__ src, const uint32_t *__restrict__ ent, uint32_t pos) {
-    if (INDEXED) return gf_load(&src[ent[pos] & 0x7fffffffu].x);
-    return gf_load(&src[pos].x);
+// An entry names a point of the source list: index in bits 0..30, bit 31 = negate (round 0 only).
+__device__ __forceinline__ AffPt fetch_entry(const AffPt *__restrict__ src, uint32_t e) {
+    AffPt p = pt_load(&src[e & 0x7fffffffu]);
+    if (e >> 31) p.y = gf_add(p.y, p.x);
+    return p;
 }
 template <bool INDEXED>
 __device__ __forceinline__ AffPt fetch_pt(const AffPt *__restrict__ src, const uint32_t *__restrict__ ent, uint32_t pos) {
-    if (INDEXED) {
-        const uint32_t e = ent[pos];
-        AffPt p = pt_load(&src[e & 0x7fffffffu]);
-        if (e >> 31) p.y = gf_add(p.y, p.x);
-        return p;
-    }
-    return pt_load(&src[pos]);
+    return fetch_entry(src, INDEXED ? ent[pos] : pos);
 }
 
-// largest s in [0, nseg) with start[s] <= t  (start has nseg + 1 entries, start[nseg] = total > t)
-__device__ __forceinline__ uint32_t seg_search(const uint32_t *__restrict__ start, uint32_t nseg, uint32_t t) {
-    uint32_t lo = 0, hi = nseg; // invariant: start[lo] <= t < start[hi]
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (start[mid] <= t) lo = mid;
-        else hi = mid;
+// ------------------------------------------------------------------------------------------------
+// plan of one round, one launch: exclusive scans of (L/2, (L+1)/2) over the segment lengths, the
+// segment tables of the next round, and one descriptor (a, b, out) per addition so that the two
+// passes never search for their segment.  Blocks publish their aggregates and every block sums its
+// predecessors' (no chain): the grid is small enough to be co-resident.
+//   info[0] = max L, info[1] = additions of this round, info[2] = points after this round
+// ------------------------------------------------------------------------------------------------
+constexpr int PLAN_THREADS = 256;
+
+__global__ void __launch_bounds__(PLAN_THREADS)
+    k_plan(const uint32_t *__restrict__ len, const uint32_t *__restrict__ in_start, const uint32_t *__restrict__ ent,
+           uint32_t nseg, uint32_t items, uint64_t *__restrict__ blk_sum, uint32_t *__restrict__ blk_flag, uint32_t epoch,
+           uint32_t *__restrict__ out_start, uint32_t *__restrict__ new_len, uint4 *__restrict__ desc,
+           uint32_t *__restrict__ info) {
+    __shared__ uint64_t sh[PLAN_THREADS / 32];
+    __shared__ uint64_t sh_base;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t base = (blockIdx.x * PLAN_THREADS + threadIdx.x) * items;
+    // phase 1: aggregate of this block
+    uint64_t s = 0;
+    uint32_t mx = 0;
+    for (uint32_t k = 0; k < items; k++) {
+        const uint32_t idx = base + k;
+        const uint32_t L = idx < nseg ? len[idx] : 0;
+        s += (uint64_t)(L >> 1) | ((uint64_t)((L + 1) >> 1) << 32);
+        mx = max(mx, L);
     }
-    return lo;
+    uint64_t incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    if (lane == 0 && mx) atomicMax(&info[0], mx);
+    if (lane == 31) sh[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const uint64_t w = lane < PLAN_THREADS / 32 ? sh[lane] : 0;
+        uint64_t wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        if (lane < PLAN_THREADS / 32) sh[lane] = wi - w; // exclusive offsets of the warps
+        if (lane == PLAN_THREADS / 32 - 1) {
+            blk_sum[blockIdx.x] = wi; // block aggregate
+            __threadfence();
+            atomicExch(&blk_flag[blockIdx.x], epoch);
+        }
+        // phase 2: sum of the predecessors' aggregates
+        uint64_t p = 0;
+        for (uint32_t b = lane; b < blockIdx.x; b += 32) {
+            while (atomicAdd(&blk_flag[b], 0u) != epoch) __nanosleep(20);
+            __threadfence();
+            p += *reinterpret_cast<volatile uint64_t *>(&blk_sum[b]);
+        }
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_down_sync(0xffffffffu, p, o);
+        if (lane == 0) sh_base = p;
+    }
+    __syncthreads();
+    // phase 3: outputs
+    uint64_t run = sh_base + sh[wid] + (incl - s);
+    for (uint32_t k = 0; k < items; k++) {
+        const uint32_t idx = base + k;
+        uint32_t L = 0, in = 0;
+        if (idx < nseg) {
+            L = len[idx];
+            in = in_start[idx];
+            out_start[idx] = (uint32_t)(run >> 32);
+            new_len[idx] = (L + 1) >> 1;
+        }
+        const uint32_t nt = L >> 1, ts = (uint32_t)run, os = (uint32_t)(run >> 32);
+        // descriptors, written by the whole warp for one segment at a time
+        uint32_t todo = __ballot_sync(0xffffffffu, nt > 0);
+        while (todo) {
+            const int src_lane = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t nt_b = __shfl_sync(0xffffffffu, nt, src_lane), ts_b = __shfl_sync(0xffffffffu, ts, src_lane);
+            const uint32_t in_b = __shfl_sync(0xffffffffu, in, src_lane), os_b = __shfl_sync(0xffffffffu, os, src_lane);
+            for (uint32_t j = lane; j < nt_b; j += 32) {
+                uint32_t a = in_b + 2 * j, b = a + 1;
+                if (ent) {
+                    a = ent[a];
+                    b = ent[b];
+                }
+                desc[ts_b + j] = make_uint4(a, b, os_b + j, 0);
+            }
+        }
+        run += (uint64_t)(L >> 1) | ((uint64_t)((L + 1) >> 1) << 32);
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == PLAN_THREADS - 1) {
+        out_start[nseg] = (uint32_t)(run >> 32);
+        info[1] = (uint32_t)run;
+        info[2] = (uint32_t)(run >> 32);
+    }
 }
 
-// pass 1: per task resolve (a, b, out), form the denominator, chain a per-thread prefix product
-template <bool INDEXED, int B>
+// pass 1: per task form the denominator and chain a per-thread prefix product
+template <int B>
 __global__ void __launch_bounds__(256)
-    k_pass1(const AffPt *__restrict__ src, const uint32_t *__restrict__ ent, const uint32_t *__restrict__ in_start,
-            const uint32_t *__restrict__ task_start, const uint32_t *__restrict__ out_start, uint32_t nseg,
-            const uint32_t *__restrict__ info, uint4 *__restrict__ desc, gf *__restrict__ prefix,
-            gf *__restrict__ thr_total) {
+    k_pass1(const AffPt *__restrict__ src, const uint32_t *__restrict__ info, const uint4 *__restrict__ desc,
+            gf *__restrict__ prefix, gf *__restrict__ thr_total) {
     const uint32_t ntasks = info[1];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = gtid & 31, warp = gtid >> 5;
     const uint32_t base = warp * (32u * B);
+    if (base >= ntasks) return;
     gf acc = gf_one();
-    uint32_t s = 0xffffffffu;
 #pragma unroll 1
     for (int k = 0; k < B; k++) {
         const uint32_t t = base + k * 32 + lane;
         if (t >= ntasks) break;
-        if (s == 0xffffffffu) s = seg_search(task_start, nseg, t);
-        else {
-            // the next task is usually in the same or the next segment; runs of empty segments
-            // (finished buckets, unused bucket slots) are skipped by a fresh binary search
-            int steps = 0;
-            while (task_start[s + 1] <= t) {
-                s++;
-                if (++steps == 4) {
-                    s = seg_search(task_start, nseg, t);
-                    break;
-                }
-            }
-        }
-        const uint32_t j = t - task_start[s];
-        const uint32_t a = in_start[s] + 2 * j, o = out_start[s] + j;
-        desc[t] = make_uint4(a, a + 1, o, 0);
-        const gf x1 = fetch_x<INDEXED>(src, ent, a), x2 = fetch_x<INDEXED>(src, ent, a + 1);
+        const uint4 de = desc[t];
+        const uint32_t ia = de.x & 0x7fffffffu, ib = de.y & 0x7fffffffu;
+        const gf x1 = gf_load(&src[ia].x), x2 = gf_load(&src[ib].x);
         gf d = gf_add(x1, x2);
         if (gf_is_zero(x1) | gf_is_zero(x2)) d = gf_one();
         else if (gf_is_zero(d)) {
-            const AffPt p1 = fetch_pt<INDEXED>(src, ent, a), p2 = fetch_pt<INDEXED>(src, ent, a + 1);
+            const AffPt p1 = fetch_entry(src, de.x), p2 = fetch_entry(src, de.y);
             d = gf_eq(p1.y, p2.y) ? x1 : gf_one();
         }
         gf_store(&prefix[t], acc);
@@ -372,11 +438,10 @@ __global__ void __launch_bounds__(256)
 __device__ __noinline__ gf gf_mul_call(const gf a, const gf b) { return gf_mul(a, b); }
 
 // pass 2: walk the same tasks backwards with the inverse of the thread total, finish the additions
-template <bool INDEXED, int B, int MINB>
+template <int B, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-    k_pass2(const AffPt *__restrict__ src, const uint32_t *__restrict__ ent, const uint32_t *__restrict__ info,
-            const uint4 *__restrict__ desc, const gf *__restrict__ prefix, const gf *__restrict__ thr_inv,
-            AffPt *__restrict__ dst) {
+    k_pass2(const AffPt *__restrict__ src, const uint32_t *__restrict__ info, const uint4 *__restrict__ desc,
+            const gf *__restrict__ prefix, const gf *__restrict__ thr_inv, AffPt *__restrict__ dst) {
     const uint32_t ntasks = info[1];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = gtid & 31, warp = gtid >> 5;
@@ -388,7 +453,7 @@ __global__ void __launch_bounds__(256, MINB)
         const uint32_t t = base + k * 32 + lane;
         if (t >= ntasks) continue;
         const uint4 de = desc[t];
-        const AffPt p1 = fetch_pt<INDEXED>(src, ent, de.x), p2 = fetch_pt<INDEXED>(src, ent, de.y);
+        const AffPt p1 = fetch_entry(src, de.x), p2 = fetch_entry(src, de.y);
         gf d;
         const int kind = pair_classify(p1, p2, d);
         const gf dinv = gf_mul_call(inv, gf_load(&prefix[t]));
@@ -500,13 +565,24 @@ __global__ void k_latency_probe(int mode, int iters, const gf *__restrict__ tabs
 // ------------------------------------------------------------------------------------------------
 // hierarchical batched inversion of n non-zero field elements
 // ------------------------------------------------------------------------------------------------
-__global__ void k_binv_direct(const gf *__restrict__ in, gf *__restrict__ out, uint32_t n, const gf *__restrict__ tabs) {
+// The number of live elements is only known on the device: n0 = whole warps of pass-1 threads that own
+// at least one task (info[1] tasks, `unit` = 32 B tasks per warp), then divided by the fan-ins above.
+__device__ __forceinline__ uint32_t binv_count(const uint32_t *__restrict__ info, uint32_t unit, uint32_t div1,
+                                               uint32_t div2) {
+    uint32_t n = ((info[1] + unit - 1) / unit) * 32u;
+    n = (n + div1 - 1) / div1;
+    return (n + div2 - 1) / div2;
+}
+__global__ void k_binv_direct(const gf *__restrict__ in, gf *__restrict__ out, const uint32_t *__restrict__ info,
+                              uint32_t unit, uint32_t div1, uint32_t div2, const gf *__restrict__ tabs) {
+    const uint32_t n = binv_count(info, unit, div1, div2);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     gf_store(&out[i], gf_inv_tab(gf_load(&in[i]), tabs));
 }
-__global__ void k_binv_up(const gf *__restrict__ in, uint32_t n, uint32_t G, gf *__restrict__ pre,
-                          gf *__restrict__ tot) {
+__global__ void k_binv_up(const gf *__restrict__ in, const uint32_t *__restrict__ info, uint32_t unit, uint32_t div1,
+                          uint32_t div2, uint32_t G, gf *__restrict__ pre, gf *__restrict__ tot) {
+    const uint32_t n = binv_count(info, unit, div1, div2);
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lo = g * G;
     if (lo >= n) return;
@@ -518,8 +594,10 @@ __global__ void k_binv_up(const gf *__restrict__ in, uint32_t n, uint32_t G, gf 
     }
     gf_store(&tot[g], acc);
 }
-__global__ void k_binv_down(const gf *__restrict__ in, uint32_t n, uint32_t G, const gf *__restrict__ pre,
-                            const gf *__restrict__ tot_inv, gf *__restrict__ out) {
+__global__ void k_binv_down(const gf *__restrict__ in, const uint32_t *__restrict__ info, uint32_t unit, uint32_t div1,
+                            uint32_t div2, uint32_t G, const gf *__restrict__ pre, const gf *__restrict__ tot_inv,
+                            gf *__restrict__ out) {
+    const uint32_t n = binv_count(info, unit, div1, div2);
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lo = g * G;
     if (lo >= n) return;
@@ -629,9 +707,27 @@ int MsmLane::init() {
     for (auto &e : ev_s) CK(cudaEventCreate(&e));
     return 0;
 }
+void MsmLane::prof_begin(int cat) {
+    if (prof_used == prof.size()) {
+        ProfRec r{cat, nullptr, nullptr};
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        prof.push_back(r);
+    }
+    prof[prof_used].cat = cat;
+    cudaEventRecord(prof[prof_used].e0, stream);
+}
+void MsmLane::prof_end() { cudaEventRecord(prof[prof_used++].e1, stream); }
+
 void MsmLane::destroy() {
-    DevBuf *all[] = {&entries, &seg_len[0], &seg_len[1], &seg_start[0], &seg_start[1], &c_len, &c_start, &task_start,
-                     &cursor, &blk, &info, &pp[0], &pp[1], &prefix, &desc, &thr_total, &thr_inv, &lvl_pre[0],
+    for (auto &r : prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    prof.clear();
+    prof_used = 0;
+    DevBuf *all[] = {&entries, &seg_len[0], &seg_len[1], &seg_start[0], &seg_start[1], &c_len, &c_start,
+                     &cursor, &blk, &blk_flag, &info, &pp[0], &pp[1], &prefix, &desc, &thr_total, &thr_inv, &lvl_pre[0],
                      &lvl_pre[1], &lvl_tot[0], &lvl_tot[1], &lvl_inv[0], &lvl_inv[1], &buckets, &rc, &ents2};
     for (auto b : all) b->release();
     if (h_info) cudaFreeHost(h_info);
@@ -672,95 +768,111 @@ void MsmEngine::destroy() {
 
 namespace {
 
+constexpr uint32_t PLAN_MAX_BLOCKS = 256; // k_plan's grid must be co-resident (blocks wait for their predecessors)
 constexpr uint32_t BINV_G = 16;        // group size of one batched-inversion level (large batches)
-constexpr uint32_t BINV_DIRECT = 8192; // at or below this many elements every thread inverts its own
 
 struct Tree {
     MsmEngine &E;
     MsmLane &L;
     cudaStream_t st;
     Tree(MsmEngine &e, MsmLane &l) : E(e), L(l), st(l.stream) {}
+    // development profiler: CUDA events around the launches of one category (E.profile, see MsmLane)
+    void pb(int cat) {
+        if (E.profile) L.prof_begin(cat);
+    }
+    void pe() {
+        if (E.profile) L.prof_end();
+    }
 
-    int scan_plan(const uint32_t *len, uint32_t nseg, uint32_t *task_start, uint32_t *out_start, uint32_t *new_len) {
-        const uint32_t nblk = cdiv(nseg, SCAN_TILE);
-        k_scan1<1><<<nblk, SCAN_THREADS, 0, st>>>(len, nseg, L.blk.as<uint64_t>(), L.info.as<uint32_t>());
-        k_scan2<<<1, SCAN_THREADS, 0, st>>>(L.blk.as<uint64_t>(), nblk);
-        k_scan3<1><<<nblk, SCAN_THREADS, 0, st>>>(len, nseg, L.blk.as<uint64_t>(), task_start, out_start, new_len,
-                                                  L.info.as<uint32_t>());
-        L.launches += 3;
+    // one launch: scans, next segment tables, descriptors; zeroes nothing itself (info is cleared here)
+    int plan(const uint32_t *len, const uint32_t *in_start, const uint32_t *ent, uint32_t nseg, uint32_t *out_start,
+             uint32_t *new_len) {
+        uint32_t items = 1;
+        while (cdiv(nseg, items * PLAN_THREADS) > PLAN_MAX_BLOCKS) items++;
+        const uint32_t nblk = cdiv(nseg, items * PLAN_THREADS);
+        pb(PC_PLAN);
+        CK(cudaMemsetAsync(L.info.p, 0, 16, st));
+        k_plan<<<nblk, PLAN_THREADS, 0, st>>>(len, in_start, ent, nseg, items, L.blk.as<uint64_t>(),
+                                              L.blk_flag.as<uint32_t>(), ++L.epoch, out_start, new_len,
+                                              L.desc.as<uint4>(), L.info.as<uint32_t>());
+        pe();
+        L.launches++;
         CK(cudaGetLastError());
         return 0;
     }
 
-    // n non-zero elements in -> inverses out
-    int batch_inv(const gf *in, gf *out, uint32_t n, int depth) {
-        if (n <= BINV_DIRECT || depth >= 2) {
-            k_binv_direct<<<cdiv(n, 64), 64, 0, st>>>(in, out, n, E.msqr_tabs.as<gf>());
+    // inverses of the pass-1 thread totals; n_ub bounds their number, the live count is read on the device
+    int batch_inv(const gf *in, gf *out, uint32_t n_ub, uint32_t unit, uint32_t div1, uint32_t div2, int depth) {
+        const uint32_t *info = L.info.as<uint32_t>();
+        const uint32_t BINV_DIRECT = E.binv_direct; // at or below this many elements every thread inverts its own
+        if (n_ub <= BINV_DIRECT || depth >= 2) {
+            pb(PC_BINV_DIRECT);
+            k_binv_direct<<<cdiv(n_ub, 64), 64, 0, st>>>(in, out, info, unit, div1, div2, E.msqr_tabs.as<gf>());
+            pe();
             L.launches++;
             CK(cudaGetLastError());
             return 0;
         }
-        // small batches are latency-bound (serial multiplications per thread): use a small fan-in
-        const uint32_t G = n <= 16 * BINV_DIRECT ? (n <= 4 * BINV_DIRECT ? 4 : 8) : BINV_G;
-        const uint32_t ng = cdiv(n, G);
+        // the smallest fan-in that reaches a directly invertible batch: the serial multiplications per
+        // thread are pure latency for small batches
+        uint32_t G = 2;
+        while (G < BINV_G && cdiv(n_ub, G) > BINV_DIRECT) G <<= 1;
+        const uint32_t ng = cdiv(n_ub, G);
         gf *pre = L.lvl_pre[depth].as<gf>(), *tot = L.lvl_tot[depth].as<gf>(), *inv = L.lvl_inv[depth].as<gf>();
-        k_binv_up<<<cdiv(ng, 64), 64, 0, st>>>(in, n, G, pre, tot);
+        pb(PC_BINV_UP);
+        k_binv_up<<<cdiv(ng, 64), 64, 0, st>>>(in, info, unit, div1, div2, G, pre, tot);
+        pe();
         L.launches++;
-        int rc = batch_inv(tot, inv, ng, depth + 1);
+        int rc = depth == 0 ? batch_inv(tot, inv, ng, unit, G, 1, 1) : batch_inv(tot, inv, ng, unit, div1, G, 2);
         if (rc) return rc;
-        k_binv_down<<<cdiv(ng, 64), 64, 0, st>>>(in, n, G, pre, inv, out);
+        pb(PC_BINV_DOWN);
+        k_binv_down<<<cdiv(ng, 64), 64, 0, st>>>(in, info, unit, div1, div2, G, pre, inv, out);
+        pe();
         L.launches++;
         CK(cudaGetLastError());
         return 0;
     }
 
-    template <bool INDEXED, int B>
-    int round(const AffPt *src, const uint32_t *ent, const uint32_t *in_start, const uint32_t *len,
-              const uint32_t *task_start, const uint32_t *out_start, uint32_t nseg, size_t task_ub, AffPt *dst) {
+    template <int B> int round_t(const AffPt *src, size_t task_ub, AffPt *dst) {
         const uint32_t nblk = cdiv(cdiv(task_ub, B), 256);
         const uint32_t nthr = nblk * 256;
-        k_pass1<INDEXED, B><<<nblk, 256, 0, st>>>(src, ent, in_start, task_start, out_start, nseg,
-                                                  L.info.as<uint32_t>(), L.desc.as<uint4>(), L.prefix.as<gf>(),
-                                                  L.thr_total.as<gf>());
+        const uint32_t *info = L.info.as<uint32_t>();
+        pb(PC_PASS1);
+        k_pass1<B><<<nblk, 256, 0, st>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_total.as<gf>());
+        pe();
         L.launches++;
-        int rc = batch_inv(L.thr_total.as<gf>(), L.thr_inv.as<gf>(), nthr, 0);
+        int rc = batch_inv(L.thr_total.as<gf>(), L.thr_inv.as<gf>(), nthr, 32u * B, 1, 1, 0);
         if (rc) return rc;
         const bool mark = L.want_k;
         if (mark) cudaEventRecord(L.ev_k[0], st);
+        pb(PC_PASS2);
         if (E.pass2_minb == 2)
-            k_pass2<INDEXED, B, 2><<<nblk, 256, 0, st>>>(src, ent, L.info.as<uint32_t>(), L.desc.as<uint4>(),
-                                                         L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
+            k_pass2<B, 2><<<nblk, 256, 0, st>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
         else if (E.pass2_minb == 3)
-            k_pass2<INDEXED, B, 3><<<nblk, 256, 0, st>>>(src, ent, L.info.as<uint32_t>(), L.desc.as<uint4>(),
-                                                         L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
+            k_pass2<B, 3><<<nblk, 256, 0, st>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
         else
-            k_pass2<INDEXED, B, 1><<<nblk, 256, 0, st>>>(src, ent, L.info.as<uint32_t>(), L.desc.as<uint4>(),
-                                                         L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
+            k_pass2<B, 1><<<nblk, 256, 0, st>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
+        pe();
         if (mark) {
             cudaEventRecord(L.ev_k[1], st);
             L.want_k = false;
         }
-        k_copy_odd<INDEXED><<<cdiv(nseg, 256), 256, 0, st>>>(src, ent, in_start, len, out_start, nseg, dst);
-        L.launches += 2;
+        L.launches++;
         CK(cudaGetLastError());
         return 0;
     }
-
-    template <bool INDEXED>
-    int round_b(int B, const AffPt *src, const uint32_t *ent, const uint32_t *in_start, const uint32_t *len,
-                const uint32_t *task_start, const uint32_t *out_start, uint32_t nseg, size_t task_ub, AffPt *dst) {
-        if (B == 16) return round<INDEXED, 16>(src, ent, in_start, len, task_start, out_start, nseg, task_ub, dst);
-        if (B == 4) return round<INDEXED, 4>(src, ent, in_start, len, task_start, out_start, nseg, task_ub, dst);
-        return round<INDEXED, 1>(src, ent, in_start, len, task_start, out_start, nseg, task_ub, dst);
+    int round(int B, const AffPt *src, size_t task_ub, AffPt *dst) {
+        if (B == 16) return round_t<16>(src, task_ub, dst);
+        if (B == 4) return round_t<4>(src, task_ub, dst);
+        return round_t<1>(src, task_ub, dst);
     }
 
-    // Plan of round 0: caller tables -> engine set 1; info[0] = longest segment, info[1] = tasks of round 0.
-    int plan0(const uint32_t *len0, uint32_t nseg, bool readback) {
-        uint32_t *info = L.info.as<uint32_t>();
-        CK(cudaMemsetAsync(info, 0, 16, st));
-        int rc = scan_plan(len0, nseg, L.task_start.as<uint32_t>(), L.seg_start[1].as<uint32_t>(), L.seg_len[1].as<uint32_t>());
+    // Plan of round 0: caller tables -> lane set 1 (+ descriptors); info[0] = longest segment,
+    // info[1] = additions of round 0.
+    int plan0(const uint32_t *start0, const uint32_t *len0, const uint32_t *ent, uint32_t nseg, bool readback) {
+        int rc = plan(len0, start0, ent, nseg, L.seg_start[1].as<uint32_t>(), L.seg_len[1].as<uint32_t>());
         if (rc) return rc;
-        if (readback) CK(cudaMemcpyAsync(L.h_info, info, 16, cudaMemcpyDeviceToHost, st));
+        if (readback) CK(cudaMemcpyAsync(L.h_info, L.info.p, 16, cudaMemcpyDeviceToHost, st));
         return 0;
     }
 
@@ -769,14 +881,15 @@ struct Tree {
     // be the lane's own seg_start[] / seg_len[] ping-pong arrays.  total_ub bounds the entry count.
     int rounds(const AffPt *src, const uint32_t *ent, const uint32_t *start0, const uint32_t *len0, uint32_t nseg,
                size_t total_ub, uint32_t maxlen, AffPt *dst, int *rounds_out) {
-        uint32_t *ts = L.task_start.as<uint32_t>(), *info = L.info.as<uint32_t>();
         uint32_t *elen[2] = {L.seg_len[0].as<uint32_t>(), L.seg_len[1].as<uint32_t>()};
         uint32_t *estart[2] = {L.seg_start[0].as<uint32_t>(), L.seg_start[1].as<uint32_t>()};
         int nr = 0;
         while ((1ull << nr) < maxlen) nr++;
         if (rounds_out) *rounds_out = nr;
         if (nr == 0) {
+            pb(PC_MISC);
             k_finalize<true><<<cdiv(nseg, 256), 256, 0, st>>>(src, ent, start0, len0, nseg, dst);
+            pe();
             L.launches++;
             CK(cudaGetLastError());
             return 0;
@@ -790,19 +903,21 @@ struct Tree {
             const size_t task_ub = (total_ub >> (r + 1)) + nseg / 2 + 1;
             const int B = task_ub >= (1u << 21) ? 16 : task_ub >= (1u << 17) ? 4 : 1;
             AffPt *out = L.pp[r & 1].as<AffPt>();
-            if (r == 0) rc = round_b<true>(B, src, ent, in_start, in_len, ts, estart[o], nseg, task_ub, out);
-            else rc = round_b<false>(B, cur_src, nullptr, in_start, in_len, ts, estart[o], nseg, task_ub, out);
-            if (rc) return rc;
+            if ((rc = round(B, cur_src, task_ub, out))) return rc;
+            pb(PC_MISC);
+            if (r == 0) k_copy_odd<true><<<cdiv(nseg, 256), 256, 0, st>>>(src, ent, in_start, in_len, estart[o], nseg, out);
+            else k_copy_odd<false><<<cdiv(nseg, 256), 256, 0, st>>>(cur_src, nullptr, in_start, in_len, estart[o], nseg, out);
+            pe();
+            L.launches++;
+            CK(cudaGetLastError());
             cur_src = out;
             in_start = estart[o];
             in_len = elen[o];
-            if (r + 1 < nr) {
-                CK(cudaMemsetAsync(info, 0, 16, st));
-                rc = scan_plan(in_len, nseg, ts, estart[o ^ 1], elen[o ^ 1]);
-                if (rc) return rc;
-            }
+            if (r + 1 < nr && (rc = plan(in_len, in_start, nullptr, nseg, estart[o ^ 1], elen[o ^ 1]))) return rc;
         }
+        pb(PC_MISC);
         k_finalize<false><<<cdiv(nseg, 256), 256, 0, st>>>(cur_src, nullptr, in_start, in_len, nseg, dst);
+        pe();
         L.launches++;
         CK(cudaGetLastError());
         return 0;
@@ -830,7 +945,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     const uint32_t R = 1u << lr, m = 1u << lm;
     const uint32_t per_b = lm * (m >> 1) + lr * (R >> 1) + m;
     // lanes: independent chains of rounds over disjoint window ranges
-    int NL = force_lanes ? force_lanes : (n >= (1u << 17) ? 4 : n >= (1u << 13) ? 2 : 1);
+    int NL = profile ? 1 : force_lanes ? force_lanes : (n >= (1u << 13) ? 2 : 1);
     NL = std::max(1, std::min(NL, W));
     while ((int)lanes.size() < NL) {
         lanes.emplace_back();
@@ -870,9 +985,13 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         }
         RS(L.c_len, nseg_max * 4);
         RS(L.c_start, nseg_max * 4);
-        RS(L.task_start, nseg_max * 4);
         RS(L.cursor, nseg_max * 4);
-        RS(L.blk, (nseg_max / SCAN_TILE + 8) * 8);
+        RS(L.blk, (std::max<size_t>(nseg_max / SCAN_TILE, PLAN_MAX_BLOCKS) + 8) * 8);
+        if (!L.blk_flag.p) {
+            RS(L.blk_flag, (PLAN_MAX_BLOCKS + 8) * 4);
+            CK(cudaMemsetAsync(L.blk_flag.p, 0, (PLAN_MAX_BLOCKS + 8) * 4, stream));
+            L.epoch = 0;
+        }
         RS(L.info, 64);
         const size_t task_ub0 = ent_max / 2 + nseg_max / 2 + 1; // round-0 bound, the largest
         const size_t out_ub0 = ent_max / 2 + nseg_max + 1;      // outputs of round 0 (ceil halves)
@@ -884,11 +1003,11 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         RS(L.thr_total, thr_ub * sizeof(gf));
         RS(L.thr_inv, thr_ub * sizeof(gf));
         RS(L.lvl_pre[0], thr_ub * sizeof(gf));
-        RS(L.lvl_tot[0], (thr_ub / 4 + 2) * sizeof(gf));
-        RS(L.lvl_inv[0], (thr_ub / 4 + 2) * sizeof(gf));
-        RS(L.lvl_pre[1], (thr_ub / 4 + 2) * sizeof(gf));
-        RS(L.lvl_tot[1], (thr_ub / 16 + 2) * sizeof(gf));
-        RS(L.lvl_inv[1], (thr_ub / 16 + 2) * sizeof(gf));
+        RS(L.lvl_tot[0], (thr_ub / 2 + 2) * sizeof(gf));
+        RS(L.lvl_inv[0], (thr_ub / 2 + 2) * sizeof(gf));
+        RS(L.lvl_pre[1], (thr_ub / 2 + 2) * sizeof(gf));
+        RS(L.lvl_tot[1], (thr_ub / 4 + 2) * sizeof(gf));
+        RS(L.lvl_inv[1], (thr_ub / 4 + 2) * sizeof(gf));
         RS(L.buckets, (size_t)p.nseg * sizeof(AffPt));
         RS(L.rc, (size_t)p.nseg_a * sizeof(AffPt));
         RS(L.ents2, (size_t)std::max(p.nent_a, p.nent_b) * 4);
@@ -920,6 +1039,8 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         CK(cudaStreamWaitEvent(L.stream, ev_recode, 0));
         const uint32_t *len0 = d_len_all + (size_t)p.w0 * nb;
         const uint32_t nblk = cdiv(p.nseg, SCAN_TILE);
+        L.prof_used = 0;
+        if (profile) L.prof_begin(PC_SORT);
         k_scan1<0><<<nblk, SCAN_THREADS, 0, L.stream>>>(len0, p.nseg, L.blk.as<uint64_t>(), L.info.as<uint32_t>());
         k_scan2<<<1, SCAN_THREADS, 0, L.stream>>>(L.blk.as<uint64_t>(), nblk);
         k_scan3<0><<<nblk, SCAN_THREADS, 0, L.stream>>>(len0, p.nseg, L.blk.as<uint64_t>(), L.c_start.as<uint32_t>(),
@@ -927,11 +1048,12 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         k_scatter<<<cdiv(p.total, 256), 256, 0, L.stream>>>(keys.as<uint32_t>() + (size_t)p.w0 * n, (uint32_t)n, p.total,
                                                             (uint32_t)p.w0 * nb, L.cursor.as<uint32_t>(),
                                                             L.entries.as<uint32_t>());
+        if (profile) L.prof_end();
         L.launches += 4;
         CK(cudaGetLastError());
         if (timing && l == 0) cudaEventRecord(L.ev_s[0], L.stream);
         Tree tree(*this, L);
-        if ((rc = tree.plan0(len0, p.nseg, true))) return rc;
+        if ((rc = tree.plan0(L.c_start.as<uint32_t>(), len0, L.entries.as<uint32_t>(), p.nseg, true))) return rc;
     }
     MsmStats stt;
     stt.window_bits = c;
@@ -958,7 +1080,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         k_gen_level_a<<<cdiv(p.nent_a, 256), 256, 0, L.stream>>>((uint32_t)p.wn, nb, lm, L.ents2.as<uint32_t>());
         k_gen_segs_a<<<cdiv(p.nseg_a + 1, 256), 256, 0, L.stream>>>((uint32_t)p.wn, nb, lm, d_start, d_len);
         L.launches += 2;
-        if ((rc = tree.plan0(d_len, p.nseg_a, false))) return rc;
+        if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a, false))) return rc;
         rc = tree.rounds(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,
                          std::max(R, m), L.rc.as<AffPt>(), &r_a);
         if (rc) return rc;
@@ -966,7 +1088,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         k_gen_level_b<<<cdiv(p.nent_b, 256), 256, 0, L.stream>>>((uint32_t)p.wn, lr, lm, L.ents2.as<uint32_t>());
         k_gen_segs_b<<<cdiv(p.nseg_b + 1, 256), 256, 0, L.stream>>>((uint32_t)p.wn, lr, lm, d_start, d_len);
         L.launches += 2;
-        if ((rc = tree.plan0(d_len, p.nseg_b, false))) return rc;
+        if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_b, false))) return rc;
         rc = tree.rounds(L.rc.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_b, p.nent_b,
                          std::max(R >> 1, m), hb.as<AffPt>() + (size_t)p.w0 * c, &r_b);
         if (rc) return rc;
@@ -1001,6 +1123,17 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         *h_result = host::ld_to_affine(acc);
     }
     stt.launches = launches;
+    if (profile) {
+        for (int i = 0; i < PC_COUNT; i++) prof_ms[i] = 0, prof_n[i] = 0;
+        for (int l = 0; l < NL; l++)
+            for (size_t i = 0; i < lanes[l].prof_used; i++) {
+                const auto &r = lanes[l].prof[i];
+                float ms = 0;
+                cudaEventElapsedTime(&ms, r.e0, r.e1);
+                prof_ms[r.cat] += ms;
+                prof_n[r.cat]++;
+            }
+    }
     if (timing) {
         cudaEventRecord(ev[2], st);
         cudaEventSynchronize(ev[2]);

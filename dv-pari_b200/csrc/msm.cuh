@@ -28,13 +28,26 @@ struct MsmStats {
 
 // One independent chain of tree rounds: its own stream and scratch.  The windows of an MSM are split
 // over the lanes so that the latency-bound late rounds of one lane overlap the big early rounds of another.
+// launch categories of the development profiler
+enum { PC_SORT = 0, PC_PLAN, PC_PASS1, PC_BINV_UP, PC_BINV_DIRECT, PC_BINV_DOWN, PC_PASS2, PC_MISC, PC_COUNT };
+
 struct MsmLane {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    DevBuf entries, seg_len[2], seg_start[2], c_len, c_start, task_start, cursor, blk, info, pp[2], prefix, desc,
+    DevBuf entries, seg_len[2], seg_start[2], c_len, c_start, cursor, blk, blk_flag, info, pp[2], prefix, desc,
         thr_total, thr_inv, lvl_pre[2], lvl_tot[2], lvl_inv[2], buckets, rc, ents2;
     void *h_info = nullptr; // pinned, 64 bytes
     unsigned long long launches = 0;
+    uint32_t epoch = 0; // k_plan launch counter (the blocks' publish flag)
+    // profiler: (category, start, stop) per bracket; events are pooled
+    struct ProfRec {
+        int cat;
+        cudaEvent_t e0, e1;
+    };
+    std::vector<ProfRec> prof;
+    size_t prof_used = 0;
+    void prof_begin(int cat);
+    void prof_end();
     // timing of the dominant kernel (lane 0 only)
     cudaEvent_t ev_k[2] = {nullptr, nullptr}, ev_s[3] = {nullptr, nullptr, nullptr};
     bool want_k = false;
@@ -53,6 +66,10 @@ struct MsmEngine {
     int force_window_bits = 0; // 0 = choose from n
     int force_lanes = 0;       // 0 = choose from n
     bool timing = false;
+    bool profile = false; // per-category CUDA-event timing of every launch (development; forces one lane)
+    float prof_ms[PC_COUNT] = {0};
+    unsigned prof_n[PC_COUNT] = {0};
+    uint32_t binv_direct = 32768; // batches up to this size are inverted one element per thread
     int pass2_minb = 2; // resident blocks per SM the pass-2 kernel is compiled for (register cap)
 
     int init(cudaStream_t s);

@@ -76,6 +76,7 @@ def lib():
         L.dvp_msm_device.argtypes = [vp, i32, sz, vp, sz, vp]
         L.dvp_msm_adhoc.argtypes = [vp, vp, vp, sz, vp]
         L.dvp_msm_last_stats.argtypes = [vp, C.POINTER(MsmStats)]
+        L.dvp_msm_last_profile.argtypes = [vp, vp, vp]
         L.dvp_point_add.argtypes = [vp, vp, vp, vp]
         L.dvp_dev_alloc.argtypes = [vp, sz, C.POINTER(vp)]
         L.dvp_dev_free.argtypes = [vp, vp]
@@ -207,6 +208,14 @@ class Context:
         st = MsmStats()
         _ck(lib().dvp_msm_last_stats(self._h, C.byref(st)))
         return {f[0]: getattr(st, f[0]) for f in MsmStats._fields_}
+
+    def msm_profile(self):
+        """Per-category kernel ms / launch counts of the last MSM run with set("msm_profile", 1)."""
+        ms = np.zeros(8, dtype=np.float32)
+        cnt = np.zeros(8, dtype=np.uint32)
+        _ck(lib().dvp_msm_last_profile(self._h, _ptr(ms), _ptr(cnt)))
+        names = ["sort", "plan", "pass1", "binv_up", "binv_direct", "binv_down", "pass2", "misc"]
+        return {nm: (float(ms[i]), int(cnt[i])) for i, nm in enumerate(names)}
 
     def point_add(self, a30, b30):
         """CurvePoint::add on encodings (curve.rs:76-82)."""

@@ -54,7 +54,7 @@ int dvp_abi_version(void);
 int dvp_ctx_create(int device, dvp_ctx **out);
 void dvp_ctx_destroy(dvp_ctx *ctx);
 /* knobs: "msm_window_bits" (0 = automatic), "msm_lanes" (0 = automatic: concurrent window groups),
- * "pass2_minb" (1..3), "timing" (0/1).  Unknown name -> DVP_ERR_BAD_ARG. */
+ * "pass2_minb" (1..3), "timing" (0/1), "msm_profile" (0/1).  Unknown name -> DVP_ERR_BAD_ARG. */
 int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value);
 
 /*
@@ -86,6 +86,9 @@ int dvp_msm_device(dvp_ctx *ctx, int slot, size_t offset, const void *d_scalars_
 /* One-shot form with encoded points from the host: decode + MSM (src/srs.rs:422). */
 int dvp_msm_adhoc(dvp_ctx *ctx, const uint8_t *pts30, const uint64_t *scalars_mont, size_t n, uint8_t out30[30]);
 int dvp_msm_last_stats(dvp_ctx *ctx, dvp_msm_stats *out);
+/* Development aid: with the "msm_profile" knob set the MSM runs on one lane with CUDA events around every
+ * launch; ms/count per category: 0 sort 1 plan 2 pass1 3 binv_up 4 binv_direct 5 binv_down 6 pass2 7 misc. */
+int dvp_msm_last_profile(dvp_ctx *ctx, float ms[8], unsigned count[8]);
 
 /* CurvePoint::add on encodings (src/curve.rs:76-82): out = a (+) b.  Runs on the device of ctx. */
 int dvp_point_add(dvp_ctx *ctx, const uint8_t a30[30], const uint8_t b30[30], uint8_t out30[30]);
