@@ -317,6 +317,18 @@ int dvp_srs_random(dvp_ctx *ctx, int slot, size_t n, uint64_t seed) {
     CKC(cudaStreamSynchronize(ctx->stream));
     return DVP_OK;
 }
+int dvp_srs_mulgen(dvp_ctx *ctx, int slot, const uint64_t *scalars_mont, size_t n) {
+    if (!slot_ok(ctx, slot) || (!scalars_mont && n)) return DVP_ERR_BAD_ARG;
+    CKC(cudaSetDevice(ctx->device));
+    SrsSlot &s = ctx->slots[slot];
+    int rc;
+    if ((rc = s.buf.reserve((n ? n : 1) * sizeof(AffPt))) != 0) return rc;
+    s.n = n;
+    if (!n) return DVP_OK;
+    if ((rc = ctx->scal.reserve(n * 32 + 32)) != 0) return rc;
+    CKC(cudaMemcpyAsync(ctx->scal.p, scalars_mont, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    return ctx->msm.mulgen((const uint32_t *)ctx->scal.p, n, s.buf.as<AffPt>());
+}
 int dvp_srs_size(dvp_ctx *ctx, int slot, size_t *n) {
     if (!slot_ok(ctx, slot) || !n) return DVP_ERR_BAD_ARG;
     *n = ctx->slots[slot].n;

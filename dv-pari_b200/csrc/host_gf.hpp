@@ -127,6 +127,19 @@ inline AffPt aff_add(const AffPt &p, const AffPt &q) {
     return r;
 }
 
+// The K-233 point behind CurvePoint::generator() (xsk233_generator, /root/reference/src/curve.rs:84-91):
+// the NIST / SEC 2 sect233k1 base point (restated convention).
+inline AffPt k233_generator() {
+    static const uint32_t gx[8] = {0xEFAD6126u, 0x0A4C9D6Eu, 0x19C26BF5u, 0x149563A4u, 0x29F22FF4u, 0x7E731AF1u, 0x32BA853Au, 0x00000172u};
+    static const uint32_t gy[8] = {0x56FAE6A3u, 0x56E0C110u, 0xF18AEB9Bu, 0x27A8CD9Bu, 0x555A67C4u, 0x19B7F70Fu, 0x537DECE8u, 0x000001DBu};
+    AffPt p;
+    for (int i = 0; i < 8; i++) {
+        p.x.v[i] = gx[i];
+        p.y.v[i] = gy[i];
+    }
+    return p;
+}
+
 // xsk233_encode of the group element P + N for P in E[r] (or infinity -> neutral -> zeros):
 // w = (y + 1)/x of P + N = (y + x + 1)/x of P, 233 bits little-endian.
 inline void encode30(uint8_t out[30], const AffPt &p) {

@@ -758,6 +758,7 @@ void MsmEngine::destroy() {
     len_all.release();
     hb.release();
     msqr_tabs.release();
+    mg_table.release();
     if (h_pts) cudaFreeHost(h_pts);
     h_pts = nullptr;
     h_pts_cap = 0;
@@ -926,6 +927,105 @@ struct Tree {
 
 } // namespace
 
+// scratch of one tree round with up to task_ub additions
+int MsmEngine::reserve_round(MsmLane &L, size_t task_ub) {
+    int rc;
+#define RS(buf, bytes) \
+    if ((rc = (buf).reserve(bytes)) != 0) return rc
+    RS(L.info, 64);
+    RS(L.prefix, task_ub * sizeof(gf));
+    RS(L.desc, task_ub * sizeof(uint4));
+    const size_t thr_ub = std::max<size_t>(task_ub / 16, 1u << 19) + 1024; // B = 16 / 4 / 1 regimes
+    RS(L.thr_total, thr_ub * sizeof(gf));
+    RS(L.thr_inv, thr_ub * sizeof(gf));
+    RS(L.lvl_pre[0], thr_ub * sizeof(gf));
+    RS(L.lvl_tot[0], (thr_ub / 2 + 2) * sizeof(gf));
+    RS(L.lvl_inv[0], (thr_ub / 2 + 2) * sizeof(gf));
+    RS(L.lvl_pre[1], (thr_ub / 2 + 2) * sizeof(gf));
+    RS(L.lvl_tot[1], (thr_ub / 4 + 2) * sizeof(gf));
+    RS(L.lvl_inv[1], (thr_ub / 4 + 2) * sizeof(gf));
+#undef RS
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched fixed-base multiplication: out[i] = k_i G  (CurvePoint::generator().mul, curve.rs:84-91,129-137;
+// compute_srs_matrices, srs.rs:126-160).  8-bit windows over a table T[j][d] = d 2^(8j) G; window j is one
+// tree round in which every accumulator adds its table point, so all n additions share one inversion.
+// ------------------------------------------------------------------------------------------------
+constexpr int MG_WINDOWS = 30, MG_DIGITS = 255;
+constexpr size_t MG_TABLE = (size_t)MG_WINDOWS * MG_DIGITS + 1; // + one point at infinity (zero digits)
+
+__global__ void k_mulgen_desc(const uint32_t *__restrict__ scalars, uint32_t n, int j, uint32_t tab0,
+                              uint4 *__restrict__ desc) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr a;
+    const uint4 *q = reinterpret_cast<const uint4 *>(scalars + (size_t)i * 8);
+    const uint4 lo = q[0], hi = q[1];
+    a.v[0] = lo.x; a.v[1] = lo.y; a.v[2] = lo.z; a.v[3] = lo.w;
+    a.v[4] = hi.x; a.v[5] = hi.y; a.v[6] = hi.z; a.v[7] = hi.w;
+    uint32_t k[8];
+    fr_to_canonical(k, a);
+    const uint32_t d = (k[j >> 2] >> (8 * (j & 3))) & 255u;
+    desc[i] = make_uint4(i, d ? tab0 + (uint32_t)j * MG_DIGITS + d - 1 : tab0 + (uint32_t)(MG_TABLE - 1), i, 0);
+}
+
+int MsmEngine::mulgen(const uint32_t *d_scalars, size_t n, AffPt *d_out) {
+    if (n == 0) return 0;
+    if (lanes.empty()) {
+        lanes.emplace_back();
+        int rc0 = lanes.back().init();
+        if (rc0) return rc0;
+    }
+    MsmLane &L = lanes[0];
+    cudaStream_t st = L.stream;
+    int rc;
+    // table on the host (once): LD doublings / additions, one conversion per entry
+    if (!mg_table.p) {
+        std::vector<AffPt> tab(MG_TABLE);
+        AffPt base = host::k233_generator();
+        for (int j = 0; j < MG_WINDOWS; j++) {
+            host::LdPt acc = host::ld_inf();
+            for (int d = 1; d <= MG_DIGITS; d++) {
+                acc = host::ld_add_affine(acc, base);
+                tab[(size_t)j * MG_DIGITS + d - 1] = host::ld_to_affine(acc);
+            }
+            host::LdPt nb = host::ld_add_affine(acc, base); // 256 * base
+            base = host::ld_to_affine(nb);
+        }
+        tab[MG_TABLE - 1] = pt_inf();
+        if ((rc = mg_table.reserve(MG_TABLE * sizeof(AffPt)))) return rc;
+        CK(cudaMemcpy(mg_table.p, tab.data(), MG_TABLE * sizeof(AffPt), cudaMemcpyHostToDevice));
+    }
+    const size_t CH = (size_t)1 << 22; // accumulators per pass (bounds the scratch)
+    const size_t chunk_max = std::min(n, CH);
+    if ((rc = reserve_round(L, chunk_max + 1))) return rc;
+    for (int i = 0; i < 2; i++)
+        if ((rc = L.pp[i].reserve((chunk_max + MG_TABLE) * sizeof(AffPt)))) return rc;
+    CK(cudaStreamSynchronize(stream)); // the scalars were written on the context stream
+    Tree tree(*this, L);
+    for (size_t off = 0; off < n; off += CH) {
+        const uint32_t m = (uint32_t)std::min(CH, n - off);
+        AffPt *A[2] = {L.pp[0].as<AffPt>(), L.pp[1].as<AffPt>()};
+        for (int i = 0; i < 2; i++)
+            CK(cudaMemcpyAsync(A[i] + m, mg_table.p, MG_TABLE * sizeof(AffPt), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemsetAsync(A[0], 0, (size_t)m * sizeof(AffPt), st)); // accumulators start at infinity
+        const uint32_t info_h[4] = {0, m, m, 0};
+        CK(cudaMemcpyAsync(L.info.p, info_h, 16, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st)); // info_h is a stack temporary
+        const int B = m >= (1u << 21) ? 16 : m >= (1u << 17) ? 4 : 1;
+        for (int j = 0; j < MG_WINDOWS; j++) {
+            k_mulgen_desc<<<cdiv(m, 256), 256, 0, st>>>(d_scalars + off * 8, m, j, m, L.desc.as<uint4>());
+            if ((rc = tree.round(B, A[j & 1], m, A[(j + 1) & 1]))) return rc;
+        }
+        CK(cudaMemcpyAsync(d_out + off, A[MG_WINDOWS & 1], (size_t)m * sizeof(AffPt), cudaMemcpyDeviceToDevice, st));
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, AffPt *h_result) {
     *h_result = pt_inf();
     if (n == 0) return 0;
@@ -997,17 +1097,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         const size_t out_ub0 = ent_max / 2 + nseg_max + 1;      // outputs of round 0 (ceil halves)
         RS(L.pp[0], out_ub0 * sizeof(AffPt));
         RS(L.pp[1], (out_ub0 / 2 + nseg_max + 1) * sizeof(AffPt));
-        RS(L.prefix, task_ub0 * sizeof(gf));
-        RS(L.desc, task_ub0 * sizeof(uint4));
-        const size_t thr_ub = std::max<size_t>(task_ub0 / 16, 1u << 19) + 1024; // B = 16 / 4 / 1 regimes
-        RS(L.thr_total, thr_ub * sizeof(gf));
-        RS(L.thr_inv, thr_ub * sizeof(gf));
-        RS(L.lvl_pre[0], thr_ub * sizeof(gf));
-        RS(L.lvl_tot[0], (thr_ub / 2 + 2) * sizeof(gf));
-        RS(L.lvl_inv[0], (thr_ub / 2 + 2) * sizeof(gf));
-        RS(L.lvl_pre[1], (thr_ub / 2 + 2) * sizeof(gf));
-        RS(L.lvl_tot[1], (thr_ub / 4 + 2) * sizeof(gf));
-        RS(L.lvl_inv[1], (thr_ub / 4 + 2) * sizeof(gf));
+        if ((rc = reserve_round(L, task_ub0)) != 0) return rc;
         RS(L.buckets, (size_t)p.nseg * sizeof(AffPt));
         RS(L.rc, (size_t)p.nseg_a * sizeof(AffPt));
         RS(L.ents2, (size_t)std::max(p.nent_a, p.nent_b) * 4);

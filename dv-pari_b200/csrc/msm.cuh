@@ -58,7 +58,7 @@ struct MsmLane {
 struct MsmEngine {
     cudaStream_t stream = nullptr; // the context's stream: recode, final read-back
     std::vector<MsmLane> lanes;
-    DevBuf keys, len_all, hb, msqr_tabs;
+    DevBuf keys, len_all, hb, msqr_tabs, mg_table;
     void *h_pts = nullptr; // pinned, receives the per-bit partial sums
     size_t h_pts_cap = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}, ev_recode = nullptr;
@@ -77,6 +77,9 @@ struct MsmEngine {
     // sum_i scalars[i] * points[i]; scalars are device pointers to n x 8 x u32 Montgomery limbs.
     // Result: affine E[r] point (or infinity) on the host.  Returns 0 or a DVP_ERR_* code.
     int run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, AffPt *h_result);
+    // d_out[i] = scalars[i] * G (batched fixed-base multiplication of the generator), all on the device
+    int mulgen(const uint32_t *d_scalars, size_t n, AffPt *d_out);
+    int reserve_round(MsmLane &L, size_t task_ub);
 };
 
 int choose_window_bits(size_t n);

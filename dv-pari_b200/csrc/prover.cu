@@ -214,6 +214,20 @@ __global__ void __launch_bounds__(128)
     if (!fr_eq(fr_mul(av, bv), cw)) atomicMin(first_bad, (unsigned long long)row);
 }
 
+// Synthetic circuits (synth.py): every row's O side ends with the row's own fresh wire 1 + k + row with
+// coefficient one and a row only reads fresh wires of lower levels (level = row mod nlevels), so one pass
+// per level makes every row hold:  w[fresh] += a b - (C w).
+__global__ void __launch_bounds__(128)
+    k_r1cs_solve_level(R1csDev r, fr *__restrict__ w, uint32_t level, uint32_t nlevels) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t row64 = (uint64_t)idx * nlevels + level;
+    if (row64 >= r.nrows) return;
+    const uint32_t row = (uint32_t)row64;
+    const fr av = row_dot(r, 0, row, w), bv = row_dot(r, 1, row, w), cw = row_dot(r, 2, row, w);
+    fr *slot = &w[1 + r.k + row];
+    fr_store(slot, fr_add(fr_load(slot), fr_sub(fr_mul(av, bv), cw)));
+}
+
 // i(X) has degree k-1 < n, so its extension to D' is its evaluation there
 __global__ void k_ivals_ext(const fr *__restrict__ w, uint32_t k, const fr *__restrict__ leaves, uint32_t n,
                             fr *__restrict__ i2) {
@@ -665,6 +679,26 @@ int dvp_r1cs_eval(dvp_r1cs *r, dvp_domain *d, const uint64_t *assignment, uint64
     w.release();
     o.release();
     return rc;
+}
+
+// Fill the fresh wires of a synthetic circuit (see k_r1cs_solve_level); assignment: nwires x 4 u64, in place.
+int dvp_r1cs_synth_solve(dvp_r1cs *r, uint64_t *assignment, unsigned nlevels) {
+    if (!r || !assignment || nlevels == 0) return DVP_ERR_BAD_ARG;
+    if (r->nwires < 1 + (size_t)r->dev.k + r->dev.nrows) return DVP_ERR_BAD_ARG;
+    CKP(cudaSetDevice(r->ctx->device));
+    cudaStream_t st = r->ctx->stream;
+    DevBuf w;
+    int rc = w.reserve(r->nwires * 32);
+    if (rc) return rc;
+    CKP(cudaMemcpyAsync(w.p, assignment, r->nwires * 32, cudaMemcpyHostToDevice, st));
+    const uint32_t per = cdivp(r->dev.nrows, nlevels);
+    for (unsigned l = 0; l < nlevels; l++)
+        k_r1cs_solve_level<<<cdivp(per, 128), 128, 0, st>>>(r->dev, w.as<fr>(), l, nlevels);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(assignment, w.p, r->nwires * 32, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    w.release();
+    return e == cudaSuccess ? DVP_OK : DVP_ERR_CUDA;
 }
 
 int dvp_prover_create(dvp_ctx *ctx, dvp_domain *dom, dvp_r1cs *r1cs, int slot_gm, int slot_gq, int slot_gk,

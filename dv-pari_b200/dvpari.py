@@ -70,6 +70,7 @@ def lib():
         L.dvp_srs_append.argtypes = [vp, i32, vp, sz, C.POINTER(C.c_int64)]
         L.dvp_srs_size.argtypes = [vp, i32, C.POINTER(sz)]
         L.dvp_srs_random.argtypes = [vp, i32, sz, C.c_uint64]
+        L.dvp_srs_mulgen.argtypes = [vp, i32, vp, sz]
         L.dvp_srs_free.argtypes = [vp, i32]
         L.dvp_srs_read.argtypes = [vp, i32, sz, sz, vp]
         L.dvp_msm.argtypes = [vp, i32, sz, vp, sz, vp]
@@ -99,6 +100,7 @@ def lib():
         L.dvp_r1cs_destroy.argtypes = [vp]
         L.dvp_r1cs_destroy.restype = None
         L.dvp_r1cs_eval.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int64)]
+        L.dvp_r1cs_synth_solve.argtypes = [vp, vp, C.c_uint]
         L.dvp_prover_create.argtypes = [vp, vp, vp, i32, i32, i32, C.POINTER(vp)]
         L.dvp_prover_destroy.argtypes = [vp]
         L.dvp_prover_destroy.restype = None
@@ -168,6 +170,11 @@ class Context:
     def srs_random(self, slot, n, seed):
         """n uniformly random group elements, deterministic in (seed, index)."""
         _ck(lib().dvp_srs_random(self._h, slot, n, seed), "dvp_srs_random")
+
+    def srs_mulgen(self, slot, scalars_mont):
+        """slot[i] = scalars[i] * generator (compute_srs_matrices, srs.rs:126-160), batched on the device."""
+        s = np.ascontiguousarray(scalars_mont, dtype=np.uint64).reshape(-1, 4)
+        _ck(lib().dvp_srs_mulgen(self._h, slot, _ptr(s), s.shape[0]), "dvp_srs_mulgen")
 
     def srs_size(self, slot):
         n = C.c_size_t()
@@ -364,6 +371,14 @@ class R1CSInstance:
         if self._h:
             lib().dvp_r1cs_destroy(self._h)
             self._h = C.c_void_p()
+
+    def synth_solve(self, assignment_mont, nlevels):
+        """Fill the fresh wires of a synth.py circuit in place (device passes, one per level)."""
+        w = np.ascontiguousarray(assignment_mont, dtype=np.uint64).reshape(-1, 4)
+        if w.shape[0] != self.nwires:
+            raise DvpError(5, "assignment length")
+        _ck(lib().dvp_r1cs_synth_solve(self._h, _ptr(w), nlevels), "dvp_r1cs_synth_solve")
+        return w
 
     def eval(self, dom, assignment_mont):
         """get_matrix_evaluations_from_witness (proving.rs:348-403) -> (a, b, c, i); raises on a bad row."""

@@ -70,6 +70,10 @@ int dvp_srs_append(dvp_ctx *ctx, int slot, const uint8_t *pts30, size_t n, int64
 /* Fill a slot with n uniformly random group elements, deterministic in (seed, index): synthetic SRS
  * for benchmarks and full-size tests (read them back with dvp_srs_read). */
 int dvp_srs_random(dvp_ctx *ctx, int slot, size_t n, uint64_t seed);
+/* slot[i] = scalars[i] * CurvePoint::generator(): the batched fixed-base multiplication of the SRS generation
+ * (compute_srs_matrices, src/srs.rs:126-160; CurvePoint::generator / point_scalar_mul_gen, src/curve.rs:84-91,129-137).
+ * scalars_mont: n x 4 u64 Montgomery limbs (host). */
+int dvp_srs_mulgen(dvp_ctx *ctx, int slot, const uint64_t *scalars_mont, size_t n);
 int dvp_srs_size(dvp_ctx *ctx, int slot, size_t *n);
 int dvp_srs_free(dvp_ctx *ctx, int slot);
 /* Read points back as 30-byte encodings (CurvePoint::to_bytes, src/curve.rs:93-100). */
@@ -139,6 +143,11 @@ void dvp_r1cs_destroy(dvp_r1cs *r1cs);
  * a, b, c, i: n x 4 each.  DVP_ERR_UNSATISFIED and *first_bad_row on a row with a*b != c + i. */
 int dvp_r1cs_eval(dvp_r1cs *r1cs, dvp_domain *dom, const uint64_t *assignment, uint64_t *a, uint64_t *b, uint64_t *c,
                   uint64_t *i, int64_t *first_bad_row);
+
+/* Synthetic circuits only (benchmarks, full-size tests; dv-pari_b200/synth.py): every row's O side ends with the
+ * row's own fresh wire 1 + num_public + row (coefficient one) and rows read fresh wires of lower levels
+ * (level = row mod nlevels) only.  Fills those wires in place so that every row holds. */
+int dvp_r1cs_synth_solve(dvp_r1cs *r1cs, uint64_t *assignment /* nwires x 4, in place */, unsigned nlevels);
 
 /*
  * Proof::prove(cache_dir, public_inputs, private_inputs) (src/proving.rs:426-688) with the artifacts resident:

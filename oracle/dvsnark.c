@@ -66,9 +66,11 @@ void dv_transcript_alpha(const uint8_t commit_p[30], const fr_t *pub, size_t k, 
 
 static fr_t *fr_vec(size_t n) { return (fr_t *)malloc((n ? n : 1) * sizeof(fr_t)); }
 
-srs_t *dv_setup(const r1cs_t *r, const ecfft_domain *dom, const trapdoor_t *td) {
+/* The discrete logs of the SRS (compute_srs_matrices, srs.rs:112-167, before the fixed-base multiplications):
+ * sc_m[nwires], sc_q[n], sc_k[4n]; bar_wts / z_vals2inv (n each, may be NULL) are the prover precomputes. */
+void dv_setup_scalars(const r1cs_t *r, const ecfft_domain *dom, const trapdoor_t *td, fr_t *sc_m, fr_t *sc_q, fr_t *sc_k,
+                      fr_t *bar_wts, fr_t *z_vals2inv) {
     const size_t n = r->n;
-    srs_t *s = (srs_t *)calloc(1, sizeof(*s));
     fr_t zt[2], delta2;
     ecfft_vanish_at(dom, 0, &td->tau, &zt[0]);
     ecfft_vanish_at(dom, 1, &td->tau, &zt[1]);
@@ -89,8 +91,8 @@ srs_t *dv_setup(const r1cs_t *r, const ecfft_domain *dom, const trapdoor_t *td) 
             fr_mul(&lt[sh][i], &lt[sh][i], &bw[sh][i]);
         }
     }
-    s->bar_wts = bw[0];
-    s->z_vals2inv = zo_inv[0]; /* 1 / Z_D(d'_i) */
+    if (bar_wts) memcpy(bar_wts, bw[0], n * sizeof(fr_t));
+    if (z_vals2inv) memcpy(z_vals2inv, zo_inv[0], n * sizeof(fr_t)); /* 1 / Z_D(d'_i) */
     /* unified-domain basis, ec_fft.rs:424-450 */
     fr_t *ltl = fr_vec(2 * n);
     for (size_t i = 0; i < n; i++) {
@@ -121,27 +123,36 @@ srs_t *dv_setup(const r1cs_t *r, const ecfft_domain *dom, const trapdoor_t *td) 
         }
     }
     /* compute_srs_matrices, srs.rs:112-167 */
-    k233_pt G;
-    k233_generator(&G);
-    fr_t *sc = fr_vec(r->nwires > 4 * n ? r->nwires : 4 * n);
-    for (size_t j = 0; j < r->nwires; j++) fr_mul(&sc[j], &mv[j], &td->epsilon);
-    s->g_m = (k233_pt *)malloc(r->nwires * sizeof(k233_pt));
-    k233_mul_batch(s->g_m, &G, sc, r->nwires);
+    for (size_t j = 0; j < r->nwires; j++) fr_mul(&sc_m[j], &mv[j], &td->epsilon);
     fr_t f;
     fr_mul(&f, &zt[0], &delta2);
     fr_mul(&f, &f, &td->epsilon);
-    for (size_t i = 0; i < n; i++) fr_mul(&sc[i], &f, &lt[1][i]);
-    s->g_q = (k233_pt *)malloc(n * sizeof(k233_pt));
-    k233_mul_batch(s->g_q, &G, sc, n);
+    for (size_t i = 0; i < n; i++) fr_mul(&sc_q[i], &f, &lt[1][i]);
     for (size_t i = 0; i < n; i++) {
-        sc[i] = lt[0][i];
-        fr_mul(&sc[n + i], &lt[0][i], &td->delta);
+        sc_k[i] = lt[0][i];
+        fr_mul(&sc_k[n + i], &lt[0][i], &td->delta);
     }
-    for (size_t j = 0; j < 2 * n; j++) fr_mul(&sc[2 * n + j], &ltl[j], &delta2);
+    for (size_t j = 0; j < 2 * n; j++) fr_mul(&sc_k[2 * n + j], &ltl[j], &delta2);
+    free(mv); free(ltl);
+    for (int sh = 0; sh < 2; sh++) { free(bw[sh]); free(zo_inv[sh]); free(lt[sh]); }
+}
+
+srs_t *dv_setup(const r1cs_t *r, const ecfft_domain *dom, const trapdoor_t *td) {
+    const size_t n = r->n;
+    srs_t *s = (srs_t *)calloc(1, sizeof(*s));
+    s->bar_wts = fr_vec(n);
+    s->z_vals2inv = fr_vec(n);
+    fr_t *sc_m = fr_vec(r->nwires), *sc_q = fr_vec(n), *sc_k = fr_vec(4 * n);
+    dv_setup_scalars(r, dom, td, sc_m, sc_q, sc_k, s->bar_wts, s->z_vals2inv);
+    k233_pt G;
+    k233_generator(&G);
+    s->g_m = (k233_pt *)malloc(r->nwires * sizeof(k233_pt));
+    k233_mul_batch(s->g_m, &G, sc_m, r->nwires);
+    s->g_q = (k233_pt *)malloc(n * sizeof(k233_pt));
+    k233_mul_batch(s->g_q, &G, sc_q, n);
     s->g_k = (k233_pt *)malloc(4 * n * sizeof(k233_pt));
-    k233_mul_batch(s->g_k, &G, sc, 4 * n);
-    free(sc); free(mv); free(ltl);
-    free(bw[1]); free(zo_inv[1]); free(lt[0]); free(lt[1]);
+    k233_mul_batch(s->g_k, &G, sc_k, 4 * n);
+    free(sc_m); free(sc_q); free(sc_k);
     return s;
 }
 void dv_srs_free(srs_t *s) {

@@ -49,6 +49,9 @@ typedef struct {
 long r1cs_eval(const r1cs_t *r, const ecfft_domain *dom, const fr_t *assignment, fr_t *a, fr_t *b, fr_t *c, fr_t *i);
 /* alpha from the 30-byte commitment and the public inputs */
 void dv_transcript_alpha(const uint8_t commit_p[30], const fr_t *pub, size_t k, fr_t *alpha);
+/* the discrete logs of the SRS points (srs.rs:112-167 before the fixed-base multiplications) */
+void dv_setup_scalars(const r1cs_t *r, const ecfft_domain *dom, const trapdoor_t *td, fr_t *sc_m, fr_t *sc_q, fr_t *sc_k,
+                      fr_t *bar_wts, fr_t *z_vals2inv);
 /* allocate and fill the SRS and prover precomputes */
 srs_t *dv_setup(const r1cs_t *r, const ecfft_domain *dom, const trapdoor_t *td);
 void dv_srs_free(srs_t *s);

@@ -440,6 +440,18 @@ class Srs:
         return self._frs(self._p.contents.bar_wts, self.n)
 
 
+def setup_scalars(r1cs, dom, td):
+    """Discrete logs of g_m / g_q / g_k (srs.rs:112-167 before the fixed-base multiplications), Montgomery."""
+    sc_m = np.zeros((r1cs.nwires, 4), dtype=np.uint64)
+    sc_q = np.zeros((r1cs.n, 4), dtype=np.uint64)
+    sc_k = np.zeros((4 * r1cs.n, 4), dtype=np.uint64)
+    L = lib()
+    L.dv_setup_scalars.restype = None
+    L.dv_setup_scalars(C.byref(r1cs._s), dom._d, C.byref(td), sc_m.ctypes.data_as(C.c_void_p),
+                       sc_q.ctypes.data_as(C.c_void_p), sc_k.ctypes.data_as(C.c_void_p), None, None)
+    return sc_m, sc_q, sc_k
+
+
 def prove(r1cs, dom, srs, assignment_mont, want_stages=False, nthreads=0):
     """Proof::prove (proving.rs:426-688).  Returns (118 proof bytes, status, stages or None)."""
     w = np.ascontiguousarray(assignment_mont, dtype=np.uint64)

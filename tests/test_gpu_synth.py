@@ -1,0 +1,95 @@
+"""Synthetic SP1-shaped circuits at scale (BASELINE config #4): the witness is solved on the device, the SRS is
+generated on the device from the oracle's setup scalars (batched fixed-base multiplication, srs.rs:126-160), the
+proof comes from dvp_prove, and the oracle decides: same 118 bytes as its own prover where that is affordable,
+and its designated verifier (srs.rs:374-428) accepts the proof in every case."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import dvpari
+import synth
+
+pytestmark = pytest.mark.gpu
+P = dvpari.P
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = dvpari.Context(0)
+    yield c
+    c.close()
+
+
+def test_mulgen_matches_oracle(ctx, oracle):
+    O = oracle
+    n = 3000
+    sc = dvpari.random_fr_mont(n, 77)
+    sc[0] = 0                                   # 0 * G = neutral
+    sc[1] = dvpari.fr_to_mont([1])[0]
+    sc[2] = dvpari.fr_to_mont([P - 1])[0]
+    sc[3] = dvpari.fr_to_mont([255])[0]
+    sc[4] = dvpari.fr_to_mont([256])[0]
+    ctx.srs_mulgen(5, sc)
+    got = ctx.srs_read(5, 0, n)
+    want = O.encode_batch(O.mul_batch(O.generator(), sc))
+    assert got.tobytes() == want.tobytes()
+    assert bytes(got[0]) == bytes(30)
+    ctx.srs_free(5)
+
+
+def _synth_case(ctx, O, lg_n, compare_with_oracle_prover):
+    circ = synth.synth_r1cs(lg_n, seed=0xD5A10003 + lg_n)
+    inst = dvpari.R1CSInstance(ctx, circ["nrows"], circ["k"], circ["nwires"], circ["rowptr"], circ["wire"],
+                               circ["coeff"], circ["coeffs_mont"])
+    w = inst.synth_solve(synth.synth_assignment(circ), circ["nlevels"])
+    r1cs = O.R1CS.from_arrays(circ["coeffs_mont"], circ["rowptr"], circ["wire"], circ["coeff"], circ["nrows"],
+                              circ["k"], circ["nwires"])
+    od = O.Domain(lg_n + 1)
+    # the device-solved witness satisfies every row according to the oracle
+    _, bad = O.r1cs_eval(r1cs, od, w)
+    assert bad == -1
+    rnd = random.Random(lg_n)
+    td = O.trapdoor(rnd.randrange(1, P), rnd.randrange(1, P), rnd.randrange(1, P))
+    sc_m, sc_q, sc_k = O.setup_scalars(r1cs, od, td)
+    ctx.srs_mulgen(0, sc_m)
+    ctx.srs_mulgen(1, sc_q)
+    ctx.srs_mulgen(2, sc_k)
+    gd = dvpari.Domain(ctx, lg_n + 1)
+    prover = dvpari.Prover(ctx, gd, inst, 0, 1, 2)
+    k = circ["k"]
+    proof = prover.prove(w[1:1 + k], w[1 + k:])
+    pub = dvpari.fr_from_mont(w[1:1 + k])
+    assert O.verify(td, pub, proof), "the oracle's verifier rejects the device proof"
+    # a tampered proof or public input is rejected
+    bad_proof = bytearray(proof)
+    bad_proof[70] ^= 1
+    assert not O.verify(td, pub, bytes(bad_proof))
+    assert not O.verify(td, [pub[0], (pub[1] + 1) % P], proof)
+    if compare_with_oracle_prover:
+        srs = O.Srs(r1cs, od, td)
+        # device-generated SRS == oracle SRS, spot-checked on g_q, and byte-equal proofs
+        assert ctx.srs_read(1, 0, min(64, circ["n"])).tobytes() == srs.g_q30()[: min(64, circ["n"])].tobytes()
+        want, rc, _ = O.prove(r1cs, od, srs, w)
+        assert rc == 0 and proof == want
+    times = prover.last_times()
+    prover.close()
+    inst.close()
+    gd.close()
+    return times
+
+
+def test_synth_prove_small_is_bit_exact(ctx, oracle):
+    _synth_case(ctx, oracle, 10, True)
+
+
+def test_synth_prove_2_14_is_bit_exact(ctx, oracle):
+    _synth_case(ctx, oracle, 14, True)
+
+
+def test_synth_prove_2_18_verifies(ctx, oracle):
+    """262 144 constraints, ~2.7 M terms; set DVP_FULL_LG=20 for the 2^20 configuration (slow CPU-side setup)."""
+    lg = int(os.environ.get("DVP_FULL_LG", "18"))
+    t = _synth_case(ctx, oracle, lg, False)
+    print(f"prove 2^{lg}: " + ", ".join(f"{k} {v:.2f} ms" for k, v in t.items()))
