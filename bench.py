@@ -9,6 +9,11 @@ resident SRS points, per GPU.  With N > 1 (torchrun) every rank owns a contiguou
 N*2^LG-point MSM (weak scaling); the 30-byte partial sums are all-gathered over NCCL and folded.
 `value` times the device-resident call (scalars already in HBM); `e2e` times the host-buffer C-ABI
 call dvp_msm (scalars copied from the host inside the timed region, 30-byte result back).
+
+The second half of BASELINE.json's metric -- DV-Pari prove ms at 2^22 constraints -- is measured in the same
+run and reported under "prove": Proof::prove (proving.rs:426-688) through dvp_prove on a synthetic SP1-shaped
+R1CS (dv-pari_b200/synth.py), witness in host memory, 118-byte proof back, with the per-stage split, the
+ECFFT extend and the R1CS row evaluation rates against their rooflines.
 """
 import argparse
 import json
@@ -136,6 +141,75 @@ def run_reference(args):
     return 0
 
 
+FR_MUL_PEAK = 4.5e10  # measured fr_mul/s of the CIOS multiplier (profiles/r1_pipe_rates.json), the ECFFT's bound
+
+
+def prove_section(ctx, args):
+    """Proof::prove at 2^prove_lg constraints on one GPU: ms per proof and the stage split."""
+    import numpy as np
+
+    import dvpari
+    import synth
+
+    lg = args.prove_lg
+    circ = synth.synth_r1cs(lg)
+    inst = dvpari.R1CSInstance(ctx, circ["nrows"], circ["k"], circ["nwires"], circ["rowptr"], circ["wire"],
+                               circ["coeff"], circ["coeffs_mont"])
+    w = inst.synth_solve(synth.synth_assignment(circ), circ["nlevels"])
+    dom = dvpari.Domain(ctx, lg + 1)
+    n, k = circ["n"], circ["k"]
+    # timing only: random group elements as SRS (tests/test_gpu_synth.py proves with a real SRS and verifies)
+    ctx.srs_random(1, circ["nwires"], 0xD5A10005)
+    ctx.srs_random(2, n, 0xD5A10006)
+    ctx.srs_random(3, 4 * n, 0xD5A10007)
+    prover = dvpari.Prover(ctx, dom, inst, 1, 2, 3)
+    pub, priv = w[1:1 + k], w[1 + k:]
+    ref = prover.prove(pub, priv)  # warm-up: sizes the scratch
+    prover.prove(pub, priv)
+    reps = max(3, min(args.steps, 5))
+    stages = {}
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        proof = prover.prove(pub, priv)
+        for a, b in prover.last_times().items():
+            stages[a] = stages.get(a, 0.0) + b / reps
+    ms = 1e3 * (time.perf_counter() - t0) / reps
+    assert proof == ref
+    terms = int(sum(len(x) for x in circ["wire"]))
+    # ECFFT extend alone: 3 polynomials of n evaluations, in place on the device
+    d = ctx.dev_alloc(3 * n * 32)
+    ctx.dev_upload(d, dvpari.random_fr_mont(3 * n, 5))
+    dom.extend_device(d, 3)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        dom.extend_device(d, 3)
+    ext_ms = 1e3 * (time.perf_counter() - t0) / 3
+    ctx.dev_free(d)
+    hbm_peak, _ = peaks()
+    mulmods = 3 * 4 * n * lg  # 4 n log2 n per polynomial
+    ext_bytes = 3 * 2 * lg * (64 * (n // 2)) + 2 * 256 * n  # data in + out per level and polynomial, matrices once per level pair
+    out = {
+        "constraints": n, "rows": circ["nrows"], "terms": terms, "wires": circ["nwires"], "public_inputs": k,
+        "ms_per_proof": ms, "proofs": reps, "stage_ms": stages,
+        "h2d_bytes_per_proof": int(circ["nwires"] * 32), "d2h_bytes_per_proof": 118,
+        "msm_points_per_proof": circ["nwires"] + 5 * n,
+        "msm_points_per_s": (circ["nwires"] + 5 * n) / (1e-3 * (stages["msm_gm"] + stages["msm_gq"] + stages["msm_gk"])),
+        "ecfft_extend": {"polys": 3, "n": n, "ms": ext_ms, "mulmods_per_s": mulmods / (ext_ms * 1e-3),
+                         "int_frac": mulmods / (ext_ms * 1e-3) / FR_MUL_PEAK,
+                         "GBps": ext_bytes / (ext_ms * 1e-3) / 1e9, "hbm_frac": ext_bytes / (ext_ms * 1e-3) / 1e9 / hbm_peak,
+                         "bound": "integer (Montgomery multiplier), see DESIGN.md 4.3"},
+        "r1cs_rows": {"ms": stages["r1cs"], "terms_per_s": terms / (stages["r1cs"] * 1e-3),
+                      "GBps": (terms * 72 + 4 * n * 32) / (stages["r1cs"] * 1e-3) / 1e9},
+        "srs": "random group elements (timing only)", "data": "synthetic SP1-shaped R1CS, dv-pari_b200/synth.py",
+    }
+    prover.close()
+    inst.close()
+    dom.close()
+    for sl in (1, 2, 3):
+        ctx.srs_free(sl)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -145,6 +219,7 @@ def main():
     ap.add_argument("--lg", type=int, default=20, help="log2 of the points per GPU")
     ap.add_argument("--cpu-lg", type=int, default=17, help="log2 of the CPU-baseline sample")
     ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--prove-lg", type=int, default=22, help="log2 of the constraint count of the prove measurement (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -234,6 +309,10 @@ def main():
     ctx.set("timing", 0)
     ctx.set("msm_lanes", 0)
 
+    prove = None
+    if args.prove_lg and rank == 0 and world == 1:
+        prove = prove_section(ctx, args)
+
     if rank == 0:
         hbm_peak, which = peaks()
         k_ms, k_adds = st["ms_pass2_round0"], st["adds_round0"]
@@ -270,6 +349,8 @@ def main():
                              "sample": f"2^{lg_s} of the same SRS points, oracle k233_msm (per-point wNAF scalar mul + sum, curve.rs:141-158), "
                                        f"{cdt:.2f} s, result equal to the GPU's"},
             "clocks": clocks,
+            "device_ms_per_step": st["ms_device"],
+            "prove": prove,
         }
         print(json.dumps(line))
     if use_dist:

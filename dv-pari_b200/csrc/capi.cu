@@ -407,6 +407,8 @@ int dvp_msm_last_stats(dvp_ctx *ctx, dvp_msm_stats *out) {
     out->ms_tail = s.ms_tail;
     out->ms_pass2_round0 = s.ms_pass2_round0;
     out->adds_round0 = s.adds_round0;
+    out->ms_device = s.ms_device;
+    out->lanes = s.lanes;
     return DVP_OK;
 }
 

@@ -744,6 +744,8 @@ int MsmEngine::init(cudaStream_t s) {
     stream = s;
     for (auto &e : ev) CK(cudaEventCreate(&e));
     CK(cudaEventCreateWithFlags(&ev_recode, cudaEventDisableTiming));
+    CK(cudaEventCreate(&ev_t0));
+    CK(cudaEventCreate(&ev_t1));
     int rc = msqr_tabs.reserve(MSQ_TABLES * MSQ_TABLE_ELEMS * sizeof(gf));
     if (rc) return rc;
     k_build_msqr_tables<<<cdiv(MSQ_TABLES * MSQ_TABLE_ELEMS, 128), 128, 0, s>>>(msqr_tabs.as<gf>());
@@ -765,6 +767,8 @@ void MsmEngine::destroy() {
     for (auto &e : ev)
         if (e) cudaEventDestroy(e), e = nullptr;
     if (ev_recode) cudaEventDestroy(ev_recode), ev_recode = nullptr;
+    if (ev_t0) cudaEventDestroy(ev_t0), ev_t0 = nullptr;
+    if (ev_t1) cudaEventDestroy(ev_t1), ev_t1 = nullptr;
 }
 
 namespace {
@@ -1113,6 +1117,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     }
 
     cudaStream_t st = stream;
+    cudaEventRecord(ev_t0, st);
     if (timing) cudaEventRecord(ev[0], st);
     // ---- recode + histogram for every window (context stream)
     uint32_t *d_len_all = len_all.as<uint32_t>();
@@ -1194,7 +1199,10 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     }
     CK(cudaMemcpyAsync(h_pts, hb.as<AffPt>(), hb_bytes, cudaMemcpyDeviceToHost, st));
     if (timing) cudaEventRecord(ev[1], st);
+    cudaEventRecord(ev_t1, st);
     CK(cudaStreamSynchronize(st));
+    float ms_dev = 0;
+    cudaEventElapsedTime(&ms_dev, ev_t0, ev_t1);
 
     // ---- host tail: sum_w 2^(off_w) [ sum_{q<c-1} 2^q HB[w][q] + HB[w][c-1] ], one double-and-add pass
     {
@@ -1213,6 +1221,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         *h_result = host::ld_to_affine(acc);
     }
     stt.launches = launches;
+    stt.ms_device = ms_dev;
     if (profile) {
         for (int i = 0; i < PC_COUNT; i++) prof_ms[i] = 0, prof_n[i] = 0;
         for (int l = 0; l < NL; l++)

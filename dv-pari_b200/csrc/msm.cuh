@@ -23,6 +23,7 @@ struct MsmStats {
     float ms_recode_sort = 0, ms_accumulate = 0, ms_reduce = 0, ms_tail = 0;
     // the dominant kernel: pass 2 of round 0 of the bucket accumulation (one launch)
     float ms_pass2_round0 = 0;
+    float ms_device = 0; // recode .. partial sums on the host (CUDA events on the context stream), always measured
     unsigned long long adds_round0 = 0, adds_total = 0;
 };
 
@@ -61,7 +62,7 @@ struct MsmEngine {
     DevBuf keys, len_all, hb, msqr_tabs, mg_table;
     void *h_pts = nullptr; // pinned, receives the per-bit partial sums
     size_t h_pts_cap = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}, ev_recode = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}, ev_recode = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     MsmStats last;
     int force_window_bits = 0; // 0 = choose from n
     int force_lanes = 0;       // 0 = choose from n

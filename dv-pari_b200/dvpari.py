@@ -35,7 +35,7 @@ class MsmStats(C.Structure):
     _fields_ = [("window_bits", C.c_int), ("windows", C.c_int), ("rounds_main", C.c_int), ("rounds_a", C.c_int),
                 ("rounds_b", C.c_int), ("launches", C.c_ulonglong), ("ms_recode_sort", C.c_float),
                 ("ms_accumulate", C.c_float), ("ms_reduce", C.c_float), ("ms_tail", C.c_float),
-                ("ms_pass2_round0", C.c_float), ("adds_round0", C.c_ulonglong)]
+                ("ms_pass2_round0", C.c_float), ("adds_round0", C.c_ulonglong), ("ms_device", C.c_float), ("lanes", C.c_int)]
 
 
 def build(force=False):
@@ -336,6 +336,10 @@ class Domain:
         out = np.zeros(4, dtype=np.uint64)
         _ck(lib().dvp_domain_vanish_at(self._h, shift, _ptr(x), _ptr(out)))
         return out
+
+    def extend_device(self, d_data, npoly):
+        """In place on device memory: npoly contiguous vectors of n Fr on D -> their values on D'."""
+        _ck(lib().dvp_ecfft_extend_device(self._h, d_data, npoly), "dvp_ecfft_extend_device")
 
     def extend(self, evals_mont):
         """tree2n.extend(evals, Moiety::S1) for one (n,4) or several (p,n,4) vectors (proving.rs:410-422)."""

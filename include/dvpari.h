@@ -45,6 +45,8 @@ typedef struct dvp_msm_stats {
     float ms_recode_sort, ms_accumulate, ms_reduce, ms_tail; /* filled when timing is enabled */
     float ms_pass2_round0;            /* the dominant kernel: one launch, CUDA events on the launching stream */
     unsigned long long adds_round0;   /* affine additions that launch finished */
+    float ms_device;                  /* scalars in HBM -> partial sums on the host, CUDA events on the context stream */
+    int lanes;                        /* concurrent window groups used */
 } dvp_msm_stats;
 
 const char *dvp_strerror(int code);
