@@ -235,7 +235,9 @@ void dvp_ctx_destroy(dvp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    dvp_comm_destroy(ctx);
     ctx->msm.destroy();
+    ctx->commbuf.release();
     for (auto &s : ctx->slots) s.buf.release();
     ctx->bytes.release();
     ctx->small.release();

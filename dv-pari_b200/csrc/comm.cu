@@ -1,0 +1,191 @@
+// Multi-GPU plumbing of the C ABI: one process per GPU, NCCL over NVLink / NVSwitch.
+//
+// The reference is single-process (rayon inside one prove).  Here the three MSMs of Proof::prove
+// (/root/reference/src/proving.rs:463,512,680) shard by contiguous point range, the row evaluation
+// (proving.rs:382-396) by row range and the extends (proving.rs:410-422) by polynomial.  The only
+// exchanges are: an all-gather of the row-range outputs, a broadcast of every extended polynomial from
+// its owner, and an all-gather of one 64-byte partial sum per rank and MSM, folded identically on every
+// rank (GF(2^233) point addition is not an NCCL reduction operator).
+// libnccl is bound at run time (dlopen) so that the library loads on hosts without it; the unique id
+// travels by whatever channel the host has (torch.distributed store, MPI, a file).
+#include <dlfcn.h>
+#include <nccl.h>
+#include <cstdio>
+#include <cstring>
+#include "ctx.cuh"
+#include "host_gf.hpp"
+
+using namespace dvp;
+
+namespace {
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+
+bool nccl_load() {
+    if (g_nccl.ok) return true;
+    if (!g_nccl.h) {
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (g_nccl.h) break;
+        }
+    }
+    if (!g_nccl.h) return false;
+#define SYM(field, name)                                            \
+    *(void **)(&g_nccl.field) = dlsym(g_nccl.h, name);              \
+    if (!g_nccl.field) return false
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllGather, "ncclAllGather");
+    SYM(Broadcast, "ncclBroadcast");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.ok = true;
+    return true;
+}
+} // namespace
+
+#define NCK(x)                                                                                                   \
+    do {                                                                                                         \
+        ncclResult_t r_ = (x);                                                                                   \
+        if (r_ != ncclSuccess) {                                                                                 \
+            fprintf(stderr, "[dvpari] NCCL error %s at %s:%d\n", g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+            return DVP_ERR_NCCL;                                                                                 \
+        }                                                                                                        \
+    } while (0)
+#define CKN(x)                                                                                                \
+    do {                                                                                                      \
+        cudaError_t e_ = (x);                                                                                 \
+        if (e_ != cudaSuccess) {                                                                              \
+            fprintf(stderr, "[dvpari] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return DVP_ERR_CUDA;                                                                              \
+        }                                                                                                     \
+    } while (0)
+
+// all-gather `bytes` per rank (device buffers) on the context stream
+int comm_all_gather(dvp_ctx *ctx, const void *send, void *recv, size_t bytes) {
+    NCK(g_nccl.AllGather(send, recv, bytes, ncclUint8, (ncclComm_t)ctx->comm, ctx->stream));
+    return DVP_OK;
+}
+int comm_broadcast(dvp_ctx *ctx, void *buf, size_t bytes, int root) {
+    NCK(g_nccl.Broadcast(buf, buf, bytes, ncclUint8, root, (ncclComm_t)ctx->comm, ctx->stream));
+    return DVP_OK;
+}
+int comm_group(bool start) {
+    NCK(start ? g_nccl.GroupStart() : g_nccl.GroupEnd());
+    return DVP_OK;
+}
+
+// Sum of the ranks' partial MSM results, identical on every rank: all-gather 64-byte affine points, fold in
+// rank order on the host (CurvePoint::add, curve.rs:76-82).
+int comm_fold_points(dvp_ctx *ctx, const AffPt &mine, AffPt *total) {
+    if (ctx->world <= 1) {
+        *total = mine;
+        return DVP_OK;
+    }
+    int rc;
+    const size_t W = (size_t)ctx->world;
+    if ((rc = ctx->commbuf.reserve((W + 1) * sizeof(AffPt))) != 0) return rc;
+    AffPt *d = ctx->commbuf.as<AffPt>();
+    CKN(cudaMemcpyAsync(d + W, &mine, sizeof(AffPt), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = comm_all_gather(ctx, d + W, d, sizeof(AffPt))) != 0) return rc;
+    AffPt all[64];
+    CKN(cudaMemcpyAsync(all, d, W * sizeof(AffPt), cudaMemcpyDeviceToHost, ctx->stream));
+    CKN(cudaStreamSynchronize(ctx->stream));
+    AffPt acc = all[0];
+    for (size_t r = 1; r < W; r++) acc = host::aff_add(acc, all[r]);
+    *total = acc;
+    return DVP_OK;
+}
+
+extern "C" {
+
+int dvp_comm_unique_id(uint8_t id[128]) {
+    if (!id) return DVP_ERR_BAD_ARG;
+    if (!nccl_load()) return DVP_ERR_NCCL;
+    ncclUniqueId u;
+    NCK(g_nccl.GetUniqueId(&u));
+    static_assert(sizeof(u) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id, &u, 128);
+    return DVP_OK;
+}
+
+int dvp_comm_init(dvp_ctx *ctx, const uint8_t id[128], int rank, int world) {
+    if (!ctx || !id || world < 1 || world > 64 || rank < 0 || rank >= world) return DVP_ERR_BAD_ARG;
+    if (ctx->comm) return DVP_ERR_BAD_ARG;
+    if (!nccl_load()) return DVP_ERR_NCCL;
+    CKN(cudaSetDevice(ctx->device));
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    ncclComm_t c;
+    NCK(g_nccl.CommInitRank(&c, world, u, rank));
+    ctx->comm = c;
+    ctx->rank = rank;
+    ctx->world = world;
+    return DVP_OK;
+}
+
+int dvp_comm_destroy(dvp_ctx *ctx) {
+    if (!ctx) return DVP_ERR_BAD_ARG;
+    if (ctx->comm) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        g_nccl.CommDestroy((ncclComm_t)ctx->comm);
+    }
+    ctx->comm = nullptr;
+    ctx->rank = 0;
+    ctx->world = 1;
+    return DVP_OK;
+}
+
+int dvp_comm_info(dvp_ctx *ctx, int *rank, int *world) {
+    if (!ctx) return DVP_ERR_BAD_ARG;
+    if (rank) *rank = ctx->rank;
+    if (world) *world = ctx->world;
+    return DVP_OK;
+}
+
+void dvp_shard_range(size_t total, int rank, int world, size_t *lo, size_t *hi) {
+    if (world < 1) world = 1;
+    const size_t a = (size_t)((unsigned __int128)total * (unsigned)rank / (unsigned)world);
+    const size_t b = (size_t)((unsigned __int128)total * (unsigned)(rank + 1) / (unsigned)world);
+    if (lo) *lo = a;
+    if (hi) *hi = b;
+}
+
+// multi_scalar_mul over a point vector sharded by contiguous range: this rank's slot holds its range, `scalars_mont`
+// are the scalars of that range.  Every rank receives the encoding of the whole sum.
+int dvp_msm_sharded(dvp_ctx *ctx, int slot, const uint64_t *scalars_mont, size_t n, int scalars_on_device, uint8_t out30[30]) {
+    if (!ctx || slot < 0 || slot >= DVP_MAX_SRS_SLOTS || !out30 || (!scalars_mont && n)) return DVP_ERR_BAD_ARG;
+    SrsSlot &s = ctx->slots[slot];
+    if (n != s.n) return DVP_ERR_LENGTH_MISMATCH;
+    CKN(cudaSetDevice(ctx->device));
+    int rc;
+    const void *d_sc = scalars_mont;
+    if (!scalars_on_device) {
+        if ((rc = ctx->scal.reserve(n * 32 + 32)) != 0) return rc;
+        if (n) CKN(cudaMemcpyAsync(ctx->scal.p, scalars_mont, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        d_sc = ctx->scal.p;
+    }
+    AffPt mine, total;
+    if ((rc = ctx->msm.run(s.buf.as<AffPt>(), (const uint32_t *)d_sc, n, &mine)) != 0) return rc;
+    if ((rc = comm_fold_points(ctx, mine, &total)) != 0) return rc;
+    host::encode30(out30, total);
+    return DVP_OK;
+}
+
+} // extern "C"

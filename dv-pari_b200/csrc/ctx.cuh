@@ -13,7 +13,16 @@ struct dvp_ctx {
     cudaStream_t stream = nullptr;
     dvp::MsmEngine msm;
     SrsSlot slots[DVP_MAX_SRS_SLOTS];
-    dvp::DevBuf bytes, small, scal, adhoc;
+    dvp::DevBuf bytes, small, scal, adhoc, commbuf;
+    // multi-GPU: NCCL communicator (ncclComm_t) of this rank, see comm.cu
+    void *comm = nullptr;
+    int rank = 0, world = 1;
 };
+
+// comm.cu
+int comm_all_gather(dvp_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);
+int comm_broadcast(dvp_ctx *ctx, void *buf, size_t bytes, int root);
+int comm_group(bool start);
+int comm_fold_points(dvp_ctx *ctx, const dvp::AffPt &mine, dvp::AffPt *total);
 
 int ctx_decode_into(dvp_ctx *ctx, const uint8_t *pts30, size_t n, dvp::AffPt *d_out, int64_t *first_invalid);

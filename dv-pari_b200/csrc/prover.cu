@@ -191,10 +191,11 @@ __device__ __forceinline__ fr row_dot(const R1csDev &r, int which, uint32_t row,
     return acc;
 }
 __global__ void __launch_bounds__(128)
-    k_r1cs_eval(R1csDev r, const fr *__restrict__ w, const fr *__restrict__ leaves, fr *__restrict__ a,
-                fr *__restrict__ b, fr *__restrict__ c, fr *__restrict__ iv, unsigned long long *__restrict__ first_bad) {
-    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= r.n) return;
+    k_r1cs_eval(R1csDev r, uint32_t row_lo, uint32_t row_hi, const fr *__restrict__ w, const fr *__restrict__ leaves,
+                fr *__restrict__ a, fr *__restrict__ b, fr *__restrict__ c, fr *__restrict__ iv,
+                unsigned long long *__restrict__ first_bad) {
+    const uint32_t row = row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= row_hi) return;
     fr av = fr_zero(), bv = fr_zero(), cw = fr_zero();
     if (row < r.nrows) {
         av = row_dot(r, 0, row, w);
@@ -637,18 +638,40 @@ void dvp_r1cs_destroy(dvp_r1cs *r) {
     delete r;
 }
 
+// rows [lo, hi) of this rank (all of them on one GPU), then the ranks exchange their ranges
 static int r1cs_eval_device(dvp_r1cs *r, dvp_domain *d, const fr *d_w, fr *a, fr *b, fr *c, fr *iv, int64_t *first_bad) {
     dvp_ctx *ctx = r->ctx;
     cudaStream_t st = ctx->stream;
     int rc;
-    if ((rc = ctx->small.reserve(64))) return rc;
+    const int W = ctx->world;
+    const size_t n = r->dev.n;
+    if (W > 1 && n % (size_t)W) return DVP_ERR_BAD_ARG;
+    size_t lo, hi;
+    dvp_shard_range(n, ctx->rank, W, &lo, &hi);
+    if ((rc = ctx->small.reserve(64 + 8 * 64))) return rc;
     unsigned long long init = ~0ull, bad = 0;
-    CKP(cudaMemcpyAsync(ctx->small.p, &init, 8, cudaMemcpyHostToDevice, st));
-    k_r1cs_eval<<<cdivp(r->dev.n, 128), 128, 0, st>>>(r->dev, d_w, d->leaves.as<fr>(), a, b, c, iv,
-                                                     (unsigned long long *)ctx->small.p);
+    unsigned long long *d_bad = (unsigned long long *)ctx->small.p; // [0] mine, [8..8+W) gathered
+    CKP(cudaMemcpyAsync(d_bad, &init, 8, cudaMemcpyHostToDevice, st));
+    k_r1cs_eval<<<cdivp(hi - lo, 128), 128, 0, st>>>(r->dev, (uint32_t)lo, (uint32_t)hi, d_w, d->leaves.as<fr>(), a, b, c,
+                                                    iv, d_bad);
     CKP(cudaGetLastError());
-    CKP(cudaMemcpyAsync(&bad, ctx->small.p, 8, cudaMemcpyDeviceToHost, st));
-    CKP(cudaStreamSynchronize(st));
+    if (W > 1) {
+        const size_t chunk = (n / W) * sizeof(fr);
+        if ((rc = comm_group(true))) return rc;
+        fr *vs[4] = {a, b, c, iv};
+        for (fr *v : vs)
+            if ((rc = comm_all_gather(ctx, v + lo, v, chunk))) return rc;
+        if ((rc = comm_all_gather(ctx, d_bad, d_bad + 8, 8))) return rc;
+        if ((rc = comm_group(false))) return rc;
+        unsigned long long all[64];
+        CKP(cudaMemcpyAsync(all, d_bad + 8, 8 * W, cudaMemcpyDeviceToHost, st));
+        CKP(cudaStreamSynchronize(st));
+        bad = ~0ull;
+        for (int i = 0; i < W; i++) bad = all[i] < bad ? all[i] : bad;
+    } else {
+        CKP(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, st));
+        CKP(cudaStreamSynchronize(st));
+    }
     if (first_bad) *first_bad = bad == ~0ull ? -1 : (int64_t)bad;
     return bad == ~0ull ? DVP_OK : DVP_ERR_UNSATISFIED;
 }
@@ -708,8 +731,16 @@ int dvp_prover_create(dvp_ctx *ctx, dvp_domain *dom, dvp_r1cs *r1cs, int slot_gm
     if (dom->n != r1cs->dev.n) return DVP_ERR_LENGTH_MISMATCH;
     const size_t n = dom->n;
     // multi_scalar_mul asserts scalars.len() == points.len() (curve.rs:142)
-    if (ctx->slots[slot_gm].n != r1cs->nwires || ctx->slots[slot_gq].n != n || ctx->slots[slot_gk].n != 4 * n)
-        return DVP_ERR_LENGTH_MISMATCH;
+    // (with a communicator: this rank's range of each vector)
+    {
+        const size_t tot[3] = {r1cs->nwires, n, 4 * n};
+        const int sl[3] = {slot_gm, slot_gq, slot_gk};
+        for (int i = 0; i < 3; i++) {
+            size_t lo, hi;
+            dvp_shard_range(tot[i], ctx->rank, ctx->world, &lo, &hi);
+            if (sl[i] < 0 || sl[i] >= DVP_MAX_SRS_SLOTS || ctx->slots[sl[i]].n != hi - lo) return DVP_ERR_LENGTH_MISMATCH;
+        }
+    }
     CKP(cudaSetDevice(ctx->device));
     dvp_prover *p = new dvp_prover();
     p->ctx = ctx;
@@ -817,11 +848,28 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     cudaEventRecord(ev[1], st);
     // commitment to the witness, proving.rs:462-463
     AffPt msm_gm, msm_q, kzg;
-    if ((rc = ctx->msm.run(ctx->slots[p->slot_gm].buf.as<AffPt>(), (const uint32_t *)w, r->nwires, &msm_gm))) return rc;
+    const int W = ctx->world, R = ctx->rank;
+    size_t wlo, whi, qlo, qhi, klo, khi;
+    dvp_shard_range(r->nwires, R, W, &wlo, &whi);
+    dvp_shard_range(n, R, W, &qlo, &qhi);
+    dvp_shard_range(4 * n, R, W, &klo, &khi);
+    AffPt part;
+    if ((rc = ctx->msm.run(ctx->slots[p->slot_gm].buf.as<AffPt>(), (const uint32_t *)(w + wlo), whi - wlo, &part))) return rc;
+    if ((rc = comm_fold_points(ctx, part, &msm_gm))) return rc;
     cudaEventRecord(ev[2], st);
     // extend a, b, c to D' (i' in closed form), proving.rs:475-482
     CKP(cudaMemcpyAsync(a2, a, 3 * n * sizeof(fr), cudaMemcpyDeviceToDevice, st));
-    if ((rc = extend_device(d, a2, 3, n))) return rc;
+    if (W == 1) {
+        if ((rc = extend_device(d, a2, 3, n))) return rc;
+    } else {
+        // independent polynomials: the owner extends, then every rank receives it
+        for (int pl = 0; pl < 3; pl++)
+            if (pl % W == R && (rc = extend_device(d, a2 + (size_t)pl * n, 1, n))) return rc;
+        if ((rc = comm_group(true))) return rc;
+        for (int pl = 0; pl < 3; pl++)
+            if ((rc = comm_broadcast(ctx, a2 + (size_t)pl * n, n * sizeof(fr), pl % W))) return rc;
+        if ((rc = comm_group(false))) return rc;
+    }
     k_ivals_ext<<<cdivp(n, 128), 128, 0, st>>>(w, (uint32_t)k, d->leaves.as<fr>(), (uint32_t)n, i2);
     if (stages) {
         CKP(cudaMemcpyAsync(stages, V, 8 * n * 32, cudaMemcpyDeviceToHost, st));
@@ -831,7 +879,8 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     k_quotient<<<cdivp(n, 128), 128, 0, st>>>(a2, b2, c2, i2, d->z_vals2inv.as<fr>(), (uint32_t)n, q);
     CKP(cudaGetLastError());
     cudaEventRecord(ev[3], st);
-    if ((rc = ctx->msm.run(ctx->slots[p->slot_gq].buf.as<AffPt>(), (const uint32_t *)q, n, &msm_q))) return rc;
+    if ((rc = ctx->msm.run(ctx->slots[p->slot_gq].buf.as<AffPt>(), (const uint32_t *)(q + qlo), qhi - qlo, &part))) return rc;
+    if ((rc = comm_fold_points(ctx, part, &msm_q))) return rc;
     cudaEventRecord(ev[4], st);
     const AffPt commit = host::aff_add(msm_q, msm_gm); // proving.rs:515
     host::encode30(proof, commit);
@@ -877,7 +926,8 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
         CKP(cudaMemcpyAsync(stages + 8 * n * 4, q, 5 * n * 32, cudaMemcpyDeviceToHost, st));
         CKP(cudaStreamSynchronize(st));
     }
-    if ((rc = ctx->msm.run(ctx->slots[p->slot_gk].buf.as<AffPt>(), (const uint32_t *)ks, 4 * n, &kzg))) return rc;
+    if ((rc = ctx->msm.run(ctx->slots[p->slot_gk].buf.as<AffPt>(), (const uint32_t *)(ks + klo), khi - klo, &part))) return rc;
+    if ((rc = comm_fold_points(ctx, part, &kzg))) return rc;
     cudaEventRecord(ev[6], st);
     cudaEventSynchronize(ev[6]);
     host::encode30(proof + 30, kzg);

@@ -79,6 +79,13 @@ def lib():
         L.dvp_msm_last_stats.argtypes = [vp, C.POINTER(MsmStats)]
         L.dvp_msm_last_profile.argtypes = [vp, vp, vp]
         L.dvp_point_add.argtypes = [vp, vp, vp, vp]
+        L.dvp_comm_unique_id.argtypes = [vp]
+        L.dvp_comm_init.argtypes = [vp, vp, i32, i32]
+        L.dvp_comm_destroy.argtypes = [vp]
+        L.dvp_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+        L.dvp_shard_range.argtypes = [sz, i32, i32, C.POINTER(sz), C.POINTER(sz)]
+        L.dvp_shard_range.restype = None
+        L.dvp_msm_sharded.argtypes = [vp, i32, vp, sz, i32, vp]
         L.dvp_dev_alloc.argtypes = [vp, sz, C.POINTER(vp)]
         L.dvp_dev_free.argtypes = [vp, vp]
         L.dvp_dev_upload.argtypes = [vp, vp, vp, sz]
@@ -211,6 +218,27 @@ class Context:
         _ck(lib().dvp_msm_adhoc(self._h, _ptr(a), _ptr(s), s.shape[0], _ptr(out)), "dvp_msm_adhoc")
         return out.tobytes()
 
+    # -- multi-GPU (one process per GPU, NCCL) ----------------------------------------------------
+    def comm_init(self, unique_id, rank, world):
+        """Join the NCCL communicator made from rank 0's comm_unique_id() (shipped by the host's own channel)."""
+        buf = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        assert buf.size == 128
+        _ck(lib().dvp_comm_init(self._h, _ptr(buf), rank, world), "dvp_comm_init")
+
+    def comm_destroy(self):
+        _ck(lib().dvp_comm_destroy(self._h))
+
+    def msm_sharded(self, scalars_mont, slot=0, on_device=False, n=None):
+        """multi_scalar_mul over a point vector sharded by contiguous range: the slot holds this rank's points,
+        scalars_mont its scalars (or a device pointer with on_device=True and n); same result on every rank."""
+        out = np.zeros(30, dtype=np.uint8)
+        if on_device:
+            _ck(lib().dvp_msm_sharded(self._h, slot, scalars_mont, n, 1, _ptr(out)), "dvp_msm_sharded")
+        else:
+            s = np.ascontiguousarray(scalars_mont, dtype=np.uint64).reshape(-1, 4)
+            _ck(lib().dvp_msm_sharded(self._h, slot, _ptr(s), s.shape[0], 0, _ptr(out)), "dvp_msm_sharded")
+        return out.tobytes()
+
     def msm_stats(self):
         st = MsmStats()
         _ck(lib().dvp_msm_last_stats(self._h, C.byref(st)))
@@ -270,6 +298,20 @@ class Context:
         v = C.c_double()
         _ck(lib().dvp_microbench(self._h, op, iters, C.byref(v)))
         return v.value
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 makes it, every rank passes it to Context.comm_init)."""
+    buf = np.zeros(128, dtype=np.uint8)
+    _ck(lib().dvp_comm_unique_id(_ptr(buf)), "dvp_comm_unique_id")
+    return buf.tobytes()
+
+
+def shard_range(total, rank, world):
+    """[lo, hi) of `total` items owned by `rank` (the rule the library shards points, rows and scalars by)."""
+    lo, hi = C.c_size_t(), C.c_size_t()
+    lib().dvp_shard_range(total, rank, world, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
 
 
 def hostcheck_op(op, a, b=None, out_stride=None):

@@ -96,6 +96,24 @@ int dvp_msm_last_stats(dvp_ctx *ctx, dvp_msm_stats *out);
  * launch; ms/count per category: 0 sort 1 plan 2 pass1 3 binv_up 4 binv_direct 5 binv_down 6 pass2 7 misc. */
 int dvp_msm_last_profile(dvp_ctx *ctx, float ms[8], unsigned count[8]);
 
+/*
+ * Multi-GPU: one process (context) per GPU.  The MSMs shard by contiguous point range, the row evaluation by row
+ * range, the extends by polynomial; exchanges run over NCCL (NVLink / NVSwitch) on the context's stream.
+ * Rank 0 makes a unique id, the host ships it to the other ranks by any channel, every rank calls dvp_comm_init.
+ * With a communicator set, dvp_prover_create expects the SRS slots to hold THIS RANK'S range of g_m / g_q / g_k
+ * (dvp_shard_range of nwires / n / 4n) and dvp_prove returns the same proof on every rank.
+ */
+int dvp_comm_unique_id(uint8_t id[128]);
+int dvp_comm_init(dvp_ctx *ctx, const uint8_t id[128], int rank, int world);
+int dvp_comm_destroy(dvp_ctx *ctx);
+int dvp_comm_info(dvp_ctx *ctx, int *rank, int *world);
+/* [lo, hi) of `total` items owned by `rank`: lo = floor(total * rank / world) */
+void dvp_shard_range(size_t total, int rank, int world, size_t *lo, size_t *hi);
+/* multi_scalar_mul over a sharded point vector: the slot holds this rank's n points, scalars_mont its n scalars
+ * (host memory, or device memory if scalars_on_device); every rank receives the encoding of the whole sum. */
+int dvp_msm_sharded(dvp_ctx *ctx, int slot, const uint64_t *scalars_mont, size_t n, int scalars_on_device,
+                    uint8_t out30[30]);
+
 /* CurvePoint::add on encodings (src/curve.rs:76-82): out = a (+) b.  Runs on the device of ctx. */
 int dvp_point_add(dvp_ctx *ctx, const uint8_t a30[30], const uint8_t b30[30], uint8_t out30[30]);
 

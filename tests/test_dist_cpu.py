@@ -1,0 +1,83 @@
+"""world_size-2 gloo run of the N > 1 host logic on CPU: the shard rule (dvp_shard_range), the exchange pattern of a
+sharded MSM (all-gather of the ranks' partial sums, fold in rank order) with the oracle standing in for the device
+MSM, and the row / polynomial ownership rules of the sharded prove."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n, q):
+    try:
+        _worker_body(rank, world, port, n, q)
+    except Exception as e:  # report instead of letting the parent wait for its time-out
+        q.put((rank, False, repr(e), 0))
+
+
+def _worker_body(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "dv-pari_b200"))
+    import dvpari
+    from oracle import oracle as O
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = dvpari.random_fr_mont(n, 21)
+    pts = O.chain_points(n, O.pt_mul(O.generator(), 12345), O.pt_mul(O.generator(), 777))
+    lo, hi = dvpari.shard_range(n, rank, world)
+    mine_pts = (O.Pt * (hi - lo))(*pts[lo:hi])
+    part = O.pt_encode(O.msm(sc[lo:hi], mine_pts, 1))  # this rank's partial sum (the device MSM's role)
+    t = torch.frombuffer(bytearray(part) + b"\0\0", dtype=torch.uint8)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t)
+    acc = O.pt_decode(bytes(outs[0].numpy()[:30]))[0]
+    for o in outs[1:]:
+        acc = O.pt_add(acc, O.pt_decode(bytes(o.numpy()[:30]))[0])
+    whole = O.pt_encode(O.msm(sc, pts, 1))
+    ok = O.pt_encode(acc) == whole
+    # every rank must hold the same bytes
+    mine = torch.frombuffer(bytearray(O.pt_encode(acc)) + b"\0\0", dtype=torch.uint8)
+    ref = mine.clone()
+    dist.broadcast(ref, src=0)
+    ok = ok and bool((ref == mine).all())
+    q.put((rank, ok, lo, hi))
+    dist.destroy_process_group()
+
+
+def test_shard_range_partitions():
+    sys.path.insert(0, os.path.join(ROOT, "dv-pari_b200"))
+    import dvpari
+
+    for total in (0, 1, 7, 4096, 4717470, (1 << 24) + 3):
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            for r in range(world):
+                lo, hi = dvpari.shard_range(total, r, world)
+                assert lo == prev and hi >= lo and hi - lo <= total // world + 1
+                prev = hi
+            assert prev == total
+    # the ownership rules of the sharded prove: rows need world | n, polynomial p lives on rank p % world
+    assert [p % 2 for p in range(3)] == [0, 1, 0] and [p % 8 for p in range(3)] == [0, 1, 2]
+
+
+def test_sharded_msm_exchange_gloo():
+    world, n = 2, 600
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29400 + os.getpid() % 500
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _, _ in res), res
+    spans = sorted((lo, hi) for _, _, lo, hi in res)
+    assert spans[0][0] == 0 and spans[-1][1] == n and spans[0][1] == spans[1][0]
