@@ -144,8 +144,9 @@ def run_reference(args):
 FR_MUL_PEAK = 4.5e10  # measured fr_mul/s of the CIOS multiplier (profiles/r1_pipe_rates.json), the ECFFT's bound
 
 
-def prove_section(ctx, args):
-    """Proof::prove at 2^prove_lg constraints on one GPU: ms per proof and the stage split."""
+def prove_section(ctx, args, rank, world, sync_all, timed):
+    """Proof::prove at 2^prove_lg constraints: ms per proof and the stage split.  With N ranks the same proof is
+    made by all of them together (strong scaling): every rank holds 1/N of g_m / g_q / g_k."""
     import numpy as np
 
     import dvpari
@@ -159,23 +160,37 @@ def prove_section(ctx, args):
     dom = dvpari.Domain(ctx, lg + 1)
     n, k = circ["n"], circ["k"]
     # timing only: random group elements as SRS (tests/test_gpu_synth.py proves with a real SRS and verifies)
-    ctx.srs_random(1, circ["nwires"], 0xD5A10005)
-    ctx.srs_random(2, n, 0xD5A10006)
-    ctx.srs_random(3, 4 * n, 0xD5A10007)
+    for slot, tot in ((1, circ["nwires"]), (2, n), (3, 4 * n)):
+        lo, hi = dvpari.shard_range(tot, rank, world)
+        ctx.srs_random(slot, hi - lo, 0xD5A10005 + 16 * slot + rank)
     prover = dvpari.Prover(ctx, dom, inst, 1, 2, 3)
-    pub, priv = w[1:1 + k], w[1 + k:]
+    import torch
+
+    # the witness sits in pinned host memory (the upload is inside every timed dvp_prove call)
+    pinned = torch.empty((circ["nwires"], 4), dtype=torch.int64).pin_memory()
+    wp = pinned.numpy().view(np.uint64)
+    wp[:] = w
+    pub, priv = wp[1:1 + k], wp[1 + k:]
     ref = prover.prove(pub, priv)  # warm-up: sizes the scratch
     prover.prove(pub, priv)
     reps = max(3, min(args.steps, 5))
     stages = {}
-    t0 = time.perf_counter()
-    for _ in range(reps):
+
+    def one():
         proof = prover.prove(pub, priv)
         for a, b in prover.last_times().items():
             stages[a] = stages.get(a, 0.0) + b / reps
-    ms = 1e3 * (time.perf_counter() - t0) / reps
+        return proof
+
+    dt, proof = timed(one, reps)  # barrier + synchronize on both sides, max over ranks
+    ms = 1e3 * dt / reps
     assert proof == ref
     terms = int(sum(len(x) for x in circ["wire"]))
+    if rank != 0:
+        prover.close()
+        inst.close()
+        dom.close()
+        return None
     # ECFFT extend alone: 3 polynomials of n evaluations, in place on the device
     d = ctx.dev_alloc(3 * n * 32)
     ctx.dev_upload(d, dvpari.random_fr_mont(3 * n, 5))
@@ -189,6 +204,7 @@ def prove_section(ctx, args):
     mulmods = 3 * 4 * n * lg  # 4 n log2 n per polynomial
     ext_bytes = 3 * 2 * lg * (64 * (n // 2)) + 2 * 256 * n  # data in + out per level and polynomial, matrices once per level pair
     out = {
+        "n_gpus": world, "scaling": "strong" if world > 1 else "single GPU",
         "constraints": n, "rows": circ["nrows"], "terms": terms, "wires": circ["nwires"], "public_inputs": k,
         "ms_per_proof": ms, "proofs": reps, "stage_ms": stages,
         "h2d_bytes_per_proof": int(circ["nwires"] * 32), "d2h_bytes_per_proof": 118,
@@ -243,6 +259,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = 1 << args.lg
     ctx = dvpari.Context(local)
+    if use_dist:
+        # the library's own NCCL communicator; torch.distributed only ships the id and runs the barriers
+        ids = [dvpari.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(ids[0], rank, world)
     if args.window_bits:
         ctx.set("msm_window_bits", args.window_bits)
     # this rank's range of the N*2^lg-point SRS and of the scalar vector
@@ -253,18 +274,6 @@ def main():
     sc_pinned = pinned.numpy().view(np.uint64)
     d_sc = ctx.dev_alloc(n * 32)
     ctx.dev_upload(d_sc, sc_host)
-
-    def fold(partial30):
-        """all-gather the 30-byte partial sums and fold them (CurvePoint::add, curve.rs:76-82)."""
-        if not use_dist:
-            return partial30
-        t = torch.frombuffer(bytearray(partial30) + b"\0\0", dtype=torch.uint8).cuda()
-        outs = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(outs, t)
-        acc = bytes(outs[0].cpu().numpy()[:30])
-        for o in outs[1:]:
-            acc = ctx.point_add(acc, bytes(o.cpu().numpy()[:30]))
-        return acc
 
     def sync_all():
         torch.cuda.synchronize()
@@ -285,8 +294,10 @@ def main():
             dt = float(t.item())
         return dt, out
 
-    step_dev = lambda: fold(ctx.multi_scalar_mul_device(d_sc, n, 0))
-    step_e2e = lambda: fold(ctx.multi_scalar_mul(sc_pinned, 0))
+    # dvp_msm_sharded: local MSM over this rank's point range, all-gather of the 64-byte partial sums over NCCL,
+    # identical fold on every rank (with one rank it is the plain MSM)
+    step_dev = lambda: ctx.msm_sharded(d_sc, 0, on_device=True, n=n)
+    step_e2e = lambda: ctx.msm_sharded(sc_pinned, 0)
 
     for _ in range(args.warmup):
         step_dev()
@@ -309,9 +320,7 @@ def main():
     ctx.set("timing", 0)
     ctx.set("msm_lanes", 0)
 
-    prove = None
-    if args.prove_lg and rank == 0 and world == 1:
-        prove = prove_section(ctx, args)
+    prove = prove_section(ctx, args, rank, world, sync_all, timed) if args.prove_lg else None
 
     if rank == 0:
         hbm_peak, which = peaks()
@@ -332,7 +341,7 @@ def main():
                        "window_bits": st["window_bits"], "windows": st["windows"],
                        "rounds": [st["rounds_main"], st["rounds_a"], st["rounds_b"]],
                        "l2": "per-step working set (sort keys, ping-pong point buffers, prefix products: >1 GB at 2^20) exceeds the 126 MB L2",
-                       "parallelism": f"point-range sharding x{world}, NCCL all-gather of 30-byte partial sums" if world > 1 else "single GPU",
+                       "parallelism": f"point-range sharding x{world}, NCCL all-gather of 64-byte partial sums, fold on every rank" if world > 1 else "single GPU",
                        "stage_ms": {"recode_sort": st["ms_recode_sort"], "accumulate": st["ms_accumulate"],
                                     "reduce": st["ms_reduce"], "tail": st["ms_tail"]}},
             "e2e": {"value": world * n * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": n * 32,

@@ -238,7 +238,10 @@ void dvp_ctx_destroy(dvp_ctx *ctx) {
     dvp_comm_destroy(ctx);
     ctx->msm.destroy();
     ctx->commbuf.release();
-    for (auto &s : ctx->slots) s.buf.release();
+    for (auto &s : ctx->slots) {
+        s.buf.release();
+        s.table.release();
+    }
     ctx->bytes.release();
     ctx->small.release();
     ctx->scal.release();
@@ -256,6 +259,21 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
     if (!strcmp(name, "msm_lanes")) {
         if (value < 0 || value > 16) return DVP_ERR_BAD_ARG;
         ctx->msm.force_lanes = (int)value;
+        return DVP_OK;
+    }
+    if (!strcmp(name, "msm_tables")) {
+        ctx->msm_tables = value != 0;
+        return DVP_OK;
+    }
+    if (!strcmp(name, "msm_table_windows")) {
+        if (value != 0 && (value < 9 || value > 59)) return DVP_ERR_BAD_ARG;
+        ctx->msm_table_windows = (int)value;
+        for (auto &sl : ctx->slots) sl.invalidate();
+        return DVP_OK;
+    }
+    if (!strcmp(name, "msm_tables_min")) {
+        if (value < 1) return DVP_ERR_BAD_ARG;
+        ctx->msm_tables_min = (size_t)value;
         return DVP_OK;
     }
     if (!strcmp(name, "binv_direct")) {
@@ -281,10 +299,46 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
 
 static int slot_ok(dvp_ctx *ctx, int slot) { return ctx && slot >= 0 && slot < DVP_MAX_SRS_SLOTS; }
 
+extern "C++" {
+// MSM over slot[offset, offset + n).  Large slots get W tables T[j] = 2^(j c) P once (W x the slot's memory), after
+// which all windows share one bucket set; small slots, small sub-ranges and tight memory use the plain layout.
+int slot_msm(dvp_ctx *ctx, int slot, size_t offset, const uint32_t *d_scalars, size_t n, AffPt *out) {
+    SrsSlot &s = ctx->slots[slot];
+    const bool want = ctx->msm_tables && s.n >= ctx->msm_tables_min && n >= s.n / 2 && !ctx->msm.force_window_bits;
+    if (want && !s.table_ok && !s.table_failed) {
+        const int W = ctx->msm_table_windows ? ctx->msm_table_windows : choose_table_windows(s.n);
+        const size_t bytes = (size_t)W * s.n * sizeof(AffPt);
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        // keep room for the MSM scratch (about as large again) and the caller's own vectors
+        if ((size_t)W * s.n < (1ull << 31) && bytes + bytes / 2 + (4ull << 30) < free_b && s.table.reserve(bytes) == 0) {
+            int rc = ctx->msm.build_table(s.buf.as<AffPt>(), s.n, W, s.table.as<AffPt>());
+            if (rc) {
+                s.table.release();
+                return rc;
+            }
+            s.tab.W = W;
+            s.tab.stride = s.n;
+            s.table_ok = true;
+        } else {
+            s.table.release();
+            s.table_failed = true;
+        }
+    }
+    if (want && s.table_ok) {
+        MsmTable t = s.tab;
+        t.offset = offset;
+        return ctx->msm.run(s.table.as<AffPt>(), d_scalars, n, out, &t);
+    }
+    return ctx->msm.run(s.buf.as<AffPt>() + offset, d_scalars, n, out);
+}
+} // extern "C++"
+
 int dvp_srs_append(dvp_ctx *ctx, int slot, const uint8_t *pts30, size_t n, int64_t *first_invalid) {
     if (!slot_ok(ctx, slot) || (!pts30 && n)) return DVP_ERR_BAD_ARG;
     CKC(cudaSetDevice(ctx->device));
     SrsSlot &s = ctx->slots[slot];
+    s.invalidate();
     const size_t need = (s.n + n) * sizeof(AffPt);
     if (need > s.buf.cap) {
         DevBuf nb;
@@ -304,12 +358,14 @@ int dvp_srs_append(dvp_ctx *ctx, int slot, const uint8_t *pts30, size_t n, int64
 int dvp_srs_load(dvp_ctx *ctx, int slot, const uint8_t *pts30, size_t n, int64_t *first_invalid) {
     if (!slot_ok(ctx, slot)) return DVP_ERR_BAD_ARG;
     ctx->slots[slot].n = 0;
+    ctx->slots[slot].invalidate();
     return dvp_srs_append(ctx, slot, pts30, n, first_invalid);
 }
 int dvp_srs_random(dvp_ctx *ctx, int slot, size_t n, uint64_t seed) {
     if (!slot_ok(ctx, slot)) return DVP_ERR_BAD_ARG;
     CKC(cudaSetDevice(ctx->device));
     SrsSlot &s = ctx->slots[slot];
+    s.invalidate();
     int rc;
     if ((rc = s.buf.reserve((n ? n : 1) * sizeof(AffPt))) != 0) return rc;
     s.n = n;
@@ -323,6 +379,7 @@ int dvp_srs_mulgen(dvp_ctx *ctx, int slot, const uint64_t *scalars_mont, size_t 
     if (!slot_ok(ctx, slot) || (!scalars_mont && n)) return DVP_ERR_BAD_ARG;
     CKC(cudaSetDevice(ctx->device));
     SrsSlot &s = ctx->slots[slot];
+    s.invalidate();
     int rc;
     if ((rc = s.buf.reserve((n ? n : 1) * sizeof(AffPt))) != 0) return rc;
     s.n = n;
@@ -340,6 +397,7 @@ int dvp_srs_free(dvp_ctx *ctx, int slot) {
     if (!slot_ok(ctx, slot)) return DVP_ERR_BAD_ARG;
     CKC(cudaSetDevice(ctx->device));
     ctx->slots[slot].buf.release();
+    ctx->slots[slot].invalidate();
     ctx->slots[slot].n = 0;
     return DVP_OK;
 }
@@ -364,7 +422,7 @@ int dvp_msm_device(dvp_ctx *ctx, int slot, size_t offset, const void *d_scalars,
     if (offset > s.n || n > s.n - offset) return DVP_ERR_LENGTH_MISMATCH;
     CKC(cudaSetDevice(ctx->device));
     AffPt r;
-    int rc = ctx->msm.run(s.buf.as<AffPt>() + offset, (const uint32_t *)d_scalars, n, &r);
+    int rc = slot_msm(ctx, slot, offset, (const uint32_t *)d_scalars, n, &r);
     if (rc) return rc;
     host::encode30(out30, r);
     return DVP_OK;
@@ -411,6 +469,7 @@ int dvp_msm_last_stats(dvp_ctx *ctx, dvp_msm_stats *out) {
     out->adds_round0 = s.adds_round0;
     out->ms_device = s.ms_device;
     out->lanes = s.lanes;
+    out->tables = s.tables;
     return DVP_OK;
 }
 

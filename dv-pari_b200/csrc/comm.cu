@@ -182,7 +182,7 @@ int dvp_msm_sharded(dvp_ctx *ctx, int slot, const uint64_t *scalars_mont, size_t
         d_sc = ctx->scal.p;
     }
     AffPt mine, total;
-    if ((rc = ctx->msm.run(s.buf.as<AffPt>(), (const uint32_t *)d_sc, n, &mine)) != 0) return rc;
+    if ((rc = slot_msm(ctx, slot, 0, (const uint32_t *)d_sc, n, &mine)) != 0) return rc;
     if ((rc = comm_fold_points(ctx, mine, &total)) != 0) return rc;
     host::encode30(out30, total);
     return DVP_OK;

@@ -6,6 +6,14 @@
 struct SrsSlot {
     dvp::DevBuf buf; // AffPt[n], decoded once (replaces read_point_vec_from_file per prove)
     size_t n = 0;
+    // precomputed window multiples of the slot (built on first use, dropped when the slot changes)
+    dvp::DevBuf table;
+    dvp::MsmTable tab;
+    bool table_ok = false, table_failed = false;
+    void invalidate() {
+        table.release();
+        table_ok = table_failed = false;
+    }
 };
 
 struct dvp_ctx {
@@ -17,7 +25,13 @@ struct dvp_ctx {
     // multi-GPU: NCCL communicator (ncclComm_t) of this rank, see comm.cu
     void *comm = nullptr;
     int rank = 0, world = 1;
+    int msm_table_windows = 0;             // 0: choose_table_windows(slot size)
+    int msm_tables = 1;                    // 0: never, 1: when the slot is large enough and the memory is there
+    size_t msm_tables_min = (size_t)1 << 15; // smallest slot that gets tables
 };
+
+// sum_i scalars[i] * slot[offset + i] on the device of ctx (device scalars); uses the slot's tables when it has them
+int slot_msm(dvp_ctx *ctx, int slot, size_t offset, const uint32_t *d_scalars, size_t n, dvp::AffPt *out);
 
 // comm.cu
 int comm_all_gather(dvp_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);

@@ -90,11 +90,13 @@ int choose_window_bits(size_t n) {
 // ------------------------------------------------------------------------------------------------
 // recode + histogram
 // ------------------------------------------------------------------------------------------------
-// Window j covers bits [off_j, off_j + width_j) with width_j = base + (j < rem), off_j = j*base + min(j, rem):
-// the 233 scalar bits are spread evenly over the W windows so that no window is nearly empty (a
-// short top window would put all n entries into a handful of buckets and double the tree depth).
+// Window j covers bits [off_j, off_j + width_j) with width_j = base + (j < rem), off_j = j*base + min(j, rem): the 233
+// scalar bits are spread evenly over the W windows so that no window is nearly empty (a short top window would put
+// all n entries into a handful of buckets and double the tree depth).  Two bucket layouts:
+//   separate bucket sets (uniform = 0): key = j*nb + d - 1, the point of an entry is P_i;
+//   one shared bucket set (uniform = 1, precomputed tables T[j] = 2^(off_j) P): key = d - 1, the point is T[j][i].
 __global__ void k_recode_count(const uint32_t *__restrict__ scalars, uint32_t n, int base, int rem, int W, uint32_t nb,
-                               uint32_t *__restrict__ keys, uint32_t *__restrict__ seg_len) {
+                               int uniform, uint32_t *__restrict__ keys, uint32_t *__restrict__ seg_len) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fr a;
@@ -128,7 +130,7 @@ __global__ void k_recode_count(const uint32_t *__restrict__ scalars, uint32_t n,
         }
         uint32_t out = 0xffffffffu;
         if (d) {
-            const uint32_t key = (uint32_t)j * nb + d - 1;
+            const uint32_t key = (uniform ? 0u : (uint32_t)j * nb) + d - 1;
             out = (key << 1) | neg;
             atomicAdd(&seg_len[key], 1u);
         }
@@ -136,16 +138,37 @@ __global__ void k_recode_count(const uint32_t *__restrict__ scalars, uint32_t n,
     }
 }
 
-// keys: the (window-major) slice of one lane; key_base = first bucket key of that slice
-__global__ void k_scatter(const uint32_t *__restrict__ keys, uint32_t n, size_t total, uint32_t key_base,
-                          uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
+// counting sort, second half: entry = index of the point in the source list | negate << 31, where the source
+// list is the point range itself (ebase_stride = 0) or the tables (window j starts at j * ebase_stride)
+__global__ void k_scatter(const uint32_t *__restrict__ keys, uint32_t n, size_t total, uint32_t ebase0,
+                          uint32_t ebase_stride, uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const uint32_t k = keys[e];
     if (k == 0xffffffffu) return;
-    const uint32_t i = (uint32_t)(e % n);
-    const uint32_t pos = atomicAdd(&cursor[(k >> 1) - key_base], 1u);
-    entries[pos] = i | ((k & 1u) << 31);
+    const uint32_t j = (uint32_t)(e / n), i = (uint32_t)(e - (size_t)j * n);
+    const uint32_t pos = atomicAdd(&cursor[k >> 1], 1u);
+    entries[pos] = (ebase0 + j * ebase_stride + i) | ((k & 1u) << 31);
+}
+
+// per lane (one block each): entries and longest bucket of the segment range [bounds[l], bounds[l+1])
+__global__ void k_lane_info(const uint32_t *__restrict__ len, const uint32_t *__restrict__ start,
+                            const uint32_t *__restrict__ bounds, uint32_t *__restrict__ out) {
+    __shared__ uint32_t sh[32];
+    const uint32_t s0 = bounds[blockIdx.x], s1 = bounds[blockIdx.x + 1];
+    uint32_t mx = 0;
+    for (uint32_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) mx = max(mx, len[s]);
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        mx = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0;
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+        if (threadIdx.x == 0) {
+            out[2 * blockIdx.x] = start[s1] - start[s0];
+            out[2 * blockIdx.x + 1] = mx;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -726,8 +749,8 @@ void MsmLane::destroy() {
     }
     prof.clear();
     prof_used = 0;
-    DevBuf *all[] = {&entries, &seg_len[0], &seg_len[1], &seg_start[0], &seg_start[1], &c_len, &c_start,
-                     &cursor, &blk, &blk_flag, &info, &pp[0], &pp[1], &prefix, &desc, &thr_total, &thr_inv, &lvl_pre[0],
+    DevBuf *all[] = {&seg_len[0], &seg_len[1], &seg_start[0], &seg_start[1], &c_len, &c_start,
+                     &blk, &blk_flag, &info, &info_r0, &pp[0], &pp[1], &prefix, &desc, &thr_total, &thr_inv, &lvl_pre[0],
                      &lvl_pre[1], &lvl_tot[0], &lvl_tot[1], &lvl_inv[0], &lvl_inv[1], &buckets, &rc, &ents2};
     for (auto b : all) b->release();
     if (h_info) cudaFreeHost(h_info);
@@ -757,6 +780,13 @@ void MsmEngine::destroy() {
     for (auto &l : lanes) l.destroy();
     lanes.clear();
     keys.release();
+    entries.release();
+    start_all.release();
+    cursor_all.release();
+    scan_blk.release();
+    lane_info.release();
+    if (h_lane) cudaFreeHost(h_lane);
+    h_lane = nullptr;
     len_all.release();
     hb.release();
     msqr_tabs.release();
@@ -905,7 +935,7 @@ struct Tree {
         for (int r = 0; r < nr; r++) {
             const int o = (r + 1) & 1; // lane set written by this round's plan
             // tasks_r <= total/2^(r+1) + nseg/2
-            const size_t task_ub = (total_ub >> (r + 1)) + nseg / 2 + 1;
+            const size_t task_ub = r == 0 ? total_ub / 2 + 1 : (total_ub >> (r + 1)) + nseg / 2 + 1;
             const int B = task_ub >= (1u << 21) ? 16 : task_ub >= (1u << 17) ? 4 : 1;
             AffPt *out = L.pp[r & 1].as<AffPt>();
             if ((rc = round(B, cur_src, task_ub, out))) return rc;
@@ -937,6 +967,7 @@ int MsmEngine::reserve_round(MsmLane &L, size_t task_ub) {
 #define RS(buf, bytes) \
     if ((rc = (buf).reserve(bytes)) != 0) return rc
     RS(L.info, 64);
+    RS(L.info_r0, 64);
     RS(L.prefix, task_ub * sizeof(gf));
     RS(L.desc, task_ub * sizeof(uint4));
     const size_t thr_ub = std::max<size_t>(task_ub / 16, 1u << 19) + 1024; // B = 16 / 4 / 1 regimes
@@ -973,6 +1004,54 @@ __global__ void k_mulgen_desc(const uint32_t *__restrict__ scalars, uint32_t n, 
     fr_to_canonical(k, a);
     const uint32_t d = (k[j >> 2] >> (8 * (j & 3))) & 255u;
     desc[i] = make_uint4(i, d ? tab0 + (uint32_t)j * MG_DIGITS + d - 1 : tab0 + (uint32_t)(MG_TABLE - 1), i, 0);
+}
+
+__global__ void k_self_desc(uint32_t n, uint4 *__restrict__ desc) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) desc[i] = make_uint4(i, i, i, 0);
+}
+
+// T[j] = 2^(width of window j-1) T[j-1]: rounds of n batched affine doublings (a pair (P, P) is the tangent case of
+// the addition); the windows are those of run(): width base + (j < rem) with base = 233 / W, rem = 233 % W
+int MsmEngine::build_table(const AffPt *d_points, size_t n, int W, AffPt *d_tab) {
+    const int base = 233 / W, rem = 233 % W;
+    if (n == 0) return 0;
+    if (lanes.empty()) {
+        lanes.emplace_back();
+        int rc0 = lanes.back().init();
+        if (rc0) return rc0;
+    }
+    MsmLane &L = lanes[0];
+    cudaStream_t st = L.stream;
+    int rc;
+    const size_t CH = (size_t)1 << 22; // points per pass (bounds the scratch)
+    const size_t chunk_max = std::min(n, CH);
+    if ((rc = reserve_round(L, chunk_max + 1))) return rc;
+    for (int i = 0; i < 2; i++)
+        if ((rc = L.pp[i].reserve(chunk_max * sizeof(AffPt)))) return rc;
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaMemcpyAsync(d_tab, d_points, n * sizeof(AffPt), cudaMemcpyDeviceToDevice, st));
+    Tree tree(*this, L);
+    for (size_t off = 0; off < n; off += CH) {
+        const uint32_t m = (uint32_t)std::min(CH, n - off);
+        const uint32_t info_h[4] = {0, m, m, 0};
+        CK(cudaMemcpyAsync(L.info.p, info_h, 16, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st)); // info_h is a stack temporary
+        k_self_desc<<<cdiv(m, 256), 256, 0, st>>>(m, L.desc.as<uint4>());
+        const int B = m >= (1u << 21) ? 16 : m >= (1u << 17) ? 4 : 1;
+        for (int j = 1; j < W; j++) {
+            const AffPt *src = d_tab + (size_t)(j - 1) * n + off;
+            AffPt *dst = d_tab + (size_t)j * n + off;
+            const int c = base + (j - 1 < rem ? 1 : 0);
+            for (int r = 0; r < c; r++) {
+                AffPt *out = r == c - 1 ? dst : L.pp[r & 1].as<AffPt>();
+                if ((rc = tree.round(B, src, m, out))) return rc;
+                src = out;
+            }
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    return 0;
 }
 
 int MsmEngine::mulgen(const uint32_t *d_scalars, size_t n, AffPt *d_out) {
@@ -1030,27 +1109,56 @@ int MsmEngine::mulgen(const uint32_t *d_scalars, size_t n, AffPt *d_out) {
     return 0;
 }
 
-int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, AffPt *h_result) {
+// cost model of the shared-bucket-set layout: W n bucket additions + ~1.5 * 2^c for the reduction
+int choose_table_windows(size_t n) {
+    int best = 16;
+    double best_cost = 1e300;
+    for (int W = 9; W <= 30; W++) {
+        const int c = 233 / W + (233 % W ? 1 : 0);
+        const double cost = (double)n * W + 1.5 * (double)(1ull << c);
+        if (cost < best_cost) best_cost = cost, best = W;
+    }
+    return best;
+}
+
+int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, AffPt *h_result, const MsmTable *tab) {
     *h_result = pt_inf();
     if (n == 0) return 0;
     if (n >= (1ull << 31)) return DVP_ERR_BAD_ARG;
-    const int c_req = force_window_bits ? force_window_bits : choose_window_bits(n);
-    if (c_req < 4 || c_req > 20) return DVP_ERR_BAD_ARG;
-    // W windows of width base or base+1 covering exactly 233 bits (bit 232 of a scalar < p is zero, so the
-    // top window never carries out); c = the widest window sizes the bucket tables
-    const int W = (233 + c_req - 1) / c_req;
-    const int base = 233 / W, rem = 233 % W;
-    const int c = base + (rem ? 1 : 0);
-    const uint32_t nb = 1u << (c - 1);
+    // ---- window layout
+    int W, base, rem, c;
+    const bool uniform = tab != nullptr;
+    if (uniform) {
+        // shared bucket set over the tables T[j] = 2^(off_j) P
+        W = tab->W;
+        base = 233 / W;
+        rem = 233 % W;
+        c = base + (rem ? 1 : 0);
+    } else {
+        const int c_req = force_window_bits ? force_window_bits : choose_window_bits(n);
+        if (c_req < 4 || c_req > 20) return DVP_ERR_BAD_ARG;
+        // W windows of width base or base+1 covering exactly 233 bits (bit 232 of a scalar < p is zero, so the
+        // top window never carries out); c = the widest window sizes the bucket tables
+        W = (233 + c_req - 1) / c_req;
+        base = 233 / W;
+        rem = 233 % W;
+        c = base + (rem ? 1 : 0);
+    }
+    const uint32_t nb = 1u << (c - 1);                    // buckets of one set
+    const size_t NB = uniform ? nb : (size_t)W * nb;      // all buckets = segments of the sorted entry list
     const size_t total = (size_t)W * n;
-    if (total >= (1ull << 32)) return DVP_ERR_BAD_ARG;
-    // bucket matrix of a window: m = 2^lm columns, R = 2^lr rows, nb = R*m
-    const uint32_t lm = (uint32_t)c / 2, lr = (uint32_t)(c - 1) - lm;
+    if (total >= (1ull << 32) || NB >= (1ull << 31) || c < 4 || c > 26) return DVP_ERR_BAD_ARG;
+    // virtual windows: aligned ranges of nbv buckets, the unit of the reduction and of the lane split
+    const int cv = uniform ? std::min(c, 15) : c;         // log2(nbv) + 1
+    const uint32_t nbv = 1u << (cv - 1);
+    const uint32_t V = (uint32_t)(NB / nbv);
+    // bucket matrix of a virtual window: m = 2^lm columns, R = 2^lr rows, nbv = R*m
+    const uint32_t lm = (uint32_t)cv / 2, lr = (uint32_t)(cv - 1) - lm;
     const uint32_t R = 1u << lr, m = 1u << lm;
     const uint32_t per_b = lm * (m >> 1) + lr * (R >> 1) + m;
-    // lanes: independent chains of rounds over disjoint window ranges
+    // lanes: independent chains of rounds over disjoint ranges of virtual windows
     int NL = profile ? 1 : force_lanes ? force_lanes : (n >= (1u << 13) ? 2 : 1);
-    NL = std::max(1, std::min(NL, W));
+    NL = std::max(1, std::min<int>(NL, (int)V));
     while ((int)lanes.size() < NL) {
         lanes.emplace_back();
         int rc0 = lanes.back().init();
@@ -1061,44 +1169,96 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
 #define RS(buf, bytes) \
     if ((rc = (buf).reserve(bytes)) != 0) return rc
     RS(keys, total * 4);
-    RS(len_all, ((size_t)W * nb + 1) * 4);
-    RS(hb, (size_t)W * c * sizeof(AffPt));
+    RS(entries, total * 4);
+    RS(len_all, (NB + 1) * 4);
+    RS(start_all, (NB + 1) * 4);
+    RS(cursor_all, (NB + 1) * 4);
+    RS(scan_blk, (NB / SCAN_TILE + 8) * 8);
+    RS(lane_info, 64 * 4);
+    RS(hb, (size_t)V * cv * sizeof(AffPt));
+    if (!h_lane) CK(cudaMallocHost(&h_lane, 64 * 4));
+    const size_t hb_bytes = (size_t)V * cv * sizeof(AffPt);
+    if (h_pts_cap < hb_bytes) {
+        if (h_pts) cudaFreeHost(h_pts);
+        h_pts = nullptr;
+        h_pts_cap = 0;
+        CK(cudaMallocHost(&h_pts, hb_bytes));
+        h_pts_cap = hb_bytes;
+    }
     struct Part {
-        int w0, wn;
+        uint32_t v0, vn;
         uint32_t nseg, nseg_a, nent_a, nseg_b, nent_b;
         size_t total;
+        uint32_t maxlen;
     };
     std::vector<Part> part(NL);
+    uint32_t bounds[17];
     for (int l = 0; l < NL; l++) {
         Part &p = part[l];
-        p.w0 = (int)((long long)W * l / NL);
-        p.wn = (int)((long long)W * (l + 1) / NL) - p.w0;
-        p.nseg = (uint32_t)p.wn * nb;
-        p.total = (size_t)p.wn * n;
-        p.nseg_a = (uint32_t)p.wn * (R + m);
-        p.nent_a = (uint32_t)p.wn * 2 * nb;
-        p.nseg_b = (uint32_t)p.wn * (uint32_t)c;
-        p.nent_b = (uint32_t)p.wn * per_b;
+        p.v0 = (uint32_t)((unsigned long long)V * l / NL);
+        p.vn = (uint32_t)((unsigned long long)V * (l + 1) / NL) - p.v0;
+        p.nseg = p.vn * nbv;
+        p.nseg_a = p.vn * (R + m);
+        p.nent_a = p.vn * 2 * nbv;
+        p.nseg_b = p.vn * (uint32_t)cv;
+        p.nent_b = p.vn * per_b;
+        bounds[l] = p.v0 * nbv;
+    }
+    bounds[NL] = (uint32_t)NB;
+
+    cudaStream_t st = stream;
+    cudaEventRecord(ev_t0, st);
+    if (timing) cudaEventRecord(ev[0], st);
+    // ---- recode + histogram, counting sort of all (point, window) entries by bucket (context stream)
+    uint32_t *d_len_all = len_all.as<uint32_t>(), *d_start_all = start_all.as<uint32_t>();
+    CK(cudaMemsetAsync(d_len_all, 0, NB * 4, st));
+    k_recode_count<<<cdiv(n, 128), 128, 0, st>>>(d_scalars, (uint32_t)n, base, rem, W, nb, uniform ? 1 : 0,
+                                                 keys.as<uint32_t>(), d_len_all);
+    {
+        const uint32_t nblk = cdiv(NB, SCAN_TILE);
+        k_scan1<0><<<nblk, SCAN_THREADS, 0, st>>>(d_len_all, (uint32_t)NB, scan_blk.as<uint64_t>(), nullptr);
+        k_scan2<<<1, SCAN_THREADS, 0, st>>>(scan_blk.as<uint64_t>(), nblk);
+        k_scan3<0><<<nblk, SCAN_THREADS, 0, st>>>(d_len_all, (uint32_t)NB, scan_blk.as<uint64_t>(), d_start_all,
+                                                  cursor_all.as<uint32_t>(), nullptr, nullptr);
+        k_scatter<<<cdiv(total, 256), 256, 0, st>>>(keys.as<uint32_t>(), (uint32_t)n, total,
+                                                    uniform ? (uint32_t)tab->offset : 0u,
+                                                    uniform ? (uint32_t)tab->stride : 0u, cursor_all.as<uint32_t>(),
+                                                    entries.as<uint32_t>());
+        CK(cudaMemcpyAsync(lane_info.as<uint32_t>() + 32, bounds, (NL + 1) * 4, cudaMemcpyHostToDevice, st));
+        k_lane_info<<<NL, 256, 0, st>>>(d_len_all, d_start_all, lane_info.as<uint32_t>() + 32, lane_info.as<uint32_t>());
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_lane, lane_info.p, 2 * NL * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaEventRecord(ev_recode, st));
+    unsigned long long launches = 7;
+    CK(cudaStreamSynchronize(st)); // the one read-back: entries and longest bucket per lane size the rounds
+    MsmStats stt;
+    stt.window_bits = c;
+    stt.windows = W;
+    stt.lanes = NL;
+    stt.tables = uniform ? 1 : 0;
+    for (int l = 0; l < NL; l++) {
+        Part &p = part[l];
+        p.total = ((const uint32_t *)h_lane)[2 * l];
+        p.maxlen = ((const uint32_t *)h_lane)[2 * l + 1];
+        stt.adds_total += p.total;
         MsmLane &L = lanes[l];
         const size_t nseg_max = std::max<size_t>(p.nseg, std::max(p.nseg_a, p.nseg_b)) + 1;
         const size_t ent_max = std::max<size_t>(p.total, std::max(p.nent_a, p.nent_b));
-        RS(L.entries, p.total * 4);
         for (int i = 0; i < 2; i++) {
             RS(L.seg_len[i], nseg_max * 4);
             RS(L.seg_start[i], nseg_max * 4);
         }
         RS(L.c_len, nseg_max * 4);
         RS(L.c_start, nseg_max * 4);
-        RS(L.cursor, nseg_max * 4);
-        RS(L.blk, (std::max<size_t>(nseg_max / SCAN_TILE, PLAN_MAX_BLOCKS) + 8) * 8);
+        RS(L.blk, (PLAN_MAX_BLOCKS + 8) * 8);
         if (!L.blk_flag.p) {
             RS(L.blk_flag, (PLAN_MAX_BLOCKS + 8) * 4);
-            CK(cudaMemsetAsync(L.blk_flag.p, 0, (PLAN_MAX_BLOCKS + 8) * 4, stream));
+            CK(cudaMemsetAsync(L.blk_flag.p, 0, (PLAN_MAX_BLOCKS + 8) * 4, L.stream));
             L.epoch = 0;
         }
-        RS(L.info, 64);
-        const size_t task_ub0 = ent_max / 2 + nseg_max / 2 + 1; // round-0 bound, the largest
-        const size_t out_ub0 = ent_max / 2 + nseg_max + 1;      // outputs of round 0 (ceil halves)
+        const size_t task_ub0 = ent_max / 2 + 1;           // round 0, the largest
+        const size_t out_ub0 = ent_max / 2 + nseg_max + 1; // outputs of round 0 (ceil halves)
         RS(L.pp[0], out_ub0 * sizeof(AffPt));
         RS(L.pp[1], (out_ub0 / 2 + nseg_max + 1) * sizeof(AffPt));
         if ((rc = reserve_round(L, task_ub0)) != 0) return rc;
@@ -1107,85 +1267,42 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         RS(L.ents2, (size_t)std::max(p.nent_a, p.nent_b) * 4);
     }
 #undef RS
-    const size_t hb_bytes = (size_t)W * c * sizeof(AffPt);
-    if (h_pts_cap < hb_bytes) {
-        if (h_pts) cudaFreeHost(h_pts);
-        h_pts = nullptr;
-        h_pts_cap = 0;
-        CK(cudaMallocHost(&h_pts, hb_bytes));
-        h_pts_cap = hb_bytes;
-    }
-
-    cudaStream_t st = stream;
-    cudaEventRecord(ev_t0, st);
-    if (timing) cudaEventRecord(ev[0], st);
-    // ---- recode + histogram for every window (context stream)
-    uint32_t *d_len_all = len_all.as<uint32_t>();
-    CK(cudaMemsetAsync(d_len_all, 0, (size_t)W * nb * 4, st));
-    k_recode_count<<<cdiv(n, 128), 128, 0, st>>>(d_scalars, (uint32_t)n, base, rem, W, nb, keys.as<uint32_t>(), d_len_all);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(ev_recode, st));
-    unsigned long long launches = 2;
-    // ---- per lane: bucket offsets, scatter (counting sort by bucket), plan of round 0
-    for (int l = 0; l < NL; l++) {
-        MsmLane &L = lanes[l];
-        const Part &p = part[l];
-        L.launches = 0;
-        CK(cudaStreamWaitEvent(L.stream, ev_recode, 0));
-        const uint32_t *len0 = d_len_all + (size_t)p.w0 * nb;
-        const uint32_t nblk = cdiv(p.nseg, SCAN_TILE);
-        L.prof_used = 0;
-        if (profile) L.prof_begin(PC_SORT);
-        k_scan1<0><<<nblk, SCAN_THREADS, 0, L.stream>>>(len0, p.nseg, L.blk.as<uint64_t>(), L.info.as<uint32_t>());
-        k_scan2<<<1, SCAN_THREADS, 0, L.stream>>>(L.blk.as<uint64_t>(), nblk);
-        k_scan3<0><<<nblk, SCAN_THREADS, 0, L.stream>>>(len0, p.nseg, L.blk.as<uint64_t>(), L.c_start.as<uint32_t>(),
-                                                        L.cursor.as<uint32_t>(), nullptr, L.info.as<uint32_t>());
-        k_scatter<<<cdiv(p.total, 256), 256, 0, L.stream>>>(keys.as<uint32_t>() + (size_t)p.w0 * n, (uint32_t)n, p.total,
-                                                            (uint32_t)p.w0 * nb, L.cursor.as<uint32_t>(),
-                                                            L.entries.as<uint32_t>());
-        if (profile) L.prof_end();
-        L.launches += 4;
-        CK(cudaGetLastError());
-        if (timing && l == 0) cudaEventRecord(L.ev_s[0], L.stream);
-        Tree tree(*this, L);
-        if ((rc = tree.plan0(L.c_start.as<uint32_t>(), len0, L.entries.as<uint32_t>(), p.nseg, true))) return rc;
-    }
-    MsmStats stt;
-    stt.window_bits = c;
-    stt.windows = W;
-    stt.lanes = NL;
+    if (timing) cudaEventRecord(ev[3], st);
     // ---- per lane: accumulate buckets, then the two reduction levels into this lane's slice of hb
     for (int l = 0; l < NL; l++) {
         MsmLane &L = lanes[l];
         const Part &p = part[l];
+        L.launches = 0;
+        L.prof_used = 0;
+        CK(cudaStreamWaitEvent(L.stream, ev_recode, 0));
+        if (timing && l == 0) cudaEventRecord(L.ev_s[0], L.stream);
         Tree tree(*this, L);
-        CK(cudaStreamSynchronize(L.stream)); // the 16-byte read-back that sizes this lane's rounds
-        const uint32_t maxlen = ((uint32_t *)L.h_info)[0];
-        if (l == 0) stt.adds_round0 = ((uint32_t *)L.h_info)[1];
-        const uint32_t *len0 = d_len_all + (size_t)p.w0 * nb;
+        const uint32_t *len0 = d_len_all + bounds[l], *start0 = d_start_all + bounds[l];
+        if ((rc = tree.plan0(start0, len0, entries.as<uint32_t>(), p.nseg, false))) return rc;
+        if (timing && l == 0) CK(cudaMemcpyAsync(L.info_r0.p, L.info.p, 16, cudaMemcpyDeviceToDevice, L.stream));
         L.want_k = timing && l == 0;
         int r_main = 0, r_a = 0, r_b = 0;
-        rc = tree.rounds(d_points, L.entries.as<uint32_t>(), L.c_start.as<uint32_t>(), len0, p.nseg, p.total, maxlen,
-                         L.buckets.as<AffPt>(), &r_main);
+        rc = tree.rounds(d_points, entries.as<uint32_t>(), start0, len0, p.nseg, p.total, p.maxlen, L.buckets.as<AffPt>(),
+                         &r_main);
         if (rc) return rc;
         L.want_k = false;
         if (timing && l == 0) cudaEventRecord(L.ev_s[1], L.stream);
-        // level A: row and column sums of each window's bucket matrix
+        // level A: row and column sums of each virtual window's bucket matrix
         uint32_t *d_start = L.c_start.as<uint32_t>(), *d_len = L.c_len.as<uint32_t>();
-        k_gen_level_a<<<cdiv(p.nent_a, 256), 256, 0, L.stream>>>((uint32_t)p.wn, nb, lm, L.ents2.as<uint32_t>());
-        k_gen_segs_a<<<cdiv(p.nseg_a + 1, 256), 256, 0, L.stream>>>((uint32_t)p.wn, nb, lm, d_start, d_len);
+        k_gen_level_a<<<cdiv(p.nent_a, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, L.ents2.as<uint32_t>());
+        k_gen_segs_a<<<cdiv(p.nseg_a + 1, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, d_start, d_len);
         L.launches += 2;
         if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a, false))) return rc;
         rc = tree.rounds(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,
                          std::max(R, m), L.rc.as<AffPt>(), &r_a);
         if (rc) return rc;
         // level B: per-bit subset sums of the row / column sums
-        k_gen_level_b<<<cdiv(p.nent_b, 256), 256, 0, L.stream>>>((uint32_t)p.wn, lr, lm, L.ents2.as<uint32_t>());
-        k_gen_segs_b<<<cdiv(p.nseg_b + 1, 256), 256, 0, L.stream>>>((uint32_t)p.wn, lr, lm, d_start, d_len);
+        k_gen_level_b<<<cdiv(p.nent_b, 256), 256, 0, L.stream>>>(p.vn, lr, lm, L.ents2.as<uint32_t>());
+        k_gen_segs_b<<<cdiv(p.nseg_b + 1, 256), 256, 0, L.stream>>>(p.vn, lr, lm, d_start, d_len);
         L.launches += 2;
         if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_b, false))) return rc;
         rc = tree.rounds(L.rc.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_b, p.nent_b,
-                         std::max(R >> 1, m), hb.as<AffPt>() + (size_t)p.w0 * c, &r_b);
+                         std::max(R >> 1, m), hb.as<AffPt>() + (size_t)p.v0 * cv, &r_b);
         if (rc) return rc;
         if (timing && l == 0) cudaEventRecord(L.ev_s[2], L.stream);
         CK(cudaEventRecord(L.done, L.stream));
@@ -1198,25 +1315,34 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         launches += lanes[l].launches;
     }
     CK(cudaMemcpyAsync(h_pts, hb.as<AffPt>(), hb_bytes, cudaMemcpyDeviceToHost, st));
-    if (timing) cudaEventRecord(ev[1], st);
+    if (timing) {
+        CK(cudaMemcpyAsync(h_lane, lanes[0].info_r0.p, 16, cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(ev[1], st);
+    }
     cudaEventRecord(ev_t1, st);
     CK(cudaStreamSynchronize(st));
     float ms_dev = 0;
     cudaEventElapsedTime(&ms_dev, ev_t0, ev_t1);
 
-    // ---- host tail: sum_w 2^(off_w) [ sum_{q<c-1} 2^q HB[w][q] + HB[w][c-1] ], one double-and-add pass
+    // ---- host tail.  Virtual window v holds buckets of digit values dbase_v + b + 1 (b local) at bit offset
+    // off_v: sum_b (dbase_v + b + 1) B_b = sum_q 2^q H[v][q] + (dbase_v + 1) S[v]; one double-and-add pass
+    // over all positions.  (Separate sets: off_v = the window's offset, dbase_v = 0.  Shared set: off_v = 0.)
     {
         const AffPt *hp = (const AffPt *)h_pts;
-        std::vector<std::vector<int>> at(W * c + 1);
-        for (int w = 0; w < W; w++) {
-            const int off = w * base + std::min(w, rem);
-            for (int q = 0; q < c - 1; q++) at[off + q].push_back(w * c + q);
-            at[off].push_back(w * c + c - 1);
+        const int npos = uniform ? c + 1 : 233 + c + 1;
+        std::vector<std::vector<uint32_t>> at(npos + 1);
+        for (uint32_t v = 0; v < V; v++) {
+            const int off = uniform ? 0 : (int)v * base + std::min((int)v, rem);
+            const uint32_t dbase = uniform ? v * nbv : 0;
+            for (int q = 0; q < cv - 1; q++) at[off + q].push_back(v * cv + q);
+            const uint32_t ws = dbase + 1;
+            for (int t = 0; t < 32; t++)
+                if ((ws >> t) & 1) at[off + t].push_back(v * cv + cv - 1);
         }
         host::LdPt acc = host::ld_inf();
-        for (int pos = W * c; pos >= 0; pos--) {
+        for (int pos = npos; pos >= 0; pos--) {
             acc = host::ld_dbl(acc);
-            for (int idx : at[pos]) acc = host::ld_add_affine(acc, hp[idx]);
+            for (uint32_t idx : at[pos]) acc = host::ld_add_affine(acc, hp[idx]);
         }
         *h_result = host::ld_to_affine(acc);
     }
@@ -1237,13 +1363,12 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         cudaEventRecord(ev[2], st);
         cudaEventSynchronize(ev[2]);
         MsmLane &L0 = lanes[0];
-        float t_all = 0;
-        cudaEventElapsedTime(&t_all, ev[0], ev[1]);
-        cudaEventElapsedTime(&stt.ms_recode_sort, ev[0], L0.ev_s[0]);
+        cudaEventElapsedTime(&stt.ms_recode_sort, ev[0], ev[3]);
         cudaEventElapsedTime(&stt.ms_accumulate, L0.ev_s[0], L0.ev_s[1]);
         cudaEventElapsedTime(&stt.ms_reduce, L0.ev_s[1], L0.ev_s[2]);
         cudaEventElapsedTime(&stt.ms_tail, ev[1], ev[2]);
         if (stt.rounds_main > 0) cudaEventElapsedTime(&stt.ms_pass2_round0, L0.ev_k[0], L0.ev_k[1]);
+        stt.adds_round0 = ((const uint32_t *)h_lane)[1]; // info of lane 0's first plan
     }
     last = stt;
     return 0;

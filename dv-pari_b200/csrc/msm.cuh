@@ -18,7 +18,7 @@ struct DevBuf {
 };
 
 struct MsmStats {
-    int window_bits = 0, windows = 0, rounds_main = 0, rounds_a = 0, rounds_b = 0, lanes = 0;
+    int window_bits = 0, windows = 0, rounds_main = 0, rounds_a = 0, rounds_b = 0, lanes = 0, tables = 0;
     unsigned long long launches = 0; // kernels launched by the last msm
     float ms_recode_sort = 0, ms_accumulate = 0, ms_reduce = 0, ms_tail = 0;
     // the dominant kernel: pass 2 of round 0 of the bucket accumulation (one launch)
@@ -35,7 +35,7 @@ enum { PC_SORT = 0, PC_PLAN, PC_PASS1, PC_BINV_UP, PC_BINV_DIRECT, PC_BINV_DOWN,
 struct MsmLane {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    DevBuf entries, seg_len[2], seg_start[2], c_len, c_start, cursor, blk, blk_flag, info, pp[2], prefix, desc,
+    DevBuf seg_len[2], seg_start[2], c_len, c_start, blk, blk_flag, info, info_r0, pp[2], prefix, desc,
         thr_total, thr_inv, lvl_pre[2], lvl_tot[2], lvl_inv[2], buckets, rc, ents2;
     void *h_info = nullptr; // pinned, 64 bytes
     unsigned long long launches = 0;
@@ -56,10 +56,20 @@ struct MsmLane {
     void destroy();
 };
 
+// Precomputed multiples of a resident point vector: T[j][i] = 2^(off_j) P_i, j < W (off_j = bit offset of window j),
+// T[j] at points + j * stride.
+// With them every window shares ONE bucket set (see MsmEngine::run), so wider windows pay off.
+struct MsmTable {
+    int W = 0;
+    size_t stride = 0; // points per window table (the slot size)
+    size_t offset = 0; // first point of the range this MSM runs over
+};
+
 struct MsmEngine {
     cudaStream_t stream = nullptr; // the context's stream: recode, final read-back
     std::vector<MsmLane> lanes;
-    DevBuf keys, len_all, hb, msqr_tabs, mg_table;
+    DevBuf keys, entries, len_all, start_all, cursor_all, scan_blk, lane_info, hb, msqr_tabs, mg_table;
+    void *h_lane = nullptr; // pinned: per-lane (entries, longest bucket)
     void *h_pts = nullptr; // pinned, receives the per-bit partial sums
     size_t h_pts_cap = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}, ev_recode = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
@@ -77,13 +87,17 @@ struct MsmEngine {
     void destroy();
     // sum_i scalars[i] * points[i]; scalars are device pointers to n x 8 x u32 Montgomery limbs.
     // Result: affine E[r] point (or infinity) on the host.  Returns 0 or a DVP_ERR_* code.
-    int run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, AffPt *h_result);
+    // With `tab`, d_points is the base of the tables and the MSM runs over points [tab->offset, tab->offset + n).
+    int run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, AffPt *h_result, const MsmTable *tab = nullptr);
+    // d_tab[j * n + i] = 2^(off_j) d_points[i] for j < W (d_tab holds W n points; j = 0 is a copy)
+    int build_table(const AffPt *d_points, size_t n, int W, AffPt *d_tab);
     // d_out[i] = scalars[i] * G (batched fixed-base multiplication of the generator), all on the device
     int mulgen(const uint32_t *d_scalars, size_t n, AffPt *d_out);
     int reserve_round(MsmLane &L, size_t task_ub);
 };
 
 int choose_window_bits(size_t n);
+int choose_table_windows(size_t n);
 int latency_probe(MsmEngine &E, int mode, int iters, float *us_per_op);
 
 } // namespace dvp

@@ -830,7 +830,8 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     if (k != r->dev.k) return DVP_ERR_BAD_ARG;                    // assert_eq!(inst.num_public_inputs, ..) proving.rs:361
     if (1 + k + npriv != r->nwires) return DVP_ERR_LENGTH_MISMATCH; // msm(assignment, g_m) length check, curve.rs:142
     CKP(cudaSetDevice(ctx->device));
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[8], ev_h2d;
+    cudaEventCreate(&ev_h2d);
     for (auto &e : ev) cudaEventCreate(&e);
     cudaEventRecord(ev[0], st);
     fr *V = p->vec.as<fr>();
@@ -842,6 +843,7 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     CKP(cudaMemcpyAsync(w, &one, 32, cudaMemcpyHostToDevice, st));
     if (k) CKP(cudaMemcpyAsync(w + 1, pub, k * 32, cudaMemcpyHostToDevice, st));
     if (npriv) CKP(cudaMemcpyAsync(w + 1 + k, priv, npriv * 32, cudaMemcpyHostToDevice, st));
+    cudaEventRecord(ev_h2d, st);
     int64_t bad = -1;
     int rc = r1cs_eval_device(r, d, w, a, b, c, iv, &bad);
     if (rc) return rc;
@@ -854,7 +856,7 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     dvp_shard_range(n, R, W, &qlo, &qhi);
     dvp_shard_range(4 * n, R, W, &klo, &khi);
     AffPt part;
-    if ((rc = ctx->msm.run(ctx->slots[p->slot_gm].buf.as<AffPt>(), (const uint32_t *)(w + wlo), whi - wlo, &part))) return rc;
+    if ((rc = slot_msm(ctx, p->slot_gm, 0, (const uint32_t *)(w + wlo), whi - wlo, &part))) return rc;
     if ((rc = comm_fold_points(ctx, part, &msm_gm))) return rc;
     cudaEventRecord(ev[2], st);
     // extend a, b, c to D' (i' in closed form), proving.rs:475-482
@@ -879,7 +881,7 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     k_quotient<<<cdivp(n, 128), 128, 0, st>>>(a2, b2, c2, i2, d->z_vals2inv.as<fr>(), (uint32_t)n, q);
     CKP(cudaGetLastError());
     cudaEventRecord(ev[3], st);
-    if ((rc = ctx->msm.run(ctx->slots[p->slot_gq].buf.as<AffPt>(), (const uint32_t *)(q + qlo), qhi - qlo, &part))) return rc;
+    if ((rc = slot_msm(ctx, p->slot_gq, 0, (const uint32_t *)(q + qlo), qhi - qlo, &part))) return rc;
     if ((rc = comm_fold_points(ctx, part, &msm_q))) return rc;
     cudaEventRecord(ev[4], st);
     const AffPt commit = host::aff_add(msm_q, msm_gm); // proving.rs:515
@@ -926,7 +928,7 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
         CKP(cudaMemcpyAsync(stages + 8 * n * 4, q, 5 * n * 32, cudaMemcpyDeviceToHost, st));
         CKP(cudaStreamSynchronize(st));
     }
-    if ((rc = ctx->msm.run(ctx->slots[p->slot_gk].buf.as<AffPt>(), (const uint32_t *)(ks + klo), khi - klo, &part))) return rc;
+    if ((rc = slot_msm(ctx, p->slot_gk, 0, (const uint32_t *)(ks + klo), khi - klo, &part))) return rc;
     if ((rc = comm_fold_points(ctx, part, &kzg))) return rc;
     cudaEventRecord(ev[6], st);
     cudaEventSynchronize(ev[6]);
@@ -934,6 +936,9 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     fr_to_le29_host(proof + 60, a0);
     fr_to_le29_host(proof + 89, b0);
     for (int i = 0; i < 6; i++) cudaEventElapsedTime(&p->ms[i], ev[i], ev[i + 1]);
+    cudaEventElapsedTime(&p->ms[6], ev[0], ev_h2d); // witness upload, part of ms[0]
+    p->ms[0] -= p->ms[6];
+    cudaEventDestroy(ev_h2d);
     for (auto &e : ev) cudaEventDestroy(e);
     return DVP_OK;
 }
@@ -949,10 +954,10 @@ int dvp_prove_stages(dvp_prover *p, const uint64_t *public_mont, size_t k, const
     if (!p || !proof118 || !stages || (!public_mont && k) || (!private_mont && npriv)) return DVP_ERR_BAD_ARG;
     return prove_impl(p, public_mont, k, private_mont, npriv, proof118, stages);
 }
-// stage times of the last prove in ms: r1cs, msm g_m, extend+quotient, msm g_q, challenge+K scalars, msm g_k
-int dvp_prove_last_times(dvp_prover *p, float ms[6]) {
+// stage times of the last prove in ms: r1cs, msm g_m, extend+quotient, msm g_q, challenge+K scalars, msm g_k, witness upload
+int dvp_prove_last_times(dvp_prover *p, float ms[7]) {
     if (!p || !ms) return DVP_ERR_BAD_ARG;
-    for (int i = 0; i < 6; i++) ms[i] = p->ms[i];
+    for (int i = 0; i < 7; i++) ms[i] = p->ms[i];
     return DVP_OK;
 }
 }

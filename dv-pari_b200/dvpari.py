@@ -35,7 +35,7 @@ class MsmStats(C.Structure):
     _fields_ = [("window_bits", C.c_int), ("windows", C.c_int), ("rounds_main", C.c_int), ("rounds_a", C.c_int),
                 ("rounds_b", C.c_int), ("launches", C.c_ulonglong), ("ms_recode_sort", C.c_float),
                 ("ms_accumulate", C.c_float), ("ms_reduce", C.c_float), ("ms_tail", C.c_float),
-                ("ms_pass2_round0", C.c_float), ("adds_round0", C.c_ulonglong), ("ms_device", C.c_float), ("lanes", C.c_int)]
+                ("ms_pass2_round0", C.c_float), ("adds_round0", C.c_ulonglong), ("ms_device", C.c_float), ("lanes", C.c_int), ("tables", C.c_int)]
 
 
 def build(force=False):
@@ -173,6 +173,10 @@ class Context:
         rc = fn(self._h, slot, _ptr(a), a.size // 30, C.byref(bad))
         if rc != OK:
             raise DvpError(rc, f"point {bad.value}")
+
+    def srs_append(self, slot, pts30):
+        """g_k_0 | g_k_1 | g_k_2 concatenation (proving.rs:666-673)."""
+        self.srs_load(slot, pts30, append=True)
 
     def srs_random(self, slot, n, seed):
         """n uniformly random group elements, deterministic in (seed, index)."""
@@ -467,9 +471,10 @@ class Prover:
         return (proof.tobytes(), st) if want_stages else proof.tobytes()
 
     def last_times(self):
-        ms = np.zeros(6, dtype=np.float32)
+        ms = np.zeros(8, dtype=np.float32)
         _ck(lib().dvp_prove_last_times(self._h, _ptr(ms)))
-        return dict(zip(["r1cs", "msm_gm", "extend_quotient", "msm_gq", "challenge_kscalars", "msm_gk"], ms.tolist()))
+        return dict(zip(["r1cs", "msm_gm", "extend_quotient", "msm_gq", "challenge_kscalars", "msm_gk", "witness_h2d"],
+                        ms.tolist()))
 
 
 def proof_to_bits(proof118):

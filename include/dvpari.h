@@ -47,6 +47,7 @@ typedef struct dvp_msm_stats {
     unsigned long long adds_round0;   /* affine additions that launch finished */
     float ms_device;                  /* scalars in HBM -> partial sums on the host, CUDA events on the context stream */
     int lanes;                        /* concurrent window groups used */
+    int tables;                       /* 1 if the MSM ran on the slot's precomputed window multiples */
 } dvp_msm_stats;
 
 const char *dvp_strerror(int code);
@@ -56,7 +57,8 @@ int dvp_abi_version(void);
 int dvp_ctx_create(int device, dvp_ctx **out);
 void dvp_ctx_destroy(dvp_ctx *ctx);
 /* knobs: "msm_window_bits" (0 = automatic), "msm_lanes" (0 = automatic: concurrent window groups),
- * "pass2_minb" (1..3), "timing" (0/1), "msm_profile" (0/1).  Unknown name -> DVP_ERR_BAD_ARG. */
+ * "pass2_minb" (1..3), "timing" (0/1), "msm_profile" (0/1), "msm_tables" (0/1: precomputed window multiples of
+ * large SRS slots, W x the slot's memory, built on first use), "msm_tables_min" (smallest such slot), "binv_direct".  Unknown name -> DVP_ERR_BAD_ARG. */
 int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value);
 
 /*
@@ -185,8 +187,9 @@ int dvp_prove(dvp_prover *p, const uint64_t *public_mont, size_t k, const uint64
  * stages = 13 n x 4 u64: a b c i a' b' c' i' q k_a k_b k_r(2n). */
 int dvp_prove_stages(dvp_prover *p, const uint64_t *public_mont, size_t k, const uint64_t *private_mont, size_t npriv,
                      uint8_t proof118[118], uint64_t *stages);
-/* ms per stage of the last prove: r1cs, msm g_m, extend+quotient, msm g_q, challenge+K scalars, msm g_k */
-int dvp_prove_last_times(dvp_prover *p, float ms[6]);
+/* ms per stage of the last prove: r1cs rows, msm g_m, extend+quotient, msm g_q, challenge+K scalars, msm g_k,
+ * witness upload (host -> device) */
+int dvp_prove_last_times(dvp_prover *p, float ms[7]);
 
 /* Single-warp latency of a dependent chain, microseconds per op: mode 0 gf inversion by squarings,
  * 1 table-driven gf inversion, 2 gf multiplication. */

@@ -136,3 +136,48 @@ def test_msm_2_20_closed_form(ctx, oracle):
     want = O.pt_encode(O.pt_add(O.pt_mul(a, s0), O.pt_mul(q, s1)))
     assert ctx.multi_scalar_mul(sc, 0) == want
     ctx.srs_free(0)
+
+
+def test_msm_with_precomputed_tables(ctx, oracle):
+    """The shared-bucket-set layout over the slot's window multiples T[j] = 2^(j c) P gives the same group element:
+    forced on small slots, with degenerate points, sub-ranges that still use the tables and ones that do not."""
+    O = oracle
+    rnd = random.Random(21)
+    G = O.generator()
+    ctx.set("msm_tables_min", 32)
+    try:
+        for n in (40, 700, 5000):
+            base = [O.pt_mul(G, rnd.randrange(1, P)) for _ in range(n - 8)]
+            pts = base + [base[0], O.pt_neg(base[1]), O.pt(), base[2], base[2], O.pt(), O.pt_neg(base[0]), base[3]]
+            arr = O.points_to_array(pts)
+            ctx.srs_load(2, O.encode_batch(arr))
+            ks = [rnd.randrange(P) for _ in range(n)]
+            ks[0], ks[1], ks[2], ks[3] = 0, 1, P - 1, (1 << 231) + 12345
+            got = ctx.multi_scalar_mul(dvpari.fr_to_mont(ks), 2)
+            assert ctx.msm_stats()["tables"] == 1
+            assert got == _oracle_msm(O, ks, arr), n
+            # a sub-range covering most of the slot keeps the tables, a short one falls back to the plain layout
+            off, m = n // 5, n - n // 5 - 3
+            got = ctx.multi_scalar_mul(dvpari.fr_to_mont(ks[:m]), 2, offset=off)
+            assert ctx.msm_stats()["tables"] == 1
+            assert got == _oracle_msm(O, ks[:m], O.points_to_array(pts[off:off + m]))
+            got = ctx.multi_scalar_mul(dvpari.fr_to_mont(ks[:7]), 2, offset=3)
+            assert ctx.msm_stats()["tables"] == 0
+            assert got == _oracle_msm(O, ks[:7], O.points_to_array(pts[3:10]))
+        # every point = G and equal scalars: one bucket carries everything, the tangent case in every round
+        n = 3000
+        enc = np.tile(np.frombuffer(O.pt_encode(G), dtype=np.uint8), (n, 1))
+        ctx.srs_load(2, enc)
+        got = ctx.multi_scalar_mul(dvpari.fr_to_mont([5] * n), 2)
+        assert got == O.pt_encode(O.pt_mul(G, 5 * n % P))
+        # appending to the slot drops the tables
+        ctx.srs_append(2, enc[:10])
+        got = ctx.multi_scalar_mul(dvpari.fr_to_mont([7] * (n + 10)), 2)
+        assert got == O.pt_encode(O.pt_mul(G, 7 * (n + 10) % P))
+        ctx.set("msm_tables", 0)
+        got = ctx.multi_scalar_mul(dvpari.fr_to_mont([7] * (n + 10)), 2)
+        assert ctx.msm_stats()["tables"] == 0 and got == O.pt_encode(O.pt_mul(G, 7 * (n + 10) % P))
+    finally:
+        ctx.set("msm_tables", 1)
+        ctx.set("msm_tables_min", 1 << 15)
+        ctx.srs_free(2)
