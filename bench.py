@@ -31,7 +31,10 @@ METRIC = "sect233k1 MSM points/s"
 UNIT = "points/s"
 # static facts about the dominant kernel (k_pass2, one batched affine addition per task), see DESIGN.md
 PASS2_BYTES_PER_ADD = 128 + 32 + 16 + 64  # two points in, prefix product, task descriptor, one point out
-PASS2_ALU_INSTR_PER_ADD = 3184             # LOP3+SHF+ISETP+SEL thread-instructions per addition (cuobjdump -sass count of k_pass2)
+# ALU-pipe issue slots per addition in k_pass2 (scripts/sass_count.py): 4 calls of the out-of-line multiplier
+# (434 IMAD.WIDE + 760 LOP3/SHF each) + the loop body (250 ALU).  IMAD.WIDE holds the FMA pipe for 4 cycles AND the
+# ALU pipe for 2 (profiles/README.md, pipe probes), so it counts as one ALU-pipe slot as well.
+PASS2_ALU_INSTR_PER_ADD = (4 * 760 + 250) + 4 * 434
 ALU_PIPE_PEAK = 1.84e13                    # measured LOP3 thread-instr/s on this pool's B200 (profiles/r1_pipe_rates.json)
 
 
@@ -315,6 +318,7 @@ def main():
     # (single lane here so that no other stream shares the GPU with the kernel being timed)
     ctx.set("timing", 1)
     ctx.set("msm_lanes", 1)
+    ctx.multi_scalar_mul_device(d_sc, n, 0)  # sizes the single lane's scratch
     ctx.multi_scalar_mul_device(d_sc, n, 0)
     st = ctx.msm_stats()
     ctx.set("timing", 0)
@@ -339,6 +343,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"msm 2^{args.lg} points per GPU, sect233k1, uniform Fr scalars, SRS resident in HBM",
                        "window_bits": st["window_bits"], "windows": st["windows"],
+                       "precomputed_tables": bool(st["tables"]),
                        "rounds": [st["rounds_main"], st["rounds_a"], st["rounds_b"]],
                        "l2": "per-step working set (sort keys, ping-pong point buffers, prefix products: >1 GB at 2^20) exceeds the 126 MB L2",
                        "parallelism": f"point-range sharding x{world}, NCCL all-gather of 64-byte partial sums, fold on every rank" if world > 1 else "single GPU",
@@ -347,13 +352,14 @@ def main():
             "e2e": {"value": world * n * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": n * 32,
                     "d2h_bytes_per_step": 30 + st["windows"] * st["window_bits"] * 64, "ms_per_step": 1e3 * dt_e2e / args.steps},
             "gpu_launches": int(st["launches"]) * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "k_pass2<indexed,16> (round 0 of the bucket accumulation)",
+            "roofline": {"bound": "hbm", "kernel": "k_pass2<16,2> (round 0 of the bucket accumulation)",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": 1.826e9 if args.lg == 20 else None, "peak_source": which,
                          "launch_ms": k_ms, "adds_per_launch": k_adds, "bytes_per_add": PASS2_BYTES_PER_ADD,
                          "note": "integer-issue bound, not HBM bound: see int_issue"},
             "int_issue": {"achieved": alu, "peak": ALU_PIPE_PEAK, "unit": "ALU-pipe thread-instr/s", "frac": alu / ALU_PIPE_PEAK,
-                          "instr_per_add": PASS2_ALU_INSTR_PER_ADD, "peak_source": "measured LOP3 issue rate, profiles/r1_pipe_rates.json"},
+                          "instr_per_add": PASS2_ALU_INSTR_PER_ADD,
+                          "peak_source": "measured LOP3 issue rate, profiles/r1_pipe_rates.json; IMAD.WIDE counted as one ALU-pipe slot (profiles/README.md)"},
             "cpu_baseline": {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"2^{lg_s} of the same SRS points, oracle k233_msm (per-point wNAF scalar mul + sum, curve.rs:141-158), "
                                        f"{cdt:.2f} s, result equal to the GPU's"},
