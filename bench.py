@@ -144,7 +144,10 @@ def run_reference(args):
     return 0
 
 
-FR_MUL_PEAK = 4.5e10  # measured fr_mul/s of the CIOS multiplier (profiles/r1_pipe_rates.json), the ECFFT's bound
+# ECFFT butterfly = 339 IMAD.WIDE (cuobjdump of k_extend_level: two 29-bit-limb dot products, fr29.cuh); IMAD.WIDE
+# issues once per 4 cycles per SMSP: 9.2e12 thread-instr/s measured (scripts/pipebench2.cu, profiles/README.md)
+EXT_WIDE_PER_BUTTERFLY = 339
+IMAD_WIDE_PEAK = 9.2e12
 
 
 def prove_section(ctx, args, rank, world, sync_all, timed):
@@ -214,9 +217,10 @@ def prove_section(ctx, args, rank, world, sync_all, timed):
         "msm_points_per_proof": circ["nwires"] + 5 * n,
         "msm_points_per_s": (circ["nwires"] + 5 * n) / (1e-3 * (stages["msm_gm"] + stages["msm_gq"] + stages["msm_gk"])),
         "ecfft_extend": {"polys": 3, "n": n, "ms": ext_ms, "mulmods_per_s": mulmods / (ext_ms * 1e-3),
-                         "int_frac": mulmods / (ext_ms * 1e-3) / FR_MUL_PEAK,
+                         "imad_wide_per_s": (mulmods / 4) * EXT_WIDE_PER_BUTTERFLY / (ext_ms * 1e-3),
+                         "int_frac": (mulmods / 4) * EXT_WIDE_PER_BUTTERFLY / (ext_ms * 1e-3) / IMAD_WIDE_PEAK,
                          "GBps": ext_bytes / (ext_ms * 1e-3) / 1e9, "hbm_frac": ext_bytes / (ext_ms * 1e-3) / 1e9 / hbm_peak,
-                         "bound": "integer (Montgomery multiplier), see DESIGN.md 4.3"},
+                         "bound": "integer (IMAD.WIDE issue), see DESIGN.md 4.3"},
         "r1cs_rows": {"ms": stages["r1cs"], "terms_per_s": terms / (stages["r1cs"] * 1e-3),
                       "GBps": (terms * 72 + 4 * n * 32) / (stages["r1cs"] * 1e-3) / 1e9},
         "srs": "random group elements (timing only)", "data": "synthetic SP1-shaped R1CS, dv-pari_b200/synth.py",

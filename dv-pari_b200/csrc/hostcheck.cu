@@ -5,6 +5,7 @@
 #include <cstring>
 #include "../../include/dvpari.h"
 #include "fr.cuh"
+#include "fr29.cuh"
 #include "host_gf.hpp"
 #include "k233_codec.cuh"
 
@@ -98,6 +99,17 @@ extern "C" int dvp_hostcheck_op(int op, const void *a_, const void *b_, void *ou
             memcpy(x.v, a + i * 32, 32);
             fr r = fr_inv(x);
             memcpy(out + i * 32, r.v, 32);
+            break;
+        }
+        case 15: { // ECFFT butterfly row on 29-bit limbs: a = (m0, x0), b = (m1, x1), 64 bytes each -> m0 x0 + m1 x1
+            fr m0, x0, m1, x1;
+            memcpy(m0.v, a + i * 64, 32);
+            memcpy(x0.v, a + i * 64 + 32, 32);
+            memcpy(m1.v, b + i * 64, 32);
+            memcpy(x1.v, b + i * 64 + 32, 32);
+            const fr29 r = fr29_dot2(fr29_prescale(m0), fr29_from_fr(x0), fr29_prescale(m1), fr29_from_fr(x1));
+            const fr o = fr_from_fr29(r);
+            memcpy(out + i * 32, o.v, 32);
             break;
         }
         default:

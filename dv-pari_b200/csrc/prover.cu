@@ -15,6 +15,7 @@
 #include "../../include/dvpari.h"
 #include "ctx.cuh"
 #include "fr.cuh"
+#include "fr29.cuh"
 #include "host_gf.hpp"
 #include "transcript_host.hpp"
 
@@ -157,6 +158,24 @@ __global__ void k_fr_inv_each(fr *__restrict__ v, uint32_t n) {
 // ------------------------------------------------------------------------------------------------
 // ECFFT extend: in-place 2x2 butterflies, level k has sub-problems of size m = n >> k
 // ------------------------------------------------------------------------------------------------
+// The matrices are stored as 29-bit limbs, pre-scaled by 2^-24 (fr29.cuh): a butterfly is two dot products with one
+// Montgomery reduction each, every partial product an IMAD.WIDE with its 64-bit accumulate.
+__global__ void k_mats_to29(fr *__restrict__ mats, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const fr29 r = fr29_prescale(fr_load(&mats[i]));
+    fr o;
+#pragma unroll
+    for (int k = 0; k < 8; k++) o.v[k] = r.l[k];
+    fr_store(&mats[i], o);
+}
+__device__ __forceinline__ fr29 fr29_load(const fr *p) {
+    const fr t = fr_load(p);
+    fr29 r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.l[k] = t.v[k];
+    return r;
+}
 __global__ void __launch_bounds__(256)
     k_extend_level(fr *__restrict__ data, uint32_t n, uint32_t h, const fr *__restrict__ mats, int npoly,
                    size_t stride) {
@@ -164,13 +183,13 @@ __global__ void __launch_bounds__(256)
     if (g >= (n >> 1)) return;
     const uint32_t j = g % h, s = g / h;
     const uint32_t i0 = s * 2 * h + j, i1 = i0 + h;
-    const fr m0 = fr_load(&mats[4 * j]), m1 = fr_load(&mats[4 * j + 1]);
-    const fr m2 = fr_load(&mats[4 * j + 2]), m3 = fr_load(&mats[4 * j + 3]);
+    const fr29 m0 = fr29_load(&mats[4 * j]), m1 = fr29_load(&mats[4 * j + 1]);
+    const fr29 m2 = fr29_load(&mats[4 * j + 2]), m3 = fr29_load(&mats[4 * j + 3]);
     for (int p = 0; p < npoly; p++) {
         fr *d = data + (size_t)p * stride;
-        const fr x0 = fr_load(&d[i0]), x1 = fr_load(&d[i1]);
-        fr_store(&d[i0], fr_add(fr_mul(m0, x0), fr_mul(m1, x1)));
-        fr_store(&d[i1], fr_add(fr_mul(m2, x0), fr_mul(m3, x1)));
+        const fr29 x0 = fr29_from_fr(fr_load(&d[i0])), x1 = fr29_from_fr(fr_load(&d[i1]));
+        fr_store(&d[i0], fr_from_fr29(fr29_dot2(m0, x0, m1, x1)));
+        fr_store(&d[i1], fr_from_fr29(fr29_dot2(m2, x0, m3, x1)));
     }
 }
 
@@ -498,6 +517,8 @@ int dvp_domain_create(dvp_ctx *ctx, unsigned log2_2n, dvp_domain **out) {
         while ((1u << e) < h) e++;
         k_dom_matrices<<<cdivp(h, 64), 64, 0, st>>>(layers[k]->as<fr>(), h, e, d->x0[k], d->dec[k].as<fr>(),
                                                    d->rec[k].as<fr>());
+        k_mats_to29<<<cdivp(4 * h, 128), 128, 0, st>>>(d->dec[k].as<fr>(), 4 * h);
+        k_mats_to29<<<cdivp(4 * h, 128), 128, 0, st>>>(d->rec[k].as<fr>(), 4 * h);
     }
     if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return fail(DVP_ERR_CUDA);
     // prover precomputes: bar_wts = 1/Z'_D(d_i), z_vals2inv = 1/Z_D(d'_i)  (proving.rs:225-325)

@@ -113,3 +113,25 @@ def test_codec_matches_oracle(oracle):
             nvalid += 1
             assert O.pt_xy(pt_from_row(O, row[:64].copy().view(np.uint32))) == O.pt_xy(q)
     assert 0 < nvalid < 40
+
+
+def test_fr29_butterfly_row():
+    """fr29_dot2 (29-bit limbs, one reduction for two products, pre-scaled matrix entries) gives exactly
+    m0 x0 + m1 x1 in ark's Montgomery form -- the row of an ECFFT butterfly (proving.rs:410-422 via ecfft extend)."""
+    rnd = random.Random(29)
+    edge = [0, 1, P - 1, P - 2, 1 << 231, (1 << 231) - 1, (1 << 203) - 1, (1 << 29) - 1, 1 << 29]
+    vals = edge + [rnd.randrange(P) for _ in range(400)]
+    n = len(vals)
+    m0, x0 = vals, vals[5:] + vals[:5]
+    m1, x1 = vals[11:] + vals[:11], vals[2:] + vals[:2]
+    # worst case for the column sums: every operand p - 1
+    m0, x0, m1, x1 = [P - 1] + m0, [P - 1] + x0, [P - 1] + m1, [P - 1] + x1
+    A = np.concatenate([dvpari.fr_to_mont(m0), dvpari.fr_to_mont(x0)], axis=1).view(np.uint32).reshape(-1, 16)
+    B = np.concatenate([dvpari.fr_to_mont(m1), dvpari.fr_to_mont(x1)], axis=1).view(np.uint32).reshape(-1, 16)
+    out = np.zeros((n + 1, 8), dtype=np.uint32)
+    dvpari._ck(dvpari.lib().dvp_hostcheck_op(15, dvpari._ptr(A), dvpari._ptr(B), dvpari._ptr(out), n + 1))
+    got = dvpari.fr_from_mont(out.view(np.uint64).reshape(-1, 4))
+    assert got == [(a * b + c * d) % P for a, b, c, d in zip(m0, x0, m1, x1)]
+    # and the limbs are canonical (fully reduced): the bytes equal the canonical Montgomery encoding
+    want = dvpari.fr_to_mont([(a * b + c * d) % P for a, b, c, d in zip(m0, x0, m1, x1)])
+    assert out.view(np.uint64).reshape(-1, 4).tobytes() == want.tobytes()
