@@ -8,6 +8,7 @@
 #include "fr29.cuh"
 #include "host_gf.hpp"
 #include "k233_codec.cuh"
+#include "k233_ld.cuh"
 
 using namespace dvp;
 
@@ -110,6 +111,33 @@ extern "C" int dvp_hostcheck_op(int op, const void *a_, const void *b_, void *ou
             const fr29 r = fr29_dot2(fr29_prescale(m0), fr29_from_fr(x0), fr29_prescale(m1), fr29_from_fr(x1));
             const fr o = fr_from_fr29(r);
             memcpy(out + i * 32, o.v, 32);
+            break;
+        }
+        case 16: { // complete LD addition on projective operands: (2a) + (b + a) = 3a + b
+            AffPt p, q;
+            memcpy(&p, a + i * 64, 64);
+            memcpy(&q, b + i * 64, 64);
+            const LdPt P1 = ld_double(ld_from_affine(p));
+            const LdPt P2 = ld_add(ld_from_affine(q), ld_from_affine(p));
+            const LdPt S = ld_add(P1, P2);
+            const AffPt r = ld_to_affine_with(S, gf_inv(S.Z));
+            memcpy(out + i * 64, &r, 64);
+            break;
+        }
+        case 17: { // LD addition of two projective copies of the same operands: (a + b) + (b + a) and (a + b) - (b + a)
+            AffPt p, q;
+            memcpy(&p, a + i * 64, 64);
+            memcpy(&q, b + i * 64, 64);
+            const LdPt P1 = ld_add(ld_from_affine(p), ld_from_affine(q));
+            LdPt P2 = ld_add(ld_double(ld_from_affine(q)), ld_add(ld_from_affine(p), ld_from_affine(pt_neg(q)))); // = a + b, other Z
+            const LdPt S = ld_add(P1, P2); // doubling branch
+            const AffPt r = ld_to_affine_with(S, gf_inv(S.Z));
+            memcpy(out + i * 128, &r, 64);
+            // negate P2: y -> y + x, in LD: Y -> Y + X Z
+            P2.Y = gf_add(P2.Y, gf_mul(P2.X, P2.Z));
+            const LdPt D = ld_add(P1, P2); // opposite branch -> infinity
+            const AffPt r2 = ld_to_affine_with(D, gf_inv(D.Z));
+            memcpy(out + i * 128 + 64, &r2, 64);
             break;
         }
         default:

@@ -22,6 +22,7 @@
 #include "../../include/dvpari.h"
 #include "fr.cuh"
 #include "host_gf.hpp"
+#include "k233_ld.cuh"
 
 namespace dvp {
 
@@ -720,6 +721,72 @@ __global__ void k_gen_segs_b(uint32_t W, uint32_t lr, uint32_t lm, uint32_t *__r
 }
 
 // ------------------------------------------------------------------------------------------------
+// reduction levels as inversion-free trees: one block sums one segment (len <= 2 * blockDim points named by an
+// index list) in Lopez-Dahab coordinates through shared memory; only the last level converts back to affine
+// (one table-driven inversion per segment).  Two launches replace ~14 latency-bound affine rounds.
+// ------------------------------------------------------------------------------------------------
+struct GfMulCall {
+    __device__ __forceinline__ gf operator()(const gf &a, const gf &b) const { return gf_mul_call(a, b); }
+};
+__device__ __forceinline__ void ld_store(LdPt *p, const LdPt &v) {
+    gf_store(&p->X, v.X);
+    gf_store(&p->Y, v.Y);
+    gf_store(&p->Z, v.Z);
+}
+__device__ __forceinline__ LdPt ld_load(const LdPt *p) {
+    LdPt r;
+    r.X = gf_load(&p->X);
+    r.Y = gf_load(&p->Y);
+    r.Z = gf_load(&p->Z);
+    return r;
+}
+template <bool SRC_LD, bool OUT_AFFINE>
+__global__ void __launch_bounds__(256)
+    k_ld_tree(const void *__restrict__ src, const uint32_t *__restrict__ ent, const uint32_t *__restrict__ seg_start,
+              const uint32_t *__restrict__ seg_len, void *__restrict__ dst, const gf *__restrict__ tabs) {
+    extern __shared__ __align__(16) unsigned char sh_raw[];
+    LdPt *sh = reinterpret_cast<LdPt *>(sh_raw);
+    const uint32_t s = blockIdx.x, t = threadIdx.x;
+    const uint32_t start = seg_start[s], len = seg_len[s];
+    auto fetch = [&](uint32_t pos) -> LdPt {
+        const uint32_t e = ent[start + pos];
+        if (SRC_LD) return ld_load(reinterpret_cast<const LdPt *>(src) + e);
+        return ld_from_affine(pt_load(reinterpret_cast<const AffPt *>(src) + e));
+    };
+    LdPt acc = ld_infinity();
+    if (2 * t < len) {
+        acc = fetch(2 * t);
+        if (2 * t + 1 < len) acc = ld_add_t(acc, fetch(2 * t + 1), GfMulCall());
+    }
+    ld_store(&sh[t], acc);
+    __syncthreads();
+    for (uint32_t n = (len + 1) >> 1; n > 1; n = (n + 1) >> 1) {
+        const bool act = 2 * t < n;
+        if (act) {
+            acc = ld_load(&sh[2 * t]);
+            if (2 * t + 1 < n) acc = ld_add_t(acc, ld_load(&sh[2 * t + 1]), GfMulCall());
+        }
+        __syncthreads();
+        if (act) ld_store(&sh[t], acc);
+        __syncthreads();
+    }
+    if (t == 0) {
+        const LdPt r = len ? ld_load(&sh[0]) : ld_infinity();
+        if (OUT_AFFINE) {
+            AffPt o = pt_inf();
+            if (!gf_is_zero(r.Z)) {
+                const gf zi = gf_inv_tab(r.Z, tabs);
+                o.x = gf_mul_call(r.X, zi);
+                o.y = gf_mul_call(r.Y, gf_sqr(zi));
+            }
+            pt_store(reinterpret_cast<AffPt *>(dst) + s, o);
+        } else {
+            ld_store(reinterpret_cast<LdPt *>(dst) + s, r);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
 int MsmLane::init() {
@@ -1263,7 +1330,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         RS(L.pp[1], (out_ub0 / 2 + nseg_max + 1) * sizeof(AffPt));
         if ((rc = reserve_round(L, task_ub0)) != 0) return rc;
         RS(L.buckets, (size_t)p.nseg * sizeof(AffPt));
-        RS(L.rc, (size_t)p.nseg_a * sizeof(AffPt));
+        RS(L.rc, (size_t)p.nseg_a * sizeof(LdPt));
         RS(L.ents2, (size_t)std::max(p.nent_a, p.nent_b) * 4);
     }
 #undef RS
@@ -1287,23 +1354,43 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         if (rc) return rc;
         L.want_k = false;
         if (timing && l == 0) cudaEventRecord(L.ev_s[1], L.stream);
-        // level A: row and column sums of each virtual window's bucket matrix
         uint32_t *d_start = L.c_start.as<uint32_t>(), *d_len = L.c_len.as<uint32_t>();
-        k_gen_level_a<<<cdiv(p.nent_a, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, L.ents2.as<uint32_t>());
-        k_gen_segs_a<<<cdiv(p.nseg_a + 1, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, d_start, d_len);
-        L.launches += 2;
-        if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a, false))) return rc;
-        rc = tree.rounds(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,
-                         std::max(R, m), L.rc.as<AffPt>(), &r_a);
-        if (rc) return rc;
-        // level B: per-bit subset sums of the row / column sums
-        k_gen_level_b<<<cdiv(p.nent_b, 256), 256, 0, L.stream>>>(p.vn, lr, lm, L.ents2.as<uint32_t>());
-        k_gen_segs_b<<<cdiv(p.nseg_b + 1, 256), 256, 0, L.stream>>>(p.vn, lr, lm, d_start, d_len);
-        L.launches += 2;
-        if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_b, false))) return rc;
-        rc = tree.rounds(L.rc.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_b, p.nent_b,
-                         std::max(R >> 1, m), hb.as<AffPt>() + (size_t)p.v0 * cv, &r_b);
-        if (rc) return rc;
+        const uint32_t tthr = std::max(32u, std::max(R, m) / 2); // a segment has at most max(R, m) points
+        if (tthr <= 256) {
+            // level A: row and column sums of each virtual window's bucket matrix (projective, one block per segment)
+            k_gen_level_a<<<cdiv(p.nent_a, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, L.ents2.as<uint32_t>());
+            k_gen_segs_a<<<cdiv(p.nseg_a + 1, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, d_start, d_len);
+            tree.pb(PC_MISC);
+            k_ld_tree<false, false><<<p.nseg_a, tthr, tthr * sizeof(LdPt), L.stream>>>(
+                L.buckets.p, L.ents2.as<uint32_t>(), d_start, d_len, L.rc.p, msqr_tabs.as<gf>());
+            tree.pe();
+            // level B: per-bit subset sums of the row / column sums, converted to affine for the host tail
+            k_gen_level_b<<<cdiv(p.nent_b, 256), 256, 0, L.stream>>>(p.vn, lr, lm, L.ents2.as<uint32_t>());
+            k_gen_segs_b<<<cdiv(p.nseg_b + 1, 256), 256, 0, L.stream>>>(p.vn, lr, lm, d_start, d_len);
+            tree.pb(PC_MISC);
+            k_ld_tree<true, true><<<p.nseg_b, tthr, tthr * sizeof(LdPt), L.stream>>>(
+                L.rc.p, L.ents2.as<uint32_t>(), d_start, d_len, hb.as<AffPt>() + (size_t)p.v0 * cv, msqr_tabs.as<gf>());
+            tree.pe();
+            L.launches += 6;
+            CK(cudaGetLastError());
+            r_a = r_b = 1;
+        } else {
+            // very wide windows (forced): the same two levels as batched-affine tree rounds
+            k_gen_level_a<<<cdiv(p.nent_a, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, L.ents2.as<uint32_t>());
+            k_gen_segs_a<<<cdiv(p.nseg_a + 1, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, d_start, d_len);
+            L.launches += 2;
+            if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a, false))) return rc;
+            rc = tree.rounds(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,
+                             std::max(R, m), L.rc.as<AffPt>(), &r_a);
+            if (rc) return rc;
+            k_gen_level_b<<<cdiv(p.nent_b, 256), 256, 0, L.stream>>>(p.vn, lr, lm, L.ents2.as<uint32_t>());
+            k_gen_segs_b<<<cdiv(p.nseg_b + 1, 256), 256, 0, L.stream>>>(p.vn, lr, lm, d_start, d_len);
+            L.launches += 2;
+            if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_b, false))) return rc;
+            rc = tree.rounds(L.rc.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_b, p.nent_b,
+                             std::max(R >> 1, m), hb.as<AffPt>() + (size_t)p.v0 * cv, &r_b);
+            if (rc) return rc;
+        }
         if (timing && l == 0) cudaEventRecord(L.ev_s[2], L.stream);
         CK(cudaEventRecord(L.done, L.stream));
         stt.rounds_main = std::max(stt.rounds_main, r_main);

@@ -135,3 +135,25 @@ def test_fr29_butterfly_row():
     # and the limbs are canonical (fully reduced): the bytes equal the canonical Montgomery encoding
     want = dvpari.fr_to_mont([(a * b + c * d) % P for a, b, c, d in zip(m0, x0, m1, x1)])
     assert out.view(np.uint64).reshape(-1, 4).tobytes() == want.tobytes()
+
+
+def test_ld_projective_addition_is_complete(oracle):
+    """k233_ld.cuh: the inversion-free addition used by the MSM's reduction trees, on projective operands with
+    Z != 1, including equal operands in different representations (doubling branch), opposite operands and infinity."""
+    O = oracle
+    rnd = random.Random(31)
+    G = O.generator()
+    pts = [O.pt_mul(G, rnd.randrange(1, P)) for _ in range(40)]
+    a = pts + [O.pt(), pts[0], pts[1], O.pt(), pts[2]]
+    b = pts[7:] + pts[:7] + [pts[3], O.pt(), O.pt_neg(pts[1]), O.pt(), pts[2]]
+    A, B = pt_arr(O, a), pt_arr(O, b)
+    got = dvpari.hostcheck_op(16, A, B)
+    for i, (p, q) in enumerate(zip(a, b)):
+        want = O.pt_add(O.pt_add(O.pt_add(p, p), p), q)
+        assert O.pt_encode(pt_from_row(O, got[i])) == O.pt_encode(want), i
+    out = np.zeros((len(a), 32), dtype=np.uint32)
+    dvpari._ck(dvpari.lib().dvp_hostcheck_op(17, dvpari._ptr(A), dvpari._ptr(B), dvpari._ptr(out), len(a)))
+    for i, (p, q) in enumerate(zip(a, b)):
+        s = O.pt_add(p, q)
+        assert O.pt_encode(pt_from_row(O, out[i, :16])) == O.pt_encode(O.pt_add(s, s)), i
+        assert not out[i, 16:].any(), i
