@@ -9,6 +9,7 @@
 //   prover precomputes (bar_wts, z_vals2inv)      src/proving.rs:225-325         -> chain-rule kernels
 // Fr is 8 x u32 Montgomery limbs in ark's memory layout (fr.cuh).  Every vector stays in HBM between
 // stages; the host sees only the two commitments, alpha and the two evaluations.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -772,7 +773,7 @@ int dvp_prover_create(dvp_ctx *ctx, dvp_domain *dom, dvp_r1cs *r1cs, int slot_gm
     p->slot_gk = slot_gk;
     int rc = 0;
     const size_t ng = (2 * n + FRB - 1) / FRB;
-    if ((rc = p->vec.reserve(13 * n * sizeof(fr))) || (rc = p->wit.reserve(r1cs->nwires * sizeof(fr))) ||
+    if ((rc = p->vec.reserve(13 * n * sizeof(fr))) || (rc = p->wit.reserve((r1cs->nwires + 64) * sizeof(fr))) ||
         (rc = p->dinv.reserve(2 * n * sizeof(fr))) || (rc = p->pre.reserve(2 * n * sizeof(fr))) ||
         (rc = p->tot.reserve(ng * sizeof(fr))) || (rc = p->tot2.reserve((ng / FRB + 2) * sizeof(fr))) ||
         (rc = p->pre2.reserve(ng * sizeof(fr))) || (rc = p->part.reserve(2 * 1024 * sizeof(fr))) ||
@@ -863,7 +864,18 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     const fr one = fr_one();
     CKP(cudaMemcpyAsync(w, &one, 32, cudaMemcpyHostToDevice, st));
     if (k) CKP(cudaMemcpyAsync(w + 1, pub, k * 32, cudaMemcpyHostToDevice, st));
-    if (npriv) CKP(cudaMemcpyAsync(w + 1 + k, priv, npriv * 32, cudaMemcpyHostToDevice, st));
+    if (ctx->world == 1) {
+        if (npriv) CKP(cudaMemcpyAsync(w + 1 + k, priv, npriv * 32, cudaMemcpyHostToDevice, st));
+    } else {
+        // every rank uploads 1/world of the private witness over its own PCIe link, the rest arrives over NVLink
+        const size_t Wn = (size_t)ctx->world, chunk = (r->nwires + Wn - 1) / Wn; // wires per rank, last one short
+        const size_t lo = std::min(r->nwires, chunk * (size_t)ctx->rank), hi = std::min(r->nwires, lo + chunk);
+        const size_t plo = std::max(lo, 1 + k), phi = std::max(hi, 1 + k); // the private part of [lo, hi)
+        if (phi > plo)
+            CKP(cudaMemcpyAsync(w + plo, priv + (plo - 1 - k) * 4, (phi - plo) * 32, cudaMemcpyHostToDevice, st));
+        int rcg = comm_all_gather(ctx, w + chunk * (size_t)ctx->rank, w, chunk * sizeof(fr));
+        if (rcg) return rcg;
+    }
     cudaEventRecord(ev_h2d, st);
     int64_t bad = -1;
     int rc = r1cs_eval_device(r, d, w, a, b, c, iv, &bad);
