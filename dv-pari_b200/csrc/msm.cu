@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(256)
     const uint32_t s = blockIdx.x, t = threadIdx.x;
     const uint32_t start = seg_start[s], len = seg_len[s];
     auto fetch = [&](uint32_t pos) -> LdPt {
-        const uint32_t e = ent[start + pos];
+        const uint32_t e = ent ? ent[start + pos] : start + pos;
         if (SRC_LD) return ld_load(reinterpret_cast<const LdPt *>(src) + e);
         return ld_from_affine(pt_load(reinterpret_cast<const AffPt *>(src) + e));
     };
@@ -871,6 +871,7 @@ void MsmEngine::destroy() {
 namespace {
 
 constexpr uint32_t PLAN_MAX_BLOCKS = 256; // k_plan's grid must be co-resident (blocks wait for their predecessors)
+constexpr size_t LD_TREE_MAX_POINTS = (size_t)1 << 17; // above this a reduction level starts with affine rounds
 constexpr uint32_t BINV_G = 16;        // group size of one batched-inversion level (large batches)
 
 struct Tree {
@@ -981,13 +982,32 @@ struct Tree {
     // Reduce every segment of the index list `ent` over `src` to one point: dst[s], s < nseg, given that
     // plan0 has run.  start0 (nseg+1) / len0 (nseg) describe the segments and are only read; they must not
     // be the lane's own seg_start[] / seg_len[] ping-pong arrays.  total_ub bounds the entry count.
+    // With `stop` set the rounds end as soon as at most stop->max_left points can remain (a later pass finishes the
+    // segments); *stop then describes the partially reduced list and dst is not written.
+    struct Partial {
+        size_t max_left;
+        const AffPt *src;          // out: the list after the last round run
+        const uint32_t *start, *len; // out: its segment tables (nseg entries; the caller's own when no round ran)
+        uint32_t maxlen;           // out: bound on the remaining segment length
+    };
     int rounds(const AffPt *src, const uint32_t *ent, const uint32_t *start0, const uint32_t *len0, uint32_t nseg,
-               size_t total_ub, uint32_t maxlen, AffPt *dst, int *rounds_out) {
+               size_t total_ub, uint32_t maxlen, AffPt *dst, int *rounds_out, Partial *stop = nullptr) {
         uint32_t *elen[2] = {L.seg_len[0].as<uint32_t>(), L.seg_len[1].as<uint32_t>()};
         uint32_t *estart[2] = {L.seg_start[0].as<uint32_t>(), L.seg_start[1].as<uint32_t>()};
         int nr = 0;
         while ((1ull << nr) < maxlen) nr++;
+        if (stop) {
+            // after r rounds at most total/2^r + nseg points remain
+            int r = 0;
+            while (r < nr && (total_ub >> r) + nseg > stop->max_left) r++;
+            nr = r;
+            stop->src = src;
+            stop->start = start0;
+            stop->len = len0;
+            stop->maxlen = maxlen;
+        }
         if (rounds_out) *rounds_out = nr;
+        if (nr == 0 && stop) return 0;
         if (nr == 0) {
             pb(PC_MISC);
             k_finalize<true><<<cdiv(nseg, 256), 256, 0, st>>>(src, ent, start0, len0, nseg, dst);
@@ -1016,6 +1036,13 @@ struct Tree {
             in_start = estart[o];
             in_len = elen[o];
             if (r + 1 < nr && (rc = plan(in_len, in_start, nullptr, nseg, estart[o ^ 1], elen[o ^ 1]))) return rc;
+        }
+        if (stop) {
+            stop->src = cur_src;
+            stop->start = in_start;
+            stop->len = in_len;
+            stop->maxlen = (maxlen + (1u << nr) - 1) >> nr;
+            return 0;
         }
         pb(PC_MISC);
         k_finalize<false><<<cdiv(nseg, 256), 256, 0, st>>>(cur_src, nullptr, in_start, in_len, nseg, dst);
@@ -1360,9 +1387,24 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
             // level A: row and column sums of each virtual window's bucket matrix (projective, one block per segment)
             k_gen_level_a<<<cdiv(p.nent_a, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, L.ents2.as<uint32_t>());
             k_gen_segs_a<<<cdiv(p.nseg_a + 1, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, d_start, d_len);
+            // large levels start with batched-affine rounds (5 instead of 15 multiplications per addition) and
+            // switch to the inversion-free tree once the work is latency-bound
+            Tree::Partial part_a{LD_TREE_MAX_POINTS, nullptr, nullptr, nullptr, 0};
+            if (p.nent_a > LD_TREE_MAX_POINTS) {
+                if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a, false))) return rc;
+                rc = tree.rounds(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,
+                                 std::max(R, m), nullptr, &r_a, &part_a);
+                if (rc) return rc;
+            }
             tree.pb(PC_MISC);
-            k_ld_tree<false, false><<<p.nseg_a, tthr, tthr * sizeof(LdPt), L.stream>>>(
-                L.buckets.p, L.ents2.as<uint32_t>(), d_start, d_len, L.rc.p, msqr_tabs.as<gf>());
+            if (r_a > 0) {
+                const uint32_t th = std::max(32u, part_a.maxlen / 2);
+                k_ld_tree<false, false><<<p.nseg_a, th, th * sizeof(LdPt), L.stream>>>(
+                    part_a.src, nullptr, part_a.start, part_a.len, L.rc.p, msqr_tabs.as<gf>());
+            } else {
+                k_ld_tree<false, false><<<p.nseg_a, tthr, tthr * sizeof(LdPt), L.stream>>>(
+                    L.buckets.p, L.ents2.as<uint32_t>(), d_start, d_len, L.rc.p, msqr_tabs.as<gf>());
+            }
             tree.pe();
             // level B: per-bit subset sums of the row / column sums, converted to affine for the host tail
             k_gen_level_b<<<cdiv(p.nent_b, 256), 256, 0, L.stream>>>(p.vn, lr, lm, L.ents2.as<uint32_t>());
@@ -1373,7 +1415,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
             tree.pe();
             L.launches += 6;
             CK(cudaGetLastError());
-            r_a = r_b = 1;
+            r_b = 1;
         } else {
             // very wide windows (forced): the same two levels as batched-affine tree rounds
             k_gen_level_a<<<cdiv(p.nent_a, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, L.ents2.as<uint32_t>());
