@@ -31,6 +31,8 @@ METRIC = "sect233k1 MSM points/s"
 UNIT = "points/s"
 # static facts about the dominant kernel (k_pass2, one batched affine addition per task), see DESIGN.md
 PASS2_BYTES_PER_ADD = 128 + 32 + 16 + 64  # two points in, prefix product, task descriptor, one point out
+# dram__bytes_read.sum + dram__bytes_write.sum of the round-0 launch / its additions (profiles/README.md, r1b capture)
+PASS2_DRAM_BYTES_PER_ADD_NCU = 385
 # ALU-pipe issue slots per addition in k_pass2 (scripts/sass_count.py): 4 calls of the out-of-line multiplier
 # (434 IMAD.WIDE + 760 LOP3/SHF each) + the loop body (250 ALU).  IMAD.WIDE holds the FMA pipe for 4 cycles AND the
 # ALU pipe for 2 (profiles/README.md, pipe probes), so it counts as one ALU-pipe slot as well.
@@ -358,7 +360,7 @@ def main():
             "gpu_launches": int(st["launches"]) * args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_pass2<16,2> (round 0 of the bucket accumulation)",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": 1.826e9 if args.lg == 20 else None, "peak_source": which,
+                         "traffic": k_adds * PASS2_DRAM_BYTES_PER_ADD_NCU, "peak_source": which,
                          "launch_ms": k_ms, "adds_per_launch": k_adds, "bytes_per_add": PASS2_BYTES_PER_ADD,
                          "note": "integer-issue bound, not HBM bound: see int_issue"},
             "int_issue": {"achieved": alu, "peak": ALU_PIPE_PEAK, "unit": "ALU-pipe thread-instr/s", "frac": alu / ALU_PIPE_PEAK,
