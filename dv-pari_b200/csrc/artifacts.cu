@@ -1,0 +1,158 @@
+// Artifact formats either side of the prover path (host code of the product, no device work):
+//   Fr vector files    u64 LE count | 29-byte LE canonical elements      /root/reference/src/io_utils.rs:27-66,113-165
+//   SP1 / gnark dumps  u32 nbCoeffs | 32-byte BE coefficients | u32 nbRows | rows of (nL nR nO | terms)
+//                      Term = (u32 wire_id, u32 coeff_id), little-endian  /root/reference/src/gnark_r1cs.rs:1-20,121-185
+//   witness files      u32 BE count | 32-byte BE elements                 /root/reference/src/gnark_r1cs.rs:58-77,188-199
+//   SP1 public input   blake3(raw u64 LE), top 4 bytes cleared, as BE int /root/reference/src/gnark_r1cs.rs:218-236
+// Everything lands in the layouts the C ABI takes: Montgomery limbs (Vec<Fr>) and CSR per matrix.
+// (Point-vector files are u64 count | 30-byte encodings: their payload goes to dvp_srs_load unchanged.)
+#include <cstring>
+#include "../../include/dvpari.h"
+#include "fr.cuh"
+#include "transcript_host.hpp"
+
+using namespace dvp;
+
+namespace {
+// value of 32 big-endian bytes mod p, as Montgomery limbs (Fr::from_be_bytes_mod_order)
+fr fr_from_be32_mod(const uint8_t *b) {
+    // split v = hi * 2^224 + lo with lo < 2^224 < p and hi < 2^32: both canonical
+    uint32_t lo[8], hi[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int w = 0; w < 8; w++) {
+        const uint8_t *q = b + 28 - 4 * w; // word w (little-endian order) sits at bytes 28-4w .. 31-4w
+        lo[w] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+    }
+    hi[0] = lo[7];
+    lo[7] = 0;
+    // 2^224 in Montgomery form = fr_from_canonical of the limb pattern with bit 224 set
+    uint32_t t224[8] = {0, 0, 0, 0, 0, 0, 0, 1};
+    const fr m224 = fr_from_canonical(t224);
+    return fr_add(fr_from_canonical(lo), fr_mul(fr_from_canonical(hi), m224));
+}
+} // namespace
+
+extern "C" {
+
+int dvp_fr_from_le29(const uint8_t *in, size_t n, uint64_t *out_mont) {
+    if ((!in || !out_mont) && n) return DVP_ERR_BAD_ARG;
+    for (size_t i = 0; i < n; i++) {
+        uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint8_t buf[32] = {0};
+        memcpy(buf, in + 29 * i, 29);
+        memcpy(c, buf, 32);
+        if (fr_geq_p(c)) return DVP_ERR_BAD_ARG; // not canonical
+        const fr m = fr_from_canonical(c);
+        memcpy(out_mont + 4 * i, m.v, 32);
+    }
+    return DVP_OK;
+}
+
+int dvp_fr_to_le29(const uint64_t *in_mont, size_t n, uint8_t *out) {
+    if ((!in_mont || !out) && n) return DVP_ERR_BAD_ARG;
+    for (size_t i = 0; i < n; i++) {
+        fr a;
+        memcpy(a.v, in_mont + 4 * i, 32);
+        uint32_t c[8];
+        fr_to_canonical(c, a);
+        uint8_t buf[32];
+        memcpy(buf, c, 32);
+        memcpy(out + 29 * i, buf, 29);
+    }
+    return DVP_OK;
+}
+
+int dvp_fr_from_be32_mod_order(const uint8_t *in, size_t n, uint64_t *out_mont) {
+    if ((!in || !out_mont) && n) return DVP_ERR_BAD_ARG;
+    for (size_t i = 0; i < n; i++) {
+        const fr m = fr_from_be32_mod(in + 32 * i);
+        memcpy(out_mont + 4 * i, m.v, 32);
+    }
+    return DVP_OK;
+}
+
+int dvp_sp1_public_input(uint64_t raw, uint64_t out_mont[4]) {
+    if (!out_mont) return DVP_ERR_BAD_ARG;
+    uint8_t le[8], h[32];
+    for (int i = 0; i < 8; i++) le[i] = (uint8_t)(raw >> (8 * i));
+    host::Blake3Small::hash(le, 8, h);
+    memset(h, 0, 4); // the first four bytes of the big-endian number are masked off: 224 bits remain
+    const fr m = fr_from_be32_mod(h);
+    memcpy(out_mont, m.v, 32);
+    return DVP_OK;
+}
+
+// First pass over a dump: sizes.  Returns DVP_ERR_BAD_ARG if the buffer is truncated or inconsistent.
+int dvp_r1cs_dump_sizes(const uint8_t *buf, size_t len, size_t *ncoeffs, size_t *nrows, size_t nnz[3], size_t *max_wire) {
+    if (!buf || !ncoeffs || !nrows || !nnz || !max_wire) return DVP_ERR_BAD_ARG;
+    size_t pos = 0;
+    auto rd32 = [&](uint32_t &v) -> bool {
+        if (pos + 4 > len) return false;
+        memcpy(&v, buf + pos, 4);
+        pos += 4;
+        return true;
+    };
+    uint32_t nc, nr;
+    if (!rd32(nc)) return DVP_ERR_BAD_ARG;
+    if (pos + (size_t)nc * 32 > len) return DVP_ERR_BAD_ARG;
+    pos += (size_t)nc * 32;
+    if (!rd32(nr)) return DVP_ERR_BAD_ARG;
+    nnz[0] = nnz[1] = nnz[2] = 0;
+    size_t mw = 0;
+    for (uint32_t r = 0; r < nr; r++) {
+        uint32_t cnt[3];
+        for (int w = 0; w < 3; w++)
+            if (!rd32(cnt[w])) return DVP_ERR_BAD_ARG;
+        for (int w = 0; w < 3; w++) {
+            if (pos + (size_t)cnt[w] * 8 > len) return DVP_ERR_BAD_ARG;
+            for (uint32_t t = 0; t < cnt[w]; t++) {
+                uint32_t wire, cid;
+                memcpy(&wire, buf + pos, 4);
+                memcpy(&cid, buf + pos + 4, 4);
+                pos += 8;
+                if (cid >= nc) return DVP_ERR_BAD_ARG;
+                if (wire > mw) mw = wire;
+            }
+            nnz[w] += cnt[w];
+        }
+    }
+    *ncoeffs = nc;
+    *nrows = nr;
+    *max_wire = mw;
+    return DVP_OK;
+}
+
+// Second pass: fill the CSR arrays (rowptr[w]: nrows + 1, wire[w] / coeff[w]: nnz[w]) and the coefficient table.
+int dvp_r1cs_dump_parse(const uint8_t *buf, size_t len, uint32_t *const rowptr[3], uint32_t *const wire[3],
+                        uint32_t *const coeff[3], uint64_t *coeffs_mont) {
+    if (!buf || !rowptr || !wire || !coeff || !coeffs_mont) return DVP_ERR_BAD_ARG;
+    size_t pos = 0;
+    uint32_t nc, nr;
+    memcpy(&nc, buf + pos, 4);
+    pos += 4;
+    for (uint32_t i = 0; i < nc; i++) {
+        const fr m = fr_from_be32_mod(buf + pos);
+        memcpy(coeffs_mont + 4 * (size_t)i, m.v, 32);
+        pos += 32;
+    }
+    memcpy(&nr, buf + pos, 4);
+    pos += 4;
+    uint32_t fill[3] = {0, 0, 0};
+    for (int w = 0; w < 3; w++) rowptr[w][0] = 0;
+    for (uint32_t r = 0; r < nr; r++) {
+        uint32_t cnt[3];
+        memcpy(cnt, buf + pos, 12);
+        pos += 12;
+        for (int w = 0; w < 3; w++) {
+            for (uint32_t t = 0; t < cnt[w]; t++) {
+                memcpy(&wire[w][fill[w]], buf + pos, 4);
+                memcpy(&coeff[w][fill[w]], buf + pos + 4, 4);
+                pos += 8;
+                fill[w]++;
+            }
+            rowptr[w][r + 1] = fill[w];
+        }
+    }
+    return pos <= len ? DVP_OK : DVP_ERR_BAD_ARG;
+}
+
+} // extern "C"

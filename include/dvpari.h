@@ -191,6 +191,24 @@ int dvp_prove_stages(dvp_prover *p, const uint64_t *public_mont, size_t k, const
  * witness upload (host -> device) */
 int dvp_prove_last_times(dvp_prover *p, float ms[7]);
 
+/*
+ * Artifact formats either side of the path (host-side conversions into the layouts above; no device work).
+ *   Fr vector files   u64 LE count | 29-byte LE canonical elements          (src/io_utils.rs:27-66,113-165)
+ *   SP1 / gnark dump  u32 nbCoeffs | 32-byte BE coefficients | u32 nbRows | (nL nR nO | (u32 wire, u32 coeff)...)
+ *                                                                            (src/gnark_r1cs.rs:1-20,121-185)
+ *   witness file      u32 BE count | 32-byte BE elements                    (src/gnark_r1cs.rs:58-77,188-199)
+ * A point-vector file is u64 LE count | 30-byte encodings: its payload goes to dvp_srs_load unchanged.
+ */
+int dvp_fr_from_le29(const uint8_t *in, size_t n, uint64_t *out_mont);           /* Fr::deserialize_uncompressed */
+int dvp_fr_to_le29(const uint64_t *in_mont, size_t n, uint8_t *out);             /* Fr::serialize_uncompressed */
+int dvp_fr_from_be32_mod_order(const uint8_t *in, size_t n, uint64_t *out_mont); /* Fr::from_be_bytes_mod_order */
+/* sp1_generate_scalar_from_raw_public_input (src/gnark_r1cs.rs:218-236) */
+int dvp_sp1_public_input(uint64_t raw, uint64_t out_mont[4]);
+/* load_sparse_r1cs_from_file in two passes over the file image: sizes, then CSR per matrix + coefficient table */
+int dvp_r1cs_dump_sizes(const uint8_t *buf, size_t len, size_t *ncoeffs, size_t *nrows, size_t nnz[3], size_t *max_wire);
+int dvp_r1cs_dump_parse(const uint8_t *buf, size_t len, uint32_t *const rowptr[3], uint32_t *const wire[3],
+                        uint32_t *const coeff[3], uint64_t *coeffs_mont);
+
 /* Single-warp latency of a dependent chain, microseconds per op: mode 0 gf inversion by squarings,
  * 1 table-driven gf inversion, 2 gf multiplication. */
 int dvp_latency_probe(dvp_ctx *ctx, int mode, int iters, float *us_per_op);

@@ -93,3 +93,48 @@ def test_synth_prove_2_18_verifies(ctx, oracle):
     lg = int(os.environ.get("DVP_FULL_LG", "18"))
     t = _synth_case(ctx, oracle, lg, False)
     print(f"prove 2^{lg}: " + ", ".join(f"{k} {v:.2f} ms" for k, v in t.items()))
+
+
+def test_prove_from_artifact_files(ctx, oracle, tmp_path):
+    """The reference's cache-dir flow (proving.rs:426-470, 511, 666-673) through its own file formats: R1CS dump,
+    gnark witness file, point-vector files for g_m / g_q / g_k_0..2 -- the proof equals the one from in-memory data."""
+    import artifacts
+
+    O = oracle
+    lg = 9
+    circ = synth.synth_r1cs(lg, seed=77, nlevels=4)
+    inst = dvpari.R1CSInstance(ctx, circ["nrows"], circ["k"], circ["nwires"], circ["rowptr"], circ["wire"],
+                               circ["coeff"], circ["coeffs_mont"])
+    w = inst.synth_solve(synth.synth_assignment(circ), circ["nlevels"])
+    r1cs = O.R1CS.from_arrays(circ["coeffs_mont"], circ["rowptr"], circ["wire"], circ["coeff"], circ["nrows"],
+                              circ["k"], circ["nwires"])
+    od = O.Domain(lg + 1)
+    td = O.trapdoor(11, 22, 33)
+    srs = O.Srs(r1cs, od, td)
+    want, rc, _ = O.prove(r1cs, od, srs, w)
+    assert rc == 0
+    n, k = circ["n"], circ["k"]
+    # write the cache directory
+    artifacts.write_sparse_r1cs_to_file(tmp_path / "r1cs", circ)
+    artifacts.write_witness_to_file(tmp_path / "witness", dvpari.fr_from_mont(w))
+    artifacts.write_point_vec_to_file(tmp_path / "g_m", srs.g_m30())
+    artifacts.write_point_vec_to_file(tmp_path / "g_q", srs.g_q30())
+    gk = srs.g_k30()
+    for i, (lo, hi) in enumerate(((0, n), (n, 2 * n), (2 * n, 4 * n))):
+        artifacts.write_point_vec_to_file(tmp_path / f"g_k_{i}", gk[lo:hi])
+    # read it back the way the reference does and prove
+    c2 = artifacts.load_sparse_r1cs_from_file(tmp_path / "r1cs", k)
+    inst2 = dvpari.R1CSInstance(ctx, c2["nrows"], c2["k"], c2["nwires"], c2["rowptr"], c2["wire"], c2["coeff"],
+                                c2["coeffs_mont"])
+    w2 = artifacts.load_witness_from_file(tmp_path / "witness")
+    ctx.srs_load(4, artifacts.read_point_vec_from_file(tmp_path / "g_m"))
+    ctx.srs_load(5, artifacts.read_point_vec_from_file(tmp_path / "g_q"))
+    ctx.srs_load(6, artifacts.read_point_vec_from_file(tmp_path / "g_k_0"))
+    ctx.srs_append(6, artifacts.read_point_vec_from_file(tmp_path / "g_k_1"))
+    ctx.srs_append(6, artifacts.read_point_vec_from_file(tmp_path / "g_k_2"))
+    gd = dvpari.Domain(ctx, lg + 1)
+    prover = dvpari.Prover(ctx, gd, inst2, 4, 5, 6)
+    assert prover.prove(w2[1:1 + k], w2[1 + k:]) == want
+    prover.close(); inst.close(); inst2.close(); gd.close()
+    for s in (4, 5, 6):
+        ctx.srs_free(s)
