@@ -470,6 +470,7 @@ int dvp_msm_last_stats(dvp_ctx *ctx, dvp_msm_stats *out) {
     out->ms_device = s.ms_device;
     out->lanes = s.lanes;
     out->tables = s.tables;
+    out->ms_tail_host = s.ms_tail_host;
     return DVP_OK;
 }
 

@@ -14,29 +14,73 @@
 namespace dvp {
 namespace host {
 
+#if defined(__PCLMUL__)
+// c[0..7] (466 bits, little-endian u64) -> reduced element; x^233 = x^74 + 1 on 64-bit words
+inline gf hreduce64(uint64_t c[8]) {
+    // word i (i >= 4) holds x^(64 i + k); 64 i - 233 = 64 (i - 4) + 23 and 64 i - 159 = 64 (i - 3) + 33
+    for (int i = 7; i >= 4; i--) {
+        const uint64_t t = c[i];
+        c[i - 4] ^= t << 23;
+        c[i - 3] ^= (t >> 41) ^ (t << 33);
+        c[i - 2] ^= t >> 31;
+    }
+    const uint64_t t = c[3] >> 41; // bits 233..255
+    c[0] ^= t;
+    c[1] ^= t << 10; // x^74 = word 1, bit 10
+    c[3] &= (1ull << 41) - 1;
+    gf r;
+    std::memcpy(r.v, c, 32);
+    return r;
+}
+#endif
 inline gf hmul(const gf &a, const gf &b) {
 #if defined(__PCLMUL__)
-    uint64_t A[4], B[4], c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // 4 x 4 words of 64 bits, two Karatsuba levels: 9 carry-less multiplications
+    uint64_t A[4], B[4];
     std::memcpy(A, a.v, 32);
     std::memcpy(B, b.v, 32);
-    for (int i = 0; i < 4; i++) {
-        __m128i ai = _mm_cvtsi64_si128((long long)A[i]);
-        for (int j = 0; j < 4; j++) {
-            __m128i p = _mm_clmulepi64_si128(ai, _mm_cvtsi64_si128((long long)B[j]), 0);
-            c[i + j] ^= (uint64_t)_mm_cvtsi128_si64(p);
-            c[i + j + 1] ^= (uint64_t)_mm_extract_epi64(p, 1);
-        }
-    }
-    uint32_t w[16];
-    std::memcpy(w, c, 64);
-    return gf_reduce(w);
+    auto mul2 = [](uint64_t a0, uint64_t a1, uint64_t b0, uint64_t b1, uint64_t r[4]) {
+        const __m128i x = _mm_set_epi64x((long long)a1, (long long)a0), y = _mm_set_epi64x((long long)b1, (long long)b0);
+        const __m128i lo = _mm_clmulepi64_si128(x, y, 0x00), hi = _mm_clmulepi64_si128(x, y, 0x11);
+        const __m128i sx = _mm_xor_si128(x, _mm_srli_si128(x, 8)), sy = _mm_xor_si128(y, _mm_srli_si128(y, 8));
+        __m128i mid = _mm_clmulepi64_si128(sx, sy, 0x00);
+        mid = _mm_xor_si128(mid, _mm_xor_si128(lo, hi));
+        r[0] = (uint64_t)_mm_cvtsi128_si64(lo);
+        r[1] = (uint64_t)_mm_extract_epi64(lo, 1) ^ (uint64_t)_mm_cvtsi128_si64(mid);
+        r[2] = (uint64_t)_mm_cvtsi128_si64(hi) ^ (uint64_t)_mm_extract_epi64(mid, 1);
+        r[3] = (uint64_t)_mm_extract_epi64(hi, 1);
+    };
+    uint64_t lo[4], hi[4], mid[4], c[8];
+    mul2(A[0], A[1], B[0], B[1], lo);
+    mul2(A[2], A[3], B[2], B[3], hi);
+    mul2(A[0] ^ A[2], A[1] ^ A[3], B[0] ^ B[2], B[1] ^ B[3], mid);
+    for (int i = 0; i < 4; i++) mid[i] ^= lo[i] ^ hi[i];
+    c[0] = lo[0]; c[1] = lo[1];
+    c[2] = lo[2] ^ mid[0]; c[3] = lo[3] ^ mid[1];
+    c[4] = hi[0] ^ mid[2]; c[5] = hi[1] ^ mid[3];
+    c[6] = hi[2]; c[7] = hi[3];
+    return hreduce64(c);
 #else
     return gf_mul(a, b);
 #endif
 }
-inline gf hsqr(const gf &a) { return gf_sqr(a); }
+inline gf hsqr(const gf &a) {
+#if defined(__PCLMUL__)
+    uint64_t A[4], c[8];
+    std::memcpy(A, a.v, 32);
+    for (int i = 0; i < 4; i++) {
+        const __m128i x = _mm_cvtsi64_si128((long long)A[i]);
+        const __m128i p = _mm_clmulepi64_si128(x, x, 0);
+        c[2 * i] = (uint64_t)_mm_cvtsi128_si64(p);
+        c[2 * i + 1] = (uint64_t)_mm_extract_epi64(p, 1);
+    }
+    return hreduce64(c);
+#else
+    return gf_sqr(a);
+#endif
+}
 inline gf hsqr_n(gf a, int n) {
-    for (int i = 0; i < n; i++) a = gf_sqr(a);
+    for (int i = 0; i < n; i++) a = hsqr(a);
     return a;
 }
 inline gf hinv(const gf &a) {

@@ -17,6 +17,7 @@
 // read-back (the longest bucket) sizes the rounds.
 #include "msm.cuh"
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <vector>
 #include "../../include/dvpari.h"
@@ -152,24 +153,16 @@ __global__ void k_scatter(const uint32_t *__restrict__ keys, uint32_t n, size_t 
     entries[pos] = (ebase0 + j * ebase_stride + i) | ((k & 1u) << 31);
 }
 
-// per lane (one block each): entries and longest bucket of the segment range [bounds[l], bounds[l+1])
+// per lane: entries and longest bucket of the segment range [bounds[l], bounds[l+1]); grid = (blocks, lanes),
+// out[2l + 1] must be zero on entry
 __global__ void k_lane_info(const uint32_t *__restrict__ len, const uint32_t *__restrict__ start,
                             const uint32_t *__restrict__ bounds, uint32_t *__restrict__ out) {
-    __shared__ uint32_t sh[32];
-    const uint32_t s0 = bounds[blockIdx.x], s1 = bounds[blockIdx.x + 1];
+    const uint32_t l = blockIdx.y, s0 = bounds[l], s1 = bounds[l + 1];
     uint32_t mx = 0;
-    for (uint32_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) mx = max(mx, len[s]);
+    for (uint32_t s = s0 + blockIdx.x * blockDim.x + threadIdx.x; s < s1; s += gridDim.x * blockDim.x) mx = max(mx, len[s]);
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        mx = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0;
-        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
-        if (threadIdx.x == 0) {
-            out[2 * blockIdx.x] = start[s1] - start[s0];
-            out[2 * blockIdx.x + 1] = mx;
-        }
-    }
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(&out[2 * l + 1], mx);
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[2 * l] = start[s1] - start[s0];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1243,7 +1236,8 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     const size_t total = (size_t)W * n;
     if (total >= (1ull << 32) || NB >= (1ull << 31) || c < 4 || c > 26) return DVP_ERR_BAD_ARG;
     // virtual windows: aligned ranges of nbv buckets, the unit of the reduction and of the lane split
-    const int cv = uniform ? std::min(c, 15) : c;         // log2(nbv) + 1
+    // (at most 32 virtual windows in the shared layout: the host tail handles V * cv points)
+    const int cv = uniform ? std::min(c, std::max(15, c - 5)) : c; // log2(nbv) + 1
     const uint32_t nbv = 1u << (cv - 1);
     const uint32_t V = (uint32_t)(NB / nbv);
     // bucket matrix of a virtual window: m = 2^lm columns, R = 2^lr rows, nbv = R*m
@@ -1319,7 +1313,9 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
                                                     uniform ? (uint32_t)tab->stride : 0u, cursor_all.as<uint32_t>(),
                                                     entries.as<uint32_t>());
         CK(cudaMemcpyAsync(lane_info.as<uint32_t>() + 32, bounds, (NL + 1) * 4, cudaMemcpyHostToDevice, st));
-        k_lane_info<<<NL, 256, 0, st>>>(d_len_all, d_start_all, lane_info.as<uint32_t>() + 32, lane_info.as<uint32_t>());
+        CK(cudaMemsetAsync(lane_info.p, 0, 32 * 4, st));
+        k_lane_info<<<dim3(std::max(1u, std::min(148u, cdiv(NB / NL, 1024))), NL), 256, 0, st>>>(
+            d_len_all, d_start_all, lane_info.as<uint32_t>() + 32, lane_info.as<uint32_t>());
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_lane, lane_info.p, 2 * NL * 4, cudaMemcpyDeviceToHost, st));
     }
@@ -1456,6 +1452,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     // ---- host tail.  Virtual window v holds buckets of digit values dbase_v + b + 1 (b local) at bit offset
     // off_v: sum_b (dbase_v + b + 1) B_b = sum_q 2^q H[v][q] + (dbase_v + 1) S[v]; one double-and-add pass
     // over all positions.  (Separate sets: off_v = the window's offset, dbase_v = 0.  Shared set: off_v = 0.)
+    const auto t_host0 = std::chrono::steady_clock::now();
     {
         const AffPt *hp = (const AffPt *)h_pts;
         const int npos = uniform ? c + 1 : 233 + c + 1;
@@ -1477,6 +1474,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     }
     stt.launches = launches;
     stt.ms_device = ms_dev;
+    stt.ms_tail_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     if (profile) {
         for (int i = 0; i < PC_COUNT; i++) prof_ms[i] = 0, prof_n[i] = 0;
         for (int l = 0; l < NL; l++)

@@ -23,6 +23,7 @@ struct MsmStats {
     float ms_recode_sort = 0, ms_accumulate = 0, ms_reduce = 0, ms_tail = 0;
     // the dominant kernel: pass 2 of round 0 of the bucket accumulation (one launch)
     float ms_pass2_round0 = 0;
+    float ms_tail_host = 0; // host fold of the per-bit sums (wall clock)
     float ms_device = 0; // recode .. partial sums on the host (CUDA events on the context stream), always measured
     unsigned long long adds_round0 = 0, adds_total = 0;
 };

@@ -35,7 +35,7 @@ class MsmStats(C.Structure):
     _fields_ = [("window_bits", C.c_int), ("windows", C.c_int), ("rounds_main", C.c_int), ("rounds_a", C.c_int),
                 ("rounds_b", C.c_int), ("launches", C.c_ulonglong), ("ms_recode_sort", C.c_float),
                 ("ms_accumulate", C.c_float), ("ms_reduce", C.c_float), ("ms_tail", C.c_float),
-                ("ms_pass2_round0", C.c_float), ("adds_round0", C.c_ulonglong), ("ms_device", C.c_float), ("lanes", C.c_int), ("tables", C.c_int)]
+                ("ms_pass2_round0", C.c_float), ("adds_round0", C.c_ulonglong), ("ms_device", C.c_float), ("lanes", C.c_int), ("tables", C.c_int), ("ms_tail_host", C.c_float)]
 
 
 def build(force=False):

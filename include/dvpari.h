@@ -48,6 +48,7 @@ typedef struct dvp_msm_stats {
     float ms_device;                  /* scalars in HBM -> partial sums on the host, CUDA events on the context stream */
     int lanes;                        /* concurrent window groups used */
     int tables;                       /* 1 if the MSM ran on the slot's precomputed window multiples */
+    float ms_tail_host;               /* host fold of the per-bit partial sums, wall clock */
 } dvp_msm_stats;
 
 const char *dvp_strerror(int code);

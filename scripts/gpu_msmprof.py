@@ -27,7 +27,7 @@ for lg in [int(a) for a in sys.argv[1:]] or [20]:
     ctx.set("msm_profile", 0); ctx.set("timing", 0)
     tot = sum(v[0] for v in pr.values())
     print(f"  profile (1 lane): " + "  ".join(f"{k} {v[0]:.3f}ms/{v[1]}" for k, v in pr.items()) + f"  sum {tot:.3f} ms")
-    print(f"  stages: sort {st['ms_recode_sort']:.3f} accumulate {st['ms_accumulate']:.3f} reduce {st['ms_reduce']:.3f} tail {st['ms_tail']:.3f}; pass2 round0 {st['ms_pass2_round0']:.3f} ms for {st['adds_round0']} adds")
+    print(f"  stages: sort {st['ms_recode_sort']:.3f} accumulate {st['ms_accumulate']:.3f} reduce {st['ms_reduce']:.3f} tail {st['ms_tail']:.3f} (host fold {st['ms_tail_host']:.3f}); pass2 round0 {st['ms_pass2_round0']:.3f} ms for {st['adds_round0']} adds")
     ctx.dev_free(d)
 # knob sweep
 n = 1 << 20
