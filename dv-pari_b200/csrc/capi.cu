@@ -223,6 +223,11 @@ int dvp_ctx_create(int device, dvp_ctx **out) {
         delete c;
         return DVP_ERR_CUDA;
     }
+    if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming) != cudaSuccess) {
+        dvp_ctx_destroy(c);
+        return DVP_ERR_CUDA;
+    }
     int rc = c->msm.init(c->stream);
     if (rc) {
         dvp_ctx_destroy(c);
@@ -246,6 +251,8 @@ void dvp_ctx_destroy(dvp_ctx *ctx) {
     ctx->small.release();
     ctx->scal.release();
     ctx->adhoc.release();
+    if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -302,8 +309,16 @@ static int slot_ok(dvp_ctx *ctx, int slot) { return ctx && slot >= 0 && slot < D
 extern "C++" {
 // MSM over slot[offset, offset + n).  Large slots get W tables T[j] = 2^(j c) P once (W x the slot's memory), after
 // which all windows share one bucket set; small slots, small sub-ranges and tight memory use the plain layout.
-int slot_msm(dvp_ctx *ctx, int slot, size_t offset, const uint32_t *d_scalars, size_t n, AffPt *out) {
+int slot_msm(dvp_ctx *ctx, int slot, size_t offset, const uint32_t *d_scalars, size_t n, AffPt *out, cudaStream_t on) {
     SrsSlot &s = ctx->slots[slot];
+    struct StreamSwap { // the engine's main stream for this call
+        MsmEngine &e;
+        cudaStream_t saved;
+        StreamSwap(MsmEngine &eng, cudaStream_t s_) : e(eng), saved(eng.stream) {
+            if (s_) e.stream = s_;
+        }
+        ~StreamSwap() { e.stream = saved; }
+    } swap(ctx->msm, on);
     const bool want = ctx->msm_tables && s.n >= ctx->msm_tables_min && n >= s.n / 2 && !ctx->msm.force_window_bits;
     if (want && !s.table_ok && !s.table_failed) {
         const int W = ctx->msm_table_windows ? ctx->msm_table_windows : choose_table_windows(s.n);

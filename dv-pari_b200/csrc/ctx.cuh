@@ -19,6 +19,8 @@ struct SrsSlot {
 struct dvp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr; // an MSM that overlaps work on `stream` runs here (dvp_prove)
+    cudaEvent_t ev_aux = nullptr;
     dvp::MsmEngine msm;
     SrsSlot slots[DVP_MAX_SRS_SLOTS];
     dvp::DevBuf bytes, small, scal, adhoc, commbuf;
@@ -31,7 +33,9 @@ struct dvp_ctx {
 };
 
 // sum_i scalars[i] * slot[offset + i] on the device of ctx (device scalars); uses the slot's tables when it has them
-int slot_msm(dvp_ctx *ctx, int slot, size_t offset, const uint32_t *d_scalars, size_t n, dvp::AffPt *out);
+// `on` = the stream the scalars were produced on and the MSM is ordered after (default: the context's stream)
+int slot_msm(dvp_ctx *ctx, int slot, size_t offset, const uint32_t *d_scalars, size_t n, dvp::AffPt *out,
+             cudaStream_t on = nullptr);
 
 // comm.cu
 int comm_all_gather(dvp_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 #include <vector>
 #include "../../include/dvpari.h"
 #include "ctx.cuh"
@@ -877,21 +878,34 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
         if (rcg) return rcg;
     }
     cudaEventRecord(ev_h2d, st);
-    int64_t bad = -1;
-    int rc = r1cs_eval_device(r, d, w, a, b, c, iv, &bad);
-    if (rc) return rc;
-    cudaEventRecord(ev[1], st);
-    // commitment to the witness, proving.rs:462-463
-    AffPt msm_gm, msm_q, kzg;
     const int W = ctx->world, R = ctx->rank;
     size_t wlo, whi, qlo, qhi, klo, khi;
     dvp_shard_range(r->nwires, R, W, &wlo, &whi);
     dvp_shard_range(n, R, W, &qlo, &qhi);
     dvp_shard_range(4 * n, R, W, &klo, &khi);
-    AffPt part;
-    if ((rc = slot_msm(ctx, p->slot_gm, 0, (const uint32_t *)(w + wlo), whi - wlo, &part))) return rc;
-    if ((rc = comm_fold_points(ctx, part, &msm_gm))) return rc;
-    cudaEventRecord(ev[2], st);
+    // The commitment to the witness (proving.rs:462-463) depends on the assignment only: it runs on its own streams
+    // from a helper thread while this thread evaluates the rows, extends and forms the quotient, so the latency-bound
+    // phases of the MSM are filled with the Fr-side work.
+    AffPt msm_gm, msm_q, kzg, part, part_gm;
+    int rc_gm = 0;
+    CKP(cudaEventRecord(ctx->ev_aux, st));
+    std::thread gm_thread([&] {
+        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_aux, 0) != cudaSuccess) {
+            rc_gm = DVP_ERR_CUDA;
+            return;
+        }
+        rc_gm = slot_msm(ctx, p->slot_gm, 0, (const uint32_t *)(w + wlo), whi - wlo, &part_gm, ctx->aux_stream);
+    });
+    struct Joiner {
+        std::thread &t;
+        ~Joiner() {
+            if (t.joinable()) t.join();
+        }
+    } joiner{gm_thread};
+    int64_t bad = -1;
+    int rc = r1cs_eval_device(r, d, w, a, b, c, iv, &bad);
+    if (rc) return rc;
+    cudaEventRecord(ev[1], st);
     // extend a, b, c to D' (i' in closed form), proving.rs:475-482
     CKP(cudaMemcpyAsync(a2, a, 3 * n * sizeof(fr), cudaMemcpyDeviceToDevice, st));
     if (W == 1) {
@@ -914,6 +928,10 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     k_quotient<<<cdivp(n, 128), 128, 0, st>>>(a2, b2, c2, i2, d->z_vals2inv.as<fr>(), (uint32_t)n, q);
     CKP(cudaGetLastError());
     cudaEventRecord(ev[3], st);
+    gm_thread.join();
+    if (rc_gm) return rc_gm;
+    if ((rc = comm_fold_points(ctx, part_gm, &msm_gm))) return rc;
+    cudaEventRecord(ev[2], st);
     if ((rc = slot_msm(ctx, p->slot_gq, 0, (const uint32_t *)(q + qlo), qhi - qlo, &part))) return rc;
     if ((rc = comm_fold_points(ctx, part, &msm_q))) return rc;
     cudaEventRecord(ev[4], st);
@@ -968,7 +986,13 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     host::encode30(proof + 30, kzg);
     fr_to_le29_host(proof + 60, a0);
     fr_to_le29_host(proof + 89, b0);
-    for (int i = 0; i < 6; i++) cudaEventElapsedTime(&p->ms[i], ev[i], ev[i + 1]);
+    // stream order of the events: 0 (h2d) r1cs 1 extend+quotient 3 [wait for the g_m MSM] 2 msm g_q 4 .. 5 msm g_k 6
+    cudaEventElapsedTime(&p->ms[0], ev[0], ev[1]);
+    cudaEventElapsedTime(&p->ms[2], ev[1], ev[3]);
+    cudaEventElapsedTime(&p->ms[1], ev[3], ev[2]); // the part of the g_m MSM that was not hidden behind the Fr-side work
+    cudaEventElapsedTime(&p->ms[3], ev[2], ev[4]);
+    cudaEventElapsedTime(&p->ms[4], ev[4], ev[5]);
+    cudaEventElapsedTime(&p->ms[5], ev[5], ev[6]);
     cudaEventElapsedTime(&p->ms[6], ev[0], ev_h2d); // witness upload, part of ms[0]
     p->ms[0] -= p->ms[6];
     cudaEventDestroy(ev_h2d);
