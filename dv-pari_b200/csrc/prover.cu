@@ -178,6 +178,7 @@ __device__ __forceinline__ fr29 fr29_load(const fr *p) {
     for (int k = 0; k < 8; k++) r.l[k] = t.v[k];
     return r;
 }
+template <int NP>
 __global__ void __launch_bounds__(256)
     k_extend_level(fr *__restrict__ data, uint32_t n, uint32_t h, const fr *__restrict__ mats, int npoly,
                    size_t stride) {
@@ -185,13 +186,24 @@ __global__ void __launch_bounds__(256)
     if (g >= (n >> 1)) return;
     const uint32_t j = g % h, s = g / h;
     const uint32_t i0 = s * 2 * h + j, i1 = i0 + h;
+    // all loads of the thread are issued before the first product (NP polynomials share the matrix)
+    fr x0[NP], x1[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        if (p < npoly) {
+            x0[p] = fr_load(&data[(size_t)p * stride + i0]);
+            x1[p] = fr_load(&data[(size_t)p * stride + i1]);
+        }
+    }
     const fr29 m0 = fr29_load(&mats[4 * j]), m1 = fr29_load(&mats[4 * j + 1]);
     const fr29 m2 = fr29_load(&mats[4 * j + 2]), m3 = fr29_load(&mats[4 * j + 3]);
-    for (int p = 0; p < npoly; p++) {
-        fr *d = data + (size_t)p * stride;
-        const fr29 x0 = fr29_from_fr(fr_load(&d[i0])), x1 = fr29_from_fr(fr_load(&d[i1]));
-        fr_store(&d[i0], fr_from_fr29(fr29_dot2(m0, x0, m1, x1)));
-        fr_store(&d[i1], fr_from_fr29(fr29_dot2(m2, x0, m3, x1)));
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        if (p < npoly) {
+            const fr29 a0 = fr29_from_fr(x0[p]), a1 = fr29_from_fr(x1[p]);
+            fr_store(&data[(size_t)p * stride + i0], fr_from_fr29(fr29_dot2(m0, a0, m1, a1)));
+            fr_store(&data[(size_t)p * stride + i1], fr_from_fr29(fr29_dot2(m2, a0, m3, a1)));
+        }
     }
 }
 
@@ -575,10 +587,15 @@ int dvp_domain_vanish_at(dvp_domain *d, int shift, const uint64_t x_mont[4], uin
 static int extend_device(dvp_domain *d, fr *data, int npoly, size_t stride) {
     cudaStream_t st = d->ctx->stream;
     const uint32_t n = d->n;
-    for (int k = 0; k < d->levels; k++)
-        k_extend_level<<<cdivp(n / 2, 256), 256, 0, st>>>(data, n, n >> (k + 1), d->dec[k].as<fr>(), npoly, stride);
-    for (int k = d->levels - 1; k >= 0; k--)
-        k_extend_level<<<cdivp(n / 2, 256), 256, 0, st>>>(data, n, n >> (k + 1), d->rec[k].as<fr>(), npoly, stride);
+    // polynomials in groups of at most 3 (the prover's a, b, c) share each matrix read
+    for (int p0 = 0; p0 < npoly; p0 += 3) {
+        const int np = std::min(3, npoly - p0);
+        fr *base = data + (size_t)p0 * stride;
+        for (int k = 0; k < d->levels; k++)
+            k_extend_level<3><<<cdivp(n / 2, 256), 256, 0, st>>>(base, n, n >> (k + 1), d->dec[k].as<fr>(), np, stride);
+        for (int k = d->levels - 1; k >= 0; k--)
+            k_extend_level<3><<<cdivp(n / 2, 256), 256, 0, st>>>(base, n, n >> (k + 1), d->rec[k].as<fr>(), np, stride);
+    }
     CKP(cudaGetLastError());
     return 0;
 }
