@@ -380,6 +380,8 @@ struct dvp_r1cs {
     dvp_ctx *ctx = nullptr;
     R1csDev dev;
     DevBuf bufs[10];
+    DevBuf tbufs[9]; // transposed matrices (colptr, row, coeff id per matrix), built on the first setup
+    bool t_ready = false;
     size_t nwires = 0;
 };
 struct dvp_prover {
@@ -675,6 +677,7 @@ void dvp_r1cs_destroy(dvp_r1cs *r) {
     if (!r) return;
     cudaSetDevice(r->ctx->device);
     for (auto &b : r->bufs) b.release();
+    for (auto &b : r->tbufs) b.release();
     delete r;
 }
 
@@ -1035,3 +1038,278 @@ int dvp_prove_last_times(dvp_prover *p, float ms[7]) {
     return DVP_OK;
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Setup on the device: the discrete logs of the SRS from a trapdoor
+// (SRS::verifier_runs_setup / compute_srs_matrices / accumulate_m_values, /root/reference/src/srs.rs:53-167,177-361),
+// then the points by the batched fixed-base multiplication (MsmEngine::mulgen).  The reference reaches
+// L_i(tau), Z_D(tau), the barycentric weights and Z on the other half-domain through vanish/exit/enter
+// (O(n log^2 n), "2 hrs+"); here they come from the chain rule in O(n log n) like the prover precomputes.
+// ------------------------------------------------------------------------------------------------
+// per leaf j = 2i + sh:  L_i^S(tau) = Z_S(tau) / ((tau - s_i) Z'_S(s_i)) for S = D (sh = 0) or D' (sh = 1), and the
+// unified-domain basis value ltl[j] = L_i^S(tau) Z_other(tau) / Z_other(s_i)   (ec_fft.rs:340-390,424-450)
+__global__ void k_setup_lagrange(const fr *__restrict__ dinv /* 1/(leaf - tau) */, const fr *__restrict__ bw0,
+                                 const fr *__restrict__ bw1, const fr *__restrict__ zo_inv0, const fr *__restrict__ zo_inv1,
+                                 fr zt0, fr zt1, uint32_t n2, fr *__restrict__ lt0, fr *__restrict__ lt1, fr *__restrict__ ltl) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n2) return;
+    const uint32_t i = j >> 1, sh = j & 1;
+    const fr ninv = fr_neg(fr_load(&dinv[j])); // 1/(tau - s)
+    const fr l = fr_mul(fr_mul(sh ? zt1 : zt0, fr_load(sh ? &bw1[i] : &bw0[i])), ninv);
+    fr_store(sh ? &lt1[i] : &lt0[i], l);
+    fr_store(&ltl[j], fr_mul(fr_mul(l, sh ? zt0 : zt1), fr_load(sh ? &zo_inv0[i] : &zo_inv1[i])));
+}
+
+// accumulate_m_values (srs.rs:53-84) as a transposed product: one warp per wire over the three column lists
+struct R1csT {
+    const uint32_t *colptr[3];
+    const uint32_t *row[3];
+    const uint32_t *cid[3];
+};
+__global__ void __launch_bounds__(128)
+    k_setup_mvals(R1csT t, const fr *__restrict__ coeffs, const fr *__restrict__ lt0, fr delta, fr delta2, fr eps,
+                  uint32_t nwires, fr *__restrict__ sc_m) {
+    const uint32_t wire = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wire >= nwires) return;
+    fr tot = fr_zero();
+    for (int which = 0; which < 3; which++) {
+        fr acc = fr_zero();
+        for (uint32_t p = t.colptr[which][wire] + lane; p < t.colptr[which][wire + 1]; p += 32)
+            acc = fr_add(acc, fr_mul(fr_load(&coeffs[t.cid[which][p]]), fr_load(&lt0[t.row[which][p]])));
+        if (which == 1) acc = fr_mul(acc, delta);
+        if (which == 2) acc = fr_mul(acc, delta2);
+        tot = fr_add(tot, acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        fr other;
+#pragma unroll
+        for (int k = 0; k < 8; k++) other.v[k] = __shfl_down_sync(0xffffffffu, tot.v[k], o);
+        tot = fr_add(tot, other);
+    }
+    if (lane == 0) fr_store(&sc_m[wire], fr_mul(tot, eps));
+}
+// Vandermonde block (gnark_r1cs.rs:357-383): partial sums of d_i^j L_i(tau), j < k (k <= 8), one set per block
+__global__ void __launch_bounds__(256)
+    k_setup_vand(const fr *__restrict__ leaves, const fr *__restrict__ lt0, uint32_t n, uint32_t k, fr *__restrict__ part) {
+    __shared__ fr sh[256];
+    fr acc[8];
+    for (uint32_t j = 0; j < 8; j++) acc[j] = fr_zero();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const fr d = fr_load(&leaves[2 * i]);
+        fr pw = fr_load(&lt0[i]);
+        for (uint32_t j = 0; j < k; j++) {
+            acc[j] = fr_add(acc[j], pw);
+            pw = fr_mul(pw, d);
+        }
+    }
+    for (uint32_t j = 0; j < k; j++) {
+        sh[threadIdx.x] = acc[j];
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) sh[threadIdx.x] = fr_add(sh[threadIdx.x], sh[threadIdx.x + o]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) part[blockIdx.x * 8 + j] = sh[0];
+        __syncthreads();
+    }
+}
+// sc_q[i] = f L'_i(tau);  sc_k = L(tau) | delta L(tau) | delta^2 ltl   (srs.rs:112-167)
+__global__ void k_setup_qk(const fr *__restrict__ lt0, const fr *__restrict__ lt1, const fr *__restrict__ ltl, fr f, fr delta,
+                           fr delta2, uint32_t n, fr *__restrict__ sc_q, fr *__restrict__ sc_k) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fr l0 = fr_load(&lt0[i]);
+    fr_store(&sc_q[i], fr_mul(f, fr_load(&lt1[i])));
+    fr_store(&sc_k[i], l0);
+    fr_store(&sc_k[n + i], fr_mul(l0, delta));
+    fr_store(&sc_k[2 * n + 2 * i], fr_mul(fr_load(&ltl[2 * i]), delta2));
+    fr_store(&sc_k[2 * n + 2 * i + 1], fr_mul(fr_load(&ltl[2 * i + 1]), delta2));
+}
+
+// the isogeny images of the leaves (layer k has n2 >> k points); layers[0] = the domain's own leaves
+static int build_layers(dvp_domain *d, std::vector<DevBuf> &store, std::vector<DevBuf *> &layers) {
+    cudaStream_t st = d->ctx->stream;
+    store.resize(d->log_n2);
+    layers.resize(d->log_n2);
+    layers[0] = &d->leaves;
+    int rc;
+    for (int k = 0; k + 1 < d->log_n2; k++) {
+        const uint32_t half = d->n2 >> (k + 1);
+        if ((rc = store[k + 1].reserve((size_t)half * sizeof(fr)))) return rc;
+        layers[k + 1] = &store[k + 1];
+        k_dom_next_layer<<<cdivp(half, 128), 128, 0, st>>>(layers[k]->as<fr>(), half, d->x0[k], d->t[k], layers[k + 1]->as<fr>());
+    }
+    CKP(cudaGetLastError());
+    return 0;
+}
+
+static int setup_scalars_device(dvp_r1cs *r, dvp_domain *d, const fr &tau, const fr &delta, const fr &eps, fr *sc_m,
+                                fr *sc_q, fr *sc_k) {
+    dvp_ctx *ctx = r->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = d->n, n2 = d->n2;
+    const size_t nw = r->nwires;
+    int rc = 0;
+    const fr zt0 = vanish_at_host(d, 0, tau), zt1 = vanish_at_host(d, 1, tau);
+    if (fr_is_zero(zt0) || fr_is_zero(zt1)) return DVP_ERR_ALPHA_IN_DOMAIN; // tau must not be a domain point
+    const fr delta2 = fr_mul(delta, delta);
+    std::vector<DevBuf> tmp(12);
+    auto cleanup = [&](int code) {
+        for (auto &b : tmp) b.release();
+        return code;
+    };
+    DevBuf &bw1 = tmp[0], &zo1 = tmp[1], &work = tmp[2], &dinv = tmp[3], &pre = tmp[4], &tot = tmp[5], &pre2 = tmp[6],
+           &tot2 = tmp[7], &lt0 = tmp[8], &lt1 = tmp[9], &ltl = tmp[10], &part = tmp[11];
+    const uint32_t ng = cdivp(n2, FRB), ng2 = cdivp(ng, FRB);
+    if ((rc = bw1.reserve((size_t)n * 32)) || (rc = zo1.reserve((size_t)n * 32)) || (rc = work.reserve((size_t)n * 32)) ||
+        (rc = dinv.reserve((size_t)n2 * 32)) || (rc = pre.reserve((size_t)n2 * 32)) || (rc = tot.reserve((size_t)ng * 32)) ||
+        (rc = pre2.reserve((size_t)ng * 32)) || (rc = tot2.reserve(((size_t)ng2 + 2) * 32)) || (rc = lt0.reserve((size_t)n * 32)) ||
+        (rc = lt1.reserve((size_t)n * 32)) || (rc = ltl.reserve((size_t)n2 * 32)) || (rc = part.reserve(592 * 8 * 32)))
+        return cleanup(rc);
+    {
+        // 1/Z'_{D'}(d'_i) and 1/Z_{D'}(d_i): the chain rule on the odd leaves (the even ones are domain precomputes)
+        std::vector<DevBuf> store;
+        std::vector<DevBuf *> layers;
+        if ((rc = build_layers(d, store, layers)) || (rc = run_chain(d, layers, 1, 1, bw1.as<fr>(), work.as<fr>())) ||
+            (rc = run_chain(d, layers, 1, 0, zo1.as<fr>(), work.as<fr>()))) {
+            for (auto &b : store) b.release();
+            return cleanup(rc);
+        }
+        cudaStreamSynchronize(st);
+        for (auto &b : store) b.release();
+    }
+    // 1/(leaf - tau) for all 2n leaves
+    const fr *leaves = d->leaves.as<fr>();
+    k_frb_up<<<cdivp(ng, 128), 128, 0, st>>>(leaves, tau, n2, pre.as<fr>(), tot.as<fr>());
+    k_frb_up2<<<cdivp(ng2, 64), 64, 0, st>>>(tot.as<fr>(), ng, pre2.as<fr>(), tot2.as<fr>());
+    k_frb_down2<<<cdivp(ng2, 64), 64, 0, st>>>(tot.as<fr>(), ng, pre2.as<fr>(), tot2.as<fr>());
+    k_frb_down<<<cdivp(ng, 128), 128, 0, st>>>(leaves, tau, n2, pre.as<fr>(), tot.as<fr>(), dinv.as<fr>());
+    k_setup_lagrange<<<cdivp(n2, 128), 128, 0, st>>>(dinv.as<fr>(), d->bar_wts.as<fr>(), bw1.as<fr>(), d->z_vals2inv.as<fr>(),
+                                                     zo1.as<fr>(), zt0, zt1, n2, lt0.as<fr>(), lt1.as<fr>(), ltl.as<fr>());
+    if (cudaGetLastError() != cudaSuccess) return cleanup(DVP_ERR_CUDA);
+    // transposed matrices (built once per circuit)
+    if (!r->t_ready) {
+        std::vector<uint32_t> rowptr, wire, cid, colptr(nw + 1), trow, tcid;
+        for (int w = 0; w < 3; w++) {
+            const size_t nrows = r->dev.nrows;
+            rowptr.resize(nrows + 1);
+            if (cudaMemcpy(rowptr.data(), r->dev.rowptr[w], (nrows + 1) * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+                return cleanup(DVP_ERR_CUDA);
+            const size_t nnz = rowptr[nrows];
+            wire.resize(nnz ? nnz : 1);
+            cid.resize(nnz ? nnz : 1);
+            if (nnz && (cudaMemcpy(wire.data(), r->dev.wire[w], nnz * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                        cudaMemcpy(cid.data(), r->dev.coeff[w], nnz * 4, cudaMemcpyDeviceToHost) != cudaSuccess))
+                return cleanup(DVP_ERR_CUDA);
+            std::fill(colptr.begin(), colptr.end(), 0u);
+            for (size_t p = 0; p < nnz; p++) colptr[wire[p] + 1]++;
+            for (size_t c = 0; c < nw; c++) colptr[c + 1] += colptr[c];
+            trow.assign(nnz ? nnz : 1, 0u);
+            tcid.assign(nnz ? nnz : 1, 0u);
+            std::vector<uint32_t> cur(colptr.begin(), colptr.end() - 1);
+            for (size_t row = 0; row < nrows; row++)
+                for (uint32_t p = rowptr[row]; p < rowptr[row + 1]; p++) {
+                    const uint32_t pos = cur[wire[p]]++;
+                    trow[pos] = (uint32_t)row;
+                    tcid[pos] = cid[p];
+                }
+            DevBuf *b = &r->tbufs[3 * w];
+            if ((rc = b[0].reserve((nw + 1) * 4)) || (rc = b[1].reserve(trow.size() * 4)) || (rc = b[2].reserve(tcid.size() * 4)))
+                return cleanup(rc);
+            cudaMemcpy(b[0].p, colptr.data(), (nw + 1) * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(b[1].p, trow.data(), trow.size() * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(b[2].p, tcid.data(), tcid.size() * 4, cudaMemcpyHostToDevice);
+        }
+        r->t_ready = true;
+    }
+    R1csT t;
+    for (int w = 0; w < 3; w++) {
+        t.colptr[w] = r->tbufs[3 * w].as<uint32_t>();
+        t.row[w] = r->tbufs[3 * w + 1].as<uint32_t>();
+        t.cid[w] = r->tbufs[3 * w + 2].as<uint32_t>();
+    }
+    k_setup_mvals<<<cdivp(nw * 32, 128), 128, 0, st>>>(t, r->dev.coeffs, lt0.as<fr>(), delta, delta2, eps, (uint32_t)nw, sc_m);
+    // public wires: minus delta^2 sum_i d_i^j L_i(tau)  (the D block appended to the O rows)
+    const uint32_t k = r->dev.k;
+    if (k > 8) return cleanup(DVP_ERR_BAD_ARG);
+    if (k) {
+        const int nblk = 592;
+        k_setup_vand<<<nblk, 256, 0, st>>>(leaves, lt0.as<fr>(), n, k, part.as<fr>());
+        std::vector<fr> hp((size_t)nblk * 8), cur(k);
+        if (cudaMemcpyAsync(hp.data(), part.p, hp.size() * 32, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(cur.data(), sc_m + 1, k * 32, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess)
+            return cleanup(DVP_ERR_CUDA);
+        for (uint32_t j = 0; j < k; j++) {
+            fr s = fr_zero();
+            for (int b = 0; b < nblk; b++) s = fr_add(s, hp[(size_t)b * 8 + j]);
+            cur[j] = fr_sub(cur[j], fr_mul(fr_mul(s, delta2), eps));
+        }
+        if (cudaMemcpyAsync(sc_m + 1, cur.data(), k * 32, cudaMemcpyHostToDevice, st) != cudaSuccess) return cleanup(DVP_ERR_CUDA);
+        cudaStreamSynchronize(st);
+    }
+    const fr f = fr_mul(fr_mul(zt0, delta2), eps);
+    k_setup_qk<<<cdivp(n, 128), 128, 0, st>>>(lt0.as<fr>(), lt1.as<fr>(), ltl.as<fr>(), f, delta, delta2, n, sc_q, sc_k);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return cleanup(DVP_ERR_CUDA);
+    return cleanup(DVP_OK);
+}
+
+extern "C" {
+
+// The discrete logs of g_m / g_q / g_k for a trapdoor (tau, delta, epsilon), host buffers (nwires, n, 4n elements).
+int dvp_setup_scalars(dvp_r1cs *r, dvp_domain *d, const uint64_t trapdoor_mont[12], uint64_t *sc_m, uint64_t *sc_q,
+                      uint64_t *sc_k) {
+    if (!r || !d || !trapdoor_mont || !sc_m || !sc_q || !sc_k) return DVP_ERR_BAD_ARG;
+    if (d->n != r->dev.n) return DVP_ERR_LENGTH_MISMATCH;
+    CKP(cudaSetDevice(r->ctx->device));
+    fr td[3];
+    memcpy(td, trapdoor_mont, 96);
+    const size_t n = d->n, nw = r->nwires;
+    DevBuf out;
+    int rc = out.reserve((nw + 5 * n) * 32);
+    if (rc) return rc;
+    fr *o = out.as<fr>();
+    rc = setup_scalars_device(r, d, td[0], td[1], td[2], o, o + nw, o + nw + n);
+    if (!rc) {
+        cudaMemcpy(sc_m, o, nw * 32, cudaMemcpyDeviceToHost);
+        cudaMemcpy(sc_q, o + nw, n * 32, cudaMemcpyDeviceToHost);
+        cudaMemcpy(sc_k, o + nw + n, 4 * n * 32, cudaMemcpyDeviceToHost);
+    }
+    out.release();
+    return rc;
+}
+
+// SRS::verifier_runs_setup with the artifacts left resident: slot_gm / slot_gq / slot_gk receive this rank's range
+// of g_m (nwires points), g_q (n) and g_k_0|g_k_1|g_k_2 (4n), ready for dvp_prover_create.
+int dvp_setup(dvp_r1cs *r, dvp_domain *d, const uint64_t trapdoor_mont[12], int slot_gm, int slot_gq, int slot_gk) {
+    if (!r || !d || !trapdoor_mont) return DVP_ERR_BAD_ARG;
+    if (d->n != r->dev.n) return DVP_ERR_LENGTH_MISMATCH;
+    dvp_ctx *ctx = r->ctx;
+    const int slots[3] = {slot_gm, slot_gq, slot_gk};
+    for (int s : slots)
+        if (s < 0 || s >= DVP_MAX_SRS_SLOTS) return DVP_ERR_BAD_ARG;
+    CKP(cudaSetDevice(ctx->device));
+    fr td[3];
+    memcpy(td, trapdoor_mont, 96);
+    const size_t n = d->n, nw = r->nwires;
+    DevBuf out;
+    int rc = out.reserve((nw + 5 * n) * 32);
+    if (rc) return rc;
+    fr *o = out.as<fr>();
+    rc = setup_scalars_device(r, d, td[0], td[1], td[2], o, o + nw, o + nw + n);
+    const size_t tot[3] = {nw, n, 4 * n};
+    const fr *base[3] = {o, o + nw, o + nw + n};
+    for (int i = 0; i < 3 && !rc; i++) {
+        size_t lo, hi;
+        dvp_shard_range(tot[i], ctx->rank, ctx->world, &lo, &hi);
+        SrsSlot &s = ctx->slots[slots[i]];
+        s.invalidate();
+        if ((rc = s.buf.reserve((hi - lo ? hi - lo : 1) * sizeof(AffPt)))) break;
+        s.n = hi - lo;
+        if (hi > lo) rc = ctx->msm.mulgen((const uint32_t *)(base[i] + lo), hi - lo, s.buf.as<AffPt>());
+    }
+    out.release();
+    return rc;
+}
+
+} // extern "C"

@@ -108,6 +108,8 @@ def lib():
         L.dvp_r1cs_destroy.restype = None
         L.dvp_r1cs_eval.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int64)]
         L.dvp_r1cs_synth_solve.argtypes = [vp, vp, C.c_uint]
+        L.dvp_setup_scalars.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.dvp_setup.argtypes = [vp, vp, vp, i32, i32, i32]
         L.dvp_prover_create.argtypes = [vp, vp, vp, i32, i32, i32, C.POINTER(vp)]
         L.dvp_prover_destroy.argtypes = [vp]
         L.dvp_prover_destroy.restype = None
@@ -441,6 +443,22 @@ class R1CSInstance:
         if rc != OK:
             raise DvpError(rc, f"constraint {bad.value}")
         return outs
+
+
+def setup_scalars(r1cs, dom, trapdoor_ints):
+    """Discrete logs of g_m / g_q / g_k for the trapdoor (tau, delta, epsilon) (srs.rs:53-167), computed on the device."""
+    td = fr_to_mont(list(trapdoor_ints))
+    sc_m = np.zeros((r1cs.nwires, 4), dtype=np.uint64)
+    sc_q = np.zeros((r1cs.n, 4), dtype=np.uint64)
+    sc_k = np.zeros((4 * r1cs.n, 4), dtype=np.uint64)
+    _ck(lib().dvp_setup_scalars(r1cs._h, dom._h, _ptr(td), _ptr(sc_m), _ptr(sc_q), _ptr(sc_k)), "dvp_setup_scalars")
+    return sc_m, sc_q, sc_k
+
+
+def setup(r1cs, dom, trapdoor_ints, slot_gm=0, slot_gq=1, slot_gk=2):
+    """SRS::verifier_runs_setup (srs.rs:177-361) with the SRS left resident in the slots (this rank's ranges)."""
+    td = fr_to_mont(list(trapdoor_ints))
+    _ck(lib().dvp_setup(r1cs._h, dom._h, _ptr(td), slot_gm, slot_gq, slot_gk), "dvp_setup")
 
 
 class Prover:

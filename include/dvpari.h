@@ -173,6 +173,17 @@ int dvp_r1cs_eval(dvp_r1cs *r1cs, dvp_domain *dom, const uint64_t *assignment, u
 int dvp_r1cs_synth_solve(dvp_r1cs *r1cs, uint64_t *assignment /* nwires x 4, in place */, unsigned nlevels);
 
 /*
+ * Setup on the device (SRS::verifier_runs_setup, src/srs.rs:177-361; compute_srs_matrices / accumulate_m_values,
+ * src/srs.rs:53-167).  trapdoor_mont = tau | delta | epsilon, 3 x 4 u64 Montgomery limbs.  L_i(tau), Z_D(tau), the
+ * barycentric weights and Z on the other half-domain come from the chain rule of the isogeny tower in O(n log n)
+ * instead of vanish / exit / enter; the points from the batched fixed-base multiplication.
+ */
+int dvp_setup_scalars(dvp_r1cs *r1cs, dvp_domain *dom, const uint64_t trapdoor_mont[12], uint64_t *sc_m /* nwires x 4 */,
+                      uint64_t *sc_q /* n x 4 */, uint64_t *sc_k /* 4n x 4 */);
+/* the SRS itself, left resident: the slots receive this rank's range of g_m, g_q and g_k_0|g_k_1|g_k_2 */
+int dvp_setup(dvp_r1cs *r1cs, dvp_domain *dom, const uint64_t trapdoor_mont[12], int slot_gm, int slot_gq, int slot_gk);
+
+/*
  * Proof::prove(cache_dir, public_inputs, private_inputs) (src/proving.rs:426-688) with the artifacts resident:
  * SRS slots hold g_m (nwires points), g_q (n) and g_k_0|g_k_1|g_k_2 (4n).
  * proof118 = commit_p (30) | kzg_k (30) | a0 (29 bytes LE) | b0 (29 bytes LE)  -- the fields of `Proof`

@@ -39,24 +39,31 @@ def test_mulgen_matches_oracle(ctx, oracle):
     ctx.srs_free(5)
 
 
-def _synth_case(ctx, O, lg_n, compare_with_oracle_prover):
+def _synth_case(ctx, O, lg_n, compare_with_oracle_prover, device_setup=False):
     circ = synth.synth_r1cs(lg_n, seed=0xD5A10003 + lg_n)
     inst = dvpari.R1CSInstance(ctx, circ["nrows"], circ["k"], circ["nwires"], circ["rowptr"], circ["wire"],
                                circ["coeff"], circ["coeffs_mont"])
     w = inst.synth_solve(synth.synth_assignment(circ), circ["nlevels"])
-    r1cs = O.R1CS.from_arrays(circ["coeffs_mont"], circ["rowptr"], circ["wire"], circ["coeff"], circ["nrows"],
-                              circ["k"], circ["nwires"])
-    od = O.Domain(lg_n + 1)
-    # the device-solved witness satisfies every row according to the oracle
-    _, bad = O.r1cs_eval(r1cs, od, w)
-    assert bad == -1
     rnd = random.Random(lg_n)
-    td = O.trapdoor(rnd.randrange(1, P), rnd.randrange(1, P), rnd.randrange(1, P))
-    sc_m, sc_q, sc_k = O.setup_scalars(r1cs, od, td)
-    ctx.srs_mulgen(0, sc_m)
-    ctx.srs_mulgen(1, sc_q)
-    ctx.srs_mulgen(2, sc_k)
+    tdi = [rnd.randrange(1, P) for _ in range(3)]
+    td = O.trapdoor(*tdi)
     gd = dvpari.Domain(ctx, lg_n + 1)
+    r1cs = od = None
+    if device_setup:
+        # SRS from the trapdoor entirely on the device (validated against the oracle in test_device_setup_matches_oracle);
+        # nothing of size n runs on the CPU, the oracle's O(1) verifier decides
+        dvpari.setup(inst, gd, tdi, 0, 1, 2)
+    else:
+        r1cs = O.R1CS.from_arrays(circ["coeffs_mont"], circ["rowptr"], circ["wire"], circ["coeff"], circ["nrows"],
+                                  circ["k"], circ["nwires"])
+        od = O.Domain(lg_n + 1)
+        # the device-solved witness satisfies every row according to the oracle
+        _, bad = O.r1cs_eval(r1cs, od, w)
+        assert bad == -1
+        sc_m, sc_q, sc_k = O.setup_scalars(r1cs, od, td)
+        ctx.srs_mulgen(0, sc_m)
+        ctx.srs_mulgen(1, sc_q)
+        ctx.srs_mulgen(2, sc_k)
     prover = dvpari.Prover(ctx, gd, inst, 0, 1, 2)
     k = circ["k"]
     proof = prover.prove(w[1:1 + k], w[1 + k:])
@@ -68,6 +75,10 @@ def _synth_case(ctx, O, lg_n, compare_with_oracle_prover):
     assert not O.verify(td, pub, bytes(bad_proof))
     assert not O.verify(td, [pub[0], (pub[1] + 1) % P], proof)
     if compare_with_oracle_prover:
+        if r1cs is None:
+            r1cs = O.R1CS.from_arrays(circ["coeffs_mont"], circ["rowptr"], circ["wire"], circ["coeff"], circ["nrows"],
+                                      circ["k"], circ["nwires"])
+            od = O.Domain(lg_n + 1)
         srs = O.Srs(r1cs, od, td)
         # device-generated SRS == oracle SRS, spot-checked on g_q, and byte-equal proofs
         assert ctx.srs_read(1, 0, min(64, circ["n"])).tobytes() == srs.g_q30()[: min(64, circ["n"])].tobytes()
@@ -89,9 +100,19 @@ def test_synth_prove_2_14_is_bit_exact(ctx, oracle):
 
 
 def test_synth_prove_2_18_verifies(ctx, oracle):
-    """262 144 constraints, ~2.7 M terms; set DVP_FULL_LG=20 for the 2^20 configuration (slow CPU-side setup)."""
+    """262 144 constraints with the oracle's setup scalars.  DVP_FULL_LG=20 / 22 runs larger ones this way (the
+    CPU-side scalars take ~0.5 / ~2 minutes); DVP_FULL_COMPARE=1 also runs the oracle's prover and compares the bytes
+    (done once at 2^20: profiles/r1c_fullsize_prove_2_20_byte_equal.log)."""
     lg = int(os.environ.get("DVP_FULL_LG", "18"))
-    t = _synth_case(ctx, oracle, lg, False)
+    t = _synth_case(ctx, oracle, lg, os.environ.get("DVP_FULL_COMPARE", "0") == "1")
+    print(f"prove 2^{lg}: " + ", ".join(f"{k} {v:.2f} ms" for k, v in t.items()))
+
+
+@pytest.mark.parametrize("lg", [20, 22])
+def test_synth_prove_full_size_device_setup_verifies(ctx, oracle, lg):
+    """BASELINE configurations #4 / #5 (2^20 and 2^22 constraints, ~10.9 M / ~43.6 M terms): setup, witness and proof
+    all on the device, accepted by the oracle's verifier; tampered proofs and public inputs are rejected."""
+    t = _synth_case(ctx, oracle, lg, False, device_setup=True)
     print(f"prove 2^{lg}: " + ", ".join(f"{k} {v:.2f} ms" for k, v in t.items()))
 
 
@@ -138,3 +159,46 @@ def test_prove_from_artifact_files(ctx, oracle, tmp_path):
     prover.close(); inst.close(); inst2.close(); gd.close()
     for s in (4, 5, 6):
         ctx.srs_free(s)
+
+
+@pytest.mark.parametrize("lg", [4, 10, 13])
+def test_device_setup_matches_oracle(ctx, oracle, lg):
+    """dvp_setup_scalars / dvp_setup (srs.rs:53-167,177-361 on the device: chain rule for L_i(tau), transposed product
+    for accumulate_m_values, batched mulgen) against the oracle's setup: byte-equal scalars, an SRS the oracle's prover
+    would also produce, and a proof its verifier accepts."""
+    O = oracle
+    rnd = random.Random(900 + lg)
+    tdi = [rnd.randrange(1, P) for _ in range(3)]
+    td = O.trapdoor(*tdi)
+    if lg == 4:
+        r1cs, pub, priv = O.toy_r1cs()
+        circ = dict(nrows=r1cs.nrows, k=r1cs.k, nwires=r1cs.nwires, rowptr=r1cs.rowptr, wire=r1cs.wire, coeff=r1cs.coeff,
+                    coeffs_mont=r1cs.coeffs, n=r1cs.n)
+        w = O.mont_array([1] + pub + priv)
+        inst = dvpari.R1CSInstance(ctx, circ["nrows"], circ["k"], circ["nwires"], circ["rowptr"], circ["wire"],
+                                   circ["coeff"], circ["coeffs_mont"])
+        lg_n2 = r1cs.n.bit_length()
+    else:
+        circ = synth.synth_r1cs(lg, seed=lg, nlevels=8)
+        inst = dvpari.R1CSInstance(ctx, circ["nrows"], circ["k"], circ["nwires"], circ["rowptr"], circ["wire"],
+                                   circ["coeff"], circ["coeffs_mont"])
+        w = inst.synth_solve(synth.synth_assignment(circ), circ["nlevels"])
+        r1cs = O.R1CS.from_arrays(circ["coeffs_mont"], circ["rowptr"], circ["wire"], circ["coeff"], circ["nrows"],
+                                  circ["k"], circ["nwires"])
+        lg_n2 = lg + 1
+    od = O.Domain(lg_n2)
+    gd = dvpari.Domain(ctx, lg_n2)
+    want = O.setup_scalars(r1cs, od, td)
+    got = dvpari.setup_scalars(inst, gd, tdi)
+    for name, g, x in zip(("sc_m", "sc_q", "sc_k"), got, want):
+        assert g.tobytes() == x.tobytes(), name
+    dvpari.setup(inst, gd, tdi, 0, 1, 2)
+    srs = O.Srs(r1cs, od, td)
+    assert ctx.srs_read(0, 0, r1cs.nwires).tobytes() == srs.g_m30().tobytes()
+    assert ctx.srs_read(1, 0, r1cs.n).tobytes() == srs.g_q30().tobytes()
+    assert ctx.srs_read(2, 0, 4 * r1cs.n).tobytes() == srs.g_k30().tobytes()
+    prover = dvpari.Prover(ctx, gd, inst, 0, 1, 2)
+    k = r1cs.k
+    proof = prover.prove(w[1:1 + k], w[1 + k:])
+    assert O.verify(td, dvpari.fr_from_mont(w[1:1 + k]), proof)
+    prover.close(); inst.close(); gd.close()
