@@ -1313,3 +1313,96 @@ int dvp_setup(dvp_r1cs *r, dvp_domain *d, const uint64_t trapdoor_mont[12], int 
 }
 
 } // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// FFTree::enter (crate ecfft; reference call sites /root/reference/src/ec_fft.rs:317,411): coefficients of a
+// polynomial of degree < n -> its values on the n leaves of the tree (natural order).  Restated from the ECFFT
+// construction: P = U + x^(m) V with deg U, V < m; their values on the even leaves of the 2m-leaf tree are the
+// values on the m-leaf tree (same points), the odd leaves come from EXTEND, and the two halves are combined with
+// s^m.  Bottom-up over block sizes m = 1, 2, .., n/2; every level extends all n/m blocks in one pass because the
+// blocks tile the array exactly like the sub-problems of a larger extend.  O(n log^2 n).
+// ------------------------------------------------------------------------------------------------
+struct dvp_ecfft_plan {
+    dvp_ctx *ctx = nullptr;
+    int log_n = 0;
+    std::vector<dvp_domain *> dom; // dom[l] = tree with 2^l leaves, l = 2 .. log_n
+    DevBuf a, b, c;
+};
+
+// out block B (size 2m) from blocks 2B, 2B+1 (size m) of cur (values on the even leaves) and ext (odd leaves)
+__global__ void k_enter_combine(const fr *__restrict__ cur, const fr *__restrict__ ext, const fr *__restrict__ leaves,
+                                uint32_t leaf_stride, uint32_t n, uint32_t m, int log_m, fr *__restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; // index over n/2 (pair, i)
+    if (t >= (n >> 1)) return;
+    const uint32_t B = t / m, i = t % m;
+    const fr s0 = fr_load(&leaves[(size_t)(2 * i) * leaf_stride]), s1 = fr_load(&leaves[(size_t)(2 * i + 1) * leaf_stride]);
+    const fr p0 = fr_pow2k(s0, log_m), p1 = fr_pow2k(s1, log_m);
+    const size_t u = (size_t)(2 * B) * m + i, v = u + m;
+    fr_store(&out[(size_t)B * 2 * m + 2 * i], fr_add(fr_load(&cur[u]), fr_mul(p0, fr_load(&cur[v]))));
+    fr_store(&out[(size_t)B * 2 * m + 2 * i + 1], fr_add(fr_load(&ext[u]), fr_mul(p1, fr_load(&ext[v]))));
+}
+
+extern "C" {
+
+int dvp_ecfft_plan_create(dvp_ctx *ctx, unsigned log2_n, dvp_ecfft_plan **out) {
+    if (!ctx || !out || log2_n < 1 || log2_n > 27) return DVP_ERR_BAD_ARG;
+    *out = nullptr;
+    dvp_ecfft_plan *p = new dvp_ecfft_plan();
+    p->ctx = ctx;
+    p->log_n = (int)log2_n;
+    p->dom.assign(log2_n + 1, nullptr);
+    int rc = 0;
+    for (unsigned l = 2; l <= std::max(2u, log2_n) && !rc; l++) rc = dvp_domain_create(ctx, l, &p->dom[l]);
+    const size_t n = (size_t)1 << log2_n;
+    if (!rc && ((rc = p->a.reserve(n * 32)) || (rc = p->b.reserve(n * 32)) || (rc = p->c.reserve(n * 32)))) {
+    }
+    if (rc) {
+        dvp_ecfft_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return DVP_OK;
+}
+
+void dvp_ecfft_plan_destroy(dvp_ecfft_plan *p) {
+    if (!p) return;
+    for (auto d : p->dom) dvp_domain_destroy(d);
+    p->a.release();
+    p->b.release();
+    p->c.release();
+    delete p;
+}
+
+// coeffs (n x 4 u64 Montgomery, low degree first) -> evals on the n leaves x(C + i G_n), host buffers
+int dvp_ecfft_enter(dvp_ecfft_plan *p, const uint64_t *coeffs, uint64_t *evals) {
+    if (!p || !coeffs || !evals) return DVP_ERR_BAD_ARG;
+    dvp_ctx *ctx = p->ctx;
+    CKP(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = 1u << p->log_n;
+    fr *cur = p->a.as<fr>(), *ext = p->b.as<fr>(), *nxt = p->c.as<fr>();
+    CKP(cudaMemcpyAsync(cur, coeffs, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    for (int lm = 0; lm < p->log_n; lm++) {
+        const uint32_t m = 1u << lm;
+        // the tree with 2m leaves; for m = 1 its two leaves are the even leaves of the 4-leaf tree
+        dvp_domain *d = p->dom[std::max(2, lm + 1)];
+        const uint32_t leaf_stride = lm + 1 < 2 ? 2 : 1;
+        CKP(cudaMemcpyAsync(ext, cur, (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
+        if (m >= 2) {
+            for (int k = 0; k < d->levels; k++)
+                k_extend_level<3><<<cdivp(n / 2, 256), 256, 0, st>>>(ext, n, m >> (k + 1), d->dec[k].as<fr>(), 1, 0);
+            for (int k = d->levels - 1; k >= 0; k--)
+                k_extend_level<3><<<cdivp(n / 2, 256), 256, 0, st>>>(ext, n, m >> (k + 1), d->rec[k].as<fr>(), 1, 0);
+        }
+        k_enter_combine<<<cdivp(n / 2, 128), 128, 0, st>>>(cur, ext, d->leaves.as<fr>(), leaf_stride, n, m, lm, nxt);
+        CKP(cudaGetLastError());
+        fr *t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    CKP(cudaMemcpyAsync(evals, cur, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    CKP(cudaStreamSynchronize(st));
+    return DVP_OK;
+}
+
+} // extern "C"

@@ -103,6 +103,10 @@ def lib():
         L.dvp_domain_vanish_at.argtypes = [vp, i32, vp, vp]
         L.dvp_ecfft_extend.argtypes = [vp, vp, vp, i32]
         L.dvp_ecfft_extend_device.argtypes = [vp, vp, i32]
+        L.dvp_ecfft_plan_create.argtypes = [vp, C.c_uint, C.POINTER(vp)]
+        L.dvp_ecfft_plan_destroy.argtypes = [vp]
+        L.dvp_ecfft_plan_destroy.restype = None
+        L.dvp_ecfft_enter.argtypes = [vp, vp, vp]
         L.dvp_r1cs_load.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp, sz, C.POINTER(vp)]
         L.dvp_r1cs_destroy.argtypes = [vp]
         L.dvp_r1cs_destroy.restype = None
@@ -397,6 +401,29 @@ class Domain:
             raise DvpError(5, "extend: evals.len() != n")
         out = np.zeros_like(a)
         _ck(lib().dvp_ecfft_extend(self._h, _ptr(a), _ptr(out), npoly), "dvp_ecfft_extend")
+        return out
+
+
+class EcfftPlan:
+    """The trees with 4 .. n leaves: FFTree::enter for polynomials of degree < n (ec_fft.rs:317,411)."""
+
+    def __init__(self, ctx, log2_n):
+        self.n = 1 << log2_n
+        self._h = C.c_void_p()
+        _ck(lib().dvp_ecfft_plan_create(ctx._h, log2_n, C.byref(self._h)), "dvp_ecfft_plan_create")
+
+    def close(self):
+        if self._h:
+            lib().dvp_ecfft_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def enter(self, coeffs_mont):
+        """coefficients (n,4), low degree first -> values on the n leaves of the n-leaf tree, natural order"""
+        a = np.ascontiguousarray(coeffs_mont, dtype=np.uint64).reshape(-1, 4)
+        if a.shape[0] != self.n:
+            raise DvpError(5, "enter: coeffs.len() != n")
+        out = np.zeros_like(a)
+        _ck(lib().dvp_ecfft_enter(self._h, _ptr(a), _ptr(out)), "dvp_ecfft_enter")
         return out
 
 

@@ -153,6 +153,17 @@ int dvp_ecfft_extend(dvp_domain *dom, const uint64_t *in, uint64_t *out, int npo
 int dvp_ecfft_extend_device(dvp_domain *dom, void *d_data, int npoly);
 
 /*
+ * FFTree::enter (crate ecfft; reference call sites src/ec_fft.rs:317,411): coefficients of a polynomial of degree < n
+ * (n x 4 u64 Montgomery, low degree first) -> its values on the n leaves x(C + i G_n) of the n-leaf tree, natural order.
+ * The plan holds the trees with 4 .. n leaves.  (exit / vanish as transforms are not built: setup and prover obtain
+ * every value they were used for from the chain rule, see dvp_setup.)
+ */
+typedef struct dvp_ecfft_plan dvp_ecfft_plan;
+int dvp_ecfft_plan_create(dvp_ctx *ctx, unsigned log2_n, dvp_ecfft_plan **out);
+void dvp_ecfft_plan_destroy(dvp_ecfft_plan *plan);
+int dvp_ecfft_enter(dvp_ecfft_plan *plan, const uint64_t *coeffs, uint64_t *evals);
+
+/*
  * R1CS in the dump's own order (src/gnark_r1cs.rs:1-20): three CSR matrices L, R, O over one coefficient
  * table (Montgomery limbs).  nrows is padded to n = next_power_of_two (gnark_r1cs.rs:291); the
  * Vandermonde block of update_to_include_vandermode_matrix_d (gnark_r1cs.rs:333-386) is applied on the fly.

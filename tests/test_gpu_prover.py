@@ -162,3 +162,47 @@ def test_prove_rejects_bad_witness_and_lengths(ctx, oracle):
     prover.close()
     inst.close()
     gd.close()
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 3, 6, 10])
+def test_enter_evaluates_on_the_leaves(ctx, log_n):
+    """FFTree::enter (ec_fft.rs:317,411): coefficients -> values on the n leaves, against Horner with big integers."""
+    n = 1 << log_n
+    rnd = random.Random(70 + log_n)
+    coeffs = [rnd.randrange(P) for _ in range(n)]
+    plan = dvpari.EcfftPlan(ctx, log_n)
+    got = dvpari.fr_from_mont(plan.enter(dvpari.fr_to_mont(coeffs)))
+    gd = dvpari.Domain(ctx, max(2, log_n))
+    leaves = dvpari.fr_from_mont(gd.leaves())
+    if log_n == 1:
+        leaves = leaves[0::2]  # the 2-leaf tree is the even half of the 4-leaf tree
+    for i, s in enumerate(leaves):
+        acc = 0
+        for c in reversed(coeffs):
+            acc = (acc * s + c) % P
+        assert got[i] == acc, i
+    with pytest.raises(dvpari.DvpError):
+        plan.enter(dvpari.fr_to_mont(coeffs[:-1] if n > 1 else []))
+    plan.close()
+    gd.close()
+
+
+def test_enter_2_16_sparse_polynomial(ctx):
+    """Full-size property: a polynomial with a few non-zero coefficients is evaluated directly at sampled leaves."""
+    log_n = 16
+    n = 1 << log_n
+    rnd = random.Random(71)
+    idx = sorted(rnd.sample(range(n), 6) + [0, n - 1])
+    vals = {i: rnd.randrange(1, P) for i in idx}
+    coeffs = np.zeros((n, 4), dtype=np.uint64)
+    coeffs[idx] = dvpari.fr_to_mont([vals[i] for i in idx])
+    plan = dvpari.EcfftPlan(ctx, log_n)
+    got = plan.enter(coeffs)
+    gd = dvpari.Domain(ctx, log_n)
+    leaves = gd.leaves()
+    for j in [0, 1, 2, n // 2, n - 1] + [rnd.randrange(n) for _ in range(20)]:
+        s = dvpari.fr_from_mont(leaves[j:j + 1])[0]
+        want = sum(v * pow(s, i, P) for i, v in vals.items()) % P
+        assert dvpari.fr_from_mont(got[j:j + 1])[0] == want, j
+    plan.close()
+    gd.close()
