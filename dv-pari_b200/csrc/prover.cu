@@ -444,7 +444,23 @@ static int run_chain(dvp_domain *d, const std::vector<DevBuf *> &layers, int shi
 
 extern "C" {
 
+// shifted = the tree on the coset C + g instead of C: its leaves are the leaves of the plain tree rotated by one, so
+// its extend maps the ODD leaves of the plain tree to the even ones (rotated by one position) -- FFTree::extend(.., Moiety::S0)
+static int domain_create_impl(dvp_ctx *ctx, unsigned log2_2n, bool shifted, dvp_domain **out);
 int dvp_domain_create(dvp_ctx *ctx, unsigned log2_2n, dvp_domain **out) {
+    return domain_create_impl(ctx, log2_2n, false, out);
+}
+} // extern "C"
+
+static void sw_add_host(SwPt &p, const SwPt &q) { // distinct x
+    const fr lam = fr_mul(fr_sub(q.y, p.y), fr_inv(fr_sub(q.x, p.x)));
+    const fr x3 = fr_sub(fr_sub(fr_sqr(lam), p.x), q.x);
+    const fr y3 = fr_sub(fr_mul(lam, fr_sub(p.x, x3)), p.y);
+    p.x = x3;
+    p.y = y3;
+}
+
+static int domain_create_impl(dvp_ctx *ctx, unsigned log2_2n, bool shifted, dvp_domain **out) {
     if (!ctx || !out || log2_2n < 2 || log2_2n > 28) return DVP_ERR_BAD_ARG;
     *out = nullptr;
     CKP(cudaSetDevice(ctx->device));
@@ -466,6 +482,7 @@ int dvp_domain_create(dvp_ctx *ctx, unsigned log2_2n, dvp_domain **out) {
     sc.C.y = fr_from_dec_host("2302954593454110051167704558708330032236229062988890422530712548754008");
     SwPt g = G;
     for (int i = 0; i < 28 - d->log_n2; i++) sw_dbl_host(g, sc.A); // ec_fft.rs:121-124
+    if (shifted) sw_add_host(sc.C, g);
     sc.pow2[0] = g;
     for (int b = 1; b < 28; b++) {
         sc.pow2[b] = sc.pow2[b - 1];
@@ -549,6 +566,8 @@ int dvp_domain_create(dvp_ctx *ctx, unsigned log2_2n, dvp_domain **out) {
     *out = d;
     return DVP_OK;
 }
+
+extern "C" {
 
 void dvp_domain_destroy(dvp_domain *d) {
     if (!d) return;
@@ -1322,11 +1341,18 @@ int dvp_setup(dvp_r1cs *r, dvp_domain *d, const uint64_t trapdoor_mont[12], int 
 // s^m.  Bottom-up over block sizes m = 1, 2, .., n/2; every level extends all n/m blocks in one pass because the
 // blocks tile the array exactly like the sub-problems of a larger extend.  O(n log^2 n).
 // ------------------------------------------------------------------------------------------------
+struct ExitLevel { // constants of the tree with m = 2h leaves (S0 = even leaves, S1 = odd leaves)
+    dvp_domain *rev = nullptr; // the tree on the shifted coset: extend S1 -> S0 (rotated by one)
+    DevBuf xh0inv, xh1;        // s^-h on S0, s^h on S1
+    DevBuf zz0, zz1;           // (Z0^2 mod x^h) on S0 and S1, Z0 = vanishing polynomial of S0
+};
 struct dvp_ecfft_plan {
     dvp_ctx *ctx = nullptr;
     int log_n = 0;
     std::vector<dvp_domain *> dom; // dom[l] = tree with 2^l leaves, l = 2 .. log_n
-    DevBuf a, b, c;
+    std::vector<ExitLevel> lv;     // lv[l] for l = 2 .. log_n
+    DevBuf a, b, c;                // n elements each
+    DevBuf h[6];                   // n/2 elements each
 };
 
 // out block B (size 2m) from blocks 2B, 2B+1 (size m) of cur (values on the even leaves) and ext (odd leaves)
@@ -1342,6 +1368,223 @@ __global__ void k_enter_combine(const fr *__restrict__ cur, const fr *__restrict
     fr_store(&out[(size_t)B * 2 * m + 2 * i + 1], fr_add(fr_load(&ext[u]), fr_mul(p1, fr_load(&ext[v]))));
 }
 
+// all blocks of size h of `v` (len elements in total) through the extend of tree `d` (whose half-domain has h points)
+static int extend_blocks(dvp_domain *d, fr *v, uint32_t len) {
+    cudaStream_t st = d->ctx->stream;
+    const uint32_t h = d->n;
+    for (int k = 0; k < d->levels; k++)
+        k_extend_level<3><<<cdivp(len / 2, 256), 256, 0, st>>>(v, len, h >> (k + 1), d->dec[k].as<fr>(), 1, 0);
+    for (int k = d->levels - 1; k >= 0; k--)
+        k_extend_level<3><<<cdivp(len / 2, 256), 256, 0, st>>>(v, len, h >> (k + 1), d->rec[k].as<fr>(), 1, 0);
+    CKP(cudaGetLastError());
+    return 0;
+}
+
+// ENTER on the device: `io` holds 2^lg coefficients (low degree first) and receives the values on the 2^lg-leaf tree
+static int enter_device(dvp_ecfft_plan *p, fr *io, int lg) {
+    cudaStream_t st = p->ctx->stream;
+    const uint32_t n = 1u << lg;
+    fr *cur = io, *ext = p->b.as<fr>(), *nxt = p->c.as<fr>();
+    for (int lm = 0; lm < lg; lm++) {
+        const uint32_t m = 1u << lm;
+        // the tree with 2m leaves; for m = 1 its two leaves are the even leaves of the 4-leaf tree
+        dvp_domain *d = p->dom[std::max(2, lm + 1)];
+        const uint32_t leaf_stride = lm + 1 < 2 ? 2 : 1;
+        CKP(cudaMemcpyAsync(ext, cur, (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
+        int rc;
+        if (m >= 2 && (rc = extend_blocks(d, ext, n))) return rc;
+        k_enter_combine<<<cdivp(n / 2, 128), 128, 0, st>>>(cur, ext, d->leaves.as<fr>(), leaf_stride, n, m, lm, nxt);
+        CKP(cudaGetLastError());
+        fr *t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    if (cur != io) CKP(cudaMemcpyAsync(io, cur, (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FFTree::exit (crate ecfft; reference call sites /root/reference/src/ec_fft.rs:266,897): values on the n leaves ->
+// coefficients.  Restated from the ECFFT construction.  With h = n/2, S0 / S1 the even / odd leaves and Z0 the
+// vanishing polynomial of S0 (monic, degree h, Z0(0) != 0), P = U + x^h V is split by a Montgomery reduction in
+// which "division by Z0" is the cheap operation (pointwise on S1 after a subtraction that vanishes on S0):
+//   REDC(Q) = (Q + x^h k) / Z0,  k = -Q x^-h on S0 extended to S1      (deg Q < 2h  ->  Q Z0^-1 mod x^h, deg < h)
+//   U = P mod x^h = REDC(REDC(P) (Z0^2 mod x^h)),   V = (P - U) x^-h on S0
+// then U and V are interpolated on the h-leaf tree.  Top-down over block sizes n, n/2, .., 4 and a closed form for 2
+// leaves; each level runs two S0 -> S1 and two S1 -> S0 extends over all blocks at once.  O(n log^2 n).
+// The per-level constants (Z0^2 mod x^h on S0 and S1) are built bottom-up with the smaller transforms:
+// Z0 - x^h = EXIT_h(-s^h), its square mod x^h from two half-size products.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_deinterleave(const fr *__restrict__ x, uint32_t half, fr *__restrict__ e, fr *__restrict__ o) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= half) return;
+    fr_store(&e[t], fr_load(&x[2 * t]));
+    fr_store(&o[t], fr_load(&x[2 * t + 1]));
+}
+// k = -q0 x^-h on S0
+__global__ void k_redc_k(const fr *__restrict__ q0, const fr *__restrict__ xh0inv, uint32_t h, uint32_t len, fr *__restrict__ k) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= len) return;
+    fr_store(&k[t], fr_neg(fr_mul(fr_load(&q0[t]), fr_load(&xh0inv[t % h]))));
+}
+// r1 = (q1 + x^h k1) / Z0 on S1, optionally times zz1
+__global__ void k_redc_fin(const fr *__restrict__ q1, const fr *__restrict__ k1, const fr *__restrict__ xh1,
+                           const fr *__restrict__ z01inv, const fr *__restrict__ mul1, uint32_t h, uint32_t len,
+                           fr *__restrict__ r1, fr *__restrict__ r1m) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= len) return;
+    const uint32_t i = t % h;
+    const fr r = fr_mul(fr_add(fr_load(&q1[t]), fr_mul(fr_load(&xh1[i]), fr_load(&k1[t]))), fr_load(&z01inv[i]));
+    fr_store(&r1[t], r);
+    if (mul1) fr_store(&r1m[t], fr_mul(r, fr_load(&mul1[i])));
+}
+// values on S0 out of the reverse extend (rotated by one inside every block), optionally times zz0
+__global__ void k_unrotate(const fr *__restrict__ rot, const fr *__restrict__ mul0, uint32_t h, uint32_t len, fr *__restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= len) return;
+    const uint32_t b = t / h, i = t % h;
+    fr v = fr_load(&rot[(size_t)b * h + (i + h - 1) % h]);
+    if (mul0) v = fr_mul(v, fr_load(&mul0[i]));
+    fr_store(&out[t], v);
+}
+// next level: block b of size 2h -> block 2b = U on S0, block 2b+1 = V = (P - U) x^-h on S0
+__global__ void k_exit_split(const fr *__restrict__ p0, const fr *__restrict__ u0, const fr *__restrict__ xh0inv, uint32_t h,
+                             uint32_t len, fr *__restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= len) return;
+    const uint32_t b = t / h, i = t % h;
+    const fr u = fr_load(&u0[t]);
+    fr_store(&out[(size_t)(2 * b) * h + i], u);
+    fr_store(&out[(size_t)(2 * b + 1) * h + i], fr_mul(fr_sub(fr_load(&p0[t]), u), fr_load(&xh0inv[i])));
+}
+// two leaves: c1 = (p1 - p0)/(s1 - s0), c0 = p0 - c1 s0
+__global__ void k_exit_base(fr *__restrict__ x, uint32_t pairs, fr s0, fr dinv) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= pairs) return;
+    const fr p0 = fr_load(&x[2 * t]), p1 = fr_load(&x[2 * t + 1]);
+    const fr c1 = fr_mul(fr_sub(p1, p0), dinv);
+    fr_store(&x[2 * t], fr_sub(p0, fr_mul(c1, s0)));
+    fr_store(&x[2 * t + 1], c1);
+}
+// per-level constants: s^h on S1, s^-h on S0 (h = 2^log_h)
+__global__ void k_exit_pows(const fr *__restrict__ leaves, uint32_t h, int log_h, fr *__restrict__ xh0inv, fr *__restrict__ xh1) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h) return;
+    fr_store(&xh0inv[i], fr_inv(fr_pow2k(fr_load(&leaves[2 * i]), log_h)));
+    fr_store(&xh1[i], fr_pow2k(fr_load(&leaves[2 * i + 1]), log_h));
+}
+__global__ void k_neg_inv(const fr *__restrict__ in, uint32_t n, fr *__restrict__ out) { // out = -1/in
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fr_store(&out[i], fr_neg(fr_inv(fr_load(&in[i]))));
+}
+__global__ void k_mul_pointwise(const fr *__restrict__ a, const fr *__restrict__ b, uint32_t n, fr *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fr_store(&out[i], fr_mul(fr_load(&a[i]), fr_load(&b[i])));
+}
+// zzc[j] = cll[j] + 2 clh[j - h/2] (j >= h/2), padded with zeros to 2h
+__global__ void k_zz_coeffs(const fr *__restrict__ cll, const fr *__restrict__ clh, uint32_t h, fr *__restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= 2 * h) return;
+    fr v = fr_zero();
+    if (j < h) {
+        v = fr_load(&cll[j]);
+        if (j >= h / 2) {
+            const fr t = fr_load(&clh[j - h / 2]);
+            v = fr_add(v, fr_add(t, t));
+        }
+    }
+    fr_store(&out[j], v);
+}
+
+// EXIT on the device: `io` holds the values on the 2^lg-leaf tree and receives the 2^lg coefficients
+static int exit_device(dvp_ecfft_plan *p, fr *io, int lg) {
+    cudaStream_t st = p->ctx->stream;
+    const uint32_t n = 1u << lg, half = n >> 1;
+    fr *x = io, *y = p->c.as<fr>();
+    fr *P0 = p->h[0].as<fr>(), *P1 = p->h[1].as<fr>(), *K = p->h[2].as<fr>(), *R1 = p->h[3].as<fr>(), *T1 = p->h[4].as<fr>(),
+       *T0 = p->h[5].as<fr>();
+    int rc;
+    for (int l = lg; l >= 2; l--) {
+        const uint32_t h = 1u << (l - 1);
+        dvp_domain *fwd = p->dom[l];
+        ExitLevel &L = p->lv[l];
+        const fr *xh0inv = L.xh0inv.as<fr>(), *xh1 = L.xh1.as<fr>(), *z01inv = fwd->z_vals2inv.as<fr>();
+        const uint32_t g = cdivp(half, 128);
+        k_deinterleave<<<g, 128, 0, st>>>(x, half, P0, P1);
+        // REDC #1: R = P / Z0 mod x^h on S1 (R1), and R (Z0^2 mod x^h) on S1 (T1)
+        k_redc_k<<<g, 128, 0, st>>>(P0, xh0inv, h, half, K);
+        if ((rc = extend_blocks(fwd, K, half))) return rc;
+        k_redc_fin<<<g, 128, 0, st>>>(P1, K, xh1, z01inv, L.zz1.as<fr>(), h, half, R1, T1);
+        // R on S0 (reverse extend, rotated), times Z0^2 mod x^h
+        if ((rc = extend_blocks(L.rev, R1, half))) return rc;
+        k_unrotate<<<g, 128, 0, st>>>(R1, L.zz0.as<fr>(), h, half, T0);
+        // REDC #2: U = P mod x^h on S1, then on S0
+        k_redc_k<<<g, 128, 0, st>>>(T0, xh0inv, h, half, K);
+        if ((rc = extend_blocks(fwd, K, half))) return rc;
+        k_redc_fin<<<g, 128, 0, st>>>(T1, K, xh1, z01inv, nullptr, h, half, R1, nullptr);
+        if ((rc = extend_blocks(L.rev, R1, half))) return rc;
+        k_unrotate<<<g, 128, 0, st>>>(R1, nullptr, h, half, T0);
+        k_exit_split<<<g, 128, 0, st>>>(P0, T0, xh0inv, h, half, y);
+        CKP(cudaGetLastError());
+        fr *t = x;
+        x = y;
+        y = t;
+    }
+    {
+        // two-leaf trees: the even leaves of the 4-leaf tree
+        fr s[3];
+        CKP(cudaMemcpyAsync(s, p->dom[2]->leaves.p, 3 * sizeof(fr), cudaMemcpyDeviceToHost, st));
+        CKP(cudaStreamSynchronize(st));
+        const fr dinv = fr_inv(fr_sub(s[2], s[0]));
+        k_exit_base<<<cdivp(half, 128), 128, 0, st>>>(x, half, s[0], dinv);
+        CKP(cudaGetLastError());
+    }
+    if (x != io) CKP(cudaMemcpyAsync(io, x, (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// constants of level l (tree with m = 2^l leaves, h = m/2), given that the levels below are ready
+static int exit_level_build(dvp_ecfft_plan *p, int l) {
+    dvp_ctx *ctx = p->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t m = 1u << l, h = m >> 1;
+    ExitLevel &L = p->lv[l];
+    int rc;
+    if ((rc = domain_create_impl(ctx, (unsigned)l, true, &L.rev))) return rc;
+    if ((rc = L.xh0inv.reserve((size_t)h * 32)) || (rc = L.xh1.reserve((size_t)h * 32)) || (rc = L.zz0.reserve((size_t)h * 32)) ||
+        (rc = L.zz1.reserve((size_t)h * 32)))
+        return rc;
+    k_exit_pows<<<cdivp(h, 64), 64, 0, st>>>(p->dom[l]->leaves.as<fr>(), h, l - 1, L.xh0inv.as<fr>(), L.xh1.as<fr>());
+    CKP(cudaGetLastError());
+    // R0 = Z0 - x^h has degree < h and equals -s^h on S0 (the leaves of the h-leaf tree): r0 = EXIT_h(-s^h)
+    DevBuf t[4];
+    auto done = [&](int code) {
+        for (auto &b : t) b.release();
+        return code;
+    };
+    for (auto &b : t)
+        if ((rc = b.reserve((size_t)m * 32))) return done(rc);
+    fr *r0 = t[0].as<fr>(), *eL = t[1].as<fr>(), *eH = t[2].as<fr>(), *w = t[3].as<fr>();
+    k_neg_inv<<<cdivp(h, 64), 64, 0, st>>>(L.xh0inv.as<fr>(), h, r0); // -(s^h) = -1/(s^-h)
+    if ((rc = exit_device(p, r0, l - 1))) return done(rc);
+    // (Z0^2 mod x^h) = (R0^2 mod x^h) = L^2 + 2 x^(h/2) (L H mod x^(h/2)),  R0 = L + x^(h/2) H
+    const uint32_t q = h >> 1;
+    CKP(cudaMemsetAsync(eL, 0, (size_t)h * 32, st));
+    CKP(cudaMemsetAsync(eH, 0, (size_t)h * 32, st));
+    CKP(cudaMemcpyAsync(eL, r0, (size_t)q * 32, cudaMemcpyDeviceToDevice, st));
+    CKP(cudaMemcpyAsync(eH, r0 + q, (size_t)q * 32, cudaMemcpyDeviceToDevice, st));
+    if ((rc = enter_device(p, eL, l - 1)) || (rc = enter_device(p, eH, l - 1))) return done(rc);
+    k_mul_pointwise<<<cdivp(h, 128), 128, 0, st>>>(eL, eH, h, eH); // L H on the h-leaf tree (degree < h - 1)
+    k_mul_pointwise<<<cdivp(h, 128), 128, 0, st>>>(eL, eL, h, eL); // L^2
+    if ((rc = exit_device(p, eL, l - 1)) || (rc = exit_device(p, eH, l - 1))) return done(rc);
+    k_zz_coeffs<<<cdivp(m, 128), 128, 0, st>>>(eL, eH, h, w);
+    if ((rc = enter_device(p, w, l))) return done(rc); // values on the m-leaf tree
+    k_deinterleave<<<cdivp(h, 128), 128, 0, st>>>(w, h, L.zz0.as<fr>(), L.zz1.as<fr>());
+    CKP(cudaGetLastError());
+    CKP(cudaStreamSynchronize(st));
+    return done(0);
+}
+
 extern "C" {
 
 int dvp_ecfft_plan_create(dvp_ctx *ctx, unsigned log2_n, dvp_ecfft_plan **out) {
@@ -1350,11 +1593,23 @@ int dvp_ecfft_plan_create(dvp_ctx *ctx, unsigned log2_n, dvp_ecfft_plan **out) {
     dvp_ecfft_plan *p = new dvp_ecfft_plan();
     p->ctx = ctx;
     p->log_n = (int)log2_n;
-    p->dom.assign(log2_n + 1, nullptr);
+    const unsigned top = std::max(2u, log2_n);
+    p->dom.assign(top + 1, nullptr);
+    p->lv.resize(top + 1);
     int rc = 0;
-    for (unsigned l = 2; l <= std::max(2u, log2_n) && !rc; l++) rc = dvp_domain_create(ctx, l, &p->dom[l]);
-    const size_t n = (size_t)1 << log2_n;
-    if (!rc && ((rc = p->a.reserve(n * 32)) || (rc = p->b.reserve(n * 32)) || (rc = p->c.reserve(n * 32)))) {
+    const size_t n = (size_t)1 << top;
+    if ((rc = p->a.reserve(n * 32)) || (rc = p->b.reserve(n * 32)) || (rc = p->c.reserve(n * 32))) {
+        dvp_ecfft_plan_destroy(p);
+        return rc;
+    }
+    for (auto &b : p->h)
+        if ((rc = b.reserve(n * 16))) {
+            dvp_ecfft_plan_destroy(p);
+            return rc;
+        }
+    for (unsigned l = 2; l <= top && !rc; l++) {
+        rc = dvp_domain_create(ctx, l, &p->dom[l]);
+        if (!rc) rc = exit_level_build(p, (int)l);
     }
     if (rc) {
         dvp_ecfft_plan_destroy(p);
@@ -1367,40 +1622,46 @@ int dvp_ecfft_plan_create(dvp_ctx *ctx, unsigned log2_n, dvp_ecfft_plan **out) {
 void dvp_ecfft_plan_destroy(dvp_ecfft_plan *p) {
     if (!p) return;
     for (auto d : p->dom) dvp_domain_destroy(d);
+    for (auto &L : p->lv) {
+        dvp_domain_destroy(L.rev);
+        L.xh0inv.release();
+        L.xh1.release();
+        L.zz0.release();
+        L.zz1.release();
+    }
     p->a.release();
     p->b.release();
     p->c.release();
+    for (auto &b : p->h) b.release();
     delete p;
 }
 
 // coeffs (n x 4 u64 Montgomery, low degree first) -> evals on the n leaves x(C + i G_n), host buffers
 int dvp_ecfft_enter(dvp_ecfft_plan *p, const uint64_t *coeffs, uint64_t *evals) {
     if (!p || !coeffs || !evals) return DVP_ERR_BAD_ARG;
-    dvp_ctx *ctx = p->ctx;
-    CKP(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    const uint32_t n = 1u << p->log_n;
-    fr *cur = p->a.as<fr>(), *ext = p->b.as<fr>(), *nxt = p->c.as<fr>();
-    CKP(cudaMemcpyAsync(cur, coeffs, (size_t)n * 32, cudaMemcpyHostToDevice, st));
-    for (int lm = 0; lm < p->log_n; lm++) {
-        const uint32_t m = 1u << lm;
-        // the tree with 2m leaves; for m = 1 its two leaves are the even leaves of the 4-leaf tree
-        dvp_domain *d = p->dom[std::max(2, lm + 1)];
-        const uint32_t leaf_stride = lm + 1 < 2 ? 2 : 1;
-        CKP(cudaMemcpyAsync(ext, cur, (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
-        if (m >= 2) {
-            for (int k = 0; k < d->levels; k++)
-                k_extend_level<3><<<cdivp(n / 2, 256), 256, 0, st>>>(ext, n, m >> (k + 1), d->dec[k].as<fr>(), 1, 0);
-            for (int k = d->levels - 1; k >= 0; k--)
-                k_extend_level<3><<<cdivp(n / 2, 256), 256, 0, st>>>(ext, n, m >> (k + 1), d->rec[k].as<fr>(), 1, 0);
-        }
-        k_enter_combine<<<cdivp(n / 2, 128), 128, 0, st>>>(cur, ext, d->leaves.as<fr>(), leaf_stride, n, m, lm, nxt);
-        CKP(cudaGetLastError());
-        fr *t = cur;
-        cur = nxt;
-        nxt = t;
-    }
-    CKP(cudaMemcpyAsync(evals, cur, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    CKP(cudaSetDevice(p->ctx->device));
+    cudaStream_t st = p->ctx->stream;
+    const size_t n = (size_t)1 << p->log_n;
+    fr *io = p->a.as<fr>();
+    CKP(cudaMemcpyAsync(io, coeffs, n * 32, cudaMemcpyHostToDevice, st));
+    int rc = enter_device(p, io, p->log_n);
+    if (rc) return rc;
+    CKP(cudaMemcpyAsync(evals, io, n * 32, cudaMemcpyDeviceToHost, st));
+    CKP(cudaStreamSynchronize(st));
+    return DVP_OK;
+}
+
+// evals on the n leaves -> coeffs (inverse of dvp_ecfft_enter), host buffers
+int dvp_ecfft_exit(dvp_ecfft_plan *p, const uint64_t *evals, uint64_t *coeffs) {
+    if (!p || !coeffs || !evals) return DVP_ERR_BAD_ARG;
+    CKP(cudaSetDevice(p->ctx->device));
+    cudaStream_t st = p->ctx->stream;
+    const size_t n = (size_t)1 << p->log_n;
+    fr *io = p->a.as<fr>();
+    CKP(cudaMemcpyAsync(io, evals, n * 32, cudaMemcpyHostToDevice, st));
+    int rc = p->log_n >= 1 ? exit_device(p, io, p->log_n) : 0;
+    if (rc) return rc;
+    CKP(cudaMemcpyAsync(coeffs, io, n * 32, cudaMemcpyDeviceToHost, st));
     CKP(cudaStreamSynchronize(st));
     return DVP_OK;
 }

@@ -107,6 +107,7 @@ def lib():
         L.dvp_ecfft_plan_destroy.argtypes = [vp]
         L.dvp_ecfft_plan_destroy.restype = None
         L.dvp_ecfft_enter.argtypes = [vp, vp, vp]
+        L.dvp_ecfft_exit.argtypes = [vp, vp, vp]
         L.dvp_r1cs_load.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp, sz, C.POINTER(vp)]
         L.dvp_r1cs_destroy.argtypes = [vp]
         L.dvp_r1cs_destroy.restype = None
@@ -424,6 +425,15 @@ class EcfftPlan:
             raise DvpError(5, "enter: coeffs.len() != n")
         out = np.zeros_like(a)
         _ck(lib().dvp_ecfft_enter(self._h, _ptr(a), _ptr(out)), "dvp_ecfft_enter")
+        return out
+
+    def exit(self, evals_mont):
+        """values on the n leaves (natural order) -> coefficients (n,4), low degree first (FFTree::exit)"""
+        a = np.ascontiguousarray(evals_mont, dtype=np.uint64).reshape(-1, 4)
+        if a.shape[0] != self.n:
+            raise DvpError(5, "exit: evals.len() != n")
+        out = np.zeros_like(a)
+        _ck(lib().dvp_ecfft_exit(self._h, _ptr(a), _ptr(out)), "dvp_ecfft_exit")
         return out
 
 

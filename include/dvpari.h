@@ -155,13 +155,16 @@ int dvp_ecfft_extend_device(dvp_domain *dom, void *d_data, int npoly);
 /*
  * FFTree::enter (crate ecfft; reference call sites src/ec_fft.rs:317,411): coefficients of a polynomial of degree < n
  * (n x 4 u64 Montgomery, low degree first) -> its values on the n leaves x(C + i G_n) of the n-leaf tree, natural order.
- * The plan holds the trees with 4 .. n leaves.  (exit / vanish as transforms are not built: setup and prover obtain
- * every value they were used for from the chain rule, see dvp_setup.)
+ * FFTree::exit (src/ec_fft.rs:266,897) is the inverse: values on the n leaves -> coefficients.
+ * The plan holds the trees with 4 .. n leaves (plain and shifted coset) and the per-level constants of exit.
+ * (Setup and prover do not need either transform: they obtain Z_D(tau), Z'_D(d_i), Z_D(d'_i), L_i(tau) from the
+ * chain rule, see dvp_setup.)
  */
 typedef struct dvp_ecfft_plan dvp_ecfft_plan;
 int dvp_ecfft_plan_create(dvp_ctx *ctx, unsigned log2_n, dvp_ecfft_plan **out);
 void dvp_ecfft_plan_destroy(dvp_ecfft_plan *plan);
 int dvp_ecfft_enter(dvp_ecfft_plan *plan, const uint64_t *coeffs, uint64_t *evals);
+int dvp_ecfft_exit(dvp_ecfft_plan *plan, const uint64_t *evals, uint64_t *coeffs);
 
 /*
  * R1CS in the dump's own order (src/gnark_r1cs.rs:1-20): three CSR matrices L, R, O over one coefficient

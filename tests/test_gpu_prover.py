@@ -206,3 +206,62 @@ def test_enter_2_16_sparse_polynomial(ctx):
         assert dvpari.fr_from_mont(got[j:j + 1])[0] == want, j
     plan.close()
     gd.close()
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 7, 11])
+def test_exit_inverts_enter(ctx, log_n):
+    """FFTree::exit (ec_fft.rs:266,897): values on the leaves -> coefficients.  exit(enter(c)) == c for random c, and
+    the values of an explicitly evaluated polynomial interpolate back to its coefficients (ec_fft.rs:883-907)."""
+    n = 1 << log_n
+    rnd = random.Random(80 + log_n)
+    coeffs = [rnd.randrange(P) for _ in range(n)]
+    plan = dvpari.EcfftPlan(ctx, log_n)
+    cm = dvpari.fr_to_mont(coeffs)
+    ev = plan.enter(cm)
+    assert plan.exit(ev).tobytes() == cm.tobytes()
+    # independent of enter: Horner values of a low-degree polynomial on the leaves
+    gd = dvpari.Domain(ctx, max(2, log_n))
+    leaves = dvpari.fr_from_mont(gd.leaves())
+    if log_n == 1:
+        leaves = leaves[0::2]
+    deg = min(n, 5)
+    small = [rnd.randrange(P) for _ in range(deg)]
+    vals = []
+    for s in leaves:
+        acc = 0
+        for c in reversed(small):
+            acc = (acc * s + c) % P
+        vals.append(acc)
+    got = dvpari.fr_from_mont(plan.exit(dvpari.fr_to_mont(vals)))
+    assert got == small + [0] * (n - deg)
+    plan.close()
+    gd.close()
+
+
+def test_exit_gives_the_vanishing_polynomial(ctx):
+    """vanish via exit, as the reference computes z_poly (ec_fft.rs:241-283): the values of Z_D on the 2n-leaf tree
+    (zero on D, the chain-rule values on D') interpolate to a monic degree-n polynomial that vanishes on D."""
+    log_n2 = 9
+    n2, n = 1 << log_n2, 1 << (log_n2 - 1)
+    gd = dvpari.Domain(ctx, log_n2)
+    zinv, _ = gd.precomputes()                      # 1 / Z_D(d'_i)
+    z_on_dprime = [pow(v, P - 2, P) for v in dvpari.fr_from_mont(zinv)]
+    vals = [0] * n2
+    vals[1::2] = z_on_dprime
+    plan = dvpari.EcfftPlan(ctx, log_n2)
+    c = dvpari.fr_from_mont(plan.exit(dvpari.fr_to_mont(vals)))
+    assert c[n] == 1 and not any(c[n + 1:])         # monic of degree n
+    leaves = dvpari.fr_from_mont(gd.leaves())
+    for s in leaves[0::2][:16] + leaves[0::2][-4:]:
+        acc = 0
+        for co in reversed(c[:n + 1]):
+            acc = (acc * s + co) % P
+        assert acc == 0
+    # and z_poly.evaluate(x) agrees with the chain rule at an arbitrary point (ec_fft.rs:475)
+    x = 0x123456789ABCDEF
+    acc = 0
+    for co in reversed(c[:n + 1]):
+        acc = (acc * x + co) % P
+    assert acc == dvpari.fr_from_mont(gd.vanish_at(0, dvpari.fr_to_mont([x])[0]))[0]
+    plan.close()
+    gd.close()
