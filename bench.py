@@ -216,6 +216,19 @@ def prove_section(ctx, args, rank, world, sync_all, timed):
         dom.extend_device(d, 3)
     ext_ms = 1e3 * (time.perf_counter() - t0) / 3
     ctx.dev_free(d)
+    # FFTree::enter / exit of a 2^20-coefficient polynomial (BASELINE config #3), host buffers, round trip checked
+    elg = min(20, lg)
+    plan = dvpari.EcfftPlan(ctx, elg)
+    coef = dvpari.random_fr_mont(1 << elg, 9)
+    ev = plan.enter(coef)
+    t0 = time.perf_counter()
+    ev = plan.enter(coef)
+    enter_ms = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    back = plan.exit(ev)
+    exit_ms = 1e3 * (time.perf_counter() - t0)
+    assert back.tobytes() == coef.tobytes(), "exit(enter(c)) != c"
+    plan.close()
     hbm_peak, _ = peaks()
     mulmods = 3 * 4 * n * lg  # 4 n log2 n per polynomial
     ext_bytes = 3 * 2 * lg * (64 * (n // 2)) + 2 * 256 * n  # data in + out per level and polynomial, matrices once per level pair
@@ -232,6 +245,8 @@ def prove_section(ctx, args, rank, world, sync_all, timed):
                          "int_frac": (mulmods / 4) * EXT_WIDE_PER_BUTTERFLY / (ext_ms * 1e-3) / IMAD_WIDE_PEAK,
                          "GBps": ext_bytes / (ext_ms * 1e-3) / 1e9, "hbm_frac": ext_bytes / (ext_ms * 1e-3) / 1e9 / hbm_peak,
                          "bound": "integer (IMAD.WIDE issue), see DESIGN.md 4.3"},
+        "ecfft_enter_exit": {"n": 1 << elg, "enter_ms": enter_ms, "exit_ms": exit_ms, "round_trip_exact": True,
+                             "note": "host buffers (2 x 32 MiB copies inside); O(n log^2 n) built from the extend butterflies"},
         "r1cs_rows": {"ms": stages["r1cs"], "terms_per_s": terms / (stages["r1cs"] * 1e-3),
                       "GBps": (terms * 72 + 4 * n * 32) / (stages["r1cs"] * 1e-3) / 1e9},
         "srs": "generated on the device from a fixed trapdoor (dvp_setup)", "setup_s": t_setup,

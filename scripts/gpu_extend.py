@@ -15,3 +15,15 @@ for lg in [int(a) for a in sys.argv[1:]] or [20, 22]:
     wides = 3 * (n // 2) * 2 * lg * 339
     print(f"extend 3 x 2^{lg}: {best*1e3:.3f} ms  {wides/best:.3e} IMAD.WIDE/s = {wides/best/9.2e12:.3f} of peak")
     ctx.dev_free(d); dom.close()
+# enter / exit (BASELINE config #3: 2^20-coefficient polynomials)
+import numpy as np
+for lg in (16, 20):
+    n = 1 << lg
+    t0 = time.perf_counter(); plan = dvpari.EcfftPlan(ctx, lg); t_plan = time.perf_counter() - t0
+    c = dvpari.random_fr_mont(n, 9)
+    ev = plan.enter(c)
+    t0 = time.perf_counter(); ev = plan.enter(c); t_enter = time.perf_counter() - t0
+    t0 = time.perf_counter(); back = plan.exit(ev); t_exit = time.perf_counter() - t0
+    assert back.tobytes() == c.tobytes()
+    print(f"2^{lg}: plan {t_plan:.2f} s, enter {t_enter*1e3:.1f} ms, exit {t_exit*1e3:.1f} ms (host buffers), exit(enter(c)) == c")
+    plan.close()

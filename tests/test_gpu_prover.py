@@ -265,3 +265,26 @@ def test_exit_gives_the_vanishing_polynomial(ctx):
     assert acc == dvpari.fr_from_mont(gd.vanish_at(0, dvpari.fr_to_mont([x])[0]))[0]
     plan.close()
     gd.close()
+
+
+def test_enter_exit_round_trip_2_16(ctx):
+    """BASELINE config #3 shape at a size the suite can afford: 2^16 random coefficients -> leaves -> coefficients."""
+    log_n = 16
+    plan = dvpari.EcfftPlan(ctx, log_n)
+    c = dvpari.random_fr_mont(1 << log_n, 99)
+    ev = plan.enter(c)
+    assert plan.exit(ev).tobytes() == c.tobytes()
+    # linearity of enter: enter(c1 + c2) = enter(c1) + enter(c2) on a sample
+    c2 = dvpari.random_fr_mont(1 << log_n, 100)
+    s = dvpari.fr_to_mont([(a + b) % P for a, b in zip(dvpari.fr_from_mont(c[:64]), dvpari.fr_from_mont(c2[:64]))])
+    csum = c.copy()
+    csum[:64] = s
+    csum[64:] = c[64:]
+    c2z = c2.copy()
+    c2z[64:] = 0
+    e1, e2 = plan.enter(csum), plan.enter(c2z)
+    for j in (0, 1, 12345, (1 << log_n) - 1):
+        lhs = dvpari.fr_from_mont(e1[j:j + 1])[0]
+        rhs = (dvpari.fr_from_mont(ev[j:j + 1])[0] + dvpari.fr_from_mont(e2[j:j + 1])[0]) % P
+        assert lhs == rhs
+    plan.close()
