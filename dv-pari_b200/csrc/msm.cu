@@ -166,19 +166,12 @@ __global__ void k_lane_info(const uint32_t *__restrict__ len, const uint32_t *__
 }
 
 // ------------------------------------------------------------------------------------------------
-// device-wide exclusive scans over segment lengths.
-//   MODE 0: value = L                    -> start[s]                  (counting-sort offsets)
-//   MODE 1: value = (L/2, (L+1)/2) packed -> task_start[s], out_start[s], new_len[s]
-// info[0] = max L, info[1] = total tasks, info[2] = total outputs
+// device-wide exclusive scan of the bucket sizes: start[s] and a copy as scatter cursors (counting-sort
+// offsets; start[nseg] = number of entries).  Three launches: tile sums, scan of the tile sums, offsets.
 // ------------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-
-template <int MODE> __device__ __forceinline__ uint64_t scan_val(uint32_t L) {
-    if (MODE == 0) return L;
-    return (uint64_t)(L >> 1) | ((uint64_t)((L + 1) >> 1) << 32);
-}
 
 __device__ __forceinline__ uint64_t block_reduce_u64(uint64_t v, uint64_t *sh) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -196,26 +189,17 @@ __device__ __forceinline__ uint64_t block_reduce_u64(uint64_t v, uint64_t *sh) {
     return v;
 }
 
-template <int MODE>
-__global__ void k_scan1(const uint32_t *__restrict__ len, uint32_t nseg, uint64_t *__restrict__ blk_sum,
-                        uint32_t *__restrict__ info) {
+__global__ void k_scan1(const uint32_t *__restrict__ len, uint32_t nseg, uint64_t *__restrict__ blk_sum) {
     __shared__ uint64_t sh[32];
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint64_t s = 0;
-    uint32_t mx = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         const uint32_t idx = base + k;
-        const uint32_t L = idx < nseg ? len[idx] : 0;
-        s += scan_val<MODE>(L);
-        mx = max(mx, L);
+        s += idx < nseg ? len[idx] : 0;
     }
     s = block_reduce_u64(s, sh);
     if (threadIdx.x == 0) blk_sum[blockIdx.x] = s;
-    if (MODE == 1) {
-        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
-        if ((threadIdx.x & 31) == 0 && mx) atomicMax(&info[0], mx);
-    }
 }
 
 // single block: exclusive scan of blk_sum[0..nblk) in place; blk_sum[nblk] = total
@@ -244,21 +228,17 @@ __global__ void k_scan2(uint64_t *__restrict__ blk_sum, uint32_t nblk) {
     if (threadIdx.x == 0) blk_sum[nblk] = carry;
 }
 
-template <int MODE>
 __global__ void k_scan3(const uint32_t *__restrict__ len, uint32_t nseg, const uint64_t *__restrict__ blk_sum,
-                        uint32_t *__restrict__ out_a, uint32_t *__restrict__ out_b, uint32_t *__restrict__ new_len,
-                        uint32_t *__restrict__ info) {
+                        uint32_t *__restrict__ start, uint32_t *__restrict__ cursor) {
     __shared__ uint64_t sh[32];
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    uint64_t v[SCAN_ITEMS];
     uint32_t L[SCAN_ITEMS];
     uint64_t s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         const uint32_t idx = base + k;
         L[k] = idx < nseg ? len[idx] : 0;
-        v[k] = scan_val<MODE>(L[k]);
-        s += v[k];
+        s += L[k];
     }
     // exclusive scan of the per-thread sums across the block
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -284,28 +264,12 @@ __global__ void k_scan3(const uint32_t *__restrict__ len, uint32_t nseg, const u
     for (int k = 0; k < SCAN_ITEMS; k++) {
         const uint32_t idx = base + k;
         if (idx < nseg) {
-            if (MODE == 0) {
-                out_a[idx] = (uint32_t)run;
-                out_b[idx] = (uint32_t)run;
-            } else {
-                out_a[idx] = (uint32_t)run;
-                out_b[idx] = (uint32_t)(run >> 32);
-                new_len[idx] = (L[k] + 1) >> 1;
-            }
+            start[idx] = (uint32_t)run;
+            cursor[idx] = (uint32_t)run;
         }
-        run += v[k];
+        run += L[k];
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
-        const uint64_t tot = blk_sum[gridDim.x];
-        if (MODE == 0) {
-            out_a[nseg] = (uint32_t)tot;
-        } else {
-            out_a[nseg] = (uint32_t)tot;
-            out_b[nseg] = (uint32_t)(tot >> 32);
-            info[1] = (uint32_t)tot;
-            info[2] = (uint32_t)(tot >> 32);
-        }
-    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) start[nseg] = (uint32_t)blk_sum[gridDim.x];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1304,10 +1268,10 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
                                                  keys.as<uint32_t>(), d_len_all);
     {
         const uint32_t nblk = cdiv(NB, SCAN_TILE);
-        k_scan1<0><<<nblk, SCAN_THREADS, 0, st>>>(d_len_all, (uint32_t)NB, scan_blk.as<uint64_t>(), nullptr);
+        k_scan1<<<nblk, SCAN_THREADS, 0, st>>>(d_len_all, (uint32_t)NB, scan_blk.as<uint64_t>());
         k_scan2<<<1, SCAN_THREADS, 0, st>>>(scan_blk.as<uint64_t>(), nblk);
-        k_scan3<0><<<nblk, SCAN_THREADS, 0, st>>>(d_len_all, (uint32_t)NB, scan_blk.as<uint64_t>(), d_start_all,
-                                                  cursor_all.as<uint32_t>(), nullptr, nullptr);
+        k_scan3<<<nblk, SCAN_THREADS, 0, st>>>(d_len_all, (uint32_t)NB, scan_blk.as<uint64_t>(), d_start_all,
+                                               cursor_all.as<uint32_t>());
         k_scatter<<<cdiv(total, 256), 256, 0, st>>>(keys.as<uint32_t>(), (uint32_t)n, total,
                                                     uniform ? (uint32_t)tab->offset : 0u,
                                                     uniform ? (uint32_t)tab->stride : 0u, cursor_all.as<uint32_t>(),

@@ -1,6 +1,6 @@
 // Experimental low-register-pressure GF(2^233) multiplier (see scripts/mulbench.cu).
 #pragma once
-#include "gf233.cuh"
+#include "../dv-pari_b200/csrc/gf233.cuh"
 
 namespace dvp {
 

@@ -5,7 +5,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../dv-pari_b200/csrc/gf233.cuh"
-#include "../dv-pari_b200/csrc/gf233_v2.cuh"
+#include "gf233_v2.cuh"
 
 using namespace dvp;
 
