@@ -283,6 +283,10 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
         ctx->msm_tables_min = (size_t)value;
         return DVP_OK;
     }
+    if (!strcmp(name, "b64_min")) {
+        ctx->msm.b64_min = value > 0 ? (size_t)value : ((size_t)1 << 23);
+        return DVP_OK;
+    }
     if (!strcmp(name, "binv_direct")) {
         if (value < 64 || value > (1 << 20)) return DVP_ERR_BAD_ARG;
         ctx->msm.binv_direct = (uint32_t)value;

@@ -394,13 +394,26 @@ __global__ void __launch_bounds__(256)
     const uint32_t base = warp * (32u * B);
     if (base >= ntasks) return;
     gf acc = gf_one();
+    // the next task's descriptor and x coordinates are in flight while the current product is computed
+    uint32_t t = base + lane;
+    uint4 de = make_uint4(0, 0, 0, 0);
+    gf x1 = gf_zero(), x2 = gf_zero();
+    if (t < ntasks) {
+        de = desc[t];
+        x1 = gf_load(&src[de.x & 0x7fffffffu].x);
+        x2 = gf_load(&src[de.y & 0x7fffffffu].x);
+    }
 #pragma unroll 1
     for (int k = 0; k < B; k++) {
-        const uint32_t t = base + k * 32 + lane;
         if (t >= ntasks) break;
-        const uint4 de = desc[t];
-        const uint32_t ia = de.x & 0x7fffffffu, ib = de.y & 0x7fffffffu;
-        const gf x1 = gf_load(&src[ia].x), x2 = gf_load(&src[ib].x);
+        const uint32_t tn = t + 32;
+        uint4 den = make_uint4(0, 0, 0, 0);
+        gf x1n = gf_zero(), x2n = gf_zero();
+        if (k + 1 < B && tn < ntasks) {
+            den = desc[tn];
+            x1n = gf_load(&src[den.x & 0x7fffffffu].x);
+            x2n = gf_load(&src[den.y & 0x7fffffffu].x);
+        }
         gf d = gf_add(x1, x2);
         if (gf_is_zero(x1) | gf_is_zero(x2)) d = gf_one();
         else if (gf_is_zero(d)) {
@@ -409,6 +422,10 @@ __global__ void __launch_bounds__(256)
         }
         gf_store(&prefix[t], acc);
         acc = gf_mul(acc, d);
+        t = tn;
+        de = den;
+        x1 = x1n;
+        x2 = x2n;
     }
     gf_store(&thr_total[gtid], acc);
 }
@@ -922,6 +939,7 @@ struct Tree {
         return 0;
     }
     int round(int B, const AffPt *src, size_t task_ub, AffPt *dst) {
+        if (B == 64) return round_t<64>(src, task_ub, dst);
         if (B == 16) return round_t<16>(src, task_ub, dst);
         if (B == 4) return round_t<4>(src, task_ub, dst);
         return round_t<1>(src, task_ub, dst);
@@ -980,7 +998,7 @@ struct Tree {
             const int o = (r + 1) & 1; // lane set written by this round's plan
             // tasks_r <= total/2^(r+1) + nseg/2
             const size_t task_ub = r == 0 ? total_ub / 2 + 1 : (total_ub >> (r + 1)) + nseg / 2 + 1;
-            const int B = task_ub >= (1u << 21) ? 16 : task_ub >= (1u << 17) ? 4 : 1;
+            const int B = task_ub >= E.b64_min ? 64 : task_ub >= (1u << 21) ? 16 : task_ub >= (1u << 17) ? 4 : 1;
             AffPt *out = L.pp[r & 1].as<AffPt>();
             if ((rc = round(B, cur_src, task_ub, out))) return rc;
             pb(PC_MISC);

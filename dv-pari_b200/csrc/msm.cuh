@@ -81,6 +81,7 @@ struct MsmEngine {
     bool profile = false; // per-category CUDA-event timing of every launch (development; forces one lane)
     float prof_ms[PC_COUNT] = {0};
     unsigned prof_n[PC_COUNT] = {0};
+    size_t b64_min = (size_t)1 << 23; // rounds with at least this many additions chain 64 per thread (off by default)
     uint32_t binv_direct = 32768; // batches up to this size are inverted one element per thread
     int pass2_minb = 2; // resident blocks per SM the pass-2 kernel is compiled for (register cap)
 
