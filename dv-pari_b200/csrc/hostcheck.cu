@@ -113,6 +113,19 @@ extern "C" int dvp_hostcheck_op(int op, const void *a_, const void *b_, void *ou
             memcpy(out + i * 32, o.v, 32);
             break;
         }
+        case 18: { // three-term dot product on 29-bit limbs + fr29_add: a = (m0, x0), b = (m1, x1) -> m0 x0 + m1 x1 + m0 x1, then + m1
+            fr m0, x0, m1, x1;
+            memcpy(m0.v, a + i * 64, 32);
+            memcpy(x0.v, a + i * 64 + 32, 32);
+            memcpy(m1.v, b + i * 64, 32);
+            memcpy(x1.v, b + i * 64 + 32, 32);
+            const fr29 mm[3] = {fr29_prescale(m0), fr29_prescale(m1), fr29_prescale(m0)};
+            const fr29 xx[3] = {fr29_from_fr(x0), fr29_from_fr(x1), fr29_from_fr(x1)};
+            const fr29 r = fr29_add(fr29_dotn<3>(mm, xx), fr29_from_fr(m1));
+            const fr o = fr_from_fr29(r);
+            memcpy(out + i * 32, o.v, 32);
+            break;
+        }
         case 16: { // complete LD addition on projective operands: (2a) + (b + a) = 3a + b
             AffPt p, q;
             memcpy(&p, a + i * 64, 64);

@@ -50,6 +50,13 @@ __device__ __forceinline__ void fr_store(fr *p, const fr &v) {
     q[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
     q[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
 }
+__device__ __forceinline__ fr29 fr29_load(const fr *p) {
+    const fr t = fr_load(p);
+    fr29 r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.l[k] = t.v[k];
+    return r;
+}
 // v^(2^e)
 __host__ __device__ inline fr fr_pow2k(fr v, int e) {
     for (int i = 0; i < e; i++) v = fr_sqr(v);
@@ -171,13 +178,6 @@ __global__ void k_mats_to29(fr *__restrict__ mats, uint32_t count) {
     for (int k = 0; k < 8; k++) o.v[k] = r.l[k];
     fr_store(&mats[i], o);
 }
-__device__ __forceinline__ fr29 fr29_load(const fr *p) {
-    const fr t = fr_load(p);
-    fr29 r;
-#pragma unroll
-    for (int k = 0; k < 8; k++) r.l[k] = t.v[k];
-    return r;
-}
 template <int NP>
 __global__ void __launch_bounds__(256)
     k_extend_level(fr *__restrict__ data, uint32_t n, uint32_t h, const fr *__restrict__ mats, int npoly,
@@ -243,6 +243,85 @@ __global__ void __launch_bounds__(128)
     }
     fr_store(&a[row], av);
     fr_store(&b[row], bv);
+    fr_store(&c[row], fr_sub(cw, ival));
+    fr_store(&iv[row], ival);
+    if (!fr_eq(fr_mul(av, bv), cw)) atomicMin(first_bad, (unsigned long long)row);
+}
+
+// ---- row products on 29-bit limbs (large circuits) ------------------------------------------------------------
+// One thread per (row, matrix) task; the tasks of every chunk of R1CS_CHUNK rows are ordered by term count, so the
+// lanes of a warp run the same number of iterations (the geometric row lengths cost ~3x in divergence otherwise).
+// Coefficients are stored pre-scaled on 29-bit limbs, the assignment is converted once; three terms share one
+// Montgomery reduction (fr29_dotn) and the partial sums are added on the limbs.
+constexpr uint32_t R1CS_CHUNK = 4096;
+__global__ void k_fr_to29(const fr *__restrict__ in, uint32_t n, fr *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fr29 r = fr29_from_fr(fr_load(&in[i]));
+    fr o;
+#pragma unroll
+    for (int k = 0; k < 8; k++) o.v[k] = r.l[k];
+    fr_store(&out[i], o);
+}
+__global__ void __launch_bounds__(128)
+    k_r1cs_sides(R1csDev r, const uint32_t *__restrict__ tasks, uint32_t task_lo, uint32_t task_hi,
+                 const fr *__restrict__ coeffs29, const fr *__restrict__ w29, fr *__restrict__ a, fr *__restrict__ b,
+                 fr *__restrict__ c) {
+    const uint32_t ti = task_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= task_hi) return;
+    const uint32_t task = tasks[ti], which = task & 3u, row = task >> 2;
+    const uint32_t *wire = r.wire[which], *cid = r.coeff[which];
+    uint32_t p = r.rowptr[which][row];
+    const uint32_t pe = r.rowptr[which][row + 1];
+    fr29 acc;
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc.l[k] = 0;
+    for (; p + 3 <= pe; p += 3) {
+        fr29 m[3], x[3];
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            m[t] = fr29_load(&coeffs29[cid[p + t]]);
+            x[t] = fr29_load(&w29[wire[p + t]]);
+        }
+        acc = fr29_add(acc, fr29_dotn<3>(m, x));
+    }
+    if (pe - p == 2) {
+        fr29 m[2], x[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            m[t] = fr29_load(&coeffs29[cid[p + t]]);
+            x[t] = fr29_load(&w29[wire[p + t]]);
+        }
+        acc = fr29_add(acc, fr29_dotn<2>(m, x));
+    } else if (pe - p == 1) {
+        const fr29 m = fr29_load(&coeffs29[cid[p]]), x = fr29_load(&w29[wire[p]]);
+        acc = fr29_add(acc, fr29_dotn<1>(&m, &x));
+    }
+    fr *out = which == 0 ? a : which == 1 ? b : c;
+    fr_store(&out[row], fr_from_fr29(acc));
+}
+// per row: i = sum_j x_j d^j, c = C w - i, the satisfiability check; rows beyond the dump are zero
+__global__ void __launch_bounds__(128)
+    k_r1cs_finish(R1csDev r, uint32_t row_lo, uint32_t row_hi, const fr *__restrict__ w, const fr *__restrict__ leaves,
+                  fr *__restrict__ a, fr *__restrict__ b, fr *__restrict__ c, fr *__restrict__ iv,
+                  unsigned long long *__restrict__ first_bad) {
+    const uint32_t row = row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= row_hi) return;
+    fr av = fr_zero(), bv = fr_zero(), cw = fr_zero();
+    if (row < r.nrows) {
+        av = fr_load(&a[row]);
+        bv = fr_load(&b[row]);
+        cw = fr_load(&c[row]);
+    } else {
+        fr_store(&a[row], av);
+        fr_store(&b[row], bv);
+    }
+    const fr d = fr_load(&leaves[2 * row]);
+    fr pw = fr_one(), ival = fr_zero();
+    for (uint32_t j = 0; j < r.k; j++) {
+        ival = fr_add(ival, fr_mul(fr_load(&w[1 + j]), pw));
+        pw = fr_mul(pw, d);
+    }
     fr_store(&c[row], fr_sub(cw, ival));
     fr_store(&iv[row], ival);
     if (!fr_eq(fr_mul(av, bv), cw)) atomicMin(first_bad, (unsigned long long)row);
@@ -380,6 +459,8 @@ struct dvp_r1cs {
     dvp_ctx *ctx = nullptr;
     R1csDev dev;
     DevBuf bufs[10];
+    DevBuf tasks, coeffs29, w29; // 29-bit-limb row products: (row, matrix) tasks ordered by length per chunk
+    bool fast = false;
     DevBuf tbufs[9]; // transposed matrices (colptr, row, coeff id per matrix), built on the first setup
     bool t_ready = false;
     size_t nwires = 0;
@@ -684,6 +765,33 @@ int dvp_r1cs_load(dvp_ctx *ctx, size_t nrows, size_t k, size_t nwires, const uin
         r->dev.coeff[w] = (const uint32_t *)up(r->bufs[3 * w + 2], coeff[w], nnz * 4);
     }
     r->dev.coeffs = (const fr *)up(r->bufs[9], coeffs_mont, ncoeffs * 32);
+    if (!rc && nrows >= R1CS_CHUNK && ncoeffs) {
+        // (row, matrix) tasks, counting-sorted by term count (longest first) inside every chunk of rows
+        std::vector<uint32_t> tasks(3 * nrows), cnt;
+        size_t pos = 0;
+        for (size_t r0 = 0; r0 < nrows; r0 += R1CS_CHUNK) {
+            const size_t r1 = std::min(nrows, r0 + R1CS_CHUNK);
+            uint32_t mx = 0;
+            for (int w = 0; w < 3; w++)
+                for (size_t q = r0; q < r1; q++) mx = std::max(mx, rowptr[w][q + 1] - rowptr[w][q]);
+            cnt.assign((size_t)mx + 2, 0u);
+            for (int w = 0; w < 3; w++)
+                for (size_t q = r0; q < r1; q++) cnt[mx - (rowptr[w][q + 1] - rowptr[w][q]) + 1]++;
+            for (size_t i = 1; i < cnt.size(); i++) cnt[i] += cnt[i - 1];
+            for (int w = 0; w < 3; w++)
+                for (size_t q = r0; q < r1; q++)
+                    tasks[pos + cnt[mx - (rowptr[w][q + 1] - rowptr[w][q])]++] = (uint32_t)(q << 2) | (uint32_t)w;
+            pos += 3 * (r1 - r0);
+        }
+        up(r->tasks, tasks.data(), tasks.size() * 4);
+        up(r->coeffs29, coeffs_mont, ncoeffs * 32);
+        if (!rc) rc = r->w29.reserve(nwires * 32);
+        if (!rc) {
+            k_mats_to29<<<cdivp(ncoeffs, 128), 128, 0, ctx->stream>>>(r->coeffs29.as<fr>(), (uint32_t)ncoeffs);
+            if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = DVP_ERR_CUDA;
+        }
+        r->fast = rc == 0;
+    }
     if (rc) {
         for (auto &b : r->bufs) b.release();
         delete r;
@@ -697,6 +805,9 @@ void dvp_r1cs_destroy(dvp_r1cs *r) {
     cudaSetDevice(r->ctx->device);
     for (auto &b : r->bufs) b.release();
     for (auto &b : r->tbufs) b.release();
+    r->tasks.release();
+    r->coeffs29.release();
+    r->w29.release();
     delete r;
 }
 
@@ -714,8 +825,19 @@ static int r1cs_eval_device(dvp_r1cs *r, dvp_domain *d, const fr *d_w, fr *a, fr
     unsigned long long init = ~0ull, bad = 0;
     unsigned long long *d_bad = (unsigned long long *)ctx->small.p; // [0] mine, [8..8+W) gathered
     CKP(cudaMemcpyAsync(d_bad, &init, 8, cudaMemcpyHostToDevice, st));
-    k_r1cs_eval<<<cdivp(hi - lo, 128), 128, 0, st>>>(r->dev, (uint32_t)lo, (uint32_t)hi, d_w, d->leaves.as<fr>(), a, b, c,
-                                                    iv, d_bad);
+    if (r->fast && lo % R1CS_CHUNK == 0 && (hi % R1CS_CHUNK == 0 || hi >= r->dev.nrows)) {
+        // rows [lo, hi) own the tasks [3 lo, 3 min(hi, nrows)): chunks are whole
+        const uint32_t t_lo = 3 * (uint32_t)std::min<size_t>(lo, r->dev.nrows), t_hi = 3 * (uint32_t)std::min<size_t>(hi, r->dev.nrows);
+        k_fr_to29<<<cdivp(r->nwires, 128), 128, 0, st>>>(d_w, (uint32_t)r->nwires, r->w29.as<fr>());
+        if (t_hi > t_lo)
+            k_r1cs_sides<<<cdivp(t_hi - t_lo, 128), 128, 0, st>>>(r->dev, r->tasks.as<uint32_t>(), t_lo, t_hi, r->coeffs29.as<fr>(),
+                                                                 r->w29.as<fr>(), a, b, c);
+        k_r1cs_finish<<<cdivp(hi - lo, 128), 128, 0, st>>>(r->dev, (uint32_t)lo, (uint32_t)hi, d_w, d->leaves.as<fr>(), a, b, c,
+                                                          iv, d_bad);
+    } else {
+        k_r1cs_eval<<<cdivp(hi - lo, 128), 128, 0, st>>>(r->dev, (uint32_t)lo, (uint32_t)hi, d_w, d->leaves.as<fr>(), a, b,
+                                                        c, iv, d_bad);
+    }
     CKP(cudaGetLastError());
     if (W > 1) {
         const size_t chunk = (n / W) * sizeof(fr);

@@ -202,3 +202,34 @@ def test_device_setup_matches_oracle(ctx, oracle, lg):
     proof = prover.prove(w[1:1 + k], w[1 + k:])
     assert O.verify(td, dvpari.fr_from_mont(w[1:1 + k]), proof)
     prover.close(); inst.close(); gd.close()
+
+
+def test_r1cs_rows_fast_path_matches_oracle(ctx, oracle):
+    """get_matrix_evaluations_from_witness (proving.rs:348-403) on a circuit large enough for the 29-bit-limb row
+    products (length-sorted (row, matrix) tasks, three terms per Montgomery reduction): a, b, c, i byte-equal to the
+    oracle, and the first unsatisfied row is reported."""
+    O = oracle
+    lg = 13
+    circ = synth.synth_r1cs(lg, seed=4242, nlevels=8)
+    inst = dvpari.R1CSInstance(ctx, circ["nrows"], circ["k"], circ["nwires"], circ["rowptr"], circ["wire"],
+                               circ["coeff"], circ["coeffs_mont"])
+    w = inst.synth_solve(synth.synth_assignment(circ), circ["nlevels"])
+    r1cs = O.R1CS.from_arrays(circ["coeffs_mont"], circ["rowptr"], circ["wire"], circ["coeff"], circ["nrows"],
+                              circ["k"], circ["nwires"])
+    od = O.Domain(lg + 1)
+    gd = dvpari.Domain(ctx, lg + 1)
+    want, bad = O.r1cs_eval(r1cs, od, w)
+    assert bad == -1
+    got = inst.eval(gd, w)
+    for name, g, x in zip("abci", got, want):
+        assert g.tobytes() == x.tobytes(), name
+    w_bad = w.copy()
+    k = circ["k"]
+    w_bad[1 + k + 5000] = w_bad[1 + k + 5001]
+    _, want_bad = O.r1cs_eval(r1cs, od, w_bad)
+    assert want_bad >= 0
+    with pytest.raises(dvpari.DvpError) as e:
+        inst.eval(gd, w_bad)
+    assert e.value.code == 6 and str(want_bad) in str(e.value)
+    inst.close()
+    gd.close()

@@ -157,3 +157,19 @@ def test_ld_projective_addition_is_complete(oracle):
         s = O.pt_add(p, q)
         assert O.pt_encode(pt_from_row(O, out[i, :16])) == O.pt_encode(O.pt_add(s, s)), i
         assert not out[i, 16:].any(), i
+
+
+def test_fr29_three_term_dot_and_add():
+    """fr29_dotn<3> + fr29_add: the accumulation step of the R1CS row products (proving.rs:382-396)."""
+    rnd = random.Random(30)
+    vals = [0, 1, P - 1, P - 2, 1 << 231, (1 << 231) - 1] + [rnd.randrange(P) for _ in range(300)]
+    m0, x0 = [P - 1] + vals, [P - 1] + vals[3:] + vals[:3]
+    m1, x1 = [P - 1] + vals[7:] + vals[:7], [P - 1] + vals[1:] + vals[:1]
+    n = len(m0)
+    A = np.concatenate([dvpari.fr_to_mont(m0), dvpari.fr_to_mont(x0)], axis=1).view(np.uint32).reshape(-1, 16)
+    B = np.concatenate([dvpari.fr_to_mont(m1), dvpari.fr_to_mont(x1)], axis=1).view(np.uint32).reshape(-1, 16)
+    out = np.zeros((n, 8), dtype=np.uint32)
+    dvpari._ck(dvpari.lib().dvp_hostcheck_op(18, dvpari._ptr(A), dvpari._ptr(B), dvpari._ptr(out), n))
+    # the addend m1 is in Montgomery form like the products, i.e. the value added is m1
+    want = [(a * b + c * d + a * d + c) % P for a, b, c, d in zip(m0, x0, m1, x1)]
+    assert out.view(np.uint64).reshape(-1, 4).tobytes() == dvpari.fr_to_mont(want).tobytes()
