@@ -283,6 +283,11 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
         ctx->msm_tables_min = (size_t)value;
         return DVP_OK;
     }
+    if (!strcmp(name, "ld_tree_max")) {
+        if (value != 0 && value < 64) return DVP_ERR_BAD_ARG;
+        ctx->msm.ld_tree_max = (size_t)value;
+        return DVP_OK;
+    }
     if (!strcmp(name, "b64_min")) {
         ctx->msm.b64_min = value > 0 ? (size_t)value : ((size_t)1 << 23);
         return DVP_OK;

@@ -845,7 +845,6 @@ void MsmEngine::destroy() {
 namespace {
 
 constexpr uint32_t PLAN_MAX_BLOCKS = 256; // k_plan's grid must be co-resident (blocks wait for their predecessors)
-constexpr size_t LD_TREE_MAX_POINTS = (size_t)1 << 17; // above this a reduction level starts with affine rounds
 constexpr uint32_t BINV_G = 16;        // group size of one batched-inversion level (large batches)
 
 struct Tree {
@@ -1339,6 +1338,9 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         RS(L.ents2, (size_t)std::max(p.nent_a, p.nent_b) * 4);
     }
 #undef RS
+    // a reduction level with more points than this starts with batched-affine rounds: large MSMs are throughput-bound
+    // (5 instead of 15 multiplications per addition), small ones latency-bound (one launch instead of a round's six)
+    const size_t ld_max = ld_tree_max ? ld_tree_max : (n >= (1u << 21) ? (size_t)1 << 13 : (size_t)1 << 16);
     if (timing) cudaEventRecord(ev[3], st);
     // ---- per lane: accumulate buckets, then the two reduction levels into this lane's slice of hb
     for (int l = 0; l < NL; l++) {
@@ -1367,8 +1369,8 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
             k_gen_segs_a<<<cdiv(p.nseg_a + 1, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, d_start, d_len);
             // large levels start with batched-affine rounds (5 instead of 15 multiplications per addition) and
             // switch to the inversion-free tree once the work is latency-bound
-            Tree::Partial part_a{LD_TREE_MAX_POINTS, nullptr, nullptr, nullptr, 0};
-            if (p.nent_a > LD_TREE_MAX_POINTS) {
+            Tree::Partial part_a{ld_max, nullptr, nullptr, nullptr, 0};
+            if (p.nent_a > ld_max) {
                 if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a, false))) return rc;
                 rc = tree.rounds(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,
                                  std::max(R, m), nullptr, &r_a, &part_a);

@@ -82,6 +82,7 @@ struct MsmEngine {
     float prof_ms[PC_COUNT] = {0};
     unsigned prof_n[PC_COUNT] = {0};
     size_t b64_min = (size_t)1 << 23; // rounds with at least this many additions chain 64 per thread (off by default)
+    size_t ld_tree_max = 0; // 0 = automatic; a reduction level with more points starts with batched-affine rounds
     uint32_t binv_direct = 32768; // batches up to this size are inverted one element per thread
     int pass2_minb = 2; // resident blocks per SM the pass-2 kernel is compiled for (register cap)
 
