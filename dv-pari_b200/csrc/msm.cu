@@ -1177,13 +1177,13 @@ int MsmEngine::mulgen(const uint32_t *d_scalars, size_t n, AffPt *d_out) {
     return 0;
 }
 
-// cost model of the shared-bucket-set layout: W n bucket additions + ~1.5 * 2^c for the reduction
+// cost model of the shared-bucket-set layout: W n bucket additions + ~3 * 2^c for the reduction (measured optimum)
 int choose_table_windows(size_t n) {
     int best = 16;
     double best_cost = 1e300;
     for (int W = 9; W <= 30; W++) {
         const int c = 233 / W + (233 % W ? 1 : 0);
-        const double cost = (double)n * W + 1.5 * (double)(1ull << c);
+        const double cost = (double)n * W + 3.0 * (double)(1ull << c);
         if (cost < best_cost) best_cost = cost, best = W;
     }
     return best;

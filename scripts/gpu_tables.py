@@ -12,7 +12,7 @@ for lg in [int(a) for a in sys.argv[1:]] or [20]:
     ctx.set("msm_tables", 0)
     ref = ctx.multi_scalar_mul_device(d, n, 0)
     ctx.set("msm_tables", 1)
-    for cb in (0, 10, 11, 12, 13, 14, 15, 16):
+    for cb in (0, 12, 13, 14, 15, 16, 17, 18, 20, 22):
         ctx.set("msm_table_windows", cb)
         t0 = time.perf_counter(); out = ctx.multi_scalar_mul_device(d, n, 0); tb = time.perf_counter() - t0
         assert out == ref, cb
