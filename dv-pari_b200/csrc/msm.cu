@@ -4,17 +4,20 @@
 // src/proving.rs:463,512,680).  The reference does one tau-adic scalar multiplication per point and
 // a tree sum; the group element is unique, so any algorithm matches bit for bit.  Here:
 //
-//   recode      Montgomery Fr -> canonical 232-bit integer -> W signed c-bit digits
-//   sort        counting sort of (point, window) entries by bucket (histogram, scan, scatter)
+//   recode      Montgomery Fr -> canonical 232-bit integer -> W signed digits (windows of even width)
+//   sort        global counting sort of the (point, window) entries by bucket (histogram, scan, scatter).
+//               Resident SRS slots carry tables T[j] = 2^(off_j) P, so all windows share ONE bucket set.
 //   plan        per round one launch: scans over the segment lengths + one (a, b, out) descriptor per addition
 //   accumulate  every bucket is a segment; segments are tree-reduced in rounds of independent
-//               affine additions sharing one inversion (Montgomery trick, hierarchical)
-//   reduce      sum_b (b+1) B_b per window without a serial running sum: rows/columns of the bucket
-//               matrix (level A), then per-bit subset sums (level B), both on the same tree engine
-//   tail        the host folds the W*c per-bit partial sums with one 232-step double-and-add
+//               affine additions sharing one inversion (Montgomery trick, hierarchical), on 2 lanes (streams)
+//   reduce      sum_b (b+1) B_b per virtual window without a serial running sum: rows/columns of the bucket
+//               matrix (level A), then per-bit subset sums (level B); batched-affine rounds while large,
+//               inversion-free Lopez-Dahab trees (one block per segment) for the rest
+//   tail        the host folds the per-bit partial sums with one double-and-add pass (PCLMULQDQ)
 //
-// Everything between the scalars and the W*c partial sums stays on the device; a single 8-byte
-// read-back (the longest bucket) sizes the rounds.
+// Everything between the scalars and the partial sums stays on the device; a single 8-byte-per-lane
+// read-back (entries and longest bucket) sizes the rounds.  Also here: the batched fixed-base multiplication
+// (mulgen) and the table builder, both expressed as tree rounds.
 #include "msm.cuh"
 #include <algorithm>
 #include <chrono>
@@ -777,7 +780,6 @@ __global__ void __launch_bounds__(256)
 int MsmLane::init() {
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-    CK(cudaMallocHost(&h_info, 64));
     for (auto &e : ev_k) CK(cudaEventCreate(&e));
     for (auto &e : ev_s) CK(cudaEventCreate(&e));
     return 0;
@@ -805,8 +807,6 @@ void MsmLane::destroy() {
                      &blk, &blk_flag, &info, &info_r0, &pp[0], &pp[1], &prefix, &desc, &thr_total, &thr_inv, &lvl_pre[0],
                      &lvl_pre[1], &lvl_tot[0], &lvl_tot[1], &lvl_inv[0], &lvl_inv[1], &buckets, &rc, &ents2};
     for (auto b : all) b->release();
-    if (h_info) cudaFreeHost(h_info);
-    h_info = nullptr;
     for (auto &e : ev_k)
         if (e) cudaEventDestroy(e), e = nullptr;
     for (auto &e : ev_s)
@@ -957,11 +957,8 @@ struct Tree {
 
     // Plan of round 0: caller tables -> lane set 1 (+ descriptors); info[0] = longest segment,
     // info[1] = additions of round 0.
-    int plan0(const uint32_t *start0, const uint32_t *len0, const uint32_t *ent, uint32_t nseg, bool readback) {
-        int rc = plan(len0, start0, ent, nseg, L.seg_start[1].as<uint32_t>(), L.seg_len[1].as<uint32_t>());
-        if (rc) return rc;
-        if (readback) CK(cudaMemcpyAsync(L.h_info, L.info.p, 16, cudaMemcpyDeviceToHost, st));
-        return 0;
+    int plan0(const uint32_t *start0, const uint32_t *len0, const uint32_t *ent, uint32_t nseg) {
+        return plan(len0, start0, ent, nseg, L.seg_start[1].as<uint32_t>(), L.seg_len[1].as<uint32_t>());
     }
 
     // Reduce every segment of the index list `ent` over `src` to one point: dst[s], s < nseg, given that
@@ -1363,7 +1360,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         if (timing && l == 0) cudaEventRecord(L.ev_s[0], L.stream);
         Tree tree(*this, L);
         const uint32_t *len0 = d_len_all + bounds[l], *start0 = d_start_all + bounds[l];
-        if ((rc = tree.plan0(start0, len0, entries.as<uint32_t>(), p.nseg, false))) return rc;
+        if ((rc = tree.plan0(start0, len0, entries.as<uint32_t>(), p.nseg))) return rc;
         if (timing && l == 0) CK(cudaMemcpyAsync(L.info_r0.p, L.info.p, 16, cudaMemcpyDeviceToDevice, L.stream));
         L.want_k = timing && l == 0;
         int r_main = 0, r_a = 0, r_b = 0;
@@ -1382,7 +1379,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
             // switch to the inversion-free tree once the work is latency-bound
             Tree::Partial part_a{ld_max, nullptr, nullptr, nullptr, 0};
             if (p.nent_a > ld_max) {
-                if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a, false))) return rc;
+                if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a))) return rc;
                 rc = tree.rounds(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,
                                  std::max(R, m), nullptr, &r_a, &part_a);
                 if (rc) return rc;
@@ -1412,14 +1409,14 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
             k_gen_level_a<<<cdiv(p.nent_a, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, L.ents2.as<uint32_t>());
             k_gen_segs_a<<<cdiv(p.nseg_a + 1, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, d_start, d_len);
             L.launches += 2;
-            if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a, false))) return rc;
+            if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a))) return rc;
             rc = tree.rounds(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,
                              std::max(R, m), L.rc.as<AffPt>(), &r_a);
             if (rc) return rc;
             k_gen_level_b<<<cdiv(p.nent_b, 256), 256, 0, L.stream>>>(p.vn, lr, lm, L.ents2.as<uint32_t>());
             k_gen_segs_b<<<cdiv(p.nseg_b + 1, 256), 256, 0, L.stream>>>(p.vn, lr, lm, d_start, d_len);
             L.launches += 2;
-            if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_b, false))) return rc;
+            if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_b))) return rc;
             rc = tree.rounds(L.rc.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_b, p.nent_b,
                              std::max(R >> 1, m), hb.as<AffPt>() + (size_t)p.v0 * cv, &r_b);
             if (rc) return rc;

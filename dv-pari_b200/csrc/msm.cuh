@@ -28,8 +28,8 @@ struct MsmStats {
     unsigned long long adds_round0 = 0, adds_total = 0;
 };
 
-// One independent chain of tree rounds: its own stream and scratch.  The windows of an MSM are split
-// over the lanes so that the latency-bound late rounds of one lane overlap the big early rounds of another.
+// One independent chain of tree rounds: its own stream and scratch.  The virtual windows of an MSM (bucket ranges)
+// are split over the lanes so that the latency-bound inversion chains of one lane overlap the large kernels of another.
 // launch categories of the development profiler
 enum { PC_SORT = 0, PC_PLAN, PC_PASS1, PC_BINV_UP, PC_BINV_DIRECT, PC_BINV_DOWN, PC_PASS2, PC_MISC, PC_COUNT };
 
@@ -38,7 +38,6 @@ struct MsmLane {
     cudaEvent_t done = nullptr;
     DevBuf seg_len[2], seg_start[2], c_len, c_start, blk, blk_flag, info, info_r0, pp[2], prefix, desc,
         thr_total, thr_inv, lvl_pre[2], lvl_tot[2], lvl_inv[2], buckets, rc, ents2;
-    void *h_info = nullptr; // pinned, 64 bytes
     unsigned long long launches = 0;
     uint32_t epoch = 0; // k_plan launch counter (the blocks' publish flag)
     // profiler: (category, start, stop) per bracket; events are pooled
