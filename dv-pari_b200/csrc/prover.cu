@@ -474,6 +474,7 @@ struct dvp_prover {
     DevBuf wit, dinv, pre, tot, tot2, pre2, part;
     void *h_part = nullptr;
     float ms[8] = {0};
+    cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 // host-side Fr helpers on the isogeny chain
@@ -921,8 +922,10 @@ int dvp_prover_create(dvp_ctx *ctx, dvp_domain *dom, dvp_r1cs *r1cs, int slot_gm
         const int sl[3] = {slot_gm, slot_gq, slot_gk};
         for (int i = 0; i < 3; i++) {
             size_t lo, hi;
-            dvp_shard_range(tot[i], ctx->rank, ctx->world, &lo, &hi);
-            if (sl[i] < 0 || sl[i] >= DVP_MAX_SRS_SLOTS || ctx->slots[sl[i]].n != hi - lo) return DVP_ERR_LENGTH_MISMATCH;
+            // g_k is sharded by the index range of D: g_k_0[ilo, ihi) | g_k_1[ilo, ihi) | g_k_2[2 ilo, 2 ihi)
+            dvp_shard_range(i == 2 ? n : tot[i], ctx->rank, ctx->world, &lo, &hi);
+            const size_t want = i == 2 ? 4 * (hi - lo) : hi - lo;
+            if (sl[i] < 0 || sl[i] >= DVP_MAX_SRS_SLOTS || ctx->slots[sl[i]].n != want) return DVP_ERR_LENGTH_MISMATCH;
         }
     }
     CKP(cudaSetDevice(ctx->device));
@@ -952,6 +955,8 @@ void dvp_prover_destroy(dvp_prover *p) {
     DevBuf *all[] = {&p->vec, &p->wit, &p->dinv, &p->pre, &p->tot, &p->tot2, &p->pre2, &p->part};
     for (auto b : all) b->release();
     if (p->h_part) cudaFreeHost(p->h_part);
+    for (auto &e : p->ev)
+        if (e) cudaEventDestroy(e);
     delete p;
 }
 
@@ -983,11 +988,11 @@ __global__ void k_frb_down2(fr *__restrict__ inout, uint32_t n, const fr *__rest
     }
 }
 
-static int denominators(dvp_prover *p, const fr &alpha) {
+// dinv[j] = 1/(leaves[leaf_lo + j] - alpha) for j < n2 (a rank's range of the leaves; all of them on one GPU)
+static int denominators(dvp_prover *p, const fr &alpha, size_t leaf_lo, uint32_t n2) {
     cudaStream_t st = p->ctx->stream;
-    const uint32_t n2 = p->dom->n2;
     const uint32_t ng = cdivp(n2, FRB), ng2 = cdivp(ng, FRB);
-    const fr *leaves = p->dom->leaves.as<fr>();
+    const fr *leaves = p->dom->leaves.as<fr>() + leaf_lo;
     k_frb_up<<<cdivp(ng, 128), 128, 0, st>>>(leaves, alpha, n2, p->pre.as<fr>(), p->tot.as<fr>());
     k_frb_up2<<<cdivp(ng2, 64), 64, 0, st>>>(p->tot.as<fr>(), ng, p->pre2.as<fr>(), p->tot2.as<fr>());
     k_frb_down2<<<cdivp(ng2, 64), 64, 0, st>>>(p->tot.as<fr>(), ng, p->pre2.as<fr>(), p->tot2.as<fr>());
@@ -1014,9 +1019,10 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     if (k != r->dev.k) return DVP_ERR_BAD_ARG;                    // assert_eq!(inst.num_public_inputs, ..) proving.rs:361
     if (1 + k + npriv != r->nwires) return DVP_ERR_LENGTH_MISMATCH; // msm(assignment, g_m) length check, curve.rs:142
     CKP(cudaSetDevice(ctx->device));
-    cudaEvent_t ev[8], ev_h2d;
-    cudaEventCreate(&ev_h2d);
-    for (auto &e : ev) cudaEventCreate(&e);
+    // stage-timing events live in the prover handle (created once), so error returns leak nothing
+    cudaEvent_t *ev = p->ev, &ev_h2d = p->ev[8];
+    if (!p->ev[0])
+        for (auto &e : p->ev) cudaEventCreate(&e);
     cudaEventRecord(ev[0], st);
     fr *V = p->vec.as<fr>();
     fr *a = V, *b = V + n, *c = V + 2 * n, *iv = V + 3 * n, *a2 = V + 4 * n, *b2 = V + 5 * n, *c2 = V + 6 * n,
@@ -1110,11 +1116,16 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     uint32_t alc[8];
     memcpy(alc, al, 32);
     const fr alpha = fr_from_canonical(alc);
-    // 1/(leaf - alpha) for all 2n leaves; a zero denominator means alpha is in D u D'
-    if ((rc = denominators(p, alpha))) return rc;
+    // From here every rank works on its own index range [ilo, ihi) of D and D' (all of it on one GPU): the
+    // denominators 1/(leaf - alpha), the partial barycentric sums and its part of the K scalars.  The g_k shard of a
+    // rank is g_k_0[ilo, ihi) | g_k_1[ilo, ihi) | g_k_2[2 ilo, 2 ihi), which is exactly what its K scalars multiply.
+    size_t ilo, ihi;
+    dvp_shard_range(n, R, W, &ilo, &ihi);
+    const uint32_t cnt = (uint32_t)(ihi - ilo);
+    if ((rc = denominators(p, alpha, 2 * ilo, 2 * cnt))) return rc;
     // a0, b0 by barycentric evaluation, i0 by Horner (ec_fft.rs:455-491, srs.rs:412)
     const int nblk = 592;
-    k_bary_partial<<<nblk, 256, 0, st>>>(a, b, d->bar_wts.as<fr>(), p->dinv.as<fr>(), (uint32_t)n, p->part.as<fr>());
+    k_bary_partial<<<nblk, 256, 0, st>>>(a + ilo, b + ilo, d->bar_wts.as<fr>() + ilo, p->dinv.as<fr>(), cnt, p->part.as<fr>());
     CKP(cudaGetLastError());
     CKP(cudaMemcpyAsync(p->h_part, p->part.p, 2 * nblk * sizeof(fr), cudaMemcpyDeviceToHost, st));
     CKP(cudaStreamSynchronize(st));
@@ -1126,6 +1137,23 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
         sa = fr_add(sa, hp[2 * i]);
         sb = fr_add(sb, hp[2 * i + 1]);
     }
+    if (W > 1) {
+        // sum of the ranks' partial sums: all-gather of 64 bytes per rank
+        if ((rc = ctx->commbuf.reserve((size_t)(W + 1) * 2 * sizeof(fr)))) return rc;
+        fr *cb = ctx->commbuf.as<fr>();
+        const fr mine[2] = {sa, sb};
+        CKP(cudaMemcpyAsync(cb + 2 * W, mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+        if ((rc = comm_all_gather(ctx, cb + 2 * W, cb, sizeof(mine)))) return rc;
+        fr all[128];
+        CKP(cudaMemcpyAsync(all, cb, (size_t)W * sizeof(mine), cudaMemcpyDeviceToHost, st));
+        CKP(cudaStreamSynchronize(st));
+        sa = fr_zero();
+        sb = fr_zero();
+        for (int i = 0; i < W; i++) {
+            sa = fr_add(sa, all[2 * i]);
+            sb = fr_add(sb, all[2 * i + 1]);
+        }
+    }
     const fr a0 = fr_mul(sa, za), b0 = fr_mul(sb, za);
     fr i0 = fr_zero(), pw = fr_one();
     for (size_t j = 0; j < k; j++) {
@@ -1133,13 +1161,16 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
         pw = fr_mul(pw, alpha);
     }
     const fr r0 = fr_sub(fr_mul(a0, b0), i0);
-    k_kscalars<<<cdivp(n, 128), 128, 0, st>>>(a, b, iv, c2, p->dinv.as<fr>(), a0, b0, r0, (uint32_t)n, ks);
+    // ks: k_a | k_b | k_r of this rank's range, contiguous (4 cnt scalars; with one rank the reference's own order)
+    k_kscalars<<<cdivp(cnt, 128), 128, 0, st>>>(a + ilo, b + ilo, iv + ilo, c2 + ilo, p->dinv.as<fr>(), a0, b0, r0, cnt, ks);
     CKP(cudaGetLastError());
     cudaEventRecord(ev[5], st);
     if (stages) {
         CKP(cudaMemcpyAsync(stages + 8 * n * 4, q, 5 * n * 32, cudaMemcpyDeviceToHost, st));
         CKP(cudaStreamSynchronize(st));
     }
+    klo = 0;
+    khi = 4 * (size_t)cnt;
     if ((rc = slot_msm(ctx, p->slot_gk, 0, (const uint32_t *)(ks + klo), khi - klo, &part))) return rc;
     if ((rc = comm_fold_points(ctx, part, &kzg))) return rc;
     cudaEventRecord(ev[6], st);
@@ -1156,8 +1187,6 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     cudaEventElapsedTime(&p->ms[5], ev[5], ev[6]);
     cudaEventElapsedTime(&p->ms[6], ev[0], ev_h2d); // witness upload, part of ms[0]
     p->ms[0] -= p->ms[6];
-    cudaEventDestroy(ev_h2d);
-    for (auto &e : ev) cudaEventDestroy(e);
     return DVP_OK;
 }
 
@@ -1438,16 +1467,28 @@ int dvp_setup(dvp_r1cs *r, dvp_domain *d, const uint64_t trapdoor_mont[12], int 
     if (rc) return rc;
     fr *o = out.as<fr>();
     rc = setup_scalars_device(r, d, td[0], td[1], td[2], o, o + nw, o + nw + n);
-    const size_t tot[3] = {nw, n, 4 * n};
-    const fr *base[3] = {o, o + nw, o + nw + n};
+    // g_m and g_q: contiguous ranges; g_k: g_k_0[ilo, ihi) | g_k_1[ilo, ihi) | g_k_2[2 ilo, 2 ihi) for the rank's range of D
+    size_t ilo, ihi;
+    dvp_shard_range(n, ctx->rank, ctx->world, &ilo, &ihi);
+    const size_t cnt = ihi - ilo;
     for (int i = 0; i < 3 && !rc; i++) {
         size_t lo, hi;
-        dvp_shard_range(tot[i], ctx->rank, ctx->world, &lo, &hi);
+        dvp_shard_range(i == 0 ? nw : n, ctx->rank, ctx->world, &lo, &hi);
+        const size_t m = i == 2 ? 4 * cnt : hi - lo;
         SrsSlot &s = ctx->slots[slots[i]];
         s.invalidate();
-        if ((rc = s.buf.reserve((hi - lo ? hi - lo : 1) * sizeof(AffPt)))) break;
-        s.n = hi - lo;
-        if (hi > lo) rc = ctx->msm.mulgen((const uint32_t *)(base[i] + lo), hi - lo, s.buf.as<AffPt>());
+        if ((rc = s.buf.reserve((m ? m : 1) * sizeof(AffPt)))) break;
+        s.n = m;
+        if (!m) continue;
+        if (i < 2) {
+            rc = ctx->msm.mulgen((const uint32_t *)((i == 0 ? o : o + nw) + lo), m, s.buf.as<AffPt>());
+        } else {
+            const fr *sk = o + nw + n;
+            AffPt *dst = s.buf.as<AffPt>();
+            rc = ctx->msm.mulgen((const uint32_t *)(sk + ilo), cnt, dst);
+            if (!rc) rc = ctx->msm.mulgen((const uint32_t *)(sk + n + ilo), cnt, dst + cnt);
+            if (!rc) rc = ctx->msm.mulgen((const uint32_t *)(sk + 2 * n + 2 * ilo), 2 * cnt, dst + 2 * cnt);
+        }
     }
     out.release();
     return rc;

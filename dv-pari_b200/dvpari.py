@@ -325,6 +325,13 @@ def shard_range(total, rank, world):
     return lo.value, hi.value
 
 
+def gk_shard_indices(n, rank, world):
+    """Indices into g_k = g_k_0 | g_k_1 | g_k_2 (4n points, proving.rs:666-673) of the points rank `rank` holds:
+    g_k_0[ilo, ihi) | g_k_1[ilo, ihi) | g_k_2[2 ilo, 2 ihi) for its range [ilo, ihi) of D."""
+    ilo, ihi = shard_range(n, rank, world)
+    return np.concatenate([np.arange(ilo, ihi), n + np.arange(ilo, ihi), 2 * n + np.arange(2 * ilo, 2 * ihi)])
+
+
 def hostcheck_op(op, a, b=None, out_stride=None):
     """Same __host__ __device__ source as the kernels, evaluated on the CPU (tests only)."""
     a = np.ascontiguousarray(a)

@@ -103,8 +103,11 @@ int dvp_msm_last_profile(dvp_ctx *ctx, float ms[8], unsigned count[8]);
  * Multi-GPU: one process (context) per GPU.  The MSMs shard by contiguous point range, the row evaluation by row
  * range, the extends by polynomial; exchanges run over NCCL (NVLink / NVSwitch) on the context's stream.
  * Rank 0 makes a unique id, the host ships it to the other ranks by any channel, every rank calls dvp_comm_init.
- * With a communicator set, dvp_prover_create expects the SRS slots to hold THIS RANK'S range of g_m / g_q / g_k
- * (dvp_shard_range of nwires / n / 4n) and dvp_prove returns the same proof on every rank.
+ * With a communicator set, dvp_prover_create expects the SRS slots to hold THIS RANK'S part of the SRS and dvp_prove
+ * returns the same proof on every rank:  g_m[lo, hi) with dvp_shard_range(nwires);  g_q[ilo, ihi) with
+ * dvp_shard_range(n);  g_k as g_k_0[ilo, ihi) | g_k_1[ilo, ihi) | g_k_2[2 ilo, 2 ihi) (the three files of
+ * src/proving.rs:666-673 cut by the same index range of D, so that a rank's K scalars need only its own range of the
+ * denominators).  dvp_setup fills the slots in exactly this layout.
  */
 int dvp_comm_unique_id(uint8_t id[128]);
 int dvp_comm_init(dvp_ctx *ctx, const uint8_t id[128], int rank, int world);

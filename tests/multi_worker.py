@@ -50,11 +50,16 @@ def main():
                               circ["k"], circ["nwires"])
     od = O.Domain(lg + 1)
     rnd = random.Random(lg)
-    td = O.trapdoor(rnd.randrange(1, P), rnd.randrange(1, P), rnd.randrange(1, P))
+    tdi = [rnd.randrange(1, P) for _ in range(3)]
+    td = O.trapdoor(*tdi)
     scs = O.setup_scalars(r1cs, od, td)
+    n = circ["n"]
     for slot, s in enumerate(scs):
-        lo, hi = dvpari.shard_range(s.shape[0], rank, world)
-        ctx.srs_mulgen(slot, s[lo:hi])
+        if slot < 2:
+            lo, hi = dvpari.shard_range(s.shape[0], rank, world)
+            ctx.srs_mulgen(slot, s[lo:hi])
+        else:  # g_k: the three parts cut by this rank's index range of D
+            ctx.srs_mulgen(slot, s[dvpari.gk_shard_indices(n, rank, world)])
     gd = dvpari.Domain(ctx, lg + 1)
     prover = dvpari.Prover(ctx, gd, inst, 0, 1, 2)
     k = circ["k"]
@@ -75,6 +80,11 @@ def main():
     outs = [None] * world
     dist.all_gather_object(outs, proof)
     assert all(o == outs[0] for o in outs)
+    # the same proof from an SRS made by the sharded device setup (dvp_setup fills every rank's slots itself)
+    dvpari.setup(inst, gd, tdi, 3, 4, 5)
+    prover2 = dvpari.Prover(ctx, gd, inst, 3, 4, 5)
+    assert prover2.prove(w[1:1 + k], w[1 + k:]) == proof
+    prover2.close()
     print(f"rank {rank}/{world}: sharded msm + prove 2^{lg} OK {prover.last_times()}", flush=True)
     prover.close(); inst.close(); gd.close()
     ctx.comm_destroy()

@@ -63,6 +63,12 @@ def test_shard_range_partitions():
                 assert lo == prev and hi >= lo and hi - lo <= total // world + 1
                 prev = hi
             assert prev == total
+    # g_k is cut by the index range of D: every point of the 4n vector belongs to exactly one rank
+    n = 1 << 10
+    for world in (1, 2, 4, 8):
+        idx = np.concatenate([dvpari.gk_shard_indices(n, r, world) for r in range(world)])
+        assert idx.size == 4 * n and np.array_equal(np.sort(idx), np.arange(4 * n))
+        assert all(dvpari.gk_shard_indices(n, r, world).size == 4 * n // world for r in range(world))
     # the ownership rules of the sharded prove: rows need world | n, polynomial p lives on rank p % world
     assert [p % 2 for p in range(3)] == [0, 1, 0] and [p % 8 for p in range(3)] == [0, 1, 2]
 
