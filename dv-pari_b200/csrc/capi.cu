@@ -223,7 +223,9 @@ int dvp_ctx_create(int device, dvp_ctx **out) {
         delete c;
         return DVP_ERR_CUDA;
     }
-    if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming) != cudaSuccess) {
         dvp_ctx_destroy(c);
         return DVP_ERR_CUDA;

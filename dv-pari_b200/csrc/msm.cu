@@ -778,7 +778,11 @@ __global__ void __launch_bounds__(256)
 // host orchestration
 // ------------------------------------------------------------------------------------------------
 int MsmLane::init() {
-    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    // high priority: when an MSM overlaps throughput-bound work on another stream (dvp_prove runs the g_m MSM beside the
+    // extends), its short latency-bound kernels must not queue behind that work's blocks
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    CK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
     CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
     for (auto &e : ev_k) CK(cudaEventCreate(&e));
     for (auto &e : ev_s) CK(cudaEventCreate(&e));
