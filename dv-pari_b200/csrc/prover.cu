@@ -207,6 +207,54 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// The deepest levels of an extend work on sub-problems of at most EXT_FUSE_M points: one block stages a whole
+// sub-problem in shared memory (as 29-bit limbs, converted once on the way in and once on the way out), runs its
+// decompose levels down and its recombine levels up with a block barrier between levels, and writes it back -- one
+// launch and one round trip to HBM instead of two per level.
+constexpr int EXT_FUSE_LOG = 11;
+constexpr uint32_t EXT_FUSE_M = 1u << EXT_FUSE_LOG;
+struct FusedMats {
+    const fr *dec[EXT_FUSE_LOG], *rec[EXT_FUSE_LOG];
+};
+__global__ void __launch_bounds__(256)
+    k_extend_fused(fr *__restrict__ data, int logm, int logc, FusedMats fm, uint32_t blocks_per_poly, size_t poly_stride) {
+    extern __shared__ __align__(16) unsigned char ext_sm_raw[];
+    fr *sm = reinterpret_cast<fr *>(ext_sm_raw); // fr29 limbs stored in fr-sized slots
+    // a block stages C = 2^logc points = C / 2^logm whole sub-problems of size 2^logm (they tile the chunk)
+    const uint32_t M = 1u << logc;
+    fr *base = data + (size_t)(blockIdx.x / blocks_per_poly) * poly_stride + (size_t)(blockIdx.x % blocks_per_poly) * M;
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
+        const fr29 v = fr29_from_fr(fr_load(&base[i]));
+        fr o;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o.v[k] = v.l[k];
+        fr_store(&sm[i], o);
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 2 * logm; pass++) {
+        const int k = pass < logm ? pass : 2 * logm - 1 - pass; // levels 0 .. logm-1 down, then back up
+        const fr *mats = pass < logm ? fm.dec[k] : fm.rec[k];
+        const uint32_t h = (1u << logm) >> (k + 1);
+        for (uint32_t g = threadIdx.x; g < (M >> 1); g += blockDim.x) {
+            const uint32_t j = g % h, i0 = (g / h) * 2 * h + j, i1 = i0 + h;
+            const fr29 m0 = fr29_load(&mats[4 * j]), m1 = fr29_load(&mats[4 * j + 1]);
+            const fr29 m2 = fr29_load(&mats[4 * j + 2]), m3 = fr29_load(&mats[4 * j + 3]);
+            const fr29 x0 = fr29_load(&sm[i0]), x1 = fr29_load(&sm[i1]);
+            const fr29 y0 = fr29_dot2(m0, x0, m1, x1), y1 = fr29_dot2(m2, x0, m3, x1);
+            fr o0, o1;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                o0.v[q] = y0.l[q];
+                o1.v[q] = y1.l[q];
+            }
+            fr_store(&sm[i0], o0);
+            fr_store(&sm[i1], o1);
+        }
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) fr_store(&base[i], fr_from_fr29(fr29_load(&sm[i])));
+}
+
 // ------------------------------------------------------------------------------------------------
 // R1CS rows: a = A w, b = B w, c = C w - i, i = sum_j x_j d^j; first unsatisfied row recorded
 // ------------------------------------------------------------------------------------------------
@@ -687,16 +735,44 @@ int dvp_domain_vanish_at(dvp_domain *d, int shift, const uint64_t x_mont[4], uin
 }
 
 // in-place extend of npoly vectors of n Fr (device), D -> D'
+// the levels of sub-problems of size <= EXT_FUSE_M in one launch: `count` contiguous groups ("polys") of
+// per_poly points each, poly_stride elements apart; per_poly is a multiple of the sub-problem size
+static int extend_fused_launch(dvp_domain *d, fr *data, uint32_t count, uint32_t per_poly, size_t poly_stride) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CKP(cudaFuncSetAttribute(k_extend_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXT_FUSE_M * sizeof(fr))));
+        attr_set = true;
+    }
+    const int logm = std::min(d->levels, EXT_FUSE_LOG), K = d->levels - logm;
+    FusedMats fm;
+    for (int k = 0; k < EXT_FUSE_LOG; k++) {
+        fm.dec[k] = k < logm ? d->dec[K + k].as<fr>() : nullptr;
+        fm.rec[k] = k < logm ? d->rec[K + k].as<fr>() : nullptr;
+    }
+    // chunk = whole sub-problems, at most EXT_FUSE_M points, but small enough that the grid still covers the SMs twice
+    int logc = logm;
+    while (logc < EXT_FUSE_LOG && (2u << logc) <= per_poly && ((size_t)count * per_poly >> (logc + 1)) >= 296) logc++;
+    const uint32_t blocks_per_poly = per_poly >> logc;
+    k_extend_fused<<<count * blocks_per_poly, 256, ((size_t)1 << logc) * sizeof(fr), d->ctx->stream>>>(
+        data, logm, logc, fm, blocks_per_poly, poly_stride);
+    CKP(cudaGetLastError());
+    return 0;
+}
+
+// in-place extend of npoly vectors of n Fr (device), D -> D'
 static int extend_device(dvp_domain *d, fr *data, int npoly, size_t stride) {
     cudaStream_t st = d->ctx->stream;
     const uint32_t n = d->n;
+    const int K = std::max(0, d->levels - EXT_FUSE_LOG); // levels above the fused ones
+    int rc;
     // polynomials in groups of at most 3 (the prover's a, b, c) share each matrix read
     for (int p0 = 0; p0 < npoly; p0 += 3) {
         const int np = std::min(3, npoly - p0);
         fr *base = data + (size_t)p0 * stride;
-        for (int k = 0; k < d->levels; k++)
+        for (int k = 0; k < K; k++)
             k_extend_level<3><<<cdivp(n / 2, 256), 256, 0, st>>>(base, n, n >> (k + 1), d->dec[k].as<fr>(), np, stride);
-        for (int k = d->levels - 1; k >= 0; k--)
+        if ((rc = extend_fused_launch(d, base, (uint32_t)np, n, stride))) return rc;
+        for (int k = K - 1; k >= 0; k--)
             k_extend_level<3><<<cdivp(n / 2, 256), 256, 0, st>>>(base, n, n >> (k + 1), d->rec[k].as<fr>(), np, stride);
     }
     CKP(cudaGetLastError());
@@ -1535,9 +1611,12 @@ __global__ void k_enter_combine(const fr *__restrict__ cur, const fr *__restrict
 static int extend_blocks(dvp_domain *d, fr *v, uint32_t len) {
     cudaStream_t st = d->ctx->stream;
     const uint32_t h = d->n;
-    for (int k = 0; k < d->levels; k++)
+    const int K = std::max(0, d->levels - EXT_FUSE_LOG);
+    for (int k = 0; k < K; k++)
         k_extend_level<3><<<cdivp(len / 2, 256), 256, 0, st>>>(v, len, h >> (k + 1), d->dec[k].as<fr>(), 1, 0);
-    for (int k = d->levels - 1; k >= 0; k--)
+    int rc = extend_fused_launch(d, v, 1, len, 0);
+    if (rc) return rc;
+    for (int k = K - 1; k >= 0; k--)
         k_extend_level<3><<<cdivp(len / 2, 256), 256, 0, st>>>(v, len, h >> (k + 1), d->rec[k].as<fr>(), 1, 0);
     CKP(cudaGetLastError());
     return 0;
