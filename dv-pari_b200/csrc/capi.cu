@@ -285,6 +285,15 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
         ctx->msm_tables_min = (size_t)value;
         return DVP_OK;
     }
+    if (!strcmp(name, "prio_split")) {
+        ctx->msm.prio_split = value != 0;
+        return DVP_OK;
+    }
+    if (!strcmp(name, "pass_b_max")) {
+        if (value != 1 && value != 4 && value != 16 && value != 64) return DVP_ERR_BAD_ARG;
+        ctx->msm.pass_b_max = (int)value;
+        return DVP_OK;
+    }
     if (!strcmp(name, "ld_tree_max")) {
         if (value != 0 && value < 64) return DVP_ERR_BAD_ARG;
         ctx->msm.ld_tree_max = (size_t)value;

@@ -783,6 +783,9 @@ int MsmLane::init() {
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     CK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&stream_lo, cudaStreamNonBlocking, prio_lo));
+    CK(cudaEventCreateWithFlags(&ev_sw[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_sw[1], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
     for (auto &e : ev_k) CK(cudaEventCreate(&e));
     for (auto &e : ev_s) CK(cudaEventCreate(&e));
@@ -816,6 +819,9 @@ void MsmLane::destroy() {
     for (auto &e : ev_s)
         if (e) cudaEventDestroy(e), e = nullptr;
     if (done) cudaEventDestroy(done), done = nullptr;
+    for (auto &e : ev_sw)
+        if (e) cudaEventDestroy(e), e = nullptr;
+    if (stream_lo) cudaStreamDestroy(stream_lo), stream_lo = nullptr;
     if (stream) cudaStreamDestroy(stream), stream = nullptr;
 }
 
@@ -928,8 +934,19 @@ struct Tree {
         const uint32_t nblk = cdiv(cdiv(task_ub, B), 256);
         const uint32_t nthr = nblk * 256;
         const uint32_t *info = L.info.as<uint32_t>();
+        // Large pass kernels detour through the lane's low-priority stream: the short, latency-bound kernels of the
+        // OTHER lanes (inversion chain, plans, small rounds) then take the next free block slot instead of queueing
+        // behind every block of this launch.
+        const bool detour = E.prio_split && task_ub >= (1u << 17);
+        cudaStream_t sb = detour ? L.stream_lo : st;
+        auto hop = [&](cudaStream_t from, cudaStream_t to, int e) {
+            cudaEventRecord(L.ev_sw[e], from);
+            cudaStreamWaitEvent(to, L.ev_sw[e], 0);
+        };
         pb(PC_PASS1);
-        k_pass1<B><<<nblk, 256, 0, st>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_total.as<gf>());
+        if (detour) hop(st, sb, 0);
+        k_pass1<B><<<nblk, 256, 0, sb>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_total.as<gf>());
+        if (detour) hop(sb, st, 1);
         pe();
         L.launches++;
         int rc = batch_inv(L.thr_total.as<gf>(), L.thr_inv.as<gf>(), nthr, 32u * B, 1, 1, 0);
@@ -937,12 +954,14 @@ struct Tree {
         const bool mark = L.want_k;
         if (mark) cudaEventRecord(L.ev_k[0], st);
         pb(PC_PASS2);
+        if (detour) hop(st, sb, 0);
         if (E.pass2_minb == 2)
-            k_pass2<B, 2><<<nblk, 256, 0, st>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
+            k_pass2<B, 2><<<nblk, 256, 0, sb>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
         else if (E.pass2_minb == 3)
-            k_pass2<B, 3><<<nblk, 256, 0, st>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
+            k_pass2<B, 3><<<nblk, 256, 0, sb>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
         else
-            k_pass2<B, 1><<<nblk, 256, 0, st>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
+            k_pass2<B, 1><<<nblk, 256, 0, sb>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
+        if (detour) hop(sb, st, 1);
         pe();
         if (mark) {
             cudaEventRecord(L.ev_k[1], st);
@@ -1009,7 +1028,8 @@ struct Tree {
             const int o = (r + 1) & 1; // lane set written by this round's plan
             // tasks_r <= total/2^(r+1) + nseg/2
             const size_t task_ub = r == 0 ? total_ub / 2 + 1 : (total_ub >> (r + 1)) + nseg / 2 + 1;
-            const int B = task_ub >= E.b64_min ? 64 : task_ub >= (1u << 21) ? 16 : task_ub >= (1u << 17) ? 4 : 1;
+            int B = task_ub >= E.b64_min ? 64 : task_ub >= (1u << 21) ? 16 : task_ub >= (1u << 17) ? 4 : 1;
+            B = std::min(B, E.pass_b_max);
             AffPt *out = L.pp[r & 1].as<AffPt>();
             if ((rc = round(B, cur_src, task_ub, out))) return rc;
             pb(PC_MISC);
@@ -1050,7 +1070,8 @@ int MsmEngine::reserve_round(MsmLane &L, size_t task_ub) {
     RS(L.info_r0, 64);
     RS(L.prefix, task_ub * sizeof(gf));
     RS(L.desc, task_ub * sizeof(uint4));
-    const size_t thr_ub = std::max<size_t>(task_ub / 16, 1u << 19) + 1024; // B = 16 / 4 / 1 regimes
+    // pass-1 threads: rounds of >= 2^21 additions chain min(16, pass_b_max) per thread, smaller ones at least 4 or 1
+    const size_t thr_ub = std::max<size_t>(task_ub / (size_t)std::min(16, pass_b_max), 1u << 19) + 1024;
     RS(L.thr_total, thr_ub * sizeof(gf));
     RS(L.thr_inv, thr_ub * sizeof(gf));
     RS(L.lvl_pre[0], thr_ub * sizeof(gf));

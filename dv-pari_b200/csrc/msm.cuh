@@ -34,7 +34,9 @@ struct MsmStats {
 enum { PC_SORT = 0, PC_PLAN, PC_PASS1, PC_BINV_UP, PC_BINV_DIRECT, PC_BINV_DOWN, PC_PASS2, PC_MISC, PC_COUNT };
 
 struct MsmLane {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;    // high priority: the lane's timeline
+    cudaStream_t stream_lo = nullptr; // low priority: large pass kernels detour through it
+    cudaEvent_t ev_sw[2] = {nullptr, nullptr};
     cudaEvent_t done = nullptr;
     DevBuf seg_len[2], seg_start[2], c_len, c_start, blk, blk_flag, info, info_r0, pp[2], prefix, desc,
         thr_total, thr_inv, lvl_pre[2], lvl_tot[2], lvl_inv[2], buckets, rc, ents2;
@@ -81,6 +83,8 @@ struct MsmEngine {
     float prof_ms[PC_COUNT] = {0};
     unsigned prof_n[PC_COUNT] = {0};
     size_t b64_min = (size_t)1 << 23; // rounds with at least this many additions chain 64 per thread (off by default)
+    bool prio_split = true; // large pass kernels on low-priority streams
+    int pass_b_max = 64;    // cap on the additions chained per thread
     size_t ld_tree_max = 0; // 0 = automatic; a reduction level with more points starts with batched-affine rounds
     uint32_t binv_direct = 32768; // batches up to this size are inverted one element per thread
     int pass2_minb = 2; // resident blocks per SM the pass-2 kernel is compiled for (register cap)
