@@ -985,6 +985,41 @@ int dvp_r1cs_synth_solve(dvp_r1cs *r, uint64_t *assignment, unsigned nlevels) {
     return e == cudaSuccess ? DVP_OK : DVP_ERR_CUDA;
 }
 
+// Row evaluation alone, outputs left on the device: average milliseconds over `reps` runs (CUDA events), for bench.py
+int dvp_r1cs_eval_time(dvp_r1cs *r, dvp_domain *d, const uint64_t *assignment, int reps, float *ms) {
+    if (!r || !d || !assignment || !ms || reps < 1) return DVP_ERR_BAD_ARG;
+    if (d->n != r->dev.n) return DVP_ERR_LENGTH_MISMATCH;
+    CKP(cudaSetDevice(r->ctx->device));
+    cudaStream_t st = r->ctx->stream;
+    DevBuf w, o;
+    int rc;
+    const size_t n = r->dev.n;
+    if ((rc = w.reserve(r->nwires * 32)) || (rc = o.reserve(4 * n * 32))) {
+        w.release();
+        o.release();
+        return rc;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaMemcpyAsync(w.p, assignment, r->nwires * 32, cudaMemcpyHostToDevice, st);
+    fr *ov = o.as<fr>();
+    int64_t bad = -1;
+    rc = r1cs_eval_device(r, d, w.as<fr>(), ov, ov + n, ov + 2 * n, ov + 3 * n, &bad); // warm-up
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps && !rc; i++) rc = r1cs_eval_device(r, d, w.as<fr>(), ov, ov + n, ov + 2 * n, ov + 3 * n, &bad);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float t = 0;
+    cudaEventElapsedTime(&t, e0, e1);
+    *ms = t / reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    w.release();
+    o.release();
+    return rc;
+}
+
 int dvp_prover_create(dvp_ctx *ctx, dvp_domain *dom, dvp_r1cs *r1cs, int slot_gm, int slot_gq, int slot_gk,
                       dvp_prover **out) {
     if (!ctx || !dom || !r1cs || !out) return DVP_ERR_BAD_ARG;

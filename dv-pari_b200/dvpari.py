@@ -113,6 +113,7 @@ def lib():
         L.dvp_r1cs_destroy.restype = None
         L.dvp_r1cs_eval.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int64)]
         L.dvp_r1cs_synth_solve.argtypes = [vp, vp, C.c_uint]
+        L.dvp_r1cs_eval_time.argtypes = [vp, vp, vp, i32, C.POINTER(C.c_float)]
         L.dvp_setup_scalars.argtypes = [vp, vp, vp, vp, vp, vp]
         L.dvp_setup.argtypes = [vp, vp, vp, i32, i32, i32]
         L.dvp_prover_create.argtypes = [vp, vp, vp, i32, i32, i32, C.POINTER(vp)]
@@ -467,6 +468,13 @@ class R1CSInstance:
         if self._h:
             lib().dvp_r1cs_destroy(self._h)
             self._h = C.c_void_p()
+
+    def eval_time(self, dom, assignment_mont, reps=5):
+        """Milliseconds of one row evaluation with the outputs left on the device (CUDA events, average of reps)."""
+        w = np.ascontiguousarray(assignment_mont, dtype=np.uint64).reshape(-1, 4)
+        ms = C.c_float()
+        _ck(lib().dvp_r1cs_eval_time(self._h, dom._h, _ptr(w), reps, C.byref(ms)), "dvp_r1cs_eval_time")
+        return ms.value
 
     def synth_solve(self, assignment_mont, nlevels):
         """Fill the fresh wires of a synth.py circuit in place (device passes, one per level)."""

@@ -184,6 +184,8 @@ void dvp_r1cs_destroy(dvp_r1cs *r1cs);
 int dvp_r1cs_eval(dvp_r1cs *r1cs, dvp_domain *dom, const uint64_t *assignment, uint64_t *a, uint64_t *b, uint64_t *c,
                   uint64_t *i, int64_t *first_bad_row);
 
+/* Row evaluation alone with the outputs left on the device: average milliseconds over reps runs (CUDA events). */
+int dvp_r1cs_eval_time(dvp_r1cs *r1cs, dvp_domain *dom, const uint64_t *assignment, int reps, float *ms);
 /* Synthetic circuits only (benchmarks, full-size tests; dv-pari_b200/synth.py): every row's O side ends with the
  * row's own fresh wire 1 + num_public + row (coefficient one) and rows read fresh wires of lower levels
  * (level = row mod nlevels) only.  Fills those wires in place so that every row holds. */
