@@ -5,17 +5,15 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../dv-pari_b200/csrc/gf233.cuh"
-#include "gf233_v2.cuh"
 
 using namespace dvp;
 
 template <int V> __device__ __forceinline__ gf mulv(const gf &a, const gf &b) {
-    if (V == 0) return gf_mul(a, b);
-    if (V == 1) return gf_mul_v2(a, b);
-    return gf_mul(a, b);
+    if (V == 0) return gf_mul_portable(a, b); // C form: compiler-chosen order
+    return gf_mul_dev(a, b);                  // explicit mul.wide / mad.wide order (the device path of gf_mul)
 }
-__device__ __noinline__ gf mul_call0(const gf a, const gf b) { return gf_mul(a, b); }
-__device__ __noinline__ gf mul_call1(const gf a, const gf b) { return gf_mul_v2(a, b); }
+__device__ __noinline__ gf mul_call0(const gf a, const gf b) { return gf_mul_portable(a, b); }
+__device__ __noinline__ gf mul_call1(const gf a, const gf b) { return gf_mul_dev(a, b); }
 
 template <int V, int THREADS, int MINB, int CALL>
 __global__ void __launch_bounds__(THREADS, MINB) k_mul(const gf *__restrict__ in, gf *__restrict__ out, int iters) {
