@@ -202,12 +202,14 @@ def prove_section(ctx, args, rank, world, sync_all, timed):
         verified = bool(O.verify(O.trapdoor(*trapdoor), dvpari.fr_from_mont(w[1:1 + k]), proof))
         assert verified, "the oracle's verifier rejects the benchmarked proof"
     terms = int(sum(len(x) for x in circ["wire"]))
+    # the row products alone (inside a proof they share the GPU with the g_m MSM).  EVERY rank calls it: with a
+    # communicator the row ranges are exchanged by an all-gather inside the call.
+    rows_ms = inst.eval_time(dom, w, 5)
     if rank != 0:
         prover.close()
         inst.close()
         dom.close()
         return None
-    rows_ms = inst.eval_time(dom, w, 5)  # the row products alone (inside a proof they share the GPU with the g_m MSM)
     # ECFFT extend alone: 3 polynomials of n evaluations, in place on the device
     d = ctx.dev_alloc(3 * n * 32)
     ctx.dev_upload(d, dvpari.random_fr_mont(3 * n, 5))
