@@ -152,6 +152,50 @@ EXT_WIDE_PER_BUTTERFLY = 339
 IMAD_WIDE_PEAK = 9.2e12
 
 
+def cpu_prove_sample(ctx, args, lg=16):
+    """The oracle's restatement of Proof::prove (all host cores) next to dvp_prove on the same 2^16-constraint circuit,
+    SRS and witness: a bounded sample of the prove workload (the 2^22 case would take minutes on the CPU).  The two
+    proofs must be the same 118 bytes."""
+    import dvpari
+    import synth
+    from oracle import oracle as O
+
+    circ = synth.synth_r1cs(lg, seed=0xD5A10003 + lg)
+    inst = dvpari.R1CSInstance(ctx, circ["nrows"], circ["k"], circ["nwires"], circ["rowptr"], circ["wire"],
+                               circ["coeff"], circ["coeffs_mont"])
+    w = inst.synth_solve(synth.synth_assignment(circ), circ["nlevels"])
+    r1cs = O.R1CS.from_arrays(circ["coeffs_mont"], circ["rowptr"], circ["wire"], circ["coeff"], circ["nrows"],
+                              circ["k"], circ["nwires"])
+    od = O.Domain(lg + 1)
+    td = O.trapdoor(0xD5A10005, 0xD5A10006, 0xD5A10007)
+    srs = O.Srs(r1cs, od, td)
+    cores = os.cpu_count()
+    t0 = time.perf_counter()
+    want, rc, _ = O.prove(r1cs, od, srs, w, nthreads=cores)
+    cpu_ms = 1e3 * (time.perf_counter() - t0)
+    assert rc == 0
+    dom = dvpari.Domain(ctx, lg + 1)
+    for slot, pts in ((4, srs.g_m30()), (5, srs.g_q30()), (6, srs.g_k30())):
+        ctx.srs_load(slot, pts)
+    prover = dvpari.Prover(ctx, dom, inst, 4, 5, 6)
+    k = circ["k"]
+    got = prover.prove(w[1:1 + k], w[1 + k:])
+    assert got == want, "device proof differs from the oracle's on the CPU-baseline sample"
+    t0 = time.perf_counter()
+    for _ in range(3):
+        prover.prove(w[1:1 + k], w[1 + k:])
+    gpu_ms = 1e3 * (time.perf_counter() - t0) / 3
+    prover.close()
+    inst.close()
+    dom.close()
+    for sl in (4, 5, 6):
+        ctx.srs_free(sl)
+    return {"constraints": 1 << lg, "cpu_ms_per_proof": cpu_ms, "cores": cores, "kind": "port",
+            "gpu_ms_per_proof_same_input": gpu_ms, "proofs_equal": True,
+            "sample": f"2^{lg}-constraint synthetic circuit, oracle dv_prove (per-point scalar multiplications, recursive extend, "
+                      "serial row loop) on all host cores"}
+
+
 def prove_section(ctx, args, rank, world, sync_all, timed):
     """Proof::prove at 2^prove_lg constraints: ms per proof and the stage split.  With N ranks the same proof is
     made by all of them together (strong scaling): every rank holds 1/N of g_m / g_q / g_k."""
@@ -232,6 +276,7 @@ def prove_section(ctx, args, rank, world, sync_all, timed):
     exit_ms = 1e3 * (time.perf_counter() - t0)
     assert back.tobytes() == coef.tobytes(), "exit(enter(c)) != c"
     plan.close()
+    cpu_prove = cpu_prove_sample(ctx, args) if world == 1 else None
     hbm_peak, _ = peaks()
     mulmods = 3 * 4 * n * lg  # 4 n log2 n per polynomial
     ext_bytes = 3 * 2 * lg * (64 * (n // 2)) + 2 * 256 * n  # data in + out per level and polynomial, matrices once per level pair
@@ -254,6 +299,7 @@ def prove_section(ctx, args, rank, world, sync_all, timed):
                       "GBps": (terms * 72 + 4 * n * 32) / (rows_ms * 1e-3) / 1e9,
                       "hbm_frac": (terms * 72 + 4 * n * 32) / (rows_ms * 1e-3) / 1e9 / hbm_peak,
                       "note": "stand-alone (CUDA events); bytes = 72 per term + 128 per row of output"},
+        "cpu_baseline": cpu_prove,
         "srs": "generated on the device from a fixed trapdoor (dvp_setup)", "setup_s": t_setup,
         "verified_by_oracle": verified, "data": "synthetic SP1-shaped R1CS, dv-pari_b200/synth.py",
     }
