@@ -86,7 +86,7 @@ struct MsmEngine {
     bool prio_split = true; // large pass kernels on low-priority streams
     int pass_b_max = 64;    // cap on the additions chained per thread
     size_t ld_tree_max = 0; // 0 = automatic; a reduction level with more points starts with batched-affine rounds
-    uint32_t binv_direct = 32768; // batches up to this size are inverted one element per thread
+    uint32_t binv_direct = 20000; // batches up to this size are inverted one element per thread
     int pass2_minb = 2; // resident blocks per SM the pass-2 kernel is compiled for (register cap)
 
     int init(cudaStream_t s);
