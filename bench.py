@@ -389,7 +389,12 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    ncu_range = os.environ.get("DVP_NCU_RANGE") == "1"  # ncu --profile-from-start off: capture the timed steps only
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStart()
     dt, res_dev = timed(step_dev, args.steps)
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.stop() if rank == 0 else None
     launches_per_step = int(ctx.msm_stats()["launches"])  # kernels of one timed step (the instrumented run below uses one lane)
     for _ in range(2):
