@@ -1944,3 +1944,67 @@ int dvp_ecfft_exit(dvp_ecfft_plan *p, const uint64_t *evals, uint64_t *coeffs) {
 }
 
 } // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// SRS::verify (/root/reference/src/srs.rs:374-428): the designated verifier's check with the trapdoor.
+//   alpha from the transcript of (public inputs, commit_p);  i0 = sum_j x_j alpha^j;  r0 = a0 b0 - i0
+//   u0 = (a0 + delta b0 + delta^2 r0) epsilon,  v0 = (tau - alpha) epsilon
+//   accept  <=>  multi_scalar_mul([v0, u0], [kzg_k, generator]) == commit_p  and all four fields decode
+// The two-term MSM (src/srs.rs:422) runs on the device like every other multi_scalar_mul.
+// ------------------------------------------------------------------------------------------------
+extern "C" int dvp_verify(dvp_ctx *ctx, const uint64_t trapdoor_mont[12], const uint64_t *public_mont, size_t k,
+                          const uint8_t proof118[118], int *accepted) {
+    if (!ctx || !trapdoor_mont || (!public_mont && k) || !proof118 || !accepted) return DVP_ERR_BAD_ARG;
+    *accepted = 0;
+    fr td[3];
+    memcpy(td, trapdoor_mont, 96);
+    const fr &tau = td[0], &delta = td[1], &eps = td[2];
+    // a0, b0: 29-byte canonical little-endian (FrBits::to_fr: must be below p)
+    fr ab[2];
+    bool fields_ok = true;
+    for (int i = 0; i < 2; i++) {
+        uint8_t buf[32] = {0};
+        memcpy(buf, proof118 + 60 + 29 * i, 29);
+        uint32_t c[8];
+        memcpy(c, buf, 32);
+        if (fr_geq_p(c)) fields_ok = false;
+        else ab[i] = fr_from_canonical(c);
+    }
+    if (!fields_ok) return DVP_OK; // not accepted
+    std::vector<uint8_t> pub29(29 * k + 1);
+    std::vector<fr> pubv(k);
+    for (size_t j = 0; j < k; j++) {
+        memcpy(pubv[j].v, public_mont + 4 * j, 32);
+        fr_to_le29_host(&pub29[29 * j], pubv[j]);
+    }
+    uint8_t al[32];
+    if (!host::transcript_alpha(proof118, pub29.data(), k, al)) return DVP_ERR_BAD_ARG;
+    uint32_t alc[8];
+    memcpy(alc, al, 32);
+    const fr alpha = fr_from_canonical(alc);
+    fr i0 = fr_zero(), pw = fr_one();
+    for (size_t j = 0; j < k; j++) {
+        i0 = fr_add(i0, fr_mul(pubv[j], pw));
+        pw = fr_mul(pw, alpha);
+    }
+    const fr r0 = fr_sub(fr_mul(ab[0], ab[1]), i0);
+    const fr u0 = fr_mul(fr_add(fr_add(ab[0], fr_mul(delta, ab[1])), fr_mul(fr_mul(delta, delta), r0)), eps);
+    const fr v0 = fr_mul(fr_sub(tau, alpha), eps);
+    // [kzg_k, generator] x [v0, u0] on the device; an encoding that does not decode rejects the proof
+    uint8_t pts[60], gen30[30], out30[30];
+    memcpy(pts, proof118 + 30, 30);
+    host::encode30(gen30, host::k233_generator());
+    memcpy(pts + 30, gen30, 30);
+    fr sc[2] = {v0, u0};
+    // commit_p must decode as well: decode it together with kzg_k by a one-term product with scalar one
+    uint8_t cp_out[30];
+    const fr one = fr_one();
+    int rc = dvp_msm_adhoc(ctx, proof118, (const uint64_t *)one.v, 1, cp_out);
+    if (rc == DVP_ERR_INVALID_POINT) return DVP_OK;
+    if (rc) return rc;
+    rc = dvp_msm_adhoc(ctx, pts, (const uint64_t *)sc, 2, out30);
+    if (rc == DVP_ERR_INVALID_POINT) return DVP_OK;
+    if (rc) return rc;
+    *accepted = memcmp(out30, proof118, 30) == 0 && memcmp(cp_out, proof118, 30) == 0;
+    return DVP_OK;
+}

@@ -122,6 +122,7 @@ def lib():
         L.dvp_prove.argtypes = [vp, vp, sz, vp, sz, vp]
         L.dvp_prove_stages.argtypes = [vp, vp, sz, vp, sz, vp, vp]
         L.dvp_prove_last_times.argtypes = [vp, vp]
+        L.dvp_verify.argtypes = [vp, vp, vp, sz, vp, C.POINTER(i32)]
         _lib = L
     return _lib
 
@@ -495,6 +496,18 @@ class R1CSInstance:
         if rc != OK:
             raise DvpError(rc, f"constraint {bad.value}")
         return outs
+
+
+def verify(ctx, trapdoor_ints, public_mont, proof118):
+    """SRS::verify (srs.rs:374-428) with the trapdoor (tau, delta, epsilon): True iff the proof is accepted."""
+    td = fr_to_mont(list(trapdoor_ints))
+    pub = np.ascontiguousarray(public_mont, dtype=np.uint64).reshape(-1, 4)
+    pr = np.frombuffer(bytes(proof118), dtype=np.uint8).copy()
+    if pr.size != 118:
+        raise DvpError(1, "proof must be 118 bytes")
+    ok = C.c_int(0)
+    _ck(lib().dvp_verify(ctx._h, _ptr(td), _ptr(pub), pub.shape[0], _ptr(pr), C.byref(ok)), "dvp_verify")
+    return bool(ok.value)
 
 
 def setup_scalars(r1cs, dom, trapdoor_ints):

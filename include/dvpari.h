@@ -218,6 +218,13 @@ int dvp_prove(dvp_prover *p, const uint64_t *public_mont, size_t k, const uint64
  * stages = 13 n x 4 u64: a b c i a' b' c' i' q k_a k_b k_r(2n). */
 int dvp_prove_stages(dvp_prover *p, const uint64_t *public_mont, size_t k, const uint64_t *private_mont, size_t npriv,
                      uint8_t proof118[118], uint64_t *stages);
+/*
+ * SRS::verify(trapdoor, public_inputs, proof) (src/srs.rs:374-428): the designated verifier's check; the two-term
+ * multi_scalar_mul of src/srs.rs:422 runs on the device.  *accepted = 1 iff the proof verifies (a field or point of
+ * the proof that does not decode gives 0, like the reference's `all_inputs_valid`).
+ */
+int dvp_verify(dvp_ctx *ctx, const uint64_t trapdoor_mont[12], const uint64_t *public_mont, size_t k,
+               const uint8_t proof118[118], int *accepted);
 /* ms per stage of the last prove: r1cs rows, msm g_m, extend+quotient, msm g_q, challenge+K scalars, msm g_k,
  * witness upload (host -> device) */
 int dvp_prove_last_times(dvp_prover *p, float ms[7]);

@@ -39,6 +39,8 @@ extern "C" {
     pub fn dvp_prover_destroy(p: *mut dvp_prover);
     pub fn dvp_prove(p: *mut dvp_prover, public_mont: *const u64, k: usize, private_mont: *const u64, npriv: usize,
                      proof118: *mut u8) -> c_int;
+    pub fn dvp_verify(ctx: *mut dvp_ctx, trapdoor_mont: *const u64, public_mont: *const u64, k: usize,
+                      proof118: *const u8, accepted: *mut c_int) -> c_int;
     pub fn dvp_comm_unique_id(id: *mut u8) -> c_int;
     pub fn dvp_comm_init(ctx: *mut dvp_ctx, id: *const u8, rank: c_int, world: c_int) -> c_int;
     pub fn dvp_shard_range(total: usize, rank: c_int, world: c_int, lo: *mut usize, hi: *mut usize);

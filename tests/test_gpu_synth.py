@@ -74,6 +74,17 @@ def _synth_case(ctx, O, lg_n, compare_with_oracle_prover, device_setup=False):
     bad_proof[70] ^= 1
     assert not O.verify(td, pub, bytes(bad_proof))
     assert not O.verify(td, [pub[0], (pub[1] + 1) % P], proof)
+    # the device verifier (dvp_verify, srs.rs:374-428) agrees with the oracle's on the proof and on tampered copies
+    pub_m = w[1:1 + k]
+    assert dvpari.verify(ctx, tdi, pub_m, proof)
+    assert not dvpari.verify(ctx, tdi, pub_m, bytes(bad_proof))
+    assert not dvpari.verify(ctx, tdi, dvpari.fr_to_mont([pub[0], (pub[1] + 1) % P]), proof)
+    assert not dvpari.verify(ctx, [tdi[0], tdi[1], (tdi[2] + 1) % P], pub_m, proof)
+    trnd = random.Random(lg_n + 1000)
+    for _ in range(6):
+        t = bytearray(proof)
+        t[trnd.randrange(118)] ^= 1 << trnd.randrange(8)
+        assert dvpari.verify(ctx, tdi, pub_m, bytes(t)) == O.verify(td, pub, bytes(t))
     if compare_with_oracle_prover:
         if r1cs is None:
             r1cs = O.R1CS.from_arrays(circ["coeffs_mont"], circ["rowptr"], circ["wire"], circ["coeff"], circ["nrows"],
