@@ -146,3 +146,59 @@ def sp1_generate_scalar_from_raw_public_input(raw_pub_input):
     out = np.zeros(4, dtype=np.uint64)
     _ck(_bind().dvp_sp1_public_input(raw_pub_input, _ptr(out)))
     return out
+
+
+# ---------------------------------------------------------------- artifacts.rs: the cache directory
+# file names of /root/reference/src/artifacts.rs:18-83
+SRS_G_M, SRS_G_Q, SRS_G_K = "g_m", "g_q", ("g_k_0", "g_k_1", "g_k_2")
+BAR_WTS, Z_VALS2_INV = "bar_wts", "z_vals2inv"
+R1CS_CONSTRAINTS_FILE, R1CS_WITNESS_FILE = "r1cs_to_dvsnark", "witness_to_dvsnark"
+
+
+def write_cache_dir(cache_dir, circ, g_m30, g_q30, g_k30, witness_ints=None, bar_wts=None, z_vals2inv=None):
+    """Lay out a cache directory the way SRS::verifier_runs_setup / prover_prepares_precomputes leave it
+    (srs.rs:330-361, proving.rs:225-325): point-vector files, the R1CS dump, optionally the witness and precomputes."""
+    import os
+
+    os.makedirs(cache_dir, exist_ok=True)
+    n = circ["n"]
+    write_sparse_r1cs_to_file(os.path.join(cache_dir, R1CS_CONSTRAINTS_FILE), circ)
+    write_point_vec_to_file(os.path.join(cache_dir, SRS_G_M), g_m30)
+    write_point_vec_to_file(os.path.join(cache_dir, SRS_G_Q), g_q30)
+    gk = np.ascontiguousarray(g_k30, dtype=np.uint8).reshape(-1, 30)
+    for name, (lo, hi) in zip(SRS_G_K, ((0, n), (n, 2 * n), (2 * n, 4 * n))):
+        write_point_vec_to_file(os.path.join(cache_dir, name), gk[lo:hi])
+    if witness_ints is not None:
+        write_witness_to_file(os.path.join(cache_dir, R1CS_WITNESS_FILE), witness_ints)
+    if bar_wts is not None:
+        write_fr_vec_to_file(os.path.join(cache_dir, BAR_WTS), bar_wts)
+    if z_vals2inv is not None:
+        write_fr_vec_to_file(os.path.join(cache_dir, Z_VALS2_INV), z_vals2inv)
+
+
+def load_prover_from_cache_dir(ctx, cache_dir, num_public, slots=(0, 1, 2)):
+    """What Proof::prove(cache_dir, ..) reads on every call (proving.rs:426-470, 511, 666-673), read ONCE: the R1CS dump
+    and the SRS point files go to the device, the domain is rebuilt from its constants (instead of the 7-15 GB tree
+    file) and, if the cache holds bar_wts / z_vals2inv, they are compared with the device's own.
+    Returns (prover, r1cs_instance, domain); prover.prove(public, private) then needs no file."""
+    import os
+
+    circ = load_sparse_r1cs_from_file(os.path.join(cache_dir, R1CS_CONSTRAINTS_FILE), num_public)
+    inst = dvpari.R1CSInstance(ctx, circ["nrows"], circ["k"], circ["nwires"], circ["rowptr"], circ["wire"], circ["coeff"],
+                               circ["coeffs_mont"])
+    dom = dvpari.Domain(ctx, circ["n"].bit_length())
+    ctx.srs_load(slots[0], read_point_vec_from_file(os.path.join(cache_dir, SRS_G_M)))
+    ctx.srs_load(slots[1], read_point_vec_from_file(os.path.join(cache_dir, SRS_G_Q)))
+    ctx.srs_load(slots[2], read_point_vec_from_file(os.path.join(cache_dir, SRS_G_K[0])))
+    for name in SRS_G_K[1:]:
+        ctx.srs_append(slots[2], read_point_vec_from_file(os.path.join(cache_dir, name)))
+    z, wts = None, None
+    for name in (BAR_WTS, Z_VALS2_INV):
+        path = os.path.join(cache_dir, name)
+        if os.path.exists(path):
+            if z is None:
+                z, wts = dom.precomputes()
+            ours = wts if name == BAR_WTS else z
+            if read_fr_vec_from_file(path).tobytes() != ours.tobytes():
+                raise ValueError(f"{name} in the cache directory differs from the device's precompute")
+    return dvpari.Prover(ctx, dom, inst, *slots), inst, dom

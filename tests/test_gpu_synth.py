@@ -154,6 +154,16 @@ def test_prove_from_artifact_files(ctx, oracle, tmp_path):
     gk = srs.g_k30()
     for i, (lo, hi) in enumerate(((0, n), (n, 2 * n), (2 * n, 4 * n))):
         artifacts.write_point_vec_to_file(tmp_path / f"g_k_{i}", gk[lo:hi])
+    # the cache-directory helpers: reference file names, precomputes cross-checked against the device's
+    cache = tmp_path / "cache"
+    artifacts.write_cache_dir(str(cache), circ, srs.g_m30(), srs.g_q30(), gk, dvpari.fr_from_mont(w),
+                              srs.bar_wts_mont(), srs.z_vals2inv_mont())
+    prover_c, inst_c, dom_c = artifacts.load_prover_from_cache_dir(ctx, str(cache), k, slots=(7, 8, 9))
+    w_c = artifacts.load_witness_from_file(cache / artifacts.R1CS_WITNESS_FILE)
+    assert prover_c.prove(w_c[1:1 + k], w_c[1 + k:]) == want
+    prover_c.close(); inst_c.close(); dom_c.close()
+    for s_ in (7, 8, 9):
+        ctx.srs_free(s_)
     # read it back the way the reference does and prove
     c2 = artifacts.load_sparse_r1cs_from_file(tmp_path / "r1cs", k)
     inst2 = dvpari.R1CSInstance(ctx, c2["nrows"], c2["k"], c2["nwires"], c2["rowptr"], c2["wire"], c2["coeff"],
