@@ -1,8 +1,8 @@
-"""The reference's artifact files read straight into the layouts of the C ABI (SURVEY.md section 8f, N3).
+"""The reference's artifact files read straight into the layouts of the C ABI (SURVEY.md section 8f, N3 and N4).
 
-Mirrors, by name, the readers of /root/reference/src/io_utils.rs (point / Fr vector files) and
-/root/reference/src/gnark_r1cs.rs (SP1 sparse-R1CS dump, gnark witness file, SP1 public input); the writers exist so
-that tests can round-trip.  Byte-level formats: include/dvpari.h, "Artifact formats"."""
+Mirrors, by name, the readers of /root/reference/src/io_utils.rs (point / Fr vector files),
+/root/reference/src/gnark_r1cs.rs (SP1 sparse-R1CS dump, gnark witness file, SP1 public input) and
+/root/reference/src/tree_io.rs (sectioned FFTree files); the writers exist so that tests can round-trip.  Byte-level formats: include/dvpari.h, "Artifact formats"."""
 import ctypes as C
 import struct
 
@@ -21,6 +21,9 @@ def _bind():
     L.dvp_sp1_public_input.argtypes = [C.c_uint64, vp]
     L.dvp_r1cs_dump_sizes.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz * 3), C.POINTER(sz)]
     L.dvp_r1cs_dump_parse.argtypes = [vp, sz, vp, vp, vp, vp]
+    L.dvp_fftree_file_sections.argtypes = [vp, sz, sz, vp, vp]
+    L.dvp_fftree_file_leaves.argtypes = [vp, sz, sz, C.POINTER(sz), vp]
+    L.dvp_fftree_file_matrices.argtypes = [vp, sz, sz, C.c_int, C.POINTER(sz), vp]
     return L
 
 
@@ -148,10 +151,82 @@ def sp1_generate_scalar_from_raw_public_input(raw_pub_input):
     return out
 
 
+# ---------------------------------------------------------------- tree_io.rs
+FFTR_MAGIC = b"FFTR\0\0\0\0"
+# SectionId, tree_io.rs:32-48
+(SEC_F_LEAVES, SEC_RECOMBINE, SEC_DECOMPOSE, SEC_RATIONAL_MAPS, SEC_XNN_S, SEC_XNN_S_INV, SEC_Z0_S1, SEC_Z1_S0,
+ SEC_Z0_INV_S1, SEC_Z1_INV_S0, SEC_Z0Z0_REM_XNN_S, SEC_Z1Z1_REM_XNN_S, SEC_SUBTREE) = range(13)
+
+
+def fftree_sections(path, depth=0):
+    """{section id: (offset, length)} of the node `depth` subtrees below the root (header walk of tree_io.rs:243-261)."""
+    raw = np.memmap(path, dtype=np.uint8, mode="r")
+    off, ln = np.zeros(13, dtype=np.uint64), np.zeros(13, dtype=np.uint64)
+    _ck(_bind().dvp_fftree_file_sections(raw.ctypes.data, raw.size, depth, _ptr(off), _ptr(ln)), "not an FFTR file")
+    return {i: (int(off[i]), int(ln[i])) for i in range(13) if ln[i]}
+
+
+def read_minimal_fftree_from_file(path, depth=0, matrices=True):
+    """The three sections FFTree::extend needs (read_minimal_fftree_from_file, tree_io.rs:353-433):
+    dict(leaves = f.leaves() as (m, 4) Montgomery limbs, recombine / decompose = (count, 2, 2, 4) heap arrays of Mat2x2).
+    depth > 0 reads the same sections of a nested subtree (tree.subtree_with_size)."""
+    raw = np.memmap(path, dtype=np.uint8, mode="r")
+    L = _bind()
+    m = C.c_size_t()
+    _ck(L.dvp_fftree_file_leaves(raw.ctypes.data, raw.size, depth, C.byref(m), None), "not an FFTR file")
+    leaves = np.zeros((m.value, 4), dtype=np.uint64)
+    _ck(L.dvp_fftree_file_leaves(raw.ctypes.data, raw.size, depth, C.byref(m), _ptr(leaves)), "FLeaves")
+    out = dict(leaves=leaves)
+    if matrices:
+        for which, name in ((1, "recombine"), (2, "decompose")):
+            cnt = C.c_size_t()
+            _ck(L.dvp_fftree_file_matrices(raw.ctypes.data, raw.size, depth, which, C.byref(cnt), None), name)
+            mats = np.zeros((max(1, cnt.value), 2, 2, 4), dtype=np.uint64)
+            _ck(L.dvp_fftree_file_matrices(raw.ctypes.data, raw.size, depth, which, C.byref(cnt), _ptr(mats)), name)
+            out[name] = mats[:cnt.value]
+    return out
+
+
+def _ark_vec(fr_mont, per_elem=1):
+    """ark-serialize compressed Vec<T>: u64 LE count, then 29-byte Fr (per_elem of them per T)."""
+    a = np.ascontiguousarray(fr_mont, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros(29 * a.shape[0], dtype=np.uint8)
+    if a.shape[0]:
+        _ck(_bind().dvp_fr_to_le29(_ptr(a), a.shape[0], _ptr(out)))
+    return struct.pack("<Q", a.shape[0] // per_elem) + out.tobytes()
+
+
+def _fftree_node(tree):
+    blobs = [(SEC_F_LEAVES, _ark_vec(tree["f"])), (SEC_RECOMBINE, _ark_vec(tree["recombine"], 4)),
+             (SEC_DECOMPOSE, _ark_vec(tree["decompose"], 4))]
+    for sid in range(SEC_RATIONAL_MAPS, SEC_SUBTREE):
+        blobs.append((sid, tree.get("raw", {}).get(sid, struct.pack("<Q", 0))))
+    if tree.get("subtree") is not None:
+        blobs.append((SEC_SUBTREE, _fftree_node(tree["subtree"])))
+    head = struct.pack("<II", len(blobs), 0)
+    cur = 8 + 24 * len(blobs)
+    for sid, b in blobs:
+        head += struct.pack("<B7xQQ", sid, cur, len(b))
+        cur += len(b)
+    return head + b"".join(b for _, b in blobs)
+
+
+def write_fftree_to_file(path, tree):
+    """write_fftree_to_file (tree_io.rs:144-214).  tree = dict(f = (2m, 4) heap array of the layers with the m leaves in
+    the upper half, recombine / decompose = (m, 2, 2, 4) heap arrays, optional raw = {section id: blob} for sections
+    3..11 (written as empty vectors otherwise), optional subtree = a dict of the same shape)."""
+    body = _fftree_node(tree)
+    with open(path, "wb") as f:
+        f.write(FFTR_MAGIC)
+        f.write(struct.pack("<Q", len(body)))
+        f.write(body)
+
+
 # ---------------------------------------------------------------- artifacts.rs: the cache directory
 # file names of /root/reference/src/artifacts.rs:18-83
 SRS_G_M, SRS_G_Q, SRS_G_K = "g_m", "g_q", ("g_k_0", "g_k_1", "g_k_2")
 BAR_WTS, Z_VALS2_INV = "bar_wts", "z_vals2inv"
+TREE_2N, TREE_2ND, TREE_N, TREE_ND = "tree2n", "tree2nd", "treen", "treend"
 R1CS_CONSTRAINTS_FILE, R1CS_WITNESS_FILE = "r1cs_to_dvsnark", "witness_to_dvsnark"
 
 
@@ -178,15 +253,23 @@ def write_cache_dir(cache_dir, circ, g_m30, g_q30, g_k30, witness_ints=None, bar
 
 def load_prover_from_cache_dir(ctx, cache_dir, num_public, slots=(0, 1, 2)):
     """What Proof::prove(cache_dir, ..) reads on every call (proving.rs:426-470, 511, 666-673), read ONCE: the R1CS dump
-    and the SRS point files go to the device, the domain is rebuilt from its constants (instead of the 7-15 GB tree
-    file) and, if the cache holds bar_wts / z_vals2inv, they are compared with the device's own.
+    and the SRS point files go to the device, the domain is rebuilt from its constants (a tree2n file, if the cache has
+    one, is read for its leaves only and must agree) and, if the cache holds bar_wts / z_vals2inv, they are compared with the device's own.
     Returns (prover, r1cs_instance, domain); prover.prove(public, private) then needs no file."""
     import os
 
     circ = load_sparse_r1cs_from_file(os.path.join(cache_dir, R1CS_CONSTRAINTS_FILE), num_public)
     inst = dvpari.R1CSInstance(ctx, circ["nrows"], circ["k"], circ["nwires"], circ["rowptr"], circ["wire"], circ["coeff"],
                                circ["coeffs_mont"])
-    dom = dvpari.Domain(ctx, circ["n"].bit_length())
+    tree = os.path.join(cache_dir, TREE_2N)
+    if os.path.exists(tree):  # proving.rs:436: sized and checked by the file, tables rebuilt on the device
+        dom = dvpari.Domain.from_fftree_file(ctx, tree)
+        if dom.n != circ["n"]:
+            dom.close()
+            inst.close()
+            raise ValueError("tree2n does not have 2n leaves for this circuit")
+    else:
+        dom = dvpari.Domain(ctx, circ["n"].bit_length())
     ctx.srs_load(slots[0], read_point_vec_from_file(os.path.join(cache_dir, SRS_G_M)))
     ctx.srs_load(slots[1], read_point_vec_from_file(os.path.join(cache_dir, SRS_G_Q)))
     ctx.srs_load(slots[2], read_point_vec_from_file(os.path.join(cache_dir, SRS_G_K[0])))

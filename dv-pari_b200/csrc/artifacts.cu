@@ -4,6 +4,8 @@
 //                      Term = (u32 wire_id, u32 coeff_id), little-endian  /root/reference/src/gnark_r1cs.rs:1-20,121-185
 //   witness files      u32 BE count | 32-byte BE elements                 /root/reference/src/gnark_r1cs.rs:58-77,188-199
 //   SP1 public input   blake3(raw u64 LE), top 4 bytes cleared, as BE int /root/reference/src/gnark_r1cs.rs:218-236
+//   FFTree files       "FFTR\0\0\0\0" | u64 len | node = u32 sections, u32 pad | 24-byte section metas | blobs,
+//                      section 12 = the child tree as a nested node           /root/reference/src/tree_io.rs:1-15
 // Everything lands in the layouts the C ABI takes: Montgomery limbs (Vec<Fr>) and CSR per matrix.
 // (Point-vector files are u64 count | 30-byte encodings: their payload goes to dvp_srs_load unchanged.)
 #include <cstring>
@@ -153,6 +155,71 @@ int dvp_r1cs_dump_parse(const uint8_t *buf, size_t len, uint32_t *const rowptr[3
         }
     }
     return pos <= len ? DVP_OK : DVP_ERR_BAD_ARG;
+}
+
+// ---- FFTR tree files (tree_io.rs).  The blobs are ark-serialize "compressed" output: a Vec<T> / BinaryTree<T> is a
+// u64 LE count followed by the elements, an Fr is 29 bytes LE canonical, a Mat2x2<Fr> is its four entries row-major.
+// A BinaryTree is the heap array of crate ecfft: 2m entries for m leaves, entry 0 unused, the leaves in the upper half.
+int dvp_fftree_file_sections(const uint8_t *file, size_t len, size_t depth, uint64_t off[13], uint64_t slen[13]) {
+    if (!file || !off || !slen || len < 16) return DVP_ERR_BAD_ARG;
+    if (memcmp(file, "FFTR\0\0\0\0", 8) != 0) return DVP_ERR_BAD_ARG; // "not an FFTR file", tree_io.rs:225,427
+    uint64_t total;
+    memcpy(&total, file + 8, 8);
+    if (total > len - 16) return DVP_ERR_BAD_ARG;
+    size_t base = 16, size = (size_t)total; // the node occupies file[base, base + size)
+    for (size_t level = 0;; level++) {
+        if (size < 8) return DVP_ERR_BAD_ARG;
+        uint32_t count;
+        memcpy(&count, file + base, 4);
+        if (count > 13 || (size_t)8 + 24 * (size_t)count > size) return DVP_ERR_BAD_ARG;
+        for (int i = 0; i < 13; i++) off[i] = slen[i] = 0;
+        for (uint32_t s = 0; s < count; s++) {
+            const uint8_t *m = file + base + 8 + 24 * (size_t)s;
+            uint64_t o, l;
+            memcpy(&o, m + 8, 8);
+            memcpy(&l, m + 16, 8);
+            if (m[0] > 12) return DVP_ERR_BAD_ARG; // "unknown section id", tree_io.rs:69
+            if (o > size || l > size - o) return DVP_ERR_BAD_ARG;
+            off[m[0]] = base + o; // offsets in the file are relative to the node (tree_io.rs:193-203)
+            slen[m[0]] = l;
+        }
+        if (level == depth) return DVP_OK;
+        if (!slen[12]) return DVP_ERR_BAD_ARG; // no subtree that deep
+        base = (size_t)off[12];
+        size = (size_t)slen[12];
+    }
+}
+
+// FLeaves of the node `depth` subtrees below the root: *n_leaves = leaves of that tree (f.leaves().len());
+// leaves_mont (n_leaves x 4, or NULL for the count alone) = f.leaves() as Montgomery limbs.
+int dvp_fftree_file_leaves(const uint8_t *file, size_t len, size_t depth, size_t *n_leaves, uint64_t *leaves_mont) {
+    if (!n_leaves) return DVP_ERR_BAD_ARG;
+    uint64_t off[13], slen[13];
+    const int rc = dvp_fftree_file_sections(file, len, depth, off, slen);
+    if (rc) return rc;
+    if (slen[0] < 8) return DVP_ERR_BAD_ARG; // "missing section", tree_io.rs:139
+    uint64_t cnt;
+    memcpy(&cnt, file + off[0], 8);
+    if (cnt > (slen[0] - 8) / 29 || cnt * 29 + 8 != slen[0] || (cnt & (cnt - 1))) return DVP_ERR_BAD_ARG;
+    *n_leaves = (size_t)(cnt / 2);
+    if (!leaves_mont) return DVP_OK;
+    return dvp_fr_from_le29(file + off[0] + 8 + 29 * (size_t)(cnt / 2), (size_t)(cnt / 2), leaves_mont);
+}
+
+// RecombineMatrices (which = 1) / DecomposeMatrices (which = 2) of that node: *count matrices (the whole heap array,
+// entry 0 included), out (count x 16 u64, or NULL) = their entries as Montgomery limbs, row-major.
+int dvp_fftree_file_matrices(const uint8_t *file, size_t len, size_t depth, int which, size_t *count, uint64_t *out) {
+    if (!count || (which != 1 && which != 2)) return DVP_ERR_BAD_ARG;
+    uint64_t off[13], slen[13];
+    const int rc = dvp_fftree_file_sections(file, len, depth, off, slen);
+    if (rc) return rc;
+    if (slen[which] < 8) return DVP_ERR_BAD_ARG;
+    uint64_t cnt;
+    memcpy(&cnt, file + off[which], 8);
+    if (cnt > (slen[which] - 8) / 116 || cnt * 116 + 8 != slen[which]) return DVP_ERR_BAD_ARG;
+    *count = (size_t)cnt;
+    if (!out) return DVP_OK;
+    return dvp_fr_from_le29(file + off[which] + 8, 4 * (size_t)cnt, out);
 }
 
 } // extern "C"

@@ -205,6 +205,7 @@ const char *dvp_strerror(int code) {
     case DVP_ERR_INTERNAL: return "internal error";
     case DVP_ERR_NO_DEVICE: return "no CUDA device";
     case DVP_ERR_NCCL: return "NCCL error";
+    case DVP_ERR_DOMAIN_MISMATCH: return "FFTree file is not the tree of the reference's domain constants";
     }
     return "unknown error";
 }

@@ -717,6 +717,29 @@ int dvp_domain_leaves(dvp_domain *d, uint64_t *out) {
     CKP(cudaMemcpy(out, d->leaves.p, (size_t)d->n2 * 32, cudaMemcpyDeviceToHost));
     return DVP_OK;
 }
+// read_minimal_fftree_from_file (tree_io.rs:419-433) for the prover's tree2n (proving.rs:436)
+int dvp_domain_from_fftree(dvp_ctx *ctx, const uint8_t *file, size_t len, dvp_domain **out) {
+    if (!ctx || !out) return DVP_ERR_BAD_ARG;
+    *out = nullptr;
+    size_t n2 = 0;
+    int rc = dvp_fftree_file_leaves(file, len, 0, &n2, nullptr);
+    if (rc) return rc;
+    unsigned lg = 0;
+    while (((size_t)1 << lg) < n2) lg++;
+    if (((size_t)1 << lg) != n2 || lg < 2 || lg > 28) return DVP_ERR_BAD_ARG;
+    std::vector<uint64_t> want(4 * n2), got(4 * n2);
+    if ((rc = dvp_fftree_file_leaves(file, len, 0, &n2, want.data()))) return rc;
+    dvp_domain *d = nullptr;
+    if ((rc = dvp_domain_create(ctx, lg, &d))) return rc;
+    if ((rc = dvp_domain_leaves(d, got.data())) == DVP_OK && memcmp(want.data(), got.data(), 32 * n2) != 0)
+        rc = DVP_ERR_DOMAIN_MISMATCH;
+    if (rc) {
+        dvp_domain_destroy(d);
+        return rc;
+    }
+    *out = d;
+    return DVP_OK;
+}
 int dvp_domain_precomputes(dvp_domain *d, uint64_t *z_vals2inv, uint64_t *bar_wts) {
     if (!d) return DVP_ERR_BAD_ARG;
     CKP(cudaSetDevice(d->ctx->device));

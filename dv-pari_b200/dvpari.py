@@ -21,7 +21,7 @@ R_INV = pow(R, -1, P)
 OK = 0
 ERR_NAMES = {
     1: "BAD_ARG", 2: "CUDA", 3: "OOM", 4: "INVALID_POINT", 5: "LENGTH_MISMATCH", 6: "UNSATISFIED",
-    7: "ALPHA_IN_DOMAIN", 8: "INTERNAL", 9: "NO_DEVICE", 10: "NCCL",
+    7: "ALPHA_IN_DOMAIN", 8: "INTERNAL", 9: "NO_DEVICE", 10: "NCCL", 11: "DOMAIN_MISMATCH",
 }
 
 
@@ -96,6 +96,7 @@ def lib():
         L.dvp_latency_probe.argtypes = [vp, i32, i32, C.POINTER(C.c_float)]
         L.dvp_pipebench.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_double)]
         L.dvp_domain_create.argtypes = [vp, C.c_uint, C.POINTER(vp)]
+        L.dvp_domain_from_fftree.argtypes = [vp, vp, sz, C.POINTER(vp)]
         L.dvp_domain_destroy.argtypes = [vp]
         L.dvp_domain_destroy.restype = None
         L.dvp_domain_leaves.argtypes = [vp, vp]
@@ -377,6 +378,24 @@ class Domain:
         self.n = self.n2 >> 1
         self._h = C.c_void_p()
         _ck(lib().dvp_domain_create(ctx._h, log2_2n, C.byref(self._h)), "dvp_domain_create")
+
+    @classmethod
+    def from_fftree_file(cls, ctx, path):
+        """read_minimal_fftree_from_file(cache_dir/tree2n) (tree_io.rs:419-433, proving.rs:436): the size comes from the
+        file, the tables are rebuilt on the device, the leaves must equal the file's (else DvpError DOMAIN_MISMATCH)."""
+        raw = np.memmap(path, dtype=np.uint8, mode="r")
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        _ck(lib().dvp_domain_from_fftree(ctx._h, raw.ctypes.data, raw.size, C.byref(self._h)), "dvp_domain_from_fftree")
+        self.n2 = 0
+        n2 = C.c_size_t()
+        import artifacts
+
+        _ck(artifacts._bind().dvp_fftree_file_leaves(raw.ctypes.data, raw.size, 0, C.byref(n2), None))
+        self.n2 = n2.value
+        self.n = self.n2 >> 1
+        return self
 
     def close(self):
         if self._h:

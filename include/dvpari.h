@@ -32,7 +32,8 @@ enum {
     DVP_ERR_ALPHA_IN_DOMAIN = 7, /* reference: assert!(!dom.contains(alpha)), proving.rs:548-556 */
     DVP_ERR_INTERNAL = 8,
     DVP_ERR_NO_DEVICE = 9,
-    DVP_ERR_NCCL = 10
+    DVP_ERR_NCCL = 10,
+    DVP_ERR_DOMAIN_MISMATCH = 11 /* an FFTree file whose leaves are not the tree of the constants at ec_fft.rs:205-229 */
 };
 
 #define DVP_MAX_SRS_SLOTS 16
@@ -144,6 +145,11 @@ int dvp_microbench(dvp_ctx *ctx, int op, int iters, double *ops_per_sec);
  */
 typedef struct dvp_domain dvp_domain;
 int dvp_domain_create(dvp_ctx *ctx, unsigned log2_2n, dvp_domain **out);
+/* read_minimal_fftree_from_file (src/tree_io.rs:419-433, called at src/proving.rs:436) on the image of a "tree2n" file:
+ * the size comes from the file's FLeaves section, the extend tables are rebuilt on the device (upstream's matrices are
+ * an internal convention of crate ecfft; the extend result is unique given the leaves) and the device's leaves must
+ * equal the file's, else DVP_ERR_DOMAIN_MISMATCH.  A malformed file gives DVP_ERR_BAD_ARG (reference: bail!/expect). */
+int dvp_domain_from_fftree(dvp_ctx *ctx, const uint8_t *file, size_t len, dvp_domain **out);
 void dvp_domain_destroy(dvp_domain *dom);
 int dvp_domain_leaves(dvp_domain *dom, uint64_t *leaves_mont /* 2n x 4 */);
 int dvp_domain_precomputes(dvp_domain *dom, uint64_t *z_vals2inv /* n x 4 or NULL */, uint64_t *bar_wts /* n x 4 or NULL */);
@@ -235,6 +241,10 @@ int dvp_prove_last_times(dvp_prover *p, float ms[7]);
  *   SP1 / gnark dump  u32 nbCoeffs | 32-byte BE coefficients | u32 nbRows | (nL nR nO | (u32 wire, u32 coeff)...)
  *                                                                            (src/gnark_r1cs.rs:1-20,121-185)
  *   witness file      u32 BE count | 32-byte BE elements                    (src/gnark_r1cs.rs:58-77,188-199)
+ *   FFTree file       "FFTR\0\0\0\0" | u64 LE byte count | node; node = u32 section count, u32 pad | section metas
+ *                     (u8 id, 7 pad, u64 offset from the node's start, u64 length) | blobs; ids 0 f, 1 recombine_matrices,
+ *                     2 decompose_matrices, 3..11 the enter/exit tables, 12 the child FFTree as a nested node; blobs are
+ *                     ark-serialize compressed: u64 LE count | 29-byte Fr (x4 per Mat2x2)       (src/tree_io.rs:1-15,32-118)
  * A point-vector file is u64 LE count | 30-byte encodings: its payload goes to dvp_srs_load unchanged.
  */
 int dvp_fr_from_le29(const uint8_t *in, size_t n, uint64_t *out_mont);           /* Fr::deserialize_uncompressed */
@@ -246,6 +256,14 @@ int dvp_sp1_public_input(uint64_t raw, uint64_t out_mont[4]);
 int dvp_r1cs_dump_sizes(const uint8_t *buf, size_t len, size_t *ncoeffs, size_t *nrows, size_t nnz[3], size_t *max_wire);
 int dvp_r1cs_dump_parse(const uint8_t *buf, size_t len, uint32_t *const rowptr[3], uint32_t *const wire[3],
                         uint32_t *const coeff[3], uint64_t *coeffs_mont);
+/* FFTree file image: the section table of the node `depth` subtrees below the root (offsets absolute in the image,
+ * absent section = length 0) -- read_fftree_from_slice's header walk, src/tree_io.rs:243-261 */
+int dvp_fftree_file_sections(const uint8_t *file, size_t len, size_t depth, uint64_t off[13], uint64_t slen[13]);
+/* tree.f.leaves() of that node: *n_leaves, and the leaves as Montgomery limbs if leaves_mont != NULL */
+int dvp_fftree_file_leaves(const uint8_t *file, size_t len, size_t depth, size_t *n_leaves, uint64_t *leaves_mont);
+/* tree.recombine_matrices (which = 1) / decompose_matrices (which = 2): *count Mat2x2 of the heap array, entries as
+ * Montgomery limbs (count x 16 u64) if out != NULL -- the other two sections read_minimal_fftree_from_slice loads */
+int dvp_fftree_file_matrices(const uint8_t *file, size_t len, size_t depth, int which, size_t *count, uint64_t *out);
 
 /* Single-warp latency of a dependent chain, microseconds per op: mode 0 gf inversion by squarings,
  * 1 table-driven gf inversion, 2 gf multiplication. */

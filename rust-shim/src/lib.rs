@@ -26,6 +26,7 @@ extern "C" {
     pub fn dvp_msm(ctx: *mut dvp_ctx, slot: c_int, offset: usize, scalars_mont: *const u64, n: usize, out30: *mut u8) -> c_int;
     pub fn dvp_msm_adhoc(ctx: *mut dvp_ctx, pts30: *const u8, scalars_mont: *const u64, n: usize, out30: *mut u8) -> c_int;
     pub fn dvp_domain_create(ctx: *mut dvp_ctx, log2_2n: c_uint, out: *mut *mut dvp_domain) -> c_int;
+    pub fn dvp_domain_from_fftree(ctx: *mut dvp_ctx, file: *const u8, len: usize, out: *mut *mut dvp_domain) -> c_int;
     pub fn dvp_domain_destroy(dom: *mut dvp_domain);
     pub fn dvp_ecfft_extend(dom: *mut dvp_domain, input: *const u64, output: *mut u64, npoly: c_int) -> c_int;
     pub fn dvp_r1cs_load(ctx: *mut dvp_ctx, nrows: usize, num_public: usize, nwires: usize,
