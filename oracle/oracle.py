@@ -49,6 +49,8 @@ def lib():
         _lib.k233_eq.restype = C.c_int
         _lib.k233_mul_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_size_t]
         _lib.k233_msm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        # callers pass numpy addresses: without argtypes ctypes would truncate a Python int to 32 bits
+        _lib.fr_batch_inv.argtypes = [C.c_void_p, C.c_size_t]
     return _lib
 
 

@@ -2,6 +2,7 @@
 
 Mirrors the reference's tests: leaf order (ec_fft.rs:633-645), extend == interpolation (ec_fft.rs:883-907),
 and setup -> prove -> verify on the toy circuit (dvsnark_test.rs:131-180) with byte-equal proofs."""
+import ctypes as C
 import random
 
 import numpy as np
@@ -31,8 +32,8 @@ def test_domain_and_precomputes(ctx, oracle, log_n2):
     # bar_wts = 1/Z'_D(d_i), z_vals2inv = 1/Z_D(d'_i)
     want_w = od.vanish_derivative_on_roots_mont(0)
     want_z = od.vanish_on_other_mont(0)
-    O.lib().fr_batch_inv(want_w.ctypes.data, want_w.shape[0])
-    O.lib().fr_batch_inv(want_z.ctypes.data, want_z.shape[0])
+    O.lib().fr_batch_inv(want_w.ctypes.data_as(C.c_void_p), C.c_size_t(want_w.shape[0]))
+    O.lib().fr_batch_inv(want_z.ctypes.data_as(C.c_void_p), C.c_size_t(want_z.shape[0]))
     assert w.tobytes() == want_w.tobytes()
     assert z.tobytes() == want_z.tobytes()
     x = 0x1234567890ABCDEF1234567890ABCDEF
