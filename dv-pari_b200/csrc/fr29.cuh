@@ -158,6 +158,55 @@ __host__ __device__ __forceinline__ fr29 fr29_dotn(const fr29 *m, const fr29 *x)
     }
     return r;
 }
+// x0 + m x1 / 2^232 mod p, fully reduced (m pre-scaled like a matrix entry, all operands normalised and < p): the row of a
+// normalised butterfly (1, m).  The addend enters the accumulator as x0 * 2^232, i.e. on columns 8..15, so the row costs one
+// product and one reduction; the reduction's result is below p^2 / 2^232 + p + x0 < 2.5 p, hence two conditional subtractions.
+__host__ __device__ __forceinline__ fr29 fr29_muladd(const fr29 &m, const fr29 &x1, const fr29 &x0) {
+    uint64_t c[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c[i] = 0;
+        c[8 + i] = x0.l[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) c[i + j] += (uint64_t)m.l[i] * x1.l[j];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t q = ((uint32_t)c[i] * DVP_NP29) & DVP_M29;
+        c[i] += (uint64_t)q * DVP_P29_0;
+        c[i + 1] += (uint64_t)q * DVP_P29_1;
+        c[i + 2] += (uint64_t)q * DVP_P29_2;
+        c[i + 3] += (uint64_t)q * DVP_P29_3;
+        c[i + 7] += (uint64_t)q << 28;
+        c[i + 1] += c[i] >> 29;
+    }
+    fr29 r;
+    uint64_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint64_t t = c[8 + k] + carry;
+        r.l[k] = k < 7 ? (uint32_t)t & DVP_M29 : (uint32_t)t;
+        carry = t >> 29;
+    }
+    const uint32_t pl[8] = {DVP_P29_0, DVP_P29_1, DVP_P29_2, DVP_P29_3, 0u, 0u, 0u, 0x10000000u};
+#pragma unroll
+    for (int rep = 0; rep < 2; rep++) {
+        uint32_t d[8], borrow = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t t = r.l[k] - pl[k] - borrow;
+            borrow = t >> 31;
+            d[k] = k < 7 ? t & DVP_M29 : t;
+        }
+        if (!borrow) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) r.l[k] = d[k];
+        }
+    }
+    return r;
+}
 // a + b mod p on normalised limbs (both < p)
 __host__ __device__ __forceinline__ fr29 fr29_add(const fr29 &a, const fr29 &b) {
     fr29 r;

@@ -113,6 +113,15 @@ extern "C" int dvp_hostcheck_op(int op, const void *a_, const void *b_, void *ou
             memcpy(out + i * 32, o.v, 32);
             break;
         }
+        case 19: { // normalised butterfly row on 29-bit limbs: a = (m, x0), b = (unused, x1) -> x0 + m x1
+            fr m, x0, x1;
+            memcpy(m.v, a + i * 64, 32);
+            memcpy(x0.v, a + i * 64 + 32, 32);
+            memcpy(x1.v, b + i * 64 + 32, 32);
+            const fr o = fr_from_fr29(fr29_muladd(fr29_prescale(m), fr29_from_fr(x1), fr29_from_fr(x0)));
+            memcpy(out + i * 32, o.v, 32);
+            break;
+        }
         case 18: { // three-term dot product on 29-bit limbs + fr29_add: a = (m0, x0), b = (m1, x1) -> m0 x0 + m1 x1 + m0 x1, then + m1
             fr m0, x0, m1, x1;
             memcpy(m0.v, a + i * 64, 32);

@@ -117,28 +117,51 @@ __device__ inline fr pow_hm1(fr b, int e) {
     return acc;
 }
 
-// level matrices for sub-problems of size m = 2h on layer L (2m points): pair j uses the even leaves
-// (2j, 2j+m) as sources and the odd leaves (2j+1, 2j+1+m) as targets.
-//   P(s) = (P0(psi(s)) + s P1(psi(s))) v(s)^(h-1),  v(x) = x - x0
-__global__ void k_dom_matrices(const fr *__restrict__ L, uint32_t h, int e, fr x0, fr *__restrict__ dec,
-                               fr *__restrict__ rec) {
+// Level tables for sub-problems of size m = 2h on layer L (2m points): pair j uses the even leaves (2j, 2j+m) as sources
+// and the odd leaves (2j+1, 2j+1+m) as targets,  P(s) = (P0(psi(s)) + s P1(psi(s))) v(s)^(h-1),  v(x) = x - x0.
+// The plain matrices are  recombine = diag(vt0, vt1) (1 t0; 1 t1)  and  decompose = ((1 s0; 1 s1))^-1 diag(1/vs0, 1/vs1).
+// Their diagonal factors depend on the position only, never on the sub-problem, so they are carried along as a scale
+// per position instead of being multiplied in at every level: the values that flow through the levels are
+// P~ = P / sigma on the way down and P~ = P / tau on the way up,
+//   down:  sigma'(j) = -sigma(s0) / (vs0 (s1 - s0)),  beta = -sigma(s1) vs0 / (sigma(s0) vs1),
+//          P0~ = -s1 x0~ - s0 beta x1~,  P1~ = x0~ + beta x1~                      (3 products instead of 4)
+//   up:    tau(t_i) = vt_i tau'(psi(t_i)),  P~(t_i) = P0~ + t_i P1~                (2 products instead of 4)
+// and the scale that is left, tau of level 0, is folded into the last recombine level (a plain 2x2 matrix).  The
+// results are the same field elements (exact arithmetic, canonical encodings), 5 products per butterfly pair for 8.
+// Table rows keep 4 entries per butterfly: down (-s1, -s0 beta, -, beta), up (-, t0, -, t1), top (tau0, tau0 t0, tau1, tau1 t1).
+__global__ void k_dom_down(const fr *__restrict__ L, uint32_t h, int e, fr x0, const fr *__restrict__ sig,
+                           fr *__restrict__ sig_next, fr *__restrict__ dec) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= h) return;
     const uint32_t m = 2 * h;
     const fr s0 = fr_load(&L[2 * j]), s1 = fr_load(&L[2 * j + m]);
-    const fr t0 = fr_load(&L[2 * j + 1]), t1 = fr_load(&L[2 * j + 1 + m]);
     const fr vs0 = pow_hm1(fr_sub(s0, x0), e), vs1 = pow_hm1(fr_sub(s1, x0), e);
-    const fr vt0 = pow_hm1(fr_sub(t0, x0), e), vt1 = pow_hm1(fr_sub(t1, x0), e);
-    fr_store(&rec[4 * j + 0], vt0);
-    fr_store(&rec[4 * j + 1], fr_mul(t0, vt0));
-    fr_store(&rec[4 * j + 2], vt1);
-    fr_store(&rec[4 * j + 3], fr_mul(t1, vt1));
-    // inverse of [[vs0, s0 vs0], [vs1, s1 vs1]]
-    const fr dinv = fr_inv(fr_mul(fr_mul(vs0, vs1), fr_sub(s1, s0)));
-    fr_store(&dec[4 * j + 0], fr_mul(fr_mul(s1, vs1), dinv));
-    fr_store(&dec[4 * j + 1], fr_neg(fr_mul(fr_mul(s0, vs0), dinv)));
-    fr_store(&dec[4 * j + 2], fr_neg(fr_mul(vs1, dinv)));
-    fr_store(&dec[4 * j + 3], fr_mul(vs0, dinv));
+    const fr g0 = sig ? fr_load(&sig[j]) : fr_one(), g1 = sig ? fr_load(&sig[j + h]) : fr_one();
+    // one inversion for 1/(vs0 (s1 - s0)) and 1/(g0 vs1)
+    const fr A = fr_mul(vs0, fr_sub(s1, s0)), B = fr_mul(g0, vs1);
+    const fr iab = fr_inv(fr_mul(A, B));
+    const fr u0 = fr_mul(g0, fr_mul(iab, B));
+    const fr beta = fr_neg(fr_mul(fr_mul(g1, vs0), fr_mul(iab, A)));
+    fr_store(&sig_next[j], fr_neg(u0));
+    fr_store(&dec[4 * j + 0], fr_neg(s1));
+    fr_store(&dec[4 * j + 1], fr_neg(fr_mul(s0, beta)));
+    fr_store(&dec[4 * j + 2], fr_zero());
+    fr_store(&dec[4 * j + 3], beta);
+}
+__global__ void k_dom_up(const fr *__restrict__ L, uint32_t h, int e, fr x0, const fr *__restrict__ tau_next,
+                         fr *__restrict__ tau, int top, fr *__restrict__ rec) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= h) return;
+    const uint32_t m = 2 * h;
+    const fr t0 = fr_load(&L[2 * j + 1]), t1 = fr_load(&L[2 * j + 1 + m]);
+    const fr tn = fr_load(&tau_next[j]);
+    const fr a0 = fr_mul(pow_hm1(fr_sub(t0, x0), e), tn), a1 = fr_mul(pow_hm1(fr_sub(t1, x0), e), tn);
+    fr_store(&tau[j], a0);
+    fr_store(&tau[j + h], a1);
+    fr_store(&rec[4 * j + 0], top ? a0 : fr_zero());
+    fr_store(&rec[4 * j + 1], top ? fr_mul(a0, t0) : t0);
+    fr_store(&rec[4 * j + 2], top ? a1 : fr_zero());
+    fr_store(&rec[4 * j + 3], top ? fr_mul(a1, t1) : t1);
 }
 
 // chain rule, one level: for the m points s_j = L[2j + shift] of S^k
@@ -178,7 +201,24 @@ __global__ void k_mats_to29(fr *__restrict__ mats, uint32_t count) {
     for (int k = 0; k < 8; k++) o.v[k] = r.l[k];
     fr_store(&mats[i], o);
 }
-template <int NP>
+// butterfly forms (k_dom_down / k_dom_up): plain 2x2 (the top recombine level), decompose (one dot product and one
+// multiply-add), recombine (two multiply-adds)
+enum { BF_GEN = 0, BF_DOWN = 1, BF_UP = 2 };
+template <int MODE>
+__device__ __forceinline__ void butterfly29(const fr29 &m0, const fr29 &m1, const fr29 &m2, const fr29 &m3, const fr29 &a0,
+                                            const fr29 &a1, fr29 &y0, fr29 &y1) {
+    if (MODE == BF_GEN) {
+        y0 = fr29_dot2(m0, a0, m1, a1);
+        y1 = fr29_dot2(m2, a0, m3, a1);
+    } else if (MODE == BF_DOWN) {
+        y0 = fr29_dot2(m0, a0, m1, a1);
+        y1 = fr29_muladd(m3, a1, a0);
+    } else {
+        y0 = fr29_muladd(m1, a1, a0);
+        y1 = fr29_muladd(m3, a1, a0);
+    }
+}
+template <int NP, int MODE>
 __global__ void __launch_bounds__(256)
     k_extend_level(fr *__restrict__ data, uint32_t n, uint32_t h, const fr *__restrict__ mats, int npoly,
                    size_t stride) {
@@ -195,16 +235,29 @@ __global__ void __launch_bounds__(256)
             x1[p] = fr_load(&data[(size_t)p * stride + i1]);
         }
     }
-    const fr29 m0 = fr29_load(&mats[4 * j]), m1 = fr29_load(&mats[4 * j + 1]);
-    const fr29 m2 = fr29_load(&mats[4 * j + 2]), m3 = fr29_load(&mats[4 * j + 3]);
+    fr29 m0, m1, m2, m3;
+    if (MODE != BF_UP) m0 = fr29_load(&mats[4 * j]);
+    m1 = fr29_load(&mats[4 * j + 1]);
+    if (MODE == BF_GEN) m2 = fr29_load(&mats[4 * j + 2]);
+    m3 = fr29_load(&mats[4 * j + 3]);
 #pragma unroll
     for (int p = 0; p < NP; p++) {
         if (p < npoly) {
             const fr29 a0 = fr29_from_fr(x0[p]), a1 = fr29_from_fr(x1[p]);
-            fr_store(&data[(size_t)p * stride + i0], fr_from_fr29(fr29_dot2(m0, a0, m1, a1)));
-            fr_store(&data[(size_t)p * stride + i1], fr_from_fr29(fr29_dot2(m2, a0, m3, a1)));
+            fr29 y0, y1;
+            butterfly29<MODE>(m0, m1, m2, m3, a0, a1, y0, y1);
+            fr_store(&data[(size_t)p * stride + i0], fr_from_fr29(y0));
+            fr_store(&data[(size_t)p * stride + i1], fr_from_fr29(y1));
         }
     }
+}
+// one level of the extend of tree d over `len` points: decompose (down) or recombine level k
+static void extend_level_launch(fr *data, uint32_t len, uint32_t h, const fr *mats, int np, size_t stride, bool down, int k,
+                                cudaStream_t st) {
+    const dim3 grid(cdivp(len / 2, 256));
+    if (down) k_extend_level<3, BF_DOWN><<<grid, 256, 0, st>>>(data, len, h, mats, np, stride);
+    else if (k == 0) k_extend_level<3, BF_GEN><<<grid, 256, 0, st>>>(data, len, h, mats, np, stride);
+    else k_extend_level<3, BF_UP><<<grid, 256, 0, st>>>(data, len, h, mats, np, stride);
 }
 
 // The deepest levels of an extend work on sub-problems of at most EXT_FUSE_M points: one block stages a whole
@@ -217,7 +270,8 @@ struct FusedMats {
     const fr *dec[EXT_FUSE_LOG], *rec[EXT_FUSE_LOG];
 };
 __global__ void __launch_bounds__(256)
-    k_extend_fused(fr *__restrict__ data, int logm, int logc, FusedMats fm, uint32_t blocks_per_poly, size_t poly_stride) {
+    k_extend_fused(fr *__restrict__ data, int logm, int logc, FusedMats fm, uint32_t blocks_per_poly, size_t poly_stride,
+                   int top) { // top: the first fused level is level 0 of the tree (its recombine matrices are plain)
     extern __shared__ __align__(16) unsigned char ext_sm_raw[];
     fr *sm = reinterpret_cast<fr *>(ext_sm_raw); // fr29 limbs stored in fr-sized slots
     // a block stages C = 2^logc points = C / 2^logm whole sub-problems of size 2^logm (they tile the chunk)
@@ -235,12 +289,21 @@ __global__ void __launch_bounds__(256)
         const int k = pass < logm ? pass : 2 * logm - 1 - pass; // levels 0 .. logm-1 down, then back up
         const fr *mats = pass < logm ? fm.dec[k] : fm.rec[k];
         const uint32_t h = (1u << logm) >> (k + 1);
+        const int mode = pass < logm ? BF_DOWN : (k == 0 && top) ? BF_GEN : BF_UP; // uniform over the block
         for (uint32_t g = threadIdx.x; g < (M >> 1); g += blockDim.x) {
             const uint32_t j = g % h, i0 = (g / h) * 2 * h + j, i1 = i0 + h;
-            const fr29 m0 = fr29_load(&mats[4 * j]), m1 = fr29_load(&mats[4 * j + 1]);
-            const fr29 m2 = fr29_load(&mats[4 * j + 2]), m3 = fr29_load(&mats[4 * j + 3]);
+            const fr29 m1 = fr29_load(&mats[4 * j + 1]), m3 = fr29_load(&mats[4 * j + 3]);
             const fr29 x0 = fr29_load(&sm[i0]), x1 = fr29_load(&sm[i1]);
-            const fr29 y0 = fr29_dot2(m0, x0, m1, x1), y1 = fr29_dot2(m2, x0, m3, x1);
+            fr29 y0, y1;
+            if (mode == BF_UP) {
+                butterfly29<BF_UP>(m1, m1, m3, m3, x0, x1, y0, y1);
+            } else if (mode == BF_DOWN) {
+                const fr29 m0 = fr29_load(&mats[4 * j]);
+                butterfly29<BF_DOWN>(m0, m1, m3, m3, x0, x1, y0, y1);
+            } else {
+                const fr29 m0 = fr29_load(&mats[4 * j]), m2 = fr29_load(&mats[4 * j + 2]);
+                butterfly29<BF_GEN>(m0, m1, m2, m3, x0, x1, y0, y1);
+            }
             fr o0, o1;
 #pragma unroll
             for (int q = 0; q < 8; q++) {
@@ -669,21 +732,44 @@ static int domain_create_impl(dvp_ctx *ctx, unsigned log2_2n, bool shifted, dvp_
     // the D / D' chains end on the two leaves of layer `levels`
     if (cudaMemcpyAsync(d->last, layers[d->levels]->p, 2 * sizeof(fr), cudaMemcpyDeviceToHost, st) != cudaSuccess)
         return fail(DVP_ERR_CUDA);
-    // extend matrices
+    // extend tables (k_dom_down / k_dom_up): the position scales sigma go down the levels, tau comes back up
     d->dec.resize(d->levels);
     d->rec.resize(d->levels);
+    DevBuf scale[2];
+    auto fail2 = [&](int code) {
+        scale[0].release();
+        scale[1].release();
+        return fail(code);
+    };
+    if ((rc = scale[0].reserve((size_t)d->n * sizeof(fr))) || (rc = scale[1].reserve((size_t)d->n * sizeof(fr)))) return fail2(rc);
+    const fr *sc_cur = nullptr; // sigma of level 0 is 1
+    int flip = 0;
     for (int k = 0; k < d->levels; k++) {
         const uint32_t h = d->n >> (k + 1);
         if ((rc = d->dec[k].reserve((size_t)h * 4 * sizeof(fr))) || (rc = d->rec[k].reserve((size_t)h * 4 * sizeof(fr))))
-            return fail(rc);
+            return fail2(rc);
         int e = 0;
         while ((1u << e) < h) e++;
-        k_dom_matrices<<<cdivp(h, 64), 64, 0, st>>>(layers[k]->as<fr>(), h, e, d->x0[k], d->dec[k].as<fr>(),
-                                                   d->rec[k].as<fr>());
+        fr *nxt = scale[flip].as<fr>();
+        k_dom_down<<<cdivp(h, 64), 64, 0, st>>>(layers[k]->as<fr>(), h, e, d->x0[k], sc_cur, nxt, d->dec[k].as<fr>());
         k_mats_to29<<<cdivp(4 * h, 128), 128, 0, st>>>(d->dec[k].as<fr>(), 4 * h);
-        k_mats_to29<<<cdivp(4 * h, 128), 128, 0, st>>>(d->rec[k].as<fr>(), 4 * h);
+        sc_cur = nxt;
+        flip ^= 1;
     }
-    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return fail(DVP_ERR_CUDA);
+    for (int k = d->levels - 1; k >= 0; k--) { // sc_cur: tau of level k + 1 (the single sigma of the last level at first)
+        const uint32_t h = d->n >> (k + 1);
+        int e = 0;
+        while ((1u << e) < h) e++;
+        fr *nxt = scale[flip].as<fr>();
+        k_dom_up<<<cdivp(h, 64), 64, 0, st>>>(layers[k]->as<fr>(), h, e, d->x0[k], sc_cur, nxt, k == 0 ? 1 : 0,
+                                             d->rec[k].as<fr>());
+        k_mats_to29<<<cdivp(4 * h, 128), 128, 0, st>>>(d->rec[k].as<fr>(), 4 * h);
+        sc_cur = nxt;
+        flip ^= 1;
+    }
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return fail2(DVP_ERR_CUDA);
+    scale[0].release();
+    scale[1].release();
     // prover precomputes: bar_wts = 1/Z'_D(d_i), z_vals2inv = 1/Z_D(d'_i)  (proving.rs:225-325)
     if ((rc = d->bar_wts.reserve((size_t)d->n * sizeof(fr))) || (rc = d->z_vals2inv.reserve((size_t)d->n * sizeof(fr))) ||
         (rc = d->work.reserve((size_t)d->n * sizeof(fr))))
@@ -777,7 +863,7 @@ static int extend_fused_launch(dvp_domain *d, fr *data, uint32_t count, uint32_t
     while (logc < EXT_FUSE_LOG && (2u << logc) <= per_poly && ((size_t)count * per_poly >> (logc + 1)) >= 296) logc++;
     const uint32_t blocks_per_poly = per_poly >> logc;
     k_extend_fused<<<count * blocks_per_poly, 256, ((size_t)1 << logc) * sizeof(fr), d->ctx->stream>>>(
-        data, logm, logc, fm, blocks_per_poly, poly_stride);
+        data, logm, logc, fm, blocks_per_poly, poly_stride, K == 0 ? 1 : 0);
     CKP(cudaGetLastError());
     return 0;
 }
@@ -792,11 +878,9 @@ static int extend_device(dvp_domain *d, fr *data, int npoly, size_t stride) {
     for (int p0 = 0; p0 < npoly; p0 += 3) {
         const int np = std::min(3, npoly - p0);
         fr *base = data + (size_t)p0 * stride;
-        for (int k = 0; k < K; k++)
-            k_extend_level<3><<<cdivp(n / 2, 256), 256, 0, st>>>(base, n, n >> (k + 1), d->dec[k].as<fr>(), np, stride);
+        for (int k = 0; k < K; k++) extend_level_launch(base, n, n >> (k + 1), d->dec[k].as<fr>(), np, stride, true, k, st);
         if ((rc = extend_fused_launch(d, base, (uint32_t)np, n, stride))) return rc;
-        for (int k = K - 1; k >= 0; k--)
-            k_extend_level<3><<<cdivp(n / 2, 256), 256, 0, st>>>(base, n, n >> (k + 1), d->rec[k].as<fr>(), np, stride);
+        for (int k = K - 1; k >= 0; k--) extend_level_launch(base, n, n >> (k + 1), d->rec[k].as<fr>(), np, stride, false, k, st);
     }
     CKP(cudaGetLastError());
     return 0;
@@ -1670,12 +1754,10 @@ static int extend_blocks(dvp_domain *d, fr *v, uint32_t len) {
     cudaStream_t st = d->ctx->stream;
     const uint32_t h = d->n;
     const int K = std::max(0, d->levels - EXT_FUSE_LOG);
-    for (int k = 0; k < K; k++)
-        k_extend_level<3><<<cdivp(len / 2, 256), 256, 0, st>>>(v, len, h >> (k + 1), d->dec[k].as<fr>(), 1, 0);
+    for (int k = 0; k < K; k++) extend_level_launch(v, len, h >> (k + 1), d->dec[k].as<fr>(), 1, 0, true, k, st);
     int rc = extend_fused_launch(d, v, 1, len, 0);
     if (rc) return rc;
-    for (int k = K - 1; k >= 0; k--)
-        k_extend_level<3><<<cdivp(len / 2, 256), 256, 0, st>>>(v, len, h >> (k + 1), d->rec[k].as<fr>(), 1, 0);
+    for (int k = K - 1; k >= 0; k--) extend_level_launch(v, len, h >> (k + 1), d->rec[k].as<fr>(), 1, 0, false, k, st);
     CKP(cudaGetLastError());
     return 0;
 }

@@ -137,6 +137,27 @@ def test_fr29_butterfly_row():
     assert out.view(np.uint64).reshape(-1, 4).tobytes() == want.tobytes()
 
 
+def test_fr29_normalised_butterfly_row():
+    """fr29_muladd: x0 + m x1 with the addend injected into the accumulator above the reduction (one product, one
+    reduction, result < 2.5 p before the conditional subtractions) -- the row (1, m) of the normalised ECFFT butterflies."""
+    rnd = random.Random(30)
+    edge = [0, 1, P - 1, P - 2, 1 << 231, (1 << 231) - 1, (1 << 203) - 1, (1 << 29) - 1, 1 << 29]
+    vals = edge + [rnd.randrange(P) for _ in range(400)]
+    m, x0, x1 = [P - 1] + vals, [P - 1] + vals[5:] + vals[:5], [P - 1] + vals[2:] + vals[:2]
+    # every combination of the edge values as well
+    for a in edge:
+        for b in edge:
+            for c in (0, 1, P - 1):
+                m.append(a), x1.append(b), x0.append(c)
+    n = len(m)
+    A = np.concatenate([dvpari.fr_to_mont(m), dvpari.fr_to_mont(x0)], axis=1).view(np.uint32).reshape(-1, 16)
+    B = np.concatenate([dvpari.fr_to_mont(m), dvpari.fr_to_mont(x1)], axis=1).view(np.uint32).reshape(-1, 16)
+    out = np.zeros((n, 8), dtype=np.uint32)
+    dvpari._ck(dvpari.lib().dvp_hostcheck_op(19, dvpari._ptr(A), dvpari._ptr(B), dvpari._ptr(out), n))
+    want = dvpari.fr_to_mont([(c + a * b) % P for a, b, c in zip(m, x1, x0)])
+    assert out.view(np.uint64).reshape(-1, 4).tobytes() == want.tobytes()
+
+
 def test_ld_projective_addition_is_complete(oracle):
     """k233_ld.cuh: the inversion-free addition used by the MSM's reduction trees, on projective operands with
     Z != 1, including equal operands in different representations (doubling branch), opposite operands and infinity."""
