@@ -146,10 +146,17 @@ def run_reference(args):
     return 0
 
 
-# ECFFT butterfly = 339 IMAD.WIDE (cuobjdump of k_extend_level: two 29-bit-limb dot products, fr29.cuh); IMAD.WIDE
-# issues once per 4 cycles per SMSP: 9.2e12 thread-instr/s measured (scripts/pipebench2.cu, profiles/README.md)
-EXT_WIDE_PER_BUTTERFLY = 339
+# ECFFT butterflies on 29-bit limbs (fr29.cuh), IMAD.WIDE per butterfly from cuobjdump of k_extend_level: decompose
+# (one dot product + one multiply-add) 273, recombine (two multiply-adds) 209, the top recombine level (plain 2x2) 337.
+# IMAD.WIDE issues once per 4 cycles per SMSP: 9.2e12 thread-instr/s measured (scripts/pipebench2.cu, profiles/README.md)
+EXT_WIDE_DOWN, EXT_WIDE_UP, EXT_WIDE_TOP = 273, 209, 337
 IMAD_WIDE_PEAK = 9.2e12
+
+
+def extend_work(n, lg, polys=3):
+    """(IMAD.WIDE thread-instructions, field products) of `polys` extends of n = 2^lg points."""
+    half = polys * (n // 2)
+    return (half * (lg * EXT_WIDE_DOWN + (lg - 1) * EXT_WIDE_UP + EXT_WIDE_TOP), half * (3 * lg + 2 * (lg - 1) + 4))
 
 
 def cpu_prove_sample(ctx, args, lg=16):
@@ -289,8 +296,11 @@ def prove_section(ctx, args, rank, world, sync_all, timed):
         # g_q + g_k only: the g_m MSM overlaps the Fr-side stages (its stage entry is the part that was not hidden)
         "msm_gq_gk_points_per_s": 5 * n / world / (1e-3 * (stages["msm_gq"] + stages["msm_gk"])),
         "ecfft_extend": {"polys": 3, "n": n, "ms": ext_ms, "mulmods_per_s": mulmods / (ext_ms * 1e-3),
-                         "imad_wide_per_s": (mulmods / 4) * EXT_WIDE_PER_BUTTERFLY / (ext_ms * 1e-3),
-                         "int_frac": (mulmods / 4) * EXT_WIDE_PER_BUTTERFLY / (ext_ms * 1e-3) / IMAD_WIDE_PEAK,
+                         "mulmods_note": "4 n log2 n per polynomial, the reference algorithm's count (SURVEY 8d); the "
+                                         "kernels execute products_per_s (position scales carried through the tree)",
+                         "products_per_s": extend_work(n, lg)[1] / (ext_ms * 1e-3),
+                         "imad_wide_per_s": extend_work(n, lg)[0] / (ext_ms * 1e-3),
+                         "int_frac": extend_work(n, lg)[0] / (ext_ms * 1e-3) / IMAD_WIDE_PEAK,
                          "GBps": ext_bytes / (ext_ms * 1e-3) / 1e9, "hbm_frac": ext_bytes / (ext_ms * 1e-3) / 1e9 / hbm_peak,
                          "bound": "integer (IMAD.WIDE issue), see DESIGN.md 4.3"},
         "ecfft_enter_exit": {"n": 1 << elg, "enter_ms": enter_ms, "exit_ms": exit_ms, "round_trip_exact": True,

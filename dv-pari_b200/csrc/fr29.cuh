@@ -207,6 +207,70 @@ __host__ __device__ __forceinline__ fr29 fr29_muladd(const fr29 &m, const fr29 &
     }
     return r;
 }
+// ---- semi-reduced rows --------------------------------------------------------------------------------------------
+// Between the levels of an extend the values only need to stay below 2^232 (< 2p, limbs normalised): the columns of the
+// next product still cannot overflow, and a full reduction is done once, by the last level.  After the Montgomery
+// reduction a row is below 2^233 + 2^232 (muladd: p + 2^232 + p; dot2: 3p), so with k = floor(y / 2^231) read off the
+// top limb, y - max(k - 1, 0) p lies in (0, 2^232): one branch-free pass instead of two conditional subtractions.
+__host__ __device__ __forceinline__ fr29 fr29_finish_semi(uint64_t (&c)[16]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t q = ((uint32_t)c[i] * DVP_NP29) & DVP_M29;
+        c[i] += (uint64_t)q * DVP_P29_0;
+        c[i + 1] += (uint64_t)q * DVP_P29_1;
+        c[i + 2] += (uint64_t)q * DVP_P29_2;
+        c[i + 3] += (uint64_t)q * DVP_P29_3;
+        c[i + 7] += (uint64_t)q << 28;
+        c[i + 1] += c[i] >> 29;
+    }
+    fr29 r;
+    uint64_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint64_t t = c[8 + k] + carry;
+        r.l[k] = k < 7 ? (uint32_t)t & DVP_M29 : (uint32_t)t;
+        carry = t >> 29;
+    }
+    const uint32_t k = r.l[7] >> 28, kk = k ? k - 1 : 0; // k <= 4, so kk p[j] < 3 * 2^29 and every t below is > -2^31
+    const uint32_t pl[4] = {DVP_P29_0, DVP_P29_1, DVP_P29_2, DVP_P29_3};
+    int32_t borrow = 0; // 0 or negative
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        const int32_t t = (int32_t)r.l[j] - (j < 4 ? (int32_t)(kk * pl[j]) : 0) + borrow;
+        r.l[j] = (uint32_t)t & DVP_M29;
+        borrow = t >> 29; // arithmetic shift: floor(t / 2^29)
+    }
+    r.l[7] = (uint32_t)((int32_t)r.l[7] - (int32_t)(kk << 28) + borrow);
+    return r;
+}
+// x0 + m x1 / 2^232, semi-reduced; m pre-scaled and < p, x0 and x1 semi-reduced
+__host__ __device__ __forceinline__ fr29 fr29_muladd_semi(const fr29 &m, const fr29 &x1, const fr29 &x0) {
+    uint64_t c[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c[i] = 0;
+        c[8 + i] = x0.l[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) c[i + j] += (uint64_t)m.l[i] * x1.l[j];
+    return fr29_finish_semi(c);
+}
+// (m0 x0 + m1 x1) / 2^232, semi-reduced; m0, m1 pre-scaled and < p, x0 and x1 semi-reduced
+__host__ __device__ __forceinline__ fr29 fr29_dot2_semi(const fr29 &m0, const fr29 &x0, const fr29 &m1, const fr29 &x1) {
+    uint64_t c[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            c[i + j] += (uint64_t)m0.l[i] * x0.l[j];
+            c[i + j] += (uint64_t)m1.l[i] * x1.l[j];
+        }
+    return fr29_finish_semi(c);
+}
 // a + b mod p on normalised limbs (both < p)
 __host__ __device__ __forceinline__ fr29 fr29_add(const fr29 &a, const fr29 &b) {
     fr29 r;

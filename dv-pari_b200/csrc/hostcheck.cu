@@ -122,6 +122,22 @@ extern "C" int dvp_hostcheck_op(int op, const void *a_, const void *b_, void *ou
             memcpy(out + i * 32, o.v, 32);
             break;
         }
+        case 20: case 21: { // semi-reduced rows on raw 232-bit operands: a = (m, x0), b = (m1, x1), m and m1 Montgomery < p;
+            // 20: x0 + m x1, 21: m x0 + m1 x1 -> 8 x 32-bit words of the semi-reduced result
+            fr m, x0, m1, x1;
+            memcpy(m.v, a + i * 64, 32);
+            memcpy(x0.v, a + i * 64 + 32, 32);
+            memcpy(m1.v, b + i * 64, 32);
+            memcpy(x1.v, b + i * 64 + 32, 32);
+            const fr29 r = op == 20 ? fr29_muladd_semi(fr29_prescale(m), fr29_from_fr(x1), fr29_from_fr(x0))
+                                    : fr29_dot2_semi(fr29_prescale(m), fr29_from_fr(x0), fr29_prescale(m1), fr29_from_fr(x1));
+            uint32_t ok = 1;
+            for (int q = 0; q < 8; q++) ok &= r.l[q] <= DVP_M29;
+            fr o = fr_from_fr29(r);
+            if (!ok) memset(o.v, 0xff, 32); // limbs not normalised
+            memcpy(out + i * 32, o.v, 32);
+            break;
+        }
         case 18: { // three-term dot product on 29-bit limbs + fr29_add: a = (m0, x0), b = (m1, x1) -> m0 x0 + m1 x1 + m0 x1, then + m1
             fr m0, x0, m1, x1;
             memcpy(m0.v, a + i * 64, 32);

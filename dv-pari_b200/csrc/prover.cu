@@ -57,6 +57,11 @@ __device__ __forceinline__ fr29 fr29_load(const fr *p) {
     for (int k = 0; k < 8; k++) r.l[k] = t.v[k];
     return r;
 }
+__device__ __forceinline__ void fr29_store(fr *p, const fr29 &v) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
 // v^(2^e)
 __host__ __device__ inline fr fr_pow2k(fr v, int e) {
     for (int i = 0; i < e; i++) v = fr_sqr(v);
@@ -207,18 +212,22 @@ enum { BF_GEN = 0, BF_DOWN = 1, BF_UP = 2 };
 template <int MODE>
 __device__ __forceinline__ void butterfly29(const fr29 &m0, const fr29 &m1, const fr29 &m2, const fr29 &m3, const fr29 &a0,
                                             const fr29 &a1, fr29 &y0, fr29 &y1) {
+    // the values between the levels are semi-reduced (< 2^232, fr29.cuh); the plain top level reduces fully
     if (MODE == BF_GEN) {
-        y0 = fr29_dot2(m0, a0, m1, a1);
-        y1 = fr29_dot2(m2, a0, m3, a1);
+        const fr29 x[2] = {a0, a1}, r0[2] = {m0, m1}, r1[2] = {m2, m3};
+        y0 = fr29_dotn<2>(r0, x);
+        y1 = fr29_dotn<2>(r1, x);
     } else if (MODE == BF_DOWN) {
-        y0 = fr29_dot2(m0, a0, m1, a1);
-        y1 = fr29_muladd(m3, a1, a0);
+        y0 = fr29_dot2_semi(m0, a0, m1, a1);
+        y1 = fr29_muladd_semi(m3, a1, a0);
     } else {
-        y0 = fr29_muladd(m1, a1, a0);
-        y1 = fr29_muladd(m3, a1, a0);
+        y0 = fr29_muladd_semi(m1, a1, a0);
+        y1 = fr29_muladd_semi(m3, a1, a0);
     }
 }
-template <int NP, int MODE>
+// Between the first decompose level and the last recombine level the vectors stay on 29-bit limbs in global memory too
+// (IN29 / OUT29): only the two ends of an extend convert from / to the 32-bit words of the ABI.
+template <int NP, int MODE, bool IN29, bool OUT29>
 __global__ void __launch_bounds__(256)
     k_extend_level(fr *__restrict__ data, uint32_t n, uint32_t h, const fr *__restrict__ mats, int npoly,
                    size_t stride) {
@@ -243,21 +252,41 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int p = 0; p < NP; p++) {
         if (p < npoly) {
-            const fr29 a0 = fr29_from_fr(x0[p]), a1 = fr29_from_fr(x1[p]);
+            fr29 a0, a1;
+            if (IN29) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    a0.l[q] = x0[p].v[q];
+                    a1.l[q] = x1[p].v[q];
+                    // fully reduced limbs; without the range the compiler widens the products (IMAD + IADD3 per term)
+                    __builtin_assume(a0.l[q] <= DVP_M29);
+                    __builtin_assume(a1.l[q] <= DVP_M29);
+                }
+            } else {
+                a0 = fr29_from_fr(x0[p]);
+                a1 = fr29_from_fr(x1[p]);
+            }
             fr29 y0, y1;
             butterfly29<MODE>(m0, m1, m2, m3, a0, a1, y0, y1);
-            fr_store(&data[(size_t)p * stride + i0], fr_from_fr29(y0));
-            fr_store(&data[(size_t)p * stride + i1], fr_from_fr29(y1));
+            if (OUT29) {
+                fr29_store(&data[(size_t)p * stride + i0], y0);
+                fr29_store(&data[(size_t)p * stride + i1], y1);
+            } else {
+                fr_store(&data[(size_t)p * stride + i0], fr_from_fr29(y0));
+                fr_store(&data[(size_t)p * stride + i1], fr_from_fr29(y1));
+            }
         }
     }
 }
-// one level of the extend of tree d over `len` points: decompose (down) or recombine level k
+// one level of the extend of tree d over `len` points: decompose (down) or recombine level k; these are the levels above
+// the fused ones, so level 0 going down reads 32-bit words and level 0 coming up (the plain matrices) writes them
 static void extend_level_launch(fr *data, uint32_t len, uint32_t h, const fr *mats, int np, size_t stride, bool down, int k,
                                 cudaStream_t st) {
     const dim3 grid(cdivp(len / 2, 256));
-    if (down) k_extend_level<3, BF_DOWN><<<grid, 256, 0, st>>>(data, len, h, mats, np, stride);
-    else if (k == 0) k_extend_level<3, BF_GEN><<<grid, 256, 0, st>>>(data, len, h, mats, np, stride);
-    else k_extend_level<3, BF_UP><<<grid, 256, 0, st>>>(data, len, h, mats, np, stride);
+    if (down && k == 0) k_extend_level<3, BF_DOWN, false, true><<<grid, 256, 0, st>>>(data, len, h, mats, np, stride);
+    else if (down) k_extend_level<3, BF_DOWN, true, true><<<grid, 256, 0, st>>>(data, len, h, mats, np, stride);
+    else if (k == 0) k_extend_level<3, BF_GEN, true, false><<<grid, 256, 0, st>>>(data, len, h, mats, np, stride);
+    else k_extend_level<3, BF_UP, true, true><<<grid, 256, 0, st>>>(data, len, h, mats, np, stride);
 }
 
 // The deepest levels of an extend work on sub-problems of at most EXT_FUSE_M points: one block stages a whole
@@ -278,7 +307,8 @@ __global__ void __launch_bounds__(256)
     const uint32_t M = 1u << logc;
     fr *base = data + (size_t)(blockIdx.x / blocks_per_poly) * poly_stride + (size_t)(blockIdx.x % blocks_per_poly) * M;
     for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
-        const fr29 v = fr29_from_fr(fr_load(&base[i]));
+        // top: the vectors arrive as 32-bit words; otherwise the levels above left them on 29-bit limbs
+        const fr29 v = top ? fr29_from_fr(fr_load(&base[i])) : fr29_load(&base[i]);
         fr o;
 #pragma unroll
         for (int k = 0; k < 8; k++) o.v[k] = v.l[k];
@@ -315,7 +345,10 @@ __global__ void __launch_bounds__(256)
         }
         __syncthreads();
     }
-    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) fr_store(&base[i], fr_from_fr29(fr29_load(&sm[i])));
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
+        if (top) fr_store(&base[i], fr_from_fr29(fr29_load(&sm[i])));
+        else fr_store(&base[i], fr_load(&sm[i]));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -158,6 +158,38 @@ def test_fr29_normalised_butterfly_row():
     assert out.view(np.uint64).reshape(-1, 4).tobytes() == want.tobytes()
 
 
+def test_fr29_semi_reduced_rows():
+    """fr29_muladd_semi / fr29_dot2_semi: the rows between the levels of an extend stay below 2^232 with normalised limbs
+    and are congruent to the exact row; operands anywhere in [0, 2^232), including the extremes."""
+    rnd = random.Random(32)
+    top = (1 << 232) - 1
+    xs = [0, 1, P - 1, P, P + 1, top, top - 1, 1 << 231, (1 << 231) - 1, top - 12345]
+    ms = [0, 1, P - 1, P - 2, 1 << 230, (1 << 29) - 1]
+    m, m1, x0, x1 = [], [], [], []
+    for a in ms:
+        for b in xs:
+            for c in xs:
+                m.append(a), m1.append(ms[(len(m) * 7) % len(ms)]), x0.append(b), x1.append(c)
+    for _ in range(3000):
+        m.append(rnd.randrange(P)), m1.append(rnd.randrange(P))
+        x0.append(rnd.randrange(1 << 232)), x1.append(rnd.randrange(1 << 232))
+    n = len(m)
+    raw = lambda v: np.array([[(x >> (64 * i)) & (2**64 - 1) for i in range(4)] for x in v], dtype=np.uint64)
+    A = np.concatenate([dvpari.fr_to_mont(m), raw(x0)], axis=1).view(np.uint32).reshape(-1, 16)
+    B = np.concatenate([dvpari.fr_to_mont(m1), raw(x1)], axis=1).view(np.uint32).reshape(-1, 16)
+    for op in (20, 21):
+        out = np.zeros((n, 4), dtype=np.uint64)
+        dvpari._ck(dvpari.lib().dvp_hostcheck_op(op, dvpari._ptr(A), dvpari._ptr(B), dvpari._ptr(out), n))
+        got = [sum(int(out[i, j]) << (64 * j) for j in range(4)) for i in range(n)]
+        assert max(got) < 1 << 232
+        if op == 20:
+            want = [(c + a * b) % P for a, b, c in zip(m, x1, x0)]
+        else:
+            want = [(a * c + a1 * b) % P for a, a1, b, c in zip(m, m1, x1, x0)]
+        assert [g % P for g in got] == want
+        assert any(g >= P for g in got)  # the rows really are only semi-reduced
+
+
 def test_ld_projective_addition_is_complete(oracle):
     """k233_ld.cuh: the inversion-free addition used by the MSM's reduction trees, on projective operands with
     Z != 1, including equal operands in different representations (doubling branch), opposite operands and infinity."""
