@@ -125,11 +125,12 @@ def test_fftr_malformed_files_are_refused(tmp_path, oracle):
 
 @pytest.mark.gpu
 def test_domain_from_fftree_file(tmp_path, oracle):
-    """tree2n read for the prover (proving.rs:436): the extend over the file's domain equals the oracle's; a tree with
-    other leaves is refused; the cache-directory loader picks the file up."""
+    """tree2n read for the prover (proving.rs:436): the extend over the file's domain equals the oracle's (the reference's
+    test_verify_that_extend_works_over_minimal_tree, tree_io.rs:482-502, uses 64 constraints = 2^7 leaves); a tree with
+    other leaves is refused."""
     O = oracle
     ctx = dvpari.Context(0)
-    for lg in (4, 11):
+    for lg in (4, 7, 11):
         tree, od = oracle_tree(O, lg)
         path = tmp_path / f"tree2n_{lg}"
         artifacts.write_fftree_to_file(path, tree)
