@@ -158,7 +158,14 @@ def test_prove_from_artifact_files(ctx, oracle, tmp_path):
     cache = tmp_path / "cache"
     artifacts.write_cache_dir(str(cache), circ, srs.g_m30(), srs.g_q30(), gk, dvpari.fr_from_mont(w),
                               srs.bar_wts_mont(), srs.z_vals2inv_mont())
+    # ... and a tree2n file (tree_io.rs) in the cache: read for its leaves, which must be the device domain's
+    leaves = od.leaves_mont()
+    f = np.zeros((2 * leaves.shape[0], 4), dtype=np.uint64)
+    f[leaves.shape[0]:] = leaves
+    none = np.zeros((0, 4), dtype=np.uint64)
+    artifacts.write_fftree_to_file(cache / artifacts.TREE_2N, dict(f=f, recombine=none, decompose=none))
     prover_c, inst_c, dom_c = artifacts.load_prover_from_cache_dir(ctx, str(cache), k, slots=(7, 8, 9))
+    assert dom_c.n == n
     w_c = artifacts.load_witness_from_file(cache / artifacts.R1CS_WITNESS_FILE)
     assert prover_c.prove(w_c[1:1 + k], w_c[1 + k:]) == want
     prover_c.close(); inst_c.close(); dom_c.close()
