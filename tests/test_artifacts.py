@@ -1,5 +1,6 @@
 """Artifact formats either side of the path (no GPU): the reference's file layouts
 (io_utils.rs:1-7, gnark_r1cs.rs:1-20,58-77) read into the C ABI's layouts, with the reference's own known answer."""
+import ctypes as C
 import os
 import random
 import struct
@@ -10,6 +11,7 @@ import pytest
 import artifacts
 import dvpari
 import synth
+from guarded import Guarded
 
 P = dvpari.P
 
@@ -93,3 +95,42 @@ def test_sparse_r1cs_dump_round_trip(tmp_path, oracle):
     (tmp_path / "short").write_bytes(raw[:-3])
     with pytest.raises(dvpari.DvpError):
         artifacts.load_sparse_r1cs_from_file(tmp_path / "short", 2)
+
+
+def test_r1cs_dump_parser_survives_mutations(tmp_path):
+    """Truncated or corrupted dumps are refused (or parsed, when the damage leaves a well-formed file): never a read
+    outside the buffer.  The reference indexes its mmap with bounds checks and panics (gnark_r1cs.rs:121-185)."""
+    circ = synth.synth_r1cs(6, seed=3, nlevels=3)
+    path = tmp_path / "r1cs"
+    artifacts.write_sparse_r1cs_to_file(path, circ)
+    raw = path.read_bytes()
+    rnd = random.Random(6)
+    guard, L = Guarded(len(raw)), artifacts._bind()
+    ok = err = 0
+    for trial in range(400):
+        data = bytearray(raw)
+        kind = trial % 3
+        if kind == 0:
+            data = data[:rnd.randrange(len(data))]
+        elif kind == 1:
+            pos = rnd.randrange(0, len(data) - 4) & ~3
+            data[pos:pos + 4] = struct.pack("<I", rnd.choice([0, 1, 0xFFFFFFFF, 1 << 31, len(raw), 1 << 20]))
+        else:
+            for _ in range(6):
+                data[rnd.randrange(len(data))] ^= 1 << rnd.randrange(8)
+        # the image ends at an inaccessible page: an over-read is a crash, not a pass
+        addr = guard.put(data)
+        nc, nr, mw = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        nnz = (C.c_size_t * 3)()
+        if L.dvp_r1cs_dump_sizes(addr, len(data), C.byref(nc), C.byref(nr), C.byref(nnz), C.byref(mw)) != 0:
+            err += 1
+            continue
+        ok += 1
+        rowptr = [np.zeros(nr.value + 1, dtype=np.uint32) for _ in range(3)]
+        wire = [np.zeros(max(1, nnz[w]), dtype=np.uint32) for w in range(3)]
+        coeff = [np.zeros(max(1, nnz[w]), dtype=np.uint32) for w in range(3)]
+        coeffs = np.zeros((max(1, nc.value), 4), dtype=np.uint64)
+        arr = lambda grp: (C.c_void_p * 3)(*[x.ctypes.data for x in grp])
+        assert L.dvp_r1cs_dump_parse(addr, len(data), arr(rowptr), arr(wire), arr(coeff), dvpari._ptr(coeffs)) == 0
+        assert all(int(rowptr[w][-1]) == nnz[w] for w in range(3))
+    assert ok and err

@@ -3,6 +3,7 @@
 The container layout (magic, node header, section metas, nesting) is restated from tree_io.rs itself; the blobs are
 ark-serialize compressed vectors (u64 count | 29-byte Fr), the same element format io_utils.rs:127 pins.  The test trees
 are built from the oracle's domain: f = heap array of the isogeny layers, matrices in the form (v0, s0 v0; v1, s1 v1)."""
+import ctypes as C
 import struct
 
 import numpy as np
@@ -10,6 +11,7 @@ import pytest
 
 import artifacts
 import dvpari
+from guarded import Guarded
 
 P = dvpari.P
 
@@ -151,3 +153,48 @@ def test_domain_from_fftree_file(tmp_path, oracle):
         dvpari.Domain.from_fftree_file(ctx, tmp_path / "junk")
     assert e.value.code == 1
     ctx.close()
+
+
+def test_fftr_parser_survives_mutations(tmp_path, oracle):
+    """Truncations and random byte flips of a valid file: the parser answers with a leaf set or an error, never reads
+    outside the image (the reference slices with bounds checks and panics, tree_io.rs:254-259)."""
+    import random
+
+    tree, od = oracle_tree(oracle, 5)
+    tree["subtree"] = dict(f=tree["f"][:32], recombine=tree["recombine"][:16 * 4], decompose=tree["decompose"][:16 * 4])
+    path = tmp_path / "tree"
+    artifacts.write_fftree_to_file(path, tree)
+    raw = path.read_bytes()
+    rnd = random.Random(5)
+    guard = Guarded(len(raw))
+    outcomes = {"ok": 0, "err": 0}
+    head = 16 + 8 + 24 * 13  # magic, length, node header, section table
+    for trial in range(400):
+        data = bytearray(raw)
+        kind = trial % 4
+        if kind == 0:
+            data = data[:rnd.randrange(len(data))]
+        elif kind == 1:
+            for _ in range(rnd.randrange(1, 4)):
+                data[rnd.randrange(head)] = rnd.randrange(256)  # header / section table
+        elif kind == 2:
+            pos = rnd.randrange(8, head - 8)
+            data[pos:pos + 8] = struct.pack("<Q", rnd.choice([0, 1, 7, len(raw), len(raw) + 1, 1 << 31, 1 << 63, (1 << 64) - 1]))
+        else:
+            for _ in range(8):
+                data[rnd.randrange(len(data))] ^= 1 << rnd.randrange(8)
+        # the image ends at an inaccessible page: an over-read is a crash, not a pass
+        addr, L = guard.put(data), artifacts._bind()
+        for depth in (0, 1):
+            m = C.c_size_t()
+            rc = L.dvp_fftree_file_leaves(addr, len(data), depth, C.byref(m), None)
+            if rc == 0:
+                leaves = np.zeros((m.value, 4), dtype=np.uint64)
+                rc = L.dvp_fftree_file_leaves(addr, len(data), depth, C.byref(m), dvpari._ptr(leaves))
+            for which in (1, 2):
+                cnt = C.c_size_t()
+                if L.dvp_fftree_file_matrices(addr, len(data), depth, which, C.byref(cnt), None) == 0:
+                    mats = np.zeros((max(1, cnt.value), 16), dtype=np.uint64)
+                    L.dvp_fftree_file_matrices(addr, len(data), depth, which, C.byref(cnt), dvpari._ptr(mats))
+            outcomes["ok" if rc == 0 else "err"] += 1
+    assert outcomes["ok"] and outcomes["err"]
