@@ -139,7 +139,7 @@ def run_reference(args):
                    "note": "C restatement of the reference algorithm (the Rust crate cannot be built offline); "
                            f"each step is a 2^{lg_s}-point sample of the workload"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{args.steps} x 2^{lg_s} points, per-point wNAF scalar mul + sum, OpenMP all cores"},
+                         "sample": f"{args.steps} x 2^{lg_s} points, per-point tau-adic (width-4 TNAF) scalar mul + sum, OpenMP all cores"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -459,7 +459,7 @@ def main():
                           "instr_per_add": PASS2_ALU_INSTR_PER_ADD,
                           "peak_source": "measured LOP3 issue rate, profiles/r1_pipe_rates.json; IMAD.WIDE counted as one ALU-pipe slot (profiles/README.md)"},
             "cpu_baseline": {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"2^{lg_s} of the same SRS points, oracle k233_msm (per-point wNAF scalar mul + sum, curve.rs:141-158), "
+                             "sample": f"2^{lg_s} of the same SRS points, oracle k233_msm (per-point tau-adic width-4 TNAF scalar mul + sum, curve.rs:141-158), "
                                        f"{cdt:.2f} s, result equal to the GPU's"},
             "clocks": clocks,
             "device_ms_per_step": st["ms_device"],

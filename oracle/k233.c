@@ -206,7 +206,7 @@ void k233_mul_bytes(k233_pt *r, const k233_pt *p, const uint8_t *k, size_t klen)
     ld_to_affine(r, &acc);
 }
 
-void k233_mul_fr(k233_pt *r, const k233_pt *p, const fr_t *k) {
+void k233_mul_fr_wnaf(k233_pt *r, const k233_pt *p, const fr_t *k) {
     /* fr_to_le_bytes (curve.rs:162-182): canonical limbs, LE bytes, truncate to 30, strip trailing zeros */
     uint64_t c[4];
     uint8_t b[32];
@@ -216,6 +216,137 @@ void k233_mul_fr(k233_pt *r, const k233_pt *p, const fr_t *k) {
     while (len && b[len - 1] == 0) len--;
     k233_mul_bytes(r, p, b, len);
 }
+
+/*
+ * tau-adic scalar multiplication on the Koblitz curve -- what the reference's xsk233_mul_frob (curve.rs:118, "frob")
+ * does inside xs233: the Frobenius map tau(x, y) = (x^2, y^2) satisfies tau^2 + tau + 2 = 0 on K-233 (a = 0, mu = -1)
+ * and acts on E[r] as multiplication by lambda (lambda^2 + lambda + 2 = 0 mod r), so k P = sum_i u_i tau^i(P) for a
+ * tau-adic expansion of k: no doublings, only squarings.  Restated from J. Solinas, "Efficient arithmetic on Koblitz
+ * curves" (2000): width-4 TNAF (digits +-1 +-3 +-5 +-7, density 1/5, representatives alpha_u of u mod tau^4 below).
+ * The reduction of k to r0 + r1 tau with |r0|, |r1| < 2^118 is done GLV-style with a reduced basis (V1, V2) of the
+ * lattice { (a, c) : a + c lambda = 0 mod r } instead of Solinas' rounding in Z[tau]; any such pair gives the same point.
+ * Constants generated and checked with Python big integers (tests/test_oracle_k233.py cross-checks against the wNAF).
+ */
+typedef unsigned __int128 u128;
+typedef __int128 i128;
+static const uint64_t TAU_G1[5] = {0x751327740a80ea96ull, 0x34a059f450a5cbbdull, 0xe974eb7675acc618ull, 0x805b961da3b46581ull, 0x000000000000064aull}; /* floor(2^384 V2C / r) */
+static const uint64_t TAU_G2[5] = {0xa8d31ce74a1c19ddull, 0x39da825e09899e5eull, 0x79966d7dcb1ecea9ull, 0xae5af5c6dc2d5428ull, 0x0000000000001105ull}; /* floor(2^384 V1C / r) */
+#define U128(hi, lo) (((u128)(hi) << 64) | (u128)(lo))
+/* V1 = (V1A, V1C), V2 = (V2A, V2C), two's complement mod 2^128; V1A V2C - V2A V1C = r */
+#define TAU_V1A U128(0x000325402dcb0ed1ull, 0xda32c0f4ba75bb3bull)
+#define TAU_V1C U128(0x000882d72d7ae36eull, 0x16aa143ccb36bee6ull)
+#define TAU_V2A U128(0xfff21f91d2d547f5ull, 0xacde987b24083d6full)
+#define TAU_V2C U128(0x000325402dcb0ed1ull, 0xda32c0f4ba75bb3bull)
+
+/* floor(k g / 2^384) for k of 4 limbs and g of 5 limbs (the result fits 128 bits) */
+static u128 mul_shift384(const uint64_t k[4], const uint64_t g[5]) {
+    uint64_t prod[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 5; j++) {
+            const u128 t = (u128)k[i] * g[j] + prod[i + j] + carry;
+            prod[i + j] = (uint64_t)t;
+            carry = (uint64_t)(t >> 64);
+        }
+        prod[i + 5] = carry;
+    }
+    return U128(prod[7], prod[6]);
+}
+/* width-4 TNAF of the canonical scalar k (4 limbs): digits in {0, +-1, +-3, +-5, +-7}, returns the length (<= 240) */
+static int tau_recode(int8_t *dig, const uint64_t k[4]) {
+    const u128 q1 = mul_shift384(k, TAU_G1), q2 = mul_shift384(k, TAU_G2);
+    /* (k, 0) - q1 V1 + q2 V2, arithmetic mod 2^128: the true values are below 2^118 in absolute value */
+    i128 r0 = (i128)(U128(k[1], k[0]) - q1 * TAU_V1A + q2 * TAU_V2A);
+    i128 r1 = (i128)(q2 * TAU_V2C - q1 * TAU_V1C);
+    /* alpha_u = beta + gamma tau for u = 1, 3, 5, 7:  1,  -3 - tau,  -1 - tau,  1 - tau;  t_4 = 10 (tau mod tau^4) */
+    static const int beta[4] = {1, -3, -1, 1}, gamma[4] = {0, -1, -1, -1};
+    int len = 0;
+    while ((r0 != 0 || r1 != 0) && len < 250) {
+        int u = 0;
+        if (r0 & 1) {
+            u = (int)((uint64_t)(r0 + r1 * 10) & 15);
+            if (u >= 8) u -= 16;
+            const int a = u > 0 ? u : -u, sg = u > 0 ? 1 : -1;
+            r0 -= sg * beta[a >> 1];
+            r1 -= sg * gamma[a >> 1];
+        }
+        dig[len++] = (int8_t)u;
+        /* (r0 + r1 tau) / tau = (r1 - r0/2) - (r0/2) tau */
+        const i128 half = r0 / 2; /* r0 is even here */
+        r0 = r1 - half;
+        r1 = -half;
+    }
+    return len;
+}
+static void ld_frobenius(ld_pt *p) {
+    gf_sqr(&p->X, &p->X);
+    gf_sqr(&p->Y, &p->Y);
+    gf_sqr(&p->Z, &p->Z);
+}
+/* r = a + b for affine a, b with x_a != x_b, given inv = 1/(x_a + x_b) */
+static void aff_add_with_inv(k233_pt *r, const k233_pt *a, const gf_t *bx, const gf_t *by, const gf_t *inv) {
+    gf_t l, t, dx, x3, y3;
+    gf_add(&dx, &a->x, bx);
+    gf_add(&t, &a->y, by);
+    gf_mul(&l, &t, inv);
+    gf_sqr(&x3, &l);
+    gf_add(&x3, &x3, &l);
+    gf_add(&x3, &x3, &dx);
+    gf_add(&t, &a->x, &x3);
+    gf_mul(&y3, &l, &t);
+    gf_add(&y3, &y3, &x3);
+    gf_add(&y3, &y3, &a->y);
+    r->x = x3;
+    r->y = y3;
+    r->inf = 0;
+}
+static void k233_mul_tau_ld(ld_pt *acc, const k233_pt *p, const fr_t *k) {
+    acc->X = GF_ONE; acc->Y = GF_ZERO; acc->Z = GF_ZERO;
+    uint64_t c[4];
+    fr_to_canonical(c, k);
+    if (p->inf || !(c[0] | c[1] | c[2] | c[3])) return;
+    int8_t dig[256];
+    const int len = tau_recode(dig, c);
+    /* table: P, alpha_3 P = tau^2 P - P, alpha_5 P = -(P + tau P), alpha_7 P = P - tau P; the two denominators
+       x_P + x_tauP and x_P + x_tau2P are inverted together.  They vanish only for points outside E[r] \ {inf}. */
+    k233_pt tab[4], T1, T2, nT, nP;
+    T1.inf = T2.inf = 0;
+    gf_sqr(&T1.x, &p->x); gf_sqr(&T1.y, &p->y);
+    gf_sqr(&T2.x, &T1.x); gf_sqr(&T2.y, &T1.y);
+    gf_t d1, d2, d12, i12, i1, i2;
+    gf_add(&d1, &p->x, &T1.x);
+    gf_add(&d2, &p->x, &T2.x);
+    if (gf_is_zero(&d1) || gf_is_zero(&d2)) { /* not a point of E[r]: plain double-and-add */
+        k233_pt t;
+        k233_mul_fr_wnaf(&t, p, k);
+        ld_from_affine(acc, &t);
+        return;
+    }
+    gf_mul(&d12, &d1, &d2);
+    gf_inv(&i12, &d12);
+    gf_mul(&i1, &i12, &d2);
+    gf_mul(&i2, &i12, &d1);
+    tab[0] = *p;
+    k233_neg(&nP, p);
+    aff_add_with_inv(&tab[1], &T2, &nP.x, &nP.y, &i2);  /* tau^2 P - P */
+    aff_add_with_inv(&tab[2], p, &T1.x, &T1.y, &i1);    /* P + tau P, negated below */
+    k233_neg(&tab[2], &tab[2]);
+    k233_neg(&nT, &T1);
+    aff_add_with_inv(&tab[3], p, &nT.x, &nT.y, &i1);    /* P - tau P */
+    for (int i = len - 1; i >= 0; i--) {
+        ld_frobenius(acc);
+        const int d = dig[i];
+        if (d > 0) ld_add_mixed(acc, acc, &tab[d >> 1]);
+        else if (d < 0) { k233_pt nq; k233_neg(&nq, &tab[(-d) >> 1]); ld_add_mixed(acc, acc, &nq); }
+    }
+}
+void k233_mul_fr_tau(k233_pt *r, const k233_pt *p, const fr_t *k) {
+    ld_pt acc;
+    k233_mul_tau_ld(&acc, p, k);
+    ld_to_affine(r, &acc);
+}
+/* point_scalar_mul (curve.rs:113-126): the reference calls xsk233_mul_frob, i.e. the tau-adic ladder */
+void k233_mul_fr(k233_pt *r, const k233_pt *p, const fr_t *k) { k233_mul_fr_tau(r, p, k); }
 
 void xsk233_encode(uint8_t out[30], const k233_pt *p) {
     if (p->inf) { memset(out, 0, 30); return; }

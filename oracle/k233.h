@@ -42,6 +42,10 @@ int  k233_eq(const k233_pt *p, const k233_pt *q);
 void k233_mul_bytes(k233_pt *r, const k233_pt *p, const uint8_t *k, size_t klen);
 /* k * P with k an Fr in Montgomery form: fr_to_le_bytes + point_scalar_mul (curve.rs:113-126,162-182) */
 void k233_mul_fr(k233_pt *r, const k233_pt *p, const fr_t *k);
+/* the two implementations behind it: tau-adic width-4 TNAF (the reference's xsk233_mul_frob; the default) and
+ * width-4 NAF double-and-add (kept as the cross-check) */
+void k233_mul_fr_tau(k233_pt *r, const k233_pt *p, const fr_t *k);
+void k233_mul_fr_wnaf(k233_pt *r, const k233_pt *p, const fr_t *k);
 
 /* xsk233 codec on the E[r] representative P = Q + N of the group element Q */
 void xsk233_encode(uint8_t out[30], const k233_pt *p);

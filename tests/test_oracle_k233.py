@@ -90,3 +90,37 @@ def test_decode_rejects_points_outside_the_group(oracle):
     assert 10 < valid < 60  # one w in four names a group element
     assert not O.pt_decode((1).to_bytes(30, "little"))[1]  # w = 1: x = 1, an order-4 point
     assert not O.pt_decode(bytes(29) + b"\x02")[1]  # bit 233 set
+
+
+def test_tau_adic_scalar_mul(oracle, ossl):
+    """k233_mul_fr_tau (width-4 TNAF over the Frobenius map, the algorithm of the reference's xsk233_mul_frob,
+    curve.rs:118) against the double-and-add wNAF and against OpenSSL: edge scalars, random scalars, several points,
+    the point at infinity, and a point outside E[r] (the ladder's table degenerates there and falls back)."""
+    O = oracle
+    L = O.lib()
+    rnd = random.Random(41)
+    G = O.generator()
+    P = O.P
+    edge = [0, 1, 2, 3, 5, 7, 9, 10, 15, 16, P - 1, P - 2, (P - 1) // 2, 1 << 231, (1 << 231) - 1, 1 << 116, (1 << 117) - 1,
+            (1 << 128) - 1, 1 << 128]
+    pts = [G, O.pt_mul(G, rnd.randrange(1, P)), O.pt_mul(G, P - 1), O.pt()]
+    for p in pts:
+        for k in edge + [rnd.randrange(P) for _ in range(150)]:
+            a, b = O.pt(), O.pt()
+            km = O.fr_mont(k)
+            L.k233_mul_fr_tau(C.byref(a), C.byref(p), C.byref(km))
+            L.k233_mul_fr_wnaf(C.byref(b), C.byref(p), C.byref(km))
+            assert O.pt_xy(a) == O.pt_xy(b), k
+    for k in [rnd.randrange(P) for _ in range(10)] + [P - 1, 1 << 231]:
+        a = O.pt()
+        km = O.fr_mont(k)
+        L.k233_mul_fr_tau(C.byref(a), C.byref(G), C.byref(km))
+        assert O.pt_xy(a) == _ossl_mul(ossl, O, k, G)
+    # N = (0, 1), the point of order 2: tau N = N, the table's denominators vanish
+    N = O.pt(0, 1)
+    for k in (1, 2, 3, P - 1):
+        a, b = O.pt(), O.pt()
+        km = O.fr_mont(k)
+        L.k233_mul_fr_tau(C.byref(a), C.byref(N), C.byref(km))
+        L.k233_mul_fr_wnaf(C.byref(b), C.byref(N), C.byref(km))
+        assert O.pt_xy(a) == O.pt_xy(b)
