@@ -104,8 +104,28 @@ static uint64_t spread32(uint32_t v) {
     x = (x | (x << 1)) & 0x5555555555555555ULL;
     return x;
 }
+#if defined(__x86_64__)
+#include <immintrin.h>
+/* squaring = bit spreading: one PDEP per 32 input bits (BMI2), chosen at run time */
+static int g_bmi2 = -1;
+__attribute__((target("bmi2"))) static void sqr_pdep(gf_t *r, const gf_t *a) {
+    uint64_t c[8];
+    for (int i = 0; i < 4; i++) {
+        c[2 * i] = _pdep_u64(a->w[i] & 0xffffffffu, 0x5555555555555555ULL);
+        c[2 * i + 1] = _pdep_u64(a->w[i] >> 32, 0x5555555555555555ULL);
+    }
+    gf_reduce(r, c);
+}
+#endif
 void gf_sqr(gf_t *r, const gf_t *a) {
     uint64_t c[8];
+#if defined(__x86_64__)
+    if (g_bmi2 < 0) g_bmi2 = __builtin_cpu_supports("bmi2") ? 1 : 0;
+    if (g_bmi2 && !g_portable) {
+        sqr_pdep(r, a);
+        return;
+    }
+#endif
 #if defined(__PCLMUL__)
     if (!g_portable) {
         __m128i a01 = _mm_loadu_si128((const __m128i *)&a->w[0]), a23 = _mm_loadu_si128((const __m128i *)&a->w[2]);
