@@ -59,29 +59,29 @@ static void mul_portable(uint64_t c[8], const gf_t *a, const gf_t *b) {
 }
 
 #if defined(__PCLMUL__)
+/* 128 x 128 -> 256 bits carry-less, Karatsuba: 3 PCLMULQDQ */
+static inline __attribute__((always_inline)) void clmul128(__m128i *lo, __m128i *hi, __m128i a, __m128i b) {
+    const __m128i t0 = _mm_clmulepi64_si128(a, b, 0x00), t2 = _mm_clmulepi64_si128(a, b, 0x11);
+    const __m128i am = _mm_xor_si128(a, _mm_srli_si128(a, 8)), bm = _mm_xor_si128(b, _mm_srli_si128(b, 8));
+    const __m128i t1 = _mm_xor_si128(_mm_clmulepi64_si128(am, bm, 0x00), _mm_xor_si128(t0, t2));
+    *lo = _mm_xor_si128(t0, _mm_slli_si128(t1, 8));
+    *hi = _mm_xor_si128(t2, _mm_srli_si128(t1, 8));
+}
 static void mul_pclmul(uint64_t c[8], const gf_t *a, const gf_t *b) {
-    /* 16 products accumulated in seven 128-bit columns (column k sits at bit offset 64 k) */
-    __m128i a01 = _mm_loadu_si128((const __m128i *)&a->w[0]), a23 = _mm_loadu_si128((const __m128i *)&a->w[2]);
-    __m128i b01 = _mm_loadu_si128((const __m128i *)&b->w[0]), b23 = _mm_loadu_si128((const __m128i *)&b->w[2]);
-    __m128i k0 = _mm_clmulepi64_si128(a01, b01, 0x00);
-    __m128i k1 = _mm_xor_si128(_mm_clmulepi64_si128(a01, b01, 0x10), _mm_clmulepi64_si128(a01, b01, 0x01));
-    __m128i k2 = _mm_xor_si128(_mm_clmulepi64_si128(a01, b01, 0x11),
-                               _mm_xor_si128(_mm_clmulepi64_si128(a01, b23, 0x00), _mm_clmulepi64_si128(a23, b01, 0x00)));
-    __m128i k3 = _mm_xor_si128(_mm_xor_si128(_mm_clmulepi64_si128(a01, b23, 0x10), _mm_clmulepi64_si128(a01, b23, 0x01)),
-                               _mm_xor_si128(_mm_clmulepi64_si128(a23, b01, 0x10), _mm_clmulepi64_si128(a23, b01, 0x01)));
-    __m128i k4 = _mm_xor_si128(_mm_clmulepi64_si128(a23, b23, 0x00),
-                               _mm_xor_si128(_mm_clmulepi64_si128(a01, b23, 0x11), _mm_clmulepi64_si128(a23, b01, 0x11)));
-    __m128i k5 = _mm_xor_si128(_mm_clmulepi64_si128(a23, b23, 0x10), _mm_clmulepi64_si128(a23, b23, 0x01));
-    __m128i k6 = _mm_clmulepi64_si128(a23, b23, 0x11);
-    /* fold odd columns into the even ones */
-    k0 = _mm_xor_si128(k0, _mm_slli_si128(k1, 8));
-    k2 = _mm_xor_si128(k2, _mm_xor_si128(_mm_srli_si128(k1, 8), _mm_slli_si128(k3, 8)));
-    k4 = _mm_xor_si128(k4, _mm_xor_si128(_mm_srli_si128(k3, 8), _mm_slli_si128(k5, 8)));
-    k6 = _mm_xor_si128(k6, _mm_srli_si128(k5, 8));
-    c[0] = (uint64_t)_mm_cvtsi128_si64(k0); c[1] = (uint64_t)_mm_extract_epi64(k0, 1);
-    c[2] = (uint64_t)_mm_cvtsi128_si64(k2); c[3] = (uint64_t)_mm_extract_epi64(k2, 1);
-    c[4] = (uint64_t)_mm_cvtsi128_si64(k4); c[5] = (uint64_t)_mm_extract_epi64(k4, 1);
-    c[6] = (uint64_t)_mm_cvtsi128_si64(k6); c[7] = (uint64_t)_mm_extract_epi64(k6, 1);
+    /* two levels of Karatsuba: 9 products instead of 16 */
+    const __m128i a0 = _mm_loadu_si128((const __m128i *)&a->w[0]), a1 = _mm_loadu_si128((const __m128i *)&a->w[2]);
+    const __m128i b0 = _mm_loadu_si128((const __m128i *)&b->w[0]), b1 = _mm_loadu_si128((const __m128i *)&b->w[2]);
+    __m128i p0l, p0h, p2l, p2h, p1l, p1h;
+    clmul128(&p0l, &p0h, a0, b0);
+    clmul128(&p2l, &p2h, a1, b1);
+    clmul128(&p1l, &p1h, _mm_xor_si128(a0, a1), _mm_xor_si128(b0, b1));
+    p1l = _mm_xor_si128(p1l, _mm_xor_si128(p0l, p2l));
+    p1h = _mm_xor_si128(p1h, _mm_xor_si128(p0h, p2h));
+    const __m128i r0 = p0l, r1 = _mm_xor_si128(p0h, p1l), r2 = _mm_xor_si128(p2l, p1h), r3 = p2h;
+    _mm_storeu_si128((__m128i *)&c[0], r0);
+    _mm_storeu_si128((__m128i *)&c[2], r1);
+    _mm_storeu_si128((__m128i *)&c[4], r2);
+    _mm_storeu_si128((__m128i *)&c[6], r3);
 }
 #endif
 
