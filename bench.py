@@ -328,7 +328,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lg", type=int, default=20, help="log2 of the points per GPU")
-    ap.add_argument("--cpu-lg", type=int, default=19, help="log2 of the CPU-baseline sample (2^19 points ~ 20 s of CPU-core time)")
+    ap.add_argument("--cpu-lg", type=int, default=20, help="log2 of the CPU-baseline sample (2^20 points = the whole workload, ~ 15-30 s of CPU-core time)")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--prove-lg", type=int, default=22, help="log2 of the constraint count of the prove measurement (0 = skip)")
     args = ap.parse_args()
