@@ -340,6 +340,45 @@ static void k233_mul_tau_ld(ld_pt *acc, const k233_pt *p, const fr_t *k) {
         else if (d < 0) { k233_pt nq; k233_neg(&nq, &tab[(-d) >> 1]); ld_add_mixed(acc, acc, &nq); }
     }
 }
+/* general Lopez-Dahab addition (Lange-Doche 2005 form, 13M + 4S), with the exceptional cases handled in front */
+static void ld_add(ld_pt *r, const ld_pt *p, const ld_pt *q) {
+    if (gf_is_zero(&p->Z)) { *r = *q; return; }
+    if (gf_is_zero(&q->Z)) { *r = *p; return; }
+    gf_t A, B, C, D, E, F, G, H, I, J, t, u;
+    ld_pt o;
+    gf_mul(&A, &p->X, &q->Z);
+    gf_mul(&B, &q->X, &p->Z);
+    gf_sqr(&t, &q->Z);
+    gf_mul(&G, &p->Y, &t);
+    gf_sqr(&t, &p->Z);
+    gf_mul(&H, &q->Y, &t);
+    gf_add(&E, &A, &B);
+    gf_add(&I, &G, &H);
+    if (gf_is_zero(&E)) { /* same x: P = Q or P = -Q */
+        if (gf_is_zero(&I)) { ld_dbl(r, p); return; }
+        r->X = GF_ONE; r->Y = GF_ZERO; r->Z = GF_ZERO;
+        return;
+    }
+    gf_sqr(&C, &A);
+    gf_sqr(&D, &B);
+    gf_add(&F, &C, &D);
+    gf_mul(&J, &I, &E);
+    gf_mul(&t, &p->Z, &q->Z);
+    gf_mul(&o.Z, &F, &t);
+    gf_add(&t, &H, &D);
+    gf_mul(&t, &A, &t);
+    gf_add(&u, &C, &G);
+    gf_mul(&u, &B, &u);
+    gf_add(&o.X, &t, &u);
+    gf_mul(&t, &A, &J);
+    gf_mul(&u, &F, &G);
+    gf_add(&t, &t, &u);
+    gf_mul(&t, &t, &F);
+    gf_add(&u, &J, &o.Z);
+    gf_mul(&u, &u, &o.X);
+    gf_add(&o.Y, &t, &u);
+    *r = o;
+}
 void k233_mul_fr_tau(k233_pt *r, const k233_pt *p, const fr_t *k) {
     ld_pt acc;
     k233_mul_tau_ld(&acc, p, k);
@@ -415,9 +454,10 @@ void k233_msm(k233_pt *r, const fr_t *scalars, const k233_pt *points, size_t n, 
 #pragma omp for schedule(dynamic, 64)
 #endif
         for (long i = 0; i < (long)n; i++) {
-            k233_pt s;
-            k233_mul_fr(&s, &points[i], &scalars[i]);
-            ld_add_mixed(&acc, &acc, &s);
+            /* the products stay projective (xs233 keeps extended coordinates too): no inversion per point */
+            ld_pt s;
+            k233_mul_tau_ld(&s, &points[i], &scalars[i]);
+            ld_add(&acc, &acc, &s);
         }
         ld_to_affine(&part[tid], &acc);
     }

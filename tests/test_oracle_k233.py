@@ -124,3 +124,36 @@ def test_tau_adic_scalar_mul(oracle, ossl):
         L.k233_mul_fr_tau(C.byref(a), C.byref(N), C.byref(km))
         L.k233_mul_fr_wnaf(C.byref(b), C.byref(N), C.byref(km))
         assert O.pt_xy(a) == O.pt_xy(b)
+
+
+def test_msm_projective_accumulation_degenerate_cases(oracle):
+    """k233_msm keeps the per-point products projective and adds them with the general Lopez-Dahab addition: equal
+    operands (doubling branch), opposite operands (infinity), infinity on either side, in a fixed order (one thread),
+    and a random set on all cores against the sum of single multiplications (curve.rs:218-232 restated)."""
+    O = oracle
+    P = O.P
+    rnd = random.Random(43)
+    G = O.generator()
+    G2, nG, inf = O.pt_mul(G, 2), O.pt_neg(G), O.pt()
+    cases = [
+        ([G, G], [1, 1]),                       # acc = G, + G: doubling
+        ([G, nG, G2], [1, 1, 1]),               # G - G = infinity, then + 2G
+        ([inf, G, inf, G], [5, 1, 7, 1]),       # infinity operands on both sides
+        ([G, G, G, G], [3, 3, P - 6, 0]),       # 3G + 3G (doubling) + (-6G) = infinity, + 0
+        ([G2, G], [1, 2]),                      # 2G + 2G from different inputs
+        ([G, G], [P - 1, 1]),                   # -G + G
+    ]
+    for pts, ks in cases:
+        want = O.pt()
+        for p, k in zip(pts, ks):
+            want = O.pt_add(want, O.pt_mul(p, k))
+        got = O.msm(O.mont_array(ks), O.points_to_array(pts), 1)
+        assert O.pt_xy(got) == O.pt_xy(want), ks
+    n = 600
+    ks = [rnd.randrange(P) for _ in range(n)]
+    pts = [O.pt_mul(G, rnd.randrange(1, P)) for _ in range(8)]
+    plist = [pts[i % 8] for i in range(n)]
+    want = O.pt()
+    for p, k in zip(plist, ks):
+        want = O.pt_add(want, O.pt_mul(p, k))
+    assert O.pt_xy(O.msm(O.mont_array(ks), O.points_to_array(plist), 0)) == O.pt_xy(want)
