@@ -65,7 +65,11 @@ static void fr_pow2k(fr_t *r, const fr_t *v, int e) {
     *r = t;
 }
 
-ecfft_domain *ecfft_domain_new(int log_n2) {
+static ecfft_domain *domain_new(int log_n2, int with_matrices);
+ecfft_domain *ecfft_domain_new(int log_n2) { return domain_new(log_n2, 1); }
+ecfft_domain *ecfft_domain_new_light(int log_n2) { return domain_new(log_n2, 0); }
+
+static ecfft_domain *domain_new(int log_n2, int with_matrices) {
     assert(log_n2 >= 1 && log_n2 <= 28);
     ecfft_domain *d = (ecfft_domain *)calloc(1, sizeof(*d));
     const size_t N = (size_t)1 << log_n2;
@@ -142,6 +146,7 @@ ecfft_domain *ecfft_domain_new(int log_n2) {
         fr_t *den = (fr_t *)malloc(half * sizeof(fr_t));
         for (size_t i = 0; i < half; i++) fr_sub(&den[i], &layer[k][i], &x0);
         fr_batch_inv(den, half);
+#pragma omp parallel for schedule(static) if (half >= 4096)
         for (size_t i = 0; i < half; i++) {
             fr_t q;
             fr_mul(&q, &t, &den[i]);
@@ -173,7 +178,7 @@ ecfft_domain *ecfft_domain_new(int log_n2) {
     const size_t n = N >> 1;
     d->dec = (fr_t **)calloc((size_t)d->levels + 1, sizeof(fr_t *));
     d->rec = (fr_t **)calloc((size_t)d->levels + 1, sizeof(fr_t *));
-    for (int k = 0; k < d->levels; k++) {
+    for (int k = 0; with_matrices && k < d->levels; k++) {
         const size_t m = n >> k, h = m >> 1;
         const fr_t *L = layer[k];
         const fr_t x0 = d->x0[k];
@@ -183,6 +188,7 @@ ecfft_domain *ecfft_domain_new(int log_n2) {
         d->rec[k] = (fr_t *)malloc(h * 4 * sizeof(fr_t));
         fr_t *det = (fr_t *)malloc(h * sizeof(fr_t));
         fr_t *sv = (fr_t *)malloc(h * 2 * sizeof(fr_t));
+#pragma omp parallel for schedule(static) if (h >= 1024)
         for (size_t j = 0; j < h; j++) {
             /* source pair (even leaves 2j, 2j+m), target pair (odd leaves 2j+1, 2j+1+m) */
             const fr_t s[2] = {L[2 * j], L[2 * j + m]}, tg[2] = {L[2 * j + 1], L[2 * j + 1 + m]};
@@ -210,6 +216,7 @@ ecfft_domain *ecfft_domain_new(int log_n2) {
             sv[2 * j + 1] = vs[1];
         }
         fr_batch_inv(det, h);
+#pragma omp parallel for schedule(static) if (h >= 1024)
         for (size_t j = 0; j < h; j++) {
             const fr_t s0 = L[2 * j], s1 = L[2 * j + m];
             fr_t *M = &d->dec[k][4 * j], tmp;
@@ -234,7 +241,7 @@ void ecfft_domain_free(ecfft_domain *d) {
     fr_t **layer = layers_of(d);
     for (int k = 0; k <= d->log_n2; k++) free(layer[k]);
     free(layer);
-    for (int k = 0; k < d->levels; k++) { free(d->dec[k]); free(d->rec[k]); }
+    for (int k = 0; k < d->levels; k++) { free(d->dec[k]); free(d->rec[k]); } /* NULL in a light domain */
     free(d->dec); free(d->rec); free(d->x0); free(d->t); free(d->last);
     free(d);
 }
@@ -296,6 +303,7 @@ void ecfft_vanish_derivative_on_roots(const ecfft_domain *d, int shift, fr_t *ou
         fr_t *inv = (fr_t *)malloc(m * sizeof(fr_t));
         memcpy(inv, den, m * sizeof(fr_t));
         fr_batch_inv(inv, m);
+#pragma omp parallel for schedule(static) if (m >= 4096)
         for (size_t j = 0; j < m; j++) {
             /* Z'_S(s) = v(s)^h psi'(s) Z'_psi(S)(psi(s)), psi' = 1 - t/(s-x0)^2 */
             fr_t pw, dpsi, q;
@@ -324,6 +332,7 @@ void ecfft_vanish_on_other(const ecfft_domain *d, int shift, fr_t *out) {
     fr_sub(&cur[0], &d->last[1 - shift], &d->last[shift]);
     for (int k = d->levels - 1; k >= 0; k--) {
         const size_t m = n >> k, h = m >> 1;
+#pragma omp parallel for schedule(static) if (m >= 4096)
         for (size_t j = 0; j < m; j++) {
             fr_t v, pw;
             fr_sub(&v, &layer[k][2 * j + (1 - shift)], &d->x0[k]);
@@ -335,4 +344,30 @@ void ecfft_vanish_on_other(const ecfft_domain *d, int shift, fr_t *out) {
     memcpy(out, cur, n * sizeof(fr_t));
     free(cur);
     free(nxt);
+}
+
+/* evaluate_poly_at_alpha_using_barycentric_weights (/root/reference/src/ec_fft.rs:455-491) for several points:
+ * out[q] = Z_D(x_q) * sum_i evals[i] * w_i / (x_q - d_i), w_i = 1/Z'_D(d_i), D = the even leaves.  O(n) per point
+ * (plus the weights once); works on a light domain.  No x_q may lie in D. */
+void ecfft_bary_eval(const ecfft_domain *d, const fr_t *evals, const fr_t *xs, size_t nx, fr_t *out) {
+    const size_t n = d->n2 >> 1;
+    fr_t *w = (fr_t *)malloc(n * sizeof(fr_t));
+    ecfft_vanish_derivative_on_roots(d, 0, w);
+    fr_batch_inv(w, n);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t q = 0; q < nx; q++) {
+        fr_t *den = (fr_t *)malloc(n * sizeof(fr_t));
+        for (size_t i = 0; i < n; i++) fr_sub(&den[i], &xs[q], &d->leaves[2 * i]);
+        fr_batch_inv(den, n);
+        fr_t acc = FR_ZERO, t, z;
+        for (size_t i = 0; i < n; i++) {
+            fr_mul(&t, &w[i], &den[i]);
+            fr_mul(&t, &t, &evals[i]);
+            fr_add(&acc, &acc, &t);
+        }
+        ecfft_vanish_at(d, 0, &xs[q], &z);
+        fr_mul(&out[q], &acc, &z);
+        free(den);
+    }
+    free(w);
 }

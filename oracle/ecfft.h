@@ -39,6 +39,9 @@ typedef struct {
 
 /* Build leaves, isogenies and the extend matrices (D -> D') for N = 2^log_n2 leaves. */
 ecfft_domain *ecfft_domain_new(int log_n2);
+/* leaves, isogeny chain and lower layers only (no extend matrices): enough for the chain-rule helpers and
+ * ecfft_bary_eval at sizes where the matrices would take minutes on one core */
+ecfft_domain *ecfft_domain_new_light(int log_n2);
 void ecfft_domain_free(ecfft_domain *d);
 /* out[i] = value at D'[i] of the interpolant of in[] on D; n = N/2 elements */
 void ecfft_extend(const ecfft_domain *d, const fr_t *in, fr_t *out);
@@ -48,6 +51,9 @@ void ecfft_vanish_at(const ecfft_domain *d, int shift, const fr_t *x, fr_t *out)
 void ecfft_vanish_derivative_on_roots(const ecfft_domain *d, int shift, fr_t *out);
 /* Z_S evaluated on the n points of the other half-domain */
 void ecfft_vanish_on_other(const ecfft_domain *d, int shift, fr_t *out);
+
+/* O(n) barycentric evaluation of the interpolant of evals on D at nx points outside D (ec_fft.rs:455-491) */
+void ecfft_bary_eval(const ecfft_domain *d, const fr_t *evals, const fr_t *xs, size_t nx, fr_t *out);
 
 #ifdef __cplusplus
 }

@@ -179,3 +179,27 @@ void fr_batch_inv(fr_t *v, size_t n) {
     }
     free(pre);
 }
+
+/* s0 = sum k_i, s1 = sum i * k_i over Montgomery-form scalars: the closed form of an MSM over points A + i Q
+ * (tests of the full-size configurations) */
+void fr_sum_weighted(const fr_t *k, size_t n, fr_t *s0, fr_t *s1) {
+    fr_t a0 = FR_ZERO, a1 = FR_ZERO;
+#pragma omp parallel
+    {
+        fr_t l0 = FR_ZERO, l1 = FR_ZERO, idx, t;
+#pragma omp for schedule(static) nowait
+        for (size_t i = 0; i < n; i++) {
+            fr_from_u64(&idx, (uint64_t)i);
+            fr_mul(&t, &idx, &k[i]);
+            fr_add(&l0, &l0, &k[i]);
+            fr_add(&l1, &l1, &t);
+        }
+#pragma omp critical
+        {
+            fr_add(&a0, &a0, &l0);
+            fr_add(&a1, &a1, &l1);
+        }
+    }
+    *s0 = a0;
+    *s1 = a1;
+}

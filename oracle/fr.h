@@ -44,6 +44,8 @@ void fr_to_le29(uint8_t out[29], const fr_t *a);
 int  fr_from_le29(fr_t *r, const uint8_t in[29]); /* returns 0 if >= p */
 /* ark_ff::batch_inversion semantics: zeros stay zero */
 void fr_batch_inv(fr_t *v, size_t n);
+/* s0 = sum k_i, s1 = sum i k_i (closed form of an MSM over the points A + i Q) */
+void fr_sum_weighted(const fr_t *k, size_t n, fr_t *s0, fr_t *s1);
 
 #ifdef __cplusplus
 }

@@ -203,6 +203,14 @@ def msm(scalars_mont, pts_arr, nthreads=0):
     return r
 
 
+def sum_weighted(scalars_mont):
+    """(sum k_i, sum i k_i) mod p as ints, for (n,4) uint64 Montgomery scalars"""
+    sc = np.ascontiguousarray(scalars_mont, dtype=np.uint64)
+    s0, s1 = Fr(), Fr()
+    lib().fr_sum_weighted(sc.ctypes.data_as(C.c_void_p), C.c_size_t(sc.shape[0]), C.byref(s0), C.byref(s1))
+    return fr_int(s0), fr_int(s1)
+
+
 # ---------------------------------------------------------------- bulk fixtures
 def chain_points(n, p0, q):
     """ctypes Pt array with out[i] = p0 + i*q"""
@@ -260,10 +268,13 @@ class Domain:
                     ("dec", C.c_void_p), ("rec", C.c_void_p), ("x0", C.c_void_p), ("t", C.c_void_p),
                     ("last", C.c_void_p)]
 
-    def __init__(self, log_n2):
+    def __init__(self, log_n2, light=False):
+        """light: leaves + isogeny chain only (no extend matrices) -- for the chain-rule helpers and bary_eval at full size"""
         L = lib()
         L.ecfft_domain_new.restype = C.POINTER(Domain._S)
-        self._d = L.ecfft_domain_new(log_n2)
+        L.ecfft_domain_new_light.restype = C.POINTER(Domain._S)
+        self._d = (L.ecfft_domain_new_light if light else L.ecfft_domain_new)(log_n2)
+        self.light = light
         self.log_n2 = log_n2
         self.n2 = 1 << log_n2
         self.n = self.n2 >> 1
@@ -288,7 +299,17 @@ class Domain:
         return (mont_array_to_ints(self._arr(self._d.contents.x0, self.log_n2)),
                 mont_array_to_ints(self._arr(self._d.contents.t, self.log_n2)))
 
+    def bary_eval_mont(self, evals_mont, xs_mont):
+        """interpolant of evals (on D) at the points xs: O(n) each, ec_fft.rs:455-491"""
+        a = np.ascontiguousarray(evals_mont, dtype=np.uint64).reshape(self.n, 4)
+        xs = np.ascontiguousarray(xs_mont, dtype=np.uint64).reshape(-1, 4)
+        out = np.zeros_like(xs)
+        lib().ecfft_bary_eval(self._d, a.ctypes.data_as(C.c_void_p), xs.ctypes.data_as(C.c_void_p),
+                              C.c_size_t(xs.shape[0]), out.ctypes.data_as(C.c_void_p))
+        return out
+
     def extend_mont(self, evals_mont):
+        assert not self.light
         a = np.ascontiguousarray(evals_mont, dtype=np.uint64).reshape(self.n, 4)
         out = np.zeros_like(a)
         lib().ecfft_extend(self._d, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
