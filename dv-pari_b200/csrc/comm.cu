@@ -6,12 +6,17 @@
 // exchanges are: an all-gather of the row-range outputs, a broadcast of every extended polynomial from
 // its owner, and an all-gather of one 64-byte partial sum per rank and MSM, folded identically on every
 // rank (GF(2^233) point addition is not an NCCL reduction operator).
+// A second backend joins several contexts of ONE process (each driven by its own host thread, on one device or
+// several) without NCCL: the same collectives as device-to-device copies between the ranks' buffers behind a
+// host-side rendezvous (dvp_comm_init_local).  It runs the whole partition logic on a single GPU.
 // libnccl is bound at run time (dlopen) so that the library loads on hosts without it; the unique id
 // travels by whatever channel the host has (torch.distributed store, MPI, a file).
 #include <dlfcn.h>
 #include <nccl.h>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include "ctx.cuh"
 #include "host_gf.hpp"
 
@@ -76,17 +81,96 @@ bool nccl_load() {
         }                                                                                                     \
     } while (0)
 
+// ------------------------------------------------------------------------------------------------
+// in-process backend: the ranks are contexts of this process; a collective is a rendezvous of their host threads
+// around plain device-to-device copies (cudaMemcpyDefault: same device, peer or staged)
+// ------------------------------------------------------------------------------------------------
+struct dvp_local_group {
+    int world = 0, refs = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived = 0;
+    unsigned long long gen = 0;
+    const void *ptr[64] = {nullptr};
+    int status[64] = {0};
+    void barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        const unsigned long long g = gen;
+        if (++arrived == world) {
+            arrived = 0;
+            gen++;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return gen != g; });
+        }
+    }
+};
+
+static int local_all_gather(dvp_ctx *ctx, const void *send, void *recv, size_t bytes) {
+    dvp_local_group *g = ctx->local;
+    CKN(cudaStreamSynchronize(ctx->stream)); // my part is complete before anybody reads it
+    g->ptr[ctx->rank] = send;
+    g->barrier();
+    for (int r = 0; r < g->world; r++) {
+        void *dst = (char *)recv + (size_t)r * bytes;
+        if (dst != g->ptr[r]) CKN(cudaMemcpyAsync(dst, g->ptr[r], bytes, cudaMemcpyDefault, ctx->stream));
+    }
+    CKN(cudaStreamSynchronize(ctx->stream));
+    g->barrier(); // every rank has read: the send buffers may change again
+    return DVP_OK;
+}
+static int local_broadcast(dvp_ctx *ctx, void *buf, size_t bytes, int root) {
+    dvp_local_group *g = ctx->local;
+    CKN(cudaStreamSynchronize(ctx->stream));
+    g->ptr[ctx->rank] = buf;
+    g->barrier();
+    if (ctx->rank != root) CKN(cudaMemcpyAsync(buf, g->ptr[root], bytes, cudaMemcpyDefault, ctx->stream));
+    CKN(cudaStreamSynchronize(ctx->stream));
+    g->barrier();
+    return DVP_OK;
+}
+
 // all-gather `bytes` per rank (device buffers) on the context stream
 int comm_all_gather(dvp_ctx *ctx, const void *send, void *recv, size_t bytes) {
+    if (ctx->local) return local_all_gather(ctx, send, recv, bytes);
     NCK(g_nccl.AllGather(send, recv, bytes, ncclUint8, (ncclComm_t)ctx->comm, ctx->stream));
     return DVP_OK;
 }
 int comm_broadcast(dvp_ctx *ctx, void *buf, size_t bytes, int root) {
+    if (ctx->local) return local_broadcast(ctx, buf, bytes, root);
     NCK(g_nccl.Broadcast(buf, buf, bytes, ncclUint8, root, (ncclComm_t)ctx->comm, ctx->stream));
     return DVP_OK;
 }
-int comm_group(bool start) {
+// several collectives as one NCCL group (the in-process backend runs them one by one)
+int comm_group(dvp_ctx *ctx, bool start) {
+    if (ctx->local || ctx->world <= 1) return DVP_OK;
     NCK(start ? g_nccl.GroupStart() : g_nccl.GroupEnd());
+    return DVP_OK;
+}
+// The first non-zero status of any rank, on every rank: a rank-local failure (out of memory, a bad handle) must not
+// leave the peers waiting in the next collective.  Host-side for the in-process backend, an 4-byte all-gather otherwise.
+int comm_agree(dvp_ctx *ctx, int rc) {
+    if (ctx->world <= 1) return rc;
+    if (ctx->local) {
+        dvp_local_group *g = ctx->local;
+        g->status[ctx->rank] = rc;
+        g->barrier();
+        int all = 0;
+        for (int r = 0; r < g->world && !all; r++) all = g->status[r];
+        g->barrier();
+        return all;
+    }
+    int rc2;
+    const size_t W = (size_t)ctx->world;
+    if ((rc2 = ctx->commbuf.reserve(4096)) != 0) return rc ? rc : rc2; // sized in dvp_comm_init: cannot fail here
+    int *d = ctx->commbuf.as<int>() + 512;
+    int all[64];
+    CKN(cudaMemcpyAsync(d + W, &rc, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    NCK(g_nccl.AllGather(d + W, d, sizeof(int), ncclUint8, (ncclComm_t)ctx->comm, ctx->stream));
+    CKN(cudaMemcpyAsync(all, d, W * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CKN(cudaStreamSynchronize(ctx->stream));
+    for (size_t r = 0; r < W; r++)
+        if (all[r]) return all[r];
     return DVP_OK;
 }
 
@@ -136,6 +220,24 @@ int dvp_comm_init(dvp_ctx *ctx, const uint8_t id[128], int rank, int world) {
     ctx->comm = c;
     ctx->rank = rank;
     ctx->world = world;
+    return ctx->commbuf.reserve(4096); // the small exchanges (partial sums, status words) never allocate later
+}
+
+// `world` contexts of this process become ranks 0 .. world-1 of one group without NCCL.  Every rank must then be
+// driven by its own host thread (the collectives rendezvous); the contexts may share a device.
+int dvp_comm_init_local(dvp_ctx *const *ctxs, int world) {
+    if (!ctxs || world < 1 || world > 64) return DVP_ERR_BAD_ARG;
+    for (int r = 0; r < world; r++)
+        if (!ctxs[r] || ctxs[r]->comm || ctxs[r]->local) return DVP_ERR_BAD_ARG;
+    dvp_local_group *g = new dvp_local_group();
+    g->world = world;
+    g->refs = world;
+    for (int r = 0; r < world; r++) {
+        ctxs[r]->local = g;
+        ctxs[r]->rank = r;
+        ctxs[r]->world = world;
+        if (cudaSetDevice(ctxs[r]->device) != cudaSuccess || ctxs[r]->commbuf.reserve(4096)) return DVP_ERR_CUDA;
+    }
     return DVP_OK;
 }
 
@@ -145,6 +247,16 @@ int dvp_comm_destroy(dvp_ctx *ctx) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         g_nccl.CommDestroy((ncclComm_t)ctx->comm);
+    }
+    if (ctx->local) {
+        dvp_local_group *g = ctx->local;
+        bool last;
+        {
+            std::lock_guard<std::mutex> lk(g->mu);
+            last = --g->refs == 0;
+        }
+        if (last) delete g;
+        ctx->local = nullptr;
     }
     ctx->comm = nullptr;
     ctx->rank = 0;

@@ -3,6 +3,7 @@
 #include "../../include/dvpari.h"
 #include "msm.cuh"
 
+struct dvp_local_group;
 struct SrsSlot {
     dvp::DevBuf buf; // AffPt[n], decoded once (replaces read_point_vec_from_file per prove)
     size_t n = 0;
@@ -26,6 +27,7 @@ struct dvp_ctx {
     dvp::DevBuf bytes, small, scal, adhoc, commbuf;
     // multi-GPU: NCCL communicator (ncclComm_t) of this rank, see comm.cu
     void *comm = nullptr;
+    struct dvp_local_group *local = nullptr; // or: a group of contexts of this process (dvp_comm_init_local)
     int rank = 0, world = 1;
     int msm_table_windows = 0;             // 0: choose_table_windows(slot size)
     int msm_tables = 1;                    // 0: never, 1: when the slot is large enough and the memory is there
@@ -40,7 +42,8 @@ int slot_msm(dvp_ctx *ctx, int slot, size_t offset, const uint32_t *d_scalars, s
 // comm.cu
 int comm_all_gather(dvp_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);
 int comm_broadcast(dvp_ctx *ctx, void *buf, size_t bytes, int root);
-int comm_group(bool start);
+int comm_group(dvp_ctx *ctx, bool start);
+int comm_agree(dvp_ctx *ctx, int rc);
 int comm_fold_points(dvp_ctx *ctx, const dvp::AffPt &mine, dvp::AffPt *total);
 
 int ctx_decode_into(dvp_ctx *ctx, const uint8_t *pts30, size_t n, dvp::AffPt *d_out, int64_t *first_invalid);

@@ -1058,12 +1058,12 @@ static int r1cs_eval_device(dvp_r1cs *r, dvp_domain *d, const fr *d_w, fr *a, fr
     CKP(cudaGetLastError());
     if (W > 1) {
         const size_t chunk = (n / W) * sizeof(fr);
-        if ((rc = comm_group(true))) return rc;
+        if ((rc = comm_group(ctx, true))) return rc;
         fr *vs[4] = {a, b, c, iv};
         for (fr *v : vs)
             if ((rc = comm_all_gather(ctx, v + lo, v, chunk))) return rc;
         if ((rc = comm_all_gather(ctx, d_bad, d_bad + 8, 8))) return rc;
-        if ((rc = comm_group(false))) return rc;
+        if ((rc = comm_group(ctx, false))) return rc;
         unsigned long long all[64];
         CKP(cudaMemcpyAsync(all, d_bad + 8, 8 * W, cudaMemcpyDeviceToHost, st));
         CKP(cudaStreamSynchronize(st));
@@ -1332,10 +1332,10 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
         // independent polynomials: the owner extends, then every rank receives it
         for (int pl = 0; pl < 3; pl++)
             if (pl % W == R && (rc = extend_device(d, a2 + (size_t)pl * n, 1, n))) return rc;
-        if ((rc = comm_group(true))) return rc;
+        if ((rc = comm_group(ctx, true))) return rc;
         for (int pl = 0; pl < 3; pl++)
             if ((rc = comm_broadcast(ctx, a2 + (size_t)pl * n, n * sizeof(fr), pl % W))) return rc;
-        if ((rc = comm_group(false))) return rc;
+        if ((rc = comm_group(ctx, false))) return rc;
     }
     k_ivals_ext<<<cdivp(n, 128), 128, 0, st>>>(w, (uint32_t)k, d->leaves.as<fr>(), (uint32_t)n, i2);
     if (stages) {

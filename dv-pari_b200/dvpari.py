@@ -81,6 +81,7 @@ def lib():
         L.dvp_point_add.argtypes = [vp, vp, vp, vp]
         L.dvp_comm_unique_id.argtypes = [vp]
         L.dvp_comm_init.argtypes = [vp, vp, i32, i32]
+        L.dvp_comm_init_local.argtypes = [vp, i32]
         L.dvp_comm_destroy.argtypes = [vp]
         L.dvp_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
         L.dvp_shard_range.argtypes = [sz, i32, i32, C.POINTER(sz), C.POINTER(sz)]
@@ -319,6 +320,36 @@ def comm_unique_id():
     buf = np.zeros(128, dtype=np.uint8)
     _ck(lib().dvp_comm_unique_id(_ptr(buf)), "dvp_comm_unique_id")
     return buf.tobytes()
+
+
+def comm_init_local(contexts):
+    """Join contexts of THIS process (one device or several) as ranks 0..len-1 without NCCL.  Every rank must then be
+    driven by its own host thread: the collectives rendezvous (ctypes releases the GIL inside the calls)."""
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    _ck(lib().dvp_comm_init_local(C.cast(arr, C.c_void_p), len(contexts)), "dvp_comm_init_local")
+
+
+def run_ranks(fn, world):
+    """fn(rank) on one host thread per rank; returns the results in rank order, re-raises the first exception."""
+    import threading
+
+    out, err = [None] * world, [None] * world
+
+    def body(r):
+        try:
+            out[r] = fn(r)
+        except BaseException as e:  # noqa: BLE001 - handed to the caller
+            err[r] = e
+
+    ts = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return out
 
 
 def shard_range(total, rank, world):

@@ -112,6 +112,10 @@ int dvp_msm_last_profile(dvp_ctx *ctx, float ms[8], unsigned count[8]);
  */
 int dvp_comm_unique_id(uint8_t id[128]);
 int dvp_comm_init(dvp_ctx *ctx, const uint8_t id[128], int rank, int world);
+/* The same sharding without NCCL: `world` contexts of ONE process (on one device or several) become ranks
+ * 0 .. world-1; every rank must be driven by its own host thread, the exchanges are device-to-device copies behind a
+ * host rendezvous.  This is how the partition logic is checked on a single GPU. */
+int dvp_comm_init_local(dvp_ctx *const *ctxs, int world);
 int dvp_comm_destroy(dvp_ctx *ctx);
 int dvp_comm_info(dvp_ctx *ctx, int *rank, int *world);
 /* [lo, hi) of `total` items owned by `rank`: lo = floor(total * rank / world) */
