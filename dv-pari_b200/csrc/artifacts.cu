@@ -83,6 +83,32 @@ int dvp_sp1_public_input(uint64_t raw, uint64_t out_mont[4]) {
     return DVP_OK;
 }
 
+// blake3::hash and the Fiat-Shamir challenge of Transcript::output (proving.rs:137-197) as the prover computes them
+// (host code; exported so that the transcript can be checked without a device)
+int dvp_blake3(const uint8_t *data, size_t len, uint8_t out32[32]) {
+    if (!out32 || (!data && len)) return DVP_ERR_BAD_ARG;
+    host::Blake3Small::hash(data, len, out32);
+    return DVP_OK;
+}
+int dvp_transcript_alpha(const uint8_t commit_p30[30], const uint64_t *public_mont, size_t k, uint64_t alpha_mont[4]) {
+    if (!commit_p30 || !alpha_mont || (!public_mont && k)) return DVP_ERR_BAD_ARG;
+    std::vector<uint8_t> pub29(29 * k + 1);
+    for (size_t j = 0; j < k; j++) {
+        fr x;
+        memcpy(x.v, public_mont + 4 * j, 32);
+        uint32_t c[8];
+        fr_to_canonical(c, x);
+        for (int i = 0; i < 29; i++) pub29[29 * j + i] = (uint8_t)(c[i >> 2] >> (8 * (i & 3)));
+    }
+    uint8_t al[32];
+    if (!host::transcript_alpha(commit_p30, pub29.data(), k, al)) return DVP_ERR_INTERNAL;
+    uint32_t alc[8];
+    memcpy(alc, al, 32);
+    const fr a = fr_from_canonical(alc);
+    memcpy(alpha_mont, a.v, 32);
+    return DVP_OK;
+}
+
 // First pass over a dump: sizes.  Returns DVP_ERR_BAD_ARG if the buffer is truncated or inconsistent.
 int dvp_r1cs_dump_sizes(const uint8_t *buf, size_t len, size_t *ncoeffs, size_t *nrows, size_t nnz[3], size_t *max_wire) {
     if (!buf || !ncoeffs || !nrows || !nnz || !max_wire) return DVP_ERR_BAD_ARG;

@@ -256,6 +256,10 @@ int dvp_fr_to_le29(const uint64_t *in_mont, size_t n, uint8_t *out);            
 int dvp_fr_from_be32_mod_order(const uint8_t *in, size_t n, uint64_t *out_mont); /* Fr::from_be_bytes_mod_order */
 /* sp1_generate_scalar_from_raw_public_input (src/gnark_r1cs.rs:218-236) */
 int dvp_sp1_public_input(uint64_t raw, uint64_t out_mont[4]);
+/* blake3::hash (any length) and Transcript::output (src/proving.rs:137-197): alpha from commit_p and the k public
+ * inputs, exactly as dvp_prove / dvp_verify derive it.  Host code, no device needed. */
+int dvp_blake3(const uint8_t *data, size_t len, uint8_t out32[32]);
+int dvp_transcript_alpha(const uint8_t commit_p30[30], const uint64_t *public_mont, size_t k, uint64_t alpha_mont[4]);
 /* load_sparse_r1cs_from_file in two passes over the file image: sizes, then CSR per matrix + coefficient table */
 int dvp_r1cs_dump_sizes(const uint8_t *buf, size_t len, size_t *ncoeffs, size_t *nrows, size_t nnz[3], size_t *max_wire);
 int dvp_r1cs_dump_parse(const uint8_t *buf, size_t len, uint32_t *const rowptr[3], uint32_t *const wire[3],

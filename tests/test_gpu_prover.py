@@ -127,7 +127,7 @@ def test_toy_prove_is_bit_exact_and_verifies(ctx, oracle):
     assert len(dvpari.proof_to_bits(proof)) == 944
 
 
-@pytest.mark.parametrize("nrows,k", [(13, 2), (200, 3), (1000, 2)])
+@pytest.mark.parametrize("nrows,k", [(13, 2), (200, 3), (1000, 2), (300, 64)])  # k = 64: a two-chunk public-input hash
 def test_random_circuit_prove_is_bit_exact(ctx, oracle, nrows, k):
     O = oracle
     rnd = random.Random(500 + nrows)

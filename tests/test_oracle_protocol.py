@@ -19,11 +19,19 @@ def _b3(oracle, data):
 
 def test_blake3_matches_reference_implementation(oracle):
     rnd = random.Random(31)
-    for n in [0, 1, 29, 30, 58, 63, 64, 65, 127, 128, 129, 1000, 1024]:
+    import dvpari
+
+    L = dvpari.lib()
+    L.dvp_blake3.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
+    # one block, one chunk, chunk boundaries, every tree shape up to 9 chunks, 29 * 64 bytes (64 public inputs)
+    sizes = [0, 1, 29, 30, 58, 63, 64, 65, 127, 128, 129, 1000, 1023, 1024, 1025, 29 * 64, 2047, 2048, 2049, 3072, 3073,
+             4096, 4097, 5000, 6144, 7168, 8192, 8193, 9000, 31 * 1024 + 5]
+    for n in sizes:
         data = bytes(rnd.getrandbits(8) for _ in range(n))
-        assert _b3(oracle, data) == pyblake3.blake3(data).digest()
-    out = (C.c_uint8 * 32)()
-    assert oracle.lib().blake3_hash_small(bytes(1025), 1025, out) == -1
+        want = pyblake3.blake3(data).digest()
+        assert _b3(oracle, data) == want, n
+        out = (C.c_uint8 * 32)()
+        assert L.dvp_blake3(data, n, out) == 0 and bytes(out) == want, n  # the product's own (independent) BLAKE3
 
 
 def test_public_input_hash_kat(oracle):
@@ -48,6 +56,31 @@ def test_transcript_alpha(oracle):
     root = bytearray(pyblake3.blake3(ct + rt).digest())
     root[28:] = b"\0\0\0\0"
     assert oracle.transcript_alpha(commit, pub) == int.from_bytes(root, "little")
+
+
+def test_transcript_alpha_many_public_inputs(oracle):
+    """k = 64 public inputs hash 1856 bytes (two chunks): the reference has no limit (proving.rs:149-161); product
+    (dvp_transcript_alpha) and oracle against the Python blake3 package."""
+    import dvpari
+
+    rnd = random.Random(33)
+    L = dvpari.lib()
+    L.dvp_transcript_alpha.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    for k in (0, 1, 35, 36, 64, 200):
+        commit = bytes(rnd.getrandbits(8) for _ in range(30))
+        pub = [rnd.randrange(P) for _ in range(k)]
+        e = pyblake3.blake3(b"").digest()
+        ct = pyblake3.blake3(e + e).digest()
+        hp = pyblake3.blake3(b"".join(x.to_bytes(29, "little") for x in pub)).digest()
+        rt = pyblake3.blake3(pyblake3.blake3(commit).digest() + hp).digest()
+        root = bytearray(pyblake3.blake3(ct + rt).digest())
+        root[28:] = b"\0\0\0\0"
+        want = int.from_bytes(root, "little")
+        assert oracle.transcript_alpha(commit, pub) == want, k
+        pm = dvpari.fr_to_mont(pub)
+        out = np.zeros(4, dtype=np.uint64)
+        assert L.dvp_transcript_alpha(commit, pm.ctypes.data if k else None, k, out.ctypes.data) == 0
+        assert dvpari.fr_from_mont(out)[0] == want, k
 
 
 def test_toy_r1cs_rows(oracle):
