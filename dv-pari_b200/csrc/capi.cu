@@ -304,6 +304,16 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
         ctx->msm.b64_min = value > 0 ? (size_t)value : ((size_t)1 << 23);
         return DVP_OK;
     }
+    if (!strcmp(name, "binv_coop_warps")) {
+        if (value < 1) return DVP_ERR_BAD_ARG;
+        ctx->msm.binv_coop_warps = (uint32_t)value;
+        return DVP_OK;
+    }
+    if (!strcmp(name, "round_warp_max")) {
+        if (value < 0) return DVP_ERR_BAD_ARG;
+        ctx->msm.round_warp_max = (size_t)value;
+        return DVP_OK;
+    }
     if (!strcmp(name, "binv_direct")) {
         if (value < 64 || value > (1 << 20)) return DVP_ERR_BAD_ARG;
         ctx->msm.binv_direct = (uint32_t)value;
@@ -521,6 +531,21 @@ int dvp_msm_last_profile(dvp_ctx *ctx, float ms[8], unsigned count[8]) {
     return DVP_OK;
 }
 
+/* development: (lane, category, start ms, end ms) of every launch bracket of the last profiled MSM */
+int dvp_msm_last_timeline(dvp_ctx *ctx, float *rows4, size_t cap_rows, size_t *count) {
+    if (!ctx || !count) return DVP_ERR_BAD_ARG;
+    const auto &t = ctx->msm.timeline;
+    *count = t.size();
+    if (rows4)
+        for (size_t i = 0; i < t.size() && i < cap_rows; i++) {
+            rows4[4 * i] = t[i].lane;
+            rows4[4 * i + 1] = t[i].cat;
+            rows4[4 * i + 2] = t[i].t0;
+            rows4[4 * i + 3] = t[i].t1;
+        }
+    return DVP_OK;
+}
+
 int dvp_point_add(dvp_ctx *ctx, const uint8_t a30[30], const uint8_t b30[30], uint8_t out30[30]) {
     if (!ctx || !a30 || !b30 || !out30) return DVP_ERR_BAD_ARG;
     CKC(cudaSetDevice(ctx->device));
@@ -571,8 +596,8 @@ int dvp_dev_download(dvp_ctx *ctx, void *host, const void *dptr, size_t bytes) {
 }
 
 int dvp_selftest_op(dvp_ctx *ctx, int op, const void *a, const void *b, void *out, size_t n) {
-    if (!ctx || !a || !out || op < 0 || op > 5) return DVP_ERR_BAD_ARG;
-    if ((op == 0 || op == 3 || op == 5) && !b) return DVP_ERR_BAD_ARG;
+    if (!ctx || !a || !out || op < 0 || op > 7) return DVP_ERR_BAD_ARG; // 6, 7: warp-cooperative gf_mul / inverse
+    if ((op == 0 || op == 3 || op == 5 || op == 6) && !b) return DVP_ERR_BAD_ARG;
     if (!n) return DVP_OK;
     CKC(cudaSetDevice(ctx->device));
     const size_t esz = op == 5 ? 64 : 32;
@@ -582,8 +607,13 @@ int dvp_selftest_op(dvp_ctx *ctx, int op, const void *a, const void *b, void *ou
     CKC(cudaMalloc(&dout, n * esz));
     CKC(cudaMemcpyAsync(da, a, n * esz, cudaMemcpyHostToDevice, ctx->stream));
     if (b) CKC(cudaMemcpyAsync(db, b, n * esz, cudaMemcpyHostToDevice, ctx->stream));
-    k_selftest<<<cdivu(n, 128), 128, 0, ctx->stream>>>(op, (const uint32_t *)da, b ? (const uint32_t *)db : nullptr,
-                                                      (uint32_t *)dout, n);
+    if (op >= 6) {
+        int rcw = selftest_warp(ctx->msm, op - 6, da, db, dout, n);
+        if (rcw) return rcw;
+    } else {
+        k_selftest<<<cdivu(n, 128), 128, 0, ctx->stream>>>(op, (const uint32_t *)da, b ? (const uint32_t *)db : nullptr,
+                                                          (uint32_t *)dout, n);
+    }
     CKC(cudaGetLastError());
     CKC(cudaMemcpyAsync(out, dout, n * esz, cudaMemcpyDeviceToHost, ctx->stream));
     CKC(cudaStreamSynchronize(ctx->stream));
@@ -594,7 +624,7 @@ int dvp_selftest_op(dvp_ctx *ctx, int op, const void *a, const void *b, void *ou
 }
 
 int dvp_latency_probe(dvp_ctx *ctx, int mode, int iters, float *us_per_op) {
-    if (!ctx || !us_per_op || mode < 0 || mode > 2 || iters <= 0) return DVP_ERR_BAD_ARG;
+    if (!ctx || !us_per_op || mode < 0 || mode > 4 || iters <= 0) return DVP_ERR_BAD_ARG;
     CKC(cudaSetDevice(ctx->device));
     return latency_probe(ctx->msm, mode, iters, us_per_op);
 }

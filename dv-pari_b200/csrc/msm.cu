@@ -26,6 +26,7 @@
 #include "../../include/dvpari.h"
 #include "fr.cuh"
 #include "host_gf.hpp"
+#include "gf233_warp.cuh"
 #include "k233_ld.cuh"
 
 namespace dvp {
@@ -298,15 +299,24 @@ __device__ __forceinline__ AffPt fetch_pt(const AffPt *__restrict__ src, const u
 // ------------------------------------------------------------------------------------------------
 constexpr int PLAN_THREADS = 256;
 
+// info[3] is a ticket counter (cleared with info): a block's position in the scan is the order in which it STARTED,
+// so the blocks it waits for are running or finished whatever order the hardware dispatches them in (decoupled
+// look-back; no assumption of ascending dispatch or of a co-resident grid).
+// The plan also carries the last point of every odd segment over to the next round (dst != nullptr).
+template <bool INDEXED>
 __global__ void __launch_bounds__(PLAN_THREADS)
     k_plan(const uint32_t *__restrict__ len, const uint32_t *__restrict__ in_start, const uint32_t *__restrict__ ent,
            uint32_t nseg, uint32_t items, uint64_t *__restrict__ blk_sum, uint32_t *__restrict__ blk_flag, uint32_t epoch,
            uint32_t *__restrict__ out_start, uint32_t *__restrict__ new_len, uint4 *__restrict__ desc,
-           uint32_t *__restrict__ info) {
+           uint32_t *__restrict__ info, const AffPt *__restrict__ src, AffPt *__restrict__ dst) {
     __shared__ uint64_t sh[PLAN_THREADS / 32];
     __shared__ uint64_t sh_base;
+    __shared__ uint32_t sh_vb;
+    if (threadIdx.x == 0) sh_vb = atomicAdd(&info[3], 1u);
+    __syncthreads();
+    const uint32_t vb = sh_vb; // virtual block id
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t base = (blockIdx.x * PLAN_THREADS + threadIdx.x) * items;
+    const uint32_t base = (vb * PLAN_THREADS + threadIdx.x) * items;
     // phase 1: aggregate of this block
     uint64_t s = 0;
     uint32_t mx = 0;
@@ -334,13 +344,13 @@ __global__ void __launch_bounds__(PLAN_THREADS)
         }
         if (lane < PLAN_THREADS / 32) sh[lane] = wi - w; // exclusive offsets of the warps
         if (lane == PLAN_THREADS / 32 - 1) {
-            blk_sum[blockIdx.x] = wi; // block aggregate
+            blk_sum[vb] = wi; // block aggregate
             __threadfence();
-            atomicExch(&blk_flag[blockIdx.x], epoch);
+            atomicExch(&blk_flag[vb], epoch);
         }
-        // phase 2: sum of the predecessors' aggregates
+        // phase 2: sum of the aggregates of the blocks that started earlier
         uint64_t p = 0;
-        for (uint32_t b = lane; b < blockIdx.x; b += 32) {
+        for (uint32_t b = lane; b < vb; b += 32) {
             while (atomicAdd(&blk_flag[b], 0u) != epoch) __nanosleep(20);
             __threadfence();
             p += *reinterpret_cast<volatile uint64_t *>(&blk_sum[b]);
@@ -359,6 +369,7 @@ __global__ void __launch_bounds__(PLAN_THREADS)
             in = in_start[idx];
             out_start[idx] = (uint32_t)(run >> 32);
             new_len[idx] = (L + 1) >> 1;
+            if (dst && (L & 1)) pt_store(&dst[(uint32_t)(run >> 32) + (L >> 1)], fetch_pt<INDEXED>(src, ent, in + L - 1));
         }
         const uint32_t nt = L >> 1, ts = (uint32_t)run, os = (uint32_t)(run >> 32);
         // descriptors, written by the whole warp for one segment at a time
@@ -370,7 +381,7 @@ __global__ void __launch_bounds__(PLAN_THREADS)
             const uint32_t in_b = __shfl_sync(0xffffffffu, in, src_lane), os_b = __shfl_sync(0xffffffffu, os, src_lane);
             for (uint32_t j = lane; j < nt_b; j += 32) {
                 uint32_t a = in_b + 2 * j, b = a + 1;
-                if (ent) {
+                if (INDEXED) {
                     a = ent[a];
                     b = ent[b];
                 }
@@ -379,122 +390,17 @@ __global__ void __launch_bounds__(PLAN_THREADS)
         }
         run += (uint64_t)(L >> 1) | ((uint64_t)((L + 1) >> 1) << 32);
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == PLAN_THREADS - 1) {
+    if (vb == gridDim.x - 1 && threadIdx.x == PLAN_THREADS - 1) {
         out_start[nseg] = (uint32_t)(run >> 32);
         info[1] = (uint32_t)run;
         info[2] = (uint32_t)(run >> 32);
     }
 }
 
-// pass 1: per task form the denominator and chain a per-thread prefix product
-template <int B>
-__global__ void __launch_bounds__(256)
-    k_pass1(const AffPt *__restrict__ src, const uint32_t *__restrict__ info, const uint4 *__restrict__ desc,
-            gf *__restrict__ prefix, gf *__restrict__ thr_total) {
-    const uint32_t ntasks = info[1];
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lane = gtid & 31, warp = gtid >> 5;
-    const uint32_t base = warp * (32u * B);
-    if (base >= ntasks) return;
-    gf acc = gf_one();
-    // the next task's descriptor and x coordinates are in flight while the current product is computed
-    uint32_t t = base + lane;
-    uint4 de = make_uint4(0, 0, 0, 0);
-    gf x1 = gf_zero(), x2 = gf_zero();
-    if (t < ntasks) {
-        de = desc[t];
-        x1 = gf_load(&src[de.x & 0x7fffffffu].x);
-        x2 = gf_load(&src[de.y & 0x7fffffffu].x);
-    }
-#pragma unroll 1
-    for (int k = 0; k < B; k++) {
-        if (t >= ntasks) break;
-        const uint32_t tn = t + 32;
-        uint4 den = make_uint4(0, 0, 0, 0);
-        gf x1n = gf_zero(), x2n = gf_zero();
-        if (k + 1 < B && tn < ntasks) {
-            den = desc[tn];
-            x1n = gf_load(&src[den.x & 0x7fffffffu].x);
-            x2n = gf_load(&src[den.y & 0x7fffffffu].x);
-        }
-        gf d = gf_add(x1, x2);
-        if (gf_is_zero(x1) | gf_is_zero(x2)) d = gf_one();
-        else if (gf_is_zero(d)) {
-            const AffPt p1 = fetch_entry(src, de.x), p2 = fetch_entry(src, de.y);
-            d = gf_eq(p1.y, p2.y) ? x1 : gf_one();
-        }
-        gf_store(&prefix[t], acc);
-        acc = gf_mul(acc, d);
-        t = tn;
-        de = den;
-        x1 = x1n;
-        x2 = x2n;
-    }
-    gf_store(&thr_total[gtid], acc);
-}
-
 // One shared copy of the 1.2k-instruction multiplier for the pass-2 loop: four inlined copies are 86 KB
 // of code (I-cache misses were 10 % of the stalls) and push the kernel to 255 registers; called out of
 // line the loop fits 128 registers, i.e. twice the resident warps.
 __device__ __noinline__ gf gf_mul_call(const gf a, const gf b) { return gf_mul(a, b); }
-
-// pass 2: walk the same tasks backwards with the inverse of the thread total, finish the additions
-template <int B, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-    k_pass2(const AffPt *__restrict__ src, const uint32_t *__restrict__ info, const uint4 *__restrict__ desc,
-            const gf *__restrict__ prefix, const gf *__restrict__ thr_inv, AffPt *__restrict__ dst) {
-    const uint32_t ntasks = info[1];
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lane = gtid & 31, warp = gtid >> 5;
-    const uint32_t base = warp * (32u * B);
-    if (base + lane >= ntasks) return;
-    gf inv = gf_load(&thr_inv[gtid]);
-#pragma unroll 1
-    for (int k = B - 1; k >= 0; k--) {
-        const uint32_t t = base + k * 32 + lane;
-        if (t >= ntasks) continue;
-        const uint4 de = desc[t];
-        const AffPt p1 = fetch_entry(src, de.x), p2 = fetch_entry(src, de.y);
-        gf d;
-        const int kind = pair_classify(p1, p2, d);
-        const gf dinv = gf_mul_call(inv, gf_load(&prefix[t]));
-        if (k) inv = gf_mul_call(inv, d);
-        AffPt r;
-        if (kind >= 2) {
-            r = pair_finish(p1, p2, kind, dinv);
-        } else {
-            // chord / tangent: lambda = num/d (+ x1 for the tangent), see pair_finish
-            gf lam = gf_mul_call(kind == 1 ? p1.y : gf_add(p1.y, p2.y), dinv);
-            if (kind == 1) lam = gf_add(lam, p1.x);
-            r.x = gf_add(gf_add(gf_sqr(lam), lam), gf_add(p1.x, p2.x));
-            r.y = gf_add(gf_add(gf_mul_call(lam, gf_add(p1.x, r.x)), r.x), p1.y);
-        }
-        pt_store(&dst[de.z], r);
-    }
-}
-
-// segments of odd length carry their last element to the next round
-template <bool INDEXED>
-__global__ void k_copy_odd(const AffPt *__restrict__ src, const uint32_t *__restrict__ ent,
-                           const uint32_t *__restrict__ in_start, const uint32_t *__restrict__ len,
-                           const uint32_t *__restrict__ out_start, uint32_t nseg, AffPt *__restrict__ dst) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nseg) return;
-    const uint32_t L = len[s];
-    if (L & 1) pt_store(&dst[out_start[s] + (L >> 1)], fetch_pt<INDEXED>(src, ent, in_start[s] + L - 1));
-}
-
-// after the last round every segment holds 0 or 1 points
-template <bool INDEXED>
-__global__ void k_finalize(const AffPt *__restrict__ src, const uint32_t *__restrict__ ent,
-                           const uint32_t *__restrict__ in_start, const uint32_t *__restrict__ len, uint32_t nseg,
-                           AffPt *__restrict__ dst) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nseg) return;
-    AffPt p = pt_inf();
-    if (len[s]) p = fetch_pt<INDEXED>(src, ent, in_start[s]);
-    pt_store(&dst[s], p);
-}
 
 // ------------------------------------------------------------------------------------------------
 // table-driven inversion: x -> x^(2^k) is GF(2)-linear, so for k in {7,14,29,58,116} it is 30 byte-indexed
@@ -558,20 +464,167 @@ __device__ __noinline__ gf gf_inv_tab(const gf &a, const gf *__restrict__ tabs) 
     return gf_sqr(b232);
 }
 
-// single-warp latency probe: iters dependent inversions (mode 0 Itoh-Tsujii by squarings, 1 table-driven, 2 gf_mul)
+// the same inversion shared by the 32 lanes of a warp (gf233_warp.cuh): ~6 us instead of 46
+__device__ __forceinline__ gf gf_inv_tab_warp(const gf &a, const gf *__restrict__ tabs, const WarpMulCtx &c) {
+    return gf_inv_warp(a, tabs, MSQ_TABLE_ELEMS, c);
+}
+
+// A tree round small enough to be pure latency: one WARP per addition, no batching -- the warp inverts its own
+// denominator cooperatively and finishes the addition with cooperative multiplications (one launch, ~10 us).
+__global__ void __launch_bounds__(128)
+    k_round_warp(const AffPt *__restrict__ src, const uint32_t *__restrict__ info, const uint4 *__restrict__ desc,
+                 AffPt *__restrict__ dst, const gf *__restrict__ tabs) {
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= info[1]) return; // whole warp
+    const WarpMulCtx c = warp_mul_ctx();
+    const uint4 de = desc[t];
+    const AffPt p1 = fetch_entry(src, de.x), p2 = fetch_entry(src, de.y);
+    gf d;
+    const int kind = pair_classify(p1, p2, d); // warp-uniform: every lane holds the same points
+    AffPt r;
+    if (kind >= 2) {
+        r = pair_finish(p1, p2, kind, d);
+    } else {
+        const gf dinv = gf_inv_tab_warp(d, tabs, c);
+        gf lam = gf_mul_warp(kind == 1 ? p1.y : gf_add(p1.y, p2.y), dinv, c);
+        if (kind == 1) lam = gf_add(lam, p1.x);
+        r.x = gf_add(gf_add(gf_sqr(lam), lam), gf_add(p1.x, p2.x));
+        r.y = gf_add(gf_add(gf_mul_warp(lam, gf_add(p1.x, r.x), c), r.x), p1.y);
+    }
+    if ((threadIdx.x & 31) == 0) pt_store(&dst[de.z], r);
+}
+
+// pass 1: per task form the denominator and chain a per-thread prefix product
+template <int B>
+__global__ void __launch_bounds__(256)
+    k_pass1(const AffPt *__restrict__ src, const uint32_t *__restrict__ info, const uint4 *__restrict__ desc,
+            gf *__restrict__ prefix, gf *__restrict__ thr_total) {
+    const uint32_t ntasks = info[1];
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = gtid & 31, warp = gtid >> 5;
+    const uint32_t base = warp * (32u * B);
+    if (base >= ntasks) return;
+    gf acc = gf_one();
+    // the next task's descriptor and x coordinates are in flight while the current product is computed
+    uint32_t t = base + lane;
+    uint4 de = make_uint4(0, 0, 0, 0);
+    gf x1 = gf_zero(), x2 = gf_zero();
+    if (t < ntasks) {
+        de = desc[t];
+        x1 = gf_load(&src[de.x & 0x7fffffffu].x);
+        x2 = gf_load(&src[de.y & 0x7fffffffu].x);
+    }
+#pragma unroll 1
+    for (int k = 0; k < B; k++) {
+        if (t >= ntasks) break;
+        const uint32_t tn = t + 32;
+        uint4 den = make_uint4(0, 0, 0, 0);
+        gf x1n = gf_zero(), x2n = gf_zero();
+        if (k + 1 < B && tn < ntasks) {
+            den = desc[tn];
+            x1n = gf_load(&src[den.x & 0x7fffffffu].x);
+            x2n = gf_load(&src[den.y & 0x7fffffffu].x);
+        }
+        gf d = gf_add(x1, x2);
+        if (gf_is_zero(x1) | gf_is_zero(x2)) d = gf_one();
+        else if (gf_is_zero(d)) {
+            const AffPt p1 = fetch_entry(src, de.x), p2 = fetch_entry(src, de.y);
+            d = gf_eq(p1.y, p2.y) ? x1 : gf_one();
+        }
+        gf_store(&prefix[t], acc);
+        acc = gf_mul(acc, d);
+        t = tn;
+        de = den;
+        x1 = x1n;
+        x2 = x2n;
+    }
+    gf_store(&thr_total[gtid], acc);
+}
+
+// pass 2: walk the same tasks backwards with the inverse of the thread total, finish the additions
+template <int B, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+    k_pass2(const AffPt *__restrict__ src, const uint32_t *__restrict__ info, const uint4 *__restrict__ desc,
+            const gf *__restrict__ prefix, const gf *__restrict__ thr_inv, AffPt *__restrict__ dst) {
+    const uint32_t ntasks = info[1];
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = gtid & 31, warp = gtid >> 5;
+    const uint32_t base = warp * (32u * B);
+    if (base + lane >= ntasks) return;
+    gf inv = gf_load(&thr_inv[gtid]);
+#pragma unroll 1
+    for (int k = B - 1; k >= 0; k--) {
+        const uint32_t t = base + k * 32 + lane;
+        if (t >= ntasks) continue;
+        const uint4 de = desc[t];
+        const AffPt p1 = fetch_entry(src, de.x), p2 = fetch_entry(src, de.y);
+        gf d;
+        const int kind = pair_classify(p1, p2, d);
+        const gf dinv = gf_mul_call(inv, gf_load(&prefix[t]));
+        if (k) inv = gf_mul_call(inv, d);
+        AffPt r;
+        if (kind >= 2) {
+            r = pair_finish(p1, p2, kind, dinv);
+        } else {
+            // chord / tangent: lambda = num/d (+ x1 for the tangent), see pair_finish
+            gf lam = gf_mul_call(kind == 1 ? p1.y : gf_add(p1.y, p2.y), dinv);
+            if (kind == 1) lam = gf_add(lam, p1.x);
+            r.x = gf_add(gf_add(gf_sqr(lam), lam), gf_add(p1.x, p2.x));
+            r.y = gf_add(gf_add(gf_mul_call(lam, gf_add(p1.x, r.x)), r.x), p1.y);
+        }
+        pt_store(&dst[de.z], r);
+    }
+}
+
+// after the last round every segment holds 0 or 1 points
+template <bool INDEXED>
+__global__ void k_finalize(const AffPt *__restrict__ src, const uint32_t *__restrict__ ent,
+                           const uint32_t *__restrict__ in_start, const uint32_t *__restrict__ len, uint32_t nseg,
+                           AffPt *__restrict__ dst) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    AffPt p = pt_inf();
+    if (len[s]) p = fetch_pt<INDEXED>(src, ent, in_start[s]);
+    pt_store(&dst[s], p);
+}
+
+// single-warp latency probe: iters dependent operations (mode 0 Itoh-Tsujii by squarings, 1 table-driven, 2 gf_mul,
+// 3 warp-cooperative gf_mul, 4 warp-cooperative table-driven inversion)
 __global__ void k_latency_probe(int mode, int iters, const gf *__restrict__ tabs, uint32_t *__restrict__ sink) {
     gf a;
-    for (int k = 0; k < 8; k++) a.v[k] = threadIdx.x * 2654435761u + k * 40503u + 1;
+    // modes 3, 4 are the warp-cooperative forms: their operands are warp-uniform
+    const uint32_t seed = mode >= 3 ? 7u : threadIdx.x;
+    for (int k = 0; k < 8; k++) a.v[k] = seed * 2654435761u + k * 40503u + 1;
     a.v[7] &= 0x1ff;
     gf b = a;
+    const WarpMulCtx wc = warp_mul_ctx();
     for (int i = 0; i < iters; i++) {
         if (mode == 0) a = gf_inv(a);
         else if (mode == 1) a = gf_inv_tab(a, tabs);
-        else a = gf_mul(a, b);
+        else if (mode == 2) a = gf_mul(a, b);
+        else if (mode == 3) a = gf_mul_warp(a, b, wc);
+        else a = gf_inv_tab_warp(a, tabs, wc);
     }
     uint32_t s = 0;
     for (int k = 0; k < 8; k++) s ^= a.v[k];
     if (s == 0x12345678u) sink[0] = s;
+}
+
+// self-test of the warp-cooperative primitives: one warp per element; op 0 a*b, 1 1/a
+__global__ void k_selftest_warp(int op, const gf *__restrict__ a, const gf *__restrict__ b, gf *__restrict__ out, uint32_t n,
+                                const gf *__restrict__ tabs) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const WarpMulCtx c = warp_mul_ctx();
+    const gf x = gf_load(&a[i]);
+    const gf r = op == 0 ? gf_mul_warp(x, gf_load(&b[i]), c) : gf_inv_tab_warp(x, tabs, c);
+    if ((threadIdx.x & 31) == 0) gf_store(&out[i], r);
+}
+int selftest_warp(MsmEngine &E, int op, const void *d_a, const void *d_b, void *d_out, size_t n) {
+    k_selftest_warp<<<cdiv(n, 4), 128, 0, E.stream>>>(op, (const gf *)d_a, (const gf *)d_b, (gf *)d_out, (uint32_t)n,
+                                                      E.msqr_tabs.as<gf>());
+    CK(cudaGetLastError());
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -585,12 +638,43 @@ __device__ __forceinline__ uint32_t binv_count(const uint32_t *__restrict__ info
     n = (n + div1 - 1) / div1;
     return (n + div2 - 1) / div2;
 }
-__global__ void k_binv_direct(const gf *__restrict__ in, gf *__restrict__ out, const uint32_t *__restrict__ info,
-                              uint32_t unit, uint32_t div1, uint32_t div2, const gf *__restrict__ tabs) {
+// Batched inversion in ONE launch: a warp owns G <= 32 consecutive elements and does the whole Montgomery trick on them
+// cooperatively (gf233_warp.cuh) -- prefix products, the inverse of its total, the walk back.  Lane j keeps element j,
+// prefix j and result j (the operands of a cooperative product are warp-uniform, so they are broadcast by shuffles).
+// 3 cooperative products per element and one cooperative inversion per warp: (3 G - 1) 0.36 us + 6.7 us of latency
+// whatever the batch size, against ~70 us per level of the thread-per-group kernels below.
+__device__ __forceinline__ gf gf_bcast(const gf &v, int src_lane) {
+    gf r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.v[k] = __shfl_sync(0xffffffffu, v.v[k], src_lane);
+    return r;
+}
+__global__ void __launch_bounds__(128)
+    k_binv_coop(const gf *__restrict__ in, gf *__restrict__ out, const uint32_t *__restrict__ info, uint32_t unit,
+                uint32_t div1, uint32_t div2, uint32_t G, const gf *__restrict__ tabs) {
     const uint32_t n = binv_count(info, unit, div1, div2);
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    gf_store(&out[i], gf_inv_tab(gf_load(&in[i]), tabs));
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t lo = w * G;
+    if (lo >= n) return; // whole warp
+    const int cnt = (int)min(G, n - lo);
+    const WarpMulCtx c = warp_mul_ctx();
+    gf mine = gf_one(), mypre = gf_one(), myout = gf_zero();
+    if ((int)lane < cnt) mine = gf_load(&in[lo + lane]);
+    gf acc = gf_bcast(mine, 0);
+#pragma unroll 1
+    for (int j = 1; j < cnt; j++) {
+        if ((int)lane == j) mypre = acc;
+        acc = gf_mul_warp(acc, gf_bcast(mine, j), c);
+    }
+    gf inv = gf_inv_tab_warp(acc, tabs, c);
+#pragma unroll 1
+    for (int j = cnt - 1; j > 0; j--) {
+        const gf o = gf_mul_warp(inv, gf_bcast(mypre, j), c);
+        if ((int)lane == j) myout = o;
+        inv = gf_mul_warp(inv, gf_bcast(mine, j), c);
+    }
+    if (lane == 0) myout = inv;
+    if ((int)lane < cnt) gf_store(&out[lo + lane], myout);
 }
 __global__ void k_binv_up(const gf *__restrict__ in, const uint32_t *__restrict__ info, uint32_t unit, uint32_t div1,
                           uint32_t div2, uint32_t G, gf *__restrict__ pre, gf *__restrict__ tot) {
@@ -758,17 +842,18 @@ __global__ void __launch_bounds__(256)
         if (act) ld_store(&sh[t], acc);
         __syncthreads();
     }
-    if (t == 0) {
+    if (t < 32) { // warp 0 (the block has at least 32 threads): the conversion to affine is shared by its lanes
         const LdPt r = len ? ld_load(&sh[0]) : ld_infinity();
         if (OUT_AFFINE) {
             AffPt o = pt_inf();
-            if (!gf_is_zero(r.Z)) {
-                const gf zi = gf_inv_tab(r.Z, tabs);
-                o.x = gf_mul_call(r.X, zi);
-                o.y = gf_mul_call(r.Y, gf_sqr(zi));
+            if (!gf_is_zero(r.Z)) { // warp-uniform
+                const WarpMulCtx c = warp_mul_ctx();
+                const gf zi = gf_inv_tab_warp(r.Z, tabs, c);
+                o.x = gf_mul_warp(r.X, zi, c);
+                o.y = gf_mul_warp(r.Y, gf_sqr(zi), c);
             }
-            pt_store(reinterpret_cast<AffPt *>(dst) + s, o);
-        } else {
+            if (t == 0) pt_store(reinterpret_cast<AffPt *>(dst) + s, o);
+        } else if (t == 0) {
             ld_store(reinterpret_cast<LdPt *>(dst) + s, r);
         }
     }
@@ -777,13 +862,17 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
-int MsmLane::init() {
+int MsmLane::init(int index) {
     // high priority: when an MSM overlaps throughput-bound work on another stream (dvp_prove runs the g_m MSM beside the
     // extends), its short latency-bound kernels must not queue behind that work's blocks
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     CK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
-    CK(cudaStreamCreateWithPriority(&stream_lo, cudaStreamNonBlocking, prio_lo));
+    // The large pass kernels of lane i outrank those of lane i+1: the lanes then run staggered instead of in lock
+    // step -- lane 0's large rounds take the SMs first, lane 1 fills the gaps of lane 0's inversion chains and is still
+    // in its large rounds when lane 0 reaches its latency-bound small rounds (lower number = higher priority)
+    const int prio_big = std::min(prio_lo, std::max(prio_hi + 1, prio_lo - 3 + index));
+    CK(cudaStreamCreateWithPriority(&stream_lo, cudaStreamNonBlocking, prio_big));
     CK(cudaEventCreateWithFlags(&ev_sw[0], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_sw[1], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
@@ -881,39 +970,48 @@ struct Tree {
         if (E.profile) L.prof_end();
     }
 
-    // one launch: scans, next segment tables, descriptors; zeroes nothing itself (info is cleared here)
+    // one launch: scans, next segment tables, descriptors, and the last point of every odd segment of `src` carried
+    // over to `dst` (the round's output list); info (incl. the ticket counter) is cleared here
     int plan(const uint32_t *len, const uint32_t *in_start, const uint32_t *ent, uint32_t nseg, uint32_t *out_start,
-             uint32_t *new_len) {
+             uint32_t *new_len, const AffPt *src, AffPt *dst) {
         uint32_t items = 1;
         while (cdiv(nseg, items * PLAN_THREADS) > PLAN_MAX_BLOCKS) items++;
         const uint32_t nblk = cdiv(nseg, items * PLAN_THREADS);
         pb(PC_PLAN);
         CK(cudaMemsetAsync(L.info.p, 0, 16, st));
-        k_plan<<<nblk, PLAN_THREADS, 0, st>>>(len, in_start, ent, nseg, items, L.blk.as<uint64_t>(),
-                                              L.blk_flag.as<uint32_t>(), ++L.epoch, out_start, new_len,
-                                              L.desc.as<uint4>(), L.info.as<uint32_t>());
+        if (ent)
+            k_plan<true><<<nblk, PLAN_THREADS, 0, st>>>(len, in_start, ent, nseg, items, L.blk.as<uint64_t>(),
+                                                        L.blk_flag.as<uint32_t>(), ++L.epoch, out_start, new_len,
+                                                        L.desc.as<uint4>(), L.info.as<uint32_t>(), src, dst);
+        else
+            k_plan<false><<<nblk, PLAN_THREADS, 0, st>>>(len, in_start, nullptr, nseg, items, L.blk.as<uint64_t>(),
+                                                         L.blk_flag.as<uint32_t>(), ++L.epoch, out_start, new_len,
+                                                         L.desc.as<uint4>(), L.info.as<uint32_t>(), src, dst);
         pe();
         L.launches++;
         CK(cudaGetLastError());
         return 0;
     }
 
-    // inverses of the pass-1 thread totals; n_ub bounds their number, the live count is read on the device
+    // inverses of the pass-1 thread totals; n_ub bounds their number, the live count is read on the device.
+    // Up to binv_coop_max elements: one cooperative launch (k_binv_coop).  More: one or two thread-per-group levels
+    // (throughput-bound at that size) bring the batch down to that size first.
     int batch_inv(const gf *in, gf *out, uint32_t n_ub, uint32_t unit, uint32_t div1, uint32_t div2, int depth) {
         const uint32_t *info = L.info.as<uint32_t>();
-        const uint32_t BINV_DIRECT = E.binv_direct; // at or below this many elements every thread inverts its own
-        if (n_ub <= BINV_DIRECT || depth >= 2) {
+        const uint32_t COOP_MAX = E.binv_direct;
+        if (n_ub <= COOP_MAX || depth >= 2) {
+            // the smallest group that keeps the launch within one wave of resident warps
+            uint32_t G = 1;
+            while (G < 32 && cdiv(n_ub, G) > E.binv_coop_warps) G <<= 1;
             pb(PC_BINV_DIRECT);
-            k_binv_direct<<<cdiv(n_ub, 64), 64, 0, st>>>(in, out, info, unit, div1, div2, E.msqr_tabs.as<gf>());
+            k_binv_coop<<<cdiv(cdiv(n_ub, G), 4), 128, 0, st>>>(in, out, info, unit, div1, div2, G, E.msqr_tabs.as<gf>());
             pe();
             L.launches++;
             CK(cudaGetLastError());
             return 0;
         }
-        // the smallest fan-in that reaches a directly invertible batch: the serial multiplications per
-        // thread are pure latency for small batches
         uint32_t G = 2;
-        while (G < BINV_G && cdiv(n_ub, G) > BINV_DIRECT) G <<= 1;
+        while (G < BINV_G && cdiv(n_ub, G) > COOP_MAX) G <<= 1;
         const uint32_t ng = cdiv(n_ub, G);
         gf *pre = L.lvl_pre[depth].as<gf>(), *tot = L.lvl_tot[depth].as<gf>(), *inv = L.lvl_inv[depth].as<gf>();
         pb(PC_BINV_UP);
@@ -971,7 +1069,17 @@ struct Tree {
         CK(cudaGetLastError());
         return 0;
     }
+    // a round of at most this many additions runs one warp per addition (k_round_warp)
+    int round_warp(const AffPt *src, size_t task_ub, AffPt *dst) {
+        pb(PC_PASS2);
+        k_round_warp<<<cdiv(task_ub, 4), 128, 0, st>>>(src, L.info.as<uint32_t>(), L.desc.as<uint4>(), dst, E.msqr_tabs.as<gf>());
+        pe();
+        L.launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
     int round(int B, const AffPt *src, size_t task_ub, AffPt *dst) {
+        if (task_ub <= E.round_warp_max) return round_warp(src, task_ub, dst);
         if (B == 64) return round_t<64>(src, task_ub, dst);
         if (B == 16) return round_t<16>(src, task_ub, dst);
         if (B == 4) return round_t<4>(src, task_ub, dst);
@@ -980,8 +1088,9 @@ struct Tree {
 
     // Plan of round 0: caller tables -> lane set 1 (+ descriptors); info[0] = longest segment,
     // info[1] = additions of round 0.
-    int plan0(const uint32_t *start0, const uint32_t *len0, const uint32_t *ent, uint32_t nseg) {
-        return plan(len0, start0, ent, nseg, L.seg_start[1].as<uint32_t>(), L.seg_len[1].as<uint32_t>());
+    int plan0(const uint32_t *start0, const uint32_t *len0, const uint32_t *ent, uint32_t nseg, const AffPt *src) {
+        return plan(len0, start0, ent, nseg, L.seg_start[1].as<uint32_t>(), L.seg_len[1].as<uint32_t>(), src,
+                    L.pp[0].as<AffPt>());
     }
 
     // Reduce every segment of the index list `ent` over `src` to one point: dst[s], s < nseg, given that
@@ -1028,20 +1137,18 @@ struct Tree {
             const int o = (r + 1) & 1; // lane set written by this round's plan
             // tasks_r <= total/2^(r+1) + nseg/2
             const size_t task_ub = r == 0 ? total_ub / 2 + 1 : (total_ub >> (r + 1)) + nseg / 2 + 1;
-            int B = task_ub >= E.b64_min ? 64 : task_ub >= (1u << 21) ? 16 : task_ub >= (1u << 17) ? 4 : 1;
+            // additions chained per thread: long chains in the throughput-bound rounds; in the latency-bound ones just
+            // enough that the thread totals fit one cooperative inversion launch
+            int B = task_ub >= E.b64_min ? 64 : task_ub >= (1u << 21) ? 16 : task_ub > E.binv_direct ? 4 : 1;
             B = std::min(B, E.pass_b_max);
             AffPt *out = L.pp[r & 1].as<AffPt>();
-            if ((rc = round(B, cur_src, task_ub, out))) return rc;
-            pb(PC_MISC);
-            if (r == 0) k_copy_odd<true><<<cdiv(nseg, 256), 256, 0, st>>>(src, ent, in_start, in_len, estart[o], nseg, out);
-            else k_copy_odd<false><<<cdiv(nseg, 256), 256, 0, st>>>(cur_src, nullptr, in_start, in_len, estart[o], nseg, out);
-            pe();
-            L.launches++;
-            CK(cudaGetLastError());
+            if ((rc = round(B, cur_src, task_ub, out))) return rc; // (the odd leftovers were carried over by the plan)
             cur_src = out;
             in_start = estart[o];
             in_len = elen[o];
-            if (r + 1 < nr && (rc = plan(in_len, in_start, nullptr, nseg, estart[o ^ 1], elen[o ^ 1]))) return rc;
+            if (r + 1 < nr &&
+                (rc = plan(in_len, in_start, nullptr, nseg, estart[o ^ 1], elen[o ^ 1], cur_src, L.pp[(r + 1) & 1].as<AffPt>())))
+                return rc;
         }
         if (stop) {
             stop->src = cur_src;
@@ -1119,7 +1226,7 @@ int MsmEngine::build_table(const AffPt *d_points, size_t n, int W, AffPt *d_tab)
     if (n == 0) return 0;
     if (lanes.empty()) {
         lanes.emplace_back();
-        int rc0 = lanes.back().init();
+        int rc0 = lanes.back().init((int)lanes.size() - 1);
         if (rc0) return rc0;
     }
     MsmLane &L = lanes[0];
@@ -1159,7 +1266,7 @@ int MsmEngine::mulgen(const uint32_t *d_scalars, size_t n, AffPt *d_out) {
     if (n == 0) return 0;
     if (lanes.empty()) {
         lanes.emplace_back();
-        int rc0 = lanes.back().init();
+        int rc0 = lanes.back().init((int)lanes.size() - 1);
         if (rc0) return rc0;
     }
     MsmLane &L = lanes[0];
@@ -1259,11 +1366,11 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     const uint32_t R = 1u << lr, m = 1u << lm;
     const uint32_t per_b = lm * (m >> 1) + lr * (R >> 1) + m;
     // lanes: independent chains of rounds over disjoint ranges of virtual windows
-    int NL = profile ? 1 : force_lanes ? force_lanes : (n >= (1u << 13) ? 2 : 1);
+    int NL = (profile && !force_lanes) ? 1 : force_lanes ? force_lanes : (n >= (1u << 13) ? 2 : 1);
     NL = std::max(1, std::min<int>(NL, (int)V));
     while ((int)lanes.size() < NL) {
         lanes.emplace_back();
-        int rc0 = lanes.back().init();
+        int rc0 = lanes.back().init((int)lanes.size() - 1);
         if (rc0) return rc0;
     }
 
@@ -1385,7 +1492,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         if (timing && l == 0) cudaEventRecord(L.ev_s[0], L.stream);
         Tree tree(*this, L);
         const uint32_t *len0 = d_len_all + bounds[l], *start0 = d_start_all + bounds[l];
-        if ((rc = tree.plan0(start0, len0, entries.as<uint32_t>(), p.nseg))) return rc;
+        if ((rc = tree.plan0(start0, len0, entries.as<uint32_t>(), p.nseg, d_points))) return rc;
         if (timing && l == 0) CK(cudaMemcpyAsync(L.info_r0.p, L.info.p, 16, cudaMemcpyDeviceToDevice, L.stream));
         L.want_k = timing && l == 0;
         int r_main = 0, r_a = 0, r_b = 0;
@@ -1404,7 +1511,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
             // switch to the inversion-free tree once the work is latency-bound
             Tree::Partial part_a{ld_max, nullptr, nullptr, nullptr, 0};
             if (p.nent_a > ld_max) {
-                if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a))) return rc;
+                if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a, L.buckets.as<AffPt>()))) return rc;
                 rc = tree.rounds(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,
                                  std::max(R, m), nullptr, &r_a, &part_a);
                 if (rc) return rc;
@@ -1434,14 +1541,14 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
             k_gen_level_a<<<cdiv(p.nent_a, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, L.ents2.as<uint32_t>());
             k_gen_segs_a<<<cdiv(p.nseg_a + 1, 256), 256, 0, L.stream>>>(p.vn, nbv, lm, d_start, d_len);
             L.launches += 2;
-            if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a))) return rc;
+            if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a, L.buckets.as<AffPt>()))) return rc;
             rc = tree.rounds(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,
                              std::max(R, m), L.rc.as<AffPt>(), &r_a);
             if (rc) return rc;
             k_gen_level_b<<<cdiv(p.nent_b, 256), 256, 0, L.stream>>>(p.vn, lr, lm, L.ents2.as<uint32_t>());
             k_gen_segs_b<<<cdiv(p.nseg_b + 1, 256), 256, 0, L.stream>>>(p.vn, lr, lm, d_start, d_len);
             L.launches += 2;
-            if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_b))) return rc;
+            if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_b, L.rc.as<AffPt>()))) return rc;
             rc = tree.rounds(L.rc.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_b, p.nent_b,
                              std::max(R >> 1, m), hb.as<AffPt>() + (size_t)p.v0 * cv, &r_b);
             if (rc) return rc;
@@ -1494,13 +1601,16 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     stt.ms_tail_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     if (profile) {
         for (int i = 0; i < PC_COUNT; i++) prof_ms[i] = 0, prof_n[i] = 0;
+        timeline.clear();
         for (int l = 0; l < NL; l++)
             for (size_t i = 0; i < lanes[l].prof_used; i++) {
                 const auto &r = lanes[l].prof[i];
-                float ms = 0;
+                float ms = 0, t0 = 0;
                 cudaEventElapsedTime(&ms, r.e0, r.e1);
+                cudaEventElapsedTime(&t0, ev_t0, r.e0);
                 prof_ms[r.cat] += ms;
                 prof_n[r.cat]++;
+                timeline.push_back({(float)l, (float)r.cat, t0, t0 + ms}); // Gantt row: lane, category, start, end (ms)
             }
     }
     if (timing) {

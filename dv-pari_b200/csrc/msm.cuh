@@ -54,7 +54,7 @@ struct MsmLane {
     // timing of the dominant kernel (lane 0 only)
     cudaEvent_t ev_k[2] = {nullptr, nullptr}, ev_s[3] = {nullptr, nullptr, nullptr};
     bool want_k = false;
-    int init();
+    int init(int index);
     void destroy();
 };
 
@@ -80,13 +80,19 @@ struct MsmEngine {
     int force_lanes = 0;       // 0 = choose from n
     bool timing = false;
     bool profile = false; // per-category CUDA-event timing of every launch (development; forces one lane)
+    struct TimelineRow {
+        float lane, cat, t0, t1;
+    };
+    std::vector<TimelineRow> timeline; // of the last profiled run: one row per bracket, ms since the start of the MSM
     float prof_ms[PC_COUNT] = {0};
     unsigned prof_n[PC_COUNT] = {0};
     size_t b64_min = (size_t)1 << 23; // rounds with at least this many additions chain 64 per thread (off by default)
     bool prio_split = true; // large pass kernels on low-priority streams
     int pass_b_max = 64;    // cap on the additions chained per thread
     size_t ld_tree_max = 0; // 0 = automatic; a reduction level with more points starts with batched-affine rounds
-    uint32_t binv_direct = 20000; // batches up to this size are inverted one element per thread
+    uint32_t binv_direct = 36864;    // batches up to this size are inverted by one cooperative launch (k_binv_coop)
+    uint32_t binv_coop_warps = 2368; // ... in groups sized so that about this many warps run (one wave)
+    size_t round_warp_max = 4096; // a round of at most this many additions runs one warp per addition (k_round_warp)
     int pass2_minb = 2; // resident blocks per SM the pass-2 kernel is compiled for (register cap)
 
     int init(cudaStream_t s);
@@ -105,5 +111,6 @@ struct MsmEngine {
 int choose_window_bits(size_t n);
 int choose_table_windows(size_t n);
 int latency_probe(MsmEngine &E, int mode, int iters, float *us_per_op);
+int selftest_warp(MsmEngine &E, int op, const void *d_a, const void *d_b, void *d_out, size_t n); // 0 mul, 1 inverse
 
 } // namespace dvp

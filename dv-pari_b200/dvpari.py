@@ -78,6 +78,7 @@ def lib():
         L.dvp_msm_adhoc.argtypes = [vp, vp, vp, sz, vp]
         L.dvp_msm_last_stats.argtypes = [vp, C.POINTER(MsmStats)]
         L.dvp_msm_last_profile.argtypes = [vp, vp, vp]
+        L.dvp_msm_last_timeline.argtypes = [vp, vp, sz, C.POINTER(sz)]
         L.dvp_point_add.argtypes = [vp, vp, vp, vp]
         L.dvp_comm_unique_id.argtypes = [vp]
         L.dvp_comm_init.argtypes = [vp, vp, i32, i32]
@@ -266,6 +267,15 @@ class Context:
         _ck(lib().dvp_msm_last_profile(self._h, _ptr(ms), _ptr(cnt)))
         names = ["sort", "plan", "pass1", "binv_up", "binv_direct", "binv_down", "pass2", "misc"]
         return {nm: (float(ms[i]), int(cnt[i])) for i, nm in enumerate(names)}
+
+    def msm_timeline(self):
+        """(lane, category name, start ms, end ms) per launch bracket of the last profiled MSM."""
+        cnt = C.c_size_t()
+        _ck(lib().dvp_msm_last_timeline(self._h, None, 0, C.byref(cnt)))
+        rows = np.zeros((max(1, cnt.value), 4), dtype=np.float32)
+        _ck(lib().dvp_msm_last_timeline(self._h, _ptr(rows), cnt.value, C.byref(cnt)))
+        names = ["sort", "plan", "pass1", "binv_up", "binv_direct", "binv_down", "pass2", "misc"]
+        return [(int(r[0]), names[int(r[1])], float(r[2]), float(r[3])) for r in rows[:cnt.value]]
 
     def point_add(self, a30, b30):
         """CurvePoint::add on encodings (curve.rs:76-82)."""

@@ -99,6 +99,8 @@ int dvp_msm_last_stats(dvp_ctx *ctx, dvp_msm_stats *out);
 /* Development aid: with the "msm_profile" knob set the MSM runs on one lane with CUDA events around every
  * launch; ms/count per category: 0 sort 1 plan 2 pass1 3 binv_up 4 binv_direct 5 binv_down 6 pass2 7 misc. */
 int dvp_msm_last_profile(dvp_ctx *ctx, float ms[8], unsigned count[8]);
+/* ... and the same brackets as a timeline: rows of (lane, category, start ms, end ms) since the start of the MSM */
+int dvp_msm_last_timeline(dvp_ctx *ctx, float *rows4, size_t cap_rows, size_t *count);
 
 /*
  * Multi-GPU: one process (context) per GPU.  The MSMs shard by contiguous point range, the row evaluation by row

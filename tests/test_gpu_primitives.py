@@ -26,6 +26,9 @@ def test_gf_ops_on_device(ctx, oracle):
     assert gf_ints(ctx.selftest_op(0, A, B)) == [oracle.gf_mul(x, y) for x, y in zip(a, b)]
     assert gf_ints(ctx.selftest_op(1, A)) == [oracle.gf_sqr(x) for x in a]
     assert gf_ints(ctx.selftest_op(2, A[:300])) == [oracle.gf_inv(x) for x in a[:300]]
+    # the warp-cooperative forms (gf233_warp.cuh): one warp per product / inverse
+    assert gf_ints(ctx.selftest_op(6, A, B)) == [oracle.gf_mul(x, y) for x, y in zip(a, b)]
+    assert gf_ints(ctx.selftest_op(7, A[:600])) == [oracle.gf_inv(x) for x in a[:600]]
 
 
 def test_fr_ops_on_device(ctx):
