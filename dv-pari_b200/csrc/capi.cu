@@ -304,6 +304,11 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
         ctx->msm.b64_min = value > 0 ? (size_t)value : ((size_t)1 << 23);
         return DVP_OK;
     }
+    if (!strcmp(name, "use_accumulate")) {
+        if (value < 0 || value > 2) return DVP_ERR_BAD_ARG;
+        ctx->msm.use_accumulate = (int)value;
+        return DVP_OK;
+    }
     if (!strcmp(name, "binv_coop_warps")) {
         if (value < 1) return DVP_ERR_BAD_ARG;
         ctx->msm.binv_coop_warps = (uint32_t)value;

@@ -47,6 +47,14 @@ __device__ __forceinline__ uint32_t warp_mul_pick(const gf &a, const WarpMulCtx 
     return (v[0] & c.nl[0]) ^ (v[1] & c.nh[0]);
 }
 
+// lane src_lane's element to every lane
+__device__ __forceinline__ gf gf_bcast(const gf &v, int src_lane) {
+    gf r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.v[k] = __shfl_sync(0xffffffffu, v.v[k], src_lane);
+    return r;
+}
+
 // a * b, operands and result warp-uniform
 __device__ __forceinline__ gf gf_mul_warp(const gf &a, const gf &b, const WarpMulCtx &c) {
     const uint32_t x = warp_mul_pick(a, c) & c.live, y = warp_mul_pick(b, c);

@@ -494,6 +494,331 @@ __global__ void __launch_bounds__(128)
     if ((threadIdx.x & 31) == 0) pt_store(&dst[de.z], r);
 }
 
+// ------------------------------------------------------------------------------------------------
+// All tree rounds of a lane in ONE persistent kernel (cooperative launch: the grid is co-resident, one or two
+// blocks per SM).  A round is  plan | grid barrier | pass 1 -> inversion -> pass 2 | grid barrier:  the additions of a
+// round are dealt evenly to the threads (chains of ceil(tasks / threads): no wave quantisation), and every WARP inverts
+// the totals of its own 32 chains in registers (butterfly product tree by shuffles, one warp-cooperative inversion at
+// its root), so between the two passes nothing is exchanged and no warp waits for another.  The number of rounds is
+// decided on the device (the longest segment the plan saw).  The blocks of the OTHER lane's kernel are resident on the
+// same SMs: a lane's latency-bound stretches (plan, inversion, barriers, the small last rounds) are filled with the
+// other lane's multiplications warp by warp.
+// Everything one block writes and another reads inside the kernel is loaded with ld.global.cg (L1 is not coherent).
+// ------------------------------------------------------------------------------------------------
+struct AccArgs {
+    const AffPt *src0;              // points named by round 0 (SRS / tables, or the buckets for a reduction level)
+    const uint32_t *ent;            // round-0 index list (entry = index | negate << 31), or nullptr: positions
+    const uint32_t *start0, *len0;  // round-0 segment tables (nseg + 1 / nseg entries)
+    uint32_t nseg;
+    AffPt *pp[2];                   // ping-pong point lists of the later rounds
+    uint32_t *seg_start[2], *seg_len[2];
+    uint4 *desc;
+    gf *prefix, *tot, *tot_inv;
+    unsigned long long *blk_sum;    // one per block
+    uint32_t *ctl;                  // [0] barrier, [1] abort flag, [8 + r] longest segment at the plan of round r
+    uint32_t *result;               // [0] rounds run, [1] additions of round 0, [2] additions of all rounds (low 32 bits)
+    unsigned long long *times;      // profiling: globaltimer of block 0 after each phase, 6 per round (or nullptr)
+    AffPt *dst;                     // finalize: dst[s] = the point of segment s (or infinity); nullptr: leave the list
+    const gf *tabs;
+    int max_rounds;                 // run at most this many rounds (a fixed count for the reduction levels)
+    int tiny_max;                   // a round of at most this many additions runs one warp per addition
+};
+constexpr int ACC_THREADS = 256;
+constexpr int ACC_MAX_ROUNDS = 48;
+constexpr int ACC_TIME_WORDS = 6 * (ACC_MAX_ROUNDS + 1) + 2; // [last] = kernel start
+
+__device__ __forceinline__ gf gf_load_cg(const gf *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    const uint4 a = __ldcg(q), b = __ldcg(q + 1);
+    gf r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ AffPt fetch_entry_cg(const AffPt *src, uint32_t e) {
+    const AffPt *q = &src[e & 0x7fffffffu];
+    AffPt p;
+    p.x = gf_load_cg(&q->x);
+    p.y = gf_load_cg(&q->y);
+    if (e >> 31) p.y = gf_add(p.y, p.x);
+    return p;
+}
+__device__ __forceinline__ unsigned long long acc_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// sense-free grid barrier on a counter that only grows; gives up (abort flag) instead of spinning for ever
+__device__ __forceinline__ bool acc_barrier(uint32_t *ctl, uint32_t &target) {
+    __shared__ uint32_t sh_abort;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(&ctl[0], 1u);
+        const unsigned long long t0 = acc_now();
+        uint32_t ab = 0;
+        while (atomicAdd(&ctl[0], 0u) < target) {
+            __nanosleep(40);
+            if (atomicAdd(&ctl[1], 0u) != 0u || acc_now() - t0 > 4000000000ull) { // 4 s: a lost block, not a slow one
+                atomicExch(&ctl[1], 1u);
+                ab = 1;
+                break;
+            }
+        }
+        __threadfence();
+        sh_abort = ab;
+    }
+    __syncthreads();
+    return sh_abort == 0;
+}
+
+__global__ void __launch_bounds__(ACC_THREADS, 2) k_accumulate(const AccArgs A) {
+    __shared__ unsigned long long sh[ACC_THREADS / 32];
+    __shared__ unsigned long long sh_base, sh_total;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t nthreads = gridDim.x * ACC_THREADS, nwarps = nthreads >> 5;
+    const uint32_t gtid = blockIdx.x * ACC_THREADS + tid, gw = gtid >> 5;
+    uint32_t bar = 0;
+    const AffPt *cur = A.src0;
+    const uint32_t *cur_ent = A.ent, *in_start = A.start0, *in_len = A.len0;
+    const uint32_t nseg = A.nseg;
+    const uint32_t items = (nseg + nthreads - 1) / nthreads;
+    const uint32_t seg_base = gtid * items;
+    uint32_t adds_r0 = 0, adds_all = 0;
+    int r = 0;
+    const bool prof = A.times != nullptr && blockIdx.x == 0 && tid == 0;
+    if (prof) A.times[ACC_TIME_WORDS - 1] = acc_now();
+    for (; r < A.max_rounds; r++) {
+        const int o = (r + 1) & 1;
+        uint32_t *out_start = A.seg_start[o], *new_len = A.seg_len[o];
+        AffPt *out = A.pp[r & 1];
+        // ---- plan, step 1: block aggregates of (additions, points after the round) and the longest segment
+        unsigned long long s = 0;
+        uint32_t mx = 0;
+        for (uint32_t k = 0; k < items; k++) {
+            const uint32_t idx = seg_base + k;
+            const uint32_t L = idx < nseg ? __ldcg(&in_len[idx]) : 0;
+            s += (unsigned long long)(L >> 1) | ((unsigned long long)((L + 1) >> 1) << 32);
+            mx = max(mx, L);
+        }
+        unsigned long long incl = s;
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
+        }
+        for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, d));
+        if (lane == 0 && mx) atomicMax(&A.ctl[8 + r], mx);
+        if (lane == 31) sh[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned long long w = lane < ACC_THREADS / 32 ? sh[lane] : 0;
+            unsigned long long wi = w;
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= (uint32_t)d) wi += t;
+            }
+            if (lane < ACC_THREADS / 32) sh[lane] = wi - w; // exclusive offsets of the warps
+            if (lane == ACC_THREADS / 32 - 1) A.blk_sum[blockIdx.x] = wi;
+        }
+        if (!acc_barrier(A.ctl, bar)) return;
+        if (prof) A.times[6 * r + 0] = acc_now();
+        const uint32_t maxlen = __ldcg(&A.ctl[8 + r]);
+        if (maxlen <= 1) break; // every segment holds at most one point
+        // ---- plan, step 2: this block's offset and the totals
+        if (wid == 0) {
+            unsigned long long p = 0, tot = 0;
+            for (uint32_t b = lane; b < gridDim.x; b += 32) {
+                const unsigned long long v = __ldcg(&A.blk_sum[b]);
+                tot += v;
+                if (b < blockIdx.x) p += v;
+            }
+            for (int d = 16; d > 0; d >>= 1) {
+                p += __shfl_down_sync(0xffffffffu, p, d);
+                tot += __shfl_down_sync(0xffffffffu, tot, d);
+            }
+            if (lane == 0) {
+                sh_base = p;
+                sh_total = tot;
+            }
+        }
+        __syncthreads();
+        const uint32_t ntasks = (uint32_t)sh_total;
+        // ---- plan, step 3: next segment tables, one descriptor per addition, odd leftovers carried over
+        {
+            unsigned long long run = sh_base + sh[wid] + (incl - s);
+            for (uint32_t k = 0; k < items; k++) {
+                const uint32_t idx = seg_base + k;
+                uint32_t L = 0, in = 0;
+                if (idx < nseg) {
+                    L = __ldcg(&in_len[idx]);
+                    in = __ldcg(&in_start[idx]);
+                    out_start[idx] = (uint32_t)(run >> 32);
+                    new_len[idx] = (L + 1) >> 1;
+                    if (L & 1) {
+                        const uint32_t e = cur_ent ? cur_ent[in + L - 1] : in + L - 1;
+                        pt_store(&out[(uint32_t)(run >> 32) + (L >> 1)], fetch_entry_cg(cur, e));
+                    }
+                }
+                const uint32_t nt = L >> 1, ts = (uint32_t)run, os = (uint32_t)(run >> 32);
+                uint32_t todo = __ballot_sync(0xffffffffu, nt > 0);
+                while (todo) {
+                    const int sl = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const uint32_t nt_b = __shfl_sync(0xffffffffu, nt, sl), ts_b = __shfl_sync(0xffffffffu, ts, sl);
+                    const uint32_t in_b = __shfl_sync(0xffffffffu, in, sl), os_b = __shfl_sync(0xffffffffu, os, sl);
+                    for (uint32_t j = lane; j < nt_b; j += 32) {
+                        uint32_t a = in_b + 2 * j, b = a + 1;
+                        if (cur_ent) {
+                            a = cur_ent[a];
+                            b = cur_ent[b];
+                        }
+                        A.desc[ts_b + j] = make_uint4(a, b, os_b + j, 0);
+                    }
+                }
+                run += (unsigned long long)(L >> 1) | ((unsigned long long)((L + 1) >> 1) << 32);
+            }
+        }
+        if (r == 0) adds_r0 = ntasks;
+        adds_all += ntasks;
+        if (!acc_barrier(A.ctl, bar)) return;
+        if (prof) A.times[6 * r + 1] = acc_now();
+        // ---- pass 1: every thread chains B additions; warp gw owns the additions [gw 32 B, (gw + 1) 32 B)
+        // chain length: the additions are dealt evenly to all threads (longer chains on fewer warps were measured
+        // 30-100 % slower: an addition of pass 2 is ~30 us of dependent loads and products at low occupancy)
+        const uint32_t B = (ntasks + nthreads - 1) / nthreads;
+        const uint32_t base = gw * 32u * B;
+        if (ntasks <= (uint32_t)A.tiny_max) {
+            // ---- a tiny round: one WARP per addition, everything cooperative, no batching
+            const WarpMulCtx wc = warp_mul_ctx();
+            for (uint32_t t = gw; t < ntasks; t += nwarps) {
+                const uint4 de = __ldcg(&A.desc[t]);
+                const AffPt p1 = fetch_entry_cg(cur, de.x), p2 = fetch_entry_cg(cur, de.y);
+                gf d;
+                const int kind = pair_classify(p1, p2, d); // warp-uniform
+                AffPt q;
+                if (kind >= 2) {
+                    q = pair_finish(p1, p2, kind, d);
+                } else {
+                    const gf dinv = gf_inv_tab_warp(d, A.tabs, wc);
+                    gf lam = gf_mul_warp(kind == 1 ? p1.y : gf_add(p1.y, p2.y), dinv, wc);
+                    if (kind == 1) lam = gf_add(lam, p1.x);
+                    q.x = gf_add(gf_add(gf_sqr(lam), lam), gf_add(p1.x, p2.x));
+                    q.y = gf_add(gf_add(gf_mul_warp(lam, gf_add(p1.x, q.x), wc), q.x), p1.y);
+                }
+                if (lane == 0) pt_store(&out[de.z], q);
+            }
+        } else if (base < ntasks) { // the whole warp or none of it
+            gf acc = gf_one();
+            {
+                uint32_t t = base + lane;
+                uint4 de = make_uint4(0, 0, 0, 0);
+                gf x1 = gf_zero(), x2 = gf_zero();
+                if (t < ntasks) {
+                    de = __ldcg(&A.desc[t]);
+                    x1 = gf_load_cg(&cur[de.x & 0x7fffffffu].x);
+                    x2 = gf_load_cg(&cur[de.y & 0x7fffffffu].x);
+                }
+#pragma unroll 1
+                for (uint32_t k = 0; k < B; k++) {
+                    if (t >= ntasks) break;
+                    const uint32_t tn = t + 32;
+                    uint4 den = make_uint4(0, 0, 0, 0);
+                    gf x1n = gf_zero(), x2n = gf_zero();
+                    if (k + 1 < B && tn < ntasks) {
+                        den = __ldcg(&A.desc[tn]);
+                        x1n = gf_load_cg(&cur[den.x & 0x7fffffffu].x);
+                        x2n = gf_load_cg(&cur[den.y & 0x7fffffffu].x);
+                    }
+                    gf d = gf_add(x1, x2);
+                    if (gf_is_zero(x1) | gf_is_zero(x2)) d = gf_one();
+                    else if (gf_is_zero(d)) {
+                        const AffPt p1 = fetch_entry_cg(cur, de.x), p2 = fetch_entry_cg(cur, de.y);
+                        d = gf_eq(p1.y, p2.y) ? x1 : gf_one();
+                    }
+                    if (B > 1) {
+                        gf_store(&A.prefix[t], acc);
+                        acc = gf_mul_call(acc, d);
+                    } else {
+                        acc = d; // a chain of one: its prefix is 1
+                    }
+                    t = tn;
+                    de = den;
+                    x1 = x1n;
+                    x2 = x2n;
+                }
+            }
+            if (prof) A.times[6 * r + 2] = acc_now();
+            // ---- the warp inverts its own 32 thread totals, in registers: five butterfly levels up (every lane keeps
+            // its sibling's sub-product), one cooperative inversion of the warp product, five levels back down.  No
+            // inversion leaves the warp, so the warps of a round never wait for each other between the two passes.
+            gf inv;
+            {
+                gf S[5], P = acc;
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) S[k].v[q] = __shfl_xor_sync(0xffffffffu, P.v[q], 1 << k);
+                    P = gf_mul_call(P, S[k]);
+                }
+                const WarpMulCtx wc = warp_mul_ctx();
+                inv = gf_inv_tab_warp(P, A.tabs, wc);
+#pragma unroll
+                for (int k = 4; k >= 0; k--) inv = gf_mul_call(inv, S[k]);
+            }
+            if (prof) A.times[6 * r + 3] = acc_now();
+            // ---- pass 2: the same additions backwards
+#pragma unroll 1
+            for (int k = (int)B - 1; k >= 0; k--) {
+                const uint32_t t = base + (uint32_t)k * 32 + lane;
+                if (t >= ntasks) continue;
+                const uint4 de = __ldcg(&A.desc[t]);
+                const AffPt p1 = fetch_entry_cg(cur, de.x), p2 = fetch_entry_cg(cur, de.y);
+                gf d;
+                const int kind = pair_classify(p1, p2, d);
+                gf dinv = inv;
+                if (B > 1) {
+                    dinv = gf_mul_call(inv, gf_load_cg(&A.prefix[t]));
+                    if (k) inv = gf_mul_call(inv, d);
+                }
+                AffPt q;
+                if (kind >= 2) {
+                    q = pair_finish(p1, p2, kind, dinv);
+                } else {
+                    gf lam = gf_mul_call(kind == 1 ? p1.y : gf_add(p1.y, p2.y), dinv);
+                    if (kind == 1) lam = gf_add(lam, p1.x);
+                    q.x = gf_add(gf_add(gf_sqr(lam), lam), gf_add(p1.x, p2.x));
+                    q.y = gf_add(gf_add(gf_mul_call(lam, gf_add(p1.x, q.x)), q.x), p1.y);
+                }
+                pt_store(&out[de.z], q);
+            }
+        }
+        if (!acc_barrier(A.ctl, bar)) return;
+        if (prof) A.times[6 * r + 4] = acc_now();
+        cur = out;
+        cur_ent = nullptr;
+        in_start = out_start;
+        in_len = new_len;
+    }
+    // ---- after the last round every segment holds 0 or 1 points
+    if (A.dst) {
+        for (uint32_t sgm = gtid; sgm < nseg; sgm += nthreads) {
+            AffPt p = pt_inf();
+            if (__ldcg(&in_len[sgm])) {
+                const uint32_t pos = __ldcg(&in_start[sgm]);
+                p = fetch_entry_cg(cur, cur_ent ? cur_ent[pos] : pos);
+            }
+            pt_store(&A.dst[sgm], p);
+        }
+    }
+    if (gtid == 0) {
+        A.result[0] = (uint32_t)r;
+        A.result[1] = adds_r0;
+        A.result[2] = adds_all;
+    }
+    if (prof) A.times[6 * r + 5] = acc_now();
+}
+
 // pass 1: per task form the denominator and chain a per-thread prefix product
 template <int B>
 __global__ void __launch_bounds__(256)
@@ -643,12 +968,6 @@ __device__ __forceinline__ uint32_t binv_count(const uint32_t *__restrict__ info
 // prefix j and result j (the operands of a cooperative product are warp-uniform, so they are broadcast by shuffles).
 // 3 cooperative products per element and one cooperative inversion per warp: (3 G - 1) 0.36 us + 6.7 us of latency
 // whatever the batch size, against ~70 us per level of the thread-per-group kernels below.
-__device__ __forceinline__ gf gf_bcast(const gf &v, int src_lane) {
-    gf r;
-#pragma unroll
-    for (int k = 0; k < 8; k++) r.v[k] = __shfl_sync(0xffffffffu, v.v[k], src_lane);
-    return r;
-}
 __global__ void __launch_bounds__(128)
     k_binv_coop(const gf *__restrict__ in, gf *__restrict__ out, const uint32_t *__restrict__ info, uint32_t unit,
                 uint32_t div1, uint32_t div2, uint32_t G, const gf *__restrict__ tabs) {
@@ -901,7 +1220,7 @@ void MsmLane::destroy() {
     prof_used = 0;
     DevBuf *all[] = {&seg_len[0], &seg_len[1], &seg_start[0], &seg_start[1], &c_len, &c_start,
                      &blk, &blk_flag, &info, &info_r0, &pp[0], &pp[1], &prefix, &desc, &thr_total, &thr_inv, &lvl_pre[0],
-                     &lvl_pre[1], &lvl_tot[0], &lvl_tot[1], &lvl_inv[0], &lvl_inv[1], &buckets, &rc, &ents2};
+                     &lvl_pre[1], &lvl_tot[0], &lvl_tot[1], &lvl_inv[0], &lvl_inv[1], &buckets, &rc, &ents2, &acc_ctl, &acc_times};
     for (auto b : all) b->release();
     for (auto &e : ev_k)
         if (e) cudaEventDestroy(e), e = nullptr;
@@ -922,6 +1241,16 @@ int MsmEngine::init(cudaStream_t s) {
     CK(cudaEventCreate(&ev_t1));
     int rc = msqr_tabs.reserve(MSQ_TABLES * MSQ_TABLE_ELEMS * sizeof(gf));
     if (rc) return rc;
+    {
+        // the persistent accumulation kernel needs its grid co-resident: blocks per SM x SMs
+        int dev = 0, sms = 0, occ = 0, coop = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        // (register budgets of 80 and 64 per thread -- 3 and 4 resident blocks -- were 10-35 % slower: spills)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_accumulate, ACC_THREADS, 0) != cudaSuccess) occ = 0;
+        acc_capacity = coop ? (uint32_t)(sms * std::min(occ, 2)) : 0u;
+    }
     k_build_msqr_tables<<<cdiv(MSQ_TABLES * MSQ_TABLE_ELEMS, 128), 128, 0, s>>>(msqr_tabs.as<gf>());
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
@@ -954,6 +1283,7 @@ void MsmEngine::destroy() {
 
 namespace {
 
+constexpr int ACC_CTL_WORDS = 128;  // control block of one k_accumulate launch: barrier, abort, longest segments, result
 constexpr uint32_t PLAN_MAX_BLOCKS = 256; // k_plan's grid must be co-resident (blocks wait for their predecessors)
 constexpr uint32_t BINV_G = 16;        // group size of one batched-inversion level (large batches)
 
@@ -1084,6 +1414,46 @@ struct Tree {
         if (B == 16) return round_t<16>(src, task_ub, dst);
         if (B == 4) return round_t<4>(src, task_ub, dst);
         return round_t<1>(src, task_ub, dst);
+    }
+
+    // All rounds of one reduction in a single persistent launch (k_accumulate).  nr_fixed < 0: until every segment has
+    // at most one point, then dst[s] = that point; nr_fixed >= 0: exactly that many rounds, the list is left in
+    // pp[(nr-1) & 1] with the segment tables of set nr & 1 (dst may be null).  `slot` selects the control block.
+    int accumulate(const AffPt *src, const uint32_t *ent, const uint32_t *start0, const uint32_t *len0, uint32_t nseg,
+                   size_t total_ub, AffPt *dst, int nr_fixed, int slot, uint32_t grid_cap) {
+        AccArgs A;
+        A.src0 = src;
+        A.ent = ent;
+        A.start0 = start0;
+        A.len0 = len0;
+        A.nseg = nseg;
+        for (int i = 0; i < 2; i++) {
+            A.pp[i] = L.pp[i].as<AffPt>();
+            A.seg_start[i] = L.seg_start[i].as<uint32_t>();
+            A.seg_len[i] = L.seg_len[i].as<uint32_t>();
+        }
+        A.desc = L.desc.as<uint4>();
+        A.prefix = L.prefix.as<gf>();
+        A.tot = L.thr_total.as<gf>();
+        A.tot_inv = L.thr_inv.as<gf>();
+        A.blk_sum = L.blk.as<unsigned long long>();
+        A.ctl = L.acc_ctl.as<uint32_t>() + slot * ACC_CTL_WORDS;
+        A.result = A.ctl + 64;
+        A.times = E.profile ? L.acc_times.as<unsigned long long>() + slot * ACC_TIME_WORDS : nullptr;
+        A.dst = dst;
+        A.tabs = E.msqr_tabs.as<gf>();
+        A.max_rounds = nr_fixed >= 0 ? nr_fixed : ACC_MAX_ROUNDS;
+        A.tiny_max = (int)E.round_warp_max;
+        // enough threads for one addition each in round 0 (a small problem pays for its barriers by the block)
+        const size_t want = std::max<size_t>(total_ub / 2 + 1, nseg);
+        const uint32_t grid = (uint32_t)std::max<size_t>(1, std::min<size_t>(grid_cap, (want + ACC_THREADS - 1) / ACC_THREADS));
+        CK(cudaMemsetAsync(A.ctl, 0, ACC_CTL_WORDS * 4, st));
+        void *params[] = {(void *)&A};
+        pb(PC_PASS2);
+        CK(cudaLaunchCooperativeKernel((const void *)k_accumulate, dim3(grid), dim3(ACC_THREADS), params, 0, st));
+        pe();
+        L.launches++;
+        return 0;
     }
 
     // Plan of round 0: caller tables -> lane set 1 (+ descriptors); info[0] = longest segment,
@@ -1385,7 +1755,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     RS(scan_blk, (NB / SCAN_TILE + 8) * 8);
     RS(lane_info, 64 * 4);
     RS(hb, (size_t)V * cv * sizeof(AffPt));
-    if (!h_lane) CK(cudaMallocHost(&h_lane, 64 * 4));
+    if (!h_lane) CK(cudaMallocHost(&h_lane, 256 * 4));
     const size_t hb_bytes = (size_t)V * cv * sizeof(AffPt);
     if (h_pts_cap < hb_bytes) {
         if (h_pts) cudaFreeHost(h_pts);
@@ -1462,7 +1832,9 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         }
         RS(L.c_len, nseg_max * 4);
         RS(L.c_start, nseg_max * 4);
-        RS(L.blk, (PLAN_MAX_BLOCKS + 8) * 8);
+        RS(L.blk, (std::max<size_t>(PLAN_MAX_BLOCKS, acc_capacity) + 8) * 8);
+        RS(L.acc_ctl, 2 * ACC_CTL_WORDS * 4);
+        if (profile) RS(L.acc_times, 2 * ACC_TIME_WORDS * 8);
         if (!L.blk_flag.p) {
             RS(L.blk_flag, (PLAN_MAX_BLOCKS + 8) * 4);
             CK(cudaMemsetAsync(L.blk_flag.p, 0, (PLAN_MAX_BLOCKS + 8) * 4, L.stream));
@@ -1481,6 +1853,12 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     // a reduction level with more points than this starts with batched-affine rounds: large MSMs are throughput-bound
     // (5 instead of 15 multiplications per addition), small ones latency-bound (one launch instead of a round's six)
     const size_t ld_max = ld_tree_max ? ld_tree_max : (n >= (1u << 21) ? (size_t)1 << 13 : (size_t)1 << 16);
+    // The persistent kernel wins between 2^17 and 2^21 points (2^18: 3.00 against 3.17 ms, 2^19: 4.67 / 4.95, 2^20: 7.72 /
+    // 7.92, 2^21: 13.60 / 13.72; 23 launches instead of 87-155); below, a few hundred additions per round do not pay for
+    // grid barriers (2^12: 1.18 / 1.10), above, the separate large launches keep two blocks of one lane on every SM
+    // (2^22: 24.4 / 23.4 ms).
+    const bool persistent_any =
+        acc_capacity > 0 && (use_accumulate == 2 || (use_accumulate == 1 && n >= ((size_t)1 << 17) && n < ((size_t)3 << 20)));
     if (timing) cudaEventRecord(ev[3], st);
     // ---- per lane: accumulate buckets, then the two reduction levels into this lane's slice of hb
     for (int l = 0; l < NL; l++) {
@@ -1492,14 +1870,28 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         if (timing && l == 0) cudaEventRecord(L.ev_s[0], L.stream);
         Tree tree(*this, L);
         const uint32_t *len0 = d_len_all + bounds[l], *start0 = d_start_all + bounds[l];
-        if ((rc = tree.plan0(start0, len0, entries.as<uint32_t>(), p.nseg, d_points))) return rc;
-        if (timing && l == 0) CK(cudaMemcpyAsync(L.info_r0.p, L.info.p, 16, cudaMemcpyDeviceToDevice, L.stream));
-        L.want_k = timing && l == 0;
         int r_main = 0, r_a = 0, r_b = 0;
-        rc = tree.rounds(d_points, entries.as<uint32_t>(), start0, len0, p.nseg, p.total, p.maxlen, L.buckets.as<AffPt>(),
-                         &r_main);
-        if (rc) return rc;
-        L.want_k = false;
+        const bool persistent = persistent_any;
+        const uint32_t acc_grid = std::max<uint32_t>(1, acc_capacity / (uint32_t)NL);
+        if (persistent) CK(cudaMemsetAsync(L.acc_ctl.p, 0, 2 * ACC_CTL_WORDS * 4, L.stream)); // (a launch clears its own again)
+        if (persistent && profile) CK(cudaMemsetAsync(L.acc_times.p, 0, 2 * ACC_TIME_WORDS * 8, L.stream));
+        if (persistent) {
+            // every round of the bucket accumulation in one persistent launch; the lanes' kernels share the SMs
+            if (timing && l == 0) cudaEventRecord(L.ev_k[0], L.stream);
+            if ((rc = tree.accumulate(d_points, entries.as<uint32_t>(), start0, len0, p.nseg, p.total, L.buckets.as<AffPt>(),
+                                      -1, 0, acc_grid)))
+                return rc;
+            if (timing && l == 0) cudaEventRecord(L.ev_k[1], L.stream);
+            while ((1ull << r_main) < p.maxlen) r_main++;
+        } else {
+            if ((rc = tree.plan0(start0, len0, entries.as<uint32_t>(), p.nseg, d_points))) return rc;
+            if (timing && l == 0) CK(cudaMemcpyAsync(L.info_r0.p, L.info.p, 16, cudaMemcpyDeviceToDevice, L.stream));
+            L.want_k = timing && l == 0;
+            rc = tree.rounds(d_points, entries.as<uint32_t>(), start0, len0, p.nseg, p.total, p.maxlen,
+                             L.buckets.as<AffPt>(), &r_main);
+            if (rc) return rc;
+            L.want_k = false;
+        }
         if (timing && l == 0) cudaEventRecord(L.ev_s[1], L.stream);
         uint32_t *d_start = L.c_start.as<uint32_t>(), *d_len = L.c_len.as<uint32_t>();
         const uint32_t tthr = std::max(32u, std::max(R, m) / 2); // a segment has at most max(R, m) points
@@ -1510,7 +1902,24 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
             // large levels start with batched-affine rounds (5 instead of 15 multiplications per addition) and
             // switch to the inversion-free tree once the work is latency-bound
             Tree::Partial part_a{ld_max, nullptr, nullptr, nullptr, 0};
-            if (p.nent_a > ld_max) {
+            if (p.nent_a > ld_max && persistent) {
+                // the segments of level A have fixed lengths, so the number of rounds is known here:
+                // after r rounds at most nent_a / 2^r + nseg_a points remain
+                const uint32_t mlen = std::max(R, m);
+                int nr = 0, full = 0;
+                while ((1u << full) < mlen) full++;
+                while (nr < full && ((size_t)p.nent_a >> nr) + p.nseg_a > ld_max) nr++;
+                if (nr > 0) {
+                    if ((rc = tree.accumulate(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,
+                                              nullptr, nr, 1, acc_grid)))
+                        return rc;
+                    part_a.src = L.pp[(nr - 1) & 1].as<AffPt>();
+                    part_a.start = L.seg_start[nr & 1].as<uint32_t>();
+                    part_a.len = L.seg_len[nr & 1].as<uint32_t>();
+                    part_a.maxlen = (mlen + (1u << nr) - 1) >> nr;
+                }
+                r_a = nr;
+            } else if (p.nent_a > ld_max) {
                 if ((rc = tree.plan0(d_start, d_len, L.ents2.as<uint32_t>(), p.nseg_a, L.buckets.as<AffPt>()))) return rc;
                 rc = tree.rounds(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,
                                  std::max(R, m), nullptr, &r_a, &part_a);
@@ -1564,12 +1973,27 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         launches += lanes[l].launches;
     }
     CK(cudaMemcpyAsync(h_pts, hb.as<AffPt>(), hb_bytes, cudaMemcpyDeviceToHost, st));
+    uint32_t *h_acc = (uint32_t *)h_lane + 64; // per lane: 2 control blocks x (abort flag, rounds, additions r0, additions)
+    if (persistent_any)
+        for (int l = 0; l < NL; l++)
+            for (int k = 0; k < 2; k++) {
+                const uint32_t *ctl = lanes[l].acc_ctl.as<uint32_t>() + k * ACC_CTL_WORDS;
+                CK(cudaMemcpyAsync(h_acc + (2 * l + k) * 4, ctl + 1, 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(h_acc + (2 * l + k) * 4 + 1, ctl + 64, 12, cudaMemcpyDeviceToHost, st));
+            }
     if (timing) {
-        CK(cudaMemcpyAsync(h_lane, lanes[0].info_r0.p, 16, cudaMemcpyDeviceToHost, st));
+        if (!persistent_any) CK(cudaMemcpyAsync(h_lane, lanes[0].info_r0.p, 16, cudaMemcpyDeviceToHost, st));
         cudaEventRecord(ev[1], st);
     }
     cudaEventRecord(ev_t1, st);
     CK(cudaStreamSynchronize(st));
+    if (persistent_any)
+        for (int l = 0; l < NL; l++)
+            for (int k = 0; k < 2; k++)
+                if (h_acc[(2 * l + k) * 4]) {
+                    fprintf(stderr, "[dvpari] k_accumulate gave up at a grid barrier (lane %d, launch %d)\n", l, k);
+                    return DVP_ERR_INTERNAL;
+                }
     float ms_dev = 0;
     cudaEventElapsedTime(&ms_dev, ev_t0, ev_t1);
 
@@ -1612,6 +2036,28 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
                 prof_n[r.cat]++;
                 timeline.push_back({(float)l, (float)r.cat, t0, t0 + ms}); // Gantt row: lane, category, start, end (ms)
             }
+        // phases inside the persistent kernels: globaltimer of block 0 after every grid barrier, relative to the kernel's
+        // own start (rows with lane = 100 + 10 lane + launch; categories as above, plan step 1 / 2 both as plan)
+        if (persistent_any) {
+            std::vector<unsigned long long> tm(2 * ACC_TIME_WORDS);
+            for (int l = 0; l < NL; l++) {
+                if (cudaMemcpy(tm.data(), lanes[l].acc_times.p, tm.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) break;
+                for (int k = 0; k < 2; k++) {
+                    const unsigned long long *t = tm.data() + k * ACC_TIME_WORDS, ts = t[ACC_TIME_WORDS - 1];
+                    if (!ts) continue;
+                    unsigned long long prev = ts;
+                    const int cats[5] = {PC_PLAN, PC_PLAN, PC_PASS1, PC_BINV_DIRECT, PC_PASS2};
+                    for (int r = 0; r <= ACC_MAX_ROUNDS; r++)
+                        for (int ph = 0; ph < 6; ph++) {
+                            const unsigned long long v = t[6 * r + ph];
+                            if (!v) continue;
+                            timeline.push_back({(float)(100 + 10 * l + k), (float)(ph < 5 ? cats[ph] : PC_MISC),
+                                                (float)((prev - ts) * 1e-6), (float)((v - ts) * 1e-6)});
+                            prev = v;
+                        }
+                }
+            }
+        }
     }
     if (timing) {
         cudaEventRecord(ev[2], st);
@@ -1622,7 +2068,13 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         cudaEventElapsedTime(&stt.ms_reduce, L0.ev_s[1], L0.ev_s[2]);
         cudaEventElapsedTime(&stt.ms_tail, ev[1], ev[2]);
         if (stt.rounds_main > 0) cudaEventElapsedTime(&stt.ms_pass2_round0, L0.ev_k[0], L0.ev_k[1]);
-        stt.adds_round0 = ((const uint32_t *)h_lane)[1]; // info of lane 0's first plan
+        if (persistent_any) {
+            // the dominant kernel is lane 0's k_accumulate: every round of its buckets in one launch
+            stt.adds_round0 = h_acc[3];
+            stt.rounds_main = (int)h_acc[1];
+        } else {
+            stt.adds_round0 = ((const uint32_t *)h_lane)[1]; // info of lane 0's first plan
+        }
     }
     last = stt;
     return 0;

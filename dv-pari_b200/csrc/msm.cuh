@@ -39,7 +39,7 @@ struct MsmLane {
     cudaEvent_t ev_sw[2] = {nullptr, nullptr};
     cudaEvent_t done = nullptr;
     DevBuf seg_len[2], seg_start[2], c_len, c_start, blk, blk_flag, info, info_r0, pp[2], prefix, desc,
-        thr_total, thr_inv, lvl_pre[2], lvl_tot[2], lvl_inv[2], buckets, rc, ents2;
+        thr_total, thr_inv, lvl_pre[2], lvl_tot[2], lvl_inv[2], buckets, rc, ents2, acc_ctl, acc_times;
     unsigned long long launches = 0;
     uint32_t epoch = 0; // k_plan launch counter (the blocks' publish flag)
     // profiler: (category, start, stop) per bracket; events are pooled
@@ -93,6 +93,9 @@ struct MsmEngine {
     uint32_t binv_direct = 36864;    // batches up to this size are inverted by one cooperative launch (k_binv_coop)
     uint32_t binv_coop_warps = 2368; // ... in groups sized so that about this many warps run (one wave)
     size_t round_warp_max = 4096; // a round of at most this many additions runs one warp per addition (k_round_warp)
+    int use_accumulate = 1; // all rounds of a lane in one persistent cooperative launch (k_accumulate): 0 never,
+                            // 1 for the sizes where it wins, 2 always
+    uint32_t acc_capacity = 0;  // blocks of k_accumulate that are co-resident on the device (0: no cooperative launch)
     int pass2_minb = 2; // resident blocks per SM the pass-2 kernel is compiled for (register cap)
 
     int init(cudaStream_t s);
