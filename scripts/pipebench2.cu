@@ -88,13 +88,23 @@ template <int OPA, int NA, int OPB, int NB> void run(const char *name, uint32_t 
     printf("%-40s %.3e thread-instr/s  IPC/SMSP(at 1.965GHz) %.3f\n", name, rate, rate / 32 / (nsm * 4) / 1.965e9);
 }
 
-int main() {
+int main(int argc, char **argv) {
+    const bool only_ncu_cases = argc > 1; // `pipebench2 ncu`: the handful of mixes captured under ncu (profiles/)
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, 0);
     const int nsm = prop.multiProcessorCount;
     uint32_t *sink;
     cudaMalloc(&sink, 64);
 #define R(a, na, b, nb) run<a, na, b, nb>(#a "x" #na " + " #b "x" #nb, sink, nsm)
+    if (only_ncu_cases) {
+        R(A_WIDE, 1, A_NONE, 0);
+        R(A_LOP, 1, A_NONE, 0);
+        R(A_WIDE, 1, A_LOP, 1);
+        R(A_WIDE, 1, A_LOP, 2);
+        R(A_WIDE, 1, A_LOP, 3);
+        R(A_LO, 1, A_LOP, 1);
+        return 0;
+    }
     R(A_WIDE, 1, A_NONE, 0);
     R(A_WIDEACC, 1, A_NONE, 0);
     R(A_LO, 1, A_NONE, 0);

@@ -11,6 +11,8 @@ import dvpari, synth
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 what = sys.argv[2] if len(sys.argv) > 2 else "both"
 ctx = dvpari.Context(0)
+for kv in filter(None, os.environ.get("DVP_KNOBS", "").split(",")):  # e.g. DVP_KNOBS=use_accumulate=0,msm_lanes=1
+    ctx.set(kv.split("=")[0], int(kv.split("=")[1]))
 n = 1 << 20
 if what in ("msm", "both"):
     ctx.srs_random(0, n, 5)
