@@ -175,23 +175,36 @@ int comm_agree(dvp_ctx *ctx, int rc) {
 }
 
 // Sum of the ranks' partial MSM results, identical on every rank: all-gather 64-byte affine points, fold in
-// rank order on the host (CurvePoint::add, curve.rs:76-82).
-int comm_fold_points(dvp_ctx *ctx, const AffPt &mine, AffPt *total) {
+// rank order on the host (CurvePoint::add, curve.rs:76-82).  The status of the local MSM travels with the point
+// (80 bytes per rank): a rank whose MSM failed still takes part, and every rank returns the first failure -- nobody
+// is left waiting in the collective.
+int comm_fold_points(dvp_ctx *ctx, const AffPt &mine, int rc_local, AffPt *total) {
     if (ctx->world <= 1) {
         *total = mine;
-        return DVP_OK;
+        return rc_local;
     }
+    struct Slot {
+        AffPt p;
+        int rc, pad[3];
+    };
+    static_assert(sizeof(Slot) == 80, "point + status");
     int rc;
     const size_t W = (size_t)ctx->world;
-    if ((rc = ctx->commbuf.reserve((W + 1) * sizeof(AffPt))) != 0) return rc;
-    AffPt *d = ctx->commbuf.as<AffPt>();
-    CKN(cudaMemcpyAsync(d + W, &mine, sizeof(AffPt), cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = comm_all_gather(ctx, d + W, d, sizeof(AffPt))) != 0) return rc;
-    AffPt all[64];
-    CKN(cudaMemcpyAsync(all, d, W * sizeof(AffPt), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = ctx->commbuf.reserve(4096 + (W + 1) * sizeof(Slot))) != 0) return rc_local ? rc_local : rc;
+    Slot *d = reinterpret_cast<Slot *>(ctx->commbuf.as<char>() + 4096);
+    Slot me;
+    me.p = rc_local ? pt_inf() : mine;
+    me.rc = rc_local;
+    me.pad[0] = me.pad[1] = me.pad[2] = 0;
+    CKN(cudaMemcpyAsync(d + W, &me, sizeof(Slot), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = comm_all_gather(ctx, d + W, d, sizeof(Slot))) != 0) return rc;
+    Slot all[64];
+    CKN(cudaMemcpyAsync(all, d, W * sizeof(Slot), cudaMemcpyDeviceToHost, ctx->stream));
     CKN(cudaStreamSynchronize(ctx->stream));
-    AffPt acc = all[0];
-    for (size_t r = 1; r < W; r++) acc = host::aff_add(acc, all[r]);
+    for (size_t r = 0; r < W; r++)
+        if (all[r].rc) return all[r].rc;
+    AffPt acc = all[0].p;
+    for (size_t r = 1; r < W; r++) acc = host::aff_add(acc, all[r].p);
     *total = acc;
     return DVP_OK;
 }
@@ -220,7 +233,7 @@ int dvp_comm_init(dvp_ctx *ctx, const uint8_t id[128], int rank, int world) {
     ctx->comm = c;
     ctx->rank = rank;
     ctx->world = world;
-    return ctx->commbuf.reserve(4096); // the small exchanges (partial sums, status words) never allocate later
+    return ctx->commbuf.reserve(16384); // the small exchanges (partial sums, status words) never allocate later
 }
 
 // `world` contexts of this process become ranks 0 .. world-1 of one group without NCCL.  Every rank must then be
@@ -236,7 +249,7 @@ int dvp_comm_init_local(dvp_ctx *const *ctxs, int world) {
         ctxs[r]->local = g;
         ctxs[r]->rank = r;
         ctxs[r]->world = world;
-        if (cudaSetDevice(ctxs[r]->device) != cudaSuccess || ctxs[r]->commbuf.reserve(4096)) return DVP_ERR_CUDA;
+        if (cudaSetDevice(ctxs[r]->device) != cudaSuccess || ctxs[r]->commbuf.reserve(16384)) return DVP_ERR_CUDA;
     }
     return DVP_OK;
 }
@@ -293,9 +306,9 @@ int dvp_msm_sharded(dvp_ctx *ctx, int slot, const uint64_t *scalars_mont, size_t
         if (n) CKN(cudaMemcpyAsync(ctx->scal.p, scalars_mont, n * 32, cudaMemcpyHostToDevice, ctx->stream));
         d_sc = ctx->scal.p;
     }
-    AffPt mine, total;
-    if ((rc = slot_msm(ctx, slot, 0, (const uint32_t *)d_sc, n, &mine)) != 0) return rc;
-    if ((rc = comm_fold_points(ctx, mine, &total)) != 0) return rc;
+    AffPt mine = pt_inf(), total;
+    rc = slot_msm(ctx, slot, 0, (const uint32_t *)d_sc, n, &mine);
+    if ((rc = comm_fold_points(ctx, mine, rc, &total)) != 0) return rc;
     host::encode30(out30, total);
     return DVP_OK;
 }

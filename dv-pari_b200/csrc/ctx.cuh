@@ -44,6 +44,6 @@ int comm_all_gather(dvp_ctx *ctx, const void *send, void *recv, size_t bytes_per
 int comm_broadcast(dvp_ctx *ctx, void *buf, size_t bytes, int root);
 int comm_group(dvp_ctx *ctx, bool start);
 int comm_agree(dvp_ctx *ctx, int rc);
-int comm_fold_points(dvp_ctx *ctx, const dvp::AffPt &mine, dvp::AffPt *total);
+int comm_fold_points(dvp_ctx *ctx, const dvp::AffPt &mine, int rc_local, dvp::AffPt *total);
 
 int ctx_decode_into(dvp_ctx *ctx, const uint8_t *pts30, size_t n, dvp::AffPt *d_out, int64_t *first_invalid);

@@ -12,6 +12,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include "../../include/dvpari.h"
@@ -609,8 +612,55 @@ struct dvp_r1cs {
     bool t_ready = false;
     size_t nwires = 0;
 };
+// One helper thread per prover handle, alive from dvp_prover_create to dvp_prover_destroy: dvp_prove hands it the
+// witness commitment (the g_m MSM) so that its host-side launch sequence overlaps the main thread's.
+struct ProverWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, done = true, quit = false;
+    void start() {
+        th = std::thread([this] {
+            std::unique_lock<std::mutex> lk(mu);
+            for (;;) {
+                cv.wait(lk, [this] { return has_job || quit; });
+                if (quit) return;
+                std::function<void()> f = std::move(job);
+                has_job = false;
+                lk.unlock();
+                f();
+                lk.lock();
+                done = true;
+                cv.notify_all();
+            }
+        });
+    }
+    void submit(std::function<void()> f) {
+        std::lock_guard<std::mutex> lk(mu);
+        job = std::move(f);
+        has_job = true;
+        done = false;
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [this] { return done; });
+    }
+    void stop() {
+        if (!th.joinable()) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+            cv.notify_all();
+        }
+        th.join();
+    }
+};
+
 struct dvp_prover {
     dvp_ctx *ctx = nullptr;
+    ProverWorker worker;
     dvp_domain *dom = nullptr;
     dvp_r1cs *r1cs = nullptr;
     int slot_gm = 0, slot_gq = 0, slot_gk = 0;
@@ -919,6 +969,53 @@ static int extend_device(dvp_domain *d, fr *data, int npoly, size_t stride) {
     return 0;
 }
 
+// The same extend with `world` ranks sharing every polynomial (all ranks hold the same inputs): after log2(world)
+// decompose levels a vector is `world` independent sub-problems in contiguous blocks, so every rank runs the levels
+// below on ITS block of each polynomial only, the blocks are all-gathered, and the top recombine levels finish the
+// vectors.  The top 2 log2(world) level passes are done by every rank on the whole vectors (6 of 44 passes at 8 ranks,
+// 2^22 points); everything else is 1 / world of the work -- against one rank per polynomial (3 busy ranks of 8) before.
+// Falls back to owner-computes + broadcast when the shapes do not allow it.  Results land in `data` on every rank.
+static int extend_device_sharded(dvp_domain *d, fr *data, int npoly, size_t stride) {
+    dvp_ctx *ctx = d->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = d->n;
+    const int W = ctx->world, R = ctx->rank;
+    const int K = std::max(0, d->levels - EXT_FUSE_LOG); // levels above the fused ones
+    int s = 0;
+    while ((1 << s) < W) s++;
+    int rc;
+    if ((1 << s) != W || s > K || npoly > 3) {
+        for (int pl = 0; pl < npoly; pl++)
+            if (pl % W == R && (rc = extend_device(d, data + (size_t)pl * stride, 1, stride))) return rc;
+        if ((rc = comm_group(ctx, true))) return rc;
+        for (int pl = 0; pl < npoly; pl++)
+            if ((rc = comm_broadcast(ctx, data + (size_t)pl * stride, (size_t)n * sizeof(fr), pl % W))) {
+                comm_group(ctx, false);
+                return rc;
+            }
+        return comm_group(ctx, false);
+    }
+    const uint32_t blk = n >> s;
+    fr *mine = data + (size_t)R * blk;
+    for (int k = 0; k < s; k++) extend_level_launch(data, n, n >> (k + 1), d->dec[k].as<fr>(), npoly, stride, true, k, st);
+    for (int k = s; k < K; k++) extend_level_launch(mine, blk, n >> (k + 1), d->dec[k].as<fr>(), npoly, stride, true, k, st);
+    if ((rc = extend_fused_launch(d, mine, (uint32_t)npoly, blk, stride))) return rc;
+    for (int k = K - 1; k >= s; k--) extend_level_launch(mine, blk, n >> (k + 1), d->rec[k].as<fr>(), npoly, stride, false, k, st);
+    CKP(cudaGetLastError());
+    if ((rc = comm_group(ctx, true))) return rc;
+    for (int pl = 0; pl < npoly; pl++) {
+        fr *v = data + (size_t)pl * stride;
+        if ((rc = comm_all_gather(ctx, v + (size_t)R * blk, v, (size_t)blk * sizeof(fr)))) {
+            comm_group(ctx, false);
+            return rc;
+        }
+    }
+    if ((rc = comm_group(ctx, false))) return rc;
+    for (int k = s - 1; k >= 0; k--) extend_level_launch(data, n, n >> (k + 1), d->rec[k].as<fr>(), npoly, stride, false, k, st);
+    CKP(cudaGetLastError());
+    return 0;
+}
+
 // FFTree::extend(evals, Moiety::S1) for npoly vectors (host buffers, npoly x n x 4 u64)
 int dvp_ecfft_extend(dvp_domain *d, const uint64_t *in, uint64_t *out, int npoly) {
     if (!d || !in || !out || npoly <= 0) return DVP_ERR_BAD_ARG;
@@ -1061,9 +1158,10 @@ static int r1cs_eval_device(dvp_r1cs *r, dvp_domain *d, const fr *d_w, fr *a, fr
         if ((rc = comm_group(ctx, true))) return rc;
         fr *vs[4] = {a, b, c, iv};
         for (fr *v : vs)
-            if ((rc = comm_all_gather(ctx, v + lo, v, chunk))) return rc;
-        if ((rc = comm_all_gather(ctx, d_bad, d_bad + 8, 8))) return rc;
-        if ((rc = comm_group(ctx, false))) return rc;
+            if (!rc) rc = comm_all_gather(ctx, v + lo, v, chunk);
+        if (!rc) rc = comm_all_gather(ctx, d_bad, d_bad + 8, 8);
+        const int rc_end = comm_group(ctx, false); // the group is closed whatever happened inside it
+        if (rc || (rc = rc_end)) return rc;
         unsigned long long all[64];
         CKP(cudaMemcpyAsync(all, d_bad + 8, 8 * W, cudaMemcpyDeviceToHost, st));
         CKP(cudaStreamSynchronize(st));
@@ -1160,8 +1258,26 @@ int dvp_r1cs_eval_time(dvp_r1cs *r, dvp_domain *d, const uint64_t *assignment, i
     return rc;
 }
 
+static int prover_create_local(dvp_ctx *ctx, dvp_domain *dom, dvp_r1cs *r1cs, int slot_gm, int slot_gq, int slot_gk,
+                               dvp_prover **out);
 int dvp_prover_create(dvp_ctx *ctx, dvp_domain *dom, dvp_r1cs *r1cs, int slot_gm, int slot_gq, int slot_gk,
                       dvp_prover **out) {
+    if (!ctx || !out) return DVP_ERR_BAD_ARG;
+    int rc = prover_create_local(ctx, dom, r1cs, slot_gm, slot_gq, slot_gk, out);
+    if (ctx->world > 1) {
+        // every rank learns whether every rank has a prover: a rank that failed here (wrong slot sizes, out of memory)
+        // must not leave the others waiting in the first collective of dvp_prove
+        const int all = comm_agree(ctx, rc);
+        if (all && !rc) {
+            dvp_prover_destroy(*out);
+            *out = nullptr;
+            rc = all;
+        }
+    }
+    return rc;
+}
+static int prover_create_local(dvp_ctx *ctx, dvp_domain *dom, dvp_r1cs *r1cs, int slot_gm, int slot_gq, int slot_gk,
+                               dvp_prover **out) {
     if (!ctx || !dom || !r1cs || !out) return DVP_ERR_BAD_ARG;
     *out = nullptr;
     if (dom->n != r1cs->dev.n) return DVP_ERR_LENGTH_MISMATCH;
@@ -1197,11 +1313,13 @@ int dvp_prover_create(dvp_ctx *ctx, dvp_domain *dom, dvp_r1cs *r1cs, int slot_gm
         dvp_prover_destroy(p);
         return rc ? rc : DVP_ERR_OOM;
     }
+    p->worker.start();
     *out = p;
     return DVP_OK;
 }
 void dvp_prover_destroy(dvp_prover *p) {
     if (!p) return;
+    p->worker.stop();
     cudaSetDevice(p->ctx->device);
     DevBuf *all[] = {&p->vec, &p->wit, &p->dinv, &p->pre, &p->tot, &p->tot2, &p->pre2, &p->part};
     for (auto b : all) b->release();
@@ -1307,19 +1425,18 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     AffPt msm_gm, msm_q, kzg, part, part_gm;
     int rc_gm = 0;
     CKP(cudaEventRecord(ctx->ev_aux, st));
-    std::thread gm_thread([&] {
+    part_gm = pt_inf();
+    p->worker.submit([&, ctx, p, w, wlo, whi] {
         if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_aux, 0) != cudaSuccess) {
             rc_gm = DVP_ERR_CUDA;
             return;
         }
         rc_gm = slot_msm(ctx, p->slot_gm, 0, (const uint32_t *)(w + wlo), whi - wlo, &part_gm, ctx->aux_stream);
     });
-    struct Joiner {
-        std::thread &t;
-        ~Joiner() {
-            if (t.joinable()) t.join();
-        }
-    } joiner{gm_thread};
+    struct Joiner { // every return path waits for the helper: it writes into this frame
+        ProverWorker &wk;
+        ~Joiner() { wk.wait(); }
+    } joiner{p->worker};
     int64_t bad = -1;
     int rc = r1cs_eval_device(r, d, w, a, b, c, iv, &bad);
     if (rc) return rc;
@@ -1329,13 +1446,8 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     if (W == 1) {
         if ((rc = extend_device(d, a2, 3, n))) return rc;
     } else {
-        // independent polynomials: the owner extends, then every rank receives it
-        for (int pl = 0; pl < 3; pl++)
-            if (pl % W == R && (rc = extend_device(d, a2 + (size_t)pl * n, 1, n))) return rc;
-        if ((rc = comm_group(ctx, true))) return rc;
-        for (int pl = 0; pl < 3; pl++)
-            if ((rc = comm_broadcast(ctx, a2 + (size_t)pl * n, n * sizeof(fr), pl % W))) return rc;
-        if ((rc = comm_group(ctx, false))) return rc;
+        // every rank works on its block of all three polynomials (extend_device_sharded)
+        if ((rc = extend_device_sharded(d, a2, 3, n))) return rc;
     }
     k_ivals_ext<<<cdivp(n, 128), 128, 0, st>>>(w, (uint32_t)k, d->leaves.as<fr>(), (uint32_t)n, i2);
     if (stages) {
@@ -1346,12 +1458,13 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     k_quotient<<<cdivp(n, 128), 128, 0, st>>>(a2, b2, c2, i2, d->z_vals2inv.as<fr>(), (uint32_t)n, q);
     CKP(cudaGetLastError());
     cudaEventRecord(ev[3], st);
-    gm_thread.join();
-    if (rc_gm) return rc_gm;
-    if ((rc = comm_fold_points(ctx, part_gm, &msm_gm))) return rc;
+    p->worker.wait();
+    // (a rank whose MSM failed still takes part in the exchange; every rank then returns that failure)
+    if ((rc = comm_fold_points(ctx, part_gm, rc_gm, &msm_gm))) return rc;
     cudaEventRecord(ev[2], st);
-    if ((rc = slot_msm(ctx, p->slot_gq, 0, (const uint32_t *)(q + qlo), qhi - qlo, &part))) return rc;
-    if ((rc = comm_fold_points(ctx, part, &msm_q))) return rc;
+    part = pt_inf();
+    rc = slot_msm(ctx, p->slot_gq, 0, (const uint32_t *)(q + qlo), qhi - qlo, &part);
+    if ((rc = comm_fold_points(ctx, part, rc, &msm_q))) return rc;
     cudaEventRecord(ev[4], st);
     const AffPt commit = host::aff_add(msm_q, msm_gm); // proving.rs:515
     host::encode30(proof, commit);
@@ -1390,8 +1503,8 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     }
     if (W > 1) {
         // sum of the ranks' partial sums: all-gather of 64 bytes per rank
-        if ((rc = ctx->commbuf.reserve((size_t)(W + 1) * 2 * sizeof(fr)))) return rc;
-        fr *cb = ctx->commbuf.as<fr>();
+        if ((rc = ctx->commbuf.reserve(16384))) return rc; // (sized when the communicator was made)
+        fr *cb = reinterpret_cast<fr *>(ctx->commbuf.as<char>() + 8192);
         const fr mine[2] = {sa, sb};
         CKP(cudaMemcpyAsync(cb + 2 * W, mine, sizeof(mine), cudaMemcpyHostToDevice, st));
         if ((rc = comm_all_gather(ctx, cb + 2 * W, cb, sizeof(mine)))) return rc;
@@ -1422,8 +1535,9 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     }
     klo = 0;
     khi = 4 * (size_t)cnt;
-    if ((rc = slot_msm(ctx, p->slot_gk, 0, (const uint32_t *)(ks + klo), khi - klo, &part))) return rc;
-    if ((rc = comm_fold_points(ctx, part, &kzg))) return rc;
+    part = pt_inf();
+    rc = slot_msm(ctx, p->slot_gk, 0, (const uint32_t *)(ks + klo), khi - klo, &part);
+    if ((rc = comm_fold_points(ctx, part, rc, &kzg))) return rc;
     cudaEventRecord(ev[6], st);
     cudaEventSynchronize(ev[6]);
     host::encode30(proof + 30, kzg);

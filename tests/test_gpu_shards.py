@@ -21,7 +21,7 @@ def _circuit(O, lg):
     return circ, r1cs
 
 
-@pytest.mark.parametrize("world,lg", [(2, 10), (4, 12), (8, 12), (8, 14)])
+@pytest.mark.parametrize("world,lg", [(2, 10), (4, 12), (8, 12), (4, 14), (8, 14)])
 def test_sharded_prove_on_one_gpu_is_bit_exact(oracle, world, lg):
     O = oracle
     circ, r1cs = _circuit(O, lg)
