@@ -292,6 +292,91 @@ static void extend_level_launch(fr *data, uint32_t len, uint32_t h, const fr *ma
     else k_extend_level<3, BF_UP, true, true><<<grid, 256, 0, st>>>(data, len, h, mats, np, stride);
 }
 
+// ---- one output per butterfly: the levels ABOVE a rank's block in the sharded extend (extend_device_sharded).
+// Going down, only the half of each sub-problem that contains the rank's block is kept (h outputs of a level instead of
+// 2 h); coming back up, only the positions that lead to the rank's own range of the result are formed.
+template <int NP, bool IN29>
+__global__ void __launch_bounds__(256)
+    k_extend_down_sel(fr *__restrict__ data, uint32_t h, const fr *__restrict__ mats, int npoly, size_t stride, int which) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; // butterfly of the one sub-problem at `data`
+    if (j >= h) return;
+    const uint32_t i0 = j, i1 = j + h;
+    fr x0[NP], x1[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+        if (p < npoly) {
+            x0[p] = fr_load(&data[(size_t)p * stride + i0]);
+            x1[p] = fr_load(&data[(size_t)p * stride + i1]);
+        }
+    const fr29 m0 = fr29_load(&mats[4 * j]), m1 = fr29_load(&mats[4 * j + 1]), m3 = fr29_load(&mats[4 * j + 3]);
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+        if (p < npoly) {
+            fr29 a0, a1;
+            if (IN29) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    a0.l[q] = x0[p].v[q];
+                    a1.l[q] = x1[p].v[q];
+                    __builtin_assume(a0.l[q] <= DVP_M29);
+                    __builtin_assume(a1.l[q] <= DVP_M29);
+                }
+            } else {
+                a0 = fr29_from_fr(x0[p]);
+                a1 = fr29_from_fr(x1[p]);
+            }
+            // the decompose butterfly (butterfly29<BF_DOWN>): y0 = m0 a0 + m1 a1 at i0, y1 = a0 + m3 a1 at i1
+            if (which == 0) fr29_store(&data[(size_t)p * stride + i0], fr29_dot2_semi(m0, a0, m1, a1));
+            else fr29_store(&data[(size_t)p * stride + i1], fr29_muladd_semi(m3, a1, a0));
+        }
+}
+// level with sub-problems of 2 h points over n points; of every sub-problem only the `blk` positions starting at q0
+// (inside its lower or its upper half) are formed.  TOP: the plain 2x2 matrices of level 0, 32-bit words out.
+template <int NP, bool TOP>
+__global__ void __launch_bounds__(256)
+    k_extend_up_sel(fr *__restrict__ data, uint32_t n, uint32_t h, uint32_t blk, uint32_t q0, const fr *__restrict__ mats,
+                    int npoly, size_t stride) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (n / (2 * h)) * blk) return;
+    const uint32_t c = t / blk, o = t % blk;
+    const bool upper = q0 >= h;
+    const uint32_t j = (upper ? q0 - h : q0) + o; // butterfly of its sub-problem
+    const uint32_t i0 = c * 2 * h + j, i1 = i0 + h;
+    fr x0[NP], x1[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+        if (p < npoly) {
+            x0[p] = fr_load(&data[(size_t)p * stride + i0]);
+            x1[p] = fr_load(&data[(size_t)p * stride + i1]);
+        }
+    fr29 m0, m1;
+    if (TOP) {
+        m0 = fr29_load(&mats[4 * j + (upper ? 2 : 0)]);
+        m1 = fr29_load(&mats[4 * j + (upper ? 3 : 1)]);
+    } else {
+        m1 = fr29_load(&mats[4 * j + (upper ? 3 : 1)]);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+        if (p < npoly) {
+            fr29 a0, a1;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                a0.l[q] = x0[p].v[q];
+                a1.l[q] = x1[p].v[q];
+                __builtin_assume(a0.l[q] <= DVP_M29);
+                __builtin_assume(a1.l[q] <= DVP_M29);
+            }
+            fr *out = &data[(size_t)p * stride + (upper ? i1 : i0)];
+            if (TOP) {
+                const fr29 x[2] = {a0, a1}, r[2] = {m0, m1};
+                fr_store(out, fr_from_fr29(fr29_dotn<2>(r, x)));
+            } else {
+                fr29_store(out, fr29_muladd_semi(m1, a1, a0)); // butterfly29<BF_UP>: y = a0 + t a1
+            }
+        }
+}
+
 // The deepest levels of an extend work on sub-problems of at most EXT_FUSE_M points: one block stages a whole
 // sub-problem in shared memory (as 29-bit limbs, converted once on the way in and once on the way out), runs its
 // decompose levels down and its recombine levels up with a block barrier between levels, and writes it back -- one
@@ -972,10 +1057,13 @@ static int extend_device(dvp_domain *d, fr *data, int npoly, size_t stride) {
 // The same extend with `world` ranks sharing every polynomial (all ranks hold the same inputs): after log2(world)
 // decompose levels a vector is `world` independent sub-problems in contiguous blocks, so every rank runs the levels
 // below on ITS block of each polynomial only, the blocks are all-gathered, and the top recombine levels finish the
-// vectors.  The top 2 log2(world) level passes are done by every rank on the whole vectors (6 of 44 passes at 8 ranks,
-// 2^22 points); everything else is 1 / world of the work -- against one rank per polynomial (3 busy ranks of 8) before.
-// Falls back to owner-computes + broadcast when the shapes do not allow it.  Results land in `data` on every rank.
-static int extend_device_sharded(dvp_domain *d, fr *data, int npoly, size_t stride) {
+// vectors.  The levels above the block compute one output per butterfly only (k_extend_down_sel / k_extend_up_sel:
+// the half that contains the block going down, the positions that lead to the rank's own result range coming up), about
+// one level pass of work for all of them; everything else is 1 / world of the work -- against one rank per polynomial
+// (3 busy ranks of 8) before.  own_range_only: the result is valid on [rank n/world, (rank+1) n/world) of every
+// polynomial only (all a prover rank reads); otherwise on the whole vectors.
+// Falls back to owner-computes + broadcast when the shapes do not allow it.
+static int extend_device_sharded(dvp_domain *d, fr *data, int npoly, size_t stride, bool own_range_only) {
     dvp_ctx *ctx = d->ctx;
     cudaStream_t st = ctx->stream;
     const uint32_t n = d->n;
@@ -997,7 +1085,19 @@ static int extend_device_sharded(dvp_domain *d, fr *data, int npoly, size_t stri
     }
     const uint32_t blk = n >> s;
     fr *mine = data + (size_t)R * blk;
-    for (int k = 0; k < s; k++) extend_level_launch(data, n, n >> (k + 1), d->dec[k].as<fr>(), npoly, stride, true, k, st);
+    // decompose levels above the block: of every sub-problem on the way only the half that contains the block
+    {
+        uint32_t off = 0;
+        for (int k = 0; k < s; k++) {
+            const uint32_t h = n >> (k + 1);
+            const int which = (R >> (s - 1 - k)) & 1;
+            if (k == 0)
+                k_extend_down_sel<3, false><<<cdivp(h, 256), 256, 0, st>>>(data + off, h, d->dec[k].as<fr>(), npoly, stride, which);
+            else
+                k_extend_down_sel<3, true><<<cdivp(h, 256), 256, 0, st>>>(data + off, h, d->dec[k].as<fr>(), npoly, stride, which);
+            off += which ? h : 0;
+        }
+    }
     for (int k = s; k < K; k++) extend_level_launch(mine, blk, n >> (k + 1), d->dec[k].as<fr>(), npoly, stride, true, k, st);
     if ((rc = extend_fused_launch(d, mine, (uint32_t)npoly, blk, stride))) return rc;
     for (int k = K - 1; k >= s; k--) extend_level_launch(mine, blk, n >> (k + 1), d->rec[k].as<fr>(), npoly, stride, false, k, st);
@@ -1011,7 +1111,19 @@ static int extend_device_sharded(dvp_domain *d, fr *data, int npoly, size_t stri
         }
     }
     if ((rc = comm_group(ctx, false))) return rc;
-    for (int k = s - 1; k >= 0; k--) extend_level_launch(data, n, n >> (k + 1), d->rec[k].as<fr>(), npoly, stride, false, k, st);
+    if (own_range_only) {
+        // recombine levels above the block: only what leads to the values on this rank's own range [R blk, (R+1) blk)
+        for (int k = s - 1; k >= 0; k--) {
+            const uint32_t h = n >> (k + 1), q0 = (uint32_t)(((size_t)R * blk) % (2 * (size_t)h));
+            const uint32_t cnt = (n / (2 * h)) * blk;
+            if (k == 0)
+                k_extend_up_sel<3, true><<<cdivp(cnt, 256), 256, 0, st>>>(data, n, h, blk, q0, d->rec[k].as<fr>(), npoly, stride);
+            else
+                k_extend_up_sel<3, false><<<cdivp(cnt, 256), 256, 0, st>>>(data, n, h, blk, q0, d->rec[k].as<fr>(), npoly, stride);
+        }
+    } else {
+        for (int k = s - 1; k >= 0; k--) extend_level_launch(data, n, n >> (k + 1), d->rec[k].as<fr>(), npoly, stride, false, k, st);
+    }
     CKP(cudaGetLastError());
     return 0;
 }
@@ -1447,15 +1559,18 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
         if ((rc = extend_device(d, a2, 3, n))) return rc;
     } else {
         // every rank works on its block of all three polynomials (extend_device_sharded)
-        if ((rc = extend_device_sharded(d, a2, 3, n))) return rc;
+        if ((rc = extend_device_sharded(d, a2, 3, n, /*own_range_only=*/stages == nullptr))) return rc;
     }
-    k_ivals_ext<<<cdivp(n, 128), 128, 0, st>>>(w, (uint32_t)k, d->leaves.as<fr>(), (uint32_t)n, i2);
+    // i', r' (overwrites c') and q, proving.rs:492-509: a rank needs them on its own index range only (its g_q shard and
+    // its K scalars), which is also where the sharded extend left valid values; the stage dump wants whole vectors
+    const size_t elo = (W > 1 && !stages) ? qlo : 0, ecnt = (W > 1 && !stages) ? qhi - qlo : n;
+    k_ivals_ext<<<cdivp(ecnt, 128), 128, 0, st>>>(w, (uint32_t)k, d->leaves.as<fr>() + 2 * elo, (uint32_t)ecnt, i2 + elo);
     if (stages) {
         CKP(cudaMemcpyAsync(stages, V, 8 * n * 32, cudaMemcpyDeviceToHost, st));
         CKP(cudaStreamSynchronize(st));
     }
-    // r' (overwrites c') and q, proving.rs:492-509
-    k_quotient<<<cdivp(n, 128), 128, 0, st>>>(a2, b2, c2, i2, d->z_vals2inv.as<fr>(), (uint32_t)n, q);
+    k_quotient<<<cdivp(ecnt, 128), 128, 0, st>>>(a2 + elo, b2 + elo, c2 + elo, i2 + elo, d->z_vals2inv.as<fr>() + elo,
+                                                (uint32_t)ecnt, q + elo);
     CKP(cudaGetLastError());
     cudaEventRecord(ev[3], st);
     p->worker.wait();

@@ -38,7 +38,7 @@ def test_sharded_prove_on_one_gpu_is_bit_exact(oracle, world, lg):
                                 circ["coeffs_mont"])
     w = inst0.synth_solve(synth.synth_assignment(circ), circ["nlevels"])
     inst0.close()
-    want, rc, _ = O.prove(r1cs, od, srs, w)
+    want, rc, want_st = O.prove(r1cs, od, srs, w, want_stages=True)
     assert rc == 0
     # sharded MSM over a vector that does not divide evenly
     m = 5003
@@ -72,8 +72,11 @@ def test_sharded_prove_on_one_gpu_is_bit_exact(oracle, world, lg):
         except dvpari.DvpError as e:
             bad = (e.code, str(e))
         proof2 = prover.prove(w[1:1 + k], w[1 + k:])  # and the prover is still usable
+        # the stage dump runs the sharded extend with whole-vector outputs: a b c i a' b' c' i' must be the oracle's
+        proof3, st = prover.prove(w[1:1 + k], w[1 + k:], want_stages=True)
+        stages_ok = proof3 == proof and st[:8 * n].tobytes() == want_st[:8 * n].tobytes()
         prover.close(); inst.close(); gd.close()
-        return got_msm, proof, bad, proof2
+        return got_msm, proof, bad, proof2, stages_ok
 
     try:
         res = dvpari.run_ranks(rank_body, world)
@@ -81,8 +84,9 @@ def test_sharded_prove_on_one_gpu_is_bit_exact(oracle, world, lg):
         for c in ctxs:
             c.comm_destroy()
             c.close()
-    for r, (got_msm, proof, bad, proof2) in enumerate(res):
+    for r, (got_msm, proof, bad, proof2, stages_ok) in enumerate(res):
         assert got_msm == want_msm, r
+        assert stages_ok, f"rank {r}/{world}: stage vectors of the sharded prove differ from the oracle's"
         assert proof == want, f"rank {r}/{world}: sharded proof differs from the oracle's"
         assert proof2 == want
         assert bad is not None and bad[0] == 6 and bad[1] == res[0][2][1]
