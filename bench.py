@@ -4,11 +4,12 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the C ABI)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm on host cores
 
-A step = one multi_scalar_mul (curve.rs:141-158) of 2^LG uniformly random Fr scalars against 2^LG
-resident SRS points, per GPU.  With N > 1 (torchrun) every rank owns a contiguous point range of the
-N*2^LG-point MSM (weak scaling); the 30-byte partial sums are all-gathered over NCCL and folded.
-`value` times the device-resident call (scalars already in HBM); `e2e` times the host-buffer C-ABI
-call dvp_msm (scalars copied from the host inside the timed region, 30-byte result back).
+A step = a batch of BATCH (default 8) multi_scalar_mul calls (curve.rs:141-158), each of 2^LG uniformly random Fr
+scalars (a different vector per call) against the 2^LG resident SRS points of the GPU -- the batch makes the timed region
+of the driver's 20 steps longer than a second.  With N > 1 (torchrun) every rank owns a contiguous point range of
+N*2^LG-point MSMs (weak scaling); the partial sums are all-gathered over NCCL and folded.
+`value` times the device-resident calls (scalars already in HBM); `e2e` times the host-buffer C-ABI
+call (scalars copied from pinned host memory inside the timed region, 30-byte results back).
 
 The second half of BASELINE.json's metric -- DV-Pari prove ms at 2^22 constraints -- is measured in the same
 run and reported under "prove": Proof::prove (proving.rs:426-688) through dvp_prove on a synthetic SP1-shaped
@@ -29,15 +30,21 @@ sys.path.insert(0, os.path.join(ROOT, "dv-pari_b200"))
 
 METRIC = "sect233k1 MSM points/s"
 UNIT = "points/s"
-# static facts about the dominant kernel (k_pass2, one batched affine addition per task), see DESIGN.md
-PASS2_BYTES_PER_ADD = 128 + 32 + 16 + 64  # two points in, prefix product, task descriptor, one point out
-# dram__bytes_read.sum + dram__bytes_write.sum of the round-0 launch / its additions (profiles/README.md, r1b capture)
-PASS2_DRAM_BYTES_PER_ADD_NCU = 385
-# ALU-pipe issue slots per addition in k_pass2 (scripts/sass_count.py): 4 calls of the out-of-line multiplier
-# (434 IMAD.WIDE + 760 LOP3/SHF each) + the loop body (250 ALU).  IMAD.WIDE holds the FMA pipe for 4 cycles AND the
-# ALU pipe for 2 (profiles/README.md, pipe probes), so it counts as one ALU-pipe slot as well.
-PASS2_ALU_INSTR_PER_ADD = (4 * 760 + 250) + 4 * 434
-ALU_PIPE_PEAK = 1.84e13                    # measured LOP3 thread-instr/s on this pool's B200 (profiles/r1_pipe_rates.json)
+# Static facts about the dominant kernel, see DESIGN.md 4.2 / profiles/README.md (r2c).  At 2^20 points it is
+# k_accumulate: ALL tree rounds of the bucket accumulation in one persistent launch (plan, pass 1, per-warp inversion,
+# pass 2 per round).  Per batched affine addition it moves, algorithmically: descriptor 16 B written + 2 x 16 B read,
+# x coordinates 2 x 32 B (pass 1), prefix product 32 B written + 32 B read, two points 128 B (pass 2), one point out 64 B.
+ACC_BYTES_PER_ADD = 48 + 64 + 64 + 128 + 64
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch / its additions (profiles/r2c_ncu_accumulate_raw.csv:
+# 2.82 GB + 0.77 GB for 6.9 M additions: the 64-byte gathers of the bucket-sorted round 0 touch whole sectors)
+ACC_DRAM_BYTES_PER_ADD_NCU = 520
+# Issue-port instructions per addition (the ALU and FMA-heavy pipes share one port of 0.5 instructions per clock and
+# scheduler: profiles/README.md r2c, ncu counters of the IMAD.WIDE / LOP3 mixes): 6 field products of 774 ALU-pipe + 434
+# IMAD.WIDE each (pass 1: 1, pass 2: 4, the warp's own inversion tree ~1 amortised), one squaring (111) and ~250 of loop
+# body -- 7.4e3; ncu's sm__pipe_alu / fmaheavy cycle counters of the same launch give 7.3e3 per addition.
+ACC_PORT_INSTR_PER_ADD = 6 * (774 + 434) + 111 + 250
+ISSUE_PORT_PEAK = 1.83e13  # measured: LOP3 alone, and every IMAD.WIDE + k LOP3 mix, stop at this many thread-instr/s
+                           # (smsp__issue_active = 50 %), profiles/r2c_ncu_pipebench2_raw.csv
 
 
 def peaks():
@@ -122,6 +129,8 @@ def run_reference(args):
 
     if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "all"])
+    # a step of the workload is a batch of MSMs of 2^lg points; the CPU arm times ONE 2^cpu_lg-point MSM per step
+    # (a bounded sample of the batch: the algorithm's cost is linear in the points) and reports points/s
     lg_s = args.cpu_lg
     for _ in range(args.warmup):
         cpu_msm_sample(None, min(lg_s, 10), 11)
@@ -135,9 +144,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 (GF(2^233) via PCLMULQDQ)", "data": "synthetic",
-        "config": {"workload": f"msm 2^{args.lg} points per GPU, sect233k1, uniform Fr scalars",
+        "config": {"workload": workload_name(args.lg, max(1, args.batch)),
                    "note": "C restatement of the reference algorithm (the Rust crate cannot be built offline); "
-                           f"each step is a 2^{lg_s}-point sample of the workload"},
+                           f"each step times one 2^{lg_s}-point MSM of the batch (bounded sample; cost linear in the points)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                          "sample": f"{args.steps} x 2^{lg_s} points, per-point tau-adic (width-4 TNAF) scalar mul + sum, OpenMP all cores"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -321,16 +330,83 @@ def prove_section(ctx, args, rank, world, sync_all, timed):
     return out
 
 
+def workload_name(lg, batch):
+    return f"sect233k1 MSM, 2^{lg} points per GPU per MSM, uniform Fr scalars, batch of {batch} MSMs per step"
+
+
+def extras_section(ctx, args, rank, world, timed, n):
+    """The configurations of BASELINE.json that the headline step does not cover, one short measurement each:
+    plain layout (no precomputed window multiples), the table build, the ad-hoc call with encoded points from the host
+    (config #2: 2^16 points), and a 2^24-point MSM split over the ranks (config #5, strong scaling)."""
+    import dvpari
+
+    out = {}
+    d_sc = ctx.dev_alloc(n * 32)
+    ctx.dev_upload(d_sc, dvpari.random_fr_mont(n, 0xD5A10011 + rank))
+    # plain layout: one bucket set per window, no tables
+    ctx.set("msm_tables", 0)
+    ref = ctx.msm_sharded(d_sc, 0, on_device=True, n=n)
+    dt, _ = timed(lambda: ctx.msm_sharded(d_sc, 0, on_device=True, n=n), 5)
+    st = ctx.msm_stats()
+    out["plain_layout"] = {"points_per_s": world * n * 5 / dt, "ms_per_msm": 1e3 * dt / 5, "window_bits": st["window_bits"],
+                           "windows": st["windows"], "note": "msm_tables=0: no precomputed window multiples (memory = the SRS only)"}
+    ctx.set("msm_tables", 1)
+    # table build: drop and rebuild the window multiples of the slot (first MSM after a reload pays it)
+    pts = ctx.srs_read(0, 0, n)
+    ctx.srs_load(0, pts)
+    t0 = time.perf_counter()
+    again = ctx.msm_sharded(d_sc, 0, on_device=True, n=n)
+    t_first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ctx.msm_sharded(d_sc, 0, on_device=True, n=n)
+    t_next = time.perf_counter() - t0
+    assert again == ref, "plain and table layouts disagree"
+    st = ctx.msm_stats()
+    out["tables"] = {"build_ms": 1e3 * (t_first - t_next), "bytes": int(st["windows"]) * n * 64, "windows": st["windows"],
+                     "note": "T[j] = 2^(off_j) P for every window j, built on the first MSM of a slot"}
+    ctx.dev_free(d_sc)
+    if rank == 0:
+        # ad-hoc form (srs.rs:422 style): encoded points AND scalars from the host on every call, 2^16 points
+        m = 1 << 16
+        sc = dvpari.random_fr_mont(m, 0xD5A10001)
+        enc = pts[:m]
+        ctx.multi_scalar_mul_adhoc(sc, enc)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ctx.multi_scalar_mul_adhoc(sc, enc)
+        dt = (time.perf_counter() - t0) / 5
+        out["adhoc_2_16"] = {"points_per_s": m / dt, "ms_per_msm": 1e3 * dt,
+                             "note": "dvp_msm_adhoc: 30-byte points + scalars from host memory, decode + MSM inside the call"}
+    # 2^24 points in total, point-range-sharded over the ranks (strong scaling)
+    big = (1 << args.big_lg) // world
+    if args.big_lg:
+        ctx.srs_random(7, big, 0xD5A10024 + rank)
+        d_big = ctx.dev_alloc(big * 32)
+        ctx.dev_upload(d_big, dvpari.random_fr_mont(big, 0xD5A10025 + rank))
+        ctx.msm_sharded(d_big, 7, on_device=True, n=big)  # builds the tables, sizes the scratch
+        dt, _ = timed(lambda: ctx.msm_sharded(d_big, 7, on_device=True, n=big), 3)
+        st = ctx.msm_stats()
+        out[f"msm_2_{args.big_lg}"] = {"points_total": big * world, "points_per_gpu": big, "ms_per_msm": 1e3 * dt / 3,
+                                       "points_per_s": big * world * 3 / dt, "scaling": "strong" if world > 1 else "single GPU",
+                                       "window_bits": st["window_bits"], "windows": st["windows"], "launches": int(st["launches"])}
+        ctx.dev_free(d_big)
+        ctx.srs_free(7)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--lg", type=int, default=20, help="log2 of the points per GPU")
-    ap.add_argument("--cpu-lg", type=int, default=20, help="log2 of the CPU-baseline sample (2^20 points = the whole workload, ~ 15-30 s of CPU-core time)")
+    ap.add_argument("--lg", type=int, default=20, help="log2 of the points per GPU and MSM")
+    ap.add_argument("--batch", type=int, default=8, help="MSMs (independent scalar vectors) per step")
+    ap.add_argument("--cpu-lg", type=int, default=20, help="log2 of the CPU-baseline sample (2^20 points = one MSM of the workload, ~ 15-30 s of CPU-core time)")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--prove-lg", type=int, default=22, help="log2 of the constraint count of the prove measurement (0 = skip)")
+    ap.add_argument("--big-lg", type=int, default=24, help="log2 of the total points of the large strong-scaled MSM (0 = skip)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the plain-layout / table-build / ad-hoc / 2^24 measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -352,7 +428,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n = 1 << args.lg
+    n, batch = 1 << args.lg, max(1, args.batch)
     ctx = dvpari.Context(local)
     if use_dist:
         # the library's own NCCL communicator; torch.distributed only ships the id and runs the barriers
@@ -361,14 +437,15 @@ def main():
         ctx.comm_init(ids[0], rank, world)
     if args.window_bits:
         ctx.set("msm_window_bits", args.window_bits)
-    # this rank's range of the N*2^lg-point SRS and of the scalar vector
+    # this rank's range of the N*2^lg-point SRS and of the `batch` scalar vectors (pinned host copies + device copies)
     ctx.srs_random(0, n, 0xD5A10002 + rank)
-    sc_host = dvpari.random_fr_mont(n, 0xD5A10001 + rank)
-    pinned = torch.empty((n, 4), dtype=torch.int64).pin_memory()
-    pinned.numpy().view(np.uint64)[:] = sc_host
+    pinned = torch.empty((batch, n, 4), dtype=torch.int64).pin_memory()
     sc_pinned = pinned.numpy().view(np.uint64)
-    d_sc = ctx.dev_alloc(n * 32)
-    ctx.dev_upload(d_sc, sc_host)
+    d_sc = []
+    for b in range(batch):
+        sc_pinned[b] = dvpari.random_fr_mont(n, 0xD5A10001 + 97 * b + rank)
+        d_sc.append(ctx.dev_alloc(n * 32))
+        ctx.dev_upload(d_sc[b], sc_pinned[b])
 
     def sync_all():
         torch.cuda.synchronize()
@@ -389,10 +466,10 @@ def main():
             dt = float(t.item())
         return dt, out
 
-    # dvp_msm_sharded: local MSM over this rank's point range, all-gather of the 64-byte partial sums over NCCL,
-    # identical fold on every rank (with one rank it is the plain MSM)
-    step_dev = lambda: ctx.msm_sharded(d_sc, 0, on_device=True, n=n)
-    step_e2e = lambda: ctx.msm_sharded(sc_pinned, 0)
+    # dvp_msm_sharded: local MSM over this rank's point range, all-gather of the partial sums over NCCL, identical fold
+    # on every rank (with one rank it is the plain MSM)
+    step_dev = lambda: [ctx.msm_sharded(d_sc[b], 0, on_device=True, n=n) for b in range(batch)]
+    step_e2e = lambda: [ctx.msm_sharded(sc_pinned[b], 0) for b in range(batch)]
 
     for _ in range(args.warmup):
         step_dev()
@@ -406,70 +483,90 @@ def main():
     if ncu_range:
         torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.stop() if rank == 0 else None
-    launches_per_step = int(ctx.msm_stats()["launches"])  # kernels of one timed step (the instrumented run below uses one lane)
+    launches_per_msm = int(ctx.msm_stats()["launches"])  # kernels of one MSM of the timed steps
     for _ in range(2):
         step_e2e()
     dt_e2e, res_e2e = timed(step_e2e, args.steps)
     assert res_dev == res_e2e, "device-resident and host-buffer calls disagree"
 
-    # one instrumented step: stage split, launches, the dominant kernel's duration (CUDA events in the library)
-    # (single lane here so that no other stream shares the GPU with the kernel being timed)
+    # one instrumented MSM: stage split and the dominant kernel's duration (CUDA events on its launching stream inside
+    # the library; a single lane here so that no other stream shares the GPU with the kernel being timed)
     ctx.set("timing", 1)
     ctx.set("msm_lanes", 1)
-    ctx.multi_scalar_mul_device(d_sc, n, 0)  # sizes the single lane's scratch
-    ctx.multi_scalar_mul_device(d_sc, n, 0)
+    ctx.multi_scalar_mul_device(d_sc[0], n, 0)  # sizes the single lane's scratch
+    ctx.multi_scalar_mul_device(d_sc[0], n, 0)
     st = ctx.msm_stats()
     ctx.set("timing", 0)
     ctx.set("msm_lanes", 0)
 
+    extras = None if args.no_extras else extras_section(ctx, args, rank, world, timed, n)
     prove = prove_section(ctx, args, rank, world, sync_all, timed) if args.prove_lg else None
 
     if rank == 0:
         hbm_peak, which = peaks()
         k_ms, k_adds = st["ms_pass2_round0"], st["adds_round0"]
-        achieved = k_adds * PASS2_BYTES_PER_ADD / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-        alu = k_adds * PASS2_ALU_INSTR_PER_ADD / (k_ms * 1e-3) if k_ms > 0 else 0.0
+        persistent = int(st["launches"]) < 40  # k_accumulate ran (the separate-launch path has > 60 launches)
+        kernel = ("k_accumulate (all tree rounds of the bucket accumulation, one persistent cooperative launch)" if persistent
+                  else "k_pass2<16,2> (pass 2 of round 0 of the bucket accumulation)")
+        bytes_per_add = ACC_BYTES_PER_ADD if persistent else 240
+        dram_per_add = ACC_DRAM_BYTES_PER_ADD_NCU if persistent else 385
+        instr_per_add = ACC_PORT_INSTR_PER_ADD if persistent else 4 * (774 + 434) + 250
+        gbps = k_adds * bytes_per_add / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        port = k_adds * instr_per_add / (k_ms * 1e-3) if k_ms > 0 else 0.0
         # bounded CPU baseline on the same SRS points (first 2^cpu_lg of rank 0's range), checked against the GPU
         lg_s = min(args.cpu_lg, args.lg)
         pps, cores, cdt, cpu_res, sc_s = cpu_msm_sample(ctx, lg_s, 0xD5A10009)
         gpu_res = ctx.multi_scalar_mul(sc_s, 0)
         assert gpu_res == cpu_res, "GPU MSM differs from the CPU oracle on the baseline sample"
+        pts_per_step = world * n * batch
+        config = {"workload": workload_name(args.lg, batch),
+                  "window_bits": st["window_bits"], "windows": st["windows"], "precomputed_tables": bool(st["tables"]),
+                  "srs": "resident in HBM (decoded once), window multiples built on first use",
+                  "rounds": [st["rounds_main"], st["rounds_a"], st["rounds_b"]], "launches_per_msm": launches_per_msm,
+                  "l2": "per-MSM working set (sort keys, ping-pong point buffers, prefix products: >1 GB at 2^20) exceeds the 126 MB L2; "
+                        "every MSM of a step has its own scalar vector",
+                  "parallelism": f"point-range sharding x{world}, NCCL all-gather of 80-byte partial sums, fold on every rank" if world > 1 else "single GPU",
+                  "stage_ms": {"recode_sort": st["ms_recode_sort"], "accumulate": st["ms_accumulate"],
+                               "reduce": st["ms_reduce"], "tail": st["ms_tail"]}}
+        if extras:
+            config["other_configs"] = extras
+        if prove:
+            # the second half of BASELINE.json's metric, kept where the driver's parsed.config keeps it
+            config["prove_ms"] = prove["ms_per_proof"]
+            config["prove_constraints"] = prove["constraints"]
+            config["prove_stage_ms"] = prove["stage_ms"]
+            config["prove_scaling"] = prove["scaling"]
         line = {
-            "metric": METRIC, "value": world * n * args.steps / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": pts_per_step * args.steps / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 (GF(2^233) carry-less arithmetic on 8x32-bit limbs; Fr 8x32-bit Montgomery)",
             "data": "synthetic",
-            "config": {"workload": f"msm 2^{args.lg} points per GPU, sect233k1, uniform Fr scalars, SRS resident in HBM",
-                       "window_bits": st["window_bits"], "windows": st["windows"],
-                       "precomputed_tables": bool(st["tables"]),
-                       "rounds": [st["rounds_main"], st["rounds_a"], st["rounds_b"]],
-                       "l2": "per-step working set (sort keys, ping-pong point buffers, prefix products: >1 GB at 2^20) exceeds the 126 MB L2",
-                       "parallelism": f"point-range sharding x{world}, NCCL all-gather of 64-byte partial sums, fold on every rank" if world > 1 else "single GPU",
-                       "stage_ms": {"recode_sort": st["ms_recode_sort"], "accumulate": st["ms_accumulate"],
-                                    "reduce": st["ms_reduce"], "tail": st["ms_tail"]}},
-            "e2e": {"value": world * n * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": n * 32,
-                    "d2h_bytes_per_step": 30 + st["windows"] * st["window_bits"] * 64, "ms_per_step": 1e3 * dt_e2e / args.steps},
-            "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "k_pass2<16,2> (round 0 of the bucket accumulation)",
-                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": k_adds * PASS2_DRAM_BYTES_PER_ADD_NCU, "peak_source": which,
-                         "launch_ms": k_ms, "adds_per_launch": k_adds, "bytes_per_add": PASS2_BYTES_PER_ADD,
-                         "note": "integer-issue bound, not HBM bound: see int_issue"},
-            "int_issue": {"achieved": alu, "peak": ALU_PIPE_PEAK, "unit": "ALU-pipe thread-instr/s", "frac": alu / ALU_PIPE_PEAK,
-                          "instr_per_add": PASS2_ALU_INSTR_PER_ADD,
-                          "peak_source": "measured LOP3 issue rate, profiles/r1_pipe_rates.json; IMAD.WIDE counted as one ALU-pipe slot (profiles/README.md)"},
+            "config": config,
+            "e2e": {"value": pts_per_step * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": batch * n * 32,
+                    "d2h_bytes_per_step": batch * (30 + st["windows"] * st["window_bits"] * 64), "ms_per_step": 1e3 * dt_e2e / args.steps},
+            "gpu_launches": launches_per_msm * batch * args.steps,
+            "roofline": {"bound": "integer issue (ALU + FMA-heavy pipes share one issue port; not HBM, not tensor)",
+                         "kernel": kernel, "achieved": port, "peak": ISSUE_PORT_PEAK, "unit": "thread-instr/s",
+                         "frac": port / ISSUE_PORT_PEAK, "instr_per_add": instr_per_add,
+                         "launch_ms": k_ms, "adds_per_launch": k_adds,
+                         "peak_source": "measured on this pool's B200: LOP3 alone and every IMAD.WIDE + k LOP3 mix stop at "
+                                        "smsp__issue_active = 50 % (profiles/r2c_ncu_pipebench2_raw.csv)",
+                         "traffic": k_adds * dram_per_add,
+                         "hbm_view": {"achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak,
+                                      "bytes_per_add": bytes_per_add, "peak_source": which}},
             "cpu_baseline": {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"2^{lg_s} of the same SRS points, oracle k233_msm (per-point tau-adic width-4 TNAF scalar mul + sum, curve.rs:141-158), "
-                                       f"{cdt:.2f} s, result equal to the GPU's"},
+                             "sample": f"one MSM of the workload: 2^{lg_s} of the same SRS points, oracle k233_msm (per-point tau-adic width-4 TNAF "
+                                       f"scalar mul + sum, curve.rs:141-158), {cdt:.2f} s, result equal to the GPU's"},
             "clocks": clocks,
-            "device_ms_per_step": st["ms_device"],
+            "device_ms_per_msm": st["ms_device"],
             "prove": prove,
         }
         print(json.dumps(line))
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.dev_free(d_sc)
+    for d in d_sc:
+        ctx.dev_free(d)
     ctx.close()
     return 0
 
