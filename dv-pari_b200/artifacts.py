@@ -20,7 +20,7 @@ def _bind():
     L.dvp_fr_from_be32_mod_order.argtypes = [vp, sz, vp]
     L.dvp_sp1_public_input.argtypes = [C.c_uint64, vp]
     L.dvp_r1cs_dump_sizes.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz * 3), C.POINTER(sz)]
-    L.dvp_r1cs_dump_parse.argtypes = [vp, sz, vp, vp, vp, vp]
+    L.dvp_r1cs_dump_parse.argtypes = [vp, sz, sz, sz, C.POINTER(sz * 3), vp, vp, vp, vp]
     L.dvp_fftree_file_sections.argtypes = [vp, sz, sz, vp, vp]
     L.dvp_fftree_file_leaves.argtypes = [vp, sz, sz, C.POINTER(sz), vp]
     L.dvp_fftree_file_matrices.argtypes = [vp, sz, sz, C.c_int, C.POINTER(sz), vp]
@@ -84,7 +84,10 @@ def load_sparse_r1cs_from_file(path, num_public):
     coeff = [np.zeros(max(1, nnz[w]), dtype=np.uint32) for w in range(3)]
     coeffs = np.zeros((max(1, nc.value), 4), dtype=np.uint64)
     arr = lambda grp: (C.c_void_p * 3)(*[x.ctypes.data for x in grp])
-    _ck(L.dvp_r1cs_dump_parse(_ptr(raw), raw.size, arr(rowptr), arr(wire), arr(coeff), _ptr(coeffs)))
+    _ck(L.dvp_r1cs_dump_parse(_ptr(raw), raw.size, nc.value, nr.value, C.byref(nnz), arr(rowptr), arr(wire), arr(coeff),
+                              _ptr(coeffs)), "R1CS dump changed between the two passes")
+    # rows.next_power_of_two() (gnark_r1cs.rs:291); the smallest domain the library builds has n = 2 (a circuit of
+    # one row pads to two rows instead of the reference's one: extra rows are zero rows, the proof format is unchanged)
     n = 2
     while n < nr.value:
         n *= 2

@@ -150,37 +150,54 @@ int dvp_r1cs_dump_sizes(const uint8_t *buf, size_t len, size_t *ncoeffs, size_t 
 }
 
 // Second pass: fill the CSR arrays (rowptr[w]: nrows + 1, wire[w] / coeff[w]: nnz[w]) and the coefficient table.
-int dvp_r1cs_dump_parse(const uint8_t *buf, size_t len, uint32_t *const rowptr[3], uint32_t *const wire[3],
-                        uint32_t *const coeff[3], uint64_t *coeffs_mont) {
-    if (!buf || !rowptr || !wire || !coeff || !coeffs_mont) return DVP_ERR_BAD_ARG;
+// The capacities are the sizes the first pass reported; the walk is validated again (every read against len, every
+// write against the capacities), so a buffer that changed or is truncated since dvp_r1cs_dump_sizes is an error, not an
+// out-of-bounds access.
+int dvp_r1cs_dump_parse(const uint8_t *buf, size_t len, size_t ncoeffs, size_t nrows, const size_t nnz[3],
+                        uint32_t *const rowptr[3], uint32_t *const wire[3], uint32_t *const coeff[3],
+                        uint64_t *coeffs_mont) {
+    if (!buf || !nnz || !rowptr || !wire || !coeff || !coeffs_mont) return DVP_ERR_BAD_ARG;
+    for (int w = 0; w < 3; w++)
+        if (!rowptr[w] || (nnz[w] && (!wire[w] || !coeff[w]))) return DVP_ERR_BAD_ARG;
     size_t pos = 0;
     uint32_t nc, nr;
+    if (len < 4) return DVP_ERR_BAD_ARG;
     memcpy(&nc, buf + pos, 4);
     pos += 4;
+    if (nc != ncoeffs || (size_t)nc * 32 > len - pos) return DVP_ERR_BAD_ARG;
     for (uint32_t i = 0; i < nc; i++) {
         const fr m = fr_from_be32_mod(buf + pos);
         memcpy(coeffs_mont + 4 * (size_t)i, m.v, 32);
         pos += 32;
     }
+    if (len - pos < 4) return DVP_ERR_BAD_ARG;
     memcpy(&nr, buf + pos, 4);
     pos += 4;
-    uint32_t fill[3] = {0, 0, 0};
+    if (nr != nrows) return DVP_ERR_BAD_ARG;
+    size_t fill[3] = {0, 0, 0};
     for (int w = 0; w < 3; w++) rowptr[w][0] = 0;
     for (uint32_t r = 0; r < nr; r++) {
         uint32_t cnt[3];
+        if (len - pos < 12) return DVP_ERR_BAD_ARG;
         memcpy(cnt, buf + pos, 12);
         pos += 12;
         for (int w = 0; w < 3; w++) {
+            if ((size_t)cnt[w] > nnz[w] - fill[w] || (size_t)cnt[w] * 8 > len - pos) return DVP_ERR_BAD_ARG;
             for (uint32_t t = 0; t < cnt[w]; t++) {
+                uint32_t cid;
                 memcpy(&wire[w][fill[w]], buf + pos, 4);
-                memcpy(&coeff[w][fill[w]], buf + pos + 4, 4);
+                memcpy(&cid, buf + pos + 4, 4);
+                if (cid >= nc) return DVP_ERR_BAD_ARG;
+                coeff[w][fill[w]] = cid;
                 pos += 8;
                 fill[w]++;
             }
-            rowptr[w][r + 1] = fill[w];
+            rowptr[w][r + 1] = (uint32_t)fill[w];
         }
     }
-    return pos <= len ? DVP_OK : DVP_ERR_BAD_ARG;
+    for (int w = 0; w < 3; w++)
+        if (fill[w] != nnz[w]) return DVP_ERR_BAD_ARG;
+    return DVP_OK;
 }
 
 // ---- FFTR tree files (tree_io.rs).  The blobs are ark-serialize "compressed" output: a Vec<T> / BinaryTree<T> is a

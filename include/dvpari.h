@@ -264,8 +264,9 @@ int dvp_blake3(const uint8_t *data, size_t len, uint8_t out32[32]);
 int dvp_transcript_alpha(const uint8_t commit_p30[30], const uint64_t *public_mont, size_t k, uint64_t alpha_mont[4]);
 /* load_sparse_r1cs_from_file in two passes over the file image: sizes, then CSR per matrix + coefficient table */
 int dvp_r1cs_dump_sizes(const uint8_t *buf, size_t len, size_t *ncoeffs, size_t *nrows, size_t nnz[3], size_t *max_wire);
-int dvp_r1cs_dump_parse(const uint8_t *buf, size_t len, uint32_t *const rowptr[3], uint32_t *const wire[3],
-                        uint32_t *const coeff[3], uint64_t *coeffs_mont);
+int dvp_r1cs_dump_parse(const uint8_t *buf, size_t len, size_t ncoeffs, size_t nrows, const size_t nnz[3],
+                        uint32_t *const rowptr[3], uint32_t *const wire[3], uint32_t *const coeff[3],
+                        uint64_t *coeffs_mont); /* sizes = what dvp_r1cs_dump_sizes reported; re-validated */
 /* FFTree file image: the section table of the node `depth` subtrees below the root (offsets absolute in the image,
  * absent section = length 0) -- read_fftree_from_slice's header walk, src/tree_io.rs:243-261 */
 int dvp_fftree_file_sections(const uint8_t *file, size_t len, size_t depth, uint64_t off[13], uint64_t slen[13]);

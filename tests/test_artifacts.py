@@ -131,6 +131,17 @@ def test_r1cs_dump_parser_survives_mutations(tmp_path):
         coeff = [np.zeros(max(1, nnz[w]), dtype=np.uint32) for w in range(3)]
         coeffs = np.zeros((max(1, nc.value), 4), dtype=np.uint64)
         arr = lambda grp: (C.c_void_p * 3)(*[x.ctypes.data for x in grp])
-        assert L.dvp_r1cs_dump_parse(addr, len(data), arr(rowptr), arr(wire), arr(coeff), dvpari._ptr(coeffs)) == 0
+        assert L.dvp_r1cs_dump_parse(addr, len(data), nc.value, nr.value, C.byref(nnz), arr(rowptr), arr(wire), arr(coeff),
+                                     dvpari._ptr(coeffs)) == 0
         assert all(int(rowptr[w][-1]) == nnz[w] for w in range(3))
+        # the second pass validates the walk itself: a shorter image, or sizes that are not this image's, are errors
+        # (never an out-of-bounds read or write; the arrays above are exactly as large as the first pass said)
+        if nnz[0] > 0:
+            less = (C.c_size_t * 3)(nnz[0] - 1, nnz[1], nnz[2])
+            assert L.dvp_r1cs_dump_parse(addr, len(data), nc.value, nr.value, C.byref(less), arr(rowptr), arr(wire),
+                                         arr(coeff), dvpari._ptr(coeffs)) != 0
+        if len(data) > 8:
+            short = guard.put(data[:len(data) - 5])
+            assert L.dvp_r1cs_dump_parse(short, len(data) - 5, nc.value, nr.value, C.byref(nnz), arr(rowptr), arr(wire),
+                                         arr(coeff), dvpari._ptr(coeffs)) != 0
     assert ok and err
