@@ -1178,6 +1178,53 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// The same tree for a level with FEW segments (level B: 15 sums per virtual window): the additions of a tree level are
+// dealt to the warps of the block and every addition is done by a whole warp with the cooperative multiplier
+// (gf233_warp.cuh: 14 products of 0.37 us instead of 1.9), the final conversion to affine likewise.  A level of the
+// tree costs ~6 us per addition and warp instead of ~29 us: 7 levels over 128 points in ~75 us instead of ~180.
+struct GfMulWarp {
+    const WarpMulCtx &c;
+    __device__ __forceinline__ gf operator()(const gf &a, const gf &b) const { return gf_mul_warp(a, b, c); }
+};
+__global__ void __launch_bounds__(512)
+    k_ld_tree_warp(const LdPt *__restrict__ src, const uint32_t *__restrict__ ent, const uint32_t *__restrict__ seg_start,
+                   const uint32_t *__restrict__ seg_len, AffPt *__restrict__ dst, const gf *__restrict__ tabs) {
+    extern __shared__ __align__(16) unsigned char sh_raw[];
+    LdPt *sh = reinterpret_cast<LdPt *>(sh_raw); // the points of the segment, halved level by level
+    const uint32_t s = blockIdx.x, t = threadIdx.x, warp = t >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t start = seg_start[s], len = seg_len[s];
+    for (uint32_t i = t; i < len; i += blockDim.x) ld_store(&sh[i], ld_load(src + ent[start + i]));
+    __syncthreads();
+    const WarpMulCtx wc = warp_mul_ctx();
+    const GfMulWarp mul{wc};
+    for (uint32_t n = len; n > 1; n = (n + 1) >> 1) {
+        // pairs (2i, 2i+1) -> i; every warp takes pairs i = warp, warp + nwarps, ...; the operands are read by all its
+        // lanes (warp-uniform), the result is kept in registers until every warp has read its inputs
+        LdPt acc[4]; // at most 4 pairs per warp and level (len <= 8 * nwarps)
+        uint32_t cnt = 0;
+        for (uint32_t i = warp; 2 * i < n; i += nwarps, cnt++) {
+            LdPt a = ld_load(&sh[2 * i]);
+            if (2 * i + 1 < n) a = ld_add_t(a, ld_load(&sh[2 * i + 1]), mul);
+            acc[cnt & 3] = a;
+        }
+        __syncthreads();
+        cnt = 0;
+        for (uint32_t i = warp; 2 * i < n; i += nwarps, cnt++)
+            if ((t & 31) == 0) ld_store(&sh[i], acc[cnt & 3]);
+        __syncthreads();
+    }
+    if (t < 32) {
+        const LdPt r = len ? ld_load(&sh[0]) : ld_infinity();
+        AffPt o = pt_inf();
+        if (!gf_is_zero(r.Z)) {
+            const gf zi = gf_inv_tab_warp(r.Z, tabs, wc);
+            o.x = gf_mul_warp(r.X, zi, wc);
+            o.y = gf_mul_warp(r.Y, gf_sqr(zi), wc);
+        }
+        if (t == 0) pt_store(dst + s, o);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
@@ -1785,6 +1832,16 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     }
     bounds[NL] = (uint32_t)NB;
 
+    // The persistent kernel wins between 2^17 and 2^21 points (2^18: 3.00 against 3.17 ms, 2^19: 4.67 / 4.95, 2^20: 7.72 /
+    // 7.92, 2^21: 13.60 / 13.72; 23 launches instead of 87-155); below, a few hundred additions per round do not pay for
+    // grid barriers (2^12: 1.18 / 1.10), above, the separate large launches keep two blocks of one lane on every SM
+    // (2^22: 24.4 / 23.4 ms).
+    const bool persistent_any =
+        acc_capacity > 0 && (use_accumulate == 2 || (use_accumulate == 1 && n >= ((size_t)1 << 17) && n < ((size_t)3 << 20)));
+    // With the persistent kernel the host needs nothing from the sort: the rounds are counted on the device and the
+    // scratch is sized from upper bounds (every entry in one lane), so the MSM is enqueued without a read-back in the
+    // middle.  (Larger MSMs keep the exact sizes: twice the scratch would be gigabytes.)
+    const bool nosync = persistent_any && !timing && total <= ((size_t)1 << 25);
     cudaStream_t st = stream;
     cudaEventRecord(ev_t0, st);
     if (timing) cudaEventRecord(ev[0], st);
@@ -1803,16 +1860,18 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
                                                     uniform ? (uint32_t)tab->offset : 0u,
                                                     uniform ? (uint32_t)tab->stride : 0u, cursor_all.as<uint32_t>(),
                                                     entries.as<uint32_t>());
-        CK(cudaMemcpyAsync(lane_info.as<uint32_t>() + 32, bounds, (NL + 1) * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync(lane_info.p, 0, 32 * 4, st));
-        k_lane_info<<<dim3(std::max(1u, std::min(148u, cdiv(NB / NL, 1024))), NL), 256, 0, st>>>(
-            d_len_all, d_start_all, lane_info.as<uint32_t>() + 32, lane_info.as<uint32_t>());
+        if (!nosync) {
+            CK(cudaMemcpyAsync(lane_info.as<uint32_t>() + 32, bounds, (NL + 1) * 4, cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(lane_info.p, 0, 32 * 4, st));
+            k_lane_info<<<dim3(std::max(1u, std::min(148u, cdiv(NB / NL, 1024))), NL), 256, 0, st>>>(
+                d_len_all, d_start_all, lane_info.as<uint32_t>() + 32, lane_info.as<uint32_t>());
+            CK(cudaMemcpyAsync(h_lane, lane_info.p, 2 * NL * 4, cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h_lane, lane_info.p, 2 * NL * 4, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaEventRecord(ev_recode, st));
-    unsigned long long launches = 7;
-    CK(cudaStreamSynchronize(st)); // the one read-back: entries and longest bucket per lane size the rounds
+    unsigned long long launches = nosync ? 6 : 7;
+    if (!nosync) CK(cudaStreamSynchronize(st)); // the read-back: entries and longest bucket per lane size the rounds
     MsmStats stt;
     stt.window_bits = c;
     stt.windows = W;
@@ -1820,9 +1879,9 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     stt.tables = uniform ? 1 : 0;
     for (int l = 0; l < NL; l++) {
         Part &p = part[l];
-        p.total = ((const uint32_t *)h_lane)[2 * l];
-        p.maxlen = ((const uint32_t *)h_lane)[2 * l + 1];
-        stt.adds_total += p.total;
+        p.total = nosync ? total : ((const uint32_t *)h_lane)[2 * l];
+        p.maxlen = nosync ? (uint32_t)std::min<size_t>(total, 0xffffffffu) : ((const uint32_t *)h_lane)[2 * l + 1];
+        if (!nosync) stt.adds_total += p.total;
         MsmLane &L = lanes[l];
         const size_t nseg_max = std::max<size_t>(p.nseg, std::max(p.nseg_a, p.nseg_b)) + 1;
         const size_t ent_max = std::max<size_t>(p.total, std::max(p.nent_a, p.nent_b));
@@ -1853,12 +1912,6 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     // a reduction level with more points than this starts with batched-affine rounds: large MSMs are throughput-bound
     // (5 instead of 15 multiplications per addition), small ones latency-bound (one launch instead of a round's six)
     const size_t ld_max = ld_tree_max ? ld_tree_max : (n >= (1u << 21) ? (size_t)1 << 13 : (size_t)1 << 16);
-    // The persistent kernel wins between 2^17 and 2^21 points (2^18: 3.00 against 3.17 ms, 2^19: 4.67 / 4.95, 2^20: 7.72 /
-    // 7.92, 2^21: 13.60 / 13.72; 23 launches instead of 87-155); below, a few hundred additions per round do not pay for
-    // grid barriers (2^12: 1.18 / 1.10), above, the separate large launches keep two blocks of one lane on every SM
-    // (2^22: 24.4 / 23.4 ms).
-    const bool persistent_any =
-        acc_capacity > 0 && (use_accumulate == 2 || (use_accumulate == 1 && n >= ((size_t)1 << 17) && n < ((size_t)3 << 20)));
     if (timing) cudaEventRecord(ev[3], st);
     // ---- per lane: accumulate buckets, then the two reduction levels into this lane's slice of hb
     for (int l = 0; l < NL; l++) {
@@ -1939,8 +1992,12 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
             k_gen_level_b<<<cdiv(p.nent_b, 256), 256, 0, L.stream>>>(p.vn, lr, lm, L.ents2.as<uint32_t>());
             k_gen_segs_b<<<cdiv(p.nseg_b + 1, 256), 256, 0, L.stream>>>(p.vn, lr, lm, d_start, d_len);
             tree.pb(PC_MISC);
-            k_ld_tree<true, true><<<p.nseg_b, tthr, tthr * sizeof(LdPt), L.stream>>>(
-                L.rc.p, L.ents2.as<uint32_t>(), d_start, d_len, hb.as<AffPt>() + (size_t)p.v0 * cv, msqr_tabs.as<gf>());
+            if (2 * tthr <= 8 * 16) // a segment has at most 2 tthr points: 4 pairs per warp and level with 16 warps
+                k_ld_tree_warp<<<p.nseg_b, 512, 2 * tthr * sizeof(LdPt), L.stream>>>(
+                    L.rc.as<LdPt>(), L.ents2.as<uint32_t>(), d_start, d_len, hb.as<AffPt>() + (size_t)p.v0 * cv, msqr_tabs.as<gf>());
+            else
+                k_ld_tree<true, true><<<p.nseg_b, tthr, tthr * sizeof(LdPt), L.stream>>>(
+                    L.rc.p, L.ents2.as<uint32_t>(), d_start, d_len, hb.as<AffPt>() + (size_t)p.v0 * cv, msqr_tabs.as<gf>());
             tree.pe();
             L.launches += 6;
             CK(cudaGetLastError());
@@ -1987,6 +2044,16 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     }
     cudaEventRecord(ev_t1, st);
     CK(cudaStreamSynchronize(st));
+    if (persistent_any) {
+        int rmax = 0;
+        unsigned long long adds = 0;
+        for (int l = 0; l < NL; l++) {
+            rmax = std::max(rmax, (int)h_acc[(2 * l) * 4 + 1]);
+            adds += h_acc[(2 * l) * 4 + 3];
+        }
+        stt.rounds_main = rmax;
+        if (nosync) stt.adds_total = adds;
+    }
     if (persistent_any)
         for (int l = 0; l < NL; l++)
             for (int k = 0; k < 2; k++)

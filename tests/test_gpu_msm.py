@@ -181,3 +181,79 @@ def test_msm_with_precomputed_tables(ctx, oracle):
         ctx.set("msm_tables", 1)
         ctx.set("msm_tables_min", 1 << 15)
         ctx.srs_free(2)
+
+
+def test_msm_beside_saturating_work_on_the_same_gpu(oracle):
+    """Scheduling stress (k_plan look-back): MSMs whose kernels wait on each other across blocks -- the
+    persistent k_accumulate (grid barriers, cooperative launch) at 2^17 points and the ticketed k_plan look-back of the
+    separate-launch path at 2^15 and 2^22/8 -- must give the same bytes while two other contexts keep the same GPU
+    saturated with extends and with MSMs of their own.  A scheduling assumption that does not hold shows up as a
+    time-out (the barriers give up after 4 s and the call returns an error) or as a wrong result, not as a hang."""
+    import threading
+
+    O = oracle
+    G = O.generator()
+    ctxs = [dvpari.Context(0) for _ in range(3)]
+    try:
+        sizes = [1 << 17, 1 << 15, 1 << 19]
+        jobs = []
+        for i, n in enumerate(sizes):
+            ctx = ctxs[i % 2]
+            slot = i
+            ctx.srs_random(slot, n, 40 + i)
+            sc = dvpari.random_fr_mont(n, 50 + i)
+            d = ctx.dev_alloc(n * 32)
+            ctx.dev_upload(d, sc)
+            ref = ctx.multi_scalar_mul_device(d, n, slot)  # quiet GPU
+            jobs.append((ctx, slot, d, n, ref))
+        # one of the references against the oracle (the others are compared with themselves under load)
+        ctx0, slot0, d0, n0, ref0 = jobs[1]
+        pts, bad = O.decode_batch(ctx0.srs_read(slot0, 0, n0))
+        assert bad < 0 and ref0 == O.pt_encode(O.msm(dvpari.random_fr_mont(n0, 51), pts, 0))
+        stop = threading.Event()
+        errors = []
+
+        def extend_load():
+            try:
+                dom = dvpari.Domain(ctxs[2], 19)
+                dd = ctxs[2].dev_alloc(3 * (1 << 18) * 32)
+                ctxs[2].dev_upload(dd, dvpari.random_fr_mont(3 << 18, 7))
+                while not stop.is_set():
+                    dom.extend_device(dd, 3)
+                ctxs[2].dev_free(dd)
+                dom.close()
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        def msm_load(job, reps):
+            ctx, slot, d, n, ref = job
+            try:
+                for _ in range(reps):
+                    got = ctx.multi_scalar_mul_device(d, n, slot)
+                    if got != ref:
+                        errors.append(AssertionError(f"MSM of 2^{n.bit_length() - 1} points changed under load"))
+                        return
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        t_ext = threading.Thread(target=extend_load)
+        t_ext.start()
+        # contexts 0 and 1 run their MSMs at the same time (two engines, four persistent kernels wanting the grid)
+        ts = [threading.Thread(target=msm_load, args=(jobs[0], 12)), threading.Thread(target=msm_load, args=(jobs[1], 25))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        ts = [threading.Thread(target=msm_load, args=(jobs[2], 6)), threading.Thread(target=msm_load, args=(jobs[1], 25))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        stop.set()
+        t_ext.join()
+        assert not errors, errors[0]
+        for ctx, slot, d, n, ref in jobs:
+            ctx.dev_free(d)
+    finally:
+        for c in ctxs:
+            c.close()
