@@ -217,10 +217,15 @@ __device__ __forceinline__ gf gf_mul_dev(const gf &a, const gf &b) {
     return gf_reduce(c);
 }
 #endif
+} // namespace dvp
+#include "gf233_mul2.cuh" // gf_mul_dev2: the same product from 32-bit IMAD only (two streams), the device path of gf_mul
+namespace dvp {
 
 __host__ __device__ __forceinline__ gf gf_mul(const gf &a, const gf &b) {
-#ifdef __CUDA_ARCH__
-    return gf_mul_dev(a, b);
+#if defined(__CUDA_ARCH__) && defined(DVP_GF_MUL_WIDE)
+    return gf_mul_dev(a, b); // the IMAD.WIDE form, kept for A/B runs (make NVFLAGS+=-DDVP_GF_MUL_WIDE)
+#elif defined(__CUDA_ARCH__)
+    return gf_mul_dev2(a, b);
 #else
     return gf_mul_portable(a, b);
 #endif

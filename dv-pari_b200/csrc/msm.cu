@@ -494,6 +494,72 @@ __global__ void __launch_bounds__(128)
     if ((threadIdx.x & 31) == 0) pt_store(&dst[de.z], r);
 }
 
+// ---- operand staging for the pass-2 loops: cp.async (LDGSTS) gathers the NEXT addition's two points, its prefix
+// product and the descriptor after it into the thread's own shared-memory slots while the current addition's four
+// products run.  No register is live across the out-of-line multiplier calls for it (a prefetch into registers is
+// spilled around the calls, and the spill store waits for the load), and with 4 warps per scheduler every warp that
+// sits on a global load is a quarter of the issue slots (ncu: 12 % of the warp samples were long-scoreboard stalls).
+// Two slot sets by parity: the copies of addition k-1 never land in the set addition k is read from.
+constexpr int STG_CHUNKS = 11;                       // 16-byte chunks: 4 + 4 (points), 2 (prefix), 1 (descriptor)
+constexpr size_t STG_BYTES = 2 * STG_CHUNKS * 256 * sizeof(uint4); // per block of 256 threads
+__device__ __forceinline__ void cp_async16(uint4 *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// slot c of set b of thread tid (chunk-major: a warp's 16-byte accesses to one chunk are contiguous, conflict-free)
+#define STG_SLOT(stage, b, c, tid) ((stage) + ((b) * STG_CHUNKS + (c)) * 256 + (tid))
+__device__ __forceinline__ void stage_issue(uint4 *stage, int b, uint32_t tid, const AffPt *src, const uint4 &de,
+                                            const gf *prefix_t, const uint4 *desc_next) {
+    const uint4 *a = reinterpret_cast<const uint4 *>(&src[de.x & 0x7fffffffu]);
+    const uint4 *c = reinterpret_cast<const uint4 *>(&src[de.y & 0x7fffffffu]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        cp_async16(STG_SLOT(stage, b, i, tid), a + i);
+        cp_async16(STG_SLOT(stage, b, 4 + i, tid), c + i);
+    }
+    if (prefix_t) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(prefix_t);
+        cp_async16(STG_SLOT(stage, b, 8, tid), q);
+        cp_async16(STG_SLOT(stage, b, 9, tid), q + 1);
+    }
+    if (desc_next) cp_async16(STG_SLOT(stage, b, 10, tid), desc_next);
+    cp_async_commit();
+}
+// pass 1 needs the x coordinates only (slots 0-1 and 4-5)
+__device__ __forceinline__ void stage_issue_x(uint4 *stage, int b, uint32_t tid, const AffPt *src, const uint4 &de,
+                                              const uint4 *desc_next) {
+    const uint4 *a = reinterpret_cast<const uint4 *>(&src[de.x & 0x7fffffffu].x);
+    const uint4 *c = reinterpret_cast<const uint4 *>(&src[de.y & 0x7fffffffu].x);
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        cp_async16(STG_SLOT(stage, b, i, tid), a + i);
+        cp_async16(STG_SLOT(stage, b, 4 + i, tid), c + i);
+    }
+    if (desc_next) cp_async16(STG_SLOT(stage, b, 10, tid), desc_next);
+    cp_async_commit();
+}
+__device__ __forceinline__ gf stage_gf(const uint4 *stage, int b, int c, uint32_t tid) {
+    const uint4 u = *STG_SLOT(stage, b, c, tid), v = *STG_SLOT(stage, b, c + 1, tid);
+    gf r;
+    r.v[0] = u.x; r.v[1] = u.y; r.v[2] = u.z; r.v[3] = u.w;
+    r.v[4] = v.x; r.v[5] = v.y; r.v[6] = v.z; r.v[7] = v.w;
+    return r;
+}
+__device__ __forceinline__ void stage_points(const uint4 *stage, int b, uint32_t tid, const uint4 &de, AffPt &p1, AffPt &p2) {
+    p1.x = stage_gf(stage, b, 0, tid);
+    p1.y = stage_gf(stage, b, 2, tid);
+    p2.x = stage_gf(stage, b, 4, tid);
+    p2.y = stage_gf(stage, b, 6, tid);
+    if (de.x >> 31) p1.y = gf_add(p1.y, p1.x); // entry = index | negate << 31 (fetch_entry)
+    if (de.y >> 31) p2.y = gf_add(p2.y, p2.x);
+}
+// the additions that need no field product: kind 2 -> P1, 3 -> P2, 4 -> infinity
+__device__ __forceinline__ AffPt pair_degenerate(const AffPt &p1, const AffPt &p2, int kind) {
+    return kind == 2 ? p1 : kind == 3 ? p2 : pt_inf();
+}
+
 // ------------------------------------------------------------------------------------------------
 // All tree rounds of a lane in ONE persistent kernel (cooperative launch: the grid is co-resident, one or two
 // blocks per SM).  A round is  plan | grid barrier | pass 1 -> inversion -> pass 2 | grid barrier:  the additions of a
@@ -524,6 +590,9 @@ struct AccArgs {
     int tiny_max;                   // a round of at most this many additions runs one warp per addition
 };
 constexpr int ACC_THREADS = 256;
+#ifndef ACC_MINB
+#define ACC_MINB 1
+#endif
 constexpr int ACC_MAX_ROUNDS = 48;
 constexpr int ACC_TIME_WORDS = 6 * (ACC_MAX_ROUNDS + 1) + 2; // [last] = kernel start
 
@@ -573,7 +642,8 @@ __device__ __forceinline__ bool acc_barrier(uint32_t *ctl, uint32_t &target) {
     return sh_abort == 0;
 }
 
-__global__ void __launch_bounds__(ACC_THREADS, 2) k_accumulate(const AccArgs A) {
+__global__ void __launch_bounds__(ACC_THREADS, ACC_MINB) k_accumulate(const AccArgs A) {
+    extern __shared__ uint4 stage[]; // STG_BYTES: the pass-2 operand slots
     __shared__ unsigned long long sh[ACC_THREADS / 32];
     __shared__ unsigned long long sh_base, sh_total;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -710,30 +780,25 @@ __global__ void __launch_bounds__(ACC_THREADS, 2) k_accumulate(const AccArgs A) 
             }
         } else if (base < ntasks) { // the whole warp or none of it
             gf acc = gf_one();
-            {
+            if (base + lane < ntasks) {
+                // operands staged one addition ahead like in pass 2: a prefetch into registers would be spilled around
+                // the out-of-line product, and the spill store waits for the load
                 uint32_t t = base + lane;
-                uint4 de = make_uint4(0, 0, 0, 0);
-                gf x1 = gf_zero(), x2 = gf_zero();
-                if (t < ntasks) {
-                    de = __ldcg(&A.desc[t]);
-                    x1 = gf_load_cg(&cur[de.x & 0x7fffffffu].x);
-                    x2 = gf_load_cg(&cur[de.y & 0x7fffffffu].x);
-                }
+                uint4 de = __ldcg(&A.desc[t]);
+                stage_issue_x(stage, 0, tid, cur, de, (B > 1 && t + 32 < ntasks) ? &A.desc[t + 32] : nullptr);
 #pragma unroll 1
-                for (uint32_t k = 0; k < B; k++) {
-                    if (t >= ntasks) break;
-                    const uint32_t tn = t + 32;
-                    uint4 den = make_uint4(0, 0, 0, 0);
-                    gf x1n = gf_zero(), x2n = gf_zero();
-                    if (k + 1 < B && tn < ntasks) {
-                        den = __ldcg(&A.desc[tn]);
-                        x1n = gf_load_cg(&cur[den.x & 0x7fffffffu].x);
-                        x2n = gf_load_cg(&cur[den.y & 0x7fffffffu].x);
+                for (uint32_t k = 0; k < B && t < ntasks; k++, t += 32) {
+                    cp_async_wait_all();
+                    const gf x1 = stage_gf(stage, k & 1, 0, tid), x2 = stage_gf(stage, k & 1, 4, tid);
+                    const uint4 de0 = de;
+                    if (k + 1 < B && t + 32 < ntasks) {
+                        de = *STG_SLOT(stage, k & 1, 10, tid);
+                        stage_issue_x(stage, (k + 1) & 1, tid, cur, de, (k + 2 < B && t + 64 < ntasks) ? &A.desc[t + 64] : nullptr);
                     }
                     gf d = gf_add(x1, x2);
                     if (gf_is_zero(x1) | gf_is_zero(x2)) d = gf_one();
                     else if (gf_is_zero(d)) {
-                        const AffPt p1 = fetch_entry_cg(cur, de.x), p2 = fetch_entry_cg(cur, de.y);
+                        const AffPt p1 = fetch_entry_cg(cur, de0.x), p2 = fetch_entry_cg(cur, de0.y);
                         d = gf_eq(p1.y, p2.y) ? x1 : gf_one();
                     }
                     if (B > 1) {
@@ -742,10 +807,6 @@ __global__ void __launch_bounds__(ACC_THREADS, 2) k_accumulate(const AccArgs A) 
                     } else {
                         acc = d; // a chain of one: its prefix is 1
                     }
-                    t = tn;
-                    de = den;
-                    x1 = x1n;
-                    x2 = x2n;
                 }
             }
             if (prof) A.times[6 * r + 2] = acc_now();
@@ -767,30 +828,41 @@ __global__ void __launch_bounds__(ACC_THREADS, 2) k_accumulate(const AccArgs A) 
                 for (int k = 4; k >= 0; k--) inv = gf_mul_call(inv, S[k]);
             }
             if (prof) A.times[6 * r + 3] = acc_now();
-            // ---- pass 2: the same additions backwards
+            // ---- pass 2: the same additions backwards, operands staged one addition ahead (stage_issue)
+            if (base + lane < ntasks) {
+                int k = (int)min(B - 1, (ntasks - 1 - base - lane) >> 5); // the thread's last task
+                uint32_t t = base + (uint32_t)k * 32 + lane;
+                uint4 de = __ldcg(&A.desc[t]);
+                stage_issue(stage, k & 1, tid, cur, de, B > 1 ? &A.prefix[t] : nullptr, k > 0 ? &A.desc[t - 32] : nullptr);
 #pragma unroll 1
-            for (int k = (int)B - 1; k >= 0; k--) {
-                const uint32_t t = base + (uint32_t)k * 32 + lane;
-                if (t >= ntasks) continue;
-                const uint4 de = __ldcg(&A.desc[t]);
-                const AffPt p1 = fetch_entry_cg(cur, de.x), p2 = fetch_entry_cg(cur, de.y);
-                gf d;
-                const int kind = pair_classify(p1, p2, d);
-                gf dinv = inv;
-                if (B > 1) {
-                    dinv = gf_mul_call(inv, gf_load_cg(&A.prefix[t]));
-                    if (k) inv = gf_mul_call(inv, d);
+                for (; k >= 0; k--, t -= 32) {
+                    cp_async_wait_all();
+                    AffPt p1, p2;
+                    stage_points(stage, k & 1, tid, de, p1, p2);
+                    gf dinv = inv;
+                    if (B > 1) dinv = stage_gf(stage, k & 1, 8, tid);
+                    const uint32_t dz = de.z;
+                    if (k > 0) {
+                        de = *STG_SLOT(stage, k & 1, 10, tid);
+                        stage_issue(stage, (k - 1) & 1, tid, cur, de, &A.prefix[t - 32], k > 1 ? &A.desc[t - 64] : nullptr);
+                    }
+                    gf d;
+                    const int kind = pair_classify(p1, p2, d);
+                    if (B > 1) {
+                        dinv = gf_mul_call(inv, dinv);
+                        if (k) inv = gf_mul_call(inv, d);
+                    }
+                    AffPt q;
+                    if (kind >= 2) {
+                        q = pair_degenerate(p1, p2, kind);
+                    } else {
+                        gf lam = gf_mul_call(kind == 1 ? p1.y : gf_add(p1.y, p2.y), dinv);
+                        if (kind == 1) lam = gf_add(lam, p1.x);
+                        q.x = gf_add(gf_add(gf_sqr(lam), lam), gf_add(p1.x, p2.x));
+                        q.y = gf_add(gf_add(gf_mul_call(lam, gf_add(p1.x, q.x)), q.x), p1.y);
+                    }
+                    pt_store(&out[dz], q);
                 }
-                AffPt q;
-                if (kind >= 2) {
-                    q = pair_finish(p1, p2, kind, dinv);
-                } else {
-                    gf lam = gf_mul_call(kind == 1 ? p1.y : gf_add(p1.y, p2.y), dinv);
-                    if (kind == 1) lam = gf_add(lam, p1.x);
-                    q.x = gf_add(gf_add(gf_sqr(lam), lam), gf_add(p1.x, p2.x));
-                    q.y = gf_add(gf_add(gf_mul_call(lam, gf_add(p1.x, q.x)), q.x), p1.y);
-                }
-                pt_store(&out[de.z], q);
             }
         }
         if (!acc_barrier(A.ctl, bar)) return;
@@ -871,25 +943,35 @@ template <int B, int MINB>
 __global__ void __launch_bounds__(256, MINB)
     k_pass2(const AffPt *__restrict__ src, const uint32_t *__restrict__ info, const uint4 *__restrict__ desc,
             const gf *__restrict__ prefix, const gf *__restrict__ thr_inv, AffPt *__restrict__ dst) {
+    extern __shared__ uint4 stage[];
     const uint32_t ntasks = info[1];
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t tid = threadIdx.x, gtid = blockIdx.x * blockDim.x + tid;
     const uint32_t lane = gtid & 31, warp = gtid >> 5;
     const uint32_t base = warp * (32u * B);
     if (base + lane >= ntasks) return;
     gf inv = gf_load(&thr_inv[gtid]);
+    int k = (int)min((uint32_t)(B - 1), (ntasks - 1 - base - lane) >> 5); // the thread's last task
+    uint32_t t = base + (uint32_t)k * 32 + lane;
+    uint4 de = desc[t];
+    stage_issue(stage, k & 1, tid, src, de, &prefix[t], k > 0 ? &desc[t - 32] : nullptr);
 #pragma unroll 1
-    for (int k = B - 1; k >= 0; k--) {
-        const uint32_t t = base + k * 32 + lane;
-        if (t >= ntasks) continue;
-        const uint4 de = desc[t];
-        const AffPt p1 = fetch_entry(src, de.x), p2 = fetch_entry(src, de.y);
+    for (; k >= 0; k--, t -= 32) {
+        cp_async_wait_all();
+        AffPt p1, p2;
+        stage_points(stage, k & 1, tid, de, p1, p2);
+        const gf pre = stage_gf(stage, k & 1, 8, tid);
+        const uint32_t dz = de.z;
+        if (k > 0) { // addition k-1 into the other set; its descriptor came with addition k
+            de = *STG_SLOT(stage, k & 1, 10, tid);
+            stage_issue(stage, (k - 1) & 1, tid, src, de, &prefix[t - 32], k > 1 ? &desc[t - 64] : nullptr);
+        }
         gf d;
         const int kind = pair_classify(p1, p2, d);
-        const gf dinv = gf_mul_call(inv, gf_load(&prefix[t]));
+        const gf dinv = gf_mul_call(inv, pre);
         if (k) inv = gf_mul_call(inv, d);
         AffPt r;
         if (kind >= 2) {
-            r = pair_finish(p1, p2, kind, dinv);
+            r = pair_degenerate(p1, p2, kind);
         } else {
             // chord / tangent: lambda = num/d (+ x1 for the tangent), see pair_finish
             gf lam = gf_mul_call(kind == 1 ? p1.y : gf_add(p1.y, p2.y), dinv);
@@ -897,7 +979,7 @@ __global__ void __launch_bounds__(256, MINB)
             r.x = gf_add(gf_add(gf_sqr(lam), lam), gf_add(p1.x, p2.x));
             r.y = gf_add(gf_add(gf_mul_call(lam, gf_add(p1.x, r.x)), r.x), p1.y);
         }
-        pt_store(&dst[de.z], r);
+        pt_store(&dst[dz], r);
     }
 }
 
@@ -1295,7 +1377,9 @@ int MsmEngine::init(cudaStream_t s) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         // (register budgets of 80 and 64 per thread -- 3 and 4 resident blocks -- were 10-35 % slower: spills)
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_accumulate, ACC_THREADS, 0) != cudaSuccess) occ = 0;
+        if (cudaFuncSetAttribute(k_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STG_BYTES) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_accumulate, ACC_THREADS, STG_BYTES) != cudaSuccess)
+            occ = 0;
         acc_capacity = coop ? (uint32_t)(sms * std::min(occ, 2)) : 0u;
     }
     k_build_msqr_tables<<<cdiv(MSQ_TABLES * MSQ_TABLE_ELEMS, 128), 128, 0, s>>>(msqr_tabs.as<gf>());
@@ -1430,12 +1514,16 @@ struct Tree {
         if (mark) cudaEventRecord(L.ev_k[0], st);
         pb(PC_PASS2);
         if (detour) hop(st, sb, 0);
+        // 88 KB of staging slots per block: above the 48 KB default, so the limit is raised (per device, cheap)
+        cudaFuncSetAttribute(k_pass2<B, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STG_BYTES);
+        cudaFuncSetAttribute(k_pass2<B, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STG_BYTES);
+        cudaFuncSetAttribute(k_pass2<B, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STG_BYTES);
         if (E.pass2_minb == 2)
-            k_pass2<B, 2><<<nblk, 256, 0, sb>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
+            k_pass2<B, 2><<<nblk, 256, STG_BYTES, sb>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
         else if (E.pass2_minb == 3)
-            k_pass2<B, 3><<<nblk, 256, 0, sb>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
+            k_pass2<B, 3><<<nblk, 256, STG_BYTES, sb>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
         else
-            k_pass2<B, 1><<<nblk, 256, 0, sb>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
+            k_pass2<B, 1><<<nblk, 256, STG_BYTES, sb>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_inv.as<gf>(), dst);
         if (detour) hop(sb, st, 1);
         pe();
         if (mark) {
@@ -1497,7 +1585,7 @@ struct Tree {
         CK(cudaMemsetAsync(A.ctl, 0, ACC_CTL_WORDS * 4, st));
         void *params[] = {(void *)&A};
         pb(PC_PASS2);
-        CK(cudaLaunchCooperativeKernel((const void *)k_accumulate, dim3(grid), dim3(ACC_THREADS), params, 0, st));
+        CK(cudaLaunchCooperativeKernel((const void *)k_accumulate, dim3(grid), dim3(ACC_THREADS), params, STG_BYTES, st));
         pe();
         L.launches++;
         return 0;
@@ -1783,7 +1871,11 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     const uint32_t R = 1u << lr, m = 1u << lm;
     const uint32_t per_b = lm * (m >> 1) + lr * (R >> 1) + m;
     // lanes: independent chains of rounds over disjoint ranges of virtual windows
-    int NL = (profile && !force_lanes) ? 1 : force_lanes ? force_lanes : (n >= (1u << 13) ? 2 : 1);
+    // The persistent kernel (one block of 255-register threads per SM) runs in ONE lane: two lanes would halve each
+    // grid (2^20: 6.95 ms against 7.17); the separate-launch path keeps two lanes (2^22: 22.2 against 23.8 ms).
+    const bool persistent_any =
+        acc_capacity > 0 && (use_accumulate == 2 || (use_accumulate == 1 && n >= ((size_t)1 << 17) && n < ((size_t)3 << 20)));
+    int NL = (profile && !force_lanes) ? 1 : force_lanes ? force_lanes : persistent_any ? 1 : (n >= (1u << 13) ? 2 : 1);
     NL = std::max(1, std::min<int>(NL, (int)V));
     while ((int)lanes.size() < NL) {
         lanes.emplace_back();
@@ -1836,8 +1928,6 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     // 7.92, 2^21: 13.60 / 13.72; 23 launches instead of 87-155); below, a few hundred additions per round do not pay for
     // grid barriers (2^12: 1.18 / 1.10), above, the separate large launches keep two blocks of one lane on every SM
     // (2^22: 24.4 / 23.4 ms).
-    const bool persistent_any =
-        acc_capacity > 0 && (use_accumulate == 2 || (use_accumulate == 1 && n >= ((size_t)1 << 17) && n < ((size_t)3 << 20)));
     // With the persistent kernel the host needs nothing from the sort: the rounds are counted on the device and the
     // scratch is sized from upper bounds (every entry in one lane), so the MSM is enqueued without a read-back in the
     // middle.  (Larger MSMs keep the exact sizes: twice the scratch would be gigabytes.)

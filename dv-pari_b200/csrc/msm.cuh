@@ -96,7 +96,8 @@ struct MsmEngine {
     int use_accumulate = 1; // all rounds of a lane in one persistent cooperative launch (k_accumulate): 0 never,
                             // 1 for the sizes where it wins, 2 always
     uint32_t acc_capacity = 0;  // blocks of k_accumulate that are co-resident on the device (0: no cooperative launch)
-    int pass2_minb = 2; // resident blocks per SM the pass-2 kernel is compiled for (register cap)
+    int pass2_minb = 1; // resident blocks per SM the pass-2 kernel is compiled for (register cap); 1 = 255 registers,
+                        // no spills: with the staged operands 8 warps per SM are enough (2^22: 22.2 ms against 23.4 at 2)
 
     int init(cudaStream_t s);
     void destroy();

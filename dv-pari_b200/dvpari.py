@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdvpari.so")
+LIB_PATH = os.environ.get("DVP_LIB") or os.path.join(_HERE, "libdvpari.so")  # DVP_LIB: development A/B builds
 
 P = 3450873173395281893717377931138512760570940988862252126328087024741343  # src/curve.rs:17
 R = 1 << 256

@@ -10,17 +10,19 @@ using namespace dvp;
 
 template <int V> __device__ __forceinline__ gf mulv(const gf &a, const gf &b) {
     if (V == 0) return gf_mul_portable(a, b); // C form: compiler-chosen order
+    if (V == 2) return gf_mul_dev2(a, b);     // 32-bit IMAD only, straight + bit-reversed streams
     return gf_mul_dev(a, b);                  // explicit mul.wide / mad.wide order (the device path of gf_mul)
 }
 __device__ __noinline__ gf mul_call0(const gf a, const gf b) { return gf_mul_portable(a, b); }
 __device__ __noinline__ gf mul_call1(const gf a, const gf b) { return gf_mul_dev(a, b); }
+__device__ __noinline__ gf mul_call2(const gf a, const gf b) { return gf_mul_dev2(a, b); }
 
 template <int V, int THREADS, int MINB, int CALL>
 __global__ void __launch_bounds__(THREADS, MINB) k_mul(const gf *__restrict__ in, gf *__restrict__ out, int iters) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     gf x = in[2 * i], y = in[2 * i + 1];
     for (int it = 0; it < iters; it++) {
-        if (CALL) x = V ? mul_call1(x, y) : mul_call0(x, y);
+        if (CALL) x = V == 2 ? mul_call2(x, y) : V ? mul_call1(x, y) : mul_call0(x, y);
         else x = mulv<V>(x, y);
         y.v[0] ^= x.v[3];
         y.v[5] ^= x.v[1];
@@ -78,6 +80,8 @@ int main(int argc, char **argv) {
     R(0, 256, 2, 1); R(0, 256, 3, 1); R(0, 256, 4, 1);
     R(1, 256, 1, 0); R(1, 256, 2, 0); R(1, 256, 3, 0); R(1, 256, 4, 0);
     R(1, 256, 2, 1); R(1, 256, 3, 1); R(1, 256, 4, 1);
+    R(2, 256, 1, 0); R(2, 256, 2, 0); R(2, 256, 3, 0); R(2, 256, 4, 0);
+    R(2, 256, 2, 1); R(2, 256, 3, 1); R(2, 256, 4, 1); R(2, 128, 4, 0);
     R(1, 128, 5, 0); R(1, 128, 6, 0); R(1, 128, 8, 0);
     return 0;
 }

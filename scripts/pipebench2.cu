@@ -16,6 +16,8 @@
 #define A_IADD3 8  // 3-input add
 #define A_PRMT 9
 #define A_LOPIMM 10 // lop3 with one immediate (2 register reads)
+#define A_BREV 11
+#define A_POPC 12
 
 template <int OP> __device__ __forceinline__ void op(uint32_t &x, uint32_t &y, uint64_t &w, uint32_t m) {
     if (OP == A_WIDE) { // w <- lo(w) * hi(w): both halves feed the next product
@@ -34,6 +36,8 @@ template <int OP> __device__ __forceinline__ void op(uint32_t &x, uint32_t &y, u
     if (OP == A_SHF) asm volatile("shf.l.wrap.b32 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(m));
     if (OP == A_ADD) asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(y));
     if (OP == A_IADD3) asm volatile("{.reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2;}" : "+r"(x) : "r"(y), "r"(m));
+    if (OP == A_BREV) asm volatile("brev.b32 %0, %0;" : "+r"(x));
+    if (OP == A_POPC) asm volatile("popc.b32 %0, %0;" : "+r"(x));
     if (OP == A_PRMT) asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(m));
 }
 
@@ -133,5 +137,11 @@ int main(int argc, char **argv) {
     R(A_LOP, 1, A_ADD, 1);
     R(A_LOP, 1, A_PRMT, 1);
     R(A_WIDE, 1, A_LO, 1);
+    R(A_BREV, 1, A_NONE, 0);
+    R(A_BREV, 1, A_LOP, 1);
+    R(A_BREV, 1, A_LOP, 4);
+    R(A_BREV, 1, A_LO, 4);
+    R(A_LO, 1, A_LOP, 2);
+    R(A_LO, 2, A_LOP, 1);
     return 0;
 }
