@@ -589,7 +589,10 @@ struct AccArgs {
     int max_rounds;                 // run at most this many rounds (a fixed count for the reduction levels)
     int tiny_max;                   // a round of at most this many additions runs one warp per addition
 };
-constexpr int ACC_THREADS = 256;
+#ifndef ACC_THREADS_N
+#define ACC_THREADS_N 256
+#endif
+constexpr int ACC_THREADS = ACC_THREADS_N; // <= 256 (the staging slots are laid out for 256 threads)
 #ifndef ACC_MINB
 #define ACC_MINB 1
 #endif
@@ -640,6 +643,114 @@ __device__ __forceinline__ bool acc_barrier(uint32_t *ctl, uint32_t &target) {
     }
     __syncthreads();
     return sh_abort == 0;
+}
+
+// ---- the three steps of a warp's share of a round (32 chains of B additions), shared by the persistent kernel and the
+// fused per-round kernel of the separate-launch path.  Lanes without a task keep the total 1.
+// pass 1: denominators and per-thread prefix products; operands staged one addition ahead (a prefetch into registers
+// would be spilled around the out-of-line product, and the spill store waits for the load)
+__device__ __forceinline__ gf chain_pass1(uint4 *stage, uint32_t tid, uint32_t lane, uint32_t base, uint32_t B, uint32_t ntasks,
+                                          const AffPt *cur, const uint4 *desc, gf *prefix) {
+    gf acc = gf_one();
+    if (base + lane >= ntasks) return acc;
+    uint32_t t = base + lane;
+    uint4 de = __ldcg(&desc[t]);
+    stage_issue_x(stage, 0, tid, cur, de, (B > 1 && t + 32 < ntasks) ? &desc[t + 32] : nullptr);
+#pragma unroll 1
+    for (uint32_t k = 0; k < B && t < ntasks; k++, t += 32) {
+        cp_async_wait_all();
+        const gf x1 = stage_gf(stage, k & 1, 0, tid), x2 = stage_gf(stage, k & 1, 4, tid);
+        const uint4 de0 = de;
+        if (k + 1 < B && t + 32 < ntasks) {
+            de = *STG_SLOT(stage, k & 1, 10, tid);
+            stage_issue_x(stage, (k + 1) & 1, tid, cur, de, (k + 2 < B && t + 64 < ntasks) ? &desc[t + 64] : nullptr);
+        }
+        gf d = gf_add(x1, x2);
+        if (gf_is_zero(x1) | gf_is_zero(x2)) d = gf_one();
+        else if (gf_is_zero(d)) {
+            const AffPt p1 = fetch_entry_cg(cur, de0.x), p2 = fetch_entry_cg(cur, de0.y);
+            d = gf_eq(p1.y, p2.y) ? x1 : gf_one();
+        }
+        if (B > 1) {
+            gf_store(&prefix[t], acc);
+            acc = gf_mul_call(acc, d);
+        } else {
+            acc = d; // a chain of one: its prefix is 1
+        }
+    }
+    return acc;
+}
+// The warp inverts its own 32 thread totals, in registers: five butterfly levels up (every lane keeps its sibling's
+// sub-product), one cooperative inversion of the warp product, five levels back down.  No inversion leaves the warp, so
+// the warps of a round never wait for each other between the two passes.  All 32 lanes must call.
+__device__ __forceinline__ gf warp_invert_totals(const gf &acc, const gf *__restrict__ tabs) {
+    gf S[5], P = acc;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) S[k].v[q] = __shfl_xor_sync(0xffffffffu, P.v[q], 1 << k);
+        P = gf_mul_call(P, S[k]);
+    }
+    const WarpMulCtx wc = warp_mul_ctx();
+    gf inv = gf_inv_tab_warp(P, tabs, wc);
+#pragma unroll
+    for (int k = 4; k >= 0; k--) inv = gf_mul_call(inv, S[k]);
+    return inv;
+}
+// pass 2: the same additions backwards with the inverse of the thread's total, operands staged one addition ahead
+__device__ __forceinline__ void chain_pass2(uint4 *stage, uint32_t tid, uint32_t lane, uint32_t base, uint32_t B, uint32_t ntasks,
+                                            const AffPt *cur, const uint4 *desc, const gf *prefix, gf inv, AffPt *out) {
+    if (base + lane >= ntasks) return;
+    int k = (int)min(B - 1, (ntasks - 1 - base - lane) >> 5); // the thread's last task
+    uint32_t t = base + (uint32_t)k * 32 + lane;
+    uint4 de = __ldcg(&desc[t]);
+    stage_issue(stage, k & 1, tid, cur, de, B > 1 ? &prefix[t] : nullptr, k > 0 ? &desc[t - 32] : nullptr);
+#pragma unroll 1
+    for (; k >= 0; k--, t -= 32) {
+        cp_async_wait_all();
+        AffPt p1, p2;
+        stage_points(stage, k & 1, tid, de, p1, p2);
+        gf dinv = inv;
+        if (B > 1) dinv = stage_gf(stage, k & 1, 8, tid);
+        const uint32_t dz = de.z;
+        if (k > 0) {
+            de = *STG_SLOT(stage, k & 1, 10, tid);
+            stage_issue(stage, (k - 1) & 1, tid, cur, de, &prefix[t - 32], k > 1 ? &desc[t - 64] : nullptr);
+        }
+        gf d;
+        const int kind = pair_classify(p1, p2, d);
+        if (B > 1) {
+            dinv = gf_mul_call(inv, dinv);
+            if (k) inv = gf_mul_call(inv, d);
+        }
+        AffPt q;
+        if (kind >= 2) {
+            q = pair_degenerate(p1, p2, kind);
+        } else {
+            // chord / tangent: lambda = num/d (+ x1 for the tangent), see pair_finish
+            gf lam = gf_mul_call(kind == 1 ? p1.y : gf_add(p1.y, p2.y), dinv);
+            if (kind == 1) lam = gf_add(lam, p1.x);
+            q.x = gf_add(gf_add(gf_sqr(lam), lam), gf_add(p1.x, p2.x));
+            q.y = gf_add(gf_add(gf_mul_call(lam, gf_add(p1.x, q.x)), q.x), p1.y);
+        }
+        pt_store(&out[dz], q);
+    }
+}
+// One round of the separate-launch path in ONE kernel: every warp runs pass 1, inverts its own 32 totals and runs pass 2
+// (no thr_total / thr_inv arrays, no hierarchical inversion launches between the passes).
+template <int B>
+__global__ void __launch_bounds__(256, 1)
+    k_round_fused(const AffPt *__restrict__ src, const uint32_t *__restrict__ info, const uint4 *__restrict__ desc,
+                  gf *__restrict__ prefix, AffPt *__restrict__ dst, const gf *__restrict__ tabs) {
+    extern __shared__ uint4 stage[];
+    const uint32_t ntasks = info[1];
+    const uint32_t tid = threadIdx.x, gtid = blockIdx.x * blockDim.x + tid;
+    const uint32_t lane = gtid & 31, warp = gtid >> 5;
+    const uint32_t base = warp * (32u * B);
+    if (base >= ntasks) return; // the whole warp
+    const gf acc = chain_pass1(stage, tid, lane, base, B, ntasks, src, desc, prefix);
+    const gf inv = warp_invert_totals(acc, tabs);
+    chain_pass2(stage, tid, lane, base, B, ntasks, src, desc, prefix, inv, dst);
 }
 
 __global__ void __launch_bounds__(ACC_THREADS, ACC_MINB) k_accumulate(const AccArgs A) {
@@ -779,91 +890,11 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MINB) k_accumulate(const AccA
                 if (lane == 0) pt_store(&out[de.z], q);
             }
         } else if (base < ntasks) { // the whole warp or none of it
-            gf acc = gf_one();
-            if (base + lane < ntasks) {
-                // operands staged one addition ahead like in pass 2: a prefetch into registers would be spilled around
-                // the out-of-line product, and the spill store waits for the load
-                uint32_t t = base + lane;
-                uint4 de = __ldcg(&A.desc[t]);
-                stage_issue_x(stage, 0, tid, cur, de, (B > 1 && t + 32 < ntasks) ? &A.desc[t + 32] : nullptr);
-#pragma unroll 1
-                for (uint32_t k = 0; k < B && t < ntasks; k++, t += 32) {
-                    cp_async_wait_all();
-                    const gf x1 = stage_gf(stage, k & 1, 0, tid), x2 = stage_gf(stage, k & 1, 4, tid);
-                    const uint4 de0 = de;
-                    if (k + 1 < B && t + 32 < ntasks) {
-                        de = *STG_SLOT(stage, k & 1, 10, tid);
-                        stage_issue_x(stage, (k + 1) & 1, tid, cur, de, (k + 2 < B && t + 64 < ntasks) ? &A.desc[t + 64] : nullptr);
-                    }
-                    gf d = gf_add(x1, x2);
-                    if (gf_is_zero(x1) | gf_is_zero(x2)) d = gf_one();
-                    else if (gf_is_zero(d)) {
-                        const AffPt p1 = fetch_entry_cg(cur, de0.x), p2 = fetch_entry_cg(cur, de0.y);
-                        d = gf_eq(p1.y, p2.y) ? x1 : gf_one();
-                    }
-                    if (B > 1) {
-                        gf_store(&A.prefix[t], acc);
-                        acc = gf_mul_call(acc, d);
-                    } else {
-                        acc = d; // a chain of one: its prefix is 1
-                    }
-                }
-            }
+            const gf acc = chain_pass1(stage, tid, lane, base, B, ntasks, cur, A.desc, A.prefix);
             if (prof) A.times[6 * r + 2] = acc_now();
-            // ---- the warp inverts its own 32 thread totals, in registers: five butterfly levels up (every lane keeps
-            // its sibling's sub-product), one cooperative inversion of the warp product, five levels back down.  No
-            // inversion leaves the warp, so the warps of a round never wait for each other between the two passes.
-            gf inv;
-            {
-                gf S[5], P = acc;
-#pragma unroll
-                for (int k = 0; k < 5; k++) {
-#pragma unroll
-                    for (int q = 0; q < 8; q++) S[k].v[q] = __shfl_xor_sync(0xffffffffu, P.v[q], 1 << k);
-                    P = gf_mul_call(P, S[k]);
-                }
-                const WarpMulCtx wc = warp_mul_ctx();
-                inv = gf_inv_tab_warp(P, A.tabs, wc);
-#pragma unroll
-                for (int k = 4; k >= 0; k--) inv = gf_mul_call(inv, S[k]);
-            }
+            const gf inv = warp_invert_totals(acc, A.tabs);
             if (prof) A.times[6 * r + 3] = acc_now();
-            // ---- pass 2: the same additions backwards, operands staged one addition ahead (stage_issue)
-            if (base + lane < ntasks) {
-                int k = (int)min(B - 1, (ntasks - 1 - base - lane) >> 5); // the thread's last task
-                uint32_t t = base + (uint32_t)k * 32 + lane;
-                uint4 de = __ldcg(&A.desc[t]);
-                stage_issue(stage, k & 1, tid, cur, de, B > 1 ? &A.prefix[t] : nullptr, k > 0 ? &A.desc[t - 32] : nullptr);
-#pragma unroll 1
-                for (; k >= 0; k--, t -= 32) {
-                    cp_async_wait_all();
-                    AffPt p1, p2;
-                    stage_points(stage, k & 1, tid, de, p1, p2);
-                    gf dinv = inv;
-                    if (B > 1) dinv = stage_gf(stage, k & 1, 8, tid);
-                    const uint32_t dz = de.z;
-                    if (k > 0) {
-                        de = *STG_SLOT(stage, k & 1, 10, tid);
-                        stage_issue(stage, (k - 1) & 1, tid, cur, de, &A.prefix[t - 32], k > 1 ? &A.desc[t - 64] : nullptr);
-                    }
-                    gf d;
-                    const int kind = pair_classify(p1, p2, d);
-                    if (B > 1) {
-                        dinv = gf_mul_call(inv, dinv);
-                        if (k) inv = gf_mul_call(inv, d);
-                    }
-                    AffPt q;
-                    if (kind >= 2) {
-                        q = pair_degenerate(p1, p2, kind);
-                    } else {
-                        gf lam = gf_mul_call(kind == 1 ? p1.y : gf_add(p1.y, p2.y), dinv);
-                        if (kind == 1) lam = gf_add(lam, p1.x);
-                        q.x = gf_add(gf_add(gf_sqr(lam), lam), gf_add(p1.x, p2.x));
-                        q.y = gf_add(gf_add(gf_mul_call(lam, gf_add(p1.x, q.x)), q.x), p1.y);
-                    }
-                    pt_store(&out[dz], q);
-                }
-            }
+            chain_pass2(stage, tid, lane, base, B, ntasks, cur, A.desc, A.prefix, inv, out);
         }
         if (!acc_barrier(A.ctl, bar)) return;
         if (prof) A.times[6 * r + 4] = acc_now();
@@ -1502,6 +1533,24 @@ struct Tree {
             cudaEventRecord(L.ev_sw[e], from);
             cudaStreamWaitEvent(to, L.ev_sw[e], 0);
         };
+        if (E.fused_rounds) {
+            // pass 1, the warps' own inversions and pass 2 in one launch (no thread totals leave the warp)
+            const bool mark = L.want_k;
+            if (mark) cudaEventRecord(L.ev_k[0], st);
+            pb(PC_PASS2);
+            if (detour) hop(st, sb, 0);
+            cudaFuncSetAttribute(k_round_fused<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STG_BYTES);
+            k_round_fused<B><<<nblk, 256, STG_BYTES, sb>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), dst, E.msqr_tabs.as<gf>());
+            if (detour) hop(sb, st, 1);
+            pe();
+            if (mark) {
+                cudaEventRecord(L.ev_k[1], st);
+                L.want_k = false;
+            }
+            L.launches++;
+            CK(cudaGetLastError());
+            return 0;
+        }
         pb(PC_PASS1);
         if (detour) hop(st, sb, 0);
         k_pass1<B><<<nblk, 256, 0, sb>>>(src, info, L.desc.as<uint4>(), L.prefix.as<gf>(), L.thr_total.as<gf>());

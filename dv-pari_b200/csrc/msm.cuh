@@ -96,6 +96,9 @@ struct MsmEngine {
     int use_accumulate = 1; // all rounds of a lane in one persistent cooperative launch (k_accumulate): 0 never,
                             // 1 for the sizes where it wins, 2 always
     uint32_t acc_capacity = 0;  // blocks of k_accumulate that are co-resident on the device (0: no cooperative launch)
+    int fused_rounds = 0; // separate-launch path: one kernel per round (pass 1, per-warp inversion, pass 2) instead of 3-7.
+                          // Off: with chains of 16 the warp's own inversion (10 products + 6.7 us) is 16 % of its work,
+                          // the hierarchical inversion 4 % (2^22: 24.9 against 22.3 ms, 2^24: 84.0 against 76.9)
     int pass2_minb = 1; // resident blocks per SM the pass-2 kernel is compiled for (register cap); 1 = 255 registers,
                         // no spills: with the staged operands 8 warps per SM are enough (2^22: 22.2 ms against 23.4 at 2)
 
