@@ -35,16 +35,18 @@ UNIT = "points/s"
 # pass 2 per round).  Per batched affine addition it moves, algorithmically: descriptor 16 B written + 2 x 16 B read,
 # x coordinates 2 x 32 B (pass 1), prefix product 32 B written + 32 B read, two points 128 B (pass 2), one point out 64 B.
 ACC_BYTES_PER_ADD = 48 + 64 + 64 + 128 + 64
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch / its additions (profiles/r2c_ncu_accumulate_raw.csv:
-# 2.82 GB + 0.77 GB for 6.9 M additions: the 64-byte gathers of the bucket-sorted round 0 touch whole sectors)
-ACC_DRAM_BYTES_PER_ADD_NCU = 520
-# Issue-port instructions per addition (the ALU and FMA-heavy pipes share one port of 0.5 instructions per clock and
-# scheduler: profiles/README.md r2c, ncu counters of the IMAD.WIDE / LOP3 mixes): 6 field products of 774 ALU-pipe + 434
-# IMAD.WIDE each (pass 1: 1, pass 2: 4, the warp's own inversion tree ~1 amortised), one squaring (111) and ~250 of loop
-# body -- 7.4e3; ncu's sm__pipe_alu / fmaheavy cycle counters of the same launch give 7.3e3 per addition.
-ACC_PORT_INSTR_PER_ADD = 6 * (774 + 434) + 111 + 250
-ISSUE_PORT_PEAK = 1.83e13  # measured: LOP3 alone, and every IMAD.WIDE + k LOP3 mix, stop at this many thread-instr/s
-                           # (smsp__issue_active = 50 %), profiles/r2c_ncu_pipebench2_raw.csv
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch / its additions (profiles/r2f_ncu_accumulate_raw.csv:
+# 5.58 GB + 1.49 GB for 13.5 M additions: the 64-byte gathers of the bucket-sorted round 0 touch whole sectors)
+ACC_DRAM_BYTES_PER_ADD_NCU = 523
+# ALU-pipe (LOP3 / SHF / ...) thread-instructions per addition, from ncu's own counters of the launch this line times
+# (profiles/r2f_ncu_accumulate_raw.csv: sm__pipe_alu_cycles_active x cycles / 2 = 2.13e9 warp-instructions of 4.33e9
+# executed, for 13 500 343 additions; k_pass2<16,1>: profiles/r2f_ncu_pass2_raw.csv).  The field product is now 32-bit
+# multiply-adds only (gf233_mul2.cuh): ~900 LOP3 on the ALU pipe and ~890 IMAD on the FMA-heavy pipe per product, which
+# dual-issue, so the ALU pipe (0.5 warp-instructions per clock and scheduler) is the pipe that binds.
+ACC_ALU_INSTR_PER_ADD = 5060
+PASS2_ALU_INSTR_PER_ADD = 4070
+ALU_PIPE_PEAK = 1.83e13  # measured on this pool's B200: LOP3 alone runs at this many thread-instr/s
+                         # (sm__pipe_alu_cycles_active = 99.9 %), profiles/r2c_ncu_pipebench2_raw.csv
 
 
 def peaks():
@@ -507,10 +509,10 @@ def main():
         k_ms, k_adds = st["ms_pass2_round0"], st["adds_round0"]
         persistent = int(st["launches"]) < 40  # k_accumulate ran (the separate-launch path has > 60 launches)
         kernel = ("k_accumulate (all tree rounds of the bucket accumulation, one persistent cooperative launch)" if persistent
-                  else "k_pass2<16,2> (pass 2 of round 0 of the bucket accumulation)")
+                  else "k_pass2<16,1> (pass 2 of round 0 of the bucket accumulation)")
         bytes_per_add = ACC_BYTES_PER_ADD if persistent else 240
         dram_per_add = ACC_DRAM_BYTES_PER_ADD_NCU if persistent else 385
-        instr_per_add = ACC_PORT_INSTR_PER_ADD if persistent else 4 * (774 + 434) + 250
+        instr_per_add = ACC_ALU_INSTR_PER_ADD if persistent else PASS2_ALU_INSTR_PER_ADD
         gbps = k_adds * bytes_per_add / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         port = k_adds * instr_per_add / (k_ms * 1e-3) if k_ms > 0 else 0.0
         # bounded CPU baseline on the same SRS points (first 2^cpu_lg of rank 0's range), checked against the GPU
@@ -545,12 +547,13 @@ def main():
             "e2e": {"value": pts_per_step * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": batch * n * 32,
                     "d2h_bytes_per_step": batch * (30 + st["windows"] * st["window_bits"] * 64), "ms_per_step": 1e3 * dt_e2e / args.steps},
             "gpu_launches": launches_per_msm * batch * args.steps,
-            "roofline": {"bound": "integer issue (ALU + FMA-heavy pipes share one issue port; not HBM, not tensor)",
-                         "kernel": kernel, "achieved": port, "peak": ISSUE_PORT_PEAK, "unit": "thread-instr/s",
-                         "frac": port / ISSUE_PORT_PEAK, "instr_per_add": instr_per_add,
+            "roofline": {"bound": "integer ALU pipe (LOP3/SHF of the carry-less field product; its IMADs dual-issue on the FMA pipe; not HBM, not tensor)",
+                         "kernel": kernel, "achieved": port, "peak": ALU_PIPE_PEAK, "unit": "ALU-pipe thread-instr/s",
+                         "frac": port / ALU_PIPE_PEAK, "alu_instr_per_add": instr_per_add,
                          "launch_ms": k_ms, "adds_per_launch": k_adds,
-                         "peak_source": "measured on this pool's B200: LOP3 alone and every IMAD.WIDE + k LOP3 mix stop at "
-                                        "smsp__issue_active = 50 % (profiles/r2c_ncu_pipebench2_raw.csv)",
+                         "peak_source": "measured on this pool's B200: LOP3 alone = 1.83e13 thread-instr/s at sm__pipe_alu_cycles_active "
+                                        "99.9 % (profiles/r2c_ncu_pipebench2_raw.csv); instructions per addition from ncu's ALU-pipe "
+                                        "counter of the same kernel (profiles/r2f_ncu_accumulate_raw.csv: ALU pipe 63.5 % busy)",
                          "traffic": k_adds * dram_per_add,
                          "hbm_view": {"achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak,
                                       "bytes_per_add": bytes_per_add, "peak_source": which}},
