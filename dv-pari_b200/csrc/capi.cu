@@ -300,6 +300,10 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
         ctx->msm.ld_tree_max = (size_t)value;
         return DVP_OK;
     }
+    if (!strcmp(name, "b16_min")) {
+        ctx->msm.b16_min = value > 0 ? (size_t)value : ((size_t)1 << 21);
+        return DVP_OK;
+    }
     if (!strcmp(name, "b64_min")) {
         ctx->msm.b64_min = value > 0 ? (size_t)value : ((size_t)1 << 23);
         return DVP_OK;

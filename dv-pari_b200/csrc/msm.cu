@@ -1693,7 +1693,7 @@ struct Tree {
             const size_t task_ub = r == 0 ? total_ub / 2 + 1 : (total_ub >> (r + 1)) + nseg / 2 + 1;
             // additions chained per thread: long chains in the throughput-bound rounds; in the latency-bound ones just
             // enough that the thread totals fit one cooperative inversion launch
-            int B = task_ub >= E.b64_min ? 64 : task_ub >= (1u << 21) ? 16 : task_ub > E.binv_direct ? 4 : 1;
+            int B = task_ub >= E.b64_min ? 64 : task_ub >= E.b16_min ? 16 : task_ub > E.binv_direct ? 4 : 1;
             B = std::min(B, E.pass_b_max);
             AffPt *out = L.pp[r & 1].as<AffPt>();
             if ((rc = round(B, cur_src, task_ub, out))) return rc; // (the odd leftovers were carried over by the plan)

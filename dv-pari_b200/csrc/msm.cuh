@@ -86,6 +86,7 @@ struct MsmEngine {
     std::vector<TimelineRow> timeline; // of the last profiled run: one row per bracket, ms since the start of the MSM
     float prof_ms[PC_COUNT] = {0};
     unsigned prof_n[PC_COUNT] = {0};
+    size_t b16_min = (size_t)1 << 21; // rounds with at least this many additions chain 16 per thread (below: 4 or 1)
     size_t b64_min = (size_t)1 << 23; // rounds with at least this many additions chain 64 per thread (off by default)
     bool prio_split = true; // large pass kernels on low-priority streams
     int pass_b_max = 64;    // cap on the additions chained per thread
