@@ -336,6 +336,10 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
         ctx->msm.fused_rounds = value ? 1 : 0;
         return DVP_OK;
     }
+    if (!strcmp(name, "ld_tree_warp_a")) {
+        ctx->msm.ld_tree_warp_a = value ? 1 : 0;
+        return DVP_OK;
+    }
     if (!strcmp(name, "pass2_minb")) {
         if (value < 1 || value > 3) return DVP_ERR_BAD_ARG;
         ctx->msm.pass2_minb = (int)value;

@@ -1299,14 +1299,21 @@ struct GfMulWarp {
     const WarpMulCtx &c;
     __device__ __forceinline__ gf operator()(const gf &a, const gf &b) const { return gf_mul_warp(a, b, c); }
 };
+// SRC_LD: the inputs are Lopez-Dahab points named by the index list `ent` (level B); otherwise affine points at the
+// positions of the segment (level A after its batched-affine rounds: short segments, thousands of them -- the thread-per-
+// addition tree above spends 0.29 ms of pure latency on them at 2^20 points).  OUT_AFFINE as above.
+template <bool SRC_LD, bool OUT_AFFINE>
 __global__ void __launch_bounds__(512)
-    k_ld_tree_warp(const LdPt *__restrict__ src, const uint32_t *__restrict__ ent, const uint32_t *__restrict__ seg_start,
-                   const uint32_t *__restrict__ seg_len, AffPt *__restrict__ dst, const gf *__restrict__ tabs) {
+    k_ld_tree_warp(const void *__restrict__ src, const uint32_t *__restrict__ ent, const uint32_t *__restrict__ seg_start,
+                   const uint32_t *__restrict__ seg_len, void *__restrict__ dst, const gf *__restrict__ tabs) {
     extern __shared__ __align__(16) unsigned char sh_raw[];
     LdPt *sh = reinterpret_cast<LdPt *>(sh_raw); // the points of the segment, halved level by level
     const uint32_t s = blockIdx.x, t = threadIdx.x, warp = t >> 5, nwarps = blockDim.x >> 5;
     const uint32_t start = seg_start[s], len = seg_len[s];
-    for (uint32_t i = t; i < len; i += blockDim.x) ld_store(&sh[i], ld_load(src + ent[start + i]));
+    for (uint32_t i = t; i < len; i += blockDim.x) {
+        if (SRC_LD) ld_store(&sh[i], ld_load(reinterpret_cast<const LdPt *>(src) + ent[start + i]));
+        else ld_store(&sh[i], ld_from_affine(pt_load(reinterpret_cast<const AffPt *>(src) + start + i)));
+    }
     __syncthreads();
     const WarpMulCtx wc = warp_mul_ctx();
     const GfMulWarp mul{wc};
@@ -1328,13 +1335,17 @@ __global__ void __launch_bounds__(512)
     }
     if (t < 32) {
         const LdPt r = len ? ld_load(&sh[0]) : ld_infinity();
-        AffPt o = pt_inf();
-        if (!gf_is_zero(r.Z)) {
-            const gf zi = gf_inv_tab_warp(r.Z, tabs, wc);
-            o.x = gf_mul_warp(r.X, zi, wc);
-            o.y = gf_mul_warp(r.Y, gf_sqr(zi), wc);
+        if (OUT_AFFINE) {
+            AffPt o = pt_inf();
+            if (!gf_is_zero(r.Z)) {
+                const gf zi = gf_inv_tab_warp(r.Z, tabs, wc);
+                o.x = gf_mul_warp(r.X, zi, wc);
+                o.y = gf_mul_warp(r.Y, gf_sqr(zi), wc);
+            }
+            if (t == 0) pt_store(reinterpret_cast<AffPt *>(dst) + s, o);
+        } else if (t == 0) {
+            ld_store(reinterpret_cast<LdPt *>(dst) + s, r);
         }
-        if (t == 0) pt_store(dst + s, o);
     }
 }
 
@@ -2118,7 +2129,12 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
                 if (rc) return rc;
             }
             tree.pb(PC_MISC);
-            if (r_a > 0) {
+            if (r_a > 0 && part_a.maxlen <= 64 && ld_tree_warp_a) {
+                // short segments: every addition by a whole warp (one pair per warp at the first level)
+                const uint32_t nw = std::max(1u, std::min(16u, part_a.maxlen / 2));
+                k_ld_tree_warp<false, false><<<p.nseg_a, 32 * nw, std::max(1u, part_a.maxlen) * sizeof(LdPt), L.stream>>>(
+                    part_a.src, nullptr, part_a.start, part_a.len, L.rc.p, msqr_tabs.as<gf>());
+            } else if (r_a > 0) {
                 const uint32_t th = std::max(32u, part_a.maxlen / 2);
                 k_ld_tree<false, false><<<p.nseg_a, th, th * sizeof(LdPt), L.stream>>>(
                     part_a.src, nullptr, part_a.start, part_a.len, L.rc.p, msqr_tabs.as<gf>());
@@ -2132,8 +2148,8 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
             k_gen_segs_b<<<cdiv(p.nseg_b + 1, 256), 256, 0, L.stream>>>(p.vn, lr, lm, d_start, d_len);
             tree.pb(PC_MISC);
             if (2 * tthr <= 8 * 16) // a segment has at most 2 tthr points: 4 pairs per warp and level with 16 warps
-                k_ld_tree_warp<<<p.nseg_b, 512, 2 * tthr * sizeof(LdPt), L.stream>>>(
-                    L.rc.as<LdPt>(), L.ents2.as<uint32_t>(), d_start, d_len, hb.as<AffPt>() + (size_t)p.v0 * cv, msqr_tabs.as<gf>());
+                k_ld_tree_warp<true, true><<<p.nseg_b, 512, 2 * tthr * sizeof(LdPt), L.stream>>>(
+                    L.rc.p, L.ents2.as<uint32_t>(), d_start, d_len, hb.as<AffPt>() + (size_t)p.v0 * cv, msqr_tabs.as<gf>());
             else
                 k_ld_tree<true, true><<<p.nseg_b, tthr, tthr * sizeof(LdPt), L.stream>>>(
                     L.rc.p, L.ents2.as<uint32_t>(), d_start, d_len, hb.as<AffPt>() + (size_t)p.v0 * cv, msqr_tabs.as<gf>());

@@ -90,6 +90,7 @@ struct MsmEngine {
     size_t b64_min = (size_t)1 << 23; // rounds with at least this many additions chain 64 per thread (off by default)
     bool prio_split = true; // large pass kernels on low-priority streams
     int pass_b_max = 64;    // cap on the additions chained per thread
+    int ld_tree_warp_a = 1; // level A's tree after the batched-affine rounds: one warp per addition (cooperative products)
     size_t ld_tree_max = 0; // 0 = automatic; a reduction level with more points starts with batched-affine rounds
     uint32_t binv_direct = 36864;    // batches up to this size are inverted by one cooperative launch (k_binv_coop)
     uint32_t binv_coop_warps = 2368; // ... in groups sized so that about this many warps run (one wave)
