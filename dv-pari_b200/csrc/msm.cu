@@ -2130,8 +2130,9 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
             }
             tree.pb(PC_MISC);
             if (r_a > 0 && part_a.maxlen <= 64 && ld_tree_warp_a) {
-                // short segments: every addition by a whole warp (one pair per warp at the first level)
-                const uint32_t nw = std::max(1u, std::min(16u, part_a.maxlen / 2));
+                // short segments: every addition by a whole warp, four pairs per warp at the first level (with a warp
+                // per pair most warps of a block idle after that level and the block slots of an SM set the time)
+                const uint32_t nw = std::max(1u, std::min(16u, part_a.maxlen / 8));
                 k_ld_tree_warp<false, false><<<p.nseg_a, 32 * nw, std::max(1u, part_a.maxlen) * sizeof(LdPt), L.stream>>>(
                     part_a.src, nullptr, part_a.start, part_a.len, L.rc.p, msqr_tabs.as<gf>());
             } else if (r_a > 0) {
