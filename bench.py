@@ -470,8 +470,14 @@ def main():
 
     # dvp_msm_sharded: local MSM over this rank's point range, all-gather of the partial sums over NCCL, identical fold
     # on every rank (with one rank it is the plain MSM)
-    step_dev = lambda: [ctx.msm_sharded(d_sc[b], 0, on_device=True, n=n) for b in range(batch)]
-    step_e2e = lambda: [ctx.msm_sharded(sc_pinned[b], 0) for b in range(batch)]
+    # A step is ONE batched call (dvp_msm_sharded_batch): the MSMs of the batch are pipelined -- the upload of the next
+    # scalar vector and the enqueue of its kernels overlap the current MSM, the host folds the previous partial sums
+    # meanwhile -- and one all-gather carries the whole batch.  The one-call-per-MSM loop is timed beside it.
+    host_vecs = [sc_pinned[b] for b in range(batch)]
+    step_dev = lambda: ctx.msm_sharded_batch(d_sc, 0, on_device=True, n=n)
+    step_e2e = lambda: ctx.msm_sharded_batch(host_vecs, 0)
+    step_dev_single = lambda: [ctx.msm_sharded(d_sc[b], 0, on_device=True, n=n) for b in range(batch)]
+    step_e2e_single = lambda: [ctx.msm_sharded(sc_pinned[b], 0) for b in range(batch)]
 
     for _ in range(args.warmup):
         step_dev()
@@ -490,6 +496,10 @@ def main():
         step_e2e()
     dt_e2e, res_e2e = timed(step_e2e, args.steps)
     assert res_dev == res_e2e, "device-resident and host-buffer calls disagree"
+    nsingle = max(2, min(5, args.steps))
+    dt_dev1, res_dev1 = timed(step_dev_single, nsingle)
+    dt_e2e1, res_e2e1 = timed(step_e2e_single, nsingle)
+    assert res_dev1 == res_dev and res_e2e1 == res_dev, "batched and one-call-per-MSM results disagree"
 
     # one instrumented MSM: stage split and the dominant kernel's duration (CUDA events on its launching stream inside
     # the library; a single lane here so that no other stream shares the GPU with the kernel being timed)
@@ -530,6 +540,10 @@ def main():
                   "parallelism": f"point-range sharding x{world}, NCCL all-gather of 80-byte partial sums, fold on every rank" if world > 1 else "single GPU",
                   "stage_ms": {"recode_sort": st["ms_recode_sort"], "accumulate": st["ms_accumulate"],
                                "reduce": st["ms_reduce"], "tail": st["ms_tail"]}}
+        config["single_call_ms_per_msm"] = {
+            "device": 1e3 * dt_dev1 / (nsingle * batch), "e2e": 1e3 * dt_e2e1 / (nsingle * batch),
+            "note": "one dvp_msm_sharded call per MSM (no overlap between calls: upload, MSM, host fold in sequence)"}
+        config["batched_ms_per_msm"] = {"device": 1e3 * dt / (args.steps * batch), "e2e": 1e3 * dt_e2e / (args.steps * batch)}
         if extras:
             config["other_configs"] = extras
         if prove:

@@ -253,7 +253,13 @@ void dvp_ctx_destroy(dvp_ctx *ctx) {
     ctx->bytes.release();
     ctx->small.release();
     ctx->scal.release();
+    ctx->scal2.release();
     ctx->adhoc.release();
+    for (int k = 0; k < 2; k++) {
+        if (ctx->ev_up[k]) cudaEventDestroy(ctx->ev_up[k]);
+        if (ctx->ev_free[k]) cudaEventDestroy(ctx->ev_free[k]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -355,18 +361,11 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
 static int slot_ok(dvp_ctx *ctx, int slot) { return ctx && slot >= 0 && slot < DVP_MAX_SRS_SLOTS; }
 
 extern "C++" {
-// MSM over slot[offset, offset + n).  Large slots get W tables T[j] = 2^(j c) P once (W x the slot's memory), after
-// which all windows share one bucket set; small slots, small sub-ranges and tight memory use the plain layout.
-int slot_msm(dvp_ctx *ctx, int slot, size_t offset, const uint32_t *d_scalars, size_t n, AffPt *out, cudaStream_t on) {
+// Where the points of slot[offset, offset + n) are for an MSM.  Large slots get W tables T[j] = 2^(j c) P once, on
+// first use (W x the slot's memory), after which all windows share one bucket set; small slots, small sub-ranges and
+// tight memory use the plain vector.
+static int slot_points(dvp_ctx *ctx, int slot, size_t offset, size_t n, const AffPt **pts, MsmTable *tab, bool *use_tab) {
     SrsSlot &s = ctx->slots[slot];
-    struct StreamSwap { // the engine's main stream for this call
-        MsmEngine &e;
-        cudaStream_t saved;
-        StreamSwap(MsmEngine &eng, cudaStream_t s_) : e(eng), saved(eng.stream) {
-            if (s_) e.stream = s_;
-        }
-        ~StreamSwap() { e.stream = saved; }
-    } swap(ctx->msm, on);
     const bool want = ctx->msm_tables && s.n >= ctx->msm_tables_min && n >= s.n / 2 && !ctx->msm.force_window_bits;
     if (want && !s.table_ok && !s.table_failed) {
         const int W = ctx->msm_table_windows ? ctx->msm_table_windows : choose_table_windows(s.n);
@@ -388,12 +387,101 @@ int slot_msm(dvp_ctx *ctx, int slot, size_t offset, const uint32_t *d_scalars, s
             s.table_failed = true;
         }
     }
-    if (want && s.table_ok) {
-        MsmTable t = s.tab;
-        t.offset = offset;
-        return ctx->msm.run(s.table.as<AffPt>(), d_scalars, n, out, &t);
+    *use_tab = want && s.table_ok;
+    if (*use_tab) {
+        *tab = s.tab;
+        tab->offset = offset;
+        *pts = s.table.as<AffPt>();
+    } else {
+        *pts = s.buf.as<AffPt>() + offset;
     }
-    return ctx->msm.run(s.buf.as<AffPt>() + offset, d_scalars, n, out);
+    return 0;
+}
+
+// MSM over slot[offset, offset + n).
+int slot_msm(dvp_ctx *ctx, int slot, size_t offset, const uint32_t *d_scalars, size_t n, AffPt *out, cudaStream_t on) {
+    struct StreamSwap { // the engine's main stream for this call
+        MsmEngine &e;
+        cudaStream_t saved;
+        StreamSwap(MsmEngine &eng, cudaStream_t s_) : e(eng), saved(eng.stream) {
+            if (s_) e.stream = s_;
+        }
+        ~StreamSwap() { e.stream = saved; }
+    } swap(ctx->msm, on);
+    const AffPt *pts = nullptr;
+    MsmTable t;
+    bool use_tab = false;
+    int rc = slot_points(ctx, slot, offset, n, &pts, &t, &use_tab);
+    if (rc) return rc;
+    return ctx->msm.run(pts, d_scalars, n, out, use_tab ? &t : nullptr);
+}
+
+int slot_msm_batch(dvp_ctx *ctx, int slot, size_t offset, const uint64_t *const *scalars, size_t n, size_t nb,
+                   bool on_device, AffPt *out) {
+    for (size_t b = 0; b < nb; b++) out[b] = pt_inf();
+    if (n == 0 || nb == 0) return DVP_OK;
+    const AffPt *pts = nullptr;
+    MsmTable t;
+    bool use_tab = false;
+    int rc = slot_points(ctx, slot, offset, n, &pts, &t, &use_tab);
+    if (rc) return rc;
+    DevBuf *stage[2] = {&ctx->scal, &ctx->scal2};
+    if (!on_device) {
+        for (int k = 0; k < (nb > 1 ? 2 : 1); k++)
+            if ((rc = stage[k]->reserve(n * 32 + 32)) != 0) return rc;
+        if (!ctx->copy_stream) {
+            CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            for (int k = 0; k < 2; k++) {
+                CKC(cudaEventCreateWithFlags(&ctx->ev_up[k], cudaEventDisableTiming));
+                CKC(cudaEventCreateWithFlags(&ctx->ev_free[k], cudaEventDisableTiming));
+            }
+        }
+    }
+    MsmEngine &E = ctx->msm;
+    // With the engine's per-stage timers on, the MSMs run one after the other (the timers are shared).
+    const bool pipelined = !E.timing && !E.profile;
+    MsmEngine::Pending pend[2];
+    size_t pend_b[2] = {0, 0};
+    auto upload = [&](size_t b) -> int {
+        const int k = (int)(b & 1);
+        if (b >= 2) CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[k], 0)); // MSM b-2 has read stage[k]
+        CKC(cudaMemcpyAsync(stage[k]->p, scalars[b], n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CKC(cudaEventRecord(ctx->ev_up[k], ctx->copy_stream));
+        return 0;
+    };
+    int first_rc = 0;
+    if (!on_device) {
+        // everything enqueued so far on the context stream (an earlier call's reads of the staging buffers) first
+        CKC(cudaEventRecord(ctx->ev_free[0], ctx->stream));
+        CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[0], 0));
+        if ((rc = upload(0)) != 0) return rc;
+    }
+    for (size_t b = 0; b < nb && !first_rc; b++) {
+        const int k = (int)(b & 1);
+        const uint32_t *d_sc = on_device ? (const uint32_t *)scalars[b] : stage[k]->as<uint32_t>();
+        if (!on_device) CKC(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[k], 0));
+        rc = E.enqueue(pts, d_sc, n, use_tab ? &t : nullptr, k, &pend[k]);
+        pend_b[k] = b;
+        if (rc) first_rc = rc;
+        if (!on_device) {
+            CKC(cudaEventRecord(ctx->ev_free[k], ctx->stream));
+            if (b + 1 < nb && !first_rc && (rc = upload(b + 1)) != 0) first_rc = rc;
+        }
+        if (!pipelined) {
+            if (!first_rc && (rc = E.finish(pend[k], &out[b])) != 0) first_rc = rc;
+        } else if (b >= 1 && pend[k ^ 1].active) {
+            if ((rc = E.finish(pend[k ^ 1], &out[b - 1])) != 0 && !first_rc) first_rc = rc;
+        }
+    }
+    // drain whatever is still in flight, older first (also on an error: the landing zones must be quiet on return)
+    for (int i = 0; i < 2; i++) {
+        const int k = (pend[0].active && pend[1].active) ? (pend_b[0] < pend_b[1] ? i : i ^ 1) : i;
+        if (!pend[k].active) continue;
+        rc = E.finish(pend[k], &out[pend_b[k]]);
+        if (rc && !first_rc) first_rc = rc;
+    }
+    if (!on_device) cudaStreamSynchronize(ctx->copy_stream);
+    return first_rc;
 }
 } // extern "C++"
 
@@ -499,6 +587,20 @@ int dvp_msm(dvp_ctx *ctx, int slot, size_t offset, const uint64_t *scalars_mont,
     if ((rc = ctx->scal.reserve(n * 32 + 32)) != 0) return rc;
     if (n) CKC(cudaMemcpyAsync(ctx->scal.p, scalars_mont, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     return dvp_msm_device(ctx, slot, offset, ctx->scal.p, n, out30);
+}
+int dvp_msm_batch(dvp_ctx *ctx, int slot, size_t offset, const uint64_t *const *scalars_mont, size_t n, size_t nb,
+                  int scalars_on_device, uint8_t *out30) {
+    if (!slot_ok(ctx, slot) || (nb && (!out30 || !scalars_mont))) return DVP_ERR_BAD_ARG;
+    SrsSlot &s = ctx->slots[slot];
+    if (offset > s.n || n > s.n - offset) return DVP_ERR_LENGTH_MISMATCH;
+    for (size_t b = 0; b < nb; b++)
+        if (!scalars_mont[b] && n) return DVP_ERR_BAD_ARG;
+    CKC(cudaSetDevice(ctx->device));
+    std::vector<AffPt> r(nb);
+    int rc = slot_msm_batch(ctx, slot, offset, scalars_mont, n, nb, scalars_on_device != 0, r.data());
+    if (rc) return rc;
+    for (size_t b = 0; b < nb; b++) host::encode30(out30 + 30 * b, r[b]);
+    return DVP_OK;
 }
 int dvp_msm_adhoc(dvp_ctx *ctx, const uint8_t *pts30, const uint64_t *scalars_mont, size_t n, uint8_t out30[30]) {
     if (!ctx || !out30 || ((!pts30 || !scalars_mont) && n)) return DVP_ERR_BAD_ARG;

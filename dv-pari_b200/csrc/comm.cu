@@ -16,6 +16,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 #include <mutex>
 #include "ctx.cuh"
 #include "host_gf.hpp"
@@ -179,8 +180,12 @@ int comm_agree(dvp_ctx *ctx, int rc) {
 // (80 bytes per rank): a rank whose MSM failed still takes part, and every rank returns the first failure -- nobody
 // is left waiting in the collective.
 int comm_fold_points(dvp_ctx *ctx, const AffPt &mine, int rc_local, AffPt *total) {
+    return comm_fold_points_n(ctx, &mine, rc_local, 1, total);
+}
+
+int comm_fold_points_n(dvp_ctx *ctx, const AffPt *mine, int rc_local, size_t nb, AffPt *total) {
     if (ctx->world <= 1) {
-        *total = mine;
+        for (size_t b = 0; b < nb; b++) total[b] = mine[b];
         return rc_local;
     }
     struct Slot {
@@ -190,22 +195,26 @@ int comm_fold_points(dvp_ctx *ctx, const AffPt &mine, int rc_local, AffPt *total
     static_assert(sizeof(Slot) == 80, "point + status");
     int rc;
     const size_t W = (size_t)ctx->world;
-    if ((rc = ctx->commbuf.reserve(4096 + (W + 1) * sizeof(Slot))) != 0) return rc_local ? rc_local : rc;
+    if (nb == 0) nb = 1; // the status still travels
+    if ((rc = ctx->commbuf.reserve(4096 + (W + 1) * nb * sizeof(Slot))) != 0) return rc_local ? rc_local : rc;
     Slot *d = reinterpret_cast<Slot *>(ctx->commbuf.as<char>() + 4096);
-    Slot me;
-    me.p = rc_local ? pt_inf() : mine;
-    me.rc = rc_local;
-    me.pad[0] = me.pad[1] = me.pad[2] = 0;
-    CKN(cudaMemcpyAsync(d + W, &me, sizeof(Slot), cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = comm_all_gather(ctx, d + W, d, sizeof(Slot))) != 0) return rc;
-    Slot all[64];
-    CKN(cudaMemcpyAsync(all, d, W * sizeof(Slot), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<Slot> me(nb), all(W * nb);
+    for (size_t b = 0; b < nb; b++) {
+        me[b].p = (rc_local || !mine) ? pt_inf() : mine[b];
+        me[b].rc = rc_local;
+        me[b].pad[0] = me[b].pad[1] = me[b].pad[2] = 0;
+    }
+    CKN(cudaMemcpyAsync(d + W * nb, me.data(), nb * sizeof(Slot), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = comm_all_gather(ctx, d + W * nb, d, nb * sizeof(Slot))) != 0) return rc;
+    CKN(cudaMemcpyAsync(all.data(), d, W * nb * sizeof(Slot), cudaMemcpyDeviceToHost, ctx->stream));
     CKN(cudaStreamSynchronize(ctx->stream));
     for (size_t r = 0; r < W; r++)
-        if (all[r].rc) return all[r].rc;
-    AffPt acc = all[0].p;
-    for (size_t r = 1; r < W; r++) acc = host::aff_add(acc, all[r].p);
-    *total = acc;
+        if (all[r * nb].rc) return all[r * nb].rc;
+    for (size_t b = 0; b < nb; b++) {
+        AffPt acc = all[b].p;
+        for (size_t r = 1; r < W; r++) acc = host::aff_add(acc, all[r * nb + b].p);
+        if (total) total[b] = acc;
+    }
     return DVP_OK;
 }
 
@@ -310,6 +319,22 @@ int dvp_msm_sharded(dvp_ctx *ctx, int slot, const uint64_t *scalars_mont, size_t
     rc = slot_msm(ctx, slot, 0, (const uint32_t *)d_sc, n, &mine);
     if ((rc = comm_fold_points(ctx, mine, rc, &total)) != 0) return rc;
     host::encode30(out30, total);
+    return DVP_OK;
+}
+
+int dvp_msm_sharded_batch(dvp_ctx *ctx, int slot, const uint64_t *const *scalars_mont, size_t n, size_t nb,
+                          int scalars_on_device, uint8_t *out30) {
+    if (!ctx || slot < 0 || slot >= DVP_MAX_SRS_SLOTS || (nb && (!out30 || !scalars_mont))) return DVP_ERR_BAD_ARG;
+    SrsSlot &s = ctx->slots[slot];
+    if (n != s.n) return DVP_ERR_LENGTH_MISMATCH;
+    for (size_t b = 0; b < nb; b++)
+        if (!scalars_mont[b] && n) return DVP_ERR_BAD_ARG;
+    CKN(cudaSetDevice(ctx->device));
+    std::vector<AffPt> mine(nb), total(nb);
+    int rc = slot_msm_batch(ctx, slot, 0, scalars_mont, n, nb, scalars_on_device != 0, mine.data());
+    // one all-gather for the whole batch: nb x (64-byte partial sum + status) per rank
+    if ((rc = comm_fold_points_n(ctx, mine.data(), rc, nb, total.data())) != 0) return rc;
+    for (size_t b = 0; b < nb; b++) host::encode30(out30 + 30 * b, total[b]);
     return DVP_OK;
 }
 

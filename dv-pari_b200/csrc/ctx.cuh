@@ -25,6 +25,11 @@ struct dvp_ctx {
     dvp::MsmEngine msm;
     SrsSlot slots[DVP_MAX_SRS_SLOTS];
     dvp::DevBuf bytes, small, scal, adhoc, commbuf;
+    // batches of MSMs (dvp_msm_batch): the scalars of the next MSM are uploaded on their own stream into a second
+    // staging buffer while the current one runs
+    dvp::DevBuf scal2;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     // multi-GPU: NCCL communicator (ncclComm_t) of this rank, see comm.cu
     void *comm = nullptr;
     struct dvp_local_group *local = nullptr; // or: a group of contexts of this process (dvp_comm_init_local)
@@ -45,5 +50,11 @@ int comm_broadcast(dvp_ctx *ctx, void *buf, size_t bytes, int root);
 int comm_group(dvp_ctx *ctx, bool start);
 int comm_agree(dvp_ctx *ctx, int rc);
 int comm_fold_points(dvp_ctx *ctx, const dvp::AffPt &mine, int rc_local, dvp::AffPt *total);
+// the same for nb partial sums at once (one all-gather): total[b] = sum over the ranks of mine[b]
+int comm_fold_points_n(dvp_ctx *ctx, const dvp::AffPt *mine, int rc_local, size_t nb, dvp::AffPt *total);
+// nb MSMs over slot[offset, offset + n), pipelined: device work of MSM b+1 (and the upload of its scalars when they
+// are host vectors) is enqueued before the host folds the partial sums of MSM b
+int slot_msm_batch(dvp_ctx *ctx, int slot, size_t offset, const uint64_t *const *scalars, size_t n, size_t nb,
+                   bool on_device, dvp::AffPt *out);
 
 int ctx_decode_into(dvp_ctx *ctx, const uint8_t *pts30, size_t n, dvp::AffPt *d_out, int64_t *first_invalid);

@@ -1408,8 +1408,10 @@ int MsmEngine::init(cudaStream_t s) {
     stream = s;
     for (auto &e : ev) CK(cudaEventCreate(&e));
     CK(cudaEventCreateWithFlags(&ev_recode, cudaEventDisableTiming));
-    CK(cudaEventCreate(&ev_t0));
-    CK(cudaEventCreate(&ev_t1));
+    for (int k = 0; k < 2; k++) {
+        CK(cudaEventCreate(&ev_t0[k]));
+        CK(cudaEventCreate(&ev_t1[k]));
+    }
     int rc = msqr_tabs.reserve(MSQ_TABLES * MSQ_TABLE_ELEMS * sizeof(gf));
     if (rc) return rc;
     {
@@ -1444,14 +1446,18 @@ void MsmEngine::destroy() {
     hb.release();
     msqr_tabs.release();
     mg_table.release();
-    if (h_pts) cudaFreeHost(h_pts);
-    h_pts = nullptr;
-    h_pts_cap = 0;
+    for (int k = 0; k < 2; k++) {
+        if (h_pts[k]) cudaFreeHost(h_pts[k]);
+        h_pts[k] = nullptr;
+        h_pts_cap[k] = 0;
+    }
     for (auto &e : ev)
         if (e) cudaEventDestroy(e), e = nullptr;
     if (ev_recode) cudaEventDestroy(ev_recode), ev_recode = nullptr;
-    if (ev_t0) cudaEventDestroy(ev_t0), ev_t0 = nullptr;
-    if (ev_t1) cudaEventDestroy(ev_t1), ev_t1 = nullptr;
+    for (int k = 0; k < 2; k++) {
+        if (ev_t0[k]) cudaEventDestroy(ev_t0[k]), ev_t0[k] = nullptr;
+        if (ev_t1[k]) cudaEventDestroy(ev_t1[k]), ev_t1[k] = nullptr;
+    }
 }
 
 namespace {
@@ -1896,8 +1902,16 @@ int choose_table_windows(size_t n) {
 
 int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, AffPt *h_result, const MsmTable *tab) {
     *h_result = pt_inf();
+    Pending P;
+    int rc = enqueue(d_points, d_scalars, n, tab, 0, &P);
+    if (rc) return rc;
+    return finish(P, h_result);
+}
+
+int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t n, const MsmTable *tab, int k, Pending *P) {
+    P->active = false;
     if (n == 0) return 0;
-    if (n >= (1ull << 31)) return DVP_ERR_BAD_ARG;
+    if (n >= (1ull << 31) || k < 0 || k > 1) return DVP_ERR_BAD_ARG;
     // ---- window layout
     int W, base, rem, c;
     const bool uniform = tab != nullptr;
@@ -1955,13 +1969,14 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     RS(lane_info, 64 * 4);
     RS(hb, (size_t)V * cv * sizeof(AffPt));
     if (!h_lane) CK(cudaMallocHost(&h_lane, 256 * 4));
+    uint32_t *const h_lane_k = (uint32_t *)h_lane + 128 * k;
     const size_t hb_bytes = (size_t)V * cv * sizeof(AffPt);
-    if (h_pts_cap < hb_bytes) {
-        if (h_pts) cudaFreeHost(h_pts);
-        h_pts = nullptr;
-        h_pts_cap = 0;
-        CK(cudaMallocHost(&h_pts, hb_bytes));
-        h_pts_cap = hb_bytes;
+    if (h_pts_cap[k] < hb_bytes) {
+        if (h_pts[k]) cudaFreeHost(h_pts[k]);
+        h_pts[k] = nullptr;
+        h_pts_cap[k] = 0;
+        CK(cudaMallocHost(&h_pts[k], hb_bytes));
+        h_pts_cap[k] = hb_bytes;
     }
     struct Part {
         uint32_t v0, vn;
@@ -1993,7 +2008,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     // middle.  (Larger MSMs keep the exact sizes: twice the scratch would be gigabytes.)
     const bool nosync = persistent_any && !timing && total <= ((size_t)1 << 25);
     cudaStream_t st = stream;
-    cudaEventRecord(ev_t0, st);
+    cudaEventRecord(ev_t0[k], st);
     if (timing) cudaEventRecord(ev[0], st);
     // ---- recode + histogram, counting sort of all (point, window) entries by bucket (context stream)
     uint32_t *d_len_all = len_all.as<uint32_t>(), *d_start_all = start_all.as<uint32_t>();
@@ -2015,7 +2030,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
             CK(cudaMemsetAsync(lane_info.p, 0, 32 * 4, st));
             k_lane_info<<<dim3(std::max(1u, std::min(148u, cdiv(NB / NL, 1024))), NL), 256, 0, st>>>(
                 d_len_all, d_start_all, lane_info.as<uint32_t>() + 32, lane_info.as<uint32_t>());
-            CK(cudaMemcpyAsync(h_lane, lane_info.p, 2 * NL * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(h_lane_k, lane_info.p, 2 * NL * 4, cudaMemcpyDeviceToHost, st));
         }
         CK(cudaGetLastError());
     }
@@ -2029,8 +2044,8 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     stt.tables = uniform ? 1 : 0;
     for (int l = 0; l < NL; l++) {
         Part &p = part[l];
-        p.total = nosync ? total : ((const uint32_t *)h_lane)[2 * l];
-        p.maxlen = nosync ? (uint32_t)std::min<size_t>(total, 0xffffffffu) : ((const uint32_t *)h_lane)[2 * l + 1];
+        p.total = nosync ? total : h_lane_k[2 * l];
+        p.maxlen = nosync ? (uint32_t)std::min<size_t>(total, 0xffffffffu) : h_lane_k[2 * l + 1];
         if (!nosync) stt.adds_total += p.total;
         MsmLane &L = lanes[l];
         const size_t nseg_max = std::max<size_t>(p.nseg, std::max(p.nseg_a, p.nseg_b)) + 1;
@@ -2185,21 +2200,50 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
         CK(cudaStreamWaitEvent(st, lanes[l].done, 0));
         launches += lanes[l].launches;
     }
-    CK(cudaMemcpyAsync(h_pts, hb.as<AffPt>(), hb_bytes, cudaMemcpyDeviceToHost, st));
-    uint32_t *h_acc = (uint32_t *)h_lane + 64; // per lane: 2 control blocks x (abort flag, rounds, additions r0, additions)
+    CK(cudaMemcpyAsync(h_pts[k], hb.as<AffPt>(), hb_bytes, cudaMemcpyDeviceToHost, st));
+    uint32_t *h_acc = h_lane_k + 64; // per lane: 2 control blocks x (abort flag, rounds, additions r0, additions)
     if (persistent_any)
         for (int l = 0; l < NL; l++)
-            for (int k = 0; k < 2; k++) {
-                const uint32_t *ctl = lanes[l].acc_ctl.as<uint32_t>() + k * ACC_CTL_WORDS;
-                CK(cudaMemcpyAsync(h_acc + (2 * l + k) * 4, ctl + 1, 4, cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(h_acc + (2 * l + k) * 4 + 1, ctl + 64, 12, cudaMemcpyDeviceToHost, st));
+            for (int q = 0; q < 2; q++) {
+                const uint32_t *ctl = lanes[l].acc_ctl.as<uint32_t>() + q * ACC_CTL_WORDS;
+                CK(cudaMemcpyAsync(h_acc + (2 * l + q) * 4, ctl + 1, 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(h_acc + (2 * l + q) * 4 + 1, ctl + 64, 12, cudaMemcpyDeviceToHost, st));
             }
     if (timing) {
-        if (!persistent_any) CK(cudaMemcpyAsync(h_lane, lanes[0].info_r0.p, 16, cudaMemcpyDeviceToHost, st));
+        if (!persistent_any) CK(cudaMemcpyAsync(h_lane_k, lanes[0].info_r0.p, 16, cudaMemcpyDeviceToHost, st));
         cudaEventRecord(ev[1], st);
     }
-    cudaEventRecord(ev_t1, st);
-    CK(cudaStreamSynchronize(st));
+    CK(cudaEventRecord(ev_t1[k], st));
+    P->active = true;
+    P->uniform = uniform;
+    P->persistent_any = persistent_any;
+    P->nosync = nosync;
+    P->k = k;
+    P->c = c;
+    P->cv = cv;
+    P->base = base;
+    P->rem = rem;
+    P->NL = NL;
+    P->V = V;
+    P->nbv = nbv;
+    P->launches = launches;
+    P->stt = stt;
+    return 0;
+}
+
+int MsmEngine::finish(Pending &P, AffPt *h_result) {
+    *h_result = pt_inf();
+    if (!P.active) return 0;
+    P.active = false;
+    const int k = P.k, NL = P.NL, c = P.c, cv = P.cv, base = P.base, rem = P.rem;
+    const bool uniform = P.uniform, persistent_any = P.persistent_any, nosync = P.nosync;
+    const uint32_t V = P.V, nbv = P.nbv;
+    const unsigned long long launches = P.launches;
+    MsmStats stt = P.stt;
+    cudaStream_t st = stream;
+    uint32_t *const h_lane_k = (uint32_t *)h_lane + 128 * k;
+    uint32_t *h_acc = h_lane_k + 64;
+    CK(cudaEventSynchronize(ev_t1[k]));
     if (persistent_any) {
         int rmax = 0;
         unsigned long long adds = 0;
@@ -2212,20 +2256,20 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     }
     if (persistent_any)
         for (int l = 0; l < NL; l++)
-            for (int k = 0; k < 2; k++)
-                if (h_acc[(2 * l + k) * 4]) {
-                    fprintf(stderr, "[dvpari] k_accumulate gave up at a grid barrier (lane %d, launch %d)\n", l, k);
+            for (int q = 0; q < 2; q++)
+                if (h_acc[(2 * l + q) * 4]) {
+                    fprintf(stderr, "[dvpari] k_accumulate gave up at a grid barrier (lane %d, launch %d)\n", l, q);
                     return DVP_ERR_INTERNAL;
                 }
     float ms_dev = 0;
-    cudaEventElapsedTime(&ms_dev, ev_t0, ev_t1);
+    cudaEventElapsedTime(&ms_dev, ev_t0[k], ev_t1[k]);
 
     // ---- host tail.  Virtual window v holds buckets of digit values dbase_v + b + 1 (b local) at bit offset
     // off_v: sum_b (dbase_v + b + 1) B_b = sum_q 2^q H[v][q] + (dbase_v + 1) S[v]; one double-and-add pass
     // over all positions.  (Separate sets: off_v = the window's offset, dbase_v = 0.  Shared set: off_v = 0.)
     const auto t_host0 = std::chrono::steady_clock::now();
     {
-        const AffPt *hp = (const AffPt *)h_pts;
+        const AffPt *hp = (const AffPt *)h_pts[k];
         const int npos = uniform ? c + 1 : 233 + c + 1;
         std::vector<std::vector<uint32_t>> at(npos + 1);
         for (uint32_t v = 0; v < V; v++) {
@@ -2254,7 +2298,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
                 const auto &r = lanes[l].prof[i];
                 float ms = 0, t0 = 0;
                 cudaEventElapsedTime(&ms, r.e0, r.e1);
-                cudaEventElapsedTime(&t0, ev_t0, r.e0);
+                cudaEventElapsedTime(&t0, ev_t0[k], r.e0);
                 prof_ms[r.cat] += ms;
                 prof_n[r.cat]++;
                 timeline.push_back({(float)l, (float)r.cat, t0, t0 + ms}); // Gantt row: lane, category, start, end (ms)
@@ -2296,7 +2340,7 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
             stt.adds_round0 = h_acc[3];
             stt.rounds_main = (int)h_acc[1];
         } else {
-            stt.adds_round0 = ((const uint32_t *)h_lane)[1]; // info of lane 0's first plan
+            stt.adds_round0 = h_lane_k[1]; // info of lane 0's first plan
         }
     }
     last = stt;

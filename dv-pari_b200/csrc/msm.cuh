@@ -71,10 +71,13 @@ struct MsmEngine {
     cudaStream_t stream = nullptr; // the context's stream: recode, final read-back
     std::vector<MsmLane> lanes;
     DevBuf keys, entries, len_all, start_all, cursor_all, scan_blk, lane_info, hb, msqr_tabs, mg_table;
-    void *h_lane = nullptr; // pinned: per-lane (entries, longest bucket)
-    void *h_pts = nullptr; // pinned, receives the per-bit partial sums
-    size_t h_pts_cap = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}, ev_recode = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    // Host-side landing zones come in two sets (index k of MsmPending), so that the device work of the next MSM of a
+    // batch can be enqueued before the host has folded the partial sums of the previous one.
+    void *h_lane = nullptr; // pinned, 2 x 128 words: per-lane (entries, longest bucket) | control words of k_accumulate
+    void *h_pts[2] = {nullptr, nullptr}; // pinned, receive the per-bit partial sums
+    size_t h_pts_cap[2] = {0, 0};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}, ev_recode = nullptr, ev_t0[2] = {nullptr, nullptr},
+                ev_t1[2] = {nullptr, nullptr};
     MsmStats last;
     int force_window_bits = 0; // 0 = choose from n
     int force_lanes = 0;       // 0 = choose from n
@@ -110,6 +113,19 @@ struct MsmEngine {
     // Result: affine E[r] point (or infinity) on the host.  Returns 0 or a DVP_ERR_* code.
     // With `tab`, d_points is the base of the tables and the MSM runs over points [tab->offset, tab->offset + n).
     int run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, AffPt *h_result, const MsmTable *tab = nullptr);
+    // The two halves of run(): enqueue() puts the whole device side of an MSM on the streams (no host wait on the
+    // persistent path) and leaves the partial sums on their way to landing zone k; finish() waits for them and folds
+    // them on the host.  Between the two the caller may enqueue the next MSM (with the other k): the engine's device
+    // scratch is reused in stream order, only the landing zones are per-k.
+    struct Pending {
+        bool active = false, uniform = false, persistent_any = false, nosync = false;
+        int k = 0, c = 0, cv = 0, base = 0, rem = 0, NL = 0;
+        uint32_t V = 0, nbv = 0;
+        unsigned long long launches = 0;
+        MsmStats stt;
+    };
+    int enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t n, const MsmTable *tab, int k, Pending *P);
+    int finish(Pending &P, AffPt *h_result);
     // d_tab[j * n + i] = 2^(off_j) d_points[i] for j < W (d_tab holds W n points; j = 0 is a copy)
     int build_table(const AffPt *d_points, size_t n, int W, AffPt *d_tab);
     // d_out[i] = scalars[i] * G (batched fixed-base multiplication of the generator), all on the device

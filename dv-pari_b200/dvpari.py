@@ -76,6 +76,8 @@ def lib():
         L.dvp_msm.argtypes = [vp, i32, sz, vp, sz, vp]
         L.dvp_msm_device.argtypes = [vp, i32, sz, vp, sz, vp]
         L.dvp_msm_adhoc.argtypes = [vp, vp, vp, sz, vp]
+        L.dvp_msm_batch.argtypes = [vp, i32, sz, vp, sz, sz, i32, vp]
+        L.dvp_msm_sharded_batch.argtypes = [vp, i32, vp, sz, sz, i32, vp]
         L.dvp_msm_last_stats.argtypes = [vp, C.POINTER(MsmStats)]
         L.dvp_msm_last_profile.argtypes = [vp, vp, vp]
         L.dvp_msm_last_timeline.argtypes = [vp, vp, sz, C.POINTER(sz)]
@@ -225,6 +227,29 @@ class Context:
         _ck(lib().dvp_msm_device(self._h, slot, offset, d_scalars, n, _ptr(out)), "dvp_msm_device")
         return out.tobytes()
 
+    @staticmethod
+    def _batch_ptrs(vectors, on_device, n):
+        """(array of nb pointers, n, keep-alive list) for the batched calls: host vectors (n,4) uint64 each, or device
+        pointers with on_device=True and n given."""
+        if on_device:
+            keep = []
+            ptrs = (C.c_void_p * len(vectors))(*[C.c_void_p(int(getattr(v, "value", v))) for v in vectors])
+            return ptrs, n, keep
+        keep = [np.ascontiguousarray(v, dtype=np.uint64).reshape(-1, 4) for v in vectors]
+        if any(k.shape[0] != keep[0].shape[0] for k in keep):
+            raise DvpError(5, "multi_scalar_mul_batch: scalar vectors of different lengths")
+        ptrs = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
+        return ptrs, (keep[0].shape[0] if keep else 0), keep
+
+    def multi_scalar_mul_batch(self, vectors, slot, offset=0, on_device=False, n=None):
+        """len(vectors) calls of multi_scalar_mul over the same points, pipelined (dvp_msm_batch): the upload and the
+        device side of the next MSM overlap the current one.  Returns the list of 30-byte sums."""
+        ptrs, n, keep = self._batch_ptrs(vectors, on_device, n)
+        out = np.zeros((max(1, len(vectors)), 30), dtype=np.uint8)
+        _ck(lib().dvp_msm_batch(self._h, slot, offset, ptrs, n, len(vectors), 1 if on_device else 0, _ptr(out)),
+            "dvp_msm_batch")
+        return [out[b].tobytes() for b in range(len(vectors))]
+
     def multi_scalar_mul_adhoc(self, scalars_mont, pts30):
         s = np.ascontiguousarray(scalars_mont, dtype=np.uint64).reshape(-1, 4)
         a = np.ascontiguousarray(pts30, dtype=np.uint8).reshape(-1, 30)
@@ -254,6 +279,14 @@ class Context:
             s = np.ascontiguousarray(scalars_mont, dtype=np.uint64).reshape(-1, 4)
             _ck(lib().dvp_msm_sharded(self._h, slot, _ptr(s), s.shape[0], 0, _ptr(out)), "dvp_msm_sharded")
         return out.tobytes()
+
+    def msm_sharded_batch(self, vectors, slot=0, on_device=False, n=None):
+        """msm_sharded for a batch of scalar vectors: pipelined local MSMs, one all-gather for all partial sums."""
+        ptrs, n, keep = self._batch_ptrs(vectors, on_device, n)
+        out = np.zeros((max(1, len(vectors)), 30), dtype=np.uint8)
+        _ck(lib().dvp_msm_sharded_batch(self._h, slot, ptrs, n, len(vectors), 1 if on_device else 0, _ptr(out)),
+            "dvp_msm_sharded_batch")
+        return [out[b].tobytes() for b in range(len(vectors))]
 
     def msm_stats(self):
         st = MsmStats()

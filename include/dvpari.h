@@ -93,6 +93,16 @@ int dvp_srs_read(dvp_ctx *ctx, int slot, size_t offset, size_t n, uint8_t *pts30
 int dvp_msm(dvp_ctx *ctx, int slot, size_t offset, const uint64_t *scalars_mont, size_t n, uint8_t out30[30]);
 /* Same with the scalars already in device memory (n x 32 bytes). */
 int dvp_msm_device(dvp_ctx *ctx, int slot, size_t offset, const void *d_scalars_mont, size_t n, uint8_t out30[30]);
+/*
+ * nb calls of multi_scalar_mul over the SAME points (src/curve.rs:141-158 called once per scalar vector, as a prover
+ * that serves several witnesses against one SRS does): scalars_mont[b] is the b-th vector (n x 4 u64 Montgomery
+ * limbs; host pointers, or device pointers if scalars_on_device), out30 + 30 b receives its sum.  The calls are
+ * pipelined: the device side of MSM b+1 is enqueued, and its scalars are uploaded on a copy stream into a second
+ * staging buffer, while MSM b runs; the host folds the partial sums of MSM b meanwhile.  Results are the same bytes
+ * as nb separate dvp_msm calls.
+ */
+int dvp_msm_batch(dvp_ctx *ctx, int slot, size_t offset, const uint64_t *const *scalars_mont, size_t n, size_t nb,
+                  int scalars_on_device, uint8_t *out30);
 /* One-shot form with encoded points from the host: decode + MSM (src/srs.rs:422). */
 int dvp_msm_adhoc(dvp_ctx *ctx, const uint8_t *pts30, const uint64_t *scalars_mont, size_t n, uint8_t out30[30]);
 int dvp_msm_last_stats(dvp_ctx *ctx, dvp_msm_stats *out);
@@ -126,6 +136,11 @@ void dvp_shard_range(size_t total, int rank, int world, size_t *lo, size_t *hi);
  * (host memory, or device memory if scalars_on_device); every rank receives the encoding of the whole sum. */
 int dvp_msm_sharded(dvp_ctx *ctx, int slot, const uint64_t *scalars_mont, size_t n, int scalars_on_device,
                     uint8_t out30[30]);
+
+/* The batched form (see dvp_msm_batch): the nb local MSMs are pipelined and ONE all-gather carries the nb partial sums
+ * of every rank (nb x 80 bytes per rank). */
+int dvp_msm_sharded_batch(dvp_ctx *ctx, int slot, const uint64_t *const *scalars_mont, size_t n, size_t nb,
+                          int scalars_on_device, uint8_t *out30);
 
 /* CurvePoint::add on encodings (src/curve.rs:76-82): out = a (+) b.  Runs on the device of ctx. */
 int dvp_point_add(dvp_ctx *ctx, const uint8_t a30[30], const uint8_t b30[30], uint8_t out30[30]);

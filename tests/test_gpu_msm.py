@@ -257,3 +257,52 @@ def test_msm_beside_saturating_work_on_the_same_gpu(oracle):
     finally:
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.parametrize("n", [0, 1, 777, 5003, (1 << 17) + 13])
+def test_msm_batch_equals_single_calls_and_oracle(ctx, oracle, n):
+    """dvp_msm_batch (pipelined calls of multi_scalar_mul over one point vector, curve.rs:141-158): same bytes as one
+    dvp_msm per vector and as the oracle -- host vectors and device vectors, batches of 1, 2, 3 and 5, on the
+    separate-launch path (small n, mid-MSM read-back) and on the persistent path (2^17 + 13 points)."""
+    O = oracle
+    pts = O.mul_batch(O.generator(), dvpari.random_fr_mont(n, 900 + n % 7)) if n else None
+    ctx.srs_load(3, O.encode_batch(pts) if n else np.zeros((0, 30), dtype=np.uint8))
+    vecs = [dvpari.random_fr_mont(n, 1000 + 31 * b + n % 11) for b in range(5)]
+    if n:
+        vecs[1][: min(n, 40)] = 0  # a vector with zero scalars, one with repeated scalars
+        vecs[2][:] = vecs[2][0]
+    single = [ctx.multi_scalar_mul(v, 3) for v in vecs]
+    nchk = 5 if n <= 5003 else 2
+    for b in range(nchk):
+        assert single[b] == (O.pt_encode(O.msm(vecs[b], pts, 0)) if n else bytes(30)), b
+    for nb in (1, 2, 3, 5):
+        assert ctx.multi_scalar_mul_batch(vecs[:nb], 3) == single[:nb], (n, nb)
+    d = [ctx.dev_alloc(max(32, n * 32)) for _ in vecs]
+    try:
+        for p, v in zip(d, vecs):
+            if n:
+                ctx.dev_upload(p, v)
+        for nb in (1, 4, 5):
+            assert ctx.multi_scalar_mul_batch(d[:nb], 3, on_device=True, n=n) == single[:nb], (n, nb)
+        # a batch followed by a plain call and another batch: the staging buffers and landing zones are reusable
+        assert ctx.multi_scalar_mul(vecs[4], 3) == single[4]
+        assert ctx.multi_scalar_mul_batch(list(reversed(vecs)), 3) == list(reversed(single))
+        # with the stage timers on the batch runs unpipelined and still returns the same bytes
+        ctx.set("timing", 1)
+        assert ctx.multi_scalar_mul_batch(vecs[:3], 3) == single[:3]
+        ctx.set("timing", 0)
+    finally:
+        for p in d:
+            ctx.dev_free(p)
+        ctx.srs_free(3)
+
+
+def test_msm_batch_rejects_bad_arguments(ctx):
+    ctx.srs_random(3, 100, 5)
+    v = dvpari.random_fr_mont(100, 1)
+    with pytest.raises(dvpari.DvpError):
+        ctx.multi_scalar_mul_batch([v, v[:50]], 3)  # ragged batch
+    with pytest.raises(dvpari.DvpError):
+        ctx.multi_scalar_mul_batch([dvpari.random_fr_mont(101, 1)], 3)  # longer than the slot (curve.rs:142)
+    assert ctx.multi_scalar_mul_batch([], 3) == []
+    ctx.srs_free(3)

@@ -46,12 +46,16 @@ def test_sharded_prove_on_one_gpu_is_bit_exact(oracle, world, lg):
     pts = O.mul_batch(O.generator(), dvpari.random_fr_mont(m, 12))
     enc = O.encode_batch(pts)
     want_msm = O.pt_encode(O.msm(sc, pts, 0))
+    sc2 = dvpari.random_fr_mont(m, 13 + world)
+    want_msm2 = O.pt_encode(O.msm(sc2, pts, 0))
 
     def rank_body(r):
         ctx = ctxs[r]
         lo, hi = dvpari.shard_range(m, r, world)
         ctx.srs_load(6, enc[lo:hi])
         got_msm = ctx.msm_sharded(sc[lo:hi], 6)
+        # the batched form: pipelined local MSMs, one all-gather for the three partial sums of every rank
+        got_batch = ctx.msm_sharded_batch([sc[lo:hi], sc2[lo:hi], sc[lo:hi]], 6)
         inst = dvpari.R1CSInstance(ctx, circ["nrows"], k, circ["nwires"], circ["rowptr"], circ["wire"], circ["coeff"],
                                    circ["coeffs_mont"])
         for slot, s in enumerate(scs):
@@ -76,7 +80,7 @@ def test_sharded_prove_on_one_gpu_is_bit_exact(oracle, world, lg):
         proof3, st = prover.prove(w[1:1 + k], w[1 + k:], want_stages=True)
         stages_ok = proof3 == proof and st[:8 * n].tobytes() == want_st[:8 * n].tobytes()
         prover.close(); inst.close(); gd.close()
-        return got_msm, proof, bad, proof2, stages_ok
+        return got_msm, proof, bad, proof2, stages_ok, got_batch
 
     try:
         res = dvpari.run_ranks(rank_body, world)
@@ -84,8 +88,9 @@ def test_sharded_prove_on_one_gpu_is_bit_exact(oracle, world, lg):
         for c in ctxs:
             c.comm_destroy()
             c.close()
-    for r, (got_msm, proof, bad, proof2, stages_ok) in enumerate(res):
+    for r, (got_msm, proof, bad, proof2, stages_ok, got_batch) in enumerate(res):
         assert got_msm == want_msm, r
+        assert got_batch == [want_msm, want_msm2, want_msm], r
         assert stages_ok, f"rank {r}/{world}: stage vectors of the sharded prove differ from the oracle's"
         assert proof == want, f"rank {r}/{world}: sharded proof differs from the oracle's"
         assert proof2 == want
