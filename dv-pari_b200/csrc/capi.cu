@@ -259,6 +259,7 @@ void dvp_ctx_destroy(dvp_ctx *ctx) {
         if (ctx->ev_up[k]) cudaEventDestroy(ctx->ev_up[k]);
         if (ctx->ev_free[k]) cudaEventDestroy(ctx->ev_free[k]);
     }
+    if (ctx->ev_batch) cudaEventDestroy(ctx->ev_batch);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
@@ -355,6 +356,10 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
         ctx->msm.timing = value != 0;
         return DVP_OK;
     }
+    if (!strcmp(name, "msm_sort_ahead")) { // batches: sort MSM b+1 on a side stream while MSM b runs (default 1)
+        ctx->msm.sort_ahead = value != 0;
+        return DVP_OK;
+    }
     return DVP_ERR_BAD_ARG;
 }
 
@@ -426,16 +431,16 @@ int slot_msm_batch(dvp_ctx *ctx, int slot, size_t offset, const uint64_t *const 
     int rc = slot_points(ctx, slot, offset, n, &pts, &t, &use_tab);
     if (rc) return rc;
     DevBuf *stage[2] = {&ctx->scal, &ctx->scal2};
-    if (!on_device) {
+    if (!on_device)
         for (int k = 0; k < (nb > 1 ? 2 : 1); k++)
             if ((rc = stage[k]->reserve(n * 32 + 32)) != 0) return rc;
-        if (!ctx->copy_stream) {
-            CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-            for (int k = 0; k < 2; k++) {
-                CKC(cudaEventCreateWithFlags(&ctx->ev_up[k], cudaEventDisableTiming));
-                CKC(cudaEventCreateWithFlags(&ctx->ev_free[k], cudaEventDisableTiming));
-            }
+    if (!ctx->copy_stream) {
+        CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            CKC(cudaEventCreateWithFlags(&ctx->ev_up[k], cudaEventDisableTiming));
+            CKC(cudaEventCreateWithFlags(&ctx->ev_free[k], cudaEventDisableTiming));
         }
+        CKC(cudaEventCreateWithFlags(&ctx->ev_batch, cudaEventDisableTiming));
     }
     MsmEngine &E = ctx->msm;
     // With the engine's per-stage timers on, the MSMs run one after the other (the timers are shared).
@@ -450,17 +455,19 @@ int slot_msm_batch(dvp_ctx *ctx, int slot, size_t offset, const uint64_t *const 
         return 0;
     };
     int first_rc = 0;
+    // everything enqueued so far on the context stream comes first (device vectors may have been written on it, an
+    // earlier call may still read the staging buffers); after that the scalars of MSM b are valid once ev_up fires
+    // (host vectors) or at once (device vectors), whatever else the batch has queued on the context stream -- which
+    // is what lets the engine sort MSM b+1 while MSM b is still running
+    CKC(cudaEventRecord(ctx->ev_batch, ctx->stream));
     if (!on_device) {
-        // everything enqueued so far on the context stream (an earlier call's reads of the staging buffers) first
-        CKC(cudaEventRecord(ctx->ev_free[0], ctx->stream));
-        CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[0], 0));
+        CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_batch, 0));
         if ((rc = upload(0)) != 0) return rc;
     }
     for (size_t b = 0; b < nb && !first_rc; b++) {
         const int k = (int)(b & 1);
         const uint32_t *d_sc = on_device ? (const uint32_t *)scalars[b] : stage[k]->as<uint32_t>();
-        if (!on_device) CKC(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[k], 0));
-        rc = E.enqueue(pts, d_sc, n, use_tab ? &t : nullptr, k, &pend[k]);
+        rc = E.enqueue(pts, d_sc, n, use_tab ? &t : nullptr, k, &pend[k], pipelined, on_device ? ctx->ev_batch : ctx->ev_up[k]);
         pend_b[k] = b;
         if (rc) first_rc = rc;
         if (!on_device) {

@@ -29,7 +29,7 @@ struct dvp_ctx {
     // staging buffer while the current one runs
     dvp::DevBuf scal2;
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_batch = nullptr;
     // multi-GPU: NCCL communicator (ncclComm_t) of this rank, see comm.cu
     void *comm = nullptr;
     struct dvp_local_group *local = nullptr; // or: a group of contexts of this process (dvp_comm_init_local)

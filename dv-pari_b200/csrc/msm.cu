@@ -1412,6 +1412,11 @@ int MsmEngine::init(cudaStream_t s) {
         CK(cudaEventCreate(&ev_t0[k]));
         CK(cudaEventCreate(&ev_t1[k]));
     }
+    {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        CK(cudaStreamCreateWithPriority(&sort_stream, cudaStreamNonBlocking, prio_lo));
+    }
     int rc = msqr_tabs.reserve(MSQ_TABLES * MSQ_TABLE_ELEMS * sizeof(gf));
     if (rc) return rc;
     {
@@ -1436,6 +1441,10 @@ void MsmEngine::destroy() {
     lanes.clear();
     keys.release();
     entries.release();
+    entries_b.release();
+    len_all_b.release();
+    start_all_b.release();
+    if (sort_stream) cudaStreamDestroy(sort_stream), sort_stream = nullptr;
     start_all.release();
     cursor_all.release();
     scan_blk.release();
@@ -1908,7 +1917,8 @@ int MsmEngine::run(const AffPt *d_points, const uint32_t *d_scalars, size_t n, A
     return finish(P, h_result);
 }
 
-int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t n, const MsmTable *tab, int k, Pending *P) {
+int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t n, const MsmTable *tab, int k, Pending *P,
+                       bool ahead, cudaEvent_t scalars_ready) {
     P->active = false;
     if (n == 0) return 0;
     if (n >= (1ull << 31) || k < 0 || k > 1) return DVP_ERR_BAD_ARG;
@@ -1949,6 +1959,7 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
     // grid (2^20: 6.95 ms against 7.17); the separate-launch path keeps two lanes (2^22: 22.2 against 23.8 ms).
     const bool persistent_any =
         acc_capacity > 0 && (use_accumulate == 2 || (use_accumulate == 1 && n >= ((size_t)1 << 17) && n < ((size_t)3 << 20)));
+    const bool nosync = persistent_any && !timing && total <= ((size_t)1 << 25);
     int NL = (profile && !force_lanes) ? 1 : force_lanes ? force_lanes : persistent_any ? 1 : (n >= (1u << 13) ? 2 : 1);
     NL = std::max(1, std::min<int>(NL, (int)V));
     while ((int)lanes.size() < NL) {
@@ -1960,10 +1971,15 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
     int rc;
 #define RS(buf, bytes) \
     if ((rc = (buf).reserve(bytes)) != 0) return rc
+    // sort ahead: on its own stream, into buffer set k, ordered only after the scalars and after the MSM that used
+    // set k before (two MSMs back in a pipelined batch)
+    const bool side = ahead && sort_ahead && nosync && !profile && sort_stream;
+    DevBuf &entries_k = (side && k) ? entries_b : entries, &len_k = (side && k) ? len_all_b : len_all,
+           &start_k = (side && k) ? start_all_b : start_all;
     RS(keys, total * 4);
-    RS(entries, total * 4);
-    RS(len_all, (NB + 1) * 4);
-    RS(start_all, (NB + 1) * 4);
+    RS(entries_k, total * 4);
+    RS(len_k, (NB + 1) * 4);
+    RS(start_k, (NB + 1) * 4);
     RS(cursor_all, (NB + 1) * 4);
     RS(scan_blk, (NB / SCAN_TILE + 8) * 8);
     RS(lane_info, 64 * 4);
@@ -2006,12 +2022,19 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
     // With the persistent kernel the host needs nothing from the sort: the rounds are counted on the device and the
     // scratch is sized from upper bounds (every entry in one lane), so the MSM is enqueued without a read-back in the
     // middle.  (Larger MSMs keep the exact sizes: twice the scratch would be gigabytes.)
-    const bool nosync = persistent_any && !timing && total <= ((size_t)1 << 25);
     cudaStream_t st = stream;
     cudaEventRecord(ev_t0[k], st);
     if (timing) cudaEventRecord(ev[0], st);
-    // ---- recode + histogram, counting sort of all (point, window) entries by bucket (context stream)
-    uint32_t *d_len_all = len_all.as<uint32_t>(), *d_start_all = start_all.as<uint32_t>();
+    // ---- recode + histogram, counting sort of all (point, window) entries by bucket (context stream, or ahead of it)
+    uint32_t *d_len_all = len_k.as<uint32_t>(), *d_start_all = start_k.as<uint32_t>();
+    const cudaStream_t st_main = st;
+    if (side) {
+        st = sort_stream;
+        if (scalars_ready) CK(cudaStreamWaitEvent(st, scalars_ready, 0));
+        CK(cudaStreamWaitEvent(st, ev_t1[k], 0)); // the MSM that read set k before (never recorded: no wait)
+    } else if (scalars_ready) {
+        CK(cudaStreamWaitEvent(st, scalars_ready, 0));
+    }
     CK(cudaMemsetAsync(d_len_all, 0, NB * 4, st));
     k_recode_count<<<cdiv(n, 128), 128, 0, st>>>(d_scalars, (uint32_t)n, base, rem, W, nb, uniform ? 1 : 0,
                                                  keys.as<uint32_t>(), d_len_all);
@@ -2024,7 +2047,7 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
         k_scatter<<<cdiv(total, 256), 256, 0, st>>>(keys.as<uint32_t>(), (uint32_t)n, total,
                                                     uniform ? (uint32_t)tab->offset : 0u,
                                                     uniform ? (uint32_t)tab->stride : 0u, cursor_all.as<uint32_t>(),
-                                                    entries.as<uint32_t>());
+                                                    entries_k.as<uint32_t>());
         if (!nosync) {
             CK(cudaMemcpyAsync(lane_info.as<uint32_t>() + 32, bounds, (NL + 1) * 4, cudaMemcpyHostToDevice, st));
             CK(cudaMemsetAsync(lane_info.p, 0, 32 * 4, st));
@@ -2035,6 +2058,7 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(ev_recode, st));
+    st = st_main;
     unsigned long long launches = nosync ? 6 : 7;
     if (!nosync) CK(cudaStreamSynchronize(st)); // the read-back: entries and longest bucket per lane size the rounds
     MsmStats stt;
@@ -2085,6 +2109,9 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
         L.launches = 0;
         L.prof_used = 0;
         CK(cudaStreamWaitEvent(L.stream, ev_recode, 0));
+        // sorted ahead: nothing on the context stream orders this MSM after the read-back of the previous one's
+        // partial sums (hb is shared), so the lane waits for it itself
+        if (side) CK(cudaStreamWaitEvent(L.stream, ev_t1[k ^ 1], 0));
         if (timing && l == 0) cudaEventRecord(L.ev_s[0], L.stream);
         Tree tree(*this, L);
         const uint32_t *len0 = d_len_all + bounds[l], *start0 = d_start_all + bounds[l];
@@ -2096,16 +2123,16 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
         if (persistent) {
             // every round of the bucket accumulation in one persistent launch; the lanes' kernels share the SMs
             if (timing && l == 0) cudaEventRecord(L.ev_k[0], L.stream);
-            if ((rc = tree.accumulate(d_points, entries.as<uint32_t>(), start0, len0, p.nseg, p.total, L.buckets.as<AffPt>(),
+            if ((rc = tree.accumulate(d_points, entries_k.as<uint32_t>(), start0, len0, p.nseg, p.total, L.buckets.as<AffPt>(),
                                       -1, 0, acc_grid)))
                 return rc;
             if (timing && l == 0) cudaEventRecord(L.ev_k[1], L.stream);
             while ((1ull << r_main) < p.maxlen) r_main++;
         } else {
-            if ((rc = tree.plan0(start0, len0, entries.as<uint32_t>(), p.nseg, d_points))) return rc;
+            if ((rc = tree.plan0(start0, len0, entries_k.as<uint32_t>(), p.nseg, d_points))) return rc;
             if (timing && l == 0) CK(cudaMemcpyAsync(L.info_r0.p, L.info.p, 16, cudaMemcpyDeviceToDevice, L.stream));
             L.want_k = timing && l == 0;
-            rc = tree.rounds(d_points, entries.as<uint32_t>(), start0, len0, p.nseg, p.total, p.maxlen,
+            rc = tree.rounds(d_points, entries_k.as<uint32_t>(), start0, len0, p.nseg, p.total, p.maxlen,
                              L.buckets.as<AffPt>(), &r_main);
             if (rc) return rc;
             L.want_k = false;

@@ -71,6 +71,11 @@ struct MsmEngine {
     cudaStream_t stream = nullptr; // the context's stream: recode, final read-back
     std::vector<MsmLane> lanes;
     DevBuf keys, entries, len_all, start_all, cursor_all, scan_blk, lane_info, hb, msqr_tabs, mg_table;
+    // second set of the sort's outputs (sorted entries, bucket lengths and starts): in a pipelined batch the sort of
+    // the next MSM runs on `sort_stream` while the current MSM is still reading its own set
+    DevBuf entries_b, len_all_b, start_all_b;
+    cudaStream_t sort_stream = nullptr; // low priority: fills the latency-bound reduction phase of the MSM before
+    int sort_ahead = 1;                 // 0: never sort ahead (every MSM starts after the previous one's read-back)
     // Host-side landing zones come in two sets (index k of MsmPending), so that the device work of the next MSM of a
     // batch can be enqueued before the host has folded the partial sums of the previous one.
     void *h_lane = nullptr; // pinned, 2 x 128 words: per-lane (entries, longest bucket) | control words of k_accumulate
@@ -124,7 +129,11 @@ struct MsmEngine {
         unsigned long long launches = 0;
         MsmStats stt;
     };
-    int enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t n, const MsmTable *tab, int k, Pending *P);
+    // `ahead`: the caller guarantees that the scalars are valid once `scalars_ready` has fired (nullptr: already) no
+    // matter what else is queued on the engine's stream; the recode + counting sort may then start before the
+    // previous MSM has finished (persistent path only).
+    int enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t n, const MsmTable *tab, int k, Pending *P,
+                bool ahead = false, cudaEvent_t scalars_ready = nullptr);
     int finish(Pending &P, AffPt *h_result);
     // d_tab[j * n + i] = 2^(off_j) d_points[i] for j < W (d_tab holds W n points; j = 0 is a copy)
     int build_table(const AffPt *d_points, size_t n, int W, AffPt *d_tab);
