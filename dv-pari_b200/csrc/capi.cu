@@ -356,6 +356,11 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
         ctx->msm.timing = value != 0;
         return DVP_OK;
     }
+    if (!strcmp(name, "prove_joint")) { // -1 automatic, 0 never, 1 always: commit_p as one MSM over g_m | g_q
+        if (value < -1 || value > 1) return DVP_ERR_BAD_ARG;
+        ctx->prove_joint = (int)value;
+        return DVP_OK;
+    }
     if (!strcmp(name, "msm_sort_ahead")) { // batches: sort MSM b+1 on a side stream while MSM b runs (default 1)
         ctx->msm.sort_ahead = value != 0;
         return DVP_OK;
@@ -369,8 +374,7 @@ extern "C++" {
 // Where the points of slot[offset, offset + n) are for an MSM.  Large slots get W tables T[j] = 2^(j c) P once, on
 // first use (W x the slot's memory), after which all windows share one bucket set; small slots, small sub-ranges and
 // tight memory use the plain vector.
-static int slot_points(dvp_ctx *ctx, int slot, size_t offset, size_t n, const AffPt **pts, MsmTable *tab, bool *use_tab) {
-    SrsSlot &s = ctx->slots[slot];
+static int slot_points(dvp_ctx *ctx, SrsSlot &s, size_t offset, size_t n, const AffPt **pts, MsmTable *tab, bool *use_tab) {
     const bool want = ctx->msm_tables && s.n >= ctx->msm_tables_min && n >= s.n / 2 && !ctx->msm.force_window_bits;
     if (want && !s.table_ok && !s.table_failed) {
         const int W = ctx->msm_table_windows ? ctx->msm_table_windows : choose_table_windows(s.n);
@@ -405,6 +409,9 @@ static int slot_points(dvp_ctx *ctx, int slot, size_t offset, size_t n, const Af
 
 // MSM over slot[offset, offset + n).
 int slot_msm(dvp_ctx *ctx, int slot, size_t offset, const uint32_t *d_scalars, size_t n, AffPt *out, cudaStream_t on) {
+    return slot_msm_at(ctx, ctx->slots[slot], offset, d_scalars, n, out, on);
+}
+int slot_msm_at(dvp_ctx *ctx, SrsSlot &s, size_t offset, const uint32_t *d_scalars, size_t n, AffPt *out, cudaStream_t on) {
     struct StreamSwap { // the engine's main stream for this call
         MsmEngine &e;
         cudaStream_t saved;
@@ -416,7 +423,7 @@ int slot_msm(dvp_ctx *ctx, int slot, size_t offset, const uint32_t *d_scalars, s
     const AffPt *pts = nullptr;
     MsmTable t;
     bool use_tab = false;
-    int rc = slot_points(ctx, slot, offset, n, &pts, &t, &use_tab);
+    int rc = slot_points(ctx, s, offset, n, &pts, &t, &use_tab);
     if (rc) return rc;
     return ctx->msm.run(pts, d_scalars, n, out, use_tab ? &t : nullptr);
 }
@@ -428,7 +435,7 @@ int slot_msm_batch(dvp_ctx *ctx, int slot, size_t offset, const uint64_t *const 
     const AffPt *pts = nullptr;
     MsmTable t;
     bool use_tab = false;
-    int rc = slot_points(ctx, slot, offset, n, &pts, &t, &use_tab);
+    int rc = slot_points(ctx, ctx->slots[slot], offset, n, &pts, &t, &use_tab);
     if (rc) return rc;
     DevBuf *stage[2] = {&ctx->scal, &ctx->scal2};
     if (!on_device)

@@ -11,9 +11,11 @@ struct SrsSlot {
     dvp::DevBuf table;
     dvp::MsmTable tab;
     bool table_ok = false, table_failed = false;
+    uint64_t version = 0; // bumped whenever the points change (a prover's joint g_m | g_q copy checks it)
     void invalidate() {
         table.release();
         table_ok = table_failed = false;
+        version++;
     }
 };
 
@@ -37,12 +39,19 @@ struct dvp_ctx {
     int msm_table_windows = 0;             // 0: choose_table_windows(slot size)
     int msm_tables = 1;                    // 0: never, 1: when the slot is large enough and the memory is there
     size_t msm_tables_min = (size_t)1 << 15; // smallest slot that gets tables
+    // dvp_prove: commit_p = msm(w, g_m) + msm(q, g_q) (proving.rs:463-515) as ONE MSM over g_m | g_q.
+    // -1: when the two vectors together are short enough that an MSM's fixed costs matter, 0 never, 1 always
+    int prove_joint = -1;
+    size_t prove_joint_max = ((size_t)3 << 20) - 1; // ... i.e. at most this many points together (automatic mode)
 };
 
 // sum_i scalars[i] * slot[offset + i] on the device of ctx (device scalars); uses the slot's tables when it has them
 // `on` = the stream the scalars were produced on and the MSM is ordered after (default: the context's stream)
 int slot_msm(dvp_ctx *ctx, int slot, size_t offset, const uint32_t *d_scalars, size_t n, dvp::AffPt *out,
              cudaStream_t on = nullptr);
+// the same over a point vector that is not one of the context's numbered slots (a prover's joint g_m | g_q copy)
+int slot_msm_at(dvp_ctx *ctx, SrsSlot &s, size_t offset, const uint32_t *d_scalars, size_t n, dvp::AffPt *out,
+                cudaStream_t on = nullptr);
 
 // comm.cu
 int comm_all_gather(dvp_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);

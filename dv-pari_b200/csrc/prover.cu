@@ -751,6 +751,11 @@ struct dvp_prover {
     int slot_gm = 0, slot_gq = 0, slot_gk = 0;
     DevBuf vec;  // 13 n Fr: a b c i a' b' c' i' q | k_a k_b k_r(2n)   (r' reuses c' after q)
     DevBuf wit, dinv, pre, tot, tot2, pre2, part;
+    // commit_p as one MSM (ctx->prove_joint): this rank's g_m | g_q shards side by side (with their own window tables,
+    // built on first use) and the scalars w | q copied next to each other
+    SrsSlot joint;
+    uint64_t joint_ver[2] = {~0ull, ~0ull};
+    DevBuf jscal;
     void *h_part = nullptr;
     float ms[8] = {0};
     cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1433,7 +1438,8 @@ void dvp_prover_destroy(dvp_prover *p) {
     if (!p) return;
     p->worker.stop();
     cudaSetDevice(p->ctx->device);
-    DevBuf *all[] = {&p->vec, &p->wit, &p->dinv, &p->pre, &p->tot, &p->tot2, &p->pre2, &p->part};
+    DevBuf *all[] = {&p->vec, &p->wit, &p->dinv, &p->pre, &p->tot, &p->tot2, &p->pre2, &p->part, &p->jscal,
+                     &p->joint.buf, &p->joint.table};
     for (auto b : all) b->release();
     if (p->h_part) cudaFreeHost(p->h_part);
     for (auto &e : p->ev)
@@ -1536,15 +1542,37 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     // phases of the MSM are filled with the Fr-side work.
     AffPt msm_gm, msm_q, kzg, part, part_gm;
     int rc_gm = 0;
+    const size_t nm = whi - wlo, nq = qhi - qlo;
+    // Short vectors: msm(w, g_m) + msm(q, g_q) (proving.rs:463, 512, 515) is ONE MSM over g_m | g_q -- one sort, one
+    // reduction, one read-back and wider windows instead of two of each (an 8-way shard of a 2^22-constraint proof:
+    // 0.59 M + 0.52 M points).  Long vectors keep the g_m MSM beside the Fr-side work.
+    const bool joint = nm + nq > 0 && (ctx->prove_joint == 1 || (ctx->prove_joint < 0 && nm + nq <= ctx->prove_joint_max));
+    if (joint) {
+        SrsSlot &gm = ctx->slots[p->slot_gm], &gq = ctx->slots[p->slot_gq];
+        if (gm.n != nm || gq.n != nq) return DVP_ERR_LENGTH_MISMATCH;
+        if (p->joint.n != nm + nq || p->joint_ver[0] != gm.version || p->joint_ver[1] != gq.version) {
+            int rcj;
+            p->joint.invalidate();
+            p->joint.n = 0;
+            if ((rcj = p->joint.buf.reserve((nm + nq) * sizeof(AffPt))) != 0 || (rcj = p->jscal.reserve((nm + nq) * sizeof(fr))) != 0)
+                return rcj;
+            if (nm) CKP(cudaMemcpyAsync(p->joint.buf.p, gm.buf.p, nm * sizeof(AffPt), cudaMemcpyDeviceToDevice, st));
+            if (nq) CKP(cudaMemcpyAsync(p->joint.buf.as<AffPt>() + nm, gq.buf.p, nq * sizeof(AffPt), cudaMemcpyDeviceToDevice, st));
+            p->joint.n = nm + nq;
+            p->joint_ver[0] = gm.version;
+            p->joint_ver[1] = gq.version;
+        }
+    }
     CKP(cudaEventRecord(ctx->ev_aux, st));
     part_gm = pt_inf();
-    p->worker.submit([&, ctx, p, w, wlo, whi] {
-        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_aux, 0) != cudaSuccess) {
-            rc_gm = DVP_ERR_CUDA;
-            return;
-        }
-        rc_gm = slot_msm(ctx, p->slot_gm, 0, (const uint32_t *)(w + wlo), whi - wlo, &part_gm, ctx->aux_stream);
-    });
+    if (!joint)
+        p->worker.submit([&, ctx, p, w, wlo, whi] {
+            if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_aux, 0) != cudaSuccess) {
+                rc_gm = DVP_ERR_CUDA;
+                return;
+            }
+            rc_gm = slot_msm(ctx, p->slot_gm, 0, (const uint32_t *)(w + wlo), whi - wlo, &part_gm, ctx->aux_stream);
+        });
     struct Joiner { // every return path waits for the helper: it writes into this frame
         ProverWorker &wk;
         ~Joiner() { wk.wait(); }
@@ -1573,15 +1601,27 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
                                                 (uint32_t)ecnt, q + elo);
     CKP(cudaGetLastError());
     cudaEventRecord(ev[3], st);
-    p->worker.wait();
-    // (a rank whose MSM failed still takes part in the exchange; every rank then returns that failure)
-    if ((rc = comm_fold_points(ctx, part_gm, rc_gm, &msm_gm))) return rc;
-    cudaEventRecord(ev[2], st);
-    part = pt_inf();
-    rc = slot_msm(ctx, p->slot_gq, 0, (const uint32_t *)(q + qlo), qhi - qlo, &part);
-    if ((rc = comm_fold_points(ctx, part, rc, &msm_q))) return rc;
-    cudaEventRecord(ev[4], st);
-    const AffPt commit = host::aff_add(msm_q, msm_gm); // proving.rs:515
+    AffPt commit;
+    if (joint) {
+        fr *js = p->jscal.as<fr>();
+        if (nm) CKP(cudaMemcpyAsync(js, w + wlo, nm * sizeof(fr), cudaMemcpyDeviceToDevice, st));
+        if (nq) CKP(cudaMemcpyAsync(js + nm, q + qlo, nq * sizeof(fr), cudaMemcpyDeviceToDevice, st));
+        cudaEventRecord(ev[2], st);
+        part = pt_inf();
+        rc = slot_msm_at(ctx, p->joint, 0, (const uint32_t *)js, nm + nq, &part);
+        // (a rank whose MSM failed still takes part in the exchange; every rank then returns that failure)
+        if ((rc = comm_fold_points(ctx, part, rc, &commit))) return rc;
+        cudaEventRecord(ev[4], st);
+    } else {
+        p->worker.wait();
+        if ((rc = comm_fold_points(ctx, part_gm, rc_gm, &msm_gm))) return rc;
+        cudaEventRecord(ev[2], st);
+        part = pt_inf();
+        rc = slot_msm(ctx, p->slot_gq, 0, (const uint32_t *)(q + qlo), qhi - qlo, &part);
+        if ((rc = comm_fold_points(ctx, part, rc, &msm_q))) return rc;
+        cudaEventRecord(ev[4], st);
+        commit = host::aff_add(msm_q, msm_gm); // proving.rs:515
+    }
     host::encode30(proof, commit);
     // Fiat-Shamir challenge, proving.rs:517-558
     std::vector<uint8_t> pub29(29 * k + 1);

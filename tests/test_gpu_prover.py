@@ -104,6 +104,14 @@ def _prove_both(ctx, O, r1cs, w, td):
     prover = dvpari.Prover(ctx, gd, inst, 0, 1, 2)
     k = r1cs.k
     got_proof, got_st = prover.prove(wm[1:1 + k], wm[1 + k:], want_stages=True)
+    # commit_p = msm(w, g_m) + msm(q, g_q) (proving.rs:463-515) as two MSMs and as one MSM over g_m | g_q: same bytes
+    for joint in (0, 1):
+        ctx.set("prove_joint", joint)
+        assert prover.prove(wm[1:1 + k], wm[1 + k:]) == got_proof, f"prove_joint={joint}"
+    ctx.set("prove_joint", -1)
+    # the joint copy follows a reloaded slot (same points here, new version): still the same proof
+    ctx.srs_load(1, srs.g_q30())
+    assert prover.prove(wm[1:1 + k], wm[1 + k:]) == got_proof
     n = r1cs.n
     names = ["a", "b", "c", "i", "a'", "b'", "c'", "i'", "q", "k_a", "k_b", "k_r", "k_r(2)"]
     for s, name in enumerate(names):
