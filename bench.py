@@ -304,8 +304,10 @@ def prove_section(ctx, args, rank, world, sync_all, timed):
         "ms_per_proof": ms, "proofs": reps, "stage_ms": stages,
         "h2d_bytes_per_proof": int(circ["nwires"] * 32), "d2h_bytes_per_proof": 118,
         "msm_points_per_proof": circ["nwires"] + 5 * n,
-        # g_q + g_k only: the g_m MSM overlaps the Fr-side stages (its stage entry is the part that was not hidden)
-        "msm_gq_gk_points_per_s": 5 * n / world / (1e-3 * (stages["msm_gq"] + stages["msm_gk"])),
+        # commit_p is ONE MSM over g_m | g_q (stage "msm_gq"; "msm_gm" is then empty), then the g_k MSM: all MSM points
+        # of a proof over the two MSM stages, per GPU
+        "msm_points_per_s_per_gpu": (circ["nwires"] + 5 * n) / world / (1e-3 * (stages["msm_gm"] + stages["msm_gq"] + stages["msm_gk"])),
+        "commit_p": "one MSM over g_m | g_q (prove_joint)",
         "ecfft_extend": {"polys": 3, "n": n, "ms": ext_ms, "mulmods_per_s": mulmods / (ext_ms * 1e-3),
                          "mulmods_note": "4 n log2 n per polynomial, the reference algorithm's count (SURVEY 8d); the "
                                          "kernels execute products_per_s (position scales carried through the tree)",

@@ -1543,24 +1543,32 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     AffPt msm_gm, msm_q, kzg, part, part_gm;
     int rc_gm = 0;
     const size_t nm = whi - wlo, nq = qhi - qlo;
-    // Short vectors: msm(w, g_m) + msm(q, g_q) (proving.rs:463, 512, 515) is ONE MSM over g_m | g_q -- one sort, one
-    // reduction, one read-back and wider windows instead of two of each (an 8-way shard of a 2^22-constraint proof:
-    // 0.59 M + 0.52 M points).  Long vectors keep the g_m MSM beside the Fr-side work.
-    const bool joint = nm + nq > 0 && (ctx->prove_joint == 1 || (ctx->prove_joint < 0 && nm + nq <= ctx->prove_joint_max));
+    // msm(w, g_m) + msm(q, g_q) (proving.rs:463, 512, 515) is ONE MSM over g_m | g_q -- one sort, one reduction, one
+    // read-back and wider windows instead of two of each.  The other form (knob prove_joint = 0, or no memory for the
+    // joint vector's window tables) runs the g_m MSM from the helper thread beside the Fr-side work.
+    // (with several ranks the choice must be the same everywhere -- the forms differ in their collectives -- so it does
+    // not depend on a rank's own memory there)
+    const bool joint = ctx->prove_joint == 1 || (ctx->prove_joint < 0 && (ctx->world > 1 || !p->joint.table_failed));
+    int rc_joint = 0; // a rank-local failure here travels with the partial sum: nobody is left waiting in a collective
     if (joint) {
         SrsSlot &gm = ctx->slots[p->slot_gm], &gq = ctx->slots[p->slot_gq];
-        if (gm.n != nm || gq.n != nq) return DVP_ERR_LENGTH_MISMATCH;
-        if (p->joint.n != nm + nq || p->joint_ver[0] != gm.version || p->joint_ver[1] != gq.version) {
-            int rcj;
+        if (gm.n != nm || gq.n != nq) {
+            rc_joint = DVP_ERR_LENGTH_MISMATCH; // a slot was reloaded with another length after dvp_prover_create
+        } else if (p->joint.n != nm + nq || p->joint_ver[0] != gm.version || p->joint_ver[1] != gq.version) {
             p->joint.invalidate();
             p->joint.n = 0;
-            if ((rcj = p->joint.buf.reserve((nm + nq) * sizeof(AffPt))) != 0 || (rcj = p->jscal.reserve((nm + nq) * sizeof(fr))) != 0)
-                return rcj;
-            if (nm) CKP(cudaMemcpyAsync(p->joint.buf.p, gm.buf.p, nm * sizeof(AffPt), cudaMemcpyDeviceToDevice, st));
-            if (nq) CKP(cudaMemcpyAsync(p->joint.buf.as<AffPt>() + nm, gq.buf.p, nq * sizeof(AffPt), cudaMemcpyDeviceToDevice, st));
-            p->joint.n = nm + nq;
-            p->joint_ver[0] = gm.version;
-            p->joint_ver[1] = gq.version;
+            if ((rc_joint = p->joint.buf.reserve((nm + nq) * sizeof(AffPt))) == 0 &&
+                (rc_joint = p->jscal.reserve((nm + nq) * sizeof(fr))) == 0) {
+                if ((nm && cudaMemcpyAsync(p->joint.buf.p, gm.buf.p, nm * sizeof(AffPt), cudaMemcpyDeviceToDevice, st) != cudaSuccess) ||
+                    (nq && cudaMemcpyAsync(p->joint.buf.as<AffPt>() + nm, gq.buf.p, nq * sizeof(AffPt), cudaMemcpyDeviceToDevice,
+                                           st) != cudaSuccess))
+                    rc_joint = DVP_ERR_CUDA;
+            }
+            if (!rc_joint) {
+                p->joint.n = nm + nq;
+                p->joint_ver[0] = gm.version;
+                p->joint_ver[1] = gq.version;
+            }
         }
     }
     CKP(cudaEventRecord(ctx->ev_aux, st));
@@ -1604,11 +1612,12 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     AffPt commit;
     if (joint) {
         fr *js = p->jscal.as<fr>();
-        if (nm) CKP(cudaMemcpyAsync(js, w + wlo, nm * sizeof(fr), cudaMemcpyDeviceToDevice, st));
-        if (nq) CKP(cudaMemcpyAsync(js + nm, q + qlo, nq * sizeof(fr), cudaMemcpyDeviceToDevice, st));
+        if (!rc_joint && ((nm && cudaMemcpyAsync(js, w + wlo, nm * sizeof(fr), cudaMemcpyDeviceToDevice, st) != cudaSuccess) ||
+                          (nq && cudaMemcpyAsync(js + nm, q + qlo, nq * sizeof(fr), cudaMemcpyDeviceToDevice, st) != cudaSuccess)))
+            rc_joint = DVP_ERR_CUDA;
         cudaEventRecord(ev[2], st);
         part = pt_inf();
-        rc = slot_msm_at(ctx, p->joint, 0, (const uint32_t *)js, nm + nq, &part);
+        rc = rc_joint ? rc_joint : slot_msm_at(ctx, p->joint, 0, (const uint32_t *)js, nm + nq, &part);
         // (a rank whose MSM failed still takes part in the exchange; every rank then returns that failure)
         if ((rc = comm_fold_points(ctx, part, rc, &commit))) return rc;
         cudaEventRecord(ev[4], st);
@@ -1647,9 +1656,16 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
     k_bary_partial<<<nblk, 256, 0, st>>>(a + ilo, b + ilo, d->bar_wts.as<fr>() + ilo, p->dinv.as<fr>(), cnt, p->part.as<fr>());
     CKP(cudaGetLastError());
     CKP(cudaMemcpyAsync(p->h_part, p->part.p, 2 * nblk * sizeof(fr), cudaMemcpyDeviceToHost, st));
-    CKP(cudaStreamSynchronize(st));
+    // Z_D(alpha), Z_D'(alpha) and i0 on the host (O(log^2 n) and O(k)) while the device forms the denominators and sums
     const fr za = vanish_at_host(d, 0, alpha);
-    if (fr_is_zero(za) || fr_is_zero(vanish_at_host(d, 1, alpha))) return DVP_ERR_ALPHA_IN_DOMAIN;
+    const bool alpha_in_domain = fr_is_zero(za) || fr_is_zero(vanish_at_host(d, 1, alpha));
+    fr i0 = fr_zero(), pw = fr_one();
+    for (size_t j = 0; j < k; j++) {
+        i0 = fr_add(i0, fr_mul(pubv[j], pw));
+        pw = fr_mul(pw, alpha);
+    }
+    CKP(cudaStreamSynchronize(st));
+    if (alpha_in_domain && W == 1) return DVP_ERR_ALPHA_IN_DOMAIN;
     fr sa = fr_zero(), sb = fr_zero();
     const fr *hp = (const fr *)p->h_part;
     for (int i = 0; i < nblk; i++) {
@@ -1673,12 +1689,8 @@ static int prove_impl(dvp_prover *p, const uint64_t *pub, size_t k, const uint64
             sb = fr_add(sb, all[2 * i + 1]);
         }
     }
+    if (alpha_in_domain) return DVP_ERR_ALPHA_IN_DOMAIN; // (the same alpha on every rank: all of them leave here)
     const fr a0 = fr_mul(sa, za), b0 = fr_mul(sb, za);
-    fr i0 = fr_zero(), pw = fr_one();
-    for (size_t j = 0; j < k; j++) {
-        i0 = fr_add(i0, fr_mul(pubv[j], pw));
-        pw = fr_mul(pw, alpha);
-    }
     const fr r0 = fr_sub(fr_mul(a0, b0), i0);
     // ks: k_a | k_b | k_r of this rank's range, contiguous (4 cnt scalars; with one rank the reference's own order)
     k_kscalars<<<cdivp(cnt, 128), 128, 0, st>>>(a + ilo, b + ilo, iv + ilo, c2 + ilo, p->dinv.as<fr>(), a0, b0, r0, cnt, ks);
