@@ -25,6 +25,8 @@ extern "C" {
     pub fn dvp_srs_mulgen(ctx: *mut dvp_ctx, slot: c_int, scalars_mont: *const u64, n: usize) -> c_int;
     pub fn dvp_msm(ctx: *mut dvp_ctx, slot: c_int, offset: usize, scalars_mont: *const u64, n: usize, out30: *mut u8) -> c_int;
     pub fn dvp_msm_adhoc(ctx: *mut dvp_ctx, pts30: *const u8, scalars_mont: *const u64, n: usize, out30: *mut u8) -> c_int;
+    pub fn dvp_msm_batch(ctx: *mut dvp_ctx, slot: c_int, offset: usize, scalars_mont: *const *const u64, n: usize, nb: usize,
+                         scalars_on_device: c_int, out30: *mut u8) -> c_int;
     pub fn dvp_domain_create(ctx: *mut dvp_ctx, log2_2n: c_uint, out: *mut *mut dvp_domain) -> c_int;
     pub fn dvp_domain_from_fftree(ctx: *mut dvp_ctx, file: *const u8, len: usize, out: *mut *mut dvp_domain) -> c_int;
     pub fn dvp_domain_destroy(dom: *mut dvp_domain);
@@ -72,6 +74,16 @@ impl Gpu {
         let rc = unsafe { dvp_msm(self.raw, slot, 0, scalars.as_ptr() as *const u64, scalars.len(), out.as_mut_ptr()) };
         assert_eq!(rc, DVP_OK, "dvp_msm failed: {rc}"); // the reference panics on a length mismatch (curve.rs:142)
         out
+    }
+    /// The same for several scalar vectors of one length against the same points, pipelined on the device.
+    pub fn multi_scalar_mul_many(&self, slot: i32, vectors: &[&[[u64; 4]]]) -> Vec<[u8; 30]> {
+        let n = vectors.first().map_or(0, |v| v.len());
+        assert!(vectors.iter().all(|v| v.len() == n), "scalar vectors of different lengths");
+        let ptrs: Vec<*const u64> = vectors.iter().map(|v| v.as_ptr() as *const u64).collect();
+        let mut out = vec![0u8; 30 * vectors.len()];
+        let rc = unsafe { dvp_msm_batch(self.raw, slot, 0, ptrs.as_ptr(), n, ptrs.len(), 0, out.as_mut_ptr()) };
+        assert_eq!(rc, DVP_OK, "dvp_msm_batch failed: {rc}");
+        out.chunks_exact(30).map(|c| { let mut a = [0u8; 30]; a.copy_from_slice(c); a }).collect()
     }
     pub fn raw(&self) -> *mut dvp_ctx { self.raw }
 }

@@ -39,7 +39,12 @@ def main():
     lo, hi = dvpari.shard_range(n, rank, world)
     ctx.srs_load(0, enc[lo:hi])
     got = ctx.msm_sharded(sc[lo:hi], 0)
-    assert got == O.pt_encode(O.msm(sc, pts, 0)), "sharded MSM differs from the oracle"
+    want_msm = O.pt_encode(O.msm(sc, pts, 0))
+    assert got == want_msm, "sharded MSM differs from the oracle"
+    # the batched form: pipelined local MSMs, one NCCL all-gather for all partial sums
+    sc2 = dvpari.random_fr_mont(n, 13)
+    got_b = ctx.msm_sharded_batch([sc[lo:hi], sc2[lo:hi], sc[lo:hi]], 0)
+    assert got_b == [want_msm, O.pt_encode(O.msm(sc2, pts, 0)), want_msm], "batched sharded MSM differs from the oracle"
 
     # sharded prove
     circ = synth.synth_r1cs(lg, seed=0xD5A10003 + lg)
@@ -77,6 +82,11 @@ def main():
         raise AssertionError("bad witness accepted")
     except dvpari.DvpError as e:
         assert e.code == 6
+    # commit_p as two MSMs (g_m from the helper thread, then g_q) and as one MSM over g_m | g_q: the same bytes
+    for joint in (0, 1):
+        ctx.set("prove_joint", joint)
+        assert prover.prove(w[1:1 + k], w[1 + k:]) == proof, f"prove_joint={joint}"
+    ctx.set("prove_joint", -1)
     outs = [None] * world
     dist.all_gather_object(outs, proof)
     assert all(o == outs[0] for o in outs)
