@@ -41,6 +41,17 @@ def test_msm_2_24_closed_form(ctx, oracle):
     try:
         assert ctx.multi_scalar_mul(sc, 0) == want
         assert ctx.msm_stats()["tables"] == 1
+        # the batched call at this size (separate-launch path: a read-back in the middle of every MSM) and on a 2^20
+        # prefix of the slot (plain layout: the sub-range is too short for the tables; persistent path, sort ahead)
+        sc2 = dvpari.random_fr_mont(n, 0xD5A10025)
+        t0, t1 = O.sum_weighted(sc2)
+        want2 = O.pt_encode(O.pt_add(O.pt_mul(a, t0), O.pt_mul(q, t1)))
+        assert ctx.multi_scalar_mul_batch([sc, sc2, sc], 0) == [want, want2, want]
+        m = 1 << 20
+        u0, u1 = O.sum_weighted(sc[:m])
+        v0, v1 = O.sum_weighted(sc2[:m])
+        wm = [O.pt_encode(O.pt_add(O.pt_mul(a, u0), O.pt_mul(q, u1))), O.pt_encode(O.pt_add(O.pt_mul(a, v0), O.pt_mul(q, v1)))]
+        assert ctx.multi_scalar_mul_batch([sc[:m], sc2[:m], sc[:m], sc2[:m], sc[:m]], 0) == [wm[0], wm[1], wm[0], wm[1], wm[0]]
         # the plain layout (one bucket set per window, no precomputed multiples) gives the same group element
         ctx.set("msm_tables", 0)
         assert ctx.multi_scalar_mul(sc, 0) == want
