@@ -361,6 +361,10 @@ int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value) {
         ctx->prove_joint = (int)value;
         return DVP_OK;
     }
+    if (!strcmp(name, "msm_preplan")) { // persistent path: plan all rounds before the launch (default 1)
+        ctx->msm.preplan = value != 0;
+        return DVP_OK;
+    }
     if (!strcmp(name, "msm_sort_ahead")) { // batches: sort MSM b+1 on a side stream while MSM b runs (default 1)
         ctx->msm.sort_ahead = value != 0;
         return DVP_OK;

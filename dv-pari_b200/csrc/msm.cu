@@ -588,7 +588,179 @@ struct AccArgs {
     const gf *tabs;
     int max_rounds;                 // run at most this many rounds (a fixed count for the reduction levels)
     int tiny_max;                   // a round of at most this many additions runs one warp per addition
+    // the plan of ALL rounds made before the launch (k_pa_*), or nullptr: every round plans itself
+    const uint32_t *pl_ctl;         // see PL_* below
+    uint32_t *pl_start, *pl_len;    // tables of round r (r >= 1) at + r * pl_stride
+    uint32_t pl_stride;
 };
+
+// ------------------------------------------------------------------------------------------------
+// The plan of all rounds at once.  Segment lengths halve (rounding up) from round to round whatever the points are, so
+// the segment tables and the descriptors of EVERY round follow from the round-0 lengths alone: three small launches
+// before the persistent kernel (block aggregates of the per-round (additions, points) pairs | scan over the blocks,
+// round count, per-round totals | tables and descriptors of all rounds) replace the two plan phases and two of the three
+// grid barriers of every round inside it; what is left of a round's plan in the kernel is the copy of the odd
+// segments' last points.  Up to PL_K rounds (segments of up to 2^PL_K points); longer segments (degenerate inputs)
+// leave mode 0 and the kernel plans round by round as before.
+// pl_ctl: [0] mode (1: plan valid) [1] rounds [2] longest segment [4 + r] additions of round r
+//         [20 + r] first descriptor of round r [40] additions of all rounds
+// ------------------------------------------------------------------------------------------------
+constexpr int PL_K = 12;
+constexpr int PL_THREADS = 256;
+constexpr uint32_t PL_MAX_BLOCKS = 1024;
+constexpr int PL_CTL_WORDS = 64;
+
+__device__ __forceinline__ void pl_thread_sums(const uint32_t *__restrict__ len0, uint32_t nseg, uint32_t base, uint32_t items,
+                                               unsigned long long s[PL_K], uint32_t &mx) {
+#pragma unroll
+    for (int r = 0; r < PL_K; r++) s[r] = 0;
+    mx = 0;
+    for (uint32_t k = 0; k < items; k++) {
+        const uint32_t idx = base + k;
+        uint32_t L = idx < nseg ? len0[idx] : 0;
+        mx = max(mx, L);
+#pragma unroll
+        for (int r = 0; r < PL_K; r++) {
+            s[r] += (unsigned long long)(L >> 1) | ((unsigned long long)((L + 1) >> 1) << 32);
+            L = (L + 1) >> 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PL_THREADS)
+    k_pa_aggr(const uint32_t *__restrict__ len0, uint32_t nseg, uint32_t items, unsigned long long *__restrict__ blk_sum,
+              uint32_t *__restrict__ pl_ctl) {
+    __shared__ unsigned long long sh[PL_K][PL_THREADS / 32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long s[PL_K];
+    uint32_t mx;
+    pl_thread_sums(len0, nseg, (blockIdx.x * PL_THREADS + threadIdx.x) * items, items, s, mx);
+#pragma unroll
+    for (int r = 0; r < PL_K; r++) {
+        unsigned long long v = s[r];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[r][wid] = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    if (lane == 0 && mx) atomicMax(&pl_ctl[2], mx);
+    __syncthreads();
+    if (threadIdx.x < PL_K) {
+        unsigned long long v = 0;
+        for (int w = 0; w < PL_THREADS / 32; w++) v += sh[threadIdx.x][w];
+        blk_sum[(size_t)blockIdx.x * PL_K + threadIdx.x] = v;
+    }
+}
+
+// one block: blk_sum[b][r] -> exclusive prefix over b (in place), totals, round count, descriptor offsets
+__global__ void __launch_bounds__(PL_THREADS)
+    k_pa_scan(unsigned long long *__restrict__ blk_sum, uint32_t nblk, int max_rounds, uint32_t *__restrict__ pl_ctl) {
+    __shared__ unsigned long long sh[PL_THREADS];
+    __shared__ unsigned long long tot[PL_K];
+    const uint32_t t = threadIdx.x;
+    const uint32_t ch = (nblk + PL_THREADS - 1) / PL_THREADS;
+    for (int r = 0; r < PL_K; r++) {
+        unsigned long long loc = 0;
+        for (uint32_t b = t * ch; b < min(nblk, (t + 1) * ch); b++) loc += blk_sum[(size_t)b * PL_K + r];
+        sh[t] = loc;
+        __syncthreads();
+        for (int o = 1; o < PL_THREADS; o <<= 1) {
+            const unsigned long long v = t >= (uint32_t)o ? sh[t - o] : 0;
+            __syncthreads();
+            sh[t] += v;
+            __syncthreads();
+        }
+        unsigned long long run = sh[t] - loc; // exclusive
+        if (t == PL_THREADS - 1) tot[r] = sh[t];
+        for (uint32_t b = t * ch; b < min(nblk, (t + 1) * ch); b++) {
+            const unsigned long long v = blk_sum[(size_t)b * PL_K + r];
+            blk_sum[(size_t)b * PL_K + r] = run;
+            run += v;
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        const uint32_t maxlen = pl_ctl[2];
+        int R = 0;
+        while (R < 32 && (1u << R) < maxlen) R++;
+        const uint32_t mode = R <= PL_K ? 1u : 0u;
+        R = min(R, max_rounds);
+        uint32_t off = 0, all = 0;
+        for (int r = 0; r < PL_K; r++) {
+            const uint32_t nt = (uint32_t)tot[r];
+            pl_ctl[4 + r] = nt;
+            pl_ctl[20 + r] = off;
+            if (r < R) off += nt, all += nt;
+        }
+        pl_ctl[40] = all;
+        pl_ctl[1] = mode ? (uint32_t)R : 0u;
+        pl_ctl[0] = mode;
+    }
+}
+
+template <bool INDEXED>
+__global__ void __launch_bounds__(PL_THREADS)
+    k_pa_emit(const uint32_t *__restrict__ len0, const uint32_t *__restrict__ start0, const uint32_t *__restrict__ ent,
+              uint32_t nseg, uint32_t items, const unsigned long long *__restrict__ blk_off,
+              const uint32_t *__restrict__ pl_ctl, uint32_t *__restrict__ pl_start, uint32_t *__restrict__ pl_len,
+              uint32_t stride, uint4 *__restrict__ desc) {
+    __shared__ unsigned long long sh[PL_K][PL_THREADS / 32];
+    if (pl_ctl[0] != 1u) return;
+    const int R = (int)pl_ctl[1];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t base = (blockIdx.x * PL_THREADS + threadIdx.x) * items;
+    unsigned long long run[PL_K];
+    {
+        unsigned long long s[PL_K];
+        uint32_t mx;
+        pl_thread_sums(len0, nseg, base, items, s, mx);
+#pragma unroll
+        for (int r = 0; r < PL_K; r++) {
+            unsigned long long incl = s[r];
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += v;
+            }
+            if (lane == 31) sh[r][wid] = incl;
+            run[r] = incl - s[r]; // exclusive inside the warp
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < PL_K; r++) {
+            unsigned long long w = 0;
+            for (uint32_t q = 0; q < wid; q++) w += sh[r][q];
+            run[r] += w + blk_off[(size_t)blockIdx.x * PL_K + r];
+        }
+    }
+    // Tables and descriptors, every thread for its own segments: the descriptors of a segment are consecutive in every
+    // round and the iterations are independent (a warp working through one segment at a time spent its time waiting
+    // for the index loads of round 0: 160 us at 2^20 points).  The longest segment is 2^PL_K points.
+    for (uint32_t k = 0; k < items; k++) {
+        const uint32_t idx = base + k;
+        if (idx >= nseg) break;
+        uint32_t L = len0[idx], in_r = start0[idx];
+#pragma unroll
+        for (int r = 0; r < PL_K; r++) {
+            if (r < R) {
+                const uint32_t nt = L >> 1, ts = pl_ctl[20 + r] + (uint32_t)run[r], os = (uint32_t)(run[r] >> 32);
+                pl_start[(size_t)(r + 1) * stride + idx] = os;
+                pl_len[(size_t)(r + 1) * stride + idx] = (L + 1) >> 1;
+                uint4 *dp = desc + ts;
+#pragma unroll 4
+                for (uint32_t j = 0; j < nt; j++) {
+                    uint32_t a = in_r + 2 * j, b = a + 1;
+                    if (INDEXED && r == 0) {
+                        a = ent[a];
+                        b = ent[b];
+                    }
+                    dp[j] = make_uint4(a, b, os + j, 0);
+                }
+                run[r] += (unsigned long long)nt | ((unsigned long long)((L + 1) >> 1) << 32);
+                L = (L + 1) >> 1;
+                in_r = os;
+            }
+        }
+    }
+}
 #ifndef ACC_THREADS_N
 #define ACC_THREADS_N 256
 #endif
@@ -770,10 +942,33 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MINB) k_accumulate(const AccA
     int r = 0;
     const bool prof = A.times != nullptr && blockIdx.x == 0 && tid == 0;
     if (prof) A.times[ACC_TIME_WORDS - 1] = acc_now();
+    // planned ahead?  (the same answer in every thread of the grid; -1: every round plans itself)
+    const int pre_rounds = (A.pl_ctl != nullptr && __ldcg(&A.pl_ctl[0]) == 1u) ? (int)__ldcg(&A.pl_ctl[1]) : -1;
     for (; r < A.max_rounds; r++) {
         const int o = (r + 1) & 1;
         uint32_t *out_start = A.seg_start[o], *new_len = A.seg_len[o];
         AffPt *out = A.pp[r & 1];
+        uint32_t doff = 0; // this round's descriptors start at A.desc + doff
+        uint32_t ntasks = 0;
+        if (pre_rounds >= 0) {
+            // ---- planned before the launch: this round's tables and descriptors exist; carry the odd segments' last
+            // points over (the passes of this round write other positions of `out`, the next round reads them)
+            if (r >= pre_rounds) break;
+            ntasks = __ldcg(&A.pl_ctl[4 + r]);
+            doff = __ldcg(&A.pl_ctl[20 + r]);
+            out_start = A.pl_start + (size_t)(r + 1) * A.pl_stride;
+            new_len = A.pl_len + (size_t)(r + 1) * A.pl_stride;
+            for (uint32_t k = 0; k < items; k++) {
+                const uint32_t idx = seg_base + k;
+                if (idx >= nseg) break;
+                const uint32_t L = __ldcg(&in_len[idx]);
+                if (L & 1) {
+                    const uint32_t in = __ldcg(&in_start[idx]), os = __ldcg(&out_start[idx]);
+                    const uint32_t e = cur_ent ? cur_ent[in + L - 1] : in + L - 1;
+                    pt_store(&out[os + (L >> 1)], fetch_entry_cg(cur, e));
+                }
+            }
+        } else {
         // ---- plan, step 1: block aggregates of (additions, points after the round) and the longest segment
         unsigned long long s = 0;
         uint32_t mx = 0;
@@ -824,7 +1019,7 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MINB) k_accumulate(const AccA
             }
         }
         __syncthreads();
-        const uint32_t ntasks = (uint32_t)sh_total;
+        ntasks = (uint32_t)sh_total;
         // ---- plan, step 3: next segment tables, one descriptor per addition, odd leftovers carried over
         {
             unsigned long long run = sh_base + sh[wid] + (incl - s);
@@ -860,10 +1055,11 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MINB) k_accumulate(const AccA
                 run += (unsigned long long)(L >> 1) | ((unsigned long long)((L + 1) >> 1) << 32);
             }
         }
+            if (!acc_barrier(A.ctl, bar)) return;
+            if (prof) A.times[6 * r + 1] = acc_now();
+        }
         if (r == 0) adds_r0 = ntasks;
         adds_all += ntasks;
-        if (!acc_barrier(A.ctl, bar)) return;
-        if (prof) A.times[6 * r + 1] = acc_now();
         // ---- pass 1: every thread chains B additions; warp gw owns the additions [gw 32 B, (gw + 1) 32 B)
         // chain length: the additions are dealt evenly to all threads (longer chains on fewer warps were measured
         // 30-100 % slower: an addition of pass 2 is ~30 us of dependent loads and products at low occupancy)
@@ -873,7 +1069,7 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MINB) k_accumulate(const AccA
             // ---- a tiny round: one WARP per addition, everything cooperative, no batching
             const WarpMulCtx wc = warp_mul_ctx();
             for (uint32_t t = gw; t < ntasks; t += nwarps) {
-                const uint4 de = __ldcg(&A.desc[t]);
+                const uint4 de = __ldcg(&A.desc[doff + t]);
                 const AffPt p1 = fetch_entry_cg(cur, de.x), p2 = fetch_entry_cg(cur, de.y);
                 gf d;
                 const int kind = pair_classify(p1, p2, d); // warp-uniform
@@ -890,11 +1086,11 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MINB) k_accumulate(const AccA
                 if (lane == 0) pt_store(&out[de.z], q);
             }
         } else if (base < ntasks) { // the whole warp or none of it
-            const gf acc = chain_pass1(stage, tid, lane, base, B, ntasks, cur, A.desc, A.prefix);
+            const gf acc = chain_pass1(stage, tid, lane, base, B, ntasks, cur, A.desc + doff, A.prefix);
             if (prof) A.times[6 * r + 2] = acc_now();
             const gf inv = warp_invert_totals(acc, A.tabs);
             if (prof) A.times[6 * r + 3] = acc_now();
-            chain_pass2(stage, tid, lane, base, B, ntasks, cur, A.desc, A.prefix, inv, out);
+            chain_pass2(stage, tid, lane, base, B, ntasks, cur, A.desc + doff, A.prefix, inv, out);
         }
         if (!acc_barrier(A.ctl, bar)) return;
         if (prof) A.times[6 * r + 4] = acc_now();
@@ -1392,6 +1588,9 @@ void MsmLane::destroy() {
     DevBuf *all[] = {&seg_len[0], &seg_len[1], &seg_start[0], &seg_start[1], &c_len, &c_start,
                      &blk, &blk_flag, &info, &info_r0, &pp[0], &pp[1], &prefix, &desc, &thr_total, &thr_inv, &lvl_pre[0],
                      &lvl_pre[1], &lvl_tot[0], &lvl_tot[1], &lvl_inv[0], &lvl_inv[1], &buckets, &rc, &ents2, &acc_ctl, &acc_times};
+    plan_main[0].release();
+    plan_main[1].release();
+    plan_a.release();
     for (auto b : all) b->release();
     for (auto &e : ev_k)
         if (e) cudaEventDestroy(e), e = nullptr;
@@ -1629,8 +1828,43 @@ struct Tree {
     // All rounds of one reduction in a single persistent launch (k_accumulate).  nr_fixed < 0: until every segment has
     // at most one point, then dst[s] = that point; nr_fixed >= 0: exactly that many rounds, the list is left in
     // pp[(nr-1) & 1] with the segment tables of set nr & 1 (dst may be null).  `slot` selects the control block.
+    // The plan of all rounds of one k_accumulate launch into `ps`, on stream s.  With a key, a set that already holds
+    // the plan of that key is left as it is.
+    int plan_launch(cudaStream_t s, MsmLane::PlanSet &ps, const uint32_t *len0, const uint32_t *start0, const uint32_t *ent,
+                    uint32_t nseg, size_t total_ub, int max_rounds, uint64_t key = 0) {
+        if (key && ps.key == key) return 0;
+        ps.key = 0;
+        int rc;
+        uint32_t items = 1;
+        while (cdiv(nseg, items * PL_THREADS) > PL_MAX_BLOCKS) items++;
+        const uint32_t nblk = cdiv(nseg, items * PL_THREADS);
+        const uint32_t stride = (nseg + 32) & ~31u;
+        if ((rc = ps.blk.reserve((size_t)nblk * PL_K * 8)) != 0) return rc;
+        if ((rc = ps.start.reserve((size_t)(PL_K + 1) * stride * 4)) != 0) return rc;
+        if ((rc = ps.len.reserve((size_t)(PL_K + 1) * stride * 4)) != 0) return rc;
+        if ((rc = ps.ctl.reserve(PL_CTL_WORDS * 4)) != 0) return rc;
+        if ((rc = ps.desc.reserve((total_ub + 64) * sizeof(uint4))) != 0) return rc; // all rounds: fewer additions than points
+        ps.stride = stride;
+        uint32_t *pc = ps.ctl.as<uint32_t>();
+        unsigned long long *blk = ps.blk.as<unsigned long long>();
+        CK(cudaMemsetAsync(pc, 0, PL_CTL_WORDS * 4, s));
+        k_pa_aggr<<<nblk, PL_THREADS, 0, s>>>(len0, nseg, items, blk, pc);
+        k_pa_scan<<<1, PL_THREADS, 0, s>>>(blk, nblk, max_rounds, pc);
+        if (ent)
+            k_pa_emit<true><<<nblk, PL_THREADS, 0, s>>>(len0, start0, ent, nseg, items, blk, pc, ps.start.as<uint32_t>(),
+                                                        ps.len.as<uint32_t>(), stride, ps.desc.as<uint4>());
+        else
+            k_pa_emit<false><<<nblk, PL_THREADS, 0, s>>>(len0, start0, nullptr, nseg, items, blk, pc, ps.start.as<uint32_t>(),
+                                                         ps.len.as<uint32_t>(), stride, ps.desc.as<uint4>());
+        CK(cudaGetLastError());
+        L.launches += 3;
+        ps.key = key;
+        return 0;
+    }
+
     int accumulate(const AffPt *src, const uint32_t *ent, const uint32_t *start0, const uint32_t *len0, uint32_t nseg,
-                   size_t total_ub, AffPt *dst, int nr_fixed, int slot, uint32_t grid_cap) {
+                   size_t total_ub, AffPt *dst, int nr_fixed, int slot, uint32_t grid_cap, MsmLane::PlanSet *ps = nullptr,
+                   bool plan_here = true, uint64_t plan_key = 0) {
         AccArgs A;
         A.src0 = src;
         A.ent = ent;
@@ -1654,6 +1888,22 @@ struct Tree {
         A.tabs = E.msqr_tabs.as<gf>();
         A.max_rounds = nr_fixed >= 0 ? nr_fixed : ACC_MAX_ROUNDS;
         A.tiny_max = (int)E.round_warp_max;
+        A.pl_ctl = nullptr;
+        A.pl_start = A.pl_len = nullptr;
+        A.pl_stride = 0;
+        if (ps) {
+            // planned ahead (see k_pa_*): by the caller on the sort stream, here on the lane's stream, or kept from the
+            // MSM before (level A)
+            if (plan_here) {
+                int rc = plan_launch(st, *ps, len0, start0, ent, nseg, total_ub, A.max_rounds, plan_key);
+                if (rc) return rc;
+            }
+            A.pl_ctl = ps->ctl.as<uint32_t>();
+            A.pl_start = ps->start.as<uint32_t>();
+            A.pl_len = ps->len.as<uint32_t>();
+            A.pl_stride = ps->stride;
+            A.desc = ps->desc.as<uint4>(); // (also the round-by-round plan's, should the device fall back to it)
+        }
         // enough threads for one addition each in round 0 (a small problem pays for its barriers by the block)
         const size_t want = std::max<size_t>(total_ub / 2 + 1, nseg);
         const uint32_t grid = (uint32_t)std::max<size_t>(1, std::min<size_t>(grid_cap, (want + ACC_THREADS - 1) / ACC_THREADS));
@@ -2057,7 +2307,11 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
         }
         CK(cudaGetLastError());
     }
-    CK(cudaEventRecord(ev_recode, st));
+    // the stream the sort ran on also plans the rounds of the bucket accumulation (k_pa_*: they need the sorted list
+    // only), so that in a pipelined batch the plan of MSM b+1 is ready before MSM b has finished
+    const cudaStream_t ss = st;
+    const bool plan_on_sort = preplan && persistent_any && nosync;
+    if (!plan_on_sort) CK(cudaEventRecord(ev_recode, ss));
     st = st_main;
     unsigned long long launches = nosync ? 6 : 7;
     if (!nosync) CK(cudaStreamSynchronize(st)); // the read-back: entries and longest bucket per lane size the rounds
@@ -2098,6 +2352,19 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
         RS(L.ents2, (size_t)std::max(p.nent_a, p.nent_b) * 4);
     }
 #undef RS
+    for (int l = 0; l < NL; l++) {
+        lanes[l].launches = 0;
+        lanes[l].prof_used = 0;
+    }
+    if (plan_on_sort) {
+        for (int l = 0; l < NL; l++) {
+            Tree tree(*this, lanes[l]);
+            if ((rc = tree.plan_launch(ss, lanes[l].plan_main[k], d_len_all + bounds[l], d_start_all + bounds[l],
+                                       entries_k.as<uint32_t>(), part[l].nseg, part[l].total, ACC_MAX_ROUNDS)))
+                return rc;
+        }
+        CK(cudaEventRecord(ev_recode, ss));
+    }
     // a reduction level with more points than this starts with batched-affine rounds: large MSMs are throughput-bound
     // (5 instead of 15 multiplications per addition), small ones latency-bound (one launch instead of a round's six)
     const size_t ld_max = ld_tree_max ? ld_tree_max : (n >= (1u << 21) ? (size_t)1 << 13 : (size_t)1 << 16);
@@ -2106,8 +2373,6 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
     for (int l = 0; l < NL; l++) {
         MsmLane &L = lanes[l];
         const Part &p = part[l];
-        L.launches = 0;
-        L.prof_used = 0;
         CK(cudaStreamWaitEvent(L.stream, ev_recode, 0));
         // sorted ahead: nothing on the context stream orders this MSM after the read-back of the previous one's
         // partial sums (hb is shared), so the lane waits for it itself
@@ -2124,7 +2389,7 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
             // every round of the bucket accumulation in one persistent launch; the lanes' kernels share the SMs
             if (timing && l == 0) cudaEventRecord(L.ev_k[0], L.stream);
             if ((rc = tree.accumulate(d_points, entries_k.as<uint32_t>(), start0, len0, p.nseg, p.total, L.buckets.as<AffPt>(),
-                                      -1, 0, acc_grid)))
+                                      -1, 0, acc_grid, preplan ? &L.plan_main[k] : nullptr, /*plan_here=*/!plan_on_sort)))
                 return rc;
             if (timing && l == 0) cudaEventRecord(L.ev_k[1], L.stream);
             while ((1ull << r_main) < p.maxlen) r_main++;
@@ -2155,12 +2420,22 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
                 while ((1u << full) < mlen) full++;
                 while (nr < full && ((size_t)p.nent_a >> nr) + p.nseg_a > ld_max) nr++;
                 if (nr > 0) {
+                    // (fixed segment lengths: whether the rounds are planned ahead is known here, and with it where
+                    // the tables of the list after the last round are)
+                    const bool pre_a = preplan != 0 && mlen <= (1u << PL_K);
+                    // the index list and the segments of level A follow from the window layout alone, and so does its plan
+                    const uint64_t key_a = ((uint64_t)p.vn << 48) ^ ((uint64_t)nbv << 16) ^ ((uint64_t)lm << 8) ^ (uint64_t)nr ^ (1ull << 63);
                     if ((rc = tree.accumulate(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,
-                                              nullptr, nr, 1, acc_grid)))
+                                              nullptr, nr, 1, acc_grid, pre_a ? &L.plan_a : nullptr, true, key_a)))
                         return rc;
                     part_a.src = L.pp[(nr - 1) & 1].as<AffPt>();
-                    part_a.start = L.seg_start[nr & 1].as<uint32_t>();
-                    part_a.len = L.seg_len[nr & 1].as<uint32_t>();
+                    if (pre_a) {
+                        part_a.start = L.plan_a.start.as<uint32_t>() + (size_t)nr * L.plan_a.stride;
+                        part_a.len = L.plan_a.len.as<uint32_t>() + (size_t)nr * L.plan_a.stride;
+                    } else {
+                        part_a.start = L.seg_start[nr & 1].as<uint32_t>();
+                        part_a.len = L.seg_len[nr & 1].as<uint32_t>();
+                    }
                     part_a.maxlen = (mlen + (1u << nr) - 1) >> nr;
                 }
                 r_a = nr;

@@ -40,6 +40,20 @@ struct MsmLane {
     cudaEvent_t done = nullptr;
     DevBuf seg_len[2], seg_start[2], c_len, c_start, blk, blk_flag, info, info_r0, pp[2], prefix, desc,
         thr_total, thr_inv, lvl_pre[2], lvl_tot[2], lvl_inv[2], buckets, rc, ents2, acc_ctl, acc_times;
+    // The plan of all rounds of a k_accumulate launch, made ahead of it (k_pa_*): per-round segment tables, control
+    // words and descriptors.  Two sets for the bucket accumulation (a pipelined batch plans MSM b+1 on the sort stream
+    // while MSM b reads its own), one for reduction level A, whose plan depends only on the window layout and is kept
+    // from one MSM to the next (key).
+    struct PlanSet {
+        DevBuf blk, start, len, ctl, desc;
+        uint64_t key = 0;
+        uint32_t stride = 0;
+        void release() {
+            blk.release(), start.release(), len.release(), ctl.release(), desc.release();
+            key = 0;
+        }
+    };
+    PlanSet plan_main[2], plan_a;
     unsigned long long launches = 0;
     uint32_t epoch = 0; // k_plan launch counter (the blocks' publish flag)
     // profiler: (category, start, stop) per bracket; events are pooled
@@ -76,6 +90,7 @@ struct MsmEngine {
     DevBuf entries_b, len_all_b, start_all_b;
     cudaStream_t sort_stream = nullptr; // low priority: fills the latency-bound reduction phase of the MSM before
     int sort_ahead = 1;                 // 0: never sort ahead (every MSM starts after the previous one's read-back)
+    int preplan = 1; // persistent path: tables and descriptors of all rounds before the launch (0: every round plans itself)
     // Host-side landing zones come in two sets (index k of MsmPending), so that the device work of the next MSM of a
     // batch can be enqueued before the host has folded the partial sums of the previous one.
     void *h_lane = nullptr; // pinned, 2 x 128 words: per-lane (entries, longest bucket) | control words of k_accumulate

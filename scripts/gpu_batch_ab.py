@@ -40,14 +40,16 @@ def main():
             return 1e3 * (time.perf_counter() - t0) / (reps * batch)
 
         for rnd in range(2):
-            row = {}
-            row["single dev"] = t(lambda: [ctx.multi_scalar_mul_device(d[b], n, 0) for b in range(batch)])
-            row["single e2e"] = t(lambda: [ctx.multi_scalar_mul(sc[b], 0) for b in range(batch)])
-            for ahead in (0, 1):
-                ctx.set("msm_sort_ahead", ahead)
-                row[f"batch dev ahead={ahead}"] = t(lambda: ctx.multi_scalar_mul_batch(d, 0, on_device=True, n=n))
-                row[f"batch e2e ahead={ahead}"] = t(lambda: ctx.multi_scalar_mul_batch(host, 0))
-            print(f"2^{lg} ms per MSM: " + ", ".join(f"{k} {v:.3f}" for k, v in row.items()), flush=True)
+            for pre in (0, 1):
+                ctx.set("msm_preplan", pre)
+                row = {}
+                row["single dev"] = t(lambda: [ctx.multi_scalar_mul_device(d[b], n, 0) for b in range(batch)])
+                row["single e2e"] = t(lambda: [ctx.multi_scalar_mul(sc[b], 0) for b in range(batch)])
+                for ahead in (0, 1):
+                    ctx.set("msm_sort_ahead", ahead)
+                    row[f"batch dev ahead={ahead}"] = t(lambda: ctx.multi_scalar_mul_batch(d, 0, on_device=True, n=n))
+                    row[f"batch e2e ahead={ahead}"] = t(lambda: ctx.multi_scalar_mul_batch(host, 0))
+                print(f"2^{lg} preplan={pre} ms per MSM: " + ", ".join(f"{k} {v:.3f}" for k, v in row.items()), flush=True)
         for p in d:
             ctx.dev_free(p)
     ctx.close()
