@@ -31,19 +31,20 @@ sys.path.insert(0, os.path.join(ROOT, "dv-pari_b200"))
 METRIC = "sect233k1 MSM points/s"
 UNIT = "points/s"
 # Static facts about the dominant kernel, see DESIGN.md 4.2 / profiles/README.md (r2c).  At 2^20 points it is
-# k_accumulate: ALL tree rounds of the bucket accumulation in one persistent launch (plan, pass 1, per-warp inversion,
-# pass 2 per round).  Per batched affine addition it moves, algorithmically: descriptor 16 B written + 2 x 16 B read,
-# x coordinates 2 x 32 B (pass 1), prefix product 32 B written + 32 B read, two points 128 B (pass 2), one point out 64 B.
-ACC_BYTES_PER_ADD = 48 + 64 + 64 + 128 + 64
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch / its additions (profiles/r2f_ncu_accumulate_raw.csv:
-# 5.58 GB + 1.49 GB for 13.5 M additions: the 64-byte gathers of the bucket-sorted round 0 touch whole sectors)
-ACC_DRAM_BYTES_PER_ADD_NCU = 523
+# k_accumulate: ALL tree rounds of the bucket accumulation in one persistent launch (pass 1, per-warp inversion, pass 2
+# per round; the rounds are planned ahead of the launch by k_pa_*).  Per batched affine addition it moves,
+# algorithmically: descriptor 2 x 16 B read, x coordinates 2 x 32 B (pass 1), prefix product 32 B written + 32 B read,
+# two points 128 B (pass 2), one point out 64 B.
+ACC_BYTES_PER_ADD = 32 + 64 + 64 + 128 + 64
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch / its additions (profiles/r2s_ncu_accumulate_raw.csv:
+# 5.55 GB + 1.27 GB for 13.5 M additions: the 64-byte gathers of the bucket-sorted round 0 touch whole sectors)
+ACC_DRAM_BYTES_PER_ADD_NCU = 505
 # ALU-pipe (LOP3 / SHF / ...) thread-instructions per addition, from ncu's own counters of the launch this line times
-# (profiles/r2f_ncu_accumulate_raw.csv: sm__pipe_alu_cycles_active x cycles / 2 = 2.13e9 warp-instructions of 4.33e9
-# executed, for 13 500 343 additions; k_pass2<16,1>: profiles/r2f_ncu_pass2_raw.csv).  The field product is now 32-bit
+# (profiles/r2s_ncu_accumulate_raw.csv: sm__pipe_alu_cycles_active 66.4 % x 10.82 M active cycles / 2 x 592 schedulers =
+# 2.13e9 warp-instructions of 4.30e9 executed, for 13 500 343 additions; k_pass2<16,1>: profiles/r2f_ncu_pass2_raw.csv).  The field product is now 32-bit
 # multiply-adds only (gf233_mul2.cuh): ~900 LOP3 on the ALU pipe and ~890 IMAD on the FMA-heavy pipe per product, which
 # dual-issue, so the ALU pipe (0.5 warp-instructions per clock and scheduler) is the pipe that binds.
-ACC_ALU_INSTR_PER_ADD = 5060
+ACC_ALU_INSTR_PER_ADD = 5044
 PASS2_ALU_INSTR_PER_ADD = 4070
 ALU_PIPE_PEAK = 1.83e13  # measured on this pool's B200: LOP3 alone runs at this many thread-instr/s
                          # (sm__pipe_alu_cycles_active = 99.9 %), profiles/r2c_ncu_pipebench2_raw.csv
@@ -569,7 +570,7 @@ def main():
                          "launch_ms": k_ms, "adds_per_launch": k_adds,
                          "peak_source": "measured on this pool's B200: LOP3 alone = 1.83e13 thread-instr/s at sm__pipe_alu_cycles_active "
                                         "99.9 % (profiles/r2c_ncu_pipebench2_raw.csv); instructions per addition from ncu's ALU-pipe "
-                                        "counter of the same kernel (profiles/r2f_ncu_accumulate_raw.csv: ALU pipe 63.5 % busy)",
+                                        "counter of the same kernel (profiles/r2s_ncu_accumulate_raw.csv: ALU pipe 66.4 % busy)",
                          "traffic": k_adds * dram_per_add,
                          "hbm_view": {"achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak,
                                       "bytes_per_add": bytes_per_add, "peak_source": which}},

@@ -731,28 +731,51 @@ __global__ void __launch_bounds__(PL_THREADS)
             run[r] += w + blk_off[(size_t)blockIdx.x * PL_K + r];
         }
     }
-    // Tables and descriptors, every thread for its own segments: the descriptors of a segment are consecutive in every
-    // round and the iterations are independent (a warp working through one segment at a time spent its time waiting
-    // for the index loads of round 0: 160 us at 2^20 points).  The longest segment is 2^PL_K points.
+    // Tables by every thread for its own segments; descriptors by the whole warp over the flat list of its 32 segments'
+    // additions in a round (a lane finds the segment of its position by a 5-step search over the lanes' offsets): the
+    // stores are coalesced and every iteration is independent of the others.  (A warp working through one segment at a
+    // time waited for the index loads of round 0: 160 us at 2^20 points; a thread per segment issued 32 partial-sector
+    // stores per instruction: 180 us.)
     for (uint32_t k = 0; k < items; k++) {
         const uint32_t idx = base + k;
-        if (idx >= nseg) break;
-        uint32_t L = len0[idx], in_r = start0[idx];
+        uint32_t L = 0, in_r = 0;
+        if (idx < nseg) {
+            L = len0[idx];
+            in_r = start0[idx];
+        }
 #pragma unroll
         for (int r = 0; r < PL_K; r++) {
-            if (r < R) {
+            if (r < R) { // (R is uniform)
                 const uint32_t nt = L >> 1, ts = pl_ctl[20 + r] + (uint32_t)run[r], os = (uint32_t)(run[r] >> 32);
-                pl_start[(size_t)(r + 1) * stride + idx] = os;
-                pl_len[(size_t)(r + 1) * stride + idx] = (L + 1) >> 1;
-                uint4 *dp = desc + ts;
-#pragma unroll 4
-                for (uint32_t j = 0; j < nt; j++) {
-                    uint32_t a = in_r + 2 * j, b = a + 1;
-                    if (INDEXED && r == 0) {
-                        a = ent[a];
-                        b = ent[b];
+                if (idx < nseg) {
+                    pl_start[(size_t)(r + 1) * stride + idx] = os;
+                    pl_len[(size_t)(r + 1) * stride + idx] = (L + 1) >> 1;
+                }
+                uint32_t incl = nt;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= (uint32_t)o) incl += v;
+                }
+                const uint32_t excl = incl - nt, total = __shfl_sync(0xffffffffu, incl, 31);
+                for (uint32_t f0 = 0; f0 < total; f0 += 32) {
+                    const uint32_t f = f0 + lane;
+                    uint32_t sg = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const uint32_t e = __shfl_sync(0xffffffffu, excl, sg + step);
+                        if (e <= f) sg += step;
                     }
-                    dp[j] = make_uint4(a, b, os + j, 0);
+                    const uint32_t j = f - __shfl_sync(0xffffffffu, excl, sg);
+                    const uint32_t in_b = __shfl_sync(0xffffffffu, in_r, sg), os_b = __shfl_sync(0xffffffffu, os, sg);
+                    const uint32_t ts_b = __shfl_sync(0xffffffffu, ts, sg);
+                    if (f < total) {
+                        uint32_t a = in_b + 2 * j, b = a + 1;
+                        if (INDEXED && r == 0) {
+                            a = ent[a];
+                            b = ent[b];
+                        }
+                        desc[ts_b + j] = make_uint4(a, b, os_b + j, 0);
+                    }
                 }
                 run[r] += (unsigned long long)nt | ((unsigned long long)((L + 1) >> 1) << 32);
                 L = (L + 1) >> 1;
@@ -2367,7 +2390,11 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
     }
     // a reduction level with more points than this starts with batched-affine rounds: large MSMs are throughput-bound
     // (5 instead of 15 multiplications per addition), small ones latency-bound (one launch instead of a round's six)
-    const size_t ld_max = ld_tree_max ? ld_tree_max : (n >= (1u << 21) ? (size_t)1 << 13 : (size_t)1 << 16);
+    // (persistent path: with the rounds planned ahead an affine round costs a barrier and an inversion, and five of them
+    // before the tree are the optimum from 2^19 to 2^21 points -- profiles/r2s_ldmax_sweep.log)
+    const size_t ld_max = ld_tree_max ? ld_tree_max
+                          : (persistent_any && preplan) ? (size_t)12000
+                                                        : (n >= (1u << 21) ? (size_t)1 << 13 : (size_t)1 << 16);
     if (timing) cudaEventRecord(ev[3], st);
     // ---- per lane: accumulate buckets, then the two reduction levels into this lane's slice of hb
     for (int l = 0; l < NL; l++) {
