@@ -2231,7 +2231,7 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
     // The persistent kernel (one block of 255-register threads per SM) runs in ONE lane: two lanes would halve each
     // grid (2^20: 6.95 ms against 7.17); the separate-launch path keeps two lanes (2^22: 22.2 against 23.8 ms).
     const bool persistent_any =
-        acc_capacity > 0 && (use_accumulate == 2 || (use_accumulate == 1 && n >= ((size_t)1 << 17) && n < ((size_t)3 << 20)));
+        acc_capacity > 0 && (use_accumulate == 2 || (use_accumulate == 1 && n >= ((size_t)1 << 10) && n < ((size_t)3 << 20)));
     const bool nosync = persistent_any && !timing && total <= ((size_t)1 << 25);
     int NL = (profile && !force_lanes) ? 1 : force_lanes ? force_lanes : persistent_any ? 1 : (n >= (1u << 13) ? 2 : 1);
     NL = std::max(1, std::min<int>(NL, (int)V));
@@ -2288,10 +2288,12 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
     }
     bounds[NL] = (uint32_t)NB;
 
-    // The persistent kernel wins between 2^17 and 2^21 points (2^18: 3.00 against 3.17 ms, 2^19: 4.67 / 4.95, 2^20: 7.72 /
-    // 7.92, 2^21: 13.60 / 13.72; 23 launches instead of 87-155); below, a few hundred additions per round do not pay for
-    // grid barriers (2^12: 1.18 / 1.10), above, the separate large launches keep two blocks of one lane on every SM
-    // (2^22: 24.4 / 23.4 ms).
+    // The persistent kernel wins from 2^10 to 2^21 points (with the rounds planned ahead: 2^10 0.77 against 0.81 ms, 2^12
+    // 0.91 / 1.03, 2^13 1.03 / 1.23, 2^14 1.06 / 1.30, 2^15 1.00 / 1.19, 2^16 1.23 / 1.51 --
+    // profiles/r2t_persistent_small.log, r2t_persistent_tiny.log; 2^18 and up were measured
+    // with the round-by-round plan: 2^18 3.00 / 3.17, 2^19 4.67 / 4.95, 2^20 7.72 / 7.92, 2^21 13.60 / 13.72; 17
+    // launches instead of 50-155); above, the separate large launches keep two blocks of one lane on every SM
+    // (2^22: 24.4 / 23.4 ms then, 30.5 / 22.3 now: profiles/r2t_persistent_forced_large_sizes.log).
     // With the persistent kernel the host needs nothing from the sort: the rounds are counted on the device and the
     // scratch is sized from upper bounds (every entry in one lane), so the MSM is enqueued without a read-back in the
     // middle.  (Larger MSMs keep the exact sizes: twice the scratch would be gigabytes.)
