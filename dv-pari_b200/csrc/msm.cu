@@ -651,34 +651,32 @@ __global__ void __launch_bounds__(PL_THREADS)
     }
 }
 
-// one block: blk_sum[b][r] -> exclusive prefix over b (in place), totals, round count, descriptor offsets
+// one block: blk_sum[b][r] -> exclusive prefix over b (in place), totals, round count, descriptor offsets.
+// One warp per round (the rounds' scans are independent), a lane per chunk of blocks.
 __global__ void __launch_bounds__(PL_THREADS)
     k_pa_scan(unsigned long long *__restrict__ blk_sum, uint32_t nblk, int max_rounds, uint32_t *__restrict__ pl_ctl) {
-    __shared__ unsigned long long sh[PL_THREADS];
     __shared__ unsigned long long tot[PL_K];
-    const uint32_t t = threadIdx.x;
-    const uint32_t ch = (nblk + PL_THREADS - 1) / PL_THREADS;
-    for (int r = 0; r < PL_K; r++) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t ch = (nblk + 31) / 32;
+    for (int r = (int)wid; r < PL_K; r += PL_THREADS / 32) {
+        const uint32_t b0 = min(nblk, lane * ch), b1 = min(nblk, (lane + 1) * ch);
         unsigned long long loc = 0;
-        for (uint32_t b = t * ch; b < min(nblk, (t + 1) * ch); b++) loc += blk_sum[(size_t)b * PL_K + r];
-        sh[t] = loc;
-        __syncthreads();
-        for (int o = 1; o < PL_THREADS; o <<= 1) {
-            const unsigned long long v = t >= (uint32_t)o ? sh[t - o] : 0;
-            __syncthreads();
-            sh[t] += v;
-            __syncthreads();
+        for (uint32_t b = b0; b < b1; b++) loc += blk_sum[(size_t)b * PL_K + r];
+        unsigned long long incl = loc;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += v;
         }
-        unsigned long long run = sh[t] - loc; // exclusive
-        if (t == PL_THREADS - 1) tot[r] = sh[t];
-        for (uint32_t b = t * ch; b < min(nblk, (t + 1) * ch); b++) {
+        if (lane == 31) tot[r] = incl;
+        unsigned long long run = incl - loc; // exclusive
+        for (uint32_t b = b0; b < b1; b++) {
             const unsigned long long v = blk_sum[(size_t)b * PL_K + r];
             blk_sum[(size_t)b * PL_K + r] = run;
             run += v;
         }
-        __syncthreads();
     }
-    if (t == 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
         const uint32_t maxlen = pl_ctl[2];
         int R = 0;
         while (R < 32 && (1u << R) < maxlen) R++;
@@ -2335,7 +2333,12 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
     // the stream the sort ran on also plans the rounds of the bucket accumulation (k_pa_*: they need the sorted list
     // only), so that in a pipelined batch the plan of MSM b+1 is ready before MSM b has finished
     const cudaStream_t ss = st;
-    const bool plan_on_sort = preplan && persistent_any && nosync;
+    // Planning ahead pays in the table layout at every size measured (2^17 .. 2^21 points: 3-8 %) and in the plain layout
+    // up to ~6 M entries (2^12 .. 2^18 points: 6-12 %); above that the plain layout LOSES 12-15 % (2^19: 6.03 against 5.24
+    // ms, 2^20: 9.89 / 8.86 -- pass 2 of rounds 0 and 1 runs slower, profiles/r2u_timeline_plain_pre*.log), so it plans
+    // round by round there.
+    const bool pre_on = preplan && (uniform || total <= ((size_t)3 << 21));
+    const bool plan_on_sort = pre_on && persistent_any && nosync;
     if (!plan_on_sort) CK(cudaEventRecord(ev_recode, ss));
     st = st_main;
     unsigned long long launches = nosync ? 6 : 7;
@@ -2395,7 +2398,7 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
     // (persistent path: with the rounds planned ahead an affine round costs a barrier and an inversion, and five of them
     // before the tree are the optimum from 2^19 to 2^21 points -- profiles/r2s_ldmax_sweep.log)
     const size_t ld_max = ld_tree_max ? ld_tree_max
-                          : (persistent_any && preplan) ? (size_t)12000
+                          : (persistent_any && pre_on) ? (size_t)12000
                                                         : (n >= (1u << 21) ? (size_t)1 << 13 : (size_t)1 << 16);
     if (timing) cudaEventRecord(ev[3], st);
     // ---- per lane: accumulate buckets, then the two reduction levels into this lane's slice of hb
@@ -2418,7 +2421,7 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
             // every round of the bucket accumulation in one persistent launch; the lanes' kernels share the SMs
             if (timing && l == 0) cudaEventRecord(L.ev_k[0], L.stream);
             if ((rc = tree.accumulate(d_points, entries_k.as<uint32_t>(), start0, len0, p.nseg, p.total, L.buckets.as<AffPt>(),
-                                      -1, 0, acc_grid, preplan ? &L.plan_main[k] : nullptr, /*plan_here=*/!plan_on_sort)))
+                                      -1, 0, acc_grid, pre_on ? &L.plan_main[k] : nullptr, /*plan_here=*/!plan_on_sort)))
                 return rc;
             if (timing && l == 0) cudaEventRecord(L.ev_k[1], L.stream);
             while ((1ull << r_main) < p.maxlen) r_main++;
@@ -2451,7 +2454,7 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
                 if (nr > 0) {
                     // (fixed segment lengths: whether the rounds are planned ahead is known here, and with it where
                     // the tables of the list after the last round are)
-                    const bool pre_a = preplan != 0 && mlen <= (1u << PL_K);
+                    const bool pre_a = pre_on && mlen <= (1u << PL_K);
                     // the index list and the segments of level A follow from the window layout alone, and so does its plan
                     const uint64_t key_a = ((uint64_t)p.vn << 48) ^ ((uint64_t)nbv << 16) ^ ((uint64_t)lm << 8) ^ (uint64_t)nr ^ (1ull << 63);
                     if ((rc = tree.accumulate(L.buckets.as<AffPt>(), L.ents2.as<uint32_t>(), d_start, d_len, p.nseg_a, p.nent_a,

@@ -9,6 +9,8 @@ ctx = dvpari.Context(0)
 n = 1 << lg
 ctx.srs_random(0, n, 5)
 d = ctx.dev_alloc(n * 32); ctx.dev_upload(d, dvpari.random_fr_mont(n, 6))
+for kv in filter(None, os.environ.get("DVP_KNOBS", "").split(",")):  # e.g. DVP_KNOBS=msm_tables=0,msm_preplan=0
+    ctx.set(kv.split("=")[0], int(kv.split("=")[1]))
 ctx.set("msm_lanes", lanes); ctx.set("msm_profile", 1); ctx.set("timing", 1)
 for _ in range(3):
     ctx.multi_scalar_mul_device(d, n, 0)
