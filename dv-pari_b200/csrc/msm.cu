@@ -85,9 +85,10 @@ int latency_probe(MsmEngine &E, int mode, int iters, float *us_per_op) {
 int choose_window_bits(size_t n) {
     // adds ~ n*W + tail(2^(c-1)*W); the tail rounds are latency-bound, so stay a little below the
     // arithmetic optimum
+    // (plain layout on the persistent path, profiles/r2w_cwin_sweep_plain.log: 2^12 / 2^13 points c = 9 0.84 / 0.93 ms
+    // against c = 8 0.91 / 1.03; 2^15 / 2^16 c = 13 1.21 / 1.53 against c = 11 1.29 / 1.70)
     if (n <= (1u << 10)) return 6;
-    if (n <= (1u << 13)) return 8;
-    if (n <= (1u << 16)) return 11;
+    if (n <= (1u << 13)) return 9;
     if (n <= (1u << 18)) return 13;
     if (n <= (1u << 21)) return 15;
     return 16;
