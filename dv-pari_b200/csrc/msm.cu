@@ -2420,9 +2420,14 @@ int MsmEngine::enqueue(const AffPt *d_points, const uint32_t *d_scalars, size_t 
         if (persistent && profile) CK(cudaMemsetAsync(L.acc_times.p, 0, 2 * ACC_TIME_WORDS * 8, L.stream));
         if (persistent) {
             // every round of the bucket accumulation in one persistent launch; the lanes' kernels share the SMs
+            // (its plan first, unless the sort stream has made it: the timed bracket below is the kernel alone)
+            if (pre_on && !plan_on_sort &&
+                (rc = tree.plan_launch(L.stream, L.plan_main[k], len0, start0, entries_k.as<uint32_t>(), p.nseg, p.total,
+                                       ACC_MAX_ROUNDS)))
+                return rc;
             if (timing && l == 0) cudaEventRecord(L.ev_k[0], L.stream);
             if ((rc = tree.accumulate(d_points, entries_k.as<uint32_t>(), start0, len0, p.nseg, p.total, L.buckets.as<AffPt>(),
-                                      -1, 0, acc_grid, pre_on ? &L.plan_main[k] : nullptr, /*plan_here=*/!plan_on_sort)))
+                                      -1, 0, acc_grid, pre_on ? &L.plan_main[k] : nullptr, /*plan_here=*/false)))
                 return rc;
             if (timing && l == 0) cudaEventRecord(L.ev_k[1], L.stream);
             while ((1ull << r_main) < p.maxlen) r_main++;
