@@ -648,33 +648,31 @@ __global__ void __launch_bounds__(PL_THREADS)
     if (threadIdx.x < PL_K) {
         unsigned long long v = 0;
         for (int w = 0; w < PL_THREADS / 32; w++) v += sh[threadIdx.x][w];
-        blk_sum[(size_t)blockIdx.x * PL_K + threadIdx.x] = v;
+        blk_sum[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = v; // [round][block]
     }
 }
 
-// one block: blk_sum[b][r] -> exclusive prefix over b (in place), totals, round count, descriptor offsets.
-// One warp per round (the rounds' scans are independent), a lane per chunk of blocks.
+// one block: blk_sum[r][b] -> exclusive prefix over b (in place), totals, round count, descriptor offsets.
+// One warp per round (the rounds' scans are independent), 32 blocks per step with a running carry (coalesced).
 __global__ void __launch_bounds__(PL_THREADS)
     k_pa_scan(unsigned long long *__restrict__ blk_sum, uint32_t nblk, int max_rounds, uint32_t *__restrict__ pl_ctl) {
     __shared__ unsigned long long tot[PL_K];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t ch = (nblk + 31) / 32;
     for (int r = (int)wid; r < PL_K; r += PL_THREADS / 32) {
-        const uint32_t b0 = min(nblk, lane * ch), b1 = min(nblk, (lane + 1) * ch);
-        unsigned long long loc = 0;
-        for (uint32_t b = b0; b < b1; b++) loc += blk_sum[(size_t)b * PL_K + r];
-        unsigned long long incl = loc;
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (uint32_t)o) incl += v;
+        unsigned long long *row = blk_sum + (size_t)r * nblk;
+        unsigned long long carry = 0;
+        for (uint32_t b0 = 0; b0 < nblk; b0 += 32) {
+            const uint32_t b = b0 + lane;
+            const unsigned long long v = b < nblk ? row[b] : 0;
+            unsigned long long incl = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += u;
+            }
+            if (b < nblk) row[b] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (lane == 31) tot[r] = incl;
-        unsigned long long run = incl - loc; // exclusive
-        for (uint32_t b = b0; b < b1; b++) {
-            const unsigned long long v = blk_sum[(size_t)b * PL_K + r];
-            blk_sum[(size_t)b * PL_K + r] = run;
-            run += v;
-        }
+        if (lane == 0) tot[r] = carry;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -727,7 +725,7 @@ __global__ void __launch_bounds__(PL_THREADS)
         for (int r = 0; r < PL_K; r++) {
             unsigned long long w = 0;
             for (uint32_t q = 0; q < wid; q++) w += sh[r][q];
-            run[r] += w + blk_off[(size_t)blockIdx.x * PL_K + r];
+            run[r] += w + blk_off[(size_t)r * gridDim.x + blockIdx.x];
         }
     }
     // Tables by every thread for its own segments; descriptors by the whole warp over the flat list of its 32 segments'
