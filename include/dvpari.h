@@ -60,7 +60,11 @@ int dvp_ctx_create(int device, dvp_ctx **out);
 void dvp_ctx_destroy(dvp_ctx *ctx);
 /* knobs: "msm_window_bits" (0 = automatic), "msm_lanes" (0 = automatic: concurrent window groups),
  * "pass2_minb" (1..3), "timing" (0/1), "msm_profile" (0/1), "msm_tables" (0/1: precomputed window multiples of
- * large SRS slots, W x the slot's memory, built on first use), "msm_tables_min" (smallest such slot), "binv_direct".  Unknown name -> DVP_ERR_BAD_ARG. */
+ * large SRS slots, W x the slot's memory, built on first use), "msm_tables_min" (smallest such slot), "binv_direct",
+ * "msm_preplan" (0/1: the rounds of the persistent accumulation kernel planned ahead of its launch), "msm_sort_ahead"
+ * (0/1: in a batched call the next MSM is sorted and planned on a side stream), "prove_joint" (-1 automatic, 0, 1:
+ * commit_p as ONE multi_scalar_mul over g_m | g_q), further tuning knobs listed in INTEGRATION.md section 5.
+ * Unknown name -> DVP_ERR_BAD_ARG. */
 int dvp_ctx_set(dvp_ctx *ctx, const char *name, long value);
 
 /*
