@@ -1,6 +1,7 @@
 """world_size-2 gloo run of the N > 1 host logic on CPU: the shard rule (dvp_shard_range), the exchange pattern of a
-sharded MSM (all-gather of the ranks' partial sums, fold in rank order) with the oracle standing in for the device
-MSM, and the row / polynomial ownership rules of the sharded prove."""
+sharded MSM (all-gather of the ranks' partial sums, fold in rank order) and of a batch of them (dvp_msm_sharded_batch:
+ONE all-gather of nb partial sums per rank, folded per MSM in rank order) with the oracle standing in for the device MSM,
+and the index ranges of the sharded g_k."""
 import os
 import sys
 
@@ -47,6 +48,18 @@ def _worker_body(rank, world, port, n, q):
     ref = mine.clone()
     dist.broadcast(ref, src=0)
     ok = ok and bool((ref == mine).all())
+    # the batched exchange: nb partial sums per rank travel together, rank r's block is [r][b]
+    nb = 3
+    scs = [sc, dvpari.random_fr_mont(n, 22), dvpari.random_fr_mont(n, 23)]
+    parts = b"".join(O.pt_encode(O.msm(s[lo:hi], mine_pts, 1)) + b"\0\0" for s in scs)
+    tb = torch.frombuffer(bytearray(parts), dtype=torch.uint8)
+    outs_b = [torch.empty_like(tb) for _ in range(world)]
+    dist.all_gather(outs_b, tb)
+    for b in range(nb):
+        acc_b = O.pt_decode(bytes(outs_b[0].numpy()[32 * b:32 * b + 30]))[0]
+        for o in outs_b[1:]:
+            acc_b = O.pt_add(acc_b, O.pt_decode(bytes(o.numpy()[32 * b:32 * b + 30]))[0])
+        ok = ok and O.pt_encode(acc_b) == O.pt_encode(O.msm(scs[b], pts, 1))
     q.put((rank, ok, lo, hi))
     dist.destroy_process_group()
 
@@ -69,8 +82,6 @@ def test_shard_range_partitions():
         idx = np.concatenate([dvpari.gk_shard_indices(n, r, world) for r in range(world)])
         assert idx.size == 4 * n and np.array_equal(np.sort(idx), np.arange(4 * n))
         assert all(dvpari.gk_shard_indices(n, r, world).size == 4 * n // world for r in range(world))
-    # the ownership rules of the sharded prove: rows need world | n, polynomial p lives on rank p % world
-    assert [p % 2 for p in range(3)] == [0, 1, 0] and [p % 8 for p in range(3)] == [0, 1, 2]
 
 
 def test_sharded_msm_exchange_gloo():
