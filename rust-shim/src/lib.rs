@@ -47,6 +47,10 @@ extern "C" {
     pub fn dvp_comm_unique_id(id: *mut u8) -> c_int;
     pub fn dvp_comm_init(ctx: *mut dvp_ctx, id: *const u8, rank: c_int, world: c_int) -> c_int;
     pub fn dvp_shard_range(total: usize, rank: c_int, world: c_int, lo: *mut usize, hi: *mut usize);
+    pub fn dvp_msm_sharded(ctx: *mut dvp_ctx, slot: c_int, scalars_mont: *const u64, n: usize, scalars_on_device: c_int,
+                           out30: *mut u8) -> c_int;
+    pub fn dvp_msm_sharded_batch(ctx: *mut dvp_ctx, slot: c_int, scalars_mont: *const *const u64, n: usize, nb: usize,
+                                 scalars_on_device: c_int, out30: *mut u8) -> c_int;
 }
 
 // The reference's Fr must be exactly four u64 limbs for the zero-copy cast below.
